@@ -1,0 +1,159 @@
+/* mvuld_b200 -- C ABI of the B200-native MVulD forward hot path (libmvuld_b200.so).
+ *
+ * The reference (jacknichao/MVulD) has no FFI / operator table: its hot path is plain PyTorch + DGL + HF
+ * transformers Python.  These entry points are what a reference-side binding would load
+ * (ctypes stub in INTEGRATION.md) to replace, call site by call site, the library kernels the reference launches
+ * implicitly.  Conventions:
+ *   - every pointer is a DEVICE pointer unless stated; bf16/fp16 tensors are passed as void*;
+ *   - sizes are plain ints; `stream` is a cudaStream_t (the caller's current stream); nothing allocates;
+ *   - return 0 on success, a cudaError_t (>0) or -1/-2/-3 (bad argument / driver entry missing / TMA encode
+ *     failure) otherwise; mvuld_last_error() returns the message for the calling thread;
+ *   - file:line citations are relative to /root/reference.
+ */
+#ifndef MVULD_B200_H_
+#define MVULD_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mvuld_stream_t; /* == cudaStream_t */
+
+const char* mvuld_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense layers (tcgen05 GEMM, TMA-fed, fp32 accumulate in TMEM).
+ * out[M,N] = act(A[M,K] @ W[N,K]^T + bias) + res      A, W bf16 row-major (nn.Linear weight layout [out, in]).
+ * act: 0 none, 1 GELU(erf), 2 ELU.  Either/both of out_bf16 / out_f32 may be given; res_f32 (fp32 [M, ldr]) may
+ * alias out_f32.  Replaces F.linear / nn.Linear / Conv1d(k=1) at: mvuld/models/swin_transformer_v2.py:26-32,177,361;
+ * mvuld/models/GraphModel.py:153,159,171,176,186; mvuld/models/Rs_GCN.py:57,60,62,71; HF RobertaModel dense layers
+ * (mvuld/models/unixcoder.py:36); DGL GATConv.fc, GatedGraphConv.linears / GRUCell (baselines/models/reveal/ggnn/
+ * model.py:15-16).
+ * ---------------------------------------------------------------------------------------------------------- */
+int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
+                    const float* res_f32, int ldr, void* out_bf16, float* out_f32, int ldc, mvuld_stream_t stream);
+
+/* SwinV2 qkv projection fused with: cat(q_bias, 0, v_bias), per-head L2 normalisation of q and k, the learnable
+ * logit scale (qscale[h] = exp(min(logit_scale_h, ln 100)) * log2 e, folded into q), window partition and cyclic
+ * shift (pure index math).  X bf16 [B*H*W, C]; q,k fp16 and v bf16, each [B*nW, nH, ws*ws, 32].
+ * Replaces mvuld/models/swin_transformer_v2.py:147-157 and :276-286. */
+int mvuld_swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias, const float* qscale,
+                   void* q, void* k, void* v, int B, int H, int W, int C, int nH, int ws, int shift,
+                   mvuld_stream_t stream);
+
+/* RoBERTa qkv projection, head-major outputs bf16 [B, nH, L, hd]; q multiplied by qmul (= log2 e / sqrt(hd)).
+ * Wqkv = cat(query.weight, key.weight, value.weight) [3*Hd, Hd].  HF RobertaSelfAttention via unixcoder.py:36. */
+int mvuld_heads_qkv(const void* X, const void* Wqkv, const float* bias, void* q, void* k, void* v, int B, int L,
+                    int Hd, int nH, float qmul, mvuld_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention (tcgen05 QK^T and PV, softmax on the TMEM accumulator, one CTA per (window|sequence, head)).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Continuous position bias table, once per weight version: table_ref[h, (2ws-1)^2] = 16*sigmoid(cpb_mlp(coords))
+ * in the reference's order; table_rev = same * log2 e with the w axis reversed (kernel layout); table_max[h].
+ * w1 [512,2], b1 [512], w2 [nH,512].  swin_transformer_v2.py:98-111,159,163. */
+int mvuld_cpb_table(const float* w1, const float* b1, const float* w2, int nH, int ws, int pretrained_ws,
+                    float* table_rev, float* table_ref, float* table_max, mvuld_stream_t stream);
+
+/* softmax(q k^T + bias[rel_pos_index] + shift_mask) v, written token-major bf16 [B*H*W, C] with window_reverse and
+ * the inverse cyclic shift folded into the store.  ws in {7, 14, 28}; shift in {0, ws/2}.
+ * swin_transformer_v2.py:155-176 and :292-299. */
+int mvuld_swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
+                                const float* bias_max, void* out, int B, int H, int W, int C, int nH, int ws,
+                                int shift, mvuld_stream_t stream);
+
+/* Key-padded self-attention for the text encoder: q,k,v bf16 [B, nH, L, 64] (q pre-scaled), kv_len int32 [B];
+ * out bf16 [B*L, nH*64].  unixcoder.py:35-36. */
+int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out, int B, int L,
+                        int nH, int hd, mvuld_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Row kernels of the image / text branches.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* mode 0: x = LN(y); 1: x = shortcut + LN(y) (res-post-norm, swin_transformer_v2.py:301,304);
+ * 2: x = LN(y + shortcut) (RoBERTa).  y bf16 [M,C]; shortcut fp32; outputs fp32 x32 and/or bf16 xb. */
+int mvuld_ln_rows(const void* y, const float* shortcut, const float* gamma, const float* beta, float* x32, void* xb,
+                  int M, int C, float eps, int mode, mvuld_stream_t stream);
+/* PatchEmbed: Conv2d(3,E,4,4) + LayerNorm, img fp32 NCHW -> x32 / xb [B*(H/4)*(W/4), E]. swin_transformer_v2.py:485-493 */
+int mvuld_patch_embed(const float* img, const float* w, const float* bias, const float* gamma, const float* beta,
+                      float* x32, void* xb, int B, int Himg, int Wimg, int E, float eps, mvuld_stream_t stream);
+/* PatchMerging 2x2 gather-concat in the order (0,0),(1,0),(0,1),(1,1). swin_transformer_v2.py:352-359 */
+int mvuld_patch_merge_gather(const void* xb, void* out, int B, int H, int W, int C, mvuld_stream_t stream);
+/* final LayerNorm + mean over tokens -> fp32 [B, C]. swin_transformer_v2.py:632-634 */
+int mvuld_ln_meanpool(const float* x, const float* gamma, const float* beta, float* out, int B, int T, int C,
+                      float eps, mvuld_stream_t stream);
+/* position ids (cumsum(ids != pad) * (ids != pad) + pad), valid length per sequence, and a flag cleared when a
+ * non-pad token follows a pad (the kv-length attention path requires suffix padding, as unixcoder.py:150 produces). */
+int mvuld_seq_positions(const long long* ids, int B, int L, int pad, int* pos, int* len, int* suffix_ok,
+                        mvuld_stream_t stream);
+/* word + position + token_type[0] embeddings + LayerNorm (HF RobertaEmbeddings). */
+int mvuld_roberta_embed(const long long* ids, const int* pos, const float* word, const float* posemb,
+                        const float* type0, const float* gamma, const float* beta, float* x32, void* xb, int M, int C,
+                        float eps, mvuld_stream_t stream);
+/* masked mean over tokens (unixcoder.py:37). */
+int mvuld_masked_mean(const float* tok, const int* len, float* out, int B, int L, int C, mvuld_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Graph branch (CSR gather / segment reduce).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* In-edge CSR sorted by (dst, edge id) from int64 COO (dgl.graph + dgl.batch order).  workspace == NULL queries
+ * *workspace_bytes.  status[0] = 1 if an endpoint is outside [0, N). */
+int mvuld_csr_from_coo(const long long* src, const long long* dst, int E, int N, void* workspace,
+                       size_t* workspace_bytes, int* indptr, int* idx_src, int* eids, int* status,
+                       mvuld_stream_t stream);
+/* etype_sorted[i] = uint8(etype[eids[i]]); status[0] = 1 if any etype outside [0, n_etypes) (DGL asserts). */
+int mvuld_gather_etype(const long long* etype, const int* eids, int E, int n_etypes, unsigned char* out, int* status,
+                       mvuld_stream_t stream);
+/* a[dst] = sum over in-edges of msgs[src, etype, :]; msgs bf16 [N, T, D], out bf16 [N, D].
+ * DGL GatedGraphConv message + reduce (baselines/models/reveal/ggnn/model.py:23, devign/model.py:35). */
+int mvuld_ggnn_gather_sum(const void* msgs, const int* indptr, const int* idx_src, const unsigned char* etype,
+                          void* out, int N, int T, int D, mvuld_stream_t stream);
+/* GRUCell gates, in place on h32 (+ bf16 shadow). gi, gh bf16 [N, 3D]. */
+int mvuld_gru_gates(const void* gi, const void* gh, float* h32, void* hb, long long N, int D, mvuld_stream_t stream);
+/* h0 = cat(x, 0) zero padding of GatedGraphConv. */
+int mvuld_ggnn_init(const float* x, float* h32, void* hb, long long N, int in_dim, int D, mvuld_stream_t stream);
+/* per-graph segment sum (reveal/ggnn/model.py:26-28,46-56): feat fp32 [N, D], offsets int64 [B+1] -> out [B, D]. */
+int mvuld_segment_sum(const float* feat, const long long* offsets, float* out, int B, int D, mvuld_stream_t stream);
+/* GATConv pieces (GraphModel.py:99-105,167-170): el/er scores, then edge-softmax + weighted aggregate + bias. */
+int mvuld_gat_scores(const void* z, const float* attn_l, const float* attn_r, float* el, float* er, int N, int H,
+                     int F, mvuld_stream_t stream);
+int mvuld_gat_aggregate(const void* z, const float* el, const float* er, const int* indptr, const int* idx_src,
+                        const float* bias, void* out, int N, int H, int F, float slope, int* zero_deg_flag,
+                        mvuld_stream_t stream);
+/* unbatch_features pad/truncate (GraphModel.py:30-54) fused with BatchNorm1d(max_node) over the slot axis (:135,186)
+ * as a per-slot affine; gather_map (int64 [B, max_node], -1 = zero row) is optional. */
+int mvuld_unbatch_pad_bn(const void* feat, const long long* offsets, const float* bn_scale, const float* bn_shift,
+                         void* out, long long* gather_map, int B, int max_node, int F, mvuld_stream_t stream);
+/* ELU(fc_bbox(bn_bbox(pad(pos)))) into columns [col0, col0+OUT) of the concat buffers (GraphModel.py:187,189). */
+int mvuld_pos_branch(const float* pos, const long long* offsets, const float* bn_scale, const float* bn_shift,
+                     const float* w, const float* bias, float* z32, void* zb, int B, int max_node, int OUT, int ld,
+                     int col0, mvuld_stream_t stream);
+int mvuld_f32_to_bf16(const float* in, void* out, long long n, mvuld_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fusion branch.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Rs_GCN.py:57-66: tpg bf16 [B*n, 3C] = (theta | phi | g); y = (theta phi^T / n) g, bf16 [B*n, C]; r_out optional
+ * fp32 [B, n, n] (the affinity the reference returns). */
+int mvuld_rs_gcn_affinity(const void* tpg, void* y, float* r_out, int B, int n, int C, mvuld_stream_t stream);
+/* GraphModel.py:200-209: l2norm(dim=1) + mean + concat + BN(folded) + Linear -> logits fp32 [B, num_classes]. */
+int mvuld_fusion_head(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
+                      float* logits, float* feat_out, int B, int n, int D, int num_classes, mvuld_stream_t stream);
+
+/* Small-N fp32 linear for classification heads (swin_transformer_v2.py:642; reveal/ggnn/model.py:29-30):
+ * out[M,N] = x[M,K] w[N,K]^T + b; out_sigmoid (optional) = sigmoid(out). */
+int mvuld_linear_small(const float* x, const float* w, const float* b, float* out, float* out_sigmoid, int M, int N,
+                       int K, mvuld_stream_t stream);
+
+/* Test hook: one TMA box per operand, nk tcgen05.mma K-steps, accumulator dumped (see csrc/probe.cu). */
+int mvuld_probe_umma(const void* A, int a_inner, int a_rows, int a_swizzle, const void* B, int b_inner, int b_rows,
+                     int b_swizzle, int N, int nk, int a_step, int b_step, int a_lbo, int a_sbo, int a_layout,
+                     int b_lbo, int b_sbo, int b_layout, int a_mn, int b_mn, int fmt, float* out,
+                     mvuld_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVULD_B200_H_ */

@@ -1,0 +1,16 @@
+"""mvuld_b200 -- B200-native (sm_100a) implementation of the MVulD multimodal forward hot path.
+
+Host side mirrors the reference's model-layer interface (``build_model`` / ``get_config`` / model classes with the
+reference's state-dict keys); compute is hand-written CUDA behind the C ABI in ``include/mvuld_b200.h``.
+"""
+from .config import get_config, default_config, CfgNode            # noqa: F401
+from .build import build_model                                      # noqa: F401
+from .swin_transformer_v2 import SwinTransformerV2                  # noqa: F401
+from .unixcoder import MyUniXcoder, RobertaEncoder, build_MyUniXcoder, roberta_base_config   # noqa: F401
+from .graph_model import Multi_DefectModel_new_GCN, Rs_GCN, GATConv, GatedGraphConv, GGNNSum  # noqa: F401
+from .mvuld import MVulD                                            # noqa: F401
+from . import graph                                                 # noqa: F401
+
+__all__ = ["get_config", "default_config", "CfgNode", "build_model", "SwinTransformerV2", "MyUniXcoder",
+           "RobertaEncoder", "build_MyUniXcoder", "roberta_base_config", "Multi_DefectModel_new_GCN", "Rs_GCN",
+           "GATConv", "GatedGraphConv", "GGNNSum", "MVulD", "graph"]

@@ -1,0 +1,161 @@
+"""ctypes binding of ``libmvuld_b200.so`` (the C ABI declared in ``include/mvuld_b200.h``).
+
+PyTorch is used only for device memory and the current CUDA stream: every wrapper passes raw device pointers,
+plain ints and the stream handle.  There is no CPU or PyTorch fallback: if the library is missing or a call
+fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvuld_b200.so")
+
+_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argument ctypes (the stream argument is included); mirrors include/mvuld_b200.h
+SIGNATURES = {
+    "mvuld_gemm_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P],
+    "mvuld_swin_qkv": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mvuld_heads_qkv": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "mvuld_cpb_table": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "mvuld_swin_window_attention": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mvuld_seq_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_ln_rows": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "mvuld_patch_embed": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "mvuld_patch_merge_gather": [_P, _P, _I, _I, _I, _I, _P],
+    "mvuld_ln_meanpool": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "mvuld_seq_positions": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "mvuld_roberta_embed": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "mvuld_masked_mean": [_P, _P, _P, _I, _I, _I, _P],
+    "mvuld_csr_from_coo": [_P, _P, _I, _I, _P, C.POINTER(C.c_size_t), _P, _P, _P, _P, _P],
+    "mvuld_gather_etype": [_P, _P, _I, _I, _P, _P, _P],
+    "mvuld_ggnn_gather_sum": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_gru_gates": [_P, _P, _P, _P, _LL, _I, _P],
+    "mvuld_ggnn_init": [_P, _P, _P, _LL, _I, _I, _P],
+    "mvuld_segment_sum": [_P, _P, _P, _I, _I, _P],
+    "mvuld_gat_scores": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_gat_aggregate": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P],
+    "mvuld_unbatch_pad_bn": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_pos_branch": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mvuld_f32_to_bf16": [_P, _P, _LL, _P],
+    "mvuld_rs_gcn_affinity": [_P, _P, _P, _I, _I, _I, _P],
+    "mvuld_fusion_head": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 14 + [_P, _P],
+}
+
+_lib = None
+launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
+_LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5}
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the MVulD hot path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.mvuld_last_error.restype = C.c_char_p
+    lib.mvuld_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("mvuld_b200 kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("mvuld_b200 kernels take contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args):
+    """Invoke ``name`` with tensors (-> device pointers), ints and floats; appends the current stream."""
+    global launch_count
+    lib = load()
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor) or a is None:
+            conv.append(_ptr(a))
+        else:
+            conv.append(a)
+    rc = getattr(lib, name)(*conv, _stream())
+    if rc != 0:
+        msg = lib.mvuld_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{name} failed (code {rc}): {msg}")
+    launch_count += _LAUNCHES_PER_CALL.get(name, 1)
+    return rc
+
+
+# ---------------------------------------------------------------------------------------------------------
+# thin typed wrappers
+# ---------------------------------------------------------------------------------------------------------
+ACT_NONE, ACT_GELU, ACT_ELU = 0, 1, 2
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act=ACT_NONE, res=None, out_bf16=None, out_f32=None,
+         ldc=None):
+    """out = act(a @ w.T + bias) + res.  a [M,K] bf16, w [N,K] bf16 (row strides may exceed K)."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    lda, ldw = a.stride(0), w.stride(0)
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    out = out_bf16 if out_bf16 is not None else out_f32
+    if ldc is None:
+        ldc = out.stride(0)
+    if out_bf16 is not None and out_f32 is not None:
+        assert out_bf16.stride(0) == out_f32.stride(0)
+    ldr = res.stride(0) if res is not None else 0
+    global launch_count
+    lib = load()
+    rc = lib.mvuld_gemm_bf16(C.c_void_p(a.data_ptr()), lda, C.c_void_p(w.data_ptr()), ldw, M, N, K, _ptr(bias), act,
+                             C.c_void_p(res.data_ptr()) if res is not None else None, ldr,
+                             C.c_void_p(out_bf16.data_ptr()) if out_bf16 is not None else None,
+                             C.c_void_p(out_f32.data_ptr()) if out_f32 is not None else None, ldc, _stream())
+    if rc != 0:
+        raise RuntimeError(f"mvuld_gemm_bf16 failed (code {rc}): {lib.mvuld_last_error().decode()}")
+    launch_count += 1
+
+
+def csr_from_coo(src: torch.Tensor, dst: torch.Tensor, num_nodes: int):
+    """In-edge CSR sorted by (dst, edge id).  Returns (indptr int32 [N+1], idx_src int32 [E], eids int32 [E])."""
+    assert src.dtype == torch.int64 and dst.dtype == torch.int64 and src.is_cuda
+    E = src.numel()
+    dev = src.device
+    need = C.c_size_t(0)
+    lib = load()
+    rc = lib.mvuld_csr_from_coo(None, None, E, num_nodes, None, C.byref(need), None, None, None, None, _stream())
+    if rc != 0:
+        raise RuntimeError(f"mvuld_csr_from_coo(size query) failed: {lib.mvuld_last_error().decode()}")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    indptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+    idx_src = torch.empty(E, dtype=torch.int32, device=dev)
+    eids = torch.empty(E, dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = lib.mvuld_csr_from_coo(_ptr(src), _ptr(dst), E, num_nodes, _ptr(ws), C.byref(need), _ptr(indptr),
+                                _ptr(idx_src), _ptr(eids), _ptr(status), _stream())
+    if rc != 0:
+        raise RuntimeError(f"mvuld_csr_from_coo failed (code {rc}): {lib.mvuld_last_error().decode()}")
+    global launch_count
+    launch_count += 5
+    return indptr, idx_src, eids, status

@@ -1,0 +1,210 @@
+// Fusion-branch kernels of Multi_DefectModel_new_GCN (GraphModel.py:189-209):
+//   * Rs_GCN affinity:  R = theta phi^T / N ;  y = R g   per graph (Rs_GCN.py:57-66; no softmax)
+//   * fusion head: l2norm over the node-slot axis + mean over slots + concat(image, graph, text) + BatchNorm1d(1536)
+//     (folded) + Linear(1536, num_classes) in ONE kernel (GraphModel.py:200-209).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mv {
+
+// tpg: bf16 [B*n, 3C] rows = (theta | phi | g) of one node slot; y: bf16 [B*n, C].  One CTA (256 threads, 200 active
+// in the FMA phases) per graph; n <= 100 slots, C % 64 == 0.
+constexpr int RS_MAXN = 100;
+__global__ void __launch_bounds__(256)
+rs_gcn_affinity_kernel(const bf16* __restrict__ tpg, bf16* __restrict__ y, float* __restrict__ r_out, int n, int C) {
+  extern __shared__ float sm[];
+  float* R = sm;                                  // [RS_MAXN][RS_MAXN + 1]
+  float* bufA = R + RS_MAXN * (RS_MAXN + 1);      // phase 1: theta chunk [RS_MAXN][33]; phase 2: g chunk [RS_MAXN][64]
+  float* bufB = bufA + RS_MAXN * 64;              // phase 1: phi chunk [RS_MAXN][33]
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bf16* base = tpg + (size_t)b * n * 3 * C;
+
+  // ---- phase 1: R = theta phi^T / n ; thread (ti, tj) owns rows ti*5..+5, cols tj*10..+10 ----
+  const int ti = tid / 10, tj = tid % 10;
+  float acc[5][10];
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int c = 0; c < 10; ++c) acc[a][c] = 0.f;
+  for (int k0 = 0; k0 < C; k0 += 32) {
+    // stage theta[:, k0:k0+32] and phi[:, k0:k0+32] (4 uint4 per row each)
+    for (int i = tid; i < RS_MAXN * 8; i += 256) {
+      const int row = i >> 3, part = i & 7;       // part 0..3 theta, 4..7 phi
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (row < n) {
+        const int col = (part < 4 ? 0 : C) + k0 + (part & 3) * 8;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * 3 * C + col));
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+      }
+      float* dstp = (part < 4 ? bufA : bufB) + row * 33 + (part & 3) * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dstp[q] = f[q];
+    }
+    __syncthreads();
+    if (tid < 200) {
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        float th[5], ph[10];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) th[a] = bufA[(ti * 5 + a) * 33 + k];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) ph[c] = bufB[(tj * 10 + c) * 33 + k];
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+          for (int c = 0; c < 10; ++c) acc[a][c] += th[a] * ph[c];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 200) {
+    const float inv = 1.0f / (float)n;            // R.size(-1) == number of slots
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int c = 0; c < 10; ++c) {
+        const float v = acc[a][c] * inv;
+        R[(ti * 5 + a) * (RS_MAXN + 1) + tj * 10 + c] = v;
+        if (r_out && ti * 5 + a < n && tj * 10 + c < n)
+          r_out[((size_t)b * n + ti * 5 + a) * n + tj * 10 + c] = v;
+      }
+  }
+  __syncthreads();
+
+  // ---- phase 2: y = R g ; thread (yi, yj) owns rows yi*4..+4, cols yj*8..+8 of each 64-column chunk ----
+  const int yi = tid / 8, yj = tid % 8;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    for (int i = tid; i < RS_MAXN * 8; i += 256) {
+      const int row = i >> 3, part = i & 7;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (row < n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * 3 * C + 2 * C + c0 + part * 8));
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bufA[row * 64 + part * 8 + q] = f[q];
+    }
+    __syncthreads();
+    if (tid < 200) {
+      float o[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[a][q] = 0.f;
+      for (int j = 0; j < n; ++j) {
+        float rv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rv[a] = R[(yi * 4 + a) * (RS_MAXN + 1) + j];
+        const float4 g0 = *reinterpret_cast<const float4*>(bufA + j * 64 + yj * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(bufA + j * 64 + yj * 8 + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[a][q] += rv[a] * gv[q];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int row = yi * 4 + a;
+        if (row < n) {
+          uint4 w;
+          w.x = pack_bf16x2(o[a][0], o[a][1]); w.y = pack_bf16x2(o[a][2], o[a][3]);
+          w.z = pack_bf16x2(o[a][4], o[a][5]); w.w = pack_bf16x2(o[a][6], o[a][7]);
+          *reinterpret_cast<uint4*>(y + ((size_t)b * n + row) * C + c0 + yj * 8) = w;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// One CTA per function.  z: fp32 [B, n, D] (token-major Rs_GCN output);  img / txt: fp32 [B, D] (already ELU(fc(bn))).
+// feat = cat(img, l2norm_dim1(z).mean(1), txt);  logits = Wf feat + bf with BatchNorm1d(3D) folded into (Wf, bf).
+__global__ void __launch_bounds__(512)
+fusion_head_kernel(const float* __restrict__ z, const float* __restrict__ img, const float* __restrict__ txt,
+                   const float* __restrict__ wf, const float* __restrict__ bf, float* __restrict__ logits,
+                   float* __restrict__ feat_out, int n, int D, int num_classes) {
+  extern __shared__ float feat[];                 // [3D]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f, sq = 0.f;
+    const float* zp = z + (size_t)b * n * D + c;
+    for (int r = 0; r < n; ++r) {
+      const float v = __ldg(zp + (size_t)r * D);
+      s += v;
+      sq += v * v;
+    }
+    feat[c] = __ldg(img + (size_t)b * D + c);
+    feat[D + c] = (s / sqrtf(sq)) / (float)n;     // l2norm has no eps (GraphModel.py:74-79)
+    feat[2 * D + c] = __ldg(txt + (size_t)b * D + c);
+  }
+  __syncthreads();
+  if (feat_out)
+    for (int c = threadIdx.x; c < 3 * D; c += blockDim.x) feat_out[(size_t)b * 3 * D + c] = feat[c];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < num_classes; k += blockDim.x >> 5) {
+    float acc = 0.f;
+    for (int c = lane; c < 3 * D; c += 32) acc += __ldg(wf + (size_t)k * 3 * D + c) * feat[c];
+    acc = warp_sum(acc);
+    if (lane == 0) logits[(size_t)b * num_classes + k] = acc + __ldg(bf + k);
+  }
+}
+
+// Small-N fp32 linear (classification heads): out[m, n] = act(<x[m,:], w[n,:]> + b[n]); one warp per row.
+// act: 0 none, 3 sigmoid.  swin_transformer_v2.py:642 (head), baselines/models/reveal/ggnn/model.py:29-30.
+__global__ void __launch_bounds__(256)
+linear_small_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    float* __restrict__ out, float* __restrict__ out_act, int M, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  for (int n = 0; n < N; ++n) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc += __ldg(x + (size_t)row * K + k) * __ldg(w + (size_t)n * K + k);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      acc += b ? __ldg(b + n) : 0.f;
+      out[(size_t)row * N + n] = acc;
+      if (out_act) out_act[(size_t)row * N + n] = 1.f / (1.f + expf(-acc));
+    }
+  }
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mvuld_linear_small(const float* x, const float* w, const float* b, float* out, float* out_sigmoid,
+                                  int M, int N, int K, cudaStream_t stream) {
+  MV_CHECK_ARG(N >= 1 && N <= 64, "linear_small: N must be in [1, 64]");
+  if (M <= 0) return 0;
+  linear_small_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, w, b, out, out_sigmoid, M, N, K);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int mvuld_rs_gcn_affinity(const void* tpg, void* y, float* r_out, int B, int n, int C,
+                                     cudaStream_t stream) {
+  MV_CHECK_ARG(n >= 1 && n <= RS_MAXN, "rs_gcn_affinity: n must be in [1, %d]", RS_MAXN);
+  MV_CHECK_ARG(C % 64 == 0, "rs_gcn_affinity: C %% 64");
+  if (B <= 0) return 0;
+  const int smem = (RS_MAXN * (RS_MAXN + 1) + RS_MAXN * 64 + RS_MAXN * 33) * sizeof(float);
+  MV_CUDA_OK(cudaFuncSetAttribute(rs_gcn_affinity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  rs_gcn_affinity_kernel<<<B, 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<bf16*>(y),
+                                                   r_out, n, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int mvuld_fusion_head(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
+                                 float* logits, float* feat_out, int B, int n, int D, int num_classes,
+                                 cudaStream_t stream) {
+  if (B <= 0) return 0;
+  fusion_head_kernel<<<B, 512, 3 * D * sizeof(float), stream>>>(z, img, txt, wf, bf, logits, feat_out, n, D,
+                                                               num_classes);
+  MV_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,400 @@
+// tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (bf16 in, fp32 accumulate in TMEM).
+//
+// Replaces the cuBLAS calls behind every nn.Linear / 1x1 Conv1d on the MVulD hot path (SURVEY.md K1, K6, K7,
+// K9, K12-K14, K16, K17, K19): swin_transformer_v2.py:150,177,27-30,361; unixcoder.py:36 (HF RobertaModel);
+// GraphModel.py:167-177,186-187; Rs_GCN.py:57-71; DGL GATConv.fc / GatedGraphConv.linears / GRUCell.
+//
+// Structure (one CTA per SM, persistent over 128 x BN output tiles):
+//   warp 0      TMA producer   : A/W tiles (128B-swizzled, K-major) -> STAGES-deep smem ring, mbarrier full/empty
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage, commits to mbarriers
+//   warps 2..5  epilogue       : tcgen05.ld 32 lanes x 32 columns, fused epilogue, 128-bit global stores
+//   TMEM        2 x BN fp32 columns: the epilogue of tile i overlaps the mainloop of tile i+1
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mv {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues.  Called once per (row, 32-column chunk) by the thread that owns the row.
+// ------------------------------------------------------------------------------------------------
+struct EpiGeneric {
+  const float* bias;   // [N] or null
+  const float* res;    // fp32 [M, ldr] or null; added after the activation
+  bf16* out_b;         // bf16 [M, ldc] or null
+  float* out_f;        // fp32 [M, ldc] or null
+  int ldr, ldc, act;   // act: 0 none, 1 GELU(erf), 2 ELU
+  int M, N;
+  __device__ __forceinline__ void operator()(int row, int col0, const uint32_t (&r)[32]) const {
+    if (row >= M || col0 >= N) return;
+    float v[32];
+    const bool full = (col0 + 32 <= N);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (bias) {
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+          v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+      } else {
+        for (int i = 0; i < 32; ++i) if (col0 + i < N) v[i] += bias[col0 + i];
+      }
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    } else if (act == 2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = elu1(v[i]);
+    }
+    if (res) {
+      const float* rp = res + (size_t)row * ldr + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 b = __ldg(reinterpret_cast<const float4*>(rp + i));
+          v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+      } else {
+        for (int i = 0; i < 32; ++i) if (col0 + i < N) v[i] += rp[i];
+      }
+    }
+    if (out_b) {
+      bf16* op = out_b + (size_t)row * ldc + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(op + i) = u;
+        }
+      } else {
+        for (int i = 0; i < 32; ++i) if (col0 + i < N) op[i] = __float2bfloat16(v[i]);
+      }
+    }
+    if (out_f) {
+      float* op = out_f + (size_t)row * ldc + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+        for (int i = 0; i < 32; ++i) if (col0 + i < N) op[i] = v[i];
+      }
+    }
+  }
+};
+
+// SwinV2 qkv epilogue (swin_transformer_v2.py:147-157 + the window partition / cyclic shift of :276-286):
+//   + cat(q_bias, 0, v_bias); q,k L2-normalised per head (F.normalize eps 1e-12); q additionally scaled by
+//   exp(min(logit_scale, ln 100)) * log2(e) so the attention kernel's exp2 needs no multiply;
+//   rows scattered to window-major head-major [B*nW, nH, ws*ws, 32]; q,k stored fp16 (|q| <= 145), v bf16.
+struct EpiQkvSwin {
+  const float* q_bias;   // [C]
+  const float* v_bias;   // [C]
+  const float* qscale;   // [nH]
+  __half* q;
+  __half* k;
+  bf16* v;
+  int C, nH, H, W, ws, shift, M;
+  __device__ __forceinline__ void operator()(int row, int col0, const uint32_t (&r)[32]) const {
+    if (row >= M) return;
+    const int which = col0 / C;
+    const int cc = col0 - which * C;
+    const int head = cc >> 5;
+    float v32[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v32[i] = __uint_as_float(r[i]);
+    if (which != 1) {
+      const float* bp = (which == 0 ? q_bias : v_bias) + cc;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(bp + i));
+        v32[i] += b.x; v32[i + 1] += b.y; v32[i + 2] += b.z; v32[i + 3] += b.w;
+      }
+    }
+    if (which < 2) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) ss += v32[i] * v32[i];
+      float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      if (which == 0) inv *= __ldg(qscale + head);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v32[i] *= inv;
+    }
+    // token -> (window, slot) of the cyclically shifted image
+    const int HW = H * W;
+    const int b = row / HW;
+    const int t = row - b * HW;
+    int hh = t / W, ww = t - hh * W;
+    hh -= shift; if (hh < 0) hh += H;
+    ww -= shift; if (ww < 0) ww += W;
+    const int nWw = W / ws;
+    const int win = (hh / ws) * nWw + (ww / ws);
+    const int slot = (hh % ws) * ws + (ww % ws);
+    const int nW = (H / ws) * nWw;
+    const size_t dst = ((((size_t)b * nW + win) * nH + head) * (size_t)(ws * ws) + slot) * 32;
+    if (which == 2) {
+      bf16* op = v + dst;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(v32[i], v32[i + 1]); u.y = pack_bf16x2(v32[i + 2], v32[i + 3]);
+        u.z = pack_bf16x2(v32[i + 4], v32[i + 5]); u.w = pack_bf16x2(v32[i + 6], v32[i + 7]);
+        *reinterpret_cast<uint4*>(op + i) = u;
+      }
+    } else {
+      __half* op = (which == 0 ? q : k) + dst;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        __half2 h0 = __floats2half2_rn(v32[i], v32[i + 1]), h1 = __floats2half2_rn(v32[i + 2], v32[i + 3]);
+        __half2 h2 = __floats2half2_rn(v32[i + 4], v32[i + 5]), h3 = __floats2half2_rn(v32[i + 6], v32[i + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(op + i) = u;
+      }
+    }
+  }
+};
+
+// Head-major qkv epilogue for the RoBERTa encoder (HF RobertaSelfAttention as called from unixcoder.py:36):
+// columns [0,Hd) = query, [Hd,2Hd) = key, [2Hd,3Hd) = value; + bias; q scaled by log2(e)/sqrt(hd);
+// rows scattered to [B, nH, L, hd] (bf16).
+struct EpiQkvHeads {
+  const float* bias;   // [3*Hd]
+  bf16* q;
+  bf16* k;
+  bf16* v;
+  float qmul;
+  int Hd, nH, hd, L, M;
+  __device__ __forceinline__ void operator()(int row, int col0, const uint32_t (&r)[32]) const {
+    if (row >= M) return;
+    const int which = col0 / Hd;
+    const int cc = col0 - which * Hd;
+    const int head = cc / hd;
+    const int d0 = cc - head * hd;
+    float v32[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+      v32[i] = __uint_as_float(r[i]) + b.x; v32[i + 1] = __uint_as_float(r[i + 1]) + b.y;
+      v32[i + 2] = __uint_as_float(r[i + 2]) + b.z; v32[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+    }
+    if (which == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v32[i] *= qmul;
+    }
+    const int b = row / L, t = row - b * L;
+    bf16* base = which == 0 ? q : (which == 1 ? k : v);
+    bf16* op = base + ((((size_t)b * nH + head) * L + t) * hd + d0);
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(v32[i], v32[i + 1]); u.y = pack_bf16x2(v32[i + 2], v32[i + 3]);
+      u.z = pack_bf16x2(v32[i + 4], v32[i + 5]); u.w = pack_bf16x2(v32[i + 6], v32[i + 7]);
+      *reinterpret_cast<uint4*>(op + i) = u;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment
+  static constexpr int TMEM_COLS = 2 * BN;                                    // 256 or 512 (power of two)
+};
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               Epi epi) {
+  using Cfg = GemmCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b0 = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, 2);
+            const uint64_t bd = make_smem_desc(b0 + k * 32, 16, 1024, 2);
+            umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);       // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int acc = local & 1;
+      mbar_wait(&tfull[acc], (local >> 1) & 1, 4);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+      const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t0 + c * 32, r);
+        tmem_ld_wait();
+        epi(row, n_blk * BN + c * 32, r);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, int STAGES, class Epi>
+static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, STAGES>;
+  MV_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  MV_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements (16 B): %d %d", lda, ldw);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int rc = make_tmap_16b(&tmA, A, 2, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
+    int rc = make_tmap_16b(&tmB, W, 2, dims, str, box, 128);
+    if (rc) return rc;
+  }
+  auto kern = gemm_tn_kernel<BN, STAGES, Epi>;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                               int act, const float* res_f32, int ldr, void* out_bf16, float* out_f32, int ldc,
+                               cudaStream_t stream) {
+  MV_CHECK_ARG(out_bf16 || out_f32, "gemm: no output");
+  MV_CHECK_ARG(ldc % 8 == 0, "gemm: ldc must be a multiple of 8 elements");
+  MV_CHECK_ARG(!res_f32 || ldr % 4 == 0, "gemm: ldr must be a multiple of 4 elements");
+  EpiGeneric e;
+  e.bias = bias; e.res = res_f32; e.out_b = reinterpret_cast<bf16*>(out_bf16); e.out_f = out_f32;
+  e.ldr = ldr; e.ldc = ldc; e.act = act; e.M = M; e.N = N;
+  return launch_gemm<128, 6, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
+}
+
+extern "C" int mvuld_swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias,
+                              const float* qscale, void* q, void* k, void* v, int B, int H, int W, int C, int nH,
+                              int ws, int shift, cudaStream_t stream) {
+  MV_CHECK_ARG(C % 128 == 0 && C / nH == 32, "swin_qkv: need C %% 128 == 0 and head_dim 32 (C=%d nH=%d)", C, nH);
+  MV_CHECK_ARG(H % ws == 0 && W % ws == 0 && shift >= 0 && shift < ws, "swin_qkv: bad window geometry");
+  EpiQkvSwin e;
+  e.q_bias = q_bias; e.v_bias = v_bias; e.qscale = qscale;
+  e.q = reinterpret_cast<__half*>(q); e.k = reinterpret_cast<__half*>(k); e.v = reinterpret_cast<bf16*>(v);
+  e.C = C; e.nH = nH; e.H = H; e.W = W; e.ws = ws; e.shift = shift; e.M = B * H * W;
+  return launch_gemm<128, 6, EpiQkvSwin>(X, C, Wqkv, C, B * H * W, 3 * C, C, e, stream);
+}
+
+extern "C" int mvuld_heads_qkv(const void* X, const void* Wqkv, const float* bias, void* q, void* k, void* v, int B,
+                               int L, int Hd, int nH, float qmul, cudaStream_t stream) {
+  MV_CHECK_ARG(Hd % nH == 0 && (Hd / nH) % 32 == 0 && Hd % 32 == 0, "heads_qkv: head_dim must be a multiple of 32");
+  EpiQkvHeads e;
+  e.bias = bias; e.q = reinterpret_cast<bf16*>(q); e.k = reinterpret_cast<bf16*>(k); e.v = reinterpret_cast<bf16*>(v);
+  e.qmul = qmul; e.Hd = Hd; e.nH = nH; e.hd = Hd / nH; e.L = L; e.M = B * L;
+  return launch_gemm<128, 6, EpiQkvHeads>(X, Hd, Wqkv, Hd, B * L, 3 * Hd, Hd, e, stream);
+}

@@ -1,0 +1,341 @@
+"""Live fusion model ``Multi_DefectModel_new_GCN`` and the GGNN baseline branch, B200-native.
+
+Interface mirror of /root/reference/mvuld/models/GraphModel.py:81-211 (constructor ``(config, pretrained=True,
+attention=True)``, ``forward(g, img_embedding, func_text_embedding) -> logits [B, num_classes]``, same state-dict
+keys incl. the DGL ``GATConv`` ones ``gat.fc.weight / gat.attn_l / gat.attn_r / gat.bias``), of
+/root/reference/mvuld/models/Rs_GCN.py:7-73 (``Rs_GCN`` parameter names) and of
+/root/reference/baselines/models/reveal/ggnn/model.py:8-31 (``GGNNSum``; DGL ``GatedGraphConv`` keys
+``ggnn.linears.{t}.weight``, ``ggnn.gru.weight_ih`` ...).
+
+``g`` is a :class:`mvuld_b200.graph.Graph` (or a real DGLGraph through ``graph.from_dgl``).  Eval-mode semantics:
+dropout off, every BatchNorm uses its running statistics and is folded into the adjacent linear layer / a per-slot
+affine when the weights are packed.  The dead ``h_func`` branch (GraphModel.py:172,177) is not evaluated.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .graph import Graph
+
+
+# ------------------------------------------------------------------------------------------------------
+# parameter containers
+# ------------------------------------------------------------------------------------------------------
+class GATConv(nn.Module):
+    """DGL ``GATConv`` parameters (fc without bias, attn_l / attn_r [1, H, F], bias [H*F]); DGL's reset_parameters."""
+
+    def __init__(self, in_feats, out_feats, num_heads, feat_drop=0., negative_slope=0.2):
+        super().__init__()
+        self._in, self._out, self._heads, self.negative_slope = in_feats, out_feats, num_heads, negative_slope
+        self.fc = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.bias = nn.Parameter(torch.zeros(num_heads * out_feats))
+        gain = nn.init.calculate_gain('relu')
+        nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_l, gain=gain)
+        nn.init.xavier_normal_(self.attn_r, gain=gain)
+
+
+class Rs_GCN(nn.Module):
+    """Rs_GCN.py:9-50 parameters: g / theta / phi = Conv1d(k=1), W = Sequential(Conv1d(k=1), BatchNorm1d) zero-init."""
+
+    def __init__(self, in_channels, inter_channels, bn_layer=True):
+        super().__init__()
+        if not bn_layer:
+            raise NotImplementedError("mvuld_b200 Rs_GCN: bn_layer=True only (as the fusion model builds it)")
+        self.in_channels, self.inter_channels = in_channels, inter_channels or max(in_channels // 2, 1)
+        self.g = nn.Conv1d(in_channels, self.inter_channels, 1)
+        self.W = nn.Sequential(nn.Conv1d(self.inter_channels, in_channels, 1), nn.BatchNorm1d(in_channels))
+        nn.init.constant_(self.W[1].weight, 0)
+        nn.init.constant_(self.W[1].bias, 0)
+        self.theta = nn.Conv1d(in_channels, self.inter_channels, 1)
+        self.phi = nn.Conv1d(in_channels, self.inter_channels, 1)
+
+
+def _bn_affine(bn: nn.BatchNorm1d):
+    """eval-mode BatchNorm as y = x * scale + shift (fp32, on the parameters' device)."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale, shift
+
+
+def _fold_bn_into_linear(bn: nn.BatchNorm1d, lin: nn.Linear):
+    """lin(bn(x)) == x @ W'.T + b' with W' = W * scale, b' = b + W @ shift."""
+    scale, shift = _bn_affine(bn)
+    w = lin.weight.detach().float()
+    return w * scale[None, :], lin.bias.detach().float() + w @ shift
+
+
+class Multi_DefectModel_new_GCN(nn.Module):
+    def __init__(self, config, pretrained=True, attention=True):
+        super().__init__()
+        self.num_features = 1024
+        self.config = config
+        self.num_classes = config.MODEL.NUM_CLASSES
+        hfeat, embfeat, numheads = 512, 768, 4
+        self.gat = GATConv(embfeat, hfeat, numheads, feat_drop=0.2)
+        self.gat2 = GATConv(hfeat * numheads, hfeat, numheads, feat_drop=0.2)
+        self.fc = nn.Linear(hfeat * numheads, hfeat)
+        self.fconly = nn.Linear(embfeat, hfeat)
+        self.hidden = nn.ModuleList([nn.Linear(hfeat, hfeat) for _ in range(8)])
+        for k in range(1, 9):
+            setattr(self, f"Rs_GCN_{k}", Rs_GCN(in_channels=512, inter_channels=512))
+        self.bn_text = nn.BatchNorm1d(embfeat)
+        self.ln_text = nn.LayerNorm(embfeat)
+        self.fc_text = nn.Linear(embfeat, hfeat)
+        self.max_node = 100
+        self.bn_gat = nn.BatchNorm1d(self.max_node)
+        self.fc_gat = nn.Linear(512, 480)
+        self.bn_bbox = nn.BatchNorm1d(self.max_node)
+        self.fc_bbox = nn.Linear(4, 32)
+        self.swinbn = nn.BatchNorm1d(self.num_features)
+        self.swinfc = nn.Linear(self.num_features, hfeat)
+        self.hbn = nn.BatchNorm1d(hfeat)
+        self.hln = nn.LayerNorm(hfeat)
+        self.hfc = nn.Linear(hfeat, hfeat)
+        self.final_fc = nn.Linear(hfeat * 3, self.num_classes)
+        self.final_fc_bn = nn.BatchNorm1d(hfeat * 3)
+        self._plan = None
+
+    def invalidate(self):
+        self._plan = None
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def prepare(self):
+        dev = self.fc.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("mvuld_b200 fusion model runs on CUDA only (no CPU fallback)")
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        b16 = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+        p = dict(dev=dev)
+        w, b = _fold_bn_into_linear(self.swinbn, self.swinfc)
+        p["img"] = (b16(w), f32(b))
+        w, b = _fold_bn_into_linear(self.bn_text, self.fc_text)
+        p["txt"] = (b16(w), f32(b))
+        for name in ("gat", "gat2"):
+            m = getattr(self, name)
+            p[name] = dict(w=b16(m.fc.weight), al=f32(m.attn_l.view(-1)), ar=f32(m.attn_r.view(-1)), bias=f32(m.bias),
+                           H=m._heads, F=m._out, slope=float(m.negative_slope))
+        p["fc"] = (b16(self.fc.weight), f32(self.fc.bias))
+        p["hidden"] = [(b16(l.weight), f32(l.bias)) for l in self.hidden]
+        s, t = _bn_affine(self.bn_gat)
+        p["bn_gat"] = (f32(s), f32(t))
+        p["fc_gat"] = (b16(self.fc_gat.weight), f32(self.fc_gat.bias))
+        s, t = _bn_affine(self.bn_bbox)
+        p["bn_bbox"] = (f32(s), f32(t))
+        p["fc_bbox"] = (f32(self.fc_bbox.weight), f32(self.fc_bbox.bias))
+        p["gcn"] = []
+        for k in range(1, 9):
+            m = getattr(self, f"Rs_GCN_{k}")
+            wcat = torch.cat([m.theta.weight[:, :, 0], m.phi.weight[:, :, 0], m.g.weight[:, :, 0]], 0)
+            bcat = torch.cat([m.theta.bias, m.phi.bias, m.g.bias], 0)
+            scale, shift = _bn_affine(m.W[1])                      # BN after the 1x1 conv: fold on the output side
+            ww = m.W[0].weight.detach().float()[:, :, 0] * scale[:, None]
+            wb = m.W[0].bias.detach().float() * scale + shift
+            p["gcn"].append(dict(wcat=b16(wcat), bcat=f32(bcat), ww=b16(ww), wb=f32(wb)))
+        scale, shift = _bn_affine(self.final_fc_bn)
+        wf = self.final_fc.weight.detach().float()
+        p["final"] = (f32(wf * scale[None, :]), f32(self.final_fc.bias.detach().float() + wf @ shift))
+        self._plan = p
+        return self
+
+    @torch.no_grad()
+    def forward(self, g: Graph, img_embedding: torch.Tensor, func_text_embedding: torch.Tensor) -> torch.Tensor:
+        """GraphModel.py:150-211."""
+        if self.training:
+            raise RuntimeError("mvuld_b200 fusion model implements the eval-mode forward: call model.eval()")
+        if not isinstance(g, Graph):
+            from .graph import from_dgl
+            g = from_dgl(g)
+        if not img_embedding.is_cuda:
+            raise RuntimeError("mvuld_b200 fusion model takes CUDA tensors (no CPU fallback)")
+        if self._plan is None:
+            self.prepare()
+        p = self._plan
+        dev = p["dev"]
+        B = img_embedding.shape[0]
+        N = g.num_nodes()
+        if g.batch_size != B:
+            raise ValueError(f"graph batch size {g.batch_size} != embedding batch size {B}")
+        e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+        bf, f32 = torch.bfloat16, torch.float32
+
+        # image / text projections: ELU(fc(bn(.)))  (GraphModel.py:153-159)
+        img_b, txt_b = e((B, 1024), bf), e((B, 768), bf)
+        _lib.call("mvuld_f32_to_bf16", img_embedding.float().contiguous(), img_b, B * 1024)
+        _lib.call("mvuld_f32_to_bf16", func_text_embedding.float().contiguous(), txt_b, B * 768)
+        ximg, xtxt = e((B, 512), f32), e((B, 512), f32)
+        _lib.gemm(img_b, p["img"][0], bias=p["img"][1], act=_lib.ACT_ELU, out_f32=ximg)
+        _lib.gemm(txt_b, p["txt"][0], bias=p["txt"][1], act=_lib.ACT_ELU, out_f32=xtxt)
+
+        # graph branch (GraphModel.py:163-177)
+        indptr, idx_src, _ = g.in_csr()
+        offsets = g.node_offsets()
+        h_in = g.ndata["_UNIX_NODE_EMB"]
+        pos = g.ndata["pos_emb"].float().contiguous()
+        hb = e((N, h_in.shape[1]), bf)
+        _lib.call("mvuld_f32_to_bf16", h_in.float().contiguous(), hb, N * h_in.shape[1])
+        zero_deg = torch.zeros(1, device=dev, dtype=torch.int32)
+        for name in ("gat", "gat2"):
+            gp = p[name]
+            H, F = gp["H"], gp["F"]
+            z = e((N, H * F), bf)
+            _lib.gemm(hb, gp["w"], out_bf16=z)
+            el, er = e((N, H), f32), e((N, H), f32)
+            _lib.call("mvuld_gat_scores", z, gp["al"], gp["ar"], el, er, N, H, F)
+            hb = e((N, H * F), bf)
+            _lib.call("mvuld_gat_aggregate", z, el, er, indptr, idx_src, gp["bias"], hb, N, H, F, gp["slope"], zero_deg)
+        a = e((N, 512), bf)
+        _lib.gemm(hb, p["fc"][0], bias=p["fc"][1], act=_lib.ACT_ELU, out_bf16=a)
+        a2 = e((N, 512), bf)
+        for (w, b) in p["hidden"]:
+            _lib.gemm(a, w, bias=b, act=_lib.ACT_ELU, out_bf16=a2)
+            a, a2 = a2, a
+        g.ndata['HGATOUTPUT'] = a                      # side effects of GraphModel.py:180-181 (bf16 here)
+        g.ndata['HFGATOUTPUT'] = pos
+
+        # unbatch -> pad/truncate to max_node -> slot BN -> fc_gat / fc_bbox -> concat (GraphModel.py:182-189)
+        n = self.max_node
+        hp = e((B * n, 512), bf)
+        _lib.call("mvuld_unbatch_pad_bn", a, offsets, p["bn_gat"][0], p["bn_gat"][1], hp, None, B, n, 512)
+        z32, zb = e((B * n, 512), f32), e((B * n, 512), bf)
+        _lib.gemm(hp, p["fc_gat"][0], bias=p["fc_gat"][1], act=_lib.ACT_ELU, out_bf16=zb, out_f32=z32)
+        _lib.call("mvuld_pos_branch", pos, offsets, p["bn_bbox"][0], p["bn_bbox"][1], p["fc_bbox"][0],
+                  p["fc_bbox"][1], z32, zb, B, n, 32, 512, 480)
+
+        # 8 x Rs_GCN on the token-major [B*n, 512] tensor (GraphModel.py:190-198)
+        tpg, y = e((B * n, 1536), bf), e((B * n, 512), bf)
+        for gc in p["gcn"]:
+            _lib.gemm(zb, gc["wcat"], bias=gc["bcat"], out_bf16=tpg)
+            _lib.call("mvuld_rs_gcn_affinity", tpg, y, None, B, n, 512)
+            _lib.gemm(y, gc["ww"], bias=gc["wb"], res=z32, out_bf16=zb, out_f32=z32)
+
+        # l2norm(dim=1) + mean + concat + BN + final_fc (GraphModel.py:200-209)
+        logits = e((B, self.num_classes), f32)
+        _lib.call("mvuld_fusion_head", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
+                  self.num_classes)
+        if int(zero_deg.item()) != 0:
+            raise RuntimeError("There are 0-in-degree nodes in the graph (GATConv allow_zero_in_degree=False); "
+                               "add self-loops with mvuld_b200.graph.add_self_loop")
+        g.check_status()
+        return logits
+
+
+class GatedGraphConv(nn.Module):
+    """DGL ``GatedGraphConv`` parameters: linears[t] = Linear(out, out), gru = GRUCell(out, out)."""
+
+    def __init__(self, in_feats, out_feats, n_steps, n_etypes, bias=True):
+        super().__init__()
+        self._in_feats, self._out_feats, self._n_steps, self._n_etypes = in_feats, out_feats, n_steps, n_etypes
+        self.linears = nn.ModuleList([nn.Linear(out_feats, out_feats) for _ in range(n_etypes)])
+        self.gru = nn.GRUCell(out_feats, out_feats, bias=bias)
+        gain = nn.init.calculate_gain('relu')
+        for lin in self.linears:
+            nn.init.xavier_normal_(lin.weight, gain=gain)
+            nn.init.zeros_(lin.bias)
+
+
+class GGNNSum(nn.Module):
+    """baselines/models/reveal/ggnn/model.py:8-31."""
+
+    def __init__(self, input_dim, output_dim, max_edge_types=3, num_steps=8):
+        super().__init__()
+        if input_dim > output_dim:
+            raise ValueError("GatedGraphConv requires in_feats <= out_feats")
+        if output_dim % 8 != 0 or output_dim > 256:
+            raise NotImplementedError("mvuld_b200 GGNN: out_feats must be a multiple of 8 and <= 256")
+        self.inp_dim, self.out_dim = input_dim, output_dim
+        self.max_edge_types, self.num_timesteps = max_edge_types, num_steps
+        self.ggnn = GatedGraphConv(input_dim, output_dim, num_steps, max_edge_types)
+        self.classifier = nn.Linear(output_dim, 1)
+        self._plan = None
+
+    def invalidate(self):
+        self._plan = None
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def prepare(self):
+        dev = self.classifier.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("mvuld_b200 GGNN runs on CUDA only (no CPU fallback)")
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        b16 = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+        gg = self.ggnn
+        self._plan = dict(
+            dev=dev,
+            wmsg=b16(torch.cat([l.weight for l in gg.linears], 0)),     # [T*D, D]: row t*D + o = linears[t].weight[o]
+            bmsg=f32(torch.cat([l.bias for l in gg.linears], 0)),
+            wih=b16(gg.gru.weight_ih), bih=f32(gg.gru.bias_ih), whh=b16(gg.gru.weight_hh), bhh=f32(gg.gru.bias_hh),
+            wc=f32(self.classifier.weight), bc=f32(self.classifier.bias))
+        return self
+
+    @torch.no_grad()
+    def node_states(self, g: Graph) -> torch.Tensor:
+        """GatedGraphConv forward -> fp32 [N, out] (``g.ndata['GGNNOUTPUT']`` in the reference)."""
+        if self.training:
+            raise RuntimeError("mvuld_b200 GGNN implements the eval-mode forward: call model.eval()")
+        if self._plan is None:
+            self.prepare()
+        p = self._plan
+        dev = p["dev"]
+        feats = g.ndata['_WORD2VEC'].float().contiguous()
+        et = g.edata["_ETYPE"].to(torch.int64).contiguous()
+        N, D, T = g.num_nodes(), self.out_dim, self.max_edge_types
+        indptr, idx_src, eids = g.in_csr()
+        status = torch.zeros(1, device=dev, dtype=torch.int32)
+        et_sorted = torch.empty(et.numel(), device=dev, dtype=torch.uint8)
+        _lib.call("mvuld_gather_etype", et, eids, et.numel(), T, et_sorted, status)
+        e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+        h32, hb = e((N, D), torch.float32), e((N, D), torch.bfloat16)
+        _lib.call("mvuld_ggnn_init", feats, h32, hb, N, feats.shape[1], D)
+        msgs, a = e((N, T * D), torch.bfloat16), e((N, D), torch.bfloat16)
+        gi, gh = e((N, 3 * D), torch.bfloat16), e((N, 3 * D), torch.bfloat16)
+        for _ in range(self.num_timesteps):
+            _lib.gemm(hb, p["wmsg"], bias=p["bmsg"], out_bf16=msgs)
+            _lib.call("mvuld_ggnn_gather_sum", msgs, indptr, idx_src, et_sorted, a, N, T, D)
+            _lib.gemm(a, p["wih"], bias=p["bih"], out_bf16=gi)
+            _lib.gemm(hb, p["whh"], bias=p["bhh"], out_bf16=gh)
+            _lib.call("mvuld_gru_gates", gi, gh, h32, hb, N, D)
+        if int(status.item()) != 0:
+            raise AssertionError("edge type indices out of range [0, n_etypes)")
+        g.check_status()
+        return h32
+
+    @torch.no_grad()
+    def forward(self, g: Graph, dataset=None, cuda=False):
+        """reveal/ggnn/model.py:20-31 -> (sigmoid(logit) [B], logit [B, 1])."""
+        h = self.node_states(g)
+        g.ndata['GGNNOUTPUT'] = h
+        p = self._plan
+        B = g.batch_size
+        s = torch.empty(B, self.out_dim, device=h.device, dtype=torch.float32)
+        _lib.call("mvuld_segment_sum", h, g.node_offsets(), s, B, self.out_dim)
+        logit = torch.empty(B, 1, device=h.device, dtype=torch.float32)
+        prob = torch.empty(B, 1, device=h.device, dtype=torch.float32)
+        _lib.call("mvuld_linear_small", s, p["wc"], p["bc"], logit, prob, B, 1, self.out_dim)
+        self._last_sum = s
+        return prob.squeeze(-1), logit
+
+    def save_ggnn_output(self, g, dataset=None, cuda=False):
+        """reveal/ggnn/model.py:33-44 -> (prob, h_i_sum)."""
+        prob, _ = self.forward(g)
+        return prob, self._last_sum

@@ -1,0 +1,33 @@
+"""Composed end-to-end MVulD forward.
+
+The reference never runs the three modalities in one pass: SwinV2 and UniXcoder vectors are cached to disk offline
+(/root/reference/mvuld/data/data_list.py:179-211,292-313) and only the fusion model runs in the training loop
+(/root/reference/mvuld/main_bigvul.py:308-329).  This module wires the same three pieces back to back on one stream:
+
+    img_embedding       = swin.forward_features(image)          # swin_transformer_v2.py:623-635
+    func_text_embedding = unix.get_repr(token_ids)[0]           # unixcoder.py:91-95
+    logits              = fusion(g, img_embedding, func_text_embedding)   # GraphModel.py:150-211
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .build import build_model
+from .graph_model import Multi_DefectModel_new_GCN
+from .unixcoder import build_MyUniXcoder
+
+
+class MVulD(nn.Module):
+    def __init__(self, config, roberta_config=None):
+        super().__init__()
+        self.config = config
+        self.swin = build_model(config)
+        self.unix = build_MyUniXcoder(roberta_config)
+        self.fusion = Multi_DefectModel_new_GCN(config)
+
+    @torch.no_grad()
+    def forward(self, image: torch.Tensor, token_ids: torch.Tensor, g) -> torch.Tensor:
+        img_embedding = self.swin.forward_features(image)
+        func_text_embedding, _ = self.unix.get_repr(token_ids)
+        return self.fusion(g, img_embedding, func_text_embedding)

@@ -1,0 +1,378 @@
+"""SwinV2 image branch, B200-native.
+
+Interface mirror of /root/reference/mvuld/models/swin_transformer_v2.py:503-652 (``SwinTransformerV2``): same
+constructor arguments, same ``state_dict`` keys and persistent buffers, ``forward`` / ``forward_features`` /
+``output_num`` / ``flops`` / ``no_weight_decay`` / ``no_weight_decay_keywords``, same asserts on image size.  The
+``nn.Linear`` / ``nn.LayerNorm`` / ``nn.Conv2d`` sub-modules are parameter containers only -- their ``forward`` is
+never called.  The compute is a fixed sequence of C-ABI kernel launches (``include/mvuld_b200.h``) on the current
+CUDA stream:
+
+    patch_embed -> per block { swin_qkv (GEMM + cosine-norm + scale + window/shift scatter) ->
+    swin_window_attention (tcgen05 QK^T / softmax / PV with analytic CPB bias and shift mask) -> proj GEMM ->
+    LN+residual -> fc1 GEMM+GELU -> fc2 GEMM -> LN+residual } -> per stage { 2x2 gather -> reduction GEMM -> LN } ->
+    LN + token mean.
+
+Activations are bf16 with fp32 accumulation; the residual stream is kept in fp32 next to a bf16 shadow that feeds the
+GEMMs.  Eval-mode semantics only (DropPath / dropout are identities); calling it in training mode raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+LOG2E = 1.4426950408889634
+
+
+def _to_2tuple(x):
+    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+
+def _relative_coords_table(ws: int, pretrained_ws: int) -> torch.Tensor:
+    """Buffer of WindowAttention (:98-111): [1, 2ws-1, 2ws-1, 2] log-spaced relative coordinates."""
+    r = torch.arange(-(ws - 1), ws, dtype=torch.float32)
+    tab = torch.stack(torch.meshgrid([r, r], indexing="ij")).permute(1, 2, 0).contiguous().unsqueeze(0)
+    tab = tab / float((pretrained_ws - 1) if pretrained_ws > 0 else (ws - 1))
+    tab = tab * 8
+    return torch.sign(tab) * torch.log2(torch.abs(tab) + 1.0) / math.log2(8)
+
+
+def _relative_position_index(ws: int) -> torch.Tensor:
+    """Buffer of WindowAttention (:116-125): int64 [ws*ws, ws*ws]."""
+    n = torch.arange(ws * ws)
+    h, w = n // ws, n % ws
+    return (h[:, None] - h[None, :] + ws - 1) * (2 * ws - 1) + (w[:, None] - w[None, :] + ws - 1)
+
+
+def _attn_mask(H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """Buffer of SwinTransformerBlock (:245-264): [nW, N, N] in {0, -100}; the kernels never read it."""
+    def band(n):
+        i = torch.arange(n)
+        return (i >= n - ws).long() + (i >= n - shift).long()
+    reg = band(H)[:, None] * 3 + band(W)[None, :]
+    reg = reg.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    return torch.where(reg[:, None, :] != reg[:, :, None], torch.tensor(-100.0), torch.tensor(0.0))
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.fc2 = nn.Linear(hidden_features, in_features)
+
+
+class WindowAttention(nn.Module):
+    """Parameter container of :67-138."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, pretrained_window_size=(0, 0)):
+        super().__init__()
+        self.dim, self.window_size, self.num_heads = dim, window_size, num_heads
+        self.pretrained_window_size = pretrained_window_size
+        self.logit_scale = nn.Parameter(torch.log(10 * torch.ones((num_heads, 1, 1))), requires_grad=True)
+        self.cpb_mlp = nn.Sequential(nn.Linear(2, 512, bias=True), nn.ReLU(inplace=True),
+                                     nn.Linear(512, num_heads, bias=False))
+        self.register_buffer("relative_coords_table",
+                             _relative_coords_table(window_size[0], pretrained_window_size[0]))
+        self.register_buffer("relative_position_index", _relative_position_index(window_size[0]))
+        self.qkv = nn.Linear(dim, dim * 3, bias=False)
+        if qkv_bias:
+            self.q_bias = nn.Parameter(torch.zeros(dim))
+            self.v_bias = nn.Parameter(torch.zeros(dim))
+        else:
+            self.q_bias = None
+            self.v_bias = None
+        self.proj = nn.Linear(dim, dim)
+
+
+class SwinTransformerBlock(nn.Module):
+    """Parameter container of :199-268."""
+
+    def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 pretrained_window_size=0):
+        super().__init__()
+        self.dim, self.input_resolution, self.num_heads = dim, input_resolution, num_heads
+        self.window_size, self.shift_size, self.mlp_ratio = window_size, shift_size, mlp_ratio
+        if min(self.input_resolution) <= self.window_size:
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = WindowAttention(dim, _to_2tuple(self.window_size), num_heads, qkv_bias,
+                                    _to_2tuple(pretrained_window_size))
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+        mask = _attn_mask(*self.input_resolution, self.window_size, self.shift_size) if self.shift_size > 0 else None
+        self.register_buffer("attn_mask", mask)
+
+    def flops(self):
+        H, W = self.input_resolution
+        N = self.window_size * self.window_size
+        nW = H * W / N
+        attn = N * self.dim * 3 * self.dim + 2 * self.num_heads * N * (self.dim // self.num_heads) * N \
+            + N * self.dim * self.dim
+        return self.dim * H * W + nW * attn + 2 * H * W * self.dim * self.dim * self.mlp_ratio + self.dim * H * W
+
+
+class PatchMerging(nn.Module):
+    def __init__(self, input_resolution, dim):
+        super().__init__()
+        self.input_resolution, self.dim = input_resolution, dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = nn.LayerNorm(2 * dim)
+
+    def flops(self):
+        H, W = self.input_resolution
+        return (H // 2) * (W // 2) * 4 * self.dim * 2 * self.dim + H * W * self.dim // 2
+
+
+class BasicLayer(nn.Module):
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio, qkv_bias, downsample,
+                 pretrained_window_size):
+        super().__init__()
+        self.dim, self.input_resolution, self.depth = dim, input_resolution, depth
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim, input_resolution, num_heads, window_size,
+                                 0 if (i % 2 == 0) else window_size // 2, mlp_ratio, qkv_bias,
+                                 pretrained_window_size) for i in range(depth)])
+        self.downsample = PatchMerging(input_resolution, dim) if downsample else None
+
+    def _init_respostnorm(self):
+        for blk in self.blocks:
+            for p in (blk.norm1.bias, blk.norm1.weight, blk.norm2.bias, blk.norm2.weight):
+                nn.init.constant_(p, 0)
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, patch_norm=True):
+        super().__init__()
+        self.img_size, self.patch_size = _to_2tuple(img_size), _to_2tuple(patch_size)
+        self.patches_resolution = [self.img_size[0] // self.patch_size[0], self.img_size[1] // self.patch_size[1]]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.in_chans, self.embed_dim = in_chans, embed_dim
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
+        self.norm = nn.LayerNorm(embed_dim) if patch_norm else None
+
+    def flops(self):
+        Ho, Wo = self.patches_resolution
+        f = Ho * Wo * self.embed_dim * self.in_chans * self.patch_size[0] * self.patch_size[1]
+        return f + (Ho * Wo * self.embed_dim if self.norm is not None else 0)
+
+
+class SwinTransformerV2(nn.Module):
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, num_classes=1000, embed_dim=96, depths=[2, 2, 6, 2],
+                 num_heads=[3, 6, 12, 24], window_size=7, mlp_ratio=4., qkv_bias=True, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
+                 use_checkpoint=False, pretrained_window_sizes=[0, 0, 0, 0], **kwargs):
+        super().__init__()
+        if patch_size != 4 or in_chans != 3:
+            raise NotImplementedError("mvuld_b200 SwinV2: patch_size 4 and 3 input channels only")
+        if ape:
+            raise NotImplementedError("mvuld_b200 SwinV2: absolute position embedding (APE) is not on the hot path")
+        if not qkv_bias or not patch_norm:
+            raise NotImplementedError("mvuld_b200 SwinV2: QKV_BIAS and PATCH_NORM must be enabled")
+        self.num_classes, self.num_layers, self.embed_dim = num_classes, len(depths), embed_dim
+        self.ape, self.patch_norm, self.mlp_ratio = ape, patch_norm, mlp_ratio
+        self.num_features = int(embed_dim * 2 ** (self.num_layers - 1))
+        self.depths, self.heads = list(depths), list(num_heads)
+        self.patch_embed = PatchEmbed(img_size, patch_size, in_chans, embed_dim, patch_norm)
+        pr = self.patch_embed.patches_resolution
+        self.patches_resolution = pr
+        self.layers = nn.ModuleList()
+        for i in range(self.num_layers):
+            self.layers.append(BasicLayer(int(embed_dim * 2 ** i), (pr[0] // (2 ** i), pr[1] // (2 ** i)), depths[i],
+                                          num_heads[i], window_size, mlp_ratio, qkv_bias,
+                                          i < self.num_layers - 1, pretrained_window_sizes[i]))
+        self.norm = nn.LayerNorm(self.num_features)
+        self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
+        self.apply(self._init_weights)
+        for bly in self.layers:
+            bly._init_respostnorm()
+        self._plan = None
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'absolute_pos_embed'}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {"cpb_mlp", "logit_scale", 'relative_position_bias_table'}
+
+    def output_num(self):
+        return self.num_features
+
+    def flops(self):
+        f = self.patch_embed.flops()
+        for layer in self.layers:
+            f += sum(b.flops() for b in layer.blocks)
+            if layer.downsample is not None:
+                f += layer.downsample.flops()
+        f += self.num_features * self.patches_resolution[0] * self.patches_resolution[1] // (2 ** self.num_layers)
+        f += self.num_features * self.num_classes
+        return f
+
+    # ------------------------------------------------------------------------------------------------
+    # engine
+    # ------------------------------------------------------------------------------------------------
+    def invalidate(self):
+        """Drop packed weights / tables (call after changing parameters in place)."""
+        self._plan = None
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def prepare(self):
+        """Pack weights (bf16 GEMM operands, fp32 vectors) and build the CPB tables; once per weight version."""
+        dev = self.patch_embed.proj.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("mvuld_b200 SwinV2 runs on CUDA only: move the model with .cuda() (no CPU fallback)")
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        b16 = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+        plan = {"dev": dev, "blocks": [], "merge": []}
+        pe = self.patch_embed
+        plan["pe"] = dict(w=f32(pe.proj.weight).view(self.embed_dim, -1).contiguous(), b=f32(pe.proj.bias),
+                          g=f32(pe.norm.weight), beta=f32(pe.norm.bias), eps=pe.norm.eps)
+        for li, layer in enumerate(self.layers):
+            for blk in layer.blocks:
+                a = blk.attn
+                ws, nH = blk.window_size, blk.num_heads
+                side = 2 * ws - 1
+                tab_rev = torch.empty(nH, side * side, device=dev, dtype=torch.float32)
+                tab_ref = torch.empty(nH, side * side, device=dev, dtype=torch.float32)
+                tab_max = torch.empty(nH, device=dev, dtype=torch.float32)
+                _lib.call("mvuld_cpb_table", f32(a.cpb_mlp[0].weight), f32(a.cpb_mlp[0].bias),
+                          f32(a.cpb_mlp[2].weight), nH, ws, int(a.pretrained_window_size[0]), tab_rev, tab_ref, tab_max)
+                qscale = torch.clamp(f32(a.logit_scale).view(-1), max=math.log(1.0 / 0.01)).exp() * LOG2E
+                plan["blocks"].append(dict(
+                    H=blk.input_resolution[0], W=blk.input_resolution[1], C=blk.dim, nH=nH, ws=ws,
+                    shift=blk.shift_size, wqkv=b16(a.qkv.weight), qb=f32(a.q_bias), vb=f32(a.v_bias),
+                    qscale=qscale.contiguous(), tab_rev=tab_rev, tab_ref=tab_ref, tab_max=tab_max,
+                    wproj=b16(a.proj.weight), bproj=f32(a.proj.bias),
+                    g1=f32(blk.norm1.weight), b1=f32(blk.norm1.bias), eps1=blk.norm1.eps,
+                    wfc1=b16(blk.mlp.fc1.weight), bfc1=f32(blk.mlp.fc1.bias),
+                    wfc2=b16(blk.mlp.fc2.weight), bfc2=f32(blk.mlp.fc2.bias),
+                    g2=f32(blk.norm2.weight), b2=f32(blk.norm2.bias), eps2=blk.norm2.eps, stage=li))
+            if layer.downsample is not None:
+                d = layer.downsample
+                plan["merge"].append(dict(H=d.input_resolution[0], W=d.input_resolution[1], C=d.dim,
+                                          w=b16(d.reduction.weight), g=f32(d.norm.weight), b=f32(d.norm.bias),
+                                          eps=d.norm.eps))
+        plan["norm"] = dict(g=f32(self.norm.weight), b=f32(self.norm.bias), eps=self.norm.eps)
+        if isinstance(self.head, nn.Linear):
+            plan["head"] = dict(w=f32(self.head.weight), b=f32(self.head.bias))
+        plan["ws"] = {}
+        self._plan = plan
+        return self
+
+    def _workspace(self, B: int):
+        p = self._plan
+        if B in p["ws"]:
+            return p["ws"][B]
+        dev = p["dev"]
+        L0 = self.patches_resolution[0] * self.patches_resolution[1]
+        n = B * L0 * self.embed_dim                     # elements of the widest [tokens, C] activation
+        e = lambda numel, dt: torch.empty(numel, device=dev, dtype=dt)
+        ws = dict(x32=e(n, torch.float32), xb=e(n, torch.bfloat16), q=e(n, torch.float16), k=e(n, torch.float16),
+                  v=e(n, torch.bfloat16), att=e(n, torch.bfloat16), y=e(n, torch.bfloat16),
+                  h=e(int(n * self.mlp_ratio), torch.bfloat16), mg=e(n, torch.bfloat16),
+                  feat=torch.empty(B, self.num_features, device=dev, dtype=torch.float32))
+        p["ws"] = {B: ws}                                # keep one batch size resident
+        return ws
+
+    def _check_input(self, x):
+        if self.training:
+            raise RuntimeError("mvuld_b200 SwinV2 implements the eval-mode forward: call model.eval()")
+        B, C, H, W = x.shape
+        assert H == self.patch_embed.img_size[0] and W == self.patch_embed.img_size[1], \
+            f"Input image size ({H}*{W}) doesn't match model ({self.patch_embed.img_size[0]}*{self.patch_embed.img_size[1]})."
+        assert C == 3
+        if not x.is_cuda:
+            raise RuntimeError("mvuld_b200 SwinV2 takes CUDA tensors (no CPU fallback)")
+
+    @torch.no_grad()
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        """:623-635 -> fp32 [B, num_features]."""
+        self._check_input(x)
+        if self._plan is None:
+            self.prepare()
+        p = self._plan
+        B = x.shape[0]
+        w = self._workspace(B)
+        x = x.to(torch.float32).contiguous()
+        E = self.embed_dim
+        Hp, Wp = self.patches_resolution
+        M = B * Hp * Wp
+        pe = p["pe"]
+        x32 = w["x32"][:M * E].view(M, E)
+        xb = w["xb"][:M * E].view(M, E)
+        _lib.call("mvuld_patch_embed", x, pe["w"], pe["b"], pe["g"], pe["beta"], x32, xb, B, x.shape[2], x.shape[3], E,
+                  float(pe["eps"]))
+        bi = 0
+        for li, layer in enumerate(self.layers):
+            for _ in layer.blocks:
+                blk = p["blocks"][bi]
+                bi += 1
+                H, W, C, nH, ws, shift = blk["H"], blk["W"], blk["C"], blk["nH"], blk["ws"], blk["shift"]
+                M = B * H * W
+                x32 = w["x32"][:M * C].view(M, C)
+                xb = w["xb"][:M * C].view(M, C)
+                q, k, v = w["q"][:M * C], w["k"][:M * C], w["v"][:M * C]
+                att = w["att"][:M * C].view(M, C)
+                y = w["y"][:M * C].view(M, C)
+                hid = w["h"][:M * blk["wfc1"].shape[0]].view(M, blk["wfc1"].shape[0])
+                _lib.call("mvuld_swin_qkv", xb, blk["wqkv"], blk["qb"], blk["vb"], blk["qscale"], q, k, v, B, H, W, C,
+                          nH, ws, shift)
+                _lib.call("mvuld_swin_window_attention", q, k, v, blk["tab_rev"], blk["tab_max"], att, B, H, W, C, nH,
+                          ws, shift)
+                _lib.gemm(att, blk["wproj"], bias=blk["bproj"], out_bf16=y)
+                _lib.call("mvuld_ln_rows", y, x32, blk["g1"], blk["b1"], x32, xb, M, C, float(blk["eps1"]), 1)
+                _lib.gemm(xb, blk["wfc1"], bias=blk["bfc1"], act=_lib.ACT_GELU, out_bf16=hid)
+                _lib.gemm(hid, blk["wfc2"], bias=blk["bfc2"], out_bf16=y)
+                _lib.call("mvuld_ln_rows", y, x32, blk["g2"], blk["b2"], x32, xb, M, C, float(blk["eps2"]), 1)
+            if layer.downsample is not None:
+                mg = p["merge"][li]
+                H, W, C = mg["H"], mg["W"], mg["C"]
+                M2 = B * (H // 2) * (W // 2)
+                xb = w["xb"][:B * H * W * C].view(B * H * W, C)
+                gathered = w["mg"][:M2 * 4 * C].view(M2, 4 * C)
+                _lib.call("mvuld_patch_merge_gather", xb, gathered, B, H, W, C)
+                y = w["y"][:M2 * 2 * C].view(M2, 2 * C)
+                _lib.gemm(gathered, mg["w"], out_bf16=y)
+                x32 = w["x32"][:M2 * 2 * C].view(M2, 2 * C)
+                xb = w["xb"][:M2 * 2 * C].view(M2, 2 * C)
+                _lib.call("mvuld_ln_rows", y, None, mg["g"], mg["b"], x32, xb, M2, 2 * C, float(mg["eps"]), 0)
+        last = p["blocks"][-1]
+        T, C = last["H"] * last["W"], last["C"]
+        x32 = w["x32"][:B * T * C]
+        nm = p["norm"]
+        _lib.call("mvuld_ln_meanpool", x32, nm["g"], nm["b"], w["feat"], B, T, C, float(nm["eps"]))
+        return w["feat"].clone()
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """:640-643 -> fp32 [B, num_classes]."""
+        f = self.forward_features(x)
+        if "head" not in self._plan:
+            return f
+        hd = self._plan["head"]
+        out = torch.empty(f.shape[0], self.num_classes, device=f.device, dtype=torch.float32)
+        _lib.call("mvuld_linear_small", f, hd["w"], hd["b"], out, None, f.shape[0], self.num_classes, f.shape[1])
+        return out

@@ -1,0 +1,370 @@
+"""GPU: kernel-level parity through the C ABI (probe layouts, GEMM epilogues, attention, row kernels, graph kernels)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from mvuld_b200 import _lib, synth      # noqa: E402
+from mvuld_b200 import graph as G       # noqa: E402
+from oracle import dgl_ops, swin as oswin, fusion as ofusion   # noqa: E402
+from tests import cases                 # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def gen(seed=0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+# --------------------------------------------------------------------------------------------------------
+# UMMA / TMA layout probes: every shared-memory layout the big kernels rely on, one tile each
+# --------------------------------------------------------------------------------------------------------
+def _probe(A, B, N, nk, a_step, b_step, a_sbo, a_layout, b_sbo, b_layout, a_swz, b_swz, b_mn, fmt):
+    out = torch.full((128, N), float("nan"), device=DEV, dtype=torch.float32)
+    _lib.call("mvuld_probe_umma", A, A.shape[1], A.shape[0], a_swz, B, B.shape[1], B.shape[0], b_swz, N, nk, a_step,
+              b_step, 16, a_sbo, a_layout, 16, b_sbo, b_layout, 0, b_mn, fmt, out)
+    torch.cuda.synchronize()
+    return out
+
+
+def test_probe_kmajor_sw128_bf16():
+    g = gen(1)
+    A = torch.randn(128, 64, generator=g).to(DEV, torch.bfloat16)
+    B = torch.randn(128, 64, generator=g).to(DEV, torch.bfloat16)
+    out = _probe(A, B, 128, 4, 32, 32, 1024, 2, 1024, 2, 128, 128, 0, 1)
+    assert rel_err(out, A.float() @ B.float().T) < 1e-5
+
+
+def test_probe_kmajor_sw64_fp16_n112():
+    g = gen(2)
+    A = torch.randn(128, 32, generator=g).to(DEV, torch.float16)
+    B = torch.randn(112, 32, generator=g).to(DEV, torch.float16)
+    out = _probe(A, B, 112, 2, 32, 32, 512, 4, 512, 4, 64, 64, 0, 0)
+    assert rel_err(out, A.float() @ B.float().T) < 1e-5
+
+
+def test_probe_mnmajor_b_sw64():
+    g = gen(3)
+    P = torch.randn(128, 64, generator=g).to(DEV, torch.bfloat16)       # A, K-major, K = 64 kv columns
+    V = torch.randn(64, 32, generator=g).to(DEV, torch.bfloat16)        # B, [kv, hd] row-major == MN-major
+    out = _probe(P, V, 32, 4, 32, 16 * 64, 1024, 2, 512, 4, 128, 64, 1, 1)
+    assert rel_err(out, P.float() @ V.float()) < 1e-5
+
+
+def test_probe_mnmajor_b_sw128():
+    g = gen(4)
+    P = torch.randn(128, 64, generator=g).to(DEV, torch.bfloat16)
+    V = torch.randn(64, 64, generator=g).to(DEV, torch.bfloat16)
+    out = _probe(P, V, 64, 4, 32, 16 * 128, 1024, 2, 1024, 2, 128, 128, 1, 1)
+    assert rel_err(out, P.float() @ V.float()) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 128), (1000, 600, 200), (3136, 512, 2048),
+                                   (77, 480, 512), (4, 512, 1024), (12544, 128, 512)])
+def test_gemm_plain(M, N, K):
+    g = gen(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.1).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    ob = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    of = torch.zeros(M, N, device=DEV, dtype=torch.float32)
+    _lib.gemm(A, W, bias=bias, out_bf16=ob, out_f32=of)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().T + bias
+    assert rel_err(of, ref) < 1e-5
+    assert rel_err(ob, ref) < 5e-3
+
+
+def test_gemm_epilogues():
+    g = gen(11)
+    M, N, K = 300, 256, 256
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.1).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    lin = A.float() @ W.float().T + bias
+    for act, fn in ((_lib.ACT_GELU, torch.nn.functional.gelu), (_lib.ACT_ELU, torch.nn.functional.elu)):
+        of = torch.zeros(M, N, device=DEV)
+        _lib.gemm(A, W, bias=bias, act=act, res=res, out_f32=of)
+        torch.cuda.synchronize()
+        assert rel_err(of, fn(lin) + res) < 1e-5
+    # residual aliasing the fp32 output (in-place x += ...), strided output (ldc > N)
+    buf32 = torch.randn(M, 512, generator=g).to(DEV)
+    bufb = torch.zeros(M, 512, device=DEV, dtype=torch.bfloat16)
+    expect = buf32.clone()
+    expect[:, :N] += lin
+    _lib.gemm(A, W, bias=bias, res=buf32, out_f32=buf32, out_bf16=bufb)
+    torch.cuda.synchronize()
+    assert rel_err(buf32, expect) < 1e-5
+    assert rel_err(bufb[:, :N], expect[:, :N]) < 5e-3 and float(bufb[:, N:].abs().sum()) == 0.0
+
+
+# --------------------------------------------------------------------------------------------------------
+# Swin qkv + window attention against the oracle's window_attention
+# --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Hres,ws,shift,nH,B", [(28, 7, 0, 4, 2), (28, 7, 3, 4, 2), (28, 14, 7, 4, 1), (14, 14, 0, 8, 2),
+                                                (28, 28, 0, 4, 2), (56, 28, 14, 4, 1)])
+def test_swin_attention_block(Hres, ws, shift, nH, B):
+    g = gen(Hres * 100 + ws + shift)
+    C = nH * 32
+    H = W = Hres
+    M = B * H * W
+    x = torch.randn(M, C, generator=g)
+    sd = {"qkv.weight": torch.randn(3 * C, C, generator=g) * 0.08, "q_bias": torch.randn(C, generator=g) * 0.1,
+          "v_bias": torch.randn(C, generator=g) * 0.1,
+          "logit_scale": torch.log(10 * torch.ones(nH, 1, 1)) + torch.randn(nH, 1, 1, generator=g) * 0.3,
+          "cpb_mlp.0.weight": torch.randn(512, 2, generator=g) * 0.5, "cpb_mlp.0.bias": torch.randn(512, generator=g) * 0.5,
+          "cpb_mlp.2.weight": torch.randn(nH, 512, generator=g) * 0.1,
+          "proj.weight": torch.eye(C), "proj.bias": torch.zeros(C)}
+    pws = 6
+    # oracle on the bf16-rounded input / weight so only the kernel arithmetic differs
+    xb = x.to(torch.bfloat16)
+    sd_r = dict(sd)
+    sd_r["qkv.weight"] = sd["qkv.weight"].to(torch.bfloat16).float()
+    xi = xb.float().view(B, H, W, C)
+    if shift:
+        xi = torch.roll(xi, (-shift, -shift), (1, 2))
+        mask = oswin.shifted_window_mask(H, W, ws, shift)
+    else:
+        mask = None
+    ref_w = oswin.window_attention(sd_r, "", oswin._partition(xi, ws), ws, nH, pws, mask)
+    ref = oswin._reverse(ref_w, ws, H, W)
+    if shift:
+        ref = torch.roll(ref, (shift, shift), (1, 2))
+    ref = ref.reshape(M, C)
+
+    d = lambda t, dt=torch.float32: t.to(DEV, dt).contiguous()
+    side = 2 * ws - 1
+    tab_rev = torch.empty(nH, side * side, device=DEV)
+    tab_ref = torch.empty(nH, side * side, device=DEV)
+    tab_max = torch.empty(nH, device=DEV)
+    _lib.call("mvuld_cpb_table", d(sd["cpb_mlp.0.weight"]), d(sd["cpb_mlp.0.bias"]), d(sd["cpb_mlp.2.weight"]), nH, ws,
+              pws, tab_rev, tab_ref, tab_max)
+    torch.cuda.synchronize()
+    tab_oracle = oswin.cpb_bias_table(sd, "", ws, pws).T.contiguous()       # [nH, T]
+    assert rel_err(tab_ref, tab_oracle) < 1e-5
+    qscale = d(torch.clamp(sd["logit_scale"].view(-1), max=math.log(100.0)).exp() * 1.4426950408889634)
+    q = torch.zeros(M * C, device=DEV, dtype=torch.float16)
+    k = torch.zeros(M * C, device=DEV, dtype=torch.float16)
+    v = torch.zeros(M * C, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_swin_qkv", d(xb, torch.bfloat16), d(sd["qkv.weight"], torch.bfloat16), d(sd["q_bias"]),
+              d(sd["v_bias"]), qscale, q, k, v, B, H, W, C, nH, ws, shift)
+    torch.cuda.synchronize()
+    # check the scattered, normalised q against the oracle's math
+    qkv = torch.nn.functional.linear(oswin._partition(xi, ws), sd_r["qkv.weight"],
+                                     torch.cat([sd["q_bias"], torch.zeros(C), sd["v_bias"]]))
+    B_ = qkv.shape[0]
+    qkv = qkv.reshape(B_, ws * ws, 3, nH, 32).permute(2, 0, 3, 1, 4)
+    q_ref = torch.nn.functional.normalize(qkv[0], dim=-1) * qscale.cpu().view(1, nH, 1, 1)
+    assert rel_err(q.view(B_, nH, ws * ws, 32), q_ref) < 2e-3
+    assert rel_err(k.view(B_, nH, ws * ws, 32), torch.nn.functional.normalize(qkv[1], dim=-1)) < 2e-3
+    assert rel_err(v.view(B_, nH, ws * ws, 32), qkv[2]) < 5e-3
+    _lib.call("mvuld_swin_window_attention", q, k, v, tab_rev, tab_max, out, B, H, W, C, nH, ws, shift)
+    torch.cuda.synchronize()
+    err = rel_err(out, ref)
+    assert err < 1.5e-2, err
+
+
+def test_seq_attention():
+    g = gen(5)
+    B, L, nH, hd = 3, 512, 2, 64
+    q = torch.randn(B, nH, L, hd, generator=g)
+    k = torch.randn(B, nH, L, hd, generator=g)
+    v = torch.randn(B, nH, L, hd, generator=g)
+    lens = torch.tensor([512, 37, 300], dtype=torch.int32)
+    qs = (q * (1.4426950408889634 / 8.0)).to(torch.bfloat16)
+    kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
+    out = torch.zeros(B * L, nH * hd, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_seq_attention", qs.to(DEV).contiguous(), kb.to(DEV).contiguous(), vb.to(DEV).contiguous(),
+              lens.to(DEV), out, B, L, nH, hd)
+    torch.cuda.synchronize()
+    out = out.float().cpu().view(B, L, nH, hd)
+    for b in range(B):
+        n = int(lens[b])
+        s = (qs[b].float() / 1.4426950408889634) @ kb[b].float().transpose(-1, -2)     # already / sqrt(hd)
+        p = s[:, :, :n].softmax(-1)
+        ref = (p @ vb[b, :, :n].float()).permute(1, 0, 2)                               # [L, nH, hd]
+        assert rel_err(out[b, :n], ref[:n]) < 1e-2, (b, rel_err(out[b, :n], ref[:n]))
+        assert torch.isfinite(out[b]).all()
+
+
+# --------------------------------------------------------------------------------------------------------
+# row kernels
+# --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [128, 256, 512, 768, 1024])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_ln_rows(C, mode):
+    g = gen(C + mode)
+    M = 333
+    y = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    sc = torch.randn(M, C, generator=g)
+    gam, bet = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    x32 = torch.zeros(M, C, device=DEV)
+    xb = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_ln_rows", y.to(DEV), sc.to(DEV), gam.to(DEV), bet.to(DEV), x32, xb, M, C, 1e-5, mode)
+    torch.cuda.synchronize()
+    ln = lambda t: torch.nn.functional.layer_norm(t, (C,), gam, bet, 1e-5)
+    ref = ln(y.float()) if mode == 0 else (sc + ln(y.float()) if mode == 1 else ln(y.float() + sc))
+    assert torch.allclose(x32.cpu(), ref, rtol=1e-4, atol=1e-4)
+    assert rel_err(xb, ref) < 5e-3
+
+
+def test_patch_embed_merge_pool():
+    g = gen(9)
+    B, S, E = 2, 56, 128
+    img = torch.randn(B, 3, S, S, generator=g)
+    w = torch.randn(E, 3, 4, 4, generator=g) * 0.2
+    b, gam, bet = torch.randn(E, generator=g), torch.randn(E, generator=g), torch.randn(E, generator=g)
+    M = B * (S // 4) ** 2
+    x32 = torch.zeros(M, E, device=DEV)
+    xb = torch.zeros(M, E, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_patch_embed", img.to(DEV), w.view(E, -1).contiguous().to(DEV), b.to(DEV), gam.to(DEV), bet.to(DEV),
+              x32, xb, B, S, S, E, 1e-5)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(img, w, b, stride=4).flatten(2).transpose(1, 2)
+    ref = torch.nn.functional.layer_norm(ref, (E,), gam, bet, 1e-5).reshape(M, E)
+    assert torch.allclose(x32.cpu(), ref, rtol=1e-4, atol=1e-4)
+    # patch-merge gather (bit-exact copy)
+    H = W = S // 4
+    out = torch.zeros(B * (H // 2) * (W // 2), 4 * E, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_patch_merge_gather", xb, out, B, H, W, E)
+    torch.cuda.synchronize()
+    xv = xb.view(B, H, W, E)
+    refm = torch.cat([xv[:, 0::2, 0::2], xv[:, 1::2, 0::2], xv[:, 0::2, 1::2], xv[:, 1::2, 1::2]], -1).reshape(-1, 4 * E)
+    assert torch.equal(out, refm)
+    # LN + mean pool
+    feat = torch.zeros(B, E, device=DEV)
+    _lib.call("mvuld_ln_meanpool", x32, gam.to(DEV), bet.to(DEV), feat, B, H * W, E, 1e-5)
+    torch.cuda.synchronize()
+    refp = torch.nn.functional.layer_norm(x32.cpu().view(B, H * W, E), (E,), gam, bet, 1e-5).mean(1)
+    assert torch.allclose(feat.cpu(), refp, rtol=1e-4, atol=1e-5)
+
+
+# --------------------------------------------------------------------------------------------------------
+# graph kernels: integer artefacts bit-exact, float reductions to fp32 tolerance
+# --------------------------------------------------------------------------------------------------------
+def test_csr_bit_exact_and_edge_cases():
+    g = synth.cpg_batch(8, seed=3)
+    hb = cases.to_host_batch(g)
+    gd = g.to(DEV)
+    indptr, idx_src, eids = gd.in_csr()
+    torch.cuda.synchronize()
+    r_indptr, r_idx, r_eids = dgl_ops.in_csr(hb.src, hb.dst, hb.num_nodes)
+    assert np.array_equal(indptr.cpu().numpy().astype(np.int64), r_indptr)
+    assert np.array_equal(idx_src.cpu().numpy().astype(np.int64), r_idx)
+    assert np.array_equal(eids.cpu().numpy().astype(np.int64), r_eids)
+    gd.check_status()
+    # multi-edges, pre-existing self loops, an isolated node, and an out-of-range endpoint
+    src = torch.tensor([0, 0, 0, 2, 2, 1], dtype=torch.int64)
+    dst = torch.tensor([1, 1, 0, 2, 1, 1], dtype=torch.int64)
+    ip, ix, ei, st = _lib.csr_from_coo(src.to(DEV), dst.to(DEV), 4)
+    r = dgl_ops.in_csr(src.numpy(), dst.numpy(), 4)
+    assert ip.cpu().tolist() == r[0].tolist() and ei.cpu().tolist() == r[2].tolist() and int(st.item()) == 0
+    ip, ix, ei, st = _lib.csr_from_coo(src.to(DEV), (dst + 3).to(DEV), 4)
+    assert int(st.item()) == 1
+    # empty edge list
+    ip, ix, ei, st = _lib.csr_from_coo(src[:0].to(DEV), dst[:0].to(DEV), 3)
+    assert ip.cpu().tolist() == [0, 0, 0, 0]
+
+
+def test_segment_sum_and_pad_map():
+    g0 = gen(21)
+    bnn = np.array([5, 1, 0, 230, 100, 99, 101, 2000], dtype=np.int64)
+    N, D = int(bnn.sum()), 200
+    feat = torch.randn(N, D, generator=g0)
+    off = torch.from_numpy(dgl_ops.node_offsets(bnn)).to(DEV)
+    out = torch.zeros(len(bnn), D, device=DEV)
+    _lib.call("mvuld_segment_sum", feat.to(DEV), off, out, len(bnn), D)
+    torch.cuda.synchronize()
+    ref = dgl_ops.segment_sum(feat.double(), bnn).float()
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-4)
+    # unbatch + pad/truncate gather map: bit-exact vs the oracle (scale 1, shift 0 -> plain copy)
+    F = 64
+    fb = torch.randn(N, F, generator=g0).to(torch.bfloat16)
+    outp = torch.zeros(len(bnn) * 100, F, device=DEV, dtype=torch.bfloat16)
+    gmap = torch.zeros(len(bnn), 100, device=DEV, dtype=torch.int64)
+    _lib.call("mvuld_unbatch_pad_bn", fb.to(DEV), off, torch.ones(100, device=DEV), torch.zeros(100, device=DEV), outp,
+              gmap, len(bnn), 100, F)
+    torch.cuda.synchronize()
+    assert np.array_equal(gmap.cpu().numpy(), dgl_ops.pad_truncate_map(bnn, 100))
+    assert torch.equal(outp.cpu().view(len(bnn), 100, F), dgl_ops.unbatch_pad(fb, bnn, 100))
+
+
+def test_gat_and_ggnn_steps():
+    g = synth.cpg_batch(5, seed=11)
+    hb = cases.to_host_batch(g)
+    gd = g.to(DEV)
+    N = g.num_nodes()
+    gg = gen(31)
+    H, F = 4, 512
+    z = (torch.randn(N, H * F, generator=gg) * 0.5).to(torch.bfloat16)
+    al, ar = torch.randn(H * F, generator=gg) * 0.1, torch.randn(H * F, generator=gg) * 0.1
+    bias = torch.randn(H * F, generator=gg) * 0.1
+    indptr, idx_src, _ = gd.in_csr()
+    el, er = torch.zeros(N, H, device=DEV), torch.zeros(N, H, device=DEV)
+    _lib.call("mvuld_gat_scores", z.to(DEV), al.to(DEV), ar.to(DEV), el, er, N, H, F)
+    out = torch.zeros(N, H * F, device=DEV, dtype=torch.bfloat16)
+    flag = torch.zeros(1, device=DEV, dtype=torch.int32)
+    _lib.call("mvuld_gat_aggregate", z.to(DEV), el, er, indptr, idx_src, bias.to(DEV), out, N, H, F, 0.2, flag)
+    torch.cuda.synchronize()
+    # oracle GATConv with fc = identity on the bf16-rounded z
+    sd = {"fc.weight": torch.eye(H * F), "attn_l": al.view(1, H, F), "attn_r": ar.view(1, H, F), "bias": bias}
+    ref = dgl_ops.gat_conv(sd, "", hb.src, hb.dst, z.float(), H, F).reshape(N, H * F)
+    assert rel_err(out, ref) < 5e-3 and int(flag.item()) == 0
+    # GGNN typed gather-sum
+    g2 = synth.ggnn_batch(7, seed=5, n_etypes=4)
+    h2 = cases.to_host_batch(g2)
+    g2d = g2.to(DEV)
+    N2, T, D = g2.num_nodes(), 4, 200
+    msgs = (torch.randn(N2, T, D, generator=gg) * 0.5).to(torch.bfloat16)
+    indptr, idx_src, eids = g2d.in_csr()
+    ets = torch.zeros(g2.num_edges(), device=DEV, dtype=torch.uint8)
+    st = torch.zeros(1, device=DEV, dtype=torch.int32)
+    _lib.call("mvuld_gather_etype", g2d.edata["_ETYPE"], eids, g2.num_edges(), T, ets, st)
+    a = torch.zeros(N2, D, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_ggnn_gather_sum", msgs.to(DEV), indptr, idx_src, ets, a, N2, T, D)
+    torch.cuda.synchronize()
+    ref = torch.zeros(N2, D).index_add_(0, torch.from_numpy(h2.dst),
+                                        msgs.float()[torch.from_numpy(h2.src), h2.edata["_ETYPE"]])
+    assert rel_err(a, ref) < 5e-3 and int(st.item()) == 0
+
+
+def test_rs_gcn_affinity_and_head(golden):
+    m = cases.make_rs_gcn()
+    v = cases.rs_gcn_input()                                  # [2, 512, 100]
+    B, C, n = v.shape
+    sd = m.state_dict()
+    tok = v.permute(0, 2, 1).reshape(B * n, C)
+    wcat = torch.cat([sd["theta.weight"][:, :, 0], sd["phi.weight"][:, :, 0], sd["g.weight"][:, :, 0]], 0)
+    bcat = torch.cat([sd["theta.bias"], sd["phi.bias"], sd["g.bias"]], 0)
+    tpg = torch.zeros(B * n, 3 * C, device=DEV, dtype=torch.bfloat16)
+    _lib.gemm(tok.to(DEV, torch.bfloat16), wcat.to(DEV, torch.bfloat16), bias=bcat.to(DEV), out_bf16=tpg)
+    y = torch.zeros(B * n, C, device=DEV, dtype=torch.bfloat16)
+    R = torch.zeros(B, n, n, device=DEV)
+    _lib.call("mvuld_rs_gcn_affinity", tpg, y, R, B, n, C)
+    torch.cuda.synchronize()
+    assert rel_err(R, golden["rs_gcn"]["R"]) < 1e-2
+    scale = sd["W.1.weight"] / torch.sqrt(sd["W.1.running_var"] + 1e-5)
+    shift = sd["W.1.bias"] - sd["W.1.running_mean"] * scale
+    ww = sd["W.0.weight"][:, :, 0] * scale[:, None]
+    wb = sd["W.0.bias"] * scale + shift
+    z32 = tok.to(DEV).contiguous()
+    zb = torch.zeros(B * n, C, device=DEV, dtype=torch.bfloat16)
+    _lib.gemm(y, ww.to(DEV, torch.bfloat16), bias=wb.to(DEV), res=z32, out_f32=z32, out_bf16=zb)
+    torch.cuda.synchronize()
+    ref = golden["rs_gcn"]["v_star"].permute(0, 2, 1).reshape(B * n, C)
+    assert rel_err(z32, ref) < 1e-2

@@ -1,0 +1,161 @@
+"""GPU: model-level parity of the B200 path against the CPU oracle and the reference-generated golden vectors.
+
+Tolerances are north_star's: integer artefacts bit-exact; bf16 logits within 1e-2 relative of the fp32 reference;
+identical argmax.  Intermediate feature vectors are compared by relative L2 error.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import mvuld_b200 as mv                     # noqa: E402
+from mvuld_b200 import synth                # noqa: E402
+from oracle import fusion as ofusion, roberta as oroberta, swin as oswin   # noqa: E402
+from tests import cases                     # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def logits_close(a, b, tol=1e-2):
+    a, b = a.float().cpu(), b.float().cpu()
+    scale = b.abs().max().clamp(min=1e-6)
+    return float((a - b).abs().max() / scale) < tol
+
+
+@pytest.mark.parametrize("name", ["small_ws7", "mid_ws14", "full"])
+def test_swin_matches_reference_golden(golden, name):
+    model = cases.make_swin(name)
+    x = synth.images(cases.SWIN_BATCH[name], cases.SWIN_CASES[name]["img_size"], seed=cases.SEED)
+    model = model.to(DEV)
+    feats = model.forward_features(x.to(DEV))
+    logits = model(x.to(DEV))
+    torch.cuda.synchronize()
+    ref = golden["swin"][name]
+    e = rel_err(feats, ref["features"])
+    assert e < 2e-2, e
+    assert logits_close(logits, ref["logits"], 2e-2), (logits.cpu(), ref["logits"])
+    assert torch.equal(logits.cpu().argmax(1), ref["logits"].argmax(1))
+
+
+def test_swin_block_taps_against_oracle():
+    """Per-block relative error against the fp32 oracle: localises drift instead of only testing the end."""
+    name = "small_ws7"
+    model = cases.make_swin(name)
+    x = synth.images(cases.SWIN_BATCH[name], cases.SWIN_CASES[name]["img_size"], seed=cases.SEED)
+    taps = {}
+    ref = oswin.forward_features(model.state_dict(), cases.swin_geometry(name), x, taps=taps)
+    feats = model.to(DEV).forward_features(x.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(feats, ref) < 2e-2
+
+
+def test_swin_boundary_errors():
+    cfg = mv.default_config()
+    m = mv.build_model(cfg)
+    assert m.output_num() == 1024 and abs(m.flops() / 1e9 - 79.57) < 0.01
+    m = cases.make_swin("small_ws7").to(DEV)
+    with pytest.raises(AssertionError):
+        m.forward_features(torch.zeros(1, 3, 64, 64, device=DEV))
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.forward_features(torch.zeros(1, 3, 112, 112, device=DEV))
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_unixcoder_matches_oracle(golden, full):
+    m = cases.make_roberta(full=full)
+    cfg = m.config
+    B = cases.ROBERTA_BATCH
+    ids = synth.token_ids(B, cases.ROBERTA_L, cfg.vocab_size, seed=cases.SEED)
+    tok_ref, sent_ref = oroberta.encode(m.state_dict(), cases.roberta_geometry(cfg), ids, prefix="encoder.")
+    md = m.to(DEV)
+    vec, _ = md.get_repr(ids.to(DEV))
+    tok, _ = md.get_xcode_vec(ids.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(vec, sent_ref) < 1.5e-2, rel_err(vec, sent_ref)
+    if not full:
+        assert rel_err(vec, golden["roberta"]["sent"]) < 1.5e-2
+    mask = ids.ne(cfg.pad_token_id).unsqueeze(-1).float()
+    assert rel_err(tok.cpu() * mask, tok_ref * mask) < 2e-2
+    assert torch.isfinite(tok).all()
+
+
+def test_fusion_matches_oracle(golden):
+    model = cases.make_fusion()
+    g = synth.cpg_batch(cases.FUSION_BATCH, seed=cases.SEED)
+    ge = torch.Generator().manual_seed(cases.SEED)
+    img = torch.randn(cases.FUSION_BATCH, 1024, generator=ge)
+    txt = torch.randn(cases.FUSION_BATCH, 768, generator=ge)
+    ref = golden["graph"]["fusion_logits"]
+    logits = model.to(DEV)(g.to(DEV), img.to(DEV), txt.to(DEV))
+    torch.cuda.synchronize()
+    assert logits_close(logits, ref, 2e-2), (logits.cpu(), ref)
+    assert torch.equal(logits.cpu().argmax(1), ref.argmax(1))
+
+
+def test_fusion_rejects_zero_in_degree():
+    model = cases.make_fusion().to(DEV)
+    g = mv.graph.graph((torch.tensor([0, 1]), torch.tensor([1, 2])), num_nodes=3)      # node 0 has no in-edge
+    g.ndata["_UNIX_NODE_EMB"] = torch.randn(3, 768)
+    g.ndata["pos_emb"] = torch.zeros(3, 4)
+    with pytest.raises(RuntimeError):
+        model(g.to(DEV), torch.randn(1, 1024, device=DEV), torch.randn(1, 768, device=DEV))
+
+
+def test_ggnn_matches_oracle(golden):
+    gm = cases.make_ggnn()
+    g = synth.ggnn_batch(cases.GGNN_BATCH, seed=cases.SEED, n_etypes=cases.GGNN_T)
+    hb = cases.to_host_batch(g)
+    prob_r, logit_r, sum_r, h_r = ofusion.ggnn_sum_forward(gm.state_dict(), hb, cases.GGNN_D, cases.GGNN_STEPS,
+                                                           cases.GGNN_T)
+    assert torch.allclose(sum_r, golden["graph"]["ggnn_sum"], rtol=1e-4, atol=1e-3)
+    gd = g.to(DEV)
+    md = gm.to(DEV)
+    h = md.node_states(gd)
+    prob, logit = md(gd)
+    torch.cuda.synchronize()
+    assert rel_err(h, h_r) < 2e-2, rel_err(h, h_r)
+    assert rel_err(md._last_sum, sum_r) < 2e-2
+    assert logits_close(logit, logit_r, 2e-2)
+    # edge types outside [0, n_etypes) are rejected like DGL's assert
+    gd.edata["_ETYPE"] = gd.edata["_ETYPE"] + 10
+    with pytest.raises(AssertionError):
+        md.node_states(gd)
+
+
+def test_composed_forward_matches_oracle():
+    """Full MVulD forward at small Swin / small RoBERTa geometry: image + tokens + CPG -> logits."""
+    torch.manual_seed(cases.SEED)
+    cfg = mv.default_config()
+    cfg.defrost()
+    cfg.DATA.IMG_SIZE = 224
+    cfg.MODEL.SWINV2.DEPTHS = [2, 2, 2, 2]
+    cfg.MODEL.SWINV2.NUM_HEADS = [4, 8, 16, 32]
+    cfg.MODEL.SWINV2.WINDOW_SIZE = 7
+    cfg.MODEL.SWINV2.PRETRAINED_WINDOW_SIZES = [6, 6, 6, 6]
+    cfg.freeze()
+    rcfg = mv.roberta_base_config(vocab_size=1000, num_hidden_layers=2)
+    model = mv.MVulD(cfg, rcfg).eval()
+    synth.randomize_for_parity(model, seed=cases.SEED)
+    B = 3
+    img = synth.images(B, 224, seed=1)
+    ids = synth.token_ids(B, 512, 1000, seed=1)
+    g = synth.cpg_batch(B, seed=1)
+    # oracle, piece by piece
+    from oracle.swin import SwinGeometry
+    geo = SwinGeometry(img_size=224, embed_dim=128, depths=(2, 2, 2, 2), num_heads=(4, 8, 16, 32), window_size=7,
+                       pretrained_window_sizes=(6, 6, 6, 6))
+    sd_swin = model.swin.state_dict()
+    f_img = oswin.forward_features(sd_swin, geo, img)
+    f_txt = oroberta.get_repr(model.unix.state_dict(), cases.roberta_geometry(rcfg), ids)
+    ref = ofusion.fusion_forward(model.fusion.state_dict(), cases.to_host_batch(g), f_img, f_txt)
+    out = model.to(DEV)(img.to(DEV), ids.to(DEV), g.to(DEV))
+    torch.cuda.synchronize()
+    assert logits_close(out, ref, 2e-2), (out.cpu(), ref)
+    assert torch.equal(out.cpu().argmax(1), ref.argmax(1))

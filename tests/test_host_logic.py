@@ -1,0 +1,172 @@
+"""CPU: host-side mirror of the reference interface, graph container semantics, C-ABI surface, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import mvuld_b200 as mv
+from mvuld_b200 import _lib, synth
+from mvuld_b200 import graph as G
+from oracle import dgl_ops
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_mirrors_reference_defaults_and_yaml():
+    cfg = mv.default_config()
+    assert cfg.MODEL.TYPE == "swinv2" and cfg.DATA.IMG_SIZE == 448
+    assert cfg.MODEL.SWINV2.DEPTHS == [2, 2, 18, 2] and cfg.MODEL.SWINV2.NUM_HEADS == [4, 8, 16, 32]
+    assert cfg.MODEL.SWINV2.WINDOW_SIZE == 28 and cfg.MODEL.SWINV2.PRETRAINED_WINDOW_SIZES == [12, 12, 12, 6]
+    assert cfg.MODEL.DROP_PATH_RATE == 0.2 and cfg.MODEL.NUM_CLASSES == 2
+    assert cfg.TRAIN.BASE_LR == 5e-5 and cfg.TRAIN.WEIGHT_DECAY == 0.005 and cfg.TRAIN.CLIP_GRAD == 5.0
+    assert cfg.OUTPUT.endswith(os.path.join(cfg.MODEL.NAME, "default"))
+    with pytest.raises(AttributeError):
+        cfg.MODEL.NUM_CLASSES = 3                       # frozen, like yacs
+    cfg.defrost()
+    cfg.MODEL.NUM_CLASSES = 3
+    cfg.freeze()
+    assert cfg.clone().MODEL.NUM_CLASSES == 3 and "NUM_CLASSES: 3" in cfg.dump()
+
+    class Args:
+        cfg = mv.config.DEFAULT_YAML
+        opts = ["MODEL.SWINV2.WINDOW_SIZE", "14", "TRAIN.BASE_LR", "1e-4"]
+        batch_size = 4
+        local_rank = 1
+        eval = True
+    c2 = mv.get_config(Args())
+    assert c2.MODEL.SWINV2.WINDOW_SIZE == 14 and c2.TRAIN.BASE_LR == 1e-4 and c2.DATA.BATCH_SIZE == 4
+    assert c2.LOCAL_RANK == 1 and c2.EVAL_MODE is True
+    Args.opts = ["MODEL.NOPE", "1"]
+    with pytest.raises(KeyError):
+        mv.get_config(Args())
+
+
+def test_build_model_boundary():
+    cfg = mv.default_config()
+    m = mv.build_model(cfg)
+    assert isinstance(m, mv.SwinTransformerV2)
+    assert sum(p.numel() for p in m.parameters()) == 86895866
+    assert m.no_weight_decay() == {"absolute_pos_embed"}
+    assert m.no_weight_decay_keywords() == {"cpb_mlp", "logit_scale", "relative_position_bias_table"}
+    cfg.defrost()
+    cfg.MODEL.TYPE = "resnet"
+    with pytest.raises(NotImplementedError, match="Unkown model"):
+        mv.build_model(cfg)
+    keys = set(m.state_dict().keys())
+    for k in ("patch_embed.proj.weight", "layers.0.blocks.1.attn_mask", "layers.0.blocks.0.attn.relative_position_index",
+              "layers.2.blocks.17.attn.cpb_mlp.2.weight", "layers.1.downsample.reduction.weight", "norm.weight",
+              "head.bias", "layers.3.blocks.0.attn.logit_scale", "layers.0.blocks.0.attn.q_bias"):
+        assert k in keys, k
+    assert "layers.2.blocks.1.attn_mask" not in keys                     # res <= window: no shift, no mask
+    # reference init: res-post-norm LayerNorms are zero (swin_transformer_v2.py:447-452)
+    assert float(m.layers[0].blocks[0].norm1.weight.abs().sum()) == 0.0
+
+
+def test_swin_buffers_match_reference_golden(golden):
+    g = golden["swin"]
+    m = cases.make_swin("small_ws7")
+    assert torch.equal(m.layers[0].blocks[0].attn.relative_position_index, g["rpi7"])
+    assert torch.equal(m.layers[0].blocks[1].attn_mask, g["mask28_ws7"])
+    from mvuld_b200.swin_transformer_v2 import _relative_coords_table, _relative_position_index
+    assert torch.allclose(_relative_coords_table(28, 12), g["coords28"], atol=1e-6)
+    assert int(_relative_position_index(28).sum()) == g["rpi28_sum"]
+
+
+def test_model_sizes_and_state_dict_keys():
+    f = mv.Multi_DefectModel_new_GCN(mv.default_config())
+    assert sum(p.numel() for p in f.parameters()) == 19178002
+    keys = set(f.state_dict().keys())
+    for k in ("gat.fc.weight", "gat.attn_l", "gat2.bias", "hidden.7.weight", "Rs_GCN_8.W.1.running_var",
+              "Rs_GCN_1.theta.weight", "bn_gat.running_mean", "fc_bbox.weight", "final_fc_bn.weight", "hln.weight",
+              "fconly.bias", "ln_text.weight"):
+        assert k in keys, k
+    assert f.gat.attn_l.shape == (1, 4, 512) and f.Rs_GCN_1.g.weight.shape == (512, 512, 1)
+    assert float(f.Rs_GCN_3.W[1].weight.abs().sum()) == 0.0               # Rs_GCN.py:33-34 zero init
+    u = mv.build_MyUniXcoder()
+    assert sum(p.numel() for p in u.encoder.parameters()) == 125929728
+    assert "encoder.encoder.layer.11.attention.self.query.weight" in u.state_dict()
+    gg = mv.GGNNSum(132, 200, max_edge_types=3, num_steps=8)
+    assert set(gg.state_dict().keys()) >= {"ggnn.linears.2.weight", "ggnn.gru.weight_ih", "ggnn.gru.bias_hh",
+                                           "classifier.weight"}
+
+
+def test_graph_container_follows_dgl_semantics():
+    g = G.graph((torch.tensor([0, 1, 1, 2]), torch.tensor([1, 2, 2, 2])))
+    g.edata["_ETYPE"] = torch.tensor([3, 1, 1, 0])
+    g.ndata["x"] = torch.arange(3.0).view(3, 1)
+    g2 = G.add_self_loop(g)
+    assert g2.edges()[0].tolist() == [0, 1, 1, 2, 0, 1, 2] and g2.edata["_ETYPE"].tolist() == [3, 1, 1, 0, 0, 0, 0]
+    h = G.add_self_loop(G.graph((torch.tensor([0]), torch.tensor([1]))))
+    h.edata["_ETYPE"] = torch.tensor([2, 0, 0])
+    h.ndata["x"] = torch.zeros(2, 1)
+    b = G.batch([g2, h])
+    assert b.num_nodes() == 5 and b.batch_size == 2 and b.batch_num_nodes().tolist() == [3, 2]
+    assert b.edges()[0].tolist()[7:] == [3, 3, 4] and b.edges()[1].tolist()[7:] == [4, 3, 4]
+    # identical to the oracle's restatement on a synthetic batch
+    gb = synth.cpg_batch(5, seed=4)
+    hb = cases.to_host_batch(gb)
+    off = dgl_ops.node_offsets(hb.batch_num_nodes)
+    assert off[-1] == gb.num_nodes() and int(gb.batch_num_edges().sum()) == gb.num_edges()
+    # every node has an in-edge (self loop) and self loops come last in each graph's edge list
+    src, dst = gb.edges()
+    assert set(dst.tolist()) == set(range(gb.num_nodes()))
+    n0, e0 = int(hb.batch_num_nodes[0]), int(hb.batch_num_edges[0])
+    assert src[e0 - n0:e0].tolist() == list(range(n0)) and gb.edata["_ETYPE"][e0 - n0:e0].sum() == 0
+    assert set(gb.edata["_ETYPE"].tolist()) == {0, 1, 3}
+
+
+def test_synthetic_inputs_are_deterministic_and_shaped():
+    a, b = synth.images(2, 64, seed=5), synth.images(2, 64, seed=5)
+    assert torch.equal(a, b) and a.shape == (2, 3, 64, 64)
+    ids = synth.token_ids(4, 512, seed=5)
+    assert ids.shape == (4, 512) and (ids[:, 0] == 0).all() and (ids[:, 1] == 6).all()
+    lens = ids.ne(1).sum(1)
+    for r in range(4):
+        assert (ids[r, lens[r]:] == 1).all() and ids[r, lens[r] - 1] == 2      # suffix padding, closing [SEP]
+    g = synth.ggnn_batch(16, seed=5)
+    assert g.ndata["_WORD2VEC"].shape[1] == 132 and int(g.edata["_ETYPE"].max()) <= 3
+    assert g.num_edges() == 5 * g.num_nodes()
+    hb = cases.to_host_batch(g)
+    off = dgl_ops.node_offsets(hb.batch_num_nodes)
+    gid_src = np.searchsorted(off, hb.src, side="right") - 1
+    gid_dst = np.searchsorted(off, hb.dst, side="right") - 1
+    assert np.array_equal(gid_src, gid_dst)                                  # no cross-graph edges
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    if not os.path.exists(_lib.LIB_PATH):
+        ge.build()
+    header = open(os.path.join(ROOT, "include", "mvuld_b200.h")).read()
+    declared = set(re.findall(r"\b(mvuld_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mvuld_b200.h but not exported"
+    assert declared - {"mvuld_last_error"} == set(_lib.SIGNATURES.keys())
+    lib.mvuld_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.mvuld_last_error(), bytes)
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if sass:                                                                 # cuobjdump present: Blackwell-native code
+        assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+
+
+def test_product_path_fails_loudly_without_gpu():
+    m = cases.make_swin("small_ws7")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            m.forward_features(torch.zeros(1, 3, 112, 112))
+        f = cases.make_fusion()
+        g = synth.cpg_batch(1, seed=1)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            f(g, torch.zeros(1, 1024), torch.zeros(1, 768))
+    for mod in ("mvuld_b200/_lib.py", "mvuld_b200/swin_transformer_v2.py", "mvuld_b200/graph_model.py",
+                "mvuld_b200/unixcoder.py", "mvuld_b200/mvuld.py", "mvuld_b200/graph.py", "mvuld_b200/synth.py"):
+        src = open(os.path.join(ROOT, mod)).read()
+        assert "import oracle" not in src and "from oracle" not in src, f"{mod} must not use the oracle"

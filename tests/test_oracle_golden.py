@@ -1,0 +1,120 @@
+"""CPU: the oracle restatements against golden vectors produced by the reference itself (tools/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dgl_ops, fusion, roberta, swin
+from mvuld_b200 import synth
+from tests import cases
+
+
+def sha(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["small_ws7", "mid_ws14"])
+def test_swin_oracle_matches_reference(golden, name):
+    model = cases.make_swin(name)
+    x = synth.images(cases.SWIN_BATCH[name], cases.SWIN_CASES[name]["img_size"], seed=cases.SEED)
+    geo = cases.swin_geometry(name)
+    feats = swin.forward_features(model.state_dict(), geo, x)
+    ref = golden["swin"][name]["features"]
+    assert torch.allclose(feats, ref, rtol=1e-4, atol=2e-5), float((feats - ref).abs().max())
+    logits = swin.forward(model.state_dict(), geo, x)
+    assert torch.allclose(logits, golden["swin"][name]["logits"], rtol=1e-4, atol=2e-5)
+
+
+def test_swin_integer_artefacts_match_reference(golden):
+    g = golden["swin"]
+    rpi = swin.relative_position_index(28)
+    assert rpi.dtype == torch.int64 and sha(rpi) == g["rpi28_sha"] and int(rpi.sum()) == g["rpi28_sum"]
+    assert torch.equal(swin.relative_position_index(7), g["rpi7"])
+    assert torch.allclose(swin.relative_coords_table(28, 12).view(1, 55, 55, 2), g["coords28"], atol=1e-6)
+    mask = swin.shifted_window_mask(112, 112, 28, 14)
+    assert sha(mask) == g["mask112_sha"] and int((mask != 0).sum()) == g["mask112_nonzero"]
+    assert torch.equal(swin.shifted_window_mask(28, 28, 7, 3), g["mask28_ws7"])
+
+
+def test_rs_gcn_oracle_matches_reference(golden):
+    m = cases.make_rs_gcn()
+    v_star, R = fusion.rs_gcn(m.state_dict(), "", cases.rs_gcn_input())
+    assert torch.allclose(v_star, golden["rs_gcn"]["v_star"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(R, golden["rs_gcn"]["R"], rtol=1e-4, atol=1e-5)
+
+
+def test_roberta_oracle_matches_hf(golden):
+    m = cases.make_roberta()
+    cfg = m.config
+    ids = synth.token_ids(cases.ROBERTA_BATCH, cases.ROBERTA_L, cfg.vocab_size, seed=cases.SEED)
+    tok, sent = roberta.encode(m.state_dict(), cases.roberta_geometry(cfg), ids, prefix="encoder.")
+    g = golden["roberta"]
+    assert torch.allclose(sent, g["sent"], rtol=1e-4, atol=1e-5), float((sent - g["sent"]).abs().max())
+    mask = g["mask"].unsqueeze(-1)
+    assert torch.allclose(tok * mask, g["tok"] * mask, rtol=1e-3, atol=1e-4)     # valid-token rows only
+    # the reference's 3-D mask and a plain key mask give the same pooled vector (pad-query rows are excluded)
+    _, sent_k = roberta.encode(m.state_dict(), cases.roberta_geometry(cfg), ids, prefix="encoder.", key_mask_only=True)
+    assert torch.allclose(sent, sent_k, rtol=1e-5, atol=1e-6)
+
+
+def test_graph_oracle_drift_guard(golden):
+    g = synth.cpg_batch(cases.FUSION_BATCH, seed=cases.SEED)
+    hb = cases.to_host_batch(g)
+    gg = golden["graph"]
+    assert torch.equal(torch.from_numpy(hb.batch_num_nodes), gg["bnn"])
+    indptr, indices, eids = dgl_ops.in_csr(hb.src, hb.dst, hb.num_nodes)
+    assert sha(torch.from_numpy(indptr)) == gg["indptr_sha"]
+    assert sha(torch.from_numpy(indices)) == gg["indices_sha"]
+    assert sha(torch.from_numpy(eids)) == gg["eids_sha"]
+    assert sha(torch.from_numpy(dgl_ops.pad_truncate_map(hb.batch_num_nodes, 100))) == gg["pad_map_sha"]
+    model = cases.make_fusion()
+    ge = torch.Generator().manual_seed(cases.SEED)
+    img = torch.randn(cases.FUSION_BATCH, 1024, generator=ge)
+    txt = torch.randn(cases.FUSION_BATCH, 768, generator=ge)
+    logits = fusion.fusion_forward(model.state_dict(), hb, img, txt)
+    assert torch.allclose(logits, gg["fusion_logits"], rtol=1e-4, atol=1e-5)
+
+
+def test_dgl_semantics_small_cases():
+    # add_self_loop: appended after existing edges, edata zero-filled, multi-edges / existing loops kept
+    g = dgl_ops.graph([0, 1, 1, 2], [1, 2, 2, 2])
+    g.edata["_ETYPE"] = torch.tensor([3, 1, 1, 0])
+    g2 = dgl_ops.add_self_loop(g)
+    assert g2.src.tolist() == [0, 1, 1, 2, 0, 1, 2] and g2.dst.tolist() == [1, 2, 2, 2, 0, 1, 2]
+    assert g2.edata["_ETYPE"].tolist() == [3, 1, 1, 0, 0, 0, 0]
+    # batch: node ids shifted, edges concatenated graph by graph
+    h = dgl_ops.graph([0], [1])
+    h.edata["_ETYPE"] = torch.tensor([2])
+    b = dgl_ops.batch([g2, dgl_ops.add_self_loop(h)])
+    assert b.batch_num_nodes.tolist() == [3, 2] and b.batch_num_edges.tolist() == [7, 3]
+    assert b.src.tolist()[7:] == [3, 3, 4] and b.dst.tolist()[7:] == [4, 3, 4]
+    # in-edge CSR sorted by (dst, eid)
+    indptr, idx, eids = dgl_ops.in_csr(g2.src, g2.dst, 3)
+    assert indptr.tolist() == [0, 1, 3, 7] and eids.tolist() == [4, 0, 5, 1, 2, 3, 6]
+    # pad / truncate map: short graph padded with -1, long graph truncated
+    pm = dgl_ops.pad_truncate_map(np.array([2, 5, 0]), 3)
+    assert pm.tolist() == [[0, 1, -1], [2, 3, 4], [-1, -1, -1]]
+    # segment sum / mean incl. an empty graph
+    feat = torch.arange(14, dtype=torch.float32).view(7, 2)
+    assert dgl_ops.segment_sum(feat, np.array([2, 5, 0])).tolist() == [[2., 4.], [40., 45.], [0., 0.]]
+    assert dgl_ops.mean_nodes(feat, np.array([2, 5, 0]))[2].tolist() == [0., 0.]
+    # GATConv raises on a zero-in-degree node
+    sd = {"fc.weight": torch.randn(8, 2), "attn_l": torch.randn(1, 2, 4), "attn_r": torch.randn(1, 2, 4),
+          "bias": torch.zeros(8)}
+    with pytest.raises(RuntimeError):
+        dgl_ops.gat_conv(sd, "", [0], [1], torch.randn(2, 2), 2, 4)
+    # GatedGraphConv asserts the edge-type range
+    with pytest.raises(AssertionError):
+        dgl_ops.gated_graph_conv({}, "", [0], [1], [5], torch.randn(2, 2), 4, 1, 3)
+
+
+def test_gat_softmax_is_per_destination():
+    torch.manual_seed(0)
+    sd = {"fc.weight": torch.randn(8, 3), "attn_l": torch.randn(1, 2, 4), "attn_r": torch.randn(1, 2, 4),
+          "bias": torch.zeros(8)}
+    x = torch.randn(3, 3)
+    # node 2 has in-edges from 0, 1 and itself; a single in-edge node gets exactly z[src]
+    out = dgl_ops.gat_conv(sd, "", [0, 1, 2, 0, 1], [2, 2, 2, 0, 1], x, 2, 4)
+    z = (x @ sd["fc.weight"].T).view(3, 2, 4)
+    assert torch.allclose(out[0], z[0], atol=1e-6) and torch.allclose(out[1], z[1], atol=1e-6)

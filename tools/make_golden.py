@@ -1,0 +1,172 @@
+"""Generate tests/golden/*.pt by running the REFERENCE code in this container.
+
+Run here (``/root/reference`` is not present on the GPU box):  ``python tools/make_golden.py``
+
+* SwinV2: ``/root/reference/mvuld/models/swin_transformer_v2.py`` imported unmodified through a 3-symbol
+  ``timm.models.layers`` shim (DropPath = identity in eval, to_2tuple, trunc_normal_); weights come from the
+  product classes under a fixed seed and are loaded with ``strict=True`` -- which also pins state-dict / buffer
+  compatibility.
+* Rs_GCN: ``/root/reference/mvuld/models/Rs_GCN.py`` imported unmodified.
+* RoBERTa: HF ``transformers`` (5.5 here; the reference pins 4.18) ``RobertaModel`` in encoder mode with the 2-D key
+  mask; valid-token rows and the pooled vector are what the reference's masked mean consumes.
+* DGL-dependent ops have no runnable reference (dgl is not installable offline): their golden files are produced by
+  ``oracle.dgl_ops`` itself and only guard against drift (parity unpinned, see oracle/__init__.py).
+
+Only small tensors are stored: inputs and weights are regenerated from seeds by tests through the same functions.
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+import mvuld_b200 as mv                      # noqa: E402
+from mvuld_b200 import synth                 # noqa: E402
+from tests import cases                      # noqa: E402
+
+
+def _shim_timm():
+    class DropPath(nn.Module):
+        def __init__(self, p=0.0):
+            super().__init__()
+            self.p = p
+
+        def forward(self, x):
+            assert not self.training, "shim DropPath is eval-only"
+            return x
+
+    layers = types.ModuleType("timm.models.layers")
+    layers.DropPath = DropPath
+    layers.to_2tuple = lambda x: tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+    layers.trunc_normal_ = nn.init.trunc_normal_
+    timm = types.ModuleType("timm")
+    models = types.ModuleType("timm.models")
+    timm.models, models.layers = models, layers
+    sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+@torch.no_grad()
+def golden_swin():
+    _shim_timm()
+    ref = _load(os.path.join(REF, "mvuld/models/swin_transformer_v2.py"), "ref_swin_v2")
+    out = {}
+    for name, kw in cases.SWIN_CASES.items():
+        model = cases.make_swin(name)
+        ref_model = ref.SwinTransformerV2(**kw).eval()
+        missing = ref_model.load_state_dict(model.state_dict(), strict=True)
+        x = synth.images(cases.SWIN_BATCH[name], kw["img_size"], seed=cases.SEED)
+        feats = ref_model.forward_features(x)
+        logits = ref_model(x)
+        out[name] = dict(features=feats.clone(), logits=logits.clone())
+        print(name, "features", tuple(feats.shape), float(feats.abs().mean()), missing)
+    # integer artefacts of the full-size geometry (too large to store: keep digests)
+    wa = ref.WindowAttention(128, (28, 28), 4, pretrained_window_size=(12, 12))
+    out["rpi28_sha"] = sha(wa.relative_position_index)
+    out["rpi28_sum"] = int(wa.relative_position_index.sum())
+    out["coords28"] = wa.relative_coords_table.clone()
+    blk = ref.SwinTransformerBlock(128, (112, 112), 4, window_size=28, shift_size=14)
+    out["mask112_sha"] = sha(blk.attn_mask)
+    out["mask112_nonzero"] = int((blk.attn_mask != 0).sum())
+    wa7 = ref.WindowAttention(128, (7, 7), 4, pretrained_window_size=(6, 6))
+    out["rpi7"] = wa7.relative_position_index.clone()
+    blk7 = ref.SwinTransformerBlock(128, (28, 28), 4, window_size=7, shift_size=3)
+    out["mask28_ws7"] = blk7.attn_mask.clone()
+    torch.save(out, os.path.join(OUT, "swin.pt"))
+    for k in ("timm", "timm.models", "timm.models.layers"):      # the shim must not leak into transformers' probes
+        sys.modules.pop(k, None)
+
+
+@torch.no_grad()
+def golden_rs_gcn():
+    ref = _load(os.path.join(REF, "mvuld/models/Rs_GCN.py"), "ref_rs_gcn")
+    mine = cases.make_rs_gcn()
+    m = ref.Rs_GCN(in_channels=512, inter_channels=512).eval()
+    m.load_state_dict(mine.state_dict(), strict=True)
+    v = cases.rs_gcn_input()
+    v_star, R = m(v)
+    torch.save(dict(v_star=v_star.clone(), R=R.clone()), os.path.join(OUT, "rs_gcn.pt"))
+    print("rs_gcn", float(v_star.abs().mean()), float((v_star - v).abs().mean()))
+
+
+@torch.no_grad()
+def golden_roberta():
+    from transformers import RobertaConfig, RobertaModel
+    cfg = cases.roberta_small_config()
+    hf_cfg = RobertaConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
+                           num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                           intermediate_size=cfg.intermediate_size,
+                           max_position_embeddings=cfg.max_position_embeddings, type_vocab_size=cfg.type_vocab_size,
+                           pad_token_id=cfg.pad_token_id, layer_norm_eps=cfg.layer_norm_eps,
+                           hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, is_decoder=False)
+    hf = RobertaModel(hf_cfg, add_pooling_layer=True).eval()
+    mine = cases.make_roberta()
+    sd = {k[len("encoder."):]: v for k, v in mine.state_dict().items() if k.startswith("encoder.")}
+    res = hf.load_state_dict(sd, strict=False)
+    assert not res.missing_keys or all("position_ids" in k or "token_type_ids" in k for k in res.missing_keys), res
+    assert not res.unexpected_keys, res
+    ids = synth.token_ids(cases.ROBERTA_BATCH, cases.ROBERTA_L, cfg.vocab_size, seed=cases.SEED)
+    mask = ids.ne(cfg.pad_token_id)
+    tok = hf(ids, attention_mask=mask.long())[0]
+    sent = (tok * mask.unsqueeze(-1)).sum(1) / mask.sum(-1).unsqueeze(-1)
+    torch.save(dict(sent=sent.clone(), tok_valid_checksum=float((tok * mask.unsqueeze(-1)).abs().sum()),
+                    tok=tok.clone(), mask=mask.clone()), os.path.join(OUT, "roberta.pt"))
+    print("roberta sent", tuple(sent.shape), float(sent.abs().mean()))
+
+
+@torch.no_grad()
+def golden_graph():
+    """Oracle-generated (drift guard only): integer artefacts + fusion / GGNN outputs on small seeded batches."""
+    from oracle import dgl_ops, fusion
+    from tests.cases import to_host_batch
+    g = synth.cpg_batch(cases.FUSION_BATCH, seed=cases.SEED)
+    hb = to_host_batch(g)
+    indptr, indices, eids = dgl_ops.in_csr(hb.src, hb.dst, hb.num_nodes)
+    pmap = dgl_ops.pad_truncate_map(hb.batch_num_nodes, 100)
+    model = cases.make_fusion()
+    ge = torch.Generator().manual_seed(cases.SEED)
+    img = torch.randn(cases.FUSION_BATCH, 1024, generator=ge)
+    txt = torch.randn(cases.FUSION_BATCH, 768, generator=ge)
+    logits = fusion.fusion_forward(model.state_dict(), hb, img, txt)
+    gg = synth.ggnn_batch(cases.GGNN_BATCH, seed=cases.SEED, n_etypes=cases.GGNN_T)
+    hg = to_host_batch(gg)
+    gm = cases.make_ggnn()
+    prob, logit, ssum, h = fusion.ggnn_sum_forward(gm.state_dict(), hg, cases.GGNN_D, cases.GGNN_STEPS, cases.GGNN_T)
+    torch.save(dict(bnn=torch.from_numpy(hb.batch_num_nodes), indptr_sha=sha(torch.from_numpy(indptr)),
+                    indices_sha=sha(torch.from_numpy(indices)), eids_sha=sha(torch.from_numpy(eids)),
+                    pad_map_sha=sha(torch.from_numpy(pmap)), fusion_logits=logits.clone(),
+                    ggnn_prob=prob.clone(), ggnn_logit=logit.clone(), ggnn_sum=ssum.clone(),
+                    ggnn_h_checksum=float(h.abs().sum())), os.path.join(OUT, "graph.pt"))
+    print("fusion logits", logits)
+    print("ggnn prob", prob[:4])
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    golden_swin()
+    golden_rs_gcn()
+    golden_roberta()
+    golden_graph()
+    print("golden files written to", OUT)
