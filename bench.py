@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- MVulD functions/sec (forward) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's kernels through the public API)
+    python bench.py --impl reference --gpus N --steps K ...   # reference arm: the CPU oracle port, host cores
+
+A "step" is one pass of the composed MVulD forward (SwinV2-B 448/w28 image branch + UniXcoder/RoBERTa-base 512-token
+text branch + GAT/Rs_GCN fusion model, SURVEY.md section 3.4 / BASELINE.json configs[3]) over one batch of synthetic
+functions per GPU.  Functions are independent, so ranks shard the batch with no data-path collective (weak scaling:
+``--batch`` functions per GPU).  ``--workload swin`` / ``ggnn`` time configs[1] / configs[2] instead.
+
+One JSON line is printed by rank 0 (contract in the task statement): value = whole-job functions/s with inputs
+resident in HBM, timed with CUDA events on the launching stream and max-reduced over ranks; e2e = the same through
+``MVulD.forward`` with pinned host inputs copied in and logits copied out inside the timed region; roofline = the
+dominant kernel family's achieved TFLOP/s (algorithmic FLOPs / CUDA-event time of every launch of that family in an
+instrumented pass) against MEASURED_PEAKS.json; cpu_baseline = the oracle port timed on the host cores on a bounded
+sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+# --------------------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="full", choices=["full", "swin", "ggnn"])
+    ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (default: 64 functions / 64 images / "
+                                                         "4096 graphs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# algorithmic work of each C-ABI call (FLOPs for tensor-pipe kernels, bytes for HBM-bound ones)
+# --------------------------------------------------------------------------------------------------------
+def work_of(name, args):
+    if name == "mvuld_gemm_bf16":
+        M, N, K = args["M"], args["N"], args["K"]
+        return "gemm", 2.0 * M * N * K, 0.0
+    if name == "mvuld_swin_qkv":
+        B, H, W, C = args[8], args[9], args[10], args[11]
+        return "gemm", 2.0 * B * H * W * C * 3 * C, 0.0
+    if name == "mvuld_heads_qkv":
+        B, L, Hd = args[6], args[7], args[8]
+        return "gemm", 2.0 * B * L * Hd * 3 * Hd, 0.0
+    if name == "mvuld_swin_window_attention":
+        B, H, W, C, nH, ws = args[6], args[7], args[8], args[9], args[10], args[11]
+        n = ws * ws
+        return "attention", 4.0 * (B * H * W // n) * nH * n * n * 32, 0.0
+    if name == "mvuld_seq_attention":
+        B, L, nH, hd = args[5], args[6], args[7], args[8]
+        return "attention", 4.0 * B * nH * L * L * hd, 0.0
+    return "other", 0.0, 0.0
+
+
+class Instrument:
+    """Brackets every C-ABI call with CUDA events on the launching stream (instrumented pass only)."""
+
+    def __init__(self):
+        self.records = []
+
+    def install(self):
+        from mvuld_b200 import _lib
+        self._lib, self._call, self._gemm = _lib, _lib.call, _lib.gemm
+        inst = self
+
+        def call(name, *a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = inst._call(name, *a)
+            e.record()
+            inst.records.append((name, a, s, e))
+            return r
+
+        def gemm(a, w, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            inst._gemm(a, w, **kw)
+            e.record()
+            inst.records.append(("mvuld_gemm_bf16", dict(M=a.shape[0], N=w.shape[0], K=a.shape[1]), s, e))
+
+        _lib.call, _lib.gemm = call, gemm
+
+    def remove(self):
+        self._lib.call, self._lib.gemm = self._call, self._gemm
+
+    def summary(self):
+        torch.cuda.synchronize()
+        fam = {}
+        per_kernel = {}
+        for name, a, s, e in self.records:
+            ms = s.elapsed_time(e)
+            f, flops, _ = work_of(name, a)
+            d = fam.setdefault(f, dict(ms=0.0, flops=0.0, launches=0))
+            d["ms"] += ms
+            d["flops"] += flops
+            d["launches"] += 1
+            k = per_kernel.setdefault(name, dict(ms=0.0, launches=0))
+            k["ms"] += ms
+            k["launches"] += 1
+        return fam, per_kernel
+
+
+# --------------------------------------------------------------------------------------------------------
+def build_workload(args, rank, device):
+    import mvuld_b200 as mv
+    from mvuld_b200 import synth
+    seed = 12345 + rank
+    torch.manual_seed(12345)                       # same weights on every rank
+    if args.workload == "full":
+        B = args.batch or 64
+        model = mv.MVulD(mv.default_config()).eval()
+        synth.randomize_for_parity(model, seed=777)
+        model = model.to(device)
+        host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=synth.token_ids(B, 512, seed=seed).pin_memory(),
+                    g=synth.cpg_batch(B, seed=seed))
+        for k in ("_UNIX_NODE_EMB", "pos_emb"):
+            host["g"].ndata[k] = host["g"].ndata[k].pin_memory()
+        host["g"].ndata.pop("_FUNC_EMB")           # feeds only the dead h_func branch (GraphModel.py:172,177)
+        host["g"]._src, host["g"]._dst = host["g"]._src.pin_memory(), host["g"]._dst.pin_memory()
+
+        def to_dev():
+            return dict(img=host["img"].to(device, non_blocking=True), ids=host["ids"].to(device, non_blocking=True),
+                        g=host["g"].to(device, non_blocking=True))
+
+        def step(d):
+            d["g"]._csr = None                     # graph collate (CSR build) is part of every step
+            return model(d["img"], d["ids"], d["g"])
+
+        h2d = host["img"].numel() * 4 + host["ids"].numel() * 8 + host["g"]._src.numel() * 16 + \
+            sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
+        name = (f"MVulD full fused inference (configs[3]): SwinV2-B 448px/w28 + UniXcoder-base 512 tok + GAT x2/"
+                f"Rs_GCN x8 fusion, {B} synthetic functions per GPU per step, avg "
+                f"{host['g'].num_nodes() / B:.0f} CPG nodes")
+        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name, flops_per_unit=262.1e9)
+    if args.workload == "swin":
+        B = args.batch or 64
+        model = mv.build_model(mv.default_config()).eval()
+        synth.randomize_for_parity(model, seed=777)
+        model = model.to(device)
+        host = dict(img=synth.images(B, 448, seed=seed).pin_memory())
+        return dict(units=B, to_dev=lambda: dict(img=host["img"].to(device, non_blocking=True)),
+                    step=lambda d: model.forward_features(d["img"]), h2d=host["img"].numel() * 4, d2h=B * 1024 * 4,
+                    name=f"SwinV2-B image branch alone (configs[1]), 448px window28, bf16 inference batch={B}",
+                    flops_per_unit=159.08e9)
+    B = args.batch or 4096
+    model = mv.GGNNSum(132, 200, max_edge_types=4, num_steps=6).eval()
+    synth.randomize_for_parity(model, seed=777)
+    model = model.to(device)
+    g = synth.ggnn_batch(B, seed=seed, n_etypes=4)
+    g.ndata["_WORD2VEC"] = g.ndata["_WORD2VEC"].pin_memory()
+
+    def step(d):
+        d["g"]._csr = None
+        return model(d["g"])[1]
+
+    h2d = g._src.numel() * 16 + g.edata["_ETYPE"].numel() * 8 + g.ndata["_WORD2VEC"].numel() * 4
+    return dict(units=B, to_dev=lambda: dict(g=g.to(device, non_blocking=True)), step=step, h2d=h2d, d2h=B * 4,
+                name=f"GGNN graph branch (configs[2]): {B} batched CPGs, {g.num_nodes()} nodes, {g.num_edges()} edges, "
+                     "4 edge types, D=200, 6 steps, segment-sum readout", flops_per_unit=0.0)
+
+
+def cpu_oracle_runner(workload, sample):
+    """The oracle port of the reference forward on the host cores; returns (units, seconds)."""
+    import mvuld_b200 as mv
+    from mvuld_b200 import synth
+    from oracle import swin as oswin, roberta as orob, fusion as ofus
+    from oracle.swin import SwinGeometry
+    from oracle.roberta import RobertaGeometry
+    from tests.cases import to_host_batch
+    torch.manual_seed(12345)
+    if workload == "ggnn":
+        m = mv.GGNNSum(132, 200, max_edge_types=4, num_steps=6).eval()
+        g = synth.ggnn_batch(sample, seed=1, n_etypes=4)
+        hb = to_host_batch(g)
+        sd = m.state_dict()
+        fn = lambda: ofus.ggnn_sum_forward(sd, hb, 200, 6, 4)
+    else:
+        model = mv.MVulD(mv.default_config()).eval() if workload == "full" else None
+        swin = model.swin if model is not None else mv.build_model(mv.default_config()).eval()
+        synth.randomize_for_parity(model if model is not None else swin, seed=777)
+        img = synth.images(sample, 448, seed=1)
+        sd_s = swin.state_dict()
+        if workload == "swin":
+            fn = lambda: oswin.forward_features(sd_s, SwinGeometry(), img)
+        else:
+            ids = synth.token_ids(sample, 512, seed=1)
+            hb = to_host_batch(synth.cpg_batch(sample, seed=1))
+            sd_u, sd_f = model.unix.state_dict(), model.fusion.state_dict()
+
+            def fn():
+                fi = oswin.forward_features(sd_s, SwinGeometry(), img)
+                ft = orob.get_repr(sd_u, RobertaGeometry(), ids)
+                return ofus.fusion_forward(sd_f, hb, fi, ft)
+    return fn
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference's own entry
+    points cannot run: no dgl/timm/yacs), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    sample = {"full": 2, "swin": 2, "ggnn": 64}[args.workload]
+    fn = cpu_oracle_runner(args.workload, sample)
+    for _ in range(max(1, min(args.warmup, 1))):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s"}[args.workload]
+    print(json.dumps({
+        "impl": "reference", "metric": "MVulD functions/sec (fwd)", "value": v, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": f"{sample} units per step on the host CPU"},
+        "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample} units x {args.steps} steps"},
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from mvuld_b200 import _lib
+    wl = build_workload(args, rank, device)
+    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s"}[args.workload]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ----
+    dev_in = wl["to_dev"]()
+    torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        out = wl["step"](dev_in)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        out = wl["step"](dev_in)
+    e.record()
+    barrier()
+    ms = max_over_ranks(s.elapsed_time(e))
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop()
+    value = wl["units"] * world * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host inputs in, logits out, every step ----
+    for _ in range(2):
+        o = wl["step"](wl["to_dev"]()).cpu()
+    barrier()
+    s.record()
+    for _ in range(args.steps):
+        o = wl["step"](wl["to_dev"]()).cpu()
+    e.record()
+    barrier()
+    ms_e2e = max_over_ranks(s.elapsed_time(e))
+    e2e = wl["units"] * world * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    line = {
+        "metric": "MVulD functions/sec (fwd)" if args.workload == "full" else f"{args.workload} branch {unit}",
+        "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["name"], "per_gpu_batch": wl["units"], "parallelism": f"batch-shard x{world}, no "
+                   "data-path collective", "l2_policy": "per-step inputs + activations exceed the 126 MB L2"},
+        "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(wl["h2d"]), "d2h_bytes_per_step": int(wl["d2h"])},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if wl["flops_per_unit"]:
+        line["model_tflops"] = wl["flops_per_unit"] * value / world / 1e12
+
+    if not args.no_roofline:
+        inst = Instrument()
+        inst.install()
+        try:
+            wl["step"](dev_in)
+        finally:
+            inst.remove()
+        fam, per_kernel = inst.summary()
+        total_ms = sum(d["ms"] for d in fam.values())
+        top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        if args.workload == "ggnn":
+            # HBM-bound path: the segment-reduce kernel (SURVEY.md section 8d row 2, bf16 messages)
+            k = per_kernel.get("mvuld_ggnn_gather_sum")
+            g = dev_in["g"]
+            alg = g.num_edges() * 200 * 2 + g.num_edges() * 5 + (g.num_nodes() + 1) * 4 + g.num_nodes() * 200 * 2
+            ach = alg / (k["ms"] / k["launches"] / 1e3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": "ggnn_gather_sum_kernel", "achieved": ach, "peak": pk["hbm"],
+                                "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                                "share_of_step": k["ms"] / total_ms}
+        else:
+            kname, d = top
+            fl = d["flops"] if d["flops"] else 0.0
+            ach = fl / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
+            line["roofline"] = {"bound": "tensor", "kernel": {"gemm": "gemm_tn_kernel (all epilogues)",
+                                                              "attention": "attn_fwd_kernel",
+                                                              "other": "row/graph kernels"}[kname],
+                                "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] +
+                                " (sustained: kernel timed inside a long step)", "share_of_step": d["ms"] / total_ms}
+        line["kernel_families"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                       "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else 0.0}
+                                   for k, v in fam.items()}
+        line["entry_points_ms"] = {k: [round(v["ms"], 3), v["launches"]] for k, v in
+                                   sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])[:12]}
+        if os.environ.get("MVULD_BENCH_DETAIL"):
+            rows = []
+            for name, a, s_, e_ in inst.records:
+                shape = a if isinstance(a, dict) else [x for x in a if isinstance(x, (int, float))]
+                rows.append({"name": name, "shape": shape, "ms": round(s_.elapsed_time(e_), 4)})
+            with open(os.environ["MVULD_BENCH_DETAIL"], "w") as fh:
+                json.dump(rows, fh)
+
+    if not args.no_cpu_baseline and world == 1:
+        torch.set_num_threads(os.cpu_count())
+        sample = {"full": 2, "swin": 2, "ggnn": 64}[args.workload]
+        fn = cpu_oracle_runner(args.workload, sample)
+        fn()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            fn()
+        dt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {"value": sample / dt, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{sample} units, mean of {reps} runs after 1 warm-up, fp32 oracle"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,7 +46,7 @@ SIGNATURES = {
     "mvuld_rs_gcn_affinity": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_fusion_head": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
-    "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 14 + [_P, _P],
+    "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 13 + [_P, _P],
 }
 
 _lib = None
