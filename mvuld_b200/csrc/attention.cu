@@ -16,6 +16,8 @@
 // transpose is ever written.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -24,6 +26,8 @@ namespace mv {
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_BM = 128;          // query rows per tile (= TMEM lanes)
 constexpr int ATT_MAX_KT = 8;        // max kv tiles resident
+constexpr int ATT_REGS_CTRL = 88;      // setmaxnreg for warps 0-3 (128 threads)
+constexpr int ATT_REGS_SOFTMAX = 208;  // 8 softmax warps: 128*88 + 256*208 = 64512 = 384 threads * 168 regs at launch
 
 enum { MODE_SWIN = 0, MODE_SEQ = 1 };
 
@@ -65,7 +69,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int TBL = (MODE == MODE_SWIN) ? (2 * WS - 1) * (2 * WS - 1) : 0;
   constexpr int ROWS_PER_TILE = (MODE == MODE_SWIN) ? KT / WS : 1;
   constexpr int SPLIT = WS - WS / 2;                 // first column / row of the "shifted-in" band
-  constexpr int NSEG = (MODE == MODE_SWIN) ? ROWS_PER_TILE * 2 : 1;
+  constexpr int NSEG = (MODE == MODE_SWIN) ? ROWS_PER_TILE * 2 : 4;     // independent max chains
   static_assert(MODE != MODE_SWIN || KT % WS == 0, "kv tile must hold whole window rows");
   static_assert(KT % 16 == 0 && KT <= 128, "kv tile");
 
@@ -98,7 +102,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* q_full = v_full + ATT_MAX_KT;     // [2]
   uint64_t* q_empty = q_full + 2;
   uint64_t* s_full = q_empty + 2;
-  uint64_t* p_full = s_full + 2;
+  uint64_t* s_free = s_full + 2;
+  uint64_t* p_full = s_free + 2;
   uint64_t* pv_done = p_full + 2;
   uint64_t* o_free = pv_done + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
@@ -118,6 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&q_full[g], 1);
       mbar_init(&q_empty[g], 1);
       mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 128);
       mbar_init(&p_full[g], 128);
       mbar_init(&pv_done[g], 1);
       mbar_init(&o_free[g], 128);
@@ -129,7 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_relinquish();
   }
   if (MODE == MODE_SWIN) {
-    // stage this head's bias table (12 KB for ws=28) -- plain coalesced loads by the softmax warps
+    // stage this head's bias table (12 KB for ws=28) -- plain coalesced loads
     const float* src = p.bias_rev + (size_t)head * TBL;
     for (int i = threadIdx.x; i < TBL; i += ATT_THREADS) sTab[i] = __ldg(src + i);
   }
@@ -140,89 +146,99 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_S = tmem_base;           // S[g] at columns g*128
   const uint32_t tmem_O = tmem_base + 256;     // O[g] at columns 256 + g*64
 
-  if (warp == 0) {
-    // =========================================== TMA producer ===========================================
-    if (lane == 0) {
-      auto load_q = [&](int g, int t) {
-        mbar_arrive_expect_tx(&q_full[g], L::Q_BYTES);
-        tma_load_3d(sQ + g * L::Q_BYTES, &tmQ, &q_full[g], 0, t * ATT_BM, bh);
-      };
-      load_q(0, 0);
-      for (int j = 0; j < nkt; ++j) {
-        mbar_arrive_expect_tx(&k_full[j], KT * L::ROW_BYTES);
-        tma_load_3d(sK + j * KT * L::ROW_BYTES, &tmK, &k_full[j], 0, j * KT, bh);
-        if (j == 0 && nq > 1) load_q(1, 1);
-        mbar_arrive_expect_tx(&v_full[j], KT * L::ROW_BYTES);
-        tma_load_3d(sV + j * KT * L::ROW_BYTES, &tmV, &v_full[j], 0, j * KT, bh);
-      }
-      uint32_t ph[2] = {0, 0};
-      for (int t = 2; t < nq; ++t) {
-        const int g = t & 1;
-        mbar_wait(&q_empty[g], ph[g], 10);
-        ph[g] ^= 1;
-        load_q(g, t);
-      }
-    }
-  } else if (warp == 1) {
-    // ============================================ MMA issuer ============================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, KT, 0, 0) & ~((QK_FP16 ? 1u : 0u) * ((1u << 7) | (1u << 10)));
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, HD, 0, 1);
-      const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), v0 = smem_u32(sV), p0 = smem_u32(sP);
-      auto issue_s = [&](int g, int j) {
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t ad = make_smem_desc(q0 + g * L::Q_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
-          const uint64_t bd = make_smem_desc(k0 + j * KT * L::ROW_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
-          umma_ss(tmem_S + g * 128, ad, bd, idesc_s, k != 0);
-        }
-        umma_commit(&s_full[g]);
-      };
-      auto issue_pv = [&](int g, int j) {
-#pragma unroll
-        for (int s = 0; s < KT / 16; ++s) {
-          const uint64_t ad = make_smem_desc(p0 + g * L::P_BYTES + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024, 2);
-          const uint64_t bd = make_smem_desc(v0 + (j * KT + s * 16) * L::ROW_BYTES, 16, L::SBO, L::LAYOUT);
-          umma_ss(tmem_O + g * 64, ad, bd, idesc_pv, (j | s) != 0);
-        }
-        umma_commit(&pv_done[g]);
-      };
-      uint32_t ph_q[2] = {0, 0}, ph_p[2] = {0, 0}, ph_o[2] = {0, 0};
-      const int n_it = (nq + 1) >> 1;
-      for (int it = 0; it < n_it; ++it) {
-        const bool valid[2] = {true, 2 * it + 1 < nq};
-        for (int g = 0; g < 2; ++g) {
-          if (!valid[g]) continue;
-          mbar_wait(&q_full[g], ph_q[g], 20);
-          ph_q[g] ^= 1;
-          if (it == 0) mbar_wait(&k_full[0], 0, 21);
-          tc_fence_after();
-          issue_s(g, 0);
-        }
+  if (warp < 4) {
+    reg_dec<ATT_REGS_CTRL>();                  // producer / MMA / allocator warps need few registers
+    if (warp == 0) {
+      // =========================================== TMA producer ===========================================
+      if (lane == 0) {
+        auto load_q = [&](int g, int t) {
+          mbar_arrive_expect_tx(&q_full[g], L::Q_BYTES);
+          tma_load_3d(sQ + g * L::Q_BYTES, &tmQ, &q_full[g], 0, t * ATT_BM, bh);
+        };
+        load_q(0, 0);
         for (int j = 0; j < nkt; ++j) {
+          mbar_arrive_expect_tx(&k_full[j], KT * L::ROW_BYTES);
+          tma_load_3d(sK + j * KT * L::ROW_BYTES, &tmK, &k_full[j], 0, j * KT, bh);
+          if (j == 0 && nq > 1) load_q(1, 1);
+          mbar_arrive_expect_tx(&v_full[j], KT * L::ROW_BYTES);
+          tma_load_3d(sV + j * KT * L::ROW_BYTES, &tmV, &v_full[j], 0, j * KT, bh);
+        }
+        uint32_t ph[2] = {0, 0};
+        for (int t = 2; t < nq; ++t) {
+          const int g = t & 1;
+          mbar_wait(&q_empty[g], ph[g], 10);
+          ph[g] ^= 1;
+          load_q(g, t);
+        }
+      }
+    } else if (warp == 1) {
+      // ============================================ MMA issuer ============================================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s =
+            make_idesc_bf16(ATT_BM, KT, 0, 0) & ~((QK_FP16 ? 1u : 0u) * ((1u << 7) | (1u << 10)));
+        constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, HD, 0, 1);
+        const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), v0 = smem_u32(sV), p0 = smem_u32(sP);
+        int s_count[2] = {0, 0};               // S tiles issued per group: S[g] is reused once its reader freed it
+        auto issue_s = [&](int g, int j, bool first_pass) {
+          if (s_count[g] > 0) mbar_wait(&s_free[g], (s_count[g] - 1) & 1, 26);
+          if (first_pass) mbar_wait(&k_full[j], 0, 21);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint64_t ad = make_smem_desc(q0 + g * L::Q_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
+            const uint64_t bd = make_smem_desc(k0 + j * KT * L::ROW_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
+            umma_ss(tmem_S + g * 128, ad, bd, idesc_s, k != 0);
+          }
+          umma_commit(&s_full[g]);
+          ++s_count[g];
+        };
+        auto issue_pv = [&](int g, int j) {
+#pragma unroll
+          for (int s = 0; s < KT / 16; ++s) {
+            const uint64_t ad = make_smem_desc(p0 + g * L::P_BYTES + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024, 2);
+            const uint64_t bd = make_smem_desc(v0 + (j * KT + s * 16) * L::ROW_BYTES, 16, L::SBO, L::LAYOUT);
+            umma_ss(tmem_O + g * 64, ad, bd, idesc_pv, (j | s) != 0);
+          }
+          umma_commit(&pv_done[g]);
+        };
+        uint32_t ph_q[2] = {0, 0}, ph_p[2] = {0, 0}, ph_o[2] = {0, 0};
+        const int n_it = (nq + 1) >> 1;
+        for (int it = 0; it < n_it; ++it) {
+          const bool valid[2] = {true, 2 * it + 1 < nq};
           for (int g = 0; g < 2; ++g) {
             if (!valid[g]) continue;
-            mbar_wait(&p_full[g], ph_p[g], 22);
-            ph_p[g] ^= 1;
-            if (j == 0 && it > 0) {
-              mbar_wait(&o_free[g], ph_o[g], 23);
-              ph_o[g] ^= 1;
+            mbar_wait(&q_full[g], ph_q[g], 20);
+            ph_q[g] ^= 1;
+            issue_s(g, 0, it == 0);
+            if (nkt == 1) umma_commit(&q_empty[g]);
+          }
+          for (int j = 0; j < nkt; ++j) {
+            // S(j+1) goes out as soon as the softmax group has pulled S(j) into registers ...
+            for (int g = 0; g < 2; ++g) {
+              if (!valid[g] || j + 1 >= nkt) continue;
+              issue_s(g, j + 1, it == 0);
+              if (j + 2 == nkt) umma_commit(&q_empty[g]);   // last read of this Q tile is in flight
             }
-            if (it == 0) mbar_wait(&v_full[j], 0, 24);
-            tc_fence_after();
-            issue_pv(g, j);
-            if (j + 1 < nkt) {
-              if (it == 0) mbar_wait(&k_full[j + 1], 0, 25);
-              issue_s(g, j + 1);
-            } else {
-              umma_commit(&q_empty[g]);
+            // ... and P(j) V(j) once the group has written P(j)
+            for (int g = 0; g < 2; ++g) {
+              if (!valid[g]) continue;
+              mbar_wait(&p_full[g], ph_p[g], 22);
+              ph_p[g] ^= 1;
+              if (j == 0 && it > 0) {
+                mbar_wait(&o_free[g], ph_o[g], 23);
+                ph_o[g] ^= 1;
+              }
+              if (it == 0) mbar_wait(&v_full[j], 0, 24);
+              tc_fence_after();
+              issue_pv(g, j);
             }
           }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ========================================= softmax warpgroups =========================================
+    reg_inc<ATT_REGS_SOFTMAX>();
     const int g = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // row within the query tile == TMEM lane
@@ -250,16 +266,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (hi > WS - 1) hi = WS - 1;                        // rows past the window only exist as padding
       }
       const bool ri = hi >= SPLIT, ci = wi >= SPLIT;
-      float m_run = -INFINITY, l_run = 0.f;
+      float m_run = -INFINITY;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};                    // split row sum: four independent add chains
 
       for (int j = 0; j < nkt; ++j) {
-        mbar_wait(&s_full[g], ph_s, 30);
-        ph_s ^= 1;
-        tc_fence_after();
         const int ncols = min(KT, kv_valid - j * KT);        // valid kv columns in this tile
-        const bool partial = ncols < KT;
 
-        // per-segment additive constants (shift mask) -- zero when the block is unshifted
+        // per-segment additive constants (shift mask) and bias-table row bases
         float cseg[NSEG];
         int tb[ROWS_PER_TILE];
 #pragma unroll
@@ -277,115 +290,104 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
 
-        // ---- pass 1: row max of the raw scores (+ segment constant); the bias is bounded by bmax ----
-        float segmax[NSEG];
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s) segmax[s] = -INFINITY;
-#pragma unroll
-        for (int c0 = 0; c0 < KT; c0 += 32) {
-          uint32_t rv[32];
-          if (c0 + 32 <= KT) {
-            tmem_ld32(tS + c0, rv);
-          } else {
-            uint32_t r16[16];
-            tmem_ld16(tS + c0, r16);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) rv[q] = r16[q];
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int c = c0 + q;
-            if (c < KT) {
-              float s = __uint_as_float(rv[q]);
-              if (partial && c >= ncols) s = -INFINITY;
-              const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : 0;
-              segmax[seg] = fmaxf(segmax[seg], s);
-            }
-          }
-        }
-        float m_tile = -INFINITY;
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s) m_tile = fmaxf(m_tile, segmax[s] + cseg[s]);
-        m_tile += bmax;
-
-        // ---- running max with lazy rescale (only when the reference point moves by > 2^8) ----
-        float m_new = fmaxf(m_run, m_tile);
-        bool need = (j > 0) && (m_new > m_run + 8.0f);
-        if (j == 0) m_run = m_new;
-        if (j > 0) {
-          mbar_wait(&pv_done[g], ph_pv, 31);                 // PV(j-1) retired: P buffer free, O up to date
-          ph_pv ^= 1;
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, need)) {
-            const float f = need ? ex2_approx(m_run - m_new) : 1.0f;
-            if (need) m_run = m_new;
-            l_run *= f;
-#pragma unroll
-            for (int c0 = 0; c0 < HD; c0 += 32) {
-              uint32_t o[32];
-              tmem_ld32(tO + c0, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * f);
-              tmem_st32(tO + c0, o);
-            }
-            tmem_st_wait();
-          }
-        }
-
-        // ---- pass 2: p = 2^(s + bias + cseg - m_run), row sum, P -> swizzled smem ----
-        float csm[NSEG];
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s) csm[s] = cseg[s] - m_run;
+        // ---- pull the whole S row into registers, then hand the TMEM buffer back to the MMA warp ----
+        mbar_wait(&s_full[g], ph_s, 30);
+        ph_s ^= 1;
+        tc_fence_after();
+        uint32_t sv[KT];
 #pragma unroll
         for (int c0 = 0; c0 < KT; c0 += 32) {
-          uint32_t rv[32];
-          if (c0 + 32 <= KT) {
-            tmem_ld32(tS + c0, rv);
-          } else {
-            uint32_t r16[16];
-            tmem_ld16(tS + c0, r16);
+          if (c0 + 32 <= KT) tmem_ld32p(tS + c0, sv + c0);
+          else tmem_ld16p(tS + c0, sv + c0);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);
+
+        auto tile = [&](auto partial_c) {
+          constexpr bool PARTIAL = decltype(partial_c)::value;
+          // sweep 1: s += bias (all shared-memory loads of the tile are independent and issued back to back: no
+          // store sits between them, so the scheduler can keep dozens of LDS in flight)
+          if (MODE == MODE_SWIN) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) rv[q] = r16[q];
+            for (int c = 0; c < KT; ++c) {
+              const int rr = c / WS, wj = c % WS;
+              float s = __uint_as_float(sv[c]) + sTab[tb[rr] + wj];
+              if (PARTIAL) s = (c < ncols) ? s : -INFINITY;
+              sv[c] = __float_as_uint(s);
+            }
+          } else if (PARTIAL) {
+#pragma unroll
+            for (int c = 0; c < KT; ++c) sv[c] = (c < ncols) ? sv[c] : 0xff800000u;   // -inf
           }
-          tmem_ld_wait();
-          float pv[32];
+          // sweep 2: exact row max (segment constants added once per segment)
+          float segmax[NSEG];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int c = c0 + q;
-            if (c < KT) {
-              float s = __uint_as_float(rv[q]);
-              if (MODE == MODE_SWIN) {
-                const int rr = c / WS, wj = c % WS;
-                s += sTab[tb[rr] + wj];
-                s += csm[rr * 2 + (wj >= SPLIT ? 1 : 0)];
-              } else {
-                s += csm[0];
+          for (int s = 0; s < NSEG; ++s) segmax[s] = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < KT; ++c) {
+            const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : (c & (NSEG - 1));
+            segmax[seg] = fmaxf(segmax[seg], __uint_as_float(sv[c]));
+          }
+          float m_tile = -INFINITY;
+#pragma unroll
+          for (int s = 0; s < NSEG; ++s) m_tile = fmaxf(m_tile, segmax[s] + ((MODE == MODE_SWIN) ? cseg[s] : 0.f));
+
+          // running max with lazy rescale (only when the reference point moves by more than 2^8)
+          const float m_new = fmaxf(m_run, m_tile);
+          const bool need = (j > 0) && (m_new > m_run + 8.0f);
+          if (j == 0) m_run = m_new;
+          if (j > 0) {
+            mbar_wait(&pv_done[g], ph_pv, 31);               // PV(j-1) retired: P buffer free, O up to date
+            ph_pv ^= 1;
+            tc_fence_after();
+            if (__any_sync(0xffffffffu, need)) {
+              const float f = need ? ex2_approx(m_run - m_new) : 1.0f;
+              if (need) m_run = m_new;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) l4[q] *= f;
+#pragma unroll
+              for (int c0 = 0; c0 < HD; c0 += 32) {
+                uint32_t o[32];
+                tmem_ld32(tO + c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * f);
+                tmem_st32(tO + c0, o);
               }
-              float e = ex2_approx(s);
-              if (partial && c >= ncols) e = 0.f;
-              l_run += e;
-              pv[q] = e;
-            } else {
-              pv[q] = 0.f;
+              tmem_st_wait();
             }
           }
-          // 8 columns = one 16-byte unit; unit u of row r lives at ((u ^ (r & 7)) * 16) within its 128-byte row
+
+          // sweep 3: p = 2^(s + cseg - m_run); row sums; P -> 128B-swizzled shared memory (A operand of PV).
+          // Masked / out-of-range columns carry -inf and come out as exactly 0.
+          float csm[NSEG];
 #pragma unroll
-          for (int u8 = 0; u8 < 4; ++u8) {
-            const int c = c0 + u8 * 8;
-            if (c < KT) {
-              uint4 w;
-              w.x = pack_bf16x2(pv[u8 * 8 + 0], pv[u8 * 8 + 1]);
-              w.y = pack_bf16x2(pv[u8 * 8 + 2], pv[u8 * 8 + 3]);
-              w.z = pack_bf16x2(pv[u8 * 8 + 4], pv[u8 * 8 + 5]);
-              w.w = pack_bf16x2(pv[u8 * 8 + 6], pv[u8 * 8 + 7]);
-              const int chunk = c >> 6, unit = (c & 63) >> 3;
-              *reinterpret_cast<uint4*>(myP + chunk * 16384 + ((unit ^ (r & 7)) << 4)) = w;
+          for (int s = 0; s < NSEG; ++s) csm[s] = ((MODE == MODE_SWIN) ? cseg[s] : 0.f) - m_run;
+#pragma unroll
+          for (int c0 = 0; c0 < KT; c0 += 8) {
+            float pv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int c = c0 + q;
+              const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : 0;
+              const float e = ex2_approx(__uint_as_float(sv[c]) + csm[seg]);
+              l4[q & 3] += e;
+              pv[q] = e;
             }
+            uint4 w;
+            w.x = pack_bf16x2(pv[0], pv[1]);
+            w.y = pack_bf16x2(pv[2], pv[3]);
+            w.z = pack_bf16x2(pv[4], pv[5]);
+            w.w = pack_bf16x2(pv[6], pv[7]);
+            // 8 columns = one 16-byte unit; unit u of row r sits at ((u ^ (r & 7)) * 16) inside its 128-byte row
+            const int chunk = c0 >> 6, unit = (c0 & 63) >> 3;
+            *reinterpret_cast<uint4*>(myP + chunk * 16384 + ((unit ^ (r & 7)) << 4)) = w;
           }
-        }
+        };
+        if (ncols < KT) tile(std::true_type{});
+        else tile(std::false_type{});
+
         fence_proxy_async_smem();      // P (generic proxy) -> visible to the tensor core (async proxy)
         tc_fence_before();             // orders our tcgen05.ld/st of S and O before the MMA warp's next issue
         mbar_arrive(&p_full[g]);
@@ -395,7 +397,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&pv_done[g], ph_pv, 32);
       ph_pv ^= 1;
       tc_fence_after();
-      const float inv = 1.0f / l_run;
+      const float inv = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
       size_t orow;
       if (MODE == MODE_SWIN) {
         const int hl = i / WS, wl = i - hl * WS;

@@ -76,8 +76,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > MV_WATCHDOG_CYCLES) {
+#ifdef MV_WATCHDOG_PRINTF
       printf("[mvuld_b200] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);
+#endif
       __trap();
     }
   }
@@ -203,8 +205,40 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// pointer forms: r must be a statically indexed slice of a register array (fully unrolled caller)
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// register re-allocation between warpgroups (all 4 warps of a warpgroup must execute it)
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -225,9 +259,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// exact-erf GELU (nn.GELU default, swin_transformer_v2.py:17,28); erff is accurate to ~1 ulp
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf-form GELU (nn.GELU default, swin_transformer_v2.py:17,28).  erf by Abramowitz-Stegun 7.1.28:
+//   erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |error| <= 3e-7 for z >= 0, odd extension for z < 0.
+// One MUFU (rcp) + 12 FMA-pipe instructions per element instead of libm erff's ~40 with branches: the libm version
+// made every fc1 GEMM epilogue-bound (12.5 k cycles per 128x128 tile against 2 k cycles of MMA).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float d = fmaf(z, 0.0000430638f, 0.0002765672f);
+  d = fmaf(z, d, 0.0001520143f);
+  d = fmaf(z, d, 0.0092705272f);
+  d = fmaf(z, d, 0.0422820123f);
+  d = fmaf(z, d, 0.0705230784f);
+  d = fmaf(z, d, 1.0f);
+  d *= d;
+  d *= d;
+  d *= d;
+  d *= d;
+  const float erf_abs = 1.0f - rcp_approx(d);          // d^16 overflows to +inf for z > ~18: rcp -> 0, erf -> 1
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);                 // 0.5 x (1 + erf(x / sqrt 2)), using x erf(|x|..) sign = |x|
+}
+// ELU(alpha = 1) (F.elu, GraphModel.py:154,159,171,176,186-187)
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : ex2_approx(x * 1.4426950408889634f) - 1.0f; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -7,7 +7,8 @@
 // Structure (one CTA per SM, persistent over 128 x BN output tiles):
 //   warp 0      TMA producer   : A/W tiles (128B-swizzled, K-major) -> STAGES-deep smem ring, mbarrier full/empty
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage, commits to mbarriers
-//   warps 2..5  epilogue       : tcgen05.ld 32 lanes x 32 columns, fused epilogue, 128-bit global stores
+//   warps 2..9  epilogue       : tcgen05.ld 32 lanes x 32 columns, fused epilogue, 128-bit global stores
+//                                (two warps per TMEM lane quarter, each draining half of the tile's columns)
 //   TMEM        2 x BN fp32 columns: the epilogue of tile i overlaps the mainloop of tile i+1
 #include "common.cuh"
 #include "host_util.h"
@@ -16,7 +17,7 @@ namespace mv {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 // ------------------------------------------------------------------------------------------------
 // Epilogues.  Called once per (row, 32-column chunk) by the thread that owns the row.
@@ -246,7 +247,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], GEMM_THREADS - 64);
     }
     fence_barrier_init();
   }
@@ -304,6 +305,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the tile's columns this warp drains
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
@@ -313,7 +315,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * GEMM_BM + quarter * 32 + lane;
       const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         tmem_ld32(t0 + c * 32, r);
         tmem_ld_wait();
@@ -375,6 +377,9 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   EpiGeneric e;
   e.bias = bias; e.res = res_f32; e.out_b = reinterpret_cast<bf16*>(out_bf16); e.out_f = out_f32;
   e.ldr = ldr; e.ldc = ldc; e.act = act; e.M = M; e.N = N;
+  // 128x256 tiles move 27 % fewer operand bytes per MAC through L2 than 128x128; use them when N fills them
+  if (N % 256 == 0 && (long long)M * N >= 256ll * 256 * 148)
+    return launch_gemm<256, 4, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
   return launch_gemm<128, 6, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
 }
 
@@ -387,6 +392,7 @@ extern "C" int mvuld_swin_qkv(const void* X, const void* Wqkv, const float* q_bi
   e.q_bias = q_bias; e.v_bias = v_bias; e.qscale = qscale;
   e.q = reinterpret_cast<__half*>(q); e.k = reinterpret_cast<__half*>(k); e.v = reinterpret_cast<bf16*>(v);
   e.C = C; e.nH = nH; e.H = H; e.W = W; e.ws = ws; e.shift = shift; e.M = B * H * W;
+  if ((3 * C) % 256 == 0) return launch_gemm<256, 4, EpiQkvSwin>(X, C, Wqkv, C, B * H * W, 3 * C, C, e, stream);
   return launch_gemm<128, 6, EpiQkvSwin>(X, C, Wqkv, C, B * H * W, 3 * C, C, e, stream);
 }
 
@@ -396,5 +402,6 @@ extern "C" int mvuld_heads_qkv(const void* X, const void* Wqkv, const float* bia
   EpiQkvHeads e;
   e.bias = bias; e.q = reinterpret_cast<bf16*>(q); e.k = reinterpret_cast<bf16*>(k); e.v = reinterpret_cast<bf16*>(v);
   e.qmul = qmul; e.Hd = Hd; e.nH = nH; e.hd = Hd / nH; e.L = L; e.M = B * L;
+  if ((3 * Hd) % 256 == 0) return launch_gemm<256, 4, EpiQkvHeads>(X, Hd, Wqkv, Hd, B * L, 3 * Hd, Hd, e, stream);
   return launch_gemm<128, 6, EpiQkvHeads>(X, Hd, Wqkv, Hd, B * L, 3 * Hd, Hd, e, stream);
 }
