@@ -61,12 +61,23 @@ __host__ __device__ constexpr int att_smem_bytes(int HD, int KT, int nkt, int ta
          + ((table_floats * 4 + 1023) / 1024) * 1024 + 512 /*barriers*/ + 1024 /*align*/;
 }
 
+// Row stride of the bias table in shared memory.  Lane l of a warp owns query slot i0 + l, i.e. (hi, wi) walks a
+// window row and then wraps to the next one; its table address is base(hi) - wi + wj.  With stride S = -WS (mod 32)
+// the wrap continues the same descending bank sequence, so the 32 lanes always hit 32 distinct banks.
+__host__ __device__ constexpr int att_tab_stride(int ws) {
+  int s = 2 * ws - 1;
+  while ((s + ws) % 32 != 0) ++s;
+  return s;
+}
+
 template <int MODE, int HD, int WS, int KT, bool QK_FP16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, AttnParams p) {
   using L = AttnLayout<HD>;
-  constexpr int TBL = (MODE == MODE_SWIN) ? (2 * WS - 1) * (2 * WS - 1) : 0;
+  constexpr int SIDE = 2 * WS - 1;
+  constexpr int TSTRIDE = att_tab_stride(WS);
+  constexpr int TBL = (MODE == MODE_SWIN) ? SIDE * TSTRIDE : 0;          // shared-memory floats (padded rows)
   constexpr int ROWS_PER_TILE = (MODE == MODE_SWIN) ? KT / WS : 1;
   constexpr int SPLIT = WS - WS / 2;                 // first column / row of the "shifted-in" band
   constexpr int NSEG = (MODE == MODE_SWIN) ? ROWS_PER_TILE * 2 : 4;     // independent max chains
@@ -136,8 +147,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (MODE == MODE_SWIN) {
     // stage this head's bias table (12 KB for ws=28) -- plain coalesced loads
-    const float* src = p.bias_rev + (size_t)head * TBL;
-    for (int i = threadIdx.x; i < TBL; i += ATT_THREADS) sTab[i] = __ldg(src + i);
+    const float* src = p.bias_rev + (size_t)head * SIDE * SIDE;
+    for (int i = threadIdx.x; i < SIDE * SIDE; i += ATT_THREADS) sTab[(i / SIDE) * TSTRIDE + (i % SIDE)] = __ldg(src + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -283,7 +294,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool rdiff = rowflag && ((hj >= SPLIT) != ri);
             cseg[2 * rr] = (rdiff || (colflag && ci)) ? NEG100 : 0.f;           // wj <  SPLIT
             cseg[2 * rr + 1] = (rdiff || (colflag && !ci)) ? NEG100 : 0.f;      // wj >= SPLIT
-            tb[rr] = (hi - hj + WS - 1) * (2 * WS - 1) + (WS - 1 - wi);
+            tb[rr] = (hi - hj + WS - 1) * TSTRIDE + (WS - 1 - wi);
           } else {
             cseg[0] = 0.f;
             tb[0] = 0;
@@ -364,14 +375,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           float csm[NSEG];
 #pragma unroll
           for (int s = 0; s < NSEG; ++s) csm[s] = ((MODE == MODE_SWIN) ? cseg[s] : 0.f) - m_run;
+          // the exponentials are issued as one long run of independent MUFU ops (the XU pipe takes one warp
+          // instruction every 8 cycles; the other warpgroup's FADD / LDS / STS work fills the issue slots in between)
+#pragma unroll
+          for (int c = 0; c < KT; ++c) {
+            const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : 0;
+            sv[c] = __float_as_uint(__uint_as_float(sv[c]) + csm[seg]);
+          }
+#pragma unroll
+          for (int c = 0; c < KT; ++c) sv[c] = __float_as_uint(ex2_approx(__uint_as_float(sv[c])));
 #pragma unroll
           for (int c0 = 0; c0 < KT; c0 += 8) {
             float pv[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const int c = c0 + q;
-              const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : 0;
-              const float e = ex2_approx(__uint_as_float(sv[c]) + csm[seg]);
+              const float e = __uint_as_float(sv[c0 + q]);
               l4[q & 3] += e;
               pv[q] = e;
             }
@@ -443,7 +461,7 @@ static int launch_attn(const void* q, const void* k, const void* v, int n_bh, co
   using L = AttnLayout<HD>;
   const int nkt = (p.Nkv + KT - 1) / KT;
   MV_CHECK_ARG(nkt <= ATT_MAX_KT, "attention: %d kv tiles exceed the resident maximum %d", nkt, ATT_MAX_KT);
-  constexpr int TBL = (MODE == MODE_SWIN) ? (2 * WS - 1) * (2 * WS - 1) : 0;
+  constexpr int TBL = (MODE == MODE_SWIN) ? (2 * WS - 1) * att_tab_stride(WS) : 0;
   const int smem = att_smem_bytes(HD, KT, nkt, TBL);
   MV_CHECK_ARG(smem <= 232448, "attention: %d B shared memory needed, 232448 available", smem);
   CUtensorMap tmQ, tmK, tmV;
