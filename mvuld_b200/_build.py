@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function",
     "-I", os.path.join(os.path.dirname(HERE), "include"),
-]
+] + (os.environ.get("MVULD_NVCC_EXTRA", "").split())
 
 
 def _nvcc() -> str:

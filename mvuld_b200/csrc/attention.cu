@@ -9,12 +9,15 @@
 //             Keys >= len are skipped (their additive -10000 underflows to exactly 0 in fp32 for valid queries).
 //
 // One CTA per (window-or-sequence, head).  K and V of that head stay resident in shared memory; the CTA walks all
-// query tiles.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer (single thread), warp 2 TMEM allocator,
-// warps 4-7 / 8-11 two softmax warpgroups (thread == query row, no cross-thread reductions) that ping-pong so one
-// group's exp/bias work overlaps the other's QK^T / PV tensor-core work.  S and O accumulators live in TMEM;
-// P goes back through 128B-swizzled shared memory as the A operand of the PV MMA; V is consumed MN-major so no
-// transpose is ever written.
+// query tiles of 128 rows.  Everything between QK^T and PV stays on chip and never touches shared memory:
+//   S (fp32) and O (fp32) are TMEM accumulators, and P (bf16) goes back into TMEM with tcgen05.st and is consumed as
+//   the A operand of the PV MMA straight from there (V is the MN-major B operand, so no transpose is ever written).
+// Warp roles: warp 0 TMA producer; warps 1 / 2 PV issuers of softmax group 0 / 1 (one thread each, blocking on that
+// group's barriers so a ready P is consumed at once); warp 3 QK^T issuer of both groups; warps 4-7 / 8-11 two softmax
+// warpgroups (thread == query row == TMEM lane, no cross-thread reductions) that work on alternate query tiles.
+// TMEM columns of group g (256 each): S [0, KT) | P buffers [KT, KT + NPB * KT/2) | O [256 - HD, 256).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -30,6 +33,27 @@ constexpr int ATT_REGS_CTRL = 88;      // setmaxnreg for warps 0-3 (128 threads)
 constexpr int ATT_REGS_SOFTMAX = 208;  // 8 softmax warps: 128*88 + 256*208 = 64512 = 384 threads * 168 regs at launch
 
 enum { MODE_SWIN = 0, MODE_SEQ = 1 };
+
+#ifdef MV_ATT_TRACE
+// debug timeline: (tag, g, t, j, clock) records of block 0 -- writer threads (3 MMA issuers, row 0 of each softmax
+// group), each with a private region and counter (no atomics: a store costs the writer nothing but its issue slot)
+__device__ long long g_att_trace[5 * 2 * 4096];
+__device__ unsigned int g_att_trace_n[5];
+__device__ __forceinline__ void att_trace(unsigned int& i, int tag, int g, int t, int j) {
+  const long long clk = clock64();
+  if (blockIdx.x != 0) return;
+  const int w = tag >= 12 ? 2 + g : (tag >= 10 ? 4 : g);
+  if (i < 4096u) {
+    g_att_trace[(w * 4096 + i) * 2] = ((long long)tag << 48) | ((long long)g << 32) | ((long long)t << 16) | j;
+    g_att_trace[(w * 4096 + i) * 2 + 1] = clk;
+  }
+  ++i;
+  g_att_trace_n[w] = i;
+}
+#define ATT_TRACE(tag, g, t, j) att_trace(trace_i, tag, g, t, j)
+#else
+#define ATT_TRACE(tag, g, t, j)
+#endif
 
 struct AttnParams {
   int Nq, Nkv;            // tokens per window / sequence
@@ -51,13 +75,11 @@ struct AttnLayout {
   static constexpr int LAYOUT = (HD == 32) ? 4 : 2;           // UMMA layout_type
   static constexpr int SBO = 8 * ROW_BYTES;                   // 8-row core-matrix group
   static constexpr int Q_BYTES = ATT_BM * ROW_BYTES;
-  static constexpr int P_BYTES = ATT_BM * 128 * 2;            // 2 chunks of [128 rows x 128 B]
 };
 
 __host__ __device__ constexpr int att_smem_bytes(int HD, int KT, int nkt, int table_floats) {
   return 2 * nkt * KT * HD * 2      // K, V
          + 2 * ATT_BM * HD * 2      // Q x2
-         + 2 * ATT_BM * 128 * 2     // P x2
          + ((table_floats * 4 + 1023) / 1024) * 1024 + 512 /*barriers*/ + 1024 /*align*/;
 }
 
@@ -68,6 +90,67 @@ __host__ __device__ constexpr int att_tab_stride(int ws) {
   int s = 2 * ws - 1;
   while ((s + ws) % 32 != 0) ++s;
   return s;
+}
+
+// packed fp32x2 arithmetic (sm_100: FADD2 issues one instruction for two lanes of work)
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void unpack2u(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]; issued by ONE thread.  A: 128 lanes x (K/2) 32-bit columns, two consecutive
+// K elements per cell (lower k in the lower half).
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8p(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 
 template <int MODE, int HD, int WS, int KT, bool QK_FP16>
@@ -81,8 +164,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int ROWS_PER_TILE = (MODE == MODE_SWIN) ? KT / WS : 1;
   constexpr int SPLIT = WS - WS / 2;                 // first column / row of the "shifted-in" band
   constexpr int NSEG = (MODE == MODE_SWIN) ? ROWS_PER_TILE * 2 : 4;     // independent max chains
+  constexpr int NCH = KT / 8;                        // 8-column chunks
+  constexpr int PW = KT / 2;                         // 32-bit TMEM columns of one P tile (two bf16 per cell)
+  constexpr int NPB = (KT + 2 * PW + HD <= 256) ? 2 : 1;                // P buffers per group
+  constexpr int COL_P = KT, COL_O = 256 - HD;
   static_assert(MODE != MODE_SWIN || KT % WS == 0, "kv tile must hold whole window rows");
   static_assert(KT % 16 == 0 && KT <= 128, "kv tile");
+  static_assert(KT + NPB * PW + HD <= 256, "TMEM budget of one softmax group");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -105,22 +193,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sK = smem;
   uint8_t* sV = sK + nkt_all * KT * L::ROW_BYTES;
   uint8_t* sQ = sV + nkt_all * KT * L::ROW_BYTES;
-  uint8_t* sP = sQ + 2 * L::Q_BYTES;
-  float* sTab = reinterpret_cast<float*>(sP + 2 * L::P_BYTES);
+  float* sTab = reinterpret_cast<float*>(sQ + 2 * L::Q_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sTab) + ((TBL * 4 + 1023) / 1024) * 1024);
   uint64_t* k_full = bars;                    // [ATT_MAX_KT]
   uint64_t* v_full = k_full + ATT_MAX_KT;     // [ATT_MAX_KT]
   uint64_t* q_full = v_full + ATT_MAX_KT;     // [2]
-  uint64_t* q_empty = q_full + 2;
-  uint64_t* s_full = q_empty + 2;
-  uint64_t* s_free = s_full + 2;
-  uint64_t* p_full = s_free + 2;
-  uint64_t* pv_done = p_full + 2;
-  uint64_t* o_free = pv_done + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* q_empty = q_full + 2;             // [2]
+  uint64_t* s_full = q_empty + 2;             // [2]
+  uint64_t* s_free = s_full + 2;              // [2]
+  uint64_t* o_free = s_free + 2;              // [2]
+  uint64_t* p_full = o_free + 2;              // [2][2]  (group, buffer)
+  uint64_t* pv_done = p_full + 4;             // [2][2]
+  uint64_t* turn = pv_done + 4;               // [2]  exponential sweeps of the two groups alternate (ping-pong)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef MV_ATT_TRACE
+  unsigned int trace_i = 0;
+#endif
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ);
@@ -135,9 +226,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&q_empty[g], 1);
       mbar_init(&s_full[g], 1);
       mbar_init(&s_free[g], 128);
-      mbar_init(&p_full[g], 128);
-      mbar_init(&pv_done[g], 1);
       mbar_init(&o_free[g], 128);
+      mbar_init(&turn[g], 128);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&p_full[2 * g + b], 128);
+        mbar_init(&pv_done[2 * g + b], 1);
+      }
     }
     fence_barrier_init();
   }
@@ -154,11 +248,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;           // S[g] at columns g*128
-  const uint32_t tmem_O = tmem_base + 256;     // O[g] at columns 256 + g*64
 
   if (warp < 4) {
-    reg_dec<ATT_REGS_CTRL>();                  // producer / MMA / allocator warps need few registers
+    reg_dec<ATT_REGS_CTRL>();                  // producer / MMA warps need few registers
     if (warp == 0) {
       // =========================================== TMA producer ===========================================
       if (lane == 0) {
@@ -182,67 +274,82 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           load_q(g, t);
         }
       }
-    } else if (warp == 1) {
-      // ============================================ MMA issuer ============================================
+    } else if (warp == 3) {
+      // ======================================= QK^T issuer (both groups) =======================================
+      // S(t, j+1) may be issued as soon as the group has pulled S(t, j) into registers (s_free); it is not needed
+      // before that group finishes tile j, so one polling thread serves both groups.
       if (lane == 0) {
         constexpr uint32_t idesc_s =
             make_idesc_bf16(ATT_BM, KT, 0, 0) & ~((QK_FP16 ? 1u : 0u) * ((1u << 7) | (1u << 10)));
-        constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, HD, 0, 1);
-        const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK), v0 = smem_u32(sV), p0 = smem_u32(sP);
-        int s_count[2] = {0, 0};               // S tiles issued per group: S[g] is reused once its reader freed it
-        auto issue_s = [&](int g, int j, bool first_pass) {
-          if (s_count[g] > 0) mbar_wait(&s_free[g], (s_count[g] - 1) & 1, 26);
-          if (first_pass) mbar_wait(&k_full[j], 0, 21);
-          tc_fence_after();
+        const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
+        int s_t[2] = {0, 1}, s_j[2] = {0, 0}, s_count[2] = {0, 0};
+        uint32_t ph_q[2] = {0, 0};
+        long long t_last = clock64();
+        while (s_t[0] < nq || s_t[1] < nq) {
+          bool progress = false;
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {
-            const uint64_t ad = make_smem_desc(q0 + g * L::Q_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
-            const uint64_t bd = make_smem_desc(k0 + j * KT * L::ROW_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
-            umma_ss(tmem_S + g * 128, ad, bd, idesc_s, k != 0);
-          }
-          umma_commit(&s_full[g]);
-          ++s_count[g];
-        };
-        auto issue_pv = [&](int g, int j) {
-#pragma unroll
-          for (int s = 0; s < KT / 16; ++s) {
-            const uint64_t ad = make_smem_desc(p0 + g * L::P_BYTES + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024, 2);
-            const uint64_t bd = make_smem_desc(v0 + (j * KT + s * 16) * L::ROW_BYTES, 16, L::SBO, L::LAYOUT);
-            umma_ss(tmem_O + g * 64, ad, bd, idesc_pv, (j | s) != 0);
-          }
-          umma_commit(&pv_done[g]);
-        };
-        uint32_t ph_q[2] = {0, 0}, ph_p[2] = {0, 0}, ph_o[2] = {0, 0};
-        const int n_it = (nq + 1) >> 1;
-        for (int it = 0; it < n_it; ++it) {
-          const bool valid[2] = {true, 2 * it + 1 < nq};
           for (int g = 0; g < 2; ++g) {
-            if (!valid[g]) continue;
-            mbar_wait(&q_full[g], ph_q[g], 20);
-            ph_q[g] ^= 1;
-            issue_s(g, 0, it == 0);
-            if (nkt == 1) umma_commit(&q_empty[g]);
+            if (s_t[g] >= nq) continue;
+            const int j = s_j[g];
+            bool ready = (j != 0) || mbar_test_wait(&q_full[g], ph_q[g]);
+            if (ready && s_count[g] > 0) ready = mbar_test_wait(&s_free[g], (s_count[g] - 1) & 1);
+            if (ready && s_t[g] == g) ready = mbar_test_wait(&k_full[j], 0);
+            if (!ready) continue;
+            ATT_TRACE(10, g, s_t[g], j);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+              const uint64_t ad = make_smem_desc(q0 + g * L::Q_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
+              const uint64_t bd = make_smem_desc(k0 + j * KT * L::ROW_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
+              umma_ss(tmem_base + g * 256, ad, bd, idesc_s, k != 0);
+            }
+            umma_commit(&s_full[g]);
+            ATT_TRACE(11, g, s_t[g], j);
+            ++s_count[g];
+            if (j == 0) ph_q[g] ^= 1;
+            if (j + 1 == nkt) {
+              umma_commit(&q_empty[g]);          // last read of this Q tile is in flight
+              s_j[g] = 0;
+              s_t[g] += 2;
+            } else {
+              s_j[g] = j + 1;
+            }
+            progress = true;
           }
-          for (int j = 0; j < nkt; ++j) {
-            // S(j+1) goes out as soon as the softmax group has pulled S(j) into registers ...
-            for (int g = 0; g < 2; ++g) {
-              if (!valid[g] || j + 1 >= nkt) continue;
-              issue_s(g, j + 1, it == 0);
-              if (j + 2 == nkt) umma_commit(&q_empty[g]);   // last read of this Q tile is in flight
+          if (progress) {
+            t_last = clock64();
+          } else if (clock64() - t_last > MV_WATCHDOG_CYCLES) {
+            __trap();
+          }
+        }
+      }
+    } else {
+      // ========================================= PV issuer of group g =========================================
+      if (lane == 0) {
+        const int g = warp - 1;
+        constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, HD, 0, 1);
+        const uint32_t v0 = smem_u32(sV);
+        const uint32_t tO = tmem_base + g * 256 + COL_O;
+        uint32_t n = 0, ph_o = 0;
+        for (int t = g; t < nq; t += 2) {
+          for (int j = 0; j < nkt; ++j, ++n) {
+            const int b = n % NPB;
+            mbar_wait(&p_full[2 * g + b], (n / NPB) & 1, 22);
+            if (j == 0 && t != g) {
+              mbar_wait(&o_free[g], ph_o, 23);
+              ph_o ^= 1;
             }
-            // ... and P(j) V(j) once the group has written P(j)
-            for (int g = 0; g < 2; ++g) {
-              if (!valid[g]) continue;
-              mbar_wait(&p_full[g], ph_p[g], 22);
-              ph_p[g] ^= 1;
-              if (j == 0 && it > 0) {
-                mbar_wait(&o_free[g], ph_o[g], 23);
-                ph_o[g] ^= 1;
-              }
-              if (it == 0) mbar_wait(&v_full[j], 0, 24);
-              tc_fence_after();
-              issue_pv(g, j);
+            if (t == g) mbar_wait(&v_full[j], 0, 24);
+            ATT_TRACE(12, g, t, j);
+            tc_fence_after();
+            const uint32_t tP = tmem_base + g * 256 + COL_P + b * PW;
+#pragma unroll
+            for (int s = 0; s < KT / 16; ++s) {
+              const uint64_t bd = make_smem_desc(v0 + (j * KT + s * 16) * L::ROW_BYTES, 16, L::SBO, L::LAYOUT);
+              umma_ts(tO, tP + s * 8, bd, idesc_pv, (j | s) != 0);
             }
+            umma_commit(&pv_done[2 * g + b]);
+            ATT_TRACE(13, g, t, j);
           }
         }
       }
@@ -254,10 +361,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                       // row within the query tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem_S + g * 128 + lane_off;
-    const uint32_t tO = tmem_O + g * 64 + lane_off;
-    uint8_t* myP = sP + g * L::P_BYTES + r * 128;
-    uint32_t ph_s = 0, ph_pv = 0;
+    const uint32_t tS = tmem_base + g * 256 + lane_off;
+    const uint32_t tO = tS + COL_O;
+    uint32_t ph_s = 0;
+    uint32_t n = 0;                                          // kv tiles processed by this group (all query tiles)
 
     // window coordinates (MODE_SWIN)
     const int nWw = (MODE == MODE_SWIN) ? p.W / WS : 1;
@@ -267,6 +374,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool colflag = (MODE == MODE_SWIN) && p.shift > 0 && (wc == nWw - 1);
     const float NEG100 = -100.0f * 1.4426950408889634f;
     const float bmax = (MODE == MODE_SWIN) ? __ldg(p.bias_max + head) : 0.f;
+
+    // PV(m) of this group has retired (its P buffer is free again, O includes it)
+    auto wait_pv = [&](uint32_t m) { mbar_wait(&pv_done[2 * g + (m % NPB)], (m / NPB) & 1, 31); };
 
     for (int t = g; t < nq; t += 2) {
       const int i = t * ATT_BM + r;                          // slot inside the window / position in the sequence
@@ -278,14 +388,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const bool ri = hi >= SPLIT, ci = wi >= SPLIT;
       float m_run = -INFINITY;
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};                    // split row sum: four independent add chains
+      uint64_t ls[2] = {0ull, 0ull};                         // row sum as two packed fp32x2 accumulators
 
-      for (int j = 0; j < nkt; ++j) {
+      for (int j = 0; j < nkt; ++j, ++n) {
         const int ncols = min(KT, kv_valid - j * KT);        // valid kv columns in this tile
 
         // per-segment additive constants (shift mask) and bias-table row bases
         float cseg[NSEG];
-        int tb[ROWS_PER_TILE];
+        const float* tb[ROWS_PER_TILE];
 #pragma unroll
         for (int rr = 0; rr < ROWS_PER_TILE; ++rr) {
           if (MODE == MODE_SWIN) {
@@ -294,17 +404,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool rdiff = rowflag && ((hj >= SPLIT) != ri);
             cseg[2 * rr] = (rdiff || (colflag && ci)) ? NEG100 : 0.f;           // wj <  SPLIT
             cseg[2 * rr + 1] = (rdiff || (colflag && !ci)) ? NEG100 : 0.f;      // wj >= SPLIT
-            tb[rr] = (hi - hj + WS - 1) * TSTRIDE + (WS - 1 - wi);
+            tb[rr] = sTab + (hi - hj + WS - 1) * TSTRIDE + (WS - 1 - wi);
           } else {
             cseg[0] = 0.f;
-            tb[0] = 0;
+            tb[0] = nullptr;
           }
         }
 
-        // ---- pull the whole S row into registers, then hand the TMEM buffer back to the MMA warp ----
+        // ---- pull the whole S row into registers, then hand the TMEM buffer back to the QK^T issuer ----
+        if (r == 0) ATT_TRACE(0, g, t, j);
         mbar_wait(&s_full[g], ph_s, 30);
         ph_s ^= 1;
         tc_fence_after();
+        if (r == 0) ATT_TRACE(1, g, t, j);
         uint32_t sv[KT];
 #pragma unroll
         for (int c0 = 0; c0 < KT; c0 += 32) {
@@ -314,108 +426,127 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&s_free[g]);
+        if (r == 0) ATT_TRACE(2, g, t, j);
 
-        auto tile = [&](auto partial_c) {
-          constexpr bool PARTIAL = decltype(partial_c)::value;
-          // sweep 1: s += bias (all shared-memory loads of the tile are independent and issued back to back: no
-          // store sits between them, so the scheduler can keep dozens of LDS in flight)
-          if (MODE == MODE_SWIN) {
+        if (ncols < KT) {
 #pragma unroll
-            for (int c = 0; c < KT; ++c) {
-              const int rr = c / WS, wj = c % WS;
-              float s = __uint_as_float(sv[c]) + sTab[tb[rr] + wj];
-              if (PARTIAL) s = (c < ncols) ? s : -INFINITY;
-              sv[c] = __float_as_uint(s);
+          for (int c = 0; c < KT; ++c) sv[c] = (c < ncols) ? sv[c] : 0xff800000u;   // -inf
+        }
+        // sweep 1: reference point of the tile = max over the RAW scores per mask segment + segment constant + the
+        // head's largest bias.  It bounds the true row maximum from above by at most (max - min) of the bias table
+        // (<= 16 log2 e), so every 2^(.) below is <= 2^8 and the largest term of a row is >= 2^-32: an exact softmax
+        // (the reference point cancels in O / l) that does not touch the bias table before the exponentials.
+        float segmax[NSEG];
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) segmax[s] = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+          const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : (c & (NSEG - 1));
+          segmax[seg] = fmaxf(segmax[seg], __uint_as_float(sv[c]));
+        }
+        float m_tile = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) m_tile = fmaxf(m_tile, segmax[s] + ((MODE == MODE_SWIN) ? cseg[s] : 0.f));
+        m_tile += bmax;
+
+        // running reference with lazy rescale (only when it moves by more than 2^8)
+        const float m_new = fmaxf(m_run, m_tile);
+        const bool need = (j > 0) && (m_new > m_run + 8.0f);
+        if (j == 0) m_run = m_new;
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          wait_pv(n - 1);                                    // O holds every PV of this query tile issued so far
+          tc_fence_after();
+          const float f = need ? ex2_approx(m_run - m_new) : 1.0f;
+          if (need) m_run = m_new;
+          const uint64_t f2 = pack2f(f, f);
+          asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ls[0]) : "l"(f2));
+          asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ls[1]) : "l"(f2));
+#pragma unroll
+          for (int c0 = 0; c0 < HD; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * f);
+            tmem_st32(tO + c0, o);
+          }
+          tmem_st_wait();
+        }
+        if (r == 0) ATT_TRACE(3, g, t, j);
+
+        // sweep 2 (fused, software pipelined over 8-column chunks so no instruction waits on the one before it):
+        //   stage A  bias loads of chunk st          (LDS, conflict free by the table stride)
+        //   stage B  s + (cseg - m_run) + bias       (FADD2) of chunk st-1
+        //   stage C  2^(.)                           (MUFU)  of chunk st-2
+        //   stage D  row sum (FADD2) + bf16 pack     (F2FP)  of chunk st-3
+        // Masked / out-of-range columns carry -inf and come out as exactly 0.
+        float csm[NSEG];
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) csm[s] = ((MODE == MODE_SWIN) ? cseg[s] : 0.f) - m_run;
+        float bb[3][8];
+        uint32_t pw[PW];
+        // P goes to TMEM buffer n % NPB (A operand of the PV MMA) once PV(n - NPB) has released it; the stores are
+        // issued from inside the sweep as soon as a run of columns is complete, so only the last one is exposed
+        if (n >= (uint32_t)NPB) wait_pv(n - NPB);
+        tc_fence_after();
+        const uint32_t tP = tS + COL_P + (n % NPB) * PW;
+        // one-time stagger: group 1 starts its first sweep when group 0 is half way through its own, so the two
+        // groups' MUFU-heavy sweeps and their latency-bound TMEM / barrier phases interleave instead of coinciding
+        if (n == 0 && g == 1) mbar_wait(&turn[0], 0, 33);
+        if (r == 0) ATT_TRACE(6, g, t, j);
+#pragma unroll
+        for (int st = 0; st < NCH + 3; ++st) {
+          // one MUFU per slot, the other pipes' work of the neighbouring stages interleaved between them: the XU pipe
+          // takes a warp instruction every 8 cycles and issue is in order, so clustered MUFUs would block the rest
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (st >= 2 && st < NCH + 2) {                   // stage C
+              const int c = (st - 2) * 8 + q;
+              sv[c] = __float_as_uint(ex2_approx(__uint_as_float(sv[c])));
             }
-          } else if (PARTIAL) {
-#pragma unroll
-            for (int c = 0; c < KT; ++c) sv[c] = (c < ncols) ? sv[c] : 0xff800000u;   // -inf
-          }
-          // sweep 2: exact row max (segment constants added once per segment)
-          float segmax[NSEG];
-#pragma unroll
-          for (int s = 0; s < NSEG; ++s) segmax[s] = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < KT; ++c) {
-            const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : (c & (NSEG - 1));
-            segmax[seg] = fmaxf(segmax[seg], __uint_as_float(sv[c]));
-          }
-          float m_tile = -INFINITY;
-#pragma unroll
-          for (int s = 0; s < NSEG; ++s) m_tile = fmaxf(m_tile, segmax[s] + ((MODE == MODE_SWIN) ? cseg[s] : 0.f));
-
-          // running max with lazy rescale (only when the reference point moves by more than 2^8)
-          const float m_new = fmaxf(m_run, m_tile);
-          const bool need = (j > 0) && (m_new > m_run + 8.0f);
-          if (j == 0) m_run = m_new;
-          if (j > 0) {
-            mbar_wait(&pv_done[g], ph_pv, 31);               // PV(j-1) retired: P buffer free, O up to date
-            ph_pv ^= 1;
-            tc_fence_after();
-            if (__any_sync(0xffffffffu, need)) {
-              const float f = need ? ex2_approx(m_run - m_new) : 1.0f;
-              if (need) m_run = m_new;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) l4[q] *= f;
-#pragma unroll
-              for (int c0 = 0; c0 < HD; c0 += 32) {
-                uint32_t o[32];
-                tmem_ld32(tO + c0, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 32; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * f);
-                tmem_st32(tO + c0, o);
-              }
-              tmem_st_wait();
+            if (MODE == MODE_SWIN && st < NCH) {             // stage A
+              const int c = st * 8 + q;
+              bb[st % 3][q] = tb[c / WS][c % WS];
+            }
+            if (st >= 1 && st < NCH + 1 && (q & 1) == 0) {   // stage B
+              const int k = st - 1;
+              const int c = k * 8 + q;
+              const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : 0;
+              const int seg1 = (MODE == MODE_SWIN) ? (((c + 1) / WS) * 2 + (((c + 1) % WS) >= SPLIT ? 1 : 0)) : 0;
+              uint64_t x = add2(pack2u(sv[c], sv[c + 1]), pack2f(csm[seg], csm[seg1]));
+              if (MODE == MODE_SWIN) x = add2(x, pack2f(bb[k % 3][q], bb[k % 3][q + 1]));
+              unpack2u(x, sv[c], sv[c + 1]);
+            }
+            if (st >= 3 && (q & 1) == 1) {                   // stage D
+              const int c = (st - 3) * 8 + q - 1;
+              ls[(q >> 1) & 1] = add2(ls[(q >> 1) & 1], pack2u(sv[c], sv[c + 1]));
+              pw[c >> 1] = pack_bf16x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
             }
           }
-
-          // sweep 3: p = 2^(s + cseg - m_run); row sums; P -> 128B-swizzled shared memory (A operand of PV).
-          // Masked / out-of-range columns carry -inf and come out as exactly 0.
-          float csm[NSEG];
-#pragma unroll
-          for (int s = 0; s < NSEG; ++s) csm[s] = ((MODE == MODE_SWIN) ? cseg[s] : 0.f) - m_run;
-          // the exponentials are issued as one long run of independent MUFU ops (the XU pipe takes one warp
-          // instruction every 8 cycles; the other warpgroup's FADD / LDS / STS work fills the issue slots in between)
-#pragma unroll
-          for (int c = 0; c < KT; ++c) {
-            const int seg = (MODE == MODE_SWIN) ? ((c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0)) : 0;
-            sv[c] = __float_as_uint(__uint_as_float(sv[c]) + csm[seg]);
+          if (st == NCH / 2 && n == 0 && g == 0) mbar_arrive(&turn[0]);
+          if (st >= 3) {
+            // words [0, 4 (st - 2)) of pw are final: flush 32-, 16- and 8-column runs as they complete
+            constexpr int R32 = (PW / 32) * 32, R16 = R32 + ((PW - R32) / 16) * 16;
+            const int done = 4 * (st - 2);
+            if (done <= R32 && done % 32 == 0) tmem_st32p(tP + done - 32, pw + done - 32);
+            else if (done == R16 && R16 > R32) tmem_st16p(tP + R32, pw + R32);
+            else if (done == PW && PW > R16) tmem_st8p(tP + R16, pw + R16);
           }
-#pragma unroll
-          for (int c = 0; c < KT; ++c) sv[c] = __float_as_uint(ex2_approx(__uint_as_float(sv[c])));
-#pragma unroll
-          for (int c0 = 0; c0 < KT; c0 += 8) {
-            float pv[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float e = __uint_as_float(sv[c0 + q]);
-              l4[q & 3] += e;
-              pv[q] = e;
-            }
-            uint4 w;
-            w.x = pack_bf16x2(pv[0], pv[1]);
-            w.y = pack_bf16x2(pv[2], pv[3]);
-            w.z = pack_bf16x2(pv[4], pv[5]);
-            w.w = pack_bf16x2(pv[6], pv[7]);
-            // 8 columns = one 16-byte unit; unit u of row r sits at ((u ^ (r & 7)) * 16) inside its 128-byte row
-            const int chunk = c0 >> 6, unit = (c0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(myP + chunk * 16384 + ((unit ^ (r & 7)) << 4)) = w;
-          }
-        };
-        if (ncols < KT) tile(std::true_type{});
-        else tile(std::false_type{});
-
-        fence_proxy_async_smem();      // P (generic proxy) -> visible to the tensor core (async proxy)
-        tc_fence_before();             // orders our tcgen05.ld/st of S and O before the MMA warp's next issue
-        mbar_arrive(&p_full[g]);
+        }
+        if (r == 0) ATT_TRACE(4, g, t, j);
+        tmem_st_wait();
+        tc_fence_before();             // orders our tcgen05.ld/st before the issuer's MMA
+        mbar_arrive(&p_full[2 * g + (n % NPB)]);
+        if (r == 0) ATT_TRACE(7, g, t, j);
       }
 
       // ---- epilogue: O / l -> bf16, token-major store ----
-      mbar_wait(&pv_done[g], ph_pv, 32);
-      ph_pv ^= 1;
+      wait_pv(n - 1);
       tc_fence_after();
-      const float inv = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+      float l0, l1, l2, l3;
+      unpack2f(ls[0], l0, l1);
+      unpack2f(ls[1], l2, l3);
+      const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
       size_t orow;
       if (MODE == MODE_SWIN) {
         const int hl = i / WS, wl = i - hl * WS;
@@ -552,6 +683,25 @@ extern "C" int mvuld_cpb_table(const float* w1, const float* b1, const float* w2
   MV_LAUNCH_OK();
   return 0;
 }
+
+#ifdef MV_ATT_TRACE
+extern "C" int mvuld_debug_att_trace(long long* host_out, int max_records) {
+  unsigned int n[5] = {0, 0, 0, 0, 0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(n, g_att_trace_n, sizeof(n));
+  static long long tmp[5 * 2 * 4096];
+  cudaMemcpyFromSymbol(tmp, g_att_trace, sizeof(tmp));
+  int out = 0;
+  for (int w = 0; w < 5; ++w)
+    for (unsigned int i = 0; i < n[w] && i < 4096u && out < max_records; ++i, ++out) {
+      host_out[4 * out] = tmp[(w * 4096 + i) * 2];
+      host_out[4 * out + 1] = tmp[(w * 4096 + i) * 2 + 1];
+    }
+  unsigned int zero[5] = {0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_att_trace_n, zero, sizeof(zero));
+  return out;
+}
+#endif
 
 extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
                                            const float* bias_max, void* out, int B, int H, int W, int C, int nH, int ws,
