@@ -96,6 +96,9 @@ def work_of(name, args):
     if name == "mvuld_gemm_bf16":
         M, N, K = args["M"], args["N"], args["K"]
         return "gemm", 2.0 * M * N * K, 0.0
+    if name == "mvuld_gemm_ln_bf16":
+        M, N, K = args[4], args[5], args[6]
+        return "gemm", 2.0 * M * N * K, 0.0
     if name == "mvuld_swin_qkv":
         B, H, W, C = args[8], args[9], args[10], args[11]
         return "gemm", 2.0 * B * H * W * C * 3 * C, 0.0

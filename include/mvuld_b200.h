@@ -35,6 +35,15 @@ const char* mvuld_last_error(void);
 int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
                     const float* res_f32, int ldr, void* out_bf16, float* out_f32, int ldc, mvuld_stream_t stream);
 
+/* Dense layer fused with a full-row LayerNorm and the res-post-norm residual (tcgen05 GEMM whose fp32 accumulator row
+ * lives in the 512 TMEM columns; N in {128, 256, 512}):
+ *   x = shortcut + LayerNorm(A W^T + bias) * gamma + beta      shortcut (fp32 [M,N], may alias x32) and bias optional;
+ * outputs fp32 x32 and/or bf16 xb.  Replaces proj + norm1 + residual and fc2 + norm2 + residual of
+ * mvuld/models/swin_transformer_v2.py:177,301 and :30,304, and PatchMerging reduction + norm (:361-362). */
+int mvuld_gemm_ln_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                       const float* gamma, const float* beta, float eps, const float* shortcut_f32, float* x32,
+                       void* xb, mvuld_stream_t stream);
+
 /* SwinV2 qkv projection fused with: cat(q_bias, 0, v_bias), per-head L2 normalisation of q and k, the learnable
  * logit scale (qscale[h] = exp(min(logit_scale_h, ln 100)) * log2 e, folded into q), window partition and cyclic
  * shift (pure index math).  X bf16 [B*H*W, C]; q,k fp16 and v bf16, each [B*nW, nH, ws*ws, 32].

@@ -20,6 +20,7 @@ _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 # name -> argument ctypes (the stream argument is included); mirrors include/mvuld_b200.h
 SIGNATURES = {
     "mvuld_gemm_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P],
+    "mvuld_gemm_ln_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
     "mvuld_swin_qkv": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_heads_qkv": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "mvuld_cpb_table": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
@@ -73,6 +74,15 @@ def load() -> C.CDLL:
     return lib
 
 
+class _Raw:
+    """A tensor passed by base pointer only (row stride given separately, so it need not be contiguous)."""
+
+    def __init__(self, t: torch.Tensor):
+        if not t.is_cuda:
+            raise RuntimeError("mvuld_b200 kernels take CUDA tensors only (no CPU fallback)")
+        self.ptr = C.c_void_p(t.data_ptr())
+
+
 def _ptr(t: Optional[torch.Tensor]):
     if t is None:
         return None
@@ -93,7 +103,9 @@ def call(name: str, *args):
     lib = load()
     conv = []
     for a in args:
-        if isinstance(a, torch.Tensor) or a is None:
+        if isinstance(a, _Raw):
+            conv.append(a.ptr)
+        elif isinstance(a, torch.Tensor) or a is None:
             conv.append(_ptr(a))
         else:
             conv.append(a)
@@ -135,6 +147,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act=ACT_NONE, res=None, ou
     if rc != 0:
         raise RuntimeError(f"mvuld_gemm_bf16 failed (code {rc}): {lib.mvuld_last_error().decode()}")
     launch_count += 1
+
+
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, gamma, beta, eps: float, bias=None, shortcut=None, x32=None, xb=None):
+    """x = shortcut + LayerNorm(a @ w.T + bias) * gamma + beta  (N = w.shape[0] in {128, 256, 512})."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    for t in (shortcut, x32, xb):
+        assert t is None or (t.is_contiguous() and t.shape == (M, N))
+    call("mvuld_gemm_ln_bf16", _Raw(a), a.stride(0), _Raw(w), w.stride(0), M, N, K, bias, gamma, beta, float(eps),
+         shortcut, x32, xb)
 
 
 def csr_from_coo(src: torch.Tensor, dst: torch.Tensor, num_nodes: int):

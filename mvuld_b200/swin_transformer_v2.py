@@ -342,11 +342,19 @@ class SwinTransformerV2(nn.Module):
                           nH, ws, shift)
                 _lib.call("mvuld_swin_window_attention", q, k, v, blk["tab_rev"], blk["tab_max"], att, B, H, W, C, nH,
                           ws, shift)
-                _lib.gemm(att, blk["wproj"], bias=blk["bproj"], out_bf16=y)
-                _lib.call("mvuld_ln_rows", y, x32, blk["g1"], blk["b1"], x32, xb, M, C, float(blk["eps1"]), 1)
-                _lib.gemm(xb, blk["wfc1"], bias=blk["bfc1"], act=_lib.ACT_GELU, out_bf16=hid)
-                _lib.gemm(hid, blk["wfc2"], bias=blk["bfc2"], out_bf16=y)
-                _lib.call("mvuld_ln_rows", y, x32, blk["g2"], blk["b2"], x32, xb, M, C, float(blk["eps2"]), 1)
+                if C <= 256:      # GEMM + LayerNorm + residual in one kernel; at C = 512 the row fills all 512 TMEM
+                                  # columns, the epilogue cannot overlap the next tile, and two kernels are faster
+                    _lib.gemm_ln(att, blk["wproj"], blk["g1"], blk["b1"], blk["eps1"], bias=blk["bproj"], shortcut=x32,
+                                 x32=x32, xb=xb)
+                    _lib.gemm(xb, blk["wfc1"], bias=blk["bfc1"], act=_lib.ACT_GELU, out_bf16=hid)
+                    _lib.gemm_ln(hid, blk["wfc2"], blk["g2"], blk["b2"], blk["eps2"], bias=blk["bfc2"], shortcut=x32,
+                                 x32=x32, xb=xb)
+                else:
+                    _lib.gemm(att, blk["wproj"], bias=blk["bproj"], out_bf16=y)
+                    _lib.call("mvuld_ln_rows", y, x32, blk["g1"], blk["b1"], x32, xb, M, C, float(blk["eps1"]), 1)
+                    _lib.gemm(xb, blk["wfc1"], bias=blk["bfc1"], act=_lib.ACT_GELU, out_bf16=hid)
+                    _lib.gemm(hid, blk["wfc2"], bias=blk["bfc2"], out_bf16=y)
+                    _lib.call("mvuld_ln_rows", y, x32, blk["g2"], blk["b2"], x32, xb, M, C, float(blk["eps2"]), 1)
             if layer.downsample is not None:
                 mg = p["merge"][li]
                 H, W, C = mg["H"], mg["W"], mg["C"]
@@ -354,11 +362,14 @@ class SwinTransformerV2(nn.Module):
                 xb = w["xb"][:B * H * W * C].view(B * H * W, C)
                 gathered = w["mg"][:M2 * 4 * C].view(M2, 4 * C)
                 _lib.call("mvuld_patch_merge_gather", xb, gathered, B, H, W, C)
-                y = w["y"][:M2 * 2 * C].view(M2, 2 * C)
-                _lib.gemm(gathered, mg["w"], out_bf16=y)
                 x32 = w["x32"][:M2 * 2 * C].view(M2, 2 * C)
                 xb = w["xb"][:M2 * 2 * C].view(M2, 2 * C)
-                _lib.call("mvuld_ln_rows", y, None, mg["g"], mg["b"], x32, xb, M2, 2 * C, float(mg["eps"]), 0)
+                if 2 * C <= 512:
+                    _lib.gemm_ln(gathered, mg["w"], mg["g"], mg["b"], mg["eps"], x32=x32, xb=xb)
+                else:
+                    y = w["y"][:M2 * 2 * C].view(M2, 2 * C)
+                    _lib.gemm(gathered, mg["w"], out_bf16=y)
+                    _lib.call("mvuld_ln_rows", y, None, mg["g"], mg["b"], x32, xb, M2, 2 * C, float(mg["eps"]), 0)
         last = p["blocks"][-1]
         T, C = last["H"] * last["W"], last["C"]
         x32 = w["x32"][:B * T * C]

@@ -112,6 +112,29 @@ def test_gemm_epilogues():
     assert rel_err(bufb[:, :N], expect[:, :N]) < 5e-3 and float(bufb[:, N:].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("M,N,K,use_bias,use_res", [(300, 128, 128, True, True), (1000, 256, 1024, True, True),
+                                                     (777, 512, 512, True, True), (640, 512, 2048, False, False),
+                                                     (64, 256, 512, False, False)])
+def test_gemm_ln_rows(M, N, K, use_bias, use_res):
+    """proj / fc2 + LayerNorm + res-post-norm residual in one kernel (swin_transformer_v2.py:301,304,361-362)."""
+    g = gen(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g) * 0.3 if use_bias else None
+    gamma, beta = 1 + 0.1 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g) if use_res else None
+    lin = A.float() @ W.float().T + (bias if use_bias else 0)
+    ref = torch.nn.functional.layer_norm(lin, (N,), gamma, beta, 1e-5) + (res if use_res else 0)
+    x32 = res.clone().to(DEV) if use_res else torch.zeros(M, N, device=DEV)
+    xb = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    d = lambda t: None if t is None else t.to(DEV)
+    _lib.gemm_ln(A.to(DEV), W.to(DEV), d(gamma), d(beta), 1e-5, bias=d(bias), shortcut=x32 if use_res else None,
+                 x32=x32, xb=xb)                                     # shortcut aliases x32: in-place residual update
+    torch.cuda.synchronize()
+    assert rel_err(x32, ref) < 2e-5, rel_err(x32, ref)
+    assert rel_err(xb, ref) < 5e-3
+
+
 # --------------------------------------------------------------------------------------------------------
 # Swin qkv + window attention against the oracle's window_attention
 # --------------------------------------------------------------------------------------------------------
