@@ -298,6 +298,55 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float hx = 0.5f * x;
   return fmaf(fabsf(hx), erf_abs, hx);                 // 0.5 x (1 + erf(x / sqrt 2)), using x erf(|x|..) sign = |x|
 }
+// packed fp32x2 helpers (sm_100 FADD2 / FMUL2 / FFMA2: one issue slot for two lanes of work)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// two erf-GELUs at once (same polynomial as gelu_erf): 13 packed FMA-pipe instructions + 2 MUFU per pair
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t ax = f2_pack(fabsf(x0), fabsf(x1));
+  const uint64_t z = f2_mul(ax, f2_pack(0.70710678118654752f, 0.70710678118654752f));
+  uint64_t d = f2_fma(z, f2_pack(0.0000430638f, 0.0000430638f), f2_pack(0.0002765672f, 0.0002765672f));
+  d = f2_fma(z, d, f2_pack(0.0001520143f, 0.0001520143f));
+  d = f2_fma(z, d, f2_pack(0.0092705272f, 0.0092705272f));
+  d = f2_fma(z, d, f2_pack(0.0422820123f, 0.0422820123f));
+  d = f2_fma(z, d, f2_pack(0.0705230784f, 0.0705230784f));
+  d = f2_fma(z, d, f2_pack(1.0f, 1.0f));
+  d = f2_mul(d, d);
+  d = f2_mul(d, d);
+  d = f2_mul(d, d);
+  d = f2_mul(d, d);
+  float d0, d1;
+  f2_unpack(d, d0, d1);
+  const uint64_t r = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  // 0.5 x + 0.5 |x| (1 - r) = 0.5 x + 0.5 |x| - 0.5 |x| r
+  const uint64_t half = f2_pack(0.5f, 0.5f);
+  const uint64_t hax = f2_mul(ax, half);
+  const uint64_t base = f2_fma(x, half, hax);
+  const uint64_t res = f2_fma(f2_mul(hax, f2_pack(-1.0f, -1.0f)), r, base);
+  f2_unpack(res, x0, x1);
+}
 // ELU(alpha = 1) (F.elu, GraphModel.py:154,159,171,176,186-187)
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : ex2_approx(x * 1.4426950408889634f) - 1.0f; }
 

@@ -17,12 +17,15 @@ namespace mv {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int GEMM_EPI_WARPS = 8;   // two per TMEM lane quarter (16 warps measured 15 % slower on the GELU GEMMs: the
+                                    // register cap of 576 threads costs more than the extra latency hiding gains)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 // ------------------------------------------------------------------------------------------------
 // Epilogues.  Called once per (row, 32-column chunk) by the thread that owns the row.
 // ------------------------------------------------------------------------------------------------
 struct EpiGeneric {
+  static constexpr bool kStaged = false;
   const float* bias;   // [N] or null
   const float* res;    // fp32 [M, ldr] or null; added after the activation
   bf16* out_b;         // bf16 [M, ldc] or null
@@ -48,7 +51,7 @@ struct EpiGeneric {
     }
     if (act == 1) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      for (int i = 0; i < 32; i += 2) gelu_erf2(v[i], v[i + 1]);
     } else if (act == 2) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = elu1(v[i]);
@@ -91,11 +94,51 @@ struct EpiGeneric {
   }
 };
 
+// bias + activation -> bf16, written through shared memory and a TMA store.  The thread-per-row epilogues above store
+// 16 bytes per lane into 32 different rows per instruction (32 L1 transactions); for the K <= 512 layers (fc1, proj,
+// RoBERTa dense) that store stream, not the MMA, set the tile time.  Here each warp stages a [32 rows x 64 columns]
+// bf16 slab (128-byte rows, 128B-swizzled: conflict-free STS) and one lane hands it to the TMA engine, which also
+// clips the M / N tails.
+struct EpiBf16Tma {
+  static constexpr bool kStaged = true;
+  const float* bias;   // [N] or null
+  int act;             // 0 none, 1 GELU(erf), 2 ELU
+  int M, N;
+  // values of one 32-column chunk -> packed bf16 (16 words)
+  __device__ __forceinline__ void compute(int col0, const uint32_t (&r)[32], uint32_t (&w)[16]) const {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (bias) {
+      if (col0 + 32 <= N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+          v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (col0 + i < N) v[i] += bias[col0 + i];
+      }
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    } else if (act == 2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = elu1(v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  }
+};
+
 // SwinV2 qkv epilogue (swin_transformer_v2.py:147-157 + the window partition / cyclic shift of :276-286):
 //   + cat(q_bias, 0, v_bias); q,k L2-normalised per head (F.normalize eps 1e-12); q additionally scaled by
 //   exp(min(logit_scale, ln 100)) * log2(e) so the attention kernel's exp2 needs no multiply;
 //   rows scattered to window-major head-major [B*nW, nH, ws*ws, 32]; q,k stored fp16 (|q| <= 145), v bf16.
 struct EpiQkvSwin {
+  static constexpr bool kStaged = false;
   const float* q_bias;   // [C]
   const float* v_bias;   // [C]
   const float* qscale;   // [nH]
@@ -168,6 +211,7 @@ struct EpiQkvSwin {
 // columns [0,Hd) = query, [Hd,2Hd) = key, [2Hd,3Hd) = value; + bias; q scaled by log2(e)/sqrt(hd);
 // rows scattered to [B, nH, L, hd] (bf16).
 struct EpiQkvHeads {
+  static constexpr bool kStaged = false;
   const float* bias;   // [3*Hd]
   bf16* q;
   bf16* k;
@@ -211,21 +255,23 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment
+  static constexpr int SLAB_BYTES = 32 * 128;                                  // [32 rows x 64 bf16] per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * SLAB_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;                                    // 256 or 512 (power of two)
 };
 
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               Epi epi) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
   using Cfg = GemmCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sC = smem + STAGES * Cfg::STAGE_BYTES;                       // staged epilogue slabs (kStaged only)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -305,7 +351,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which half of the tile's columns this warp drains
+    const int part = (warp - 2) >> 2;    // which slice of the tile's columns this warp drains
+    constexpr int PARTS = GEMM_EPI_WARPS / 4;
+    constexpr int CPP = (BN / 32) / PARTS;   // 32-column chunks per warp
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
@@ -314,16 +362,50 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int row = m_blk * GEMM_BM + quarter * 32 + lane;
       const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-        uint32_t r[32];
-        tmem_ld32(t0 + c * 32, r);
-        tmem_ld_wait();
-        epi(row, n_blk * BN + c * 32, r);
+      // the TMEM load of the next chunk is in flight while the epilogue math of this one runs
+      uint32_t r[2][32];
+      tmem_ld32(t0 + part * CPP * 32, r[0]);
+      if constexpr (Epi::kStaged) {
+        uint8_t* slab = sC + (warp - 2) * Cfg::SLAB_BYTES;
+        const int rl = lane;                                            // row inside this warp's slab
+#pragma unroll
+        for (int i = 0; i < CPP; ++i) {
+          const int c = part * CPP + i;
+          tmem_ld_wait();
+          if (i + 1 < CPP) tmem_ld32(t0 + (c + 1) * 32, r[(i + 1) & 1]);
+          uint32_t w[16];
+          epi.compute(n_blk * BN + c * 32, r[i & 1], w);
+          if ((i & 1) == 0) {
+            // the previous TMA store of this warp must have finished reading the slab
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)                                   // 16-byte unit (i & 1) * 4 + u of the 128-byte row
+            *reinterpret_cast<uint4*>(slab + rl * 128 + (((((i & 1) << 2) + u) ^ (rl & 7)) << 4)) =
+                make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+          if ((i & 1) == 1 || i + 1 == CPP) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, slab, n_blk * BN + (c & ~1) * 32, m_blk * GEMM_BM + quarter * 32);
+              tma_store_commit();
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPP; ++i) {
+          const int c = part * CPP + i;
+          tmem_ld_wait();
+          if (i + 1 < CPP) tmem_ld32(t0 + (c + 1) * 32, r[(i + 1) & 1]);
+          epi(row, n_blk * BN + c * 32, r[i & 1]);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
     }
+    if (Epi::kStaged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
   }
   tc_fence_before();
   __syncthreads();
@@ -332,7 +414,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int BN, int STAGES, class Epi>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, void* out_bf16 = nullptr, int ldc = 0) {
   using Cfg = GemmCfg<BN, STAGES>;
   MV_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   MV_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements (16 B): %d %d", lda, ldw);
@@ -351,6 +433,14 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, in
     int rc = make_tmap_16b(&tmB, W, 2, dims, str, box, 128);
     if (rc) return rc;
   }
+  CUtensorMap tmC = tmA;          // placeholder for the thread-per-row epilogues (never dereferenced)
+  if (Epi::kStaged) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)ldc * 2};
+    uint32_t box[2] = {64, 32};
+    int rc = make_tmap_16b(&tmC, out_bf16, 2, dims, str, box, 128);
+    if (rc) return rc;
+  }
   auto kern = gemm_tn_kernel<BN, STAGES, Epi>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
@@ -359,7 +449,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, in
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -374,6 +464,13 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   MV_CHECK_ARG(out_bf16 || out_f32, "gemm: no output");
   MV_CHECK_ARG(ldc % 8 == 0, "gemm: ldc must be a multiple of 8 elements");
   MV_CHECK_ARG(!res_f32 || ldr % 4 == 0, "gemm: ldr must be a multiple of 4 elements");
+  const bool big = (N % 256 == 0 && (long long)M * N >= 256ll * 256 * 148);
+  if (out_bf16 && !out_f32 && !res_f32 && ((uintptr_t)out_bf16 % 16) == 0) {
+    EpiBf16Tma t;
+    t.bias = bias; t.act = act; t.M = M; t.N = N;
+    if (big) return launch_gemm<256, 4, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
+    return launch_gemm<128, 6, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
+  }
   EpiGeneric e;
   e.bias = bias; e.res = res_f32; e.out_b = reinterpret_cast<bf16*>(out_bf16); e.out_f = out_f32;
   e.ldr = ldr; e.ldc = ldc; e.act = act; e.M = M; e.N = N;
