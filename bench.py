@@ -28,6 +28,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout; rank 0 prints ONE JSON line there
 
 import torch  # noqa: E402
 

@@ -156,6 +156,63 @@ int mvuld_fusion_head(const float* z, const float* img, const float* txt, const 
 int mvuld_linear_small(const float* x, const float* w, const float* b, float* out, float* out_sigmoid, int M, int N,
                        int K, mvuld_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step of the fusion model (mvuld/main_bigvul.py:294-342 drives GraphModel.py:150-211 in train mode with
+ * CrossEntropyLoss, clip_grad_norm_(5.0) and AdamW).  Dense backward passes reuse mvuld_gemm_bf16 on transposed
+ * operands; these entry points are the non-GEMM pieces.  Activation gradients bf16 / fp32, parameter gradients fp32
+ * (accumulated: callers zero them once per step).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* out[c, r] = in[r, c] (bf16), out row stride ldo >= R with zero fill: operand transposes of dW = dY^T X. */
+int mvuld_transpose_bf16(const void* in, void* out, int R, int C, int ldo, mvuld_stream_t stream);
+/* out[c] += sum_r x[r, c] (bias gradients); x bf16 (is_bf16 != 0) or fp32. */
+int mvuld_colsum(const void* x, int is_bf16, float* out, int R, int C, mvuld_stream_t stream);
+/* dx = dy * ELU'(pre) through y = dropout(ELU(pre), p) with the mask regenerated from seed (F.elu + nn.Dropout,
+ * GraphModel.py:171,176); is_f32 selects fp32 tensors (no dropout). */
+int mvuld_elu_bwd(const void* dy, const void* y, void* dx, long long n, int is_f32, unsigned long long seed, float p,
+                  mvuld_stream_t stream);
+/* out = mask(seed) * x / (1 - p), bf16: nn.Dropout forward, and the backward of GATConv's feat_drop. */
+int mvuld_dropout_bf16(const void* x, void* out, long long n, unsigned long long seed, float p, mvuld_stream_t stream);
+/* BatchNorm1d in training mode over the rows of x fp32 [R, C] (swinbn, bn_text, final_fc_bn, Rs_GCN W[1]):
+ * saves mean / rstd, updates the running statistics when given. */
+int mvuld_bn_cols_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, void* yb,
+                      float* mean, float* rstd, float* run_mean, float* run_var, float momentum, int R, int C,
+                      mvuld_stream_t stream);
+int mvuld_bn_cols_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd,
+                      float* dx32, void* dxb, float* dgamma, float* dbeta, int R, int C, mvuld_stream_t stream);
+/* BatchNorm1d(max_node) over the node-slot axis of x bf16 [B, n, F] (bn_gat / bn_bbox, GraphModel.py:135,186). */
+int mvuld_bn_slot_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                      float* rstd, float* run_mean, float* run_var, float momentum, int B, int n, int F,
+                      mvuld_stream_t stream);
+int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
+                      void* dx, float* dgamma, float* dbeta, int B, int n, int F, mvuld_stream_t stream);
+/* backward of unbatch_features pad / truncate (GraphModel.py:30-54). */
+int mvuld_unbatch_pad_bwd(const void* dhp, const long long* offsets, void* dh, int B, int max_node, int F,
+                          mvuld_stream_t stream);
+/* GATConv backward: edge-softmax backward per destination (in-CSR), gather over out-edges per source (out-CSR sorted
+ * by src, pos_in[k] = in-CSR position of out-edge k), attention vector gradients (accumulated).  Scratch: alpha_e,
+ * ds_e fp32 [E, H]; del, der fp32 [N, H]. */
+int mvuld_gat_bwd(const void* z, const void* dout, const float* el, const float* er, const int* indptr,
+                  const int* idx_src, const int* out_indptr, const int* out_dst, const int* pos_in,
+                  const float* attn_l, const float* attn_r, float* alpha_e, float* ds_e, float* del, float* der,
+                  void* dz, float* dattn_l, float* dattn_r, int N, int H, int F, float slope, mvuld_stream_t stream);
+/* Rs_GCN.py:57-66 backward: dtpg = (dtheta | dphi | dg) from dy. */
+int mvuld_rs_gcn_affinity_bwd(const void* tpg, const void* dy, void* dtpg, int B, int n, int C, mvuld_stream_t stream);
+/* l2norm over the node axis + node mean (GraphModel.py:200-204), forward into a strided feature row, and backward. */
+int mvuld_l2norm_mean_fwd(const float* z, float* out, int ldo, float* inv_s, int B, int n, int D, mvuld_stream_t stream);
+int mvuld_l2norm_mean_bwd(const float* z, const float* inv_s, const float* dm, int ldm, float* dz32, void* dzb, int B,
+                          int n, int D, mvuld_stream_t stream);
+/* CrossEntropyLoss (main_bigvul.py:298,332): loss_sum += scale * sum CE; dlogits = scale * (softmax - onehot). */
+int mvuld_ce_loss(const float* logits, const long long* labels, float* loss_sum, float* dlogits, int B, int C,
+                  float scale, mvuld_stream_t stream);
+int mvuld_linear_small_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int M,
+                           int N, int K, mvuld_stream_t stream);
+/* out += sum x^2 (global gradient norm of clip_grad_norm_, utils_multi.py:233). */
+int mvuld_sumsq_f32(const float* x, long long n, float* out, mvuld_stream_t stream);
+/* clipped AdamW on a flat fp32 buffer with per-segment weight decay (optimizer.py:11-33: decay / no-decay groups). */
+int mvuld_adamw(float* p, const float* g, float* m, float* v, long long n, const long long* seg_end,
+                const float* seg_wd, int nseg, const float* gnorm_sq, float max_norm, float lr, float beta1,
+                float beta2, float eps, int step, mvuld_stream_t stream);
+
 /* Test hook: one TMA box per operand, nk tcgen05.mma K-steps, accumulator dumped (see csrc/probe.cu). */
 int mvuld_probe_umma(const void* A, int a_inner, int a_rows, int a_swizzle, const void* B, int b_inner, int b_rows,
                      int b_swizzle, int N, int nk, int a_step, int b_step, int a_lbo, int a_sbo, int a_layout,

@@ -47,12 +47,29 @@ SIGNATURES = {
     "mvuld_rs_gcn_affinity": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_fusion_head": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_transpose_bf16": [_P, _P, _I, _I, _I, _P],
+    "mvuld_colsum": [_P, _I, _P, _I, _I, _P],
+    "mvuld_elu_bwd": [_P, _P, _P, _LL, _I, C.c_ulonglong, _F, _P],
+    "mvuld_dropout_bf16": [_P, _P, _LL, C.c_ulonglong, _F, _P],
+    "mvuld_bn_cols_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _I, _I, _P],
+    "mvuld_bn_cols_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "mvuld_bn_slot_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
+    "mvuld_bn_slot_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_unbatch_pad_bwd": [_P, _P, _P, _I, _I, _I, _P],
+    "mvuld_gat_bwd": [_P] * 18 + [_I, _I, _I, _F, _P],
+    "mvuld_rs_gcn_affinity_bwd": [_P, _P, _P, _I, _I, _I, _P],
+    "mvuld_l2norm_mean_fwd": [_P, _P, _I, _P, _I, _I, _I, _P],
+    "mvuld_l2norm_mean_bwd": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
+    "mvuld_ce_loss": [_P, _P, _P, _P, _I, _I, _F, _P],
+    "mvuld_linear_small_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_sumsq_f32": [_P, _LL, _P, _P],
+    "mvuld_adamw": [_P, _P, _P, _P, _LL, _P, _P, _I, _P, _F, _F, _F, _F, _F, _I, _P],
     "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 13 + [_P, _P],
 }
 
 _lib = None
 launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5}
+_LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3}
 
 
 def load() -> C.CDLL:

@@ -1,0 +1,865 @@
+// Backward / optimiser kernels of the fusion model's training step (reference loop: mvuld/main_bigvul.py:294-342;
+// model: mvuld/models/GraphModel.py:150-211, mvuld/models/Rs_GCN.py:52-73, DGL GATConv).
+//
+// Every dense backward (dX = dY W, dW = dY^T X) runs on the tcgen05 GEMM of gemm.cu: the kernels here provide the
+// operand transposes, the bias / BatchNorm / activation / dropout backward passes, the sparse GATConv backward
+// (edge-softmax backward per destination, gather over out-edges per source), the Rs_GCN affinity backward, the
+// l2norm / mean / cross-entropy head, and the clipped AdamW update (optimizer.py:11-33, config.py:157).
+// Gradients of activations travel in bf16 (GEMM operands) or fp32 (residual stream, BatchNorm), parameter
+// gradients and optimiser state in fp32.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mv {
+
+// ------------------------------------------------ small utilities ------------------------------------------------
+// counter-based uniform in [0,1): one 32-bit mix of (seed, index); the backward pass regenerates the same mask
+__device__ __forceinline__ float u01(unsigned long long seed, unsigned long long idx) {
+  unsigned long long x = idx * 0x9E3779B97F4A7C15ull + seed;
+  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+  return (float)(unsigned int)(x >> 40) * (1.0f / 16777216.0f);
+}
+
+// out[c, r] = in[r, c]; out row stride ldo >= R, columns [R, ldo) zero filled (TMA strides need 16-byte multiples)
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int C, int ldo) {
+  __shared__ bf16 tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < ldo) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float ldf<bf16>(const bf16* p, size_t i) { return __bfloat162float(p[i]); }
+
+// out[c] (+)= sum_r x[r, c]; grid (C/32 column groups, row slabs), atomics across slabs
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int R, int C, int rows_per_block) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const int rbeg = blockIdx.y * rows_per_block, rend = min(R, rbeg + rows_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (int r = rbeg + ry; r < rend; r += 8) s += ldf<T>(x, (size_t)r * C + c);
+  part[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// activation backward through y = dropout(elu(pre)):  kept elements carry elu(pre) / (1 - p)
+__global__ void elu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ dx,
+                               long long n, unsigned long long seed, float p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = __bfloat162float(dy[i]);
+  float e = __bfloat162float(y[i]);
+  if (p > 0.f) {
+    const bool keep = u01(seed, (unsigned long long)i) >= p;
+    const float inv = 1.0f / (1.0f - p);
+    g = keep ? g * inv : 0.f;
+    e = e * (1.0f - p);                     // elu(pre) of a kept element (dropped ones have g == 0 anyway)
+  }
+  dx[i] = __float2bfloat16(g * (e > 0.f ? 1.0f : e + 1.0f));
+}
+__global__ void elu_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                   long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float e = y[i];
+  dx[i] = dy[i] * (e > 0.f ? 1.0f : e + 1.0f);
+}
+// out = mask * x / (1 - p)   (forward dropout, and the backward of a dropout applied to an input)
+__global__ void dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long n,
+                                    unsigned long long seed, float p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool keep = u01(seed, (unsigned long long)i) >= p;
+  out[i] = keep ? __float2bfloat16(__bfloat162float(x[i]) / (1.0f - p)) : __float2bfloat16(0.f);
+}
+
+// ------------------------------------------- BatchNorm over columns -------------------------------------------
+// x fp32 [R, C], statistics per column over the R rows (biased variance, F.batch_norm training semantics).
+// One block per 32 columns; 8 row lanes; two passes (mean, then centred second moment).
+__global__ void __launch_bounds__(256)
+bn_cols_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, float* __restrict__ y32, bf16* __restrict__ yb, float* __restrict__ mean_out,
+                   float* __restrict__ rstd_out, float* __restrict__ run_mean, float* __restrict__ run_var,
+                   float momentum, int R, int C) {
+  __shared__ float part[8][33];
+  __shared__ float stat[2][32];
+  const int cl = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c < C)
+    for (int r = ry; r < R; r += 8) s += x[(size_t)r * C + c];
+  part[ry][cl] = s;
+  __syncthreads();
+  if (ry == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][cl];
+    stat[0][cl] = t / (float)R;
+  }
+  __syncthreads();
+  const float mean = stat[0][cl];
+  float q = 0.f;
+  if (c < C)
+    for (int r = ry; r < R; r += 8) {
+      const float d = x[(size_t)r * C + c] - mean;
+      q += d * d;
+    }
+  part[ry][cl] = q;
+  __syncthreads();
+  if (ry == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][cl];
+    const float var = t / (float)R;
+    stat[1][cl] = rsqrtf(var + eps);
+    if (c < C) {
+      mean_out[c] = mean;
+      rstd_out[c] = stat[1][cl];
+      if (run_mean) {                     // nn.BatchNorm1d running statistics (unbiased variance, momentum 0.1)
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * ((float)R / (float)max(R - 1, 1));
+      }
+    }
+  }
+  __syncthreads();
+  if (c >= C) return;
+  const float rstd = stat[1][cl], g = gamma[c], b = beta[c];
+  for (int r = ry; r < R; r += 8) {
+    const float v = (x[(size_t)r * C + c] - mean) * rstd * g + b;
+    if (y32) y32[(size_t)r * C + c] = v;
+    if (yb) yb[(size_t)r * C + c] = __float2bfloat16(v);
+  }
+}
+
+// dx = gamma rstd / R * (R dy - sum(dy) - xhat sum(dy xhat));  dgamma += sum(dy xhat);  dbeta += sum(dy)
+__global__ void __launch_bounds__(256)
+bn_cols_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx32,
+                   bf16* __restrict__ dxb, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
+  __shared__ float part[2][8][33];
+  __shared__ float tot[2][32];
+  const int cl = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const float m = c < C ? mean[c] : 0.f, rs = c < C ? rstd[c] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C)
+    for (int r = ry; r < R; r += 8) {
+      const float g = dy[(size_t)r * C + c];
+      s1 += g;
+      s2 += g * (x[(size_t)r * C + c] - m) * rs;
+    }
+  part[0][ry][cl] = s1;
+  part[1][ry][cl] = s2;
+  __syncthreads();
+  if (ry == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += part[0][k][cl]; b += part[1][k][cl]; }
+    tot[0][cl] = a;
+    tot[1][cl] = b;
+    if (c < C) {
+      dbeta[c] += a;
+      dgamma[c] += b;
+    }
+  }
+  __syncthreads();
+  if (c >= C || (!dx32 && !dxb)) return;
+  const float a = tot[0][cl], b = tot[1][cl], k = gamma[c] * rs / (float)R;
+  for (int r = ry; r < R; r += 8) {
+    const float xh = (x[(size_t)r * C + c] - m) * rs;
+    const float v = k * ((float)R * dy[(size_t)r * C + c] - a - xh * b);
+    if (dx32) dx32[(size_t)r * C + c] = v;
+    if (dxb) dxb[(size_t)r * C + c] = __float2bfloat16(v);
+  }
+}
+
+// --------------------------------- BatchNorm1d(max_node) over the node-slot axis ---------------------------------
+// x bf16 [B, n, F]: channel = slot r; statistics over the B * F values of the slot (GraphModel.py:135,186).
+// One block per slot.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+__global__ void __launch_bounds__(256)
+bn_slot_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                   float* __restrict__ run_mean, float* __restrict__ run_var, float momentum, int B, int n, int F) {
+  __shared__ float sh[8];
+  const int r = blockIdx.x;
+  const int cnt = B * F;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+    s += __bfloat162float(x[((size_t)(i / F) * n + r) * F + i % F]);
+  const float mean = block_sum(s, sh) / (float)cnt;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float d = __bfloat162float(x[((size_t)(i / F) * n + r) * F + i % F]) - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, sh) / (float)cnt;
+  const float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
+    if (run_mean) {
+      run_mean[r] = (1.f - momentum) * run_mean[r] + momentum * mean;
+      run_var[r] = (1.f - momentum) * run_var[r] + momentum * var * ((float)cnt / (float)max(cnt - 1, 1));
+    }
+  }
+  const float g = gamma[r], b = beta[r];
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const size_t o = ((size_t)(i / F) * n + r) * F + i % F;
+    y[o] = __float2bfloat16((__bfloat162float(x[o]) - mean) * rstd * g + b);
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_slot_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ gamma,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, bf16* __restrict__ dx,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int n, int F) {
+  __shared__ float sh[8];
+  const int r = blockIdx.x;
+  const int cnt = B * F;
+  const float m = mean[r], rs = rstd[r];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const size_t o = ((size_t)(i / F) * n + r) * F + i % F;
+    const float g = __bfloat162float(dy[o]);
+    s1 += g;
+    s2 += g * (__bfloat162float(x[o]) - m) * rs;
+  }
+  const float a = block_sum(s1, sh);
+  const float b = block_sum(s2, sh);
+  if (threadIdx.x == 0) {
+    dbeta[r] += a;
+    dgamma[r] += b;
+  }
+  if (!dx) return;
+  const float k = gamma[r] * rs / (float)cnt;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const size_t o = ((size_t)(i / F) * n + r) * F + i % F;
+    const float xh = (__bfloat162float(x[o]) - m) * rs;
+    dx[o] = __float2bfloat16(k * ((float)cnt * __bfloat162float(dy[o]) - a - xh * b));
+  }
+}
+
+// backward of unbatch_features pad / truncate (GraphModel.py:30-54): dh[node] = dhp[b, r] for r < max_node, else 0
+__global__ void unbatch_pad_bwd_kernel(const bf16* __restrict__ dhp, const long long* __restrict__ off,
+                                       bf16* __restrict__ dh, int B, int max_node, int F) {
+  const int b = blockIdx.y;
+  const long long beg = off[b], cnt = off[b + 1] - beg;
+  const int units = F >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt * units; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / units;
+    const int u = (int)(i % units);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < max_node) v = reinterpret_cast<const uint4*>(dhp + ((size_t)b * max_node + r) * F)[u];
+    reinterpret_cast<uint4*>(dh + (size_t)(beg + r) * F)[u] = v;
+  }
+}
+
+// ------------------------------------------------ GATConv backward ------------------------------------------------
+// Pass 1, one warp per destination v: recompute the edge softmax, a_e = <dout[v,h,:], z[u,h,:]>,
+// ds_e = alpha_e (a_e - sum alpha a) * leaky'(el[u] + er[v]); writes alpha and ds per in-CSR position and
+// der[v,h] = sum_e ds_e.  z, dout bf16 [N, H*F]; F % 256 == 0; H <= 4.
+template <int NH>
+__global__ void __launch_bounds__(128)
+gat_bwd_dst_kernel(const bf16* __restrict__ z, const bf16* __restrict__ dout, const float* __restrict__ el,
+                   const float* __restrict__ er, const int* __restrict__ indptr, const int* __restrict__ idx_src,
+                   float* __restrict__ alpha_e, float* __restrict__ ds_e, float* __restrict__ der, int N, int F,
+                   float slope) {
+  const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int lane = threadIdx.x & 31;
+  const int beg = __ldg(indptr + node), end = __ldg(indptr + node + 1);
+  float hmax[NH], hsum[NH], erd[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    hmax[h] = -INFINITY;
+    hsum[h] = 0.f;
+    erd[h] = __ldg(er + (size_t)node * NH + h);
+  }
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    const int s = e < end ? __ldg(idx_src + e) : 0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float sc = -INFINITY;
+      if (e < end) {
+        sc = __ldg(el + (size_t)s * NH + h) + erd[h];
+        sc = sc > 0.f ? sc : sc * slope;
+      }
+      hmax[h] = fmaxf(hmax[h], warp_max(sc));
+    }
+  }
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    const int s = e < end ? __ldg(idx_src + e) : 0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float pe = 0.f;
+      if (e < end) {
+        float sc = __ldg(el + (size_t)s * NH + h) + erd[h];
+        sc = sc > 0.f ? sc : sc * slope;
+        pe = __expf(sc - hmax[h]);
+      }
+      hsum[h] += warp_sum(pe);
+    }
+  }
+  // a_e per edge (warp-cooperative dot over the H*F row), accumulated t_h = sum alpha a
+  const int upr = F >> 3;                         // uint4 per head
+  float th[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) th[h] = 0.f;
+  const uint4* drow = reinterpret_cast<const uint4*>(dout + (size_t)node * NH * F);
+  for (int e = beg; e < end; ++e) {
+    const int s = __ldg(idx_src + e);
+    const uint4* zrow = reinterpret_cast<const uint4*>(z + (size_t)s * NH * F);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float a = 0.f;
+      for (int u = lane; u < upr; u += 32) {
+        const uint4 zv = __ldg(zrow + h * upr + u), dv = __ldg(drow + h * upr + u);
+        a += bf16_lo(zv.x) * bf16_lo(dv.x) + bf16_hi(zv.x) * bf16_hi(dv.x) + bf16_lo(zv.y) * bf16_lo(dv.y) +
+             bf16_hi(zv.y) * bf16_hi(dv.y) + bf16_lo(zv.z) * bf16_lo(dv.z) + bf16_hi(zv.z) * bf16_hi(dv.z) +
+             bf16_lo(zv.w) * bf16_lo(dv.w) + bf16_hi(zv.w) * bf16_hi(dv.w);
+      }
+      a = warp_sum(a);
+      float sc = __ldg(el + (size_t)s * NH + h) + erd[h];
+      sc = sc > 0.f ? sc : sc * slope;
+      const float al = __expf(sc - hmax[h]) / hsum[h];
+      th[h] += al * a;
+      if (lane == 0) {
+        alpha_e[(size_t)e * NH + h] = al;
+        ds_e[(size_t)e * NH + h] = a;             // a_e for now; turned into ds_e below
+      }
+    }
+  }
+  __syncwarp();
+  float dsum[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) dsum[h] = 0.f;
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    if (e < end) {
+      const int s = __ldg(idx_src + e);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float pre = __ldg(el + (size_t)s * NH + h) + erd[h];
+        const float d = alpha_e[(size_t)e * NH + h] * (ds_e[(size_t)e * NH + h] - th[h]) * (pre > 0.f ? 1.0f : slope);
+        ds_e[(size_t)e * NH + h] = d;
+        dsum[h] += d;
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const float t = warp_sum(dsum[h]);
+    if (lane == 0) der[(size_t)node * NH + h] = t;
+  }
+}
+
+// Pass 2, one warp per source u over its out-edges (out-CSR sorted by src; pos_in[k] = in-CSR position of out-edge k):
+//   dz[u,h,:] = sum_e alpha_e dout[dst_e,h,:] + del[u,h] attn_l[h,:] + der[u,h] attn_r[h,:],  del[u,h] = sum_e ds_e
+template <int NH>
+__global__ void __launch_bounds__(128)
+gat_bwd_src_kernel(const bf16* __restrict__ dout, const float* __restrict__ alpha_e, const float* __restrict__ ds_e,
+                   const float* __restrict__ der, const int* __restrict__ out_indptr, const int* __restrict__ out_dst,
+                   const int* __restrict__ pos_in, const float* __restrict__ attn_l, const float* __restrict__ attn_r,
+                   bf16* __restrict__ dz, float* __restrict__ del, int N, int F) {
+  const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (node >= N) return;
+  const int lane = threadIdx.x & 31;
+  const int beg = __ldg(out_indptr + node), end = __ldg(out_indptr + node + 1);
+  float dl[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) dl[h] = 0.f;
+  for (int base = beg; base < end; base += 32) {
+    const int k = base + lane;
+    if (k < end) {
+      const int pe = __ldg(pos_in + k);
+#pragma unroll
+      for (int h = 0; h < NH; ++h) dl[h] += __ldg(ds_e + (size_t)pe * NH + h);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    dl[h] = warp_sum(dl[h]);
+    if (lane == 0) del[(size_t)node * NH + h] = dl[h];
+  }
+  const int upr = F >> 3;
+  for (int h = 0; h < NH; ++h) {
+    const float drh = __ldg(der + (size_t)node * NH + h);
+    for (int u = lane; u < upr; u += 32) {
+      float acc[8];
+      const float4* lp = reinterpret_cast<const float4*>(attn_l + h * F + u * 8);
+      const float4* rp = reinterpret_cast<const float4*>(attn_r + h * F + u * 8);
+      const float4 l0 = __ldg(lp), l1 = __ldg(lp + 1), r0 = __ldg(rp), r1 = __ldg(rp + 1);
+      acc[0] = dl[h] * l0.x + drh * r0.x; acc[1] = dl[h] * l0.y + drh * r0.y;
+      acc[2] = dl[h] * l0.z + drh * r0.z; acc[3] = dl[h] * l0.w + drh * r0.w;
+      acc[4] = dl[h] * l1.x + drh * r1.x; acc[5] = dl[h] * l1.y + drh * r1.y;
+      acc[6] = dl[h] * l1.z + drh * r1.z; acc[7] = dl[h] * l1.w + drh * r1.w;
+      for (int k = beg; k < end; ++k) {
+        const int d = __ldg(out_dst + k);
+        const float al = __ldg(alpha_e + (size_t)__ldg(pos_in + k) * NH + h);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dout + (size_t)d * NH * F) + h * upr + u);
+        acc[0] += al * bf16_lo(v.x); acc[1] += al * bf16_hi(v.x); acc[2] += al * bf16_lo(v.y); acc[3] += al * bf16_hi(v.y);
+        acc[4] += al * bf16_lo(v.z); acc[5] += al * bf16_hi(v.z); acc[6] += al * bf16_lo(v.w); acc[7] += al * bf16_hi(v.w);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      reinterpret_cast<uint4*>(dz + (size_t)node * NH * F)[h * upr + u] = o;
+    }
+  }
+}
+
+// dattn_l[h,f] += sum_n del[n,h] z[n,h,f];  dattn_r likewise with der.  grid (H*F/256 chunks, node slabs)
+__global__ void __launch_bounds__(256)
+gat_attn_grad_kernel(const bf16* __restrict__ z, const float* __restrict__ del, const float* __restrict__ der,
+                     float* __restrict__ dal, float* __restrict__ dar, int N, int H, int F, int nodes_per_block) {
+  const int col = blockIdx.x * 256 + threadIdx.x;          // column of the H*F row
+  if (col >= H * F) return;
+  const int h = col / F;
+  const int nbeg = blockIdx.y * nodes_per_block, nend = min(N, nbeg + nodes_per_block);
+  float sl = 0.f, sr = 0.f;
+  for (int n = nbeg; n < nend; ++n) {
+    const float zv = __bfloat162float(z[(size_t)n * H * F + col]);
+    sl += __ldg(del + (size_t)n * H + h) * zv;
+    sr += __ldg(der + (size_t)n * H + h) * zv;
+  }
+  atomicAdd(dal + col, sl);
+  atomicAdd(dar + col, sr);
+}
+
+// --------------------------------------------- Rs_GCN affinity backward ---------------------------------------------
+// Per graph (n <= 100 slots, C features): theta, phi, g = column blocks of tpg bf16 [n, 3C]; dy bf16 [n, C].
+//   R = theta phi^T / n;  dg = R^T dy;  dS = dy g^T / n;  dtheta = dS phi;  dphi = dS^T theta   -> dtpg bf16 [n, 3C]
+constexpr int AB_N = 100;
+// S[i][j] = scale * sum_c X[i, c] Y[j, c]   (X, Y: bf16 rows with stride ld, C columns); 256 threads, 200 active
+__device__ void aff_nt(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ Y, int ldy, int n, int C,
+                       float scale, float* __restrict__ S, float* bufA, float* bufB) {
+  const int tid = threadIdx.x;
+  const int ti = tid / 10, tj = tid % 10;
+  float acc[5][10];
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int c = 0; c < 10; ++c) acc[a][c] = 0.f;
+  for (int k0 = 0; k0 < C; k0 += 32) {
+    for (int i = tid; i < AB_N * 8; i += 256) {
+      const int row = i >> 3, part = i & 7;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (row < n) {
+        const bf16* src = (part < 4 ? X + (size_t)row * ldx : Y + (size_t)row * ldy) + k0 + (part & 3) * 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(src);
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+      }
+      float* dstp = (part < 4 ? bufA : bufB) + row * 33 + (part & 3) * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dstp[q] = f[q];
+    }
+    __syncthreads();
+    if (tid < 200) {
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        float xa[5], yb[10];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) xa[a] = bufA[(ti * 5 + a) * 33 + k];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) yb[c] = bufB[(tj * 10 + c) * 33 + k];
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+          for (int c = 0; c < 10; ++c) acc[a][c] += xa[a] * yb[c];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 200) {
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int c = 0; c < 10; ++c) S[(ti * 5 + a) * (AB_N + 1) + tj * 10 + c] = acc[a][c] * scale;
+  }
+  __syncthreads();
+}
+// out[i, c] = sum_j (TRANS ? S[j][i] : S[i][j]) Y[j, c]   -> bf16 rows (stride ldo)
+template <bool TRANS>
+__device__ void aff_sy(const float* __restrict__ S, const bf16* __restrict__ Y, int ldy, int n, int C,
+                       bf16* __restrict__ out, int ldo, float* bufA) {
+  const int tid = threadIdx.x;
+  const int yi = tid / 8, yj = tid % 8;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    for (int i = tid; i < AB_N * 8; i += 256) {
+      const int row = i >> 3, part = i & 7;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (row < n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(Y + (size_t)row * ldy + c0 + part * 8);
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bufA[row * 64 + part * 8 + q] = f[q];
+    }
+    __syncthreads();
+    if (tid < 200) {
+      float o[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[a][q] = 0.f;
+      for (int j = 0; j < n; ++j) {
+        float rv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          rv[a] = TRANS ? S[j * (AB_N + 1) + yi * 4 + a] : S[(yi * 4 + a) * (AB_N + 1) + j];
+        const float4 g0 = *reinterpret_cast<const float4*>(bufA + j * 64 + yj * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(bufA + j * 64 + yj * 8 + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[a][q] += rv[a] * gv[q];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int row = yi * 4 + a;
+        if (row < n) {
+          uint4 w;
+          w.x = pack_bf16x2(o[a][0], o[a][1]); w.y = pack_bf16x2(o[a][2], o[a][3]);
+          w.z = pack_bf16x2(o[a][4], o[a][5]); w.w = pack_bf16x2(o[a][6], o[a][7]);
+          *reinterpret_cast<uint4*>(out + (size_t)row * ldo + c0 + yj * 8) = w;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256)
+rs_gcn_affinity_bwd_kernel(const bf16* __restrict__ tpg, const bf16* __restrict__ dy, bf16* __restrict__ dtpg, int n,
+                           int C) {
+  extern __shared__ float sm[];
+  float* R = sm;                                  // [AB_N][AB_N + 1]
+  float* dS = R + AB_N * (AB_N + 1);
+  float* bufA = dS + AB_N * (AB_N + 1);           // [AB_N][64]
+  float* bufB = bufA + AB_N * 64;                 // [AB_N][33]
+  const int b = blockIdx.x;
+  const bf16* th = tpg + (size_t)b * n * 3 * C;
+  const bf16* ph = th + C;
+  const bf16* gg = th + 2 * C;
+  const bf16* dyb = dy + (size_t)b * n * C;
+  bf16* dth = dtpg + (size_t)b * n * 3 * C;
+  const float inv = 1.0f / (float)n;
+  aff_nt(th, 3 * C, ph, 3 * C, n, C, inv, R, bufA, bufB);     // R  = theta phi^T / n
+  aff_nt(dyb, C, gg, 3 * C, n, C, inv, dS, bufA, bufB);       // dS = dy g^T / n
+  aff_sy<true>(R, dyb, C, n, C, dth + 2 * C, 3 * C, bufA);    // dg     = R^T dy
+  aff_sy<false>(dS, ph, 3 * C, n, C, dth, 3 * C, bufA);       // dtheta = dS phi
+  aff_sy<true>(dS, th, 3 * C, n, C, dth + C, 3 * C, bufA);    // dphi   = dS^T theta
+}
+
+// --------------------------------------- l2norm over the node axis + node mean ---------------------------------------
+// z fp32 [B, n, D] -> out[b, d] = mean_r z[b,r,d] / sqrt(sum_r z[b,r,d]^2)   (GraphModel.py:74-79,200-204; no eps);
+// out has row stride ldo (it is the middle third of the [B, 3D] feature row); inv_s[b,d] = 1 / sqrt(sum z^2)
+__global__ void l2norm_mean_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, int ldo,
+                                       float* __restrict__ inv_s, int n, int D) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float* zp = z + (size_t)b * n * D + d;
+  float s = 0.f, sq = 0.f;
+  for (int r = 0; r < n; ++r) {
+    const float v = zp[(size_t)r * D];
+    s += v;
+    sq += v * v;
+  }
+  const float is = rsqrtf(sq);
+  out[(size_t)b * ldo + d] = s * is / (float)n;
+  inv_s[(size_t)b * D + d] = is;
+}
+// y_r = z_r inv_s;  dy_r = dm / n;  dz_r = (dy_r - y_r sum_m dy_m y_m) inv_s = dm inv_s / n (1 - y_r sum_m y_m)
+__global__ void l2norm_mean_bwd_kernel(const float* __restrict__ z, const float* __restrict__ inv_s,
+                                       const float* __restrict__ dm, int ldm, float* __restrict__ dz32,
+                                       bf16* __restrict__ dzb, int n, int D) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float* zp = z + (size_t)b * n * D + d;
+  const float is = inv_s[(size_t)b * D + d];
+  float sy = 0.f;
+  for (int r = 0; r < n; ++r) sy += zp[(size_t)r * D] * is;
+  const float k = dm[(size_t)b * ldm + d] * is / (float)n;
+  for (int r = 0; r < n; ++r) {
+    const float v = k * (1.0f - zp[(size_t)r * D] * is * sy);
+    const size_t o = ((size_t)b * n + r) * D + d;
+    dz32[o] = v;
+    if (dzb) dzb[o] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------- cross entropy (mean) fwd + bwd -------------------------------------------
+// logits fp32 [B, C<=8], labels int64; loss_sum += sum_b CE_b * scale; dlogits = (softmax - onehot) * scale
+__global__ void ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                               float* __restrict__ loss_sum, float* __restrict__ dlogits, int B, int C, float scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, logits[(size_t)b * C + c]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(logits[(size_t)b * C + c] - m);
+  const int y = (int)labels[b];
+  const float lse = m + logf(s);
+  atomicAdd(loss_sum, (lse - logits[(size_t)b * C + y]) * scale);
+  for (int c = 0; c < C; ++c)
+    dlogits[(size_t)b * C + c] = (expf(logits[(size_t)b * C + c] - lse) - (c == y ? 1.f : 0.f)) * scale;
+}
+
+// small fp32 linear backward (heads): dX[M,K] = dY[M,N] W[N,K];  dW[N,K] += dY^T X;  db[N] += sum dY.   N <= 8
+__global__ void __launch_bounds__(256)
+linear_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dy,
+                        float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int M, int N, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) {
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int m = 0; m < M; ++m) acc += dy[(size_t)m * N + n] * x[(size_t)m * K + k];
+      dw[(size_t)n * K + k] += acc;
+    }
+    if (dx)
+      for (int m = 0; m < M; ++m) {
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc += dy[(size_t)m * N + n] * w[(size_t)n * K + k];
+        dx[(size_t)m * K + k] = acc;
+      }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < N) {
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) acc += dy[(size_t)m * N + threadIdx.x];
+    db[threadIdx.x] += acc;
+  }
+}
+
+// ------------------------------------------------ optimiser ------------------------------------------------
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    s += v * v;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+// AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments) on a flat fp32 parameter
+// buffer; gradients are first scaled by min(1, max_norm / (||g|| + 1e-6)) (clip_grad_norm_, utils_multi.py:233).
+// seg_end[k] / seg_wd[k]: exclusive end offset and weight decay of parameter segment k (no-decay group = 0).
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long long n, const long long* __restrict__ seg_end, const float* __restrict__ seg_wd, int nseg,
+             const float* __restrict__ gnorm_sq, float max_norm, float lr, float beta1, float beta2, float eps,
+             float bc1, float bc2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float clip = 1.0f;
+  if (max_norm > 0.f) {
+    const float gn = sqrtf(*gnorm_sq);
+    clip = fminf(1.0f, max_norm / (gn + 1e-6f));
+  }
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (i < seg_end[mid]) hi = mid; else lo = mid + 1;
+  }
+  const float wd = seg_wd[lo];
+  const float gi = g[i] * clip;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float pi = p[i] * (1.f - lr * wd);
+  pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  p[i] = pi;
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+#define GRID1(n, t) (unsigned)(((n) + (t) - 1) / (t))
+
+extern "C" int mvuld_transpose_bf16(const void* in, void* out, int R, int C, int ldo, cudaStream_t stream) {
+  MV_CHECK_ARG(ldo >= R, "transpose: ldo < R");
+  if (R <= 0 || C <= 0) return 0;
+  dim3 grid((C + 31) / 32, (ldo + 31) / 32), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), R, C, ldo);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_colsum(const void* x, int is_bf16, float* out, int R, int C, cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return 0;
+  const int rpb = 512;
+  dim3 grid((C + 31) / 32, (R + rpb - 1) / rpb);
+  if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), out, R, C, rpb);
+  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), out, R, C, rpb);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_elu_bwd(const void* dy, const void* y, void* dx, long long n, int is_f32, unsigned long long seed,
+                             float p, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (is_f32) elu_bwd_f32_kernel<<<GRID1(n, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(y), reinterpret_cast<float*>(dx), n);
+  else elu_bwd_kernel<<<GRID1(n, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(y), reinterpret_cast<bf16*>(dx), n, seed, p);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_dropout_bf16(const void* x, void* out, long long n, unsigned long long seed, float p,
+                                  cudaStream_t stream) {
+  MV_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1)");
+  if (n <= 0) return 0;
+  dropout_bf16_kernel<<<GRID1(n, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n, seed, p);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_bn_cols_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, void* yb,
+                                 float* mean, float* rstd, float* run_mean, float* run_var, float momentum, int R,
+                                 int C, cudaStream_t stream) {
+  MV_CHECK_ARG(R >= 1 && C >= 1, "bn_cols_fwd: empty");
+  bn_cols_fwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, gamma, beta, eps, y32, reinterpret_cast<bf16*>(yb), mean, rstd, run_mean, run_var, momentum, R, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_bn_cols_bwd(const float* x, const float* dy, const float* gamma, const float* mean,
+                                 const float* rstd, float* dx32, void* dxb, float* dgamma, float* dbeta, int R, int C,
+                                 cudaStream_t stream) {
+  bn_cols_bwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, dy, gamma, mean, rstd, dx32, reinterpret_cast<bf16*>(dxb), dgamma, dbeta, R, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_bn_slot_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
+                                 float* rstd, float* run_mean, float* run_var, float momentum, int B, int n, int F,
+                                 cudaStream_t stream) {
+  bn_slot_fwd_kernel<<<n, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), gamma, beta, eps, reinterpret_cast<bf16*>(y), mean, rstd, run_mean, run_var, momentum, B, n, F);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gamma, const float* mean,
+                                 const float* rstd, void* dx, float* dgamma, float* dbeta, int B, int n, int F,
+                                 cudaStream_t stream) {
+  bn_slot_bwd_kernel<<<n, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), gamma, mean, rstd, reinterpret_cast<bf16*>(dx), dgamma, dbeta, B, n, F);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_unbatch_pad_bwd(const void* dhp, const long long* offsets, void* dh, int B, int max_node, int F,
+                                     cudaStream_t stream) {
+  MV_CHECK_ARG(F % 8 == 0, "unbatch_pad_bwd: F %% 8");
+  if (B <= 0) return 0;
+  dim3 grid(64, B);
+  unbatch_pad_bwd_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dhp), offsets, reinterpret_cast<bf16*>(dh), B, max_node, F);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_gat_bwd(const void* z, const void* dout, const float* el, const float* er, const int* indptr,
+                             const int* idx_src, const int* out_indptr, const int* out_dst, const int* pos_in,
+                             const float* attn_l, const float* attn_r, float* alpha_e, float* ds_e, float* del,
+                             float* der, void* dz, float* dattn_l, float* dattn_r, int N, int H, int F, float slope,
+                             cudaStream_t stream) {
+  MV_CHECK_ARG(H == 4 && F % 256 == 0, "gat_bwd: H == 4 and F %% 256 == 0 (H=%d F=%d)", H, F);
+  if (N <= 0) return 0;
+  gat_bwd_dst_kernel<4><<<(N + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<const bf16*>(dout), el, er, indptr, idx_src, alpha_e, ds_e, der, N, F, slope);
+  MV_LAUNCH_OK();
+  gat_bwd_src_kernel<4><<<(N + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const bf16*>(dout), alpha_e, ds_e, der, out_indptr, out_dst, pos_in, attn_l, attn_r, reinterpret_cast<bf16*>(dz), del, N, F);
+  MV_LAUNCH_OK();
+  const int npb = 256;
+  dim3 grid((H * F + 255) / 256, (N + npb - 1) / npb);
+  gat_attn_grad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(z), del, der, dattn_l, dattn_r, N, H, F, npb);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_rs_gcn_affinity_bwd(const void* tpg, const void* dy, void* dtpg, int B, int n, int C,
+                                         cudaStream_t stream) {
+  MV_CHECK_ARG(n >= 1 && n <= AB_N && C % 64 == 0, "rs_gcn_affinity_bwd: n in [1, %d], C %% 64", AB_N);
+  if (B <= 0) return 0;
+  const int smem = (2 * AB_N * (AB_N + 1) + AB_N * 64 + AB_N * 33) * sizeof(float);
+  MV_CUDA_OK(cudaFuncSetAttribute(rs_gcn_affinity_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  rs_gcn_affinity_bwd_kernel<<<B, 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dtpg), n, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_l2norm_mean_fwd(const float* z, float* out, int ldo, float* inv_s, int B, int n, int D,
+                                     cudaStream_t stream) {
+  if (B <= 0) return 0;
+  dim3 grid((D + 127) / 128, B);
+  l2norm_mean_fwd_kernel<<<grid, 128, 0, stream>>>(z, out, ldo, inv_s, n, D);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_l2norm_mean_bwd(const float* z, const float* inv_s, const float* dm, int ldm, float* dz32,
+                                     void* dzb, int B, int n, int D, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  dim3 grid((D + 127) / 128, B);
+  l2norm_mean_bwd_kernel<<<grid, 128, 0, stream>>>(z, inv_s, dm, ldm, dz32, reinterpret_cast<bf16*>(dzb), n, D);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_ce_loss(const float* logits, const long long* labels, float* loss_sum, float* dlogits, int B,
+                             int C, float scale, cudaStream_t stream) {
+  MV_CHECK_ARG(C >= 1 && C <= 64, "ce_loss: C in [1, 64]");
+  if (B <= 0) return 0;
+  ce_loss_kernel<<<GRID1(B, 128), 128, 0, stream>>>(logits, labels, loss_sum, dlogits, B, C, scale);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_linear_small_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                                      int M, int N, int K, cudaStream_t stream) {
+  MV_CHECK_ARG(N >= 1 && N <= 8, "linear_small_bwd: N in [1, 8]");
+  if (M <= 0) return 0;
+  linear_small_bwd_kernel<<<GRID1(K, 256), 256, 0, stream>>>(x, w, dy, dx, dw, db, M, N, K);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_sumsq_f32(const float* x, long long n, float* out, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, out);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_adamw(float* p, const float* g, float* m, float* v, long long n, const long long* seg_end,
+                           const float* seg_wd, int nseg, const float* gnorm_sq, float max_norm, float lr, float beta1,
+                           float beta2, float eps, int step, cudaStream_t stream) {
+  MV_CHECK_ARG(nseg >= 1 && step >= 1, "adamw: nseg >= 1 and step >= 1");
+  if (n <= 0) return 0;
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_kernel<<<GRID1(n, 256), 256, 0, stream>>>(p, g, m, v, n, seg_end, seg_wd, nseg, gnorm_sq, max_norm, lr, beta1, beta2, eps, bc1, bc2);
+  MV_LAUNCH_OK();
+  return 0;
+}
