@@ -164,8 +164,8 @@ int mvuld_linear_small(const float* x, const float* w, const float* b, float* ou
  * ---------------------------------------------------------------------------------------------------------- */
 /* out[c, r] = in[r, c] (bf16), out row stride ldo >= R with zero fill: operand transposes of dW = dY^T X. */
 int mvuld_transpose_bf16(const void* in, void* out, int R, int C, int ldo, mvuld_stream_t stream);
-/* out[c] += sum_r x[r, c] (bias gradients); x bf16 (is_bf16 != 0) or fp32. */
-int mvuld_colsum(const void* x, int is_bf16, float* out, int R, int C, mvuld_stream_t stream);
+/* out[c] += sum_r x[r, c] (bias gradients); x bf16 (is_bf16 != 0) or fp32, row stride ldx >= C. */
+int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, int R, int C, mvuld_stream_t stream);
 /* dx = dy * ELU'(pre) through y = dropout(ELU(pre), p) with the mask regenerated from seed (F.elu + nn.Dropout,
  * GraphModel.py:171,176); is_f32 selects fp32 tensors (no dropout). */
 int mvuld_elu_bwd(const void* dy, const void* y, void* dx, long long n, int is_f32, unsigned long long seed, float p,
@@ -173,18 +173,33 @@ int mvuld_elu_bwd(const void* dy, const void* y, void* dx, long long n, int is_f
 /* out = mask(seed) * x / (1 - p), bf16: nn.Dropout forward, and the backward of GATConv's feat_drop. */
 int mvuld_dropout_bf16(const void* x, void* out, long long n, unsigned long long seed, float p, mvuld_stream_t stream);
 /* BatchNorm1d in training mode over the rows of x fp32 [R, C] (swinbn, bn_text, final_fc_bn, Rs_GCN W[1]):
- * saves mean / rstd, updates the running statistics when given. */
-int mvuld_bn_cols_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, void* yb,
-                      float* mean, float* rstd, float* run_mean, float* run_var, float momentum, int R, int C,
+ * saves mean / rstd, updates the running statistics when given; y32 (row stride ldy) = BN(x) + res (row stride ldr,
+ * optional: the Rs_GCN residual, Rs_GCN.py:70; may alias y32). */
+int mvuld_bn_cols_fwd(const float* x, const float* gamma, const float* beta, float eps, const float* res, int ldr,
+                      float* y32, int ldy, void* yb, float* mean, float* rstd, float* run_mean, float* run_var,
+                      float momentum, int R, int C, mvuld_stream_t stream);
+/* dy has row stride ldy (a column slice of the [B, 1536] feature row); x, dx32, dxb are dense [R, C]. */
+int mvuld_bn_cols_bwd(const float* x, const float* dy, int ldy, const float* gamma, const float* mean,
+                      const float* rstd, float* dx32, void* dxb, float* dgamma, float* dbeta, int R, int C,
                       mvuld_stream_t stream);
-int mvuld_bn_cols_bwd(const float* x, const float* dy, const float* gamma, const float* mean, const float* rstd,
-                      float* dx32, void* dxb, float* dgamma, float* dbeta, int R, int C, mvuld_stream_t stream);
 /* BatchNorm1d(max_node) over the node-slot axis of x bf16 [B, n, F] (bn_gat / bn_bbox, GraphModel.py:135,186). */
 int mvuld_bn_slot_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y, float* mean,
                       float* rstd, float* run_mean, float* run_var, float momentum, int B, int n, int F,
                       mvuld_stream_t stream);
 int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
                       void* dx, float* dgamma, float* dbeta, int B, int n, int F, mvuld_stream_t stream);
+/* fp32 strided ELU backward with a bf16 result (image / text projections, GraphModel.py:153-159). */
+int mvuld_elu_bwd_rows(const float* dy, int ldy, const float* y, int ldyy, void* dx, int ldx, int R, int C,
+                       mvuld_stream_t stream);
+/* bn_bbox (GraphModel.py:137,187) batch statistics of the padded [B, n, 4] box tensor -> the per-slot affine that
+ * mvuld_pos_branch applies; and the backward of ELU(fc_bbox(bn_bbox(.))) (dpre = ELU-backpropagated bf16 columns
+ * [col0, col0 + OUT) of a [B*n, ld] gradient), accumulating dW [OUT, 4], db, dgamma, dbeta. */
+int mvuld_pos_slot_stats(const float* pos, const long long* offsets, const float* gamma, const float* beta, float eps,
+                         float* scale, float* shift, float* mean, float* rstd, float* run_mean, float* run_var,
+                         float momentum, int B, int n, mvuld_stream_t stream);
+int mvuld_pos_branch_bwd(const float* pos, const long long* offsets, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, const float* w, const void* dpre, float* dw, float* db,
+                         float* dgamma, float* dbeta, int B, int n, int OUT, int ld, int col0, mvuld_stream_t stream);
 /* backward of unbatch_features pad / truncate (GraphModel.py:30-54). */
 int mvuld_unbatch_pad_bwd(const void* dhp, const long long* offsets, void* dh, int B, int max_node, int F,
                           mvuld_stream_t stream);

@@ -48,11 +48,14 @@ SIGNATURES = {
     "mvuld_fusion_head": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_transpose_bf16": [_P, _P, _I, _I, _I, _P],
-    "mvuld_colsum": [_P, _I, _P, _I, _I, _P],
+    "mvuld_colsum": [_P, _I, _I, _P, _I, _I, _P],
     "mvuld_elu_bwd": [_P, _P, _P, _LL, _I, C.c_ulonglong, _F, _P],
     "mvuld_dropout_bf16": [_P, _P, _LL, C.c_ulonglong, _F, _P],
-    "mvuld_bn_cols_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _I, _I, _P],
-    "mvuld_bn_cols_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "mvuld_bn_cols_fwd": [_P, _P, _P, _F, _P, _I, _P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P],
+    "mvuld_bn_cols_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "mvuld_elu_bwd_rows": [_P, _I, _P, _I, _P, _I, _I, _I, _P],
+    "mvuld_pos_slot_stats": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _I, _I, _P],
+    "mvuld_pos_branch_bwd": [_P] * 12 + [_I, _I, _I, _I, _I, _P],
     "mvuld_bn_slot_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
     "mvuld_bn_slot_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_unbatch_pad_bwd": [_P, _P, _P, _I, _I, _I, _P],

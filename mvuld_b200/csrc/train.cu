@@ -45,14 +45,14 @@ __device__ __forceinline__ float ldf<bf16>(const bf16* p, size_t i) { return __b
 // out[c] (+)= sum_r x[r, c]; grid (C/32 column groups, row slabs), atomics across slabs
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int R, int C, int rows_per_block) {
+colsum_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, int R, int C, int rows_per_block) {
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
   const int rbeg = blockIdx.y * rows_per_block, rend = min(R, rbeg + rows_per_block);
   float s = 0.f;
   if (c < C)
-    for (int r = rbeg + ry; r < rend; r += 8) s += ldf<T>(x, (size_t)r * C + c);
+    for (int r = rbeg + ry; r < rend; r += 8) s += ldf<T>(x, (size_t)r * ldx + c);
   part[ry][threadIdx.x & 31] = s;
   __syncthreads();
   if (ry == 0 && c < C) {
@@ -86,7 +86,7 @@ __global__ void elu_bwd_f32_kernel(const float* __restrict__ dy, const float* __
   dx[i] = dy[i] * (e > 0.f ? 1.0f : e + 1.0f);
 }
 // out = mask * x / (1 - p)   (forward dropout, and the backward of a dropout applied to an input)
-__global__ void dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long n,
+__global__ void dropout_bf16_kernel(const bf16* x, bf16* out, long long n,
                                     unsigned long long seed, float p) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -99,7 +99,8 @@ __global__ void dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict
 // One block per 32 columns; 8 row lanes; two passes (mean, then centred second moment).
 __global__ void __launch_bounds__(256)
 bn_cols_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float eps, float* __restrict__ y32, bf16* __restrict__ yb, float* __restrict__ mean_out,
+                   float eps, const float* res, int ldr, float* y32, int ldy, bf16* __restrict__ yb,
+                   float* __restrict__ mean_out,
                    float* __restrict__ rstd_out, float* __restrict__ run_mean, float* __restrict__ run_var,
                    float momentum, int R, int C) {
   __shared__ float part[8][33];
@@ -146,15 +147,16 @@ bn_cols_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   if (c >= C) return;
   const float rstd = stat[1][cl], g = gamma[c], b = beta[c];
   for (int r = ry; r < R; r += 8) {
-    const float v = (x[(size_t)r * C + c] - mean) * rstd * g + b;
-    if (y32) y32[(size_t)r * C + c] = v;
+    float v = (x[(size_t)r * C + c] - mean) * rstd * g + b;
+    if (res) v += res[(size_t)r * ldr + c];            // Rs_GCN.py:70: W_y + v (res may alias y32)
+    if (y32) y32[(size_t)r * ldy + c] = v;
     if (yb) yb[(size_t)r * C + c] = __float2bfloat16(v);
   }
 }
 
 // dx = gamma rstd / R * (R dy - sum(dy) - xhat sum(dy xhat));  dgamma += sum(dy xhat);  dbeta += sum(dy)
 __global__ void __launch_bounds__(256)
-bn_cols_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+bn_cols_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int ldy, const float* __restrict__ gamma,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx32,
                    bf16* __restrict__ dxb, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
   __shared__ float part[2][8][33];
@@ -165,7 +167,7 @@ bn_cols_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, co
   float s1 = 0.f, s2 = 0.f;
   if (c < C)
     for (int r = ry; r < R; r += 8) {
-      const float g = dy[(size_t)r * C + c];
+      const float g = dy[(size_t)r * ldy + c];
       s1 += g;
       s2 += g * (x[(size_t)r * C + c] - m) * rs;
     }
@@ -188,7 +190,7 @@ bn_cols_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, co
   const float a = tot[0][cl], b = tot[1][cl], k = gamma[c] * rs / (float)R;
   for (int r = ry; r < R; r += 8) {
     const float xh = (x[(size_t)r * C + c] - m) * rs;
-    const float v = k * ((float)R * dy[(size_t)r * C + c] - a - xh * b);
+    const float v = k * ((float)R * dy[(size_t)r * ldy + c] - a - xh * b);
     if (dx32) dx32[(size_t)r * C + c] = v;
     if (dxb) dxb[(size_t)r * C + c] = __float2bfloat16(v);
   }
@@ -266,6 +268,97 @@ bn_slot_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, cons
     const size_t o = ((size_t)(i / F) * n + r) * F + i % F;
     const float xh = (__bfloat162float(x[o]) - m) * rs;
     dx[o] = __float2bfloat16(k * ((float)cnt * __bfloat162float(dy[o]) - a - xh * b));
+  }
+}
+
+
+// strided fp32 ELU backward with a bf16 result: dx[r, c] = dy[r, c] * ELU'(pre) from y = ELU(pre)  (image / text
+// projections, GraphModel.py:153-159: dy and y are column slices of the [B, 1536] feature row)
+__global__ void elu_bwd_rows_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ y, int ldyy,
+                                    bf16* __restrict__ dx, int ldx, int R, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * C) return;
+  const int r = (int)(i / C), c = (int)(i % C);
+  const float e = y[(size_t)r * ldyy + c];
+  dx[(size_t)r * ldx + c] = __float2bfloat16(dy[(size_t)r * ldy + c] * (e > 0.f ? 1.0f : e + 1.0f));
+}
+
+// ------------------------------ bounding-box branch: BatchNorm1d(max_node) statistics ------------------------------
+// pos fp32 [N, 4] -> padded [B, n, 4] (zeros past a graph's node count, GraphModel.py:30-54); slot r's statistics run
+// over its B * 4 values (GraphModel.py:137,187).  Emits the affine (scale, shift) that mvuld_pos_branch applies.
+__global__ void __launch_bounds__(128)
+pos_slot_stats_kernel(const float* __restrict__ pos, const long long* __restrict__ off, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                      float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ run_mean,
+                      float* __restrict__ run_var, float momentum, int B, int n) {
+  __shared__ float sh[8];
+  const int r = blockIdx.x;
+  const int cnt = B * 4;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int b = i >> 2;
+    const long long beg = off[b], nn = off[b + 1] - beg;
+    s += r < nn ? pos[(beg + r) * 4 + (i & 3)] : 0.f;
+  }
+  const float mean = block_sum(s, sh) / (float)cnt;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int b = i >> 2;
+    const long long beg = off[b], nn = off[b + 1] - beg;
+    const float d = (r < nn ? pos[(beg + r) * 4 + (i & 3)] : 0.f) - mean;
+    q += d * d;
+  }
+  const float var = block_sum(q, sh) / (float)cnt;
+  if (threadIdx.x == 0) {
+    const float rstd = rsqrtf(var + eps);
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
+    scale[r] = gamma[r] * rstd;
+    shift[r] = beta[r] - mean * gamma[r] * rstd;
+    if (run_mean) {
+      run_mean[r] = (1.f - momentum) * run_mean[r] + momentum * mean;
+      run_var[r] = (1.f - momentum) * run_var[r] + momentum * var * ((float)cnt / (float)max(cnt - 1, 1));
+    }
+  }
+}
+// backward of ELU(fc_bbox(bn_bbox(pad(pos)))): dpre bf16 = columns [col0, col0 + 32) of the [B*n, ld] gradient (ELU'
+// already applied); accumulates dW [32, 4], db [32], dgamma [n], dbeta [n].  One block per slot, warp = 32 outputs.
+__global__ void __launch_bounds__(128)
+pos_branch_bwd_kernel(const float* __restrict__ pos, const long long* __restrict__ off, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ w, const bf16* __restrict__ dpre, float* __restrict__ dw,
+                      float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int n,
+                      int ld, int col0) {
+  const int r = blockIdx.x;
+  const int o = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const float m = mean[r], rs = rstd[r], ga = gamma[r], be = beta[r];
+  float wk[4], aw[4] = {0.f, 0.f, 0.f, 0.f}, ab = 0.f, ag = 0.f, abt = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wk[k] = w[o * 4 + k];
+  for (int b = q; b < B; b += 4) {
+    const long long beg = off[b], nn = off[b + 1] - beg;
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < nn) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(pos + (beg + r) * 4));
+      p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+    }
+    const float d = __bfloat162float(dpre[((size_t)b * n + r) * ld + col0 + o]);
+    ab += d;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (p[k] - m) * rs;
+      aw[k] += d * (xh * ga + be);
+      const float dxn = warp_sum(d * wk[k]);          // d L / d bn_out[b, r, k]
+      ag += dxn * xh;
+      abt += dxn;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) atomicAdd(dw + o * 4 + k, aw[k]);
+  atomicAdd(db + o, ab);
+  if (o == 0) {
+    atomicAdd(dgamma + r, ag);
+    atomicAdd(dbeta + r, abt);
   }
 }
 
@@ -723,12 +816,13 @@ extern "C" int mvuld_transpose_bf16(const void* in, void* out, int R, int C, int
   MV_LAUNCH_OK();
   return 0;
 }
-extern "C" int mvuld_colsum(const void* x, int is_bf16, float* out, int R, int C, cudaStream_t stream) {
+extern "C" int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, int R, int C, cudaStream_t stream) {
+  MV_CHECK_ARG(ldx >= C, "colsum: ldx < C");
   if (R <= 0 || C <= 0) return 0;
   const int rpb = 512;
   dim3 grid((C + 31) / 32, (R + rpb - 1) / rpb);
-  if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), out, R, C, rpb);
-  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), out, R, C, rpb);
+  if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, R, C, rpb);
+  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, out, R, C, rpb);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -748,18 +842,18 @@ extern "C" int mvuld_dropout_bf16(const void* x, void* out, long long n, unsigne
   MV_LAUNCH_OK();
   return 0;
 }
-extern "C" int mvuld_bn_cols_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, void* yb,
-                                 float* mean, float* rstd, float* run_mean, float* run_var, float momentum, int R,
-                                 int C, cudaStream_t stream) {
+extern "C" int mvuld_bn_cols_fwd(const float* x, const float* gamma, const float* beta, float eps, const float* res,
+                                 int ldr, float* y32, int ldy, void* yb, float* mean, float* rstd, float* run_mean,
+                                 float* run_var, float momentum, int R, int C, cudaStream_t stream) {
   MV_CHECK_ARG(R >= 1 && C >= 1, "bn_cols_fwd: empty");
-  bn_cols_fwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, gamma, beta, eps, y32, reinterpret_cast<bf16*>(yb), mean, rstd, run_mean, run_var, momentum, R, C);
+  bn_cols_fwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, gamma, beta, eps, res, ldr, y32, ldy, reinterpret_cast<bf16*>(yb), mean, rstd, run_mean, run_var, momentum, R, C);
   MV_LAUNCH_OK();
   return 0;
 }
-extern "C" int mvuld_bn_cols_bwd(const float* x, const float* dy, const float* gamma, const float* mean,
+extern "C" int mvuld_bn_cols_bwd(const float* x, const float* dy, int ldy, const float* gamma, const float* mean,
                                  const float* rstd, float* dx32, void* dxb, float* dgamma, float* dbeta, int R, int C,
                                  cudaStream_t stream) {
-  bn_cols_bwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, dy, gamma, mean, rstd, dx32, reinterpret_cast<bf16*>(dxb), dgamma, dbeta, R, C);
+  bn_cols_bwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, dy, ldy, gamma, mean, rstd, dx32, reinterpret_cast<bf16*>(dxb), dgamma, dbeta, R, C);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -774,6 +868,31 @@ extern "C" int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gam
                                  const float* rstd, void* dx, float* dgamma, float* dbeta, int B, int n, int F,
                                  cudaStream_t stream) {
   bn_slot_bwd_kernel<<<n, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), gamma, mean, rstd, reinterpret_cast<bf16*>(dx), dgamma, dbeta, B, n, F);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_elu_bwd_rows(const float* dy, int ldy, const float* y, int ldyy, void* dx, int ldx, int R, int C,
+                                  cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return 0;
+  elu_bwd_rows_kernel<<<GRID1((long long)R * C, 256), 256, 0, stream>>>(dy, ldy, y, ldyy, reinterpret_cast<bf16*>(dx), ldx, R, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_pos_slot_stats(const float* pos, const long long* offsets, const float* gamma, const float* beta,
+                                    float eps, float* scale, float* shift, float* mean, float* rstd, float* run_mean,
+                                    float* run_var, float momentum, int B, int n, cudaStream_t stream) {
+  MV_CHECK_ARG(B >= 1 && n >= 1, "pos_slot_stats: empty");
+  pos_slot_stats_kernel<<<n, 128, 0, stream>>>(pos, offsets, gamma, beta, eps, scale, shift, mean, rstd, run_mean, run_var, momentum, B, n);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_pos_branch_bwd(const float* pos, const long long* offsets, const float* mean, const float* rstd,
+                                    const float* gamma, const float* beta, const float* w, const void* dpre, float* dw,
+                                    float* db, float* dgamma, float* dbeta, int B, int n, int OUT, int ld, int col0,
+                                    cudaStream_t stream) {
+  MV_CHECK_ARG(OUT == 32, "pos_branch_bwd: fc_bbox has 32 outputs (got %d)", OUT);
+  if (B <= 0) return 0;
+  pos_branch_bwd_kernel<<<n, 128, 0, stream>>>(pos, offsets, mean, rstd, gamma, beta, w, reinterpret_cast<const bf16*>(dpre), dw, db, dgamma, dbeta, B, n, ld, col0);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -35,6 +35,7 @@ class Graph:
         self.ndata: Dict[str, torch.Tensor] = {}
         self.edata: Dict[str, torch.Tensor] = {}
         self._csr = None
+        self._ocsr = None
         self._offsets = None
 
     # ---- the DGLGraph members the reference uses ----
@@ -72,6 +73,7 @@ class Graph:
         g.ndata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.ndata.items()}
         g.edata = {k: v.to(device, non_blocking=non_blocking) for k, v in self.edata.items()}
         g._csr = None
+        g._ocsr = None
         g._offsets = None
         return g
 
@@ -90,6 +92,17 @@ class Graph:
             indptr, idx_src, eids, status = _lib.csr_from_coo(self._src, self._dst, self._num_nodes)
             self._csr = (indptr, idx_src, eids, status)
         return self._csr[:3]
+
+    def out_csr(self):
+        """Out-edge CSR for the backward pass of GATConv: (out_indptr int32 [N+1], out_dst int32 [E], pos_in int32 [E])
+        sorted by (src, in-CSR position); ``pos_in[k]`` is the in-CSR position of out-edge ``k`` (so per-edge values
+        stored in in-CSR order can be gathered per source)."""
+        if getattr(self, "_ocsr", None) is None:
+            _, idx_src, eids = self.in_csr()
+            dst_sorted = self._dst[eids.long()]                 # destination of each in-CSR position
+            out_indptr, out_dst, pos_in, _ = _lib.csr_from_coo(dst_sorted, idx_src.long(), self._num_nodes)
+            self._ocsr = (out_indptr, out_dst, pos_in)
+        return self._ocsr
 
     def check_status(self):
         """Raise if the CSR build saw an endpoint outside [0, N) (one small D2H read)."""

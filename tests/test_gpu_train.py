@@ -1,0 +1,360 @@
+"""GPU: the fusion model's training step (BASELINE.json configs[4]) against the fp32 autograd oracle.
+
+oracle/fusion_train.py restates main_bigvul.py:294-342 + GraphModel.py:150-211 in train mode with plain PyTorch fp32
+autograd on the CPU.  Tolerances: the loss and logits within 1e-2 relative (bf16 operands, north_star); parameter
+gradients by relative L2 error per tensor (bf16 operands in every product: a few 1e-2); BatchNorm running statistics
+and the AdamW update (fp32 arithmetic) to 1e-5.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import mvuld_b200 as mv                          # noqa: E402
+from mvuld_b200 import _lib, synth, train       # noqa: E402
+from oracle import fusion_train as otrain       # noqa: E402
+from tests import cases                          # noqa: E402
+
+DEV = "cuda"
+B_TRAIN = 6
+
+
+def rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def gen(seed=0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def _inputs(B=B_TRAIN, seed=cases.SEED):
+    g = synth.cpg_batch(B, seed=seed)
+    r = gen(seed + 9)
+    img, txt = torch.randn(B, 1024, generator=r), torch.randn(B, 768, generator=r) * 0.5
+    labels = torch.randint(0, 2, (B,), generator=r)
+    return g, img, txt, labels
+
+
+# --------------------------------------------------------------------------------------------------------
+# kernels
+# --------------------------------------------------------------------------------------------------------
+def test_transpose_and_colsum():
+    x = torch.randn(70, 200, generator=gen(1)).to(torch.bfloat16)
+    out = torch.empty(200, 72, dtype=torch.bfloat16, device=DEV)
+    _lib.call("mvuld_transpose_bf16", x.to(DEV), out, 70, 200, 72)
+    assert torch.equal(out[:, :70].cpu(), x.t())
+    assert float(out[:, 70:].float().abs().sum()) == 0.0
+    s = torch.zeros(200, device=DEV)
+    _lib.call("mvuld_colsum", x.to(DEV), 1, 200, s, 70, 200)
+    assert rel_err(s, x.float().sum(0)) < 1e-5
+    y = torch.randn(1000, 48, generator=gen(2))
+    s2 = torch.ones(40, device=DEV)
+    _lib.call("mvuld_colsum", y.to(DEV), 0, 48, s2, 1000, 40)            # strided: first 40 of 48 columns, accumulates
+    assert rel_err(s2, y[:, :40].sum(0) + 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("R,C", [(6, 1536), (600, 512)])
+def test_bn_cols_forward_backward(R, C):
+    r = gen(3)
+    x = torch.randn(R, C, generator=r) * 2 + 0.5
+    gamma, beta = torch.randn(C, generator=r) * 0.1 + 1, torch.randn(C, generator=r) * 0.1
+    dy = torch.randn(R, C, generator=r)
+    res = torch.randn(R, C, generator=r)
+    bn = torch.nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    xr = x.clone().requires_grad_(True)
+    yr = bn.train()(xr)
+    yr.backward(dy)
+    y32, yb = torch.empty(R, C, device=DEV), torch.empty(R, C, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    _lib.call("mvuld_bn_cols_fwd", x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5, res.to(DEV), C, y32, C, yb, mean, rstd,
+              rm, rv, 0.1, R, C)
+    assert rel_err(y32, yr.detach() + res) < 1e-5
+    assert rel_err(yb, yr.detach()) < 5e-3
+    assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+    dx, dxb = torch.empty(R, C, device=DEV), torch.empty(R, C, device=DEV, dtype=torch.bfloat16)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    _lib.call("mvuld_bn_cols_bwd", x.to(DEV), dy.to(DEV), C, gamma.to(DEV), mean, rstd, dx, dxb, dg, db, R, C)
+    assert rel_err(dx, xr.grad) < 1e-4
+    assert rel_err(dxb, xr.grad) < 5e-3
+    assert rel_err(dg, bn.weight.grad) < 1e-4 and rel_err(db, bn.bias.grad) < 1e-4
+
+
+def test_bn_slot_forward_backward():
+    B, n, Fd = 5, 100, 64
+    r = gen(4)
+    x = (torch.randn(B, n, Fd, generator=r) * 1.5).to(torch.bfloat16)
+    dy = torch.randn(B, n, Fd, generator=r).to(torch.bfloat16)
+    bn = torch.nn.BatchNorm1d(n)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(n, generator=r) * 0.1 + 1)
+        bn.bias.copy_(torch.randn(n, generator=r) * 0.1)
+    xr = x.float().requires_grad_(True)
+    yr = bn.train()(xr)
+    yr.backward(dy.float())
+    y = torch.empty(B, n, Fd, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(n, device=DEV), torch.empty(n, device=DEV)
+    rm, rv = torch.zeros(n, device=DEV), torch.ones(n, device=DEV)
+    w, b = bn.weight.detach().to(DEV), bn.bias.detach().to(DEV)
+    _lib.call("mvuld_bn_slot_fwd", x.to(DEV), w, b, 1e-5, y, mean, rstd, rm, rv, 0.1, B, n, Fd)
+    assert rel_err(y, yr.detach()) < 5e-3
+    assert rel_err(rm, bn.running_mean) < 1e-4 and rel_err(rv, bn.running_var) < 1e-4
+    dx = torch.empty(B, n, Fd, device=DEV, dtype=torch.bfloat16)
+    dg, db = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    _lib.call("mvuld_bn_slot_bwd", x.to(DEV), dy.to(DEV), w, mean, rstd, dx, dg, db, B, n, Fd)
+    assert rel_err(dx, xr.grad) < 6e-3
+    assert rel_err(dg, bn.weight.grad) < 1e-3 and rel_err(db, bn.bias.grad) < 1e-3
+
+
+def test_gat_backward_matches_autograd():
+    g = synth.cpg_batch(3, seed=5)
+    N, H, Fd = g.num_nodes(), 4, 512
+    r = gen(6)
+    z = (torch.randn(N, H * Fd, generator=r) * 0.3).to(torch.bfloat16)
+    dout = (torch.randn(N, H * Fd, generator=r) * 0.1).to(torch.bfloat16)
+    al, ar = torch.randn(H, Fd, generator=r) * 0.1, torch.randn(H, Fd, generator=r) * 0.1
+    src, dst = g.edges()
+    # autograd reference on the same (bf16-rounded) z
+    zr = z.float().view(N, H, Fd).requires_grad_(True)
+    alr, arr = al.clone().requires_grad_(True), ar.clone().requires_grad_(True)
+    el = (zr * alr).sum(-1)
+    er = (zr * arr).sum(-1)
+    e = F.leaky_relu(el[src] + er[dst], 0.2)
+    emax = torch.full((N, H), -float("inf")).scatter_reduce(0, dst[:, None].expand_as(e), e.detach(), "amax")
+    pexp = torch.exp(e - emax[dst])
+    den = torch.zeros(N, H).index_add(0, dst, pexp)
+    out = torch.zeros(N, H, Fd).index_add(0, dst, (pexp / den[dst])[..., None] * zr[src])
+    out.backward(dout.float().view(N, H, Fd))
+
+    gd = g.to(DEV)
+    indptr, idx_src, _ = gd.in_csr()
+    oi, od, pin = gd.out_csr()
+    # index construction of the out-CSR is exact: out-edge k of source u sits at in-CSR position pin[k]
+    in_dst = torch.repeat_interleave(torch.arange(N), (indptr[1:] - indptr[:-1]).long().cpu())
+    assert torch.equal(in_dst[pin.long().cpu()], od.long().cpu())
+    out_src = torch.repeat_interleave(torch.arange(N), (oi[1:] - oi[:-1]).long().cpu())
+    assert torch.equal(idx_src.long().cpu()[pin.long().cpu()], out_src)
+    E = idx_src.numel()
+    zd, dd = z.to(DEV), dout.to(DEV)
+    eld, erd = torch.empty(N, H, device=DEV), torch.empty(N, H, device=DEV)
+    _lib.call("mvuld_gat_scores", zd, al.to(DEV).view(-1), ar.to(DEV).view(-1), eld, erd, N, H, Fd)
+    alpha_e, ds_e = torch.empty(E, H, device=DEV), torch.empty(E, H, device=DEV)
+    dl, dr = torch.empty(N, H, device=DEV), torch.empty(N, H, device=DEV)
+    dz = torch.empty(N, H * Fd, device=DEV, dtype=torch.bfloat16)
+    dal, dar = torch.zeros(H * Fd, device=DEV), torch.zeros(H * Fd, device=DEV)
+    _lib.call("mvuld_gat_bwd", zd, dd, eld, erd, indptr, idx_src, oi, od, pin, al.to(DEV).view(-1), ar.to(DEV).view(-1),
+              alpha_e, ds_e, dl, dr, dz, dal, dar, N, H, Fd, 0.2)
+    torch.cuda.synchronize()
+    assert rel_err(dz, zr.grad.view(N, H * Fd)) < 1e-2
+    assert rel_err(dal, alr.grad.view(-1)) < 1e-2
+    assert rel_err(dar, arr.grad.view(-1)) < 1e-2
+
+
+def test_rs_gcn_affinity_backward():
+    B, n, C = 3, 100, 512
+    r = gen(7)
+    tpg = (torch.randn(B, n, 3 * C, generator=r) * 0.3).to(torch.bfloat16)
+    dy = (torch.randn(B, n, C, generator=r) * 0.1).to(torch.bfloat16)
+    t = tpg.float().requires_grad_(True)
+    th, ph, gg = t[..., :C], t[..., C:2 * C], t[..., 2 * C:]
+    y = ((th @ ph.transpose(1, 2)) / n) @ gg
+    y.backward(dy.float())
+    out = torch.empty(B, n, 3 * C, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_rs_gcn_affinity_bwd", tpg.to(DEV), dy.to(DEV), out, B, n, C)
+    assert rel_err(out, t.grad) < 1e-2
+
+
+def test_head_kernels_l2norm_ce_linear():
+    B, n, D = 5, 100, 512
+    r = gen(8)
+    z = torch.randn(B, n, D, generator=r)
+    zr = z.clone().requires_grad_(True)
+    zn = zr / torch.pow(zr, 2).sum(dim=1, keepdim=True).sqrt()
+    mref = zn.mean(1)
+    dm = torch.randn(B, 3 * D, generator=r)
+    mref.backward(dm[:, D:2 * D])
+    feats = torch.zeros(B, 3 * D, device=DEV)
+    inv_s = torch.empty(B, D, device=DEV)
+    _lib.call("mvuld_l2norm_mean_fwd", z.to(DEV), _lib._Raw(feats[:, D:2 * D]), 3 * D, inv_s, B, n, D)
+    assert rel_err(feats[:, D:2 * D], mref.detach()) < 1e-5
+    dz, dzb = torch.empty(B, n, D, device=DEV), torch.empty(B, n, D, device=DEV, dtype=torch.bfloat16)
+    dmd = dm.to(DEV)
+    _lib.call("mvuld_l2norm_mean_bwd", z.to(DEV), inv_s, _lib._Raw(dmd[:, D:2 * D]), 3 * D, dz, dzb, B, n, D)
+    assert rel_err(dz, zr.grad) < 1e-4
+
+    logits = torch.randn(B, 2, generator=r)
+    labels = torch.randint(0, 2, (B,), generator=r)
+    lr_ = logits.clone().requires_grad_(True)
+    loss = F.cross_entropy(lr_, labels)
+    loss.backward()
+    ls, dl = torch.zeros(1, device=DEV), torch.empty(B, 2, device=DEV)
+    _lib.call("mvuld_ce_loss", logits.to(DEV), labels.to(DEV), ls, dl, B, 2, 1.0 / B)
+    assert abs(float(ls) - float(loss)) < 1e-5 and rel_err(dl, lr_.grad) < 1e-5
+
+    x, w = torch.randn(B, 1536, generator=r), torch.randn(2, 1536, generator=r) * 0.05
+    dy = torch.randn(B, 2, generator=r)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    br = torch.zeros(2, requires_grad=True)
+    F.linear(xr, wr, br).backward(dy)
+    dx, dw, db = torch.empty(B, 1536, device=DEV), torch.zeros(2, 1536, device=DEV), torch.zeros(2, device=DEV)
+    _lib.call("mvuld_linear_small_bwd", x.to(DEV), w.to(DEV), dy.to(DEV), dx, dw, db, B, 2, 1536)
+    assert rel_err(dx, xr.grad) < 1e-5 and rel_err(dw, wr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
+
+
+def test_adamw_with_clipping_matches_torch():
+    r = gen(9)
+    n = 5000
+    p0, g0 = torch.randn(n, generator=r), torch.randn(n, generator=r) * 3
+    seg_end = torch.tensor([1024, 3008, n], dtype=torch.int64)
+    seg_wd = torch.tensor([0.005, 0.0, 0.005])
+    parts = [p0[:1024].clone().requires_grad_(True), p0[1024:3008].clone().requires_grad_(True),
+             p0[3008:].clone().requires_grad_(True)]
+    opt = torch.optim.AdamW([{"params": [parts[0], parts[2]], "weight_decay": 0.005},
+                             {"params": [parts[1]], "weight_decay": 0.0}], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    p, m, v = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in (1, 2, 3):
+        gs = g0 * step
+        for q, (lo, hi) in zip(parts, ((0, 1024), (1024, 3008), (3008, n))):
+            q.grad = gs[lo:hi].clone()
+        torch.nn.utils.clip_grad_norm_(parts, 5.0)
+        opt.step()
+        gd = gs.to(DEV)
+        nsq = torch.zeros(1, device=DEV)
+        _lib.call("mvuld_sumsq_f32", gd, n, nsq)
+        assert abs(float(nsq.sqrt()) - float(gs.norm())) / float(gs.norm()) < 1e-5
+        _lib.call("mvuld_adamw", p, gd, m, v, n, seg_end.to(DEV), seg_wd.to(DEV), 3, nsq, 5.0, 1e-3, 0.9, 0.999, 1e-8, step)
+    ref = torch.cat([q.detach() for q in parts])
+    assert float((p.cpu() - ref).abs().max()) < 1e-5
+
+
+def test_dropout_mask_is_reproducible_and_unbiased():
+    n = 1 << 20
+    x = torch.ones(n, device=DEV, dtype=torch.bfloat16)
+    a, b, c = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    _lib.call("mvuld_dropout_bf16", x, a, n, 1234, 0.2)
+    _lib.call("mvuld_dropout_bf16", x, b, n, 1234, 0.2)
+    _lib.call("mvuld_dropout_bf16", x, c, n, 1235, 0.2)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    keep = float((a > 0).float().mean())
+    assert abs(keep - 0.8) < 3e-3
+    assert abs(float(a.float().mean()) - 1.0) < 5e-3                      # kept values scaled by 1 / (1 - p)
+    # elu_bwd regenerates the same mask: gradient is zero exactly where the forward dropped
+    y = a                                                                 # y = dropout(elu(pre)) with elu(pre) = 1
+    dx = torch.empty_like(x)
+    _lib.call("mvuld_elu_bwd", x, y, dx, n, 0, 1234, 0.2)
+    assert torch.equal(dx > 0, a > 0)
+    assert abs(float(dx[dx > 0].float().mean()) - 1.25) < 1e-2
+
+
+# --------------------------------------------------------------------------------------------------------
+# the whole step
+# --------------------------------------------------------------------------------------------------------
+def _make_trainer(dropout=0.0, **kw):
+    model = cases.make_fusion()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV)
+    return model, sd, train.FusionTrainer(model, dropout=dropout, world_size=1, **kw)
+
+
+def test_forward_backward_matches_autograd_oracle():
+    model, sd, tr = _make_trainer(0.0)
+    g, img, txt, labels = _inputs()
+    loss_ref, logits_ref, grads_ref = otrain.loss_and_grads(sd, cases.to_host_batch(g), img, txt, labels)
+    loss, logits = tr.forward_backward(g.to(DEV), img.to(DEV), txt.to(DEV), labels.to(DEV))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)) < 1e-2, (float(loss), float(loss_ref))
+    scale = logits_ref.abs().max()
+    assert float((logits.cpu() - logits_ref).abs().max() / scale) < 1e-2
+    assert torch.equal(logits.cpu().argmax(1), logits_ref.argmax(1))
+    grads = tr.named_grads()
+    assert set(grads) == set(grads_ref), set(grads) ^ set(grads_ref)
+    worst = {}
+    for name, gref in grads_ref.items():
+        err = rel_err(grads[name].reshape(gref.shape), gref)
+        worst[name] = err
+    bad = {k: round(v, 4) for k, v in worst.items() if not v < 3e-2}
+    assert not bad, bad
+    # the whole gradient vector (what clip_grad_norm_ and AdamW see)
+    tot_ref = math.sqrt(sum(float(v.pow(2).sum()) for v in grads_ref.values()))
+    tot = math.sqrt(sum(float(v.float().pow(2).sum()) for v in grads.values()))
+    assert abs(tot - tot_ref) / tot_ref < 1e-2
+    # BatchNorm running statistics were updated exactly as nn.BatchNorm1d does (momentum 0.1, unbiased variance)
+    x = img.float()
+    rm = 0.9 * sd["swinbn.running_mean"] + 0.1 * x.mean(0)
+    rv = 0.9 * sd["swinbn.running_var"] + 0.1 * x.var(0, unbiased=True)
+    assert rel_err(model.swinbn.running_mean, rm) < 1e-5 and rel_err(model.swinbn.running_var, rv) < 1e-5
+    assert int(model.swinbn.num_batches_tracked) == int(sd["swinbn.num_batches_tracked"]) + 1
+
+
+def test_three_steps_follow_torch_adamw_on_oracle_gradients():
+    """Three optimiser steps: the CUDA step against fp32 autograd + clip_grad_norm_(5) + torch.optim.AdamW."""
+    lr, wd = 1e-3, 0.005
+    model, sd, tr = _make_trainer(0.0, lr=lr, weight_decay=wd)
+    ref_sd = {k: v.clone().float() for k, v in sd.items()}
+    names = [n for n in ref_sd if otrain.is_trained(n)]
+    params = {n: ref_sd[n].clone().requires_grad_(True) for n in names}
+    decay = [params[n] for n in names if not (params[n].dim() == 1 or n.endswith(".bias"))]
+    no_decay = [params[n] for n in names if (params[n].dim() == 1 or n.endswith(".bias"))]
+    opt = torch.optim.AdamW([{"params": decay}, {"params": no_decay, "weight_decay": 0.0}], lr=lr, weight_decay=wd,
+                            betas=(0.9, 0.999), eps=1e-8)
+    losses, losses_ref = [], []
+    for step in range(3):
+        g, img, txt, labels = _inputs(seed=cases.SEED + step)
+        cur = dict(ref_sd)
+        cur.update({n: p.detach() for n, p in params.items()})
+        loss_ref, _, grads_ref = otrain.loss_and_grads(cur, cases.to_host_batch(g), img, txt, labels)
+        for n in names:
+            params[n].grad = grads_ref[n].clone()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 5.0)
+        opt.step()
+        loss, _ = tr.step(g.to(DEV), img.to(DEV), txt.to(DEV), labels.to(DEV))
+        losses.append(float(loss))
+        losses_ref.append(float(loss_ref))
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) / abs(b) < 2e-2, (losses, losses_ref)
+    # parameters moved the same way: compare the update direction of the big matrices
+    msd = model.state_dict()
+    for n in ("fc.weight", "gat2.fc.weight", "Rs_GCN_4.theta.weight", "final_fc.weight", "hidden.3.bias"):
+        d = msd[n].float().cpu() - sd[n].float()
+        dr = params[n].detach() - sd[n].float()
+        cos = float((d * dr).sum() / (d.norm() * dr.norm() + 1e-20))
+        assert cos > 0.9, (n, cos)
+    # the eval-mode forward sees the updated weights (plan invalidated by the trainer)
+    g, img, txt, _ = _inputs(seed=cases.SEED + 7)
+    out = model.eval()(g.to(DEV), img.to(DEV), txt.to(DEV))
+    assert torch.isfinite(out).all()
+
+
+def test_dropout_step_runs_and_is_seeded():
+    """p = 0.2 (the reference's gatdrop / mlpdropout / hdropout): same seed -> identical step, other seed -> different."""
+    outs = []
+    for seed in (1, 1, 2):
+        model, sd, tr = _make_trainer(0.2, seed=seed)
+        g, img, txt, labels = _inputs()
+        loss, logits = tr.step(g.to(DEV), img.to(DEV), txt.to(DEV), labels.to(DEV))
+        outs.append((float(loss), logits.cpu().clone(), tr.named_grads()["fc.weight"].cpu().clone()))
+        assert math.isfinite(float(loss)) and float(tr.grad_norm()) > 0
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert not torch.equal(outs[0][1], outs[2][1])
+
+
+def test_trainer_boundary_errors():
+    model = cases.make_fusion()
+    with pytest.raises(RuntimeError):
+        train.FusionTrainer(model)                      # CPU model: no fallback
+    model, sd, tr = _make_trainer(0.0)
+    g, img, txt, labels = _inputs(B=2)
+    with pytest.raises(RuntimeError):
+        tr.forward_backward(g.to(DEV), img, txt.to(DEV), labels.to(DEV))       # CPU tensor
+    with pytest.raises(ValueError):
+        tr.forward_backward(g.to(DEV), img[:1].to(DEV), txt[:1].to(DEV), labels[:1].to(DEV))

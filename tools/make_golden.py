@@ -110,6 +110,27 @@ def golden_rs_gcn():
     print("rs_gcn", float(v_star.abs().mean()), float((v_star - v).abs().mean()))
 
 
+def golden_rs_gcn_train():
+    """Reference Rs_GCN.py in TRAIN mode (BatchNorm on batch statistics) with autograd: pins the train-mode oracle
+    (oracle/fusion_train.py::_rs_gcn) that the CUDA training step is checked against.  Slices only (small file)."""
+    ref = _load(os.path.join(REF, "mvuld/models/Rs_GCN.py"), "ref_rs_gcn_train")
+    mine = cases.make_rs_gcn()
+    m = ref.Rs_GCN(in_channels=512, inter_channels=512).train()
+    m.load_state_dict(mine.state_dict(), strict=True)
+    v = cases.rs_gcn_input().requires_grad_(True)
+    v_star, R = m(v)
+    gsel = torch.Generator().manual_seed(cases.SEED + 1)
+    dout = torch.randn(v_star.shape, generator=gsel)
+    (v_star * dout).sum().backward()
+    torch.save(dict(v_star=v_star.detach()[:, :16].clone(), dv=v.grad[:, :16].clone(),
+                    d_theta=m.theta.weight.grad[:16].clone(), d_phi_bias=m.phi.bias.grad.clone(),
+                    d_g=m.g.weight.grad[:16].clone(), d_W0=m.W[0].weight.grad[:16].clone(),
+                    d_bn_weight=m.W[1].weight.grad.clone(), d_bn_bias=m.W[1].bias.grad.clone(),
+                    running_mean=m.W[1].running_mean.clone(), running_var=m.W[1].running_var.clone()),
+               os.path.join(OUT, "rs_gcn_train.pt"))
+    print("rs_gcn_train", float(v_star.abs().mean()), float(v.grad.abs().mean()))
+
+
 @torch.no_grad()
 def golden_roberta():
     from transformers import RobertaConfig, RobertaModel
@@ -165,6 +186,10 @@ def golden_graph():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if "rs_gcn_train" in sys.argv[1:]:
+        golden_rs_gcn_train()
+        sys.exit(0)
+    golden_rs_gcn_train()
     golden_swin()
     golden_rs_gcn()
     golden_roberta()
