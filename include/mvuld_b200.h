@@ -147,6 +147,12 @@ int mvuld_f32_to_bf16(const float* in, void* out, long long n, mvuld_stream_t st
 /* Rs_GCN.py:57-66: tpg bf16 [B*n, 3C] = (theta | phi | g); y = (theta phi^T / n) g, bf16 [B*n, C]; r_out optional
  * fp32 [B, n, n] (the affinity the reference returns). */
 int mvuld_rs_gcn_affinity(const void* tpg, void* y, float* r_out, int B, int n, int C, mvuld_stream_t stream);
+/* The variant the models use: tpg fp32 [B*n, 3C]; y3 = bf16x3 split operand [B*n, 3C] = (hi | lo | hi) of the fp32 y,
+ * to be multiplied against a (W_hi | W_hi | W_lo) weight (mvuld_split3_bf16, w_side = 1): fp32-class products on the
+ * bf16 tensor-core GEMM.  Rs_GCN has no softmax and feeds a BatchNorm: plain bf16 operands cost 1-2 % per block. */
+int mvuld_rs_gcn_affinity_f32(const float* tpg, void* y3, float* r_out, int B, int n, int C, mvuld_stream_t stream);
+/* x fp32 [R, C] (row stride ldx) -> out bf16 [R, 3C]: (hi | lo | hi) for w_side == 0, (hi | hi | lo) otherwise. */
+int mvuld_split3_bf16(const float* x, int ldx, void* out, int R, int C, int w_side, mvuld_stream_t stream);
 /* GraphModel.py:200-209: l2norm(dim=1) + mean + concat + BN(folded) + Linear -> logits fp32 [B, num_classes]. */
 int mvuld_fusion_head(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
                       float* logits, float* feat_out, int B, int n, int D, int num_classes, mvuld_stream_t stream);
@@ -162,8 +168,9 @@ int mvuld_linear_small(const float* x, const float* w, const float* b, float* ou
  * operands; these entry points are the non-GEMM pieces.  Activation gradients bf16 / fp32, parameter gradients fp32
  * (accumulated: callers zero them once per step).
  * ---------------------------------------------------------------------------------------------------------- */
-/* out[c, r] = in[r, c] (bf16), out row stride ldo >= R with zero fill: operand transposes of dW = dY^T X. */
-int mvuld_transpose_bf16(const void* in, void* out, int R, int C, int ldo, mvuld_stream_t stream);
+/* out[c, r] = in[r, c] (bf16, in row stride ldi), out row stride ldo >= R with zero fill: operand transposes of
+ * dW = dY^T X. */
+int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, int C, int ldo, mvuld_stream_t stream);
 /* out[c] += sum_r x[r, c] (bias gradients); x bf16 (is_bf16 != 0) or fp32, row stride ldx >= C. */
 int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, int R, int C, mvuld_stream_t stream);
 /* dx = dy * ELU'(pre) through y = dropout(ELU(pre), p) with the mask regenerated from seed (F.elu + nn.Dropout,

@@ -45,9 +45,11 @@ SIGNATURES = {
     "mvuld_pos_branch": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mvuld_f32_to_bf16": [_P, _P, _LL, _P],
     "mvuld_rs_gcn_affinity": [_P, _P, _P, _I, _I, _I, _P],
+    "mvuld_rs_gcn_affinity_f32": [_P, _P, _P, _I, _I, _I, _P],
+    "mvuld_split3_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "mvuld_fusion_head": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
-    "mvuld_transpose_bf16": [_P, _P, _I, _I, _I, _P],
+    "mvuld_transpose_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "mvuld_colsum": [_P, _I, _I, _P, _I, _I, _P],
     "mvuld_elu_bwd": [_P, _P, _P, _LL, _I, C.c_ulonglong, _F, _P],
     "mvuld_dropout_bf16": [_P, _P, _LL, C.c_ulonglong, _F, _P],

@@ -9,16 +9,42 @@ namespace mv {
 
 // tpg: bf16 [B*n, 3C] rows = (theta | phi | g) of one node slot; y: bf16 [B*n, C].  One CTA (256 threads, 200 active
 // in the FMA phases) per graph; n <= 100 slots, C % 64 == 0.
+//
+// F32 variant (the one the models use): tpg is fp32 and y is written as the bf16x3 split operand [B*n, 3C] =
+// (hi | lo | hi), hi = bf16(v), lo = bf16(v - hi), so that the following 1x1-conv GEMM against (W_hi | W_hi | W_lo)
+// reproduces the fp32 product to ~2^-16.  Rs_GCN has no softmax and is followed by a BatchNorm whose batch deviation
+// is small against the magnitude of W y: a plain bf16 y costs 1.6 % per block there (measured), 9 % after 8 blocks.
 constexpr int RS_MAXN = 100;
+__device__ __forceinline__ void rs_load8(const bf16* p, float* f) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ void rs_load8(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+// 8 fp32 -> (hi, lo) bf16 words
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    l[i] = pack_bf16x2(v[2 * i] - bf16_lo(h[i]), v[2 * i + 1] - bf16_hi(h[i]));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+template <typename TIn, bool SPLIT>
 __global__ void __launch_bounds__(256)
-rs_gcn_affinity_kernel(const bf16* __restrict__ tpg, bf16* __restrict__ y, float* __restrict__ r_out, int n, int C) {
+rs_gcn_affinity_kernel(const TIn* __restrict__ tpg, bf16* __restrict__ y, float* __restrict__ r_out, int n, int C) {
   extern __shared__ float sm[];
   float* R = sm;                                  // [RS_MAXN][RS_MAXN + 1]
   float* bufA = R + RS_MAXN * (RS_MAXN + 1);      // phase 1: theta chunk [RS_MAXN][33]; phase 2: g chunk [RS_MAXN][64]
   float* bufB = bufA + RS_MAXN * 64;              // phase 1: phi chunk [RS_MAXN][33]
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
-  const bf16* base = tpg + (size_t)b * n * 3 * C;
+  const TIn* base = tpg + (size_t)b * n * 3 * C;
 
   // ---- phase 1: R = theta phi^T / n ; thread (ti, tj) owns rows ti*5..+5, cols tj*10..+10 ----
   const int ti = tid / 10, tj = tid % 10;
@@ -34,9 +60,7 @@ rs_gcn_affinity_kernel(const bf16* __restrict__ tpg, bf16* __restrict__ y, float
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (row < n) {
         const int col = (part < 4 ? 0 : C) + k0 + (part & 3) * 8;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * 3 * C + col));
-        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+        rs_load8(base + (size_t)row * 3 * C + col, f);
       }
       float* dstp = (part < 4 ? bufA : bufB) + row * 33 + (part & 3) * 8;
 #pragma unroll
@@ -79,11 +103,7 @@ rs_gcn_affinity_kernel(const bf16* __restrict__ tpg, bf16* __restrict__ y, float
     for (int i = tid; i < RS_MAXN * 8; i += 256) {
       const int row = i >> 3, part = i & 7;
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (row < n) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * 3 * C + 2 * C + c0 + part * 8));
-        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
-      }
+      if (row < n) rs_load8(base + (size_t)row * 3 * C + 2 * C + c0 + part * 8, f);
 #pragma unroll
       for (int q = 0; q < 8; ++q) bufA[row * 64 + part * 8 + q] = f[q];
     }
@@ -110,14 +130,43 @@ rs_gcn_affinity_kernel(const bf16* __restrict__ tpg, bf16* __restrict__ y, float
       for (int a = 0; a < 4; ++a) {
         const int row = yi * 4 + a;
         if (row < n) {
-          uint4 w;
-          w.x = pack_bf16x2(o[a][0], o[a][1]); w.y = pack_bf16x2(o[a][2], o[a][3]);
-          w.z = pack_bf16x2(o[a][4], o[a][5]); w.w = pack_bf16x2(o[a][6], o[a][7]);
-          *reinterpret_cast<uint4*>(y + ((size_t)b * n + row) * C + c0 + yj * 8) = w;
+          if (SPLIT) {
+            uint4 hi, lo;
+            split8(o[a], hi, lo);
+            bf16* yr = y + ((size_t)b * n + row) * 3 * C + c0 + yj * 8;
+            *reinterpret_cast<uint4*>(yr) = hi;
+            *reinterpret_cast<uint4*>(yr + C) = lo;
+            *reinterpret_cast<uint4*>(yr + 2 * C) = hi;
+          } else {
+            uint4 w;
+            w.x = pack_bf16x2(o[a][0], o[a][1]); w.y = pack_bf16x2(o[a][2], o[a][3]);
+            w.z = pack_bf16x2(o[a][4], o[a][5]); w.w = pack_bf16x2(o[a][6], o[a][7]);
+            *reinterpret_cast<uint4*>(y + ((size_t)b * n + row) * C + c0 + yj * 8) = w;
+          }
         }
       }
     }
     __syncthreads();
+  }
+}
+
+// bf16x3 split of an fp32 matrix x [R, C] (row stride ldx) into out bf16 [R, 3C]:
+//   w_side == 0 (activations, the A operand): (hi | lo | hi);   w_side != 0 (weights, the W operand): (hi | hi | lo)
+// so that  A3 W3^T = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T  (the lo*lo term, ~2^-18, is dropped).
+__global__ void split3_kernel(const float* __restrict__ x, int ldx, bf16* __restrict__ out, int R, int C, int w_side) {
+  const int units = C >> 3;
+  const long long total = (long long)R * units;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(i % units);
+    const long long r = i / units;
+    float f[8];
+    rs_load8(x + r * ldx + u * 8, f);
+    uint4 hi, lo;
+    split8(f, hi, lo);
+    bf16* o = out + r * 3 * C + u * 8;
+    *reinterpret_cast<uint4*>(o) = hi;
+    *reinterpret_cast<uint4*>(o + C) = w_side ? hi : lo;
+    *reinterpret_cast<uint4*>(o + 2 * C) = w_side ? lo : hi;
   }
 }
 
@@ -192,9 +241,32 @@ extern "C" int mvuld_rs_gcn_affinity(const void* tpg, void* y, float* r_out, int
   MV_CHECK_ARG(C % 64 == 0, "rs_gcn_affinity: C %% 64");
   if (B <= 0) return 0;
   const int smem = (RS_MAXN * (RS_MAXN + 1) + RS_MAXN * 64 + RS_MAXN * 33) * sizeof(float);
-  MV_CUDA_OK(cudaFuncSetAttribute(rs_gcn_affinity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  rs_gcn_affinity_kernel<<<B, 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<bf16*>(y),
-                                                   r_out, n, C);
+  auto kern = rs_gcn_affinity_kernel<bf16, false>;
+  MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<B, 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<bf16*>(y), r_out, n, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int mvuld_rs_gcn_affinity_f32(const float* tpg, void* y3, float* r_out, int B, int n, int C,
+                                         cudaStream_t stream) {
+  MV_CHECK_ARG(n >= 1 && n <= RS_MAXN, "rs_gcn_affinity_f32: n must be in [1, %d]", RS_MAXN);
+  MV_CHECK_ARG(C % 64 == 0, "rs_gcn_affinity_f32: C %% 64");
+  if (B <= 0) return 0;
+  const int smem = (RS_MAXN * (RS_MAXN + 1) + RS_MAXN * 64 + RS_MAXN * 33) * sizeof(float);
+  auto kern = rs_gcn_affinity_kernel<float, true>;
+  MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<B, 256, smem, stream>>>(tpg, reinterpret_cast<bf16*>(y3), r_out, n, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int mvuld_split3_bf16(const float* x, int ldx, void* out, int R, int C, int w_side, cudaStream_t stream) {
+  MV_CHECK_ARG(C % 8 == 0 && ldx % 4 == 0 && ldx >= C, "split3: C %% 8, ldx %% 4, ldx >= C (C=%d ldx=%d)", C, ldx);
+  if (R <= 0) return 0;
+  long long blocks = ((long long)R * (C / 8) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split3_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, reinterpret_cast<bf16*>(out), R, C, w_side);
   MV_LAUNCH_OK();
   return 0;
 }

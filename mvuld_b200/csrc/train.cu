@@ -20,13 +20,15 @@ __device__ __forceinline__ float u01(unsigned long long seed, unsigned long long
   return (float)(unsigned int)(x >> 40) * (1.0f / 16777216.0f);
 }
 
-// out[c, r] = in[r, c]; out row stride ldo >= R, columns [R, ldo) zero filled (TMA strides need 16-byte multiples)
-__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int C, int ldo) {
+// out[c, r] = in[r, c] (in row stride ldi); out row stride ldo >= R, columns [R, ldo) zero filled (TMA strides need
+// 16-byte multiples)
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, int ldi, bf16* __restrict__ out, int R, int C,
+                                      int ldo) {
   __shared__ bf16 tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : __float2bfloat16(0.f);
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * ldi + c] : __float2bfloat16(0.f);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -808,11 +810,11 @@ using namespace mv;
 
 #define GRID1(n, t) (unsigned)(((n) + (t) - 1) / (t))
 
-extern "C" int mvuld_transpose_bf16(const void* in, void* out, int R, int C, int ldo, cudaStream_t stream) {
-  MV_CHECK_ARG(ldo >= R, "transpose: ldo < R");
+extern "C" int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, int C, int ldo, cudaStream_t stream) {
+  MV_CHECK_ARG(ldo >= R && ldi >= C, "transpose: ldo < R or ldi < C");
   if (R <= 0 || C <= 0) return 0;
   dim3 grid((C + 31) / 32, (ldo + 31) / 32), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), R, C, ldo);
+  transpose_bf16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const bf16*>(in), ldi, reinterpret_cast<bf16*>(out), R, C, ldo);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -143,7 +143,13 @@ class Multi_DefectModel_new_GCN(nn.Module):
             scale, shift = _bn_affine(m.W[1])                      # BN after the 1x1 conv: fold on the output side
             ww = m.W[0].weight.detach().float()[:, :, 0] * scale[:, None]
             wb = m.W[0].bias.detach().float() * scale + shift
-            p["gcn"].append(dict(wcat=b16(wcat), bcat=f32(bcat), ww=b16(ww), wb=f32(wb)))
+            # bf16x3 split weights (W_hi | W_hi | W_lo): fp32-class 1x1 convolutions (see mvuld_rs_gcn_affinity_f32)
+            split = []
+            for w32 in (f32(wcat), f32(ww)):
+                w3 = torch.empty(w32.shape[0], 3 * w32.shape[1], device=dev, dtype=torch.bfloat16)
+                _lib.call("mvuld_split3_bf16", w32, w32.shape[1], w3, w32.shape[0], w32.shape[1], 1)
+                split.append(w3)
+            p["gcn"].append(dict(wcat3=split[0], bcat=f32(bcat), ww3=split[1], wb=f32(wb)))
         scale, shift = _bn_affine(self.final_fc_bn)
         wf = self.final_fc.weight.detach().float()
         p["final"] = (f32(wf * scale[None, :]), f32(self.final_fc.bias.detach().float() + wf @ shift))
@@ -215,11 +221,14 @@ class Multi_DefectModel_new_GCN(nn.Module):
                   p["fc_bbox"][1], z32, zb, B, n, 32, 512, 480)
 
         # 8 x Rs_GCN on the token-major [B*n, 512] tensor (GraphModel.py:190-198)
-        tpg, y = e((B * n, 1536), bf), e((B * n, 512), bf)
+        # the residual stream stays fp32 and every product uses bf16x3 split operands: no softmax bounds the affinity
+        # and a BatchNorm follows, so plain bf16 operands cost 1-2 % per block (measured in train mode)
+        z3, y3, tpg = e((B * n, 1536), bf), e((B * n, 1536), bf), e((B * n, 1536), f32)
         for gc in p["gcn"]:
-            _lib.gemm(zb, gc["wcat"], bias=gc["bcat"], out_bf16=tpg)
-            _lib.call("mvuld_rs_gcn_affinity", tpg, y, None, B, n, 512)
-            _lib.gemm(y, gc["ww"], bias=gc["wb"], res=z32, out_bf16=zb, out_f32=z32)
+            _lib.call("mvuld_split3_bf16", z32, 512, z3, B * n, 512, 0)
+            _lib.gemm(z3, gc["wcat3"], bias=gc["bcat"], out_f32=tpg)
+            _lib.call("mvuld_rs_gcn_affinity_f32", tpg, y3, None, B, n, 512)
+            _lib.gemm(y3, gc["ww3"], bias=gc["wb"], res=z32, out_f32=z32)
 
         # l2norm(dim=1) + mean + concat + BN + final_fc (GraphModel.py:200-209)
         logits = e((B, self.num_classes), f32)

@@ -145,6 +145,7 @@ class FusionTrainer:
         self.loss_buf = torch.zeros(1, **f32)
         self._refresh_shadows()
         self.last = {}
+        self.debug_taps = None      # tests set this to a dict to receive intermediate activations
 
     # ----------------------------------------------------------------------------------------------------
     def _view(self, flat: torch.Tensor, name: str, shape=None) -> torch.Tensor:
@@ -179,18 +180,26 @@ class FusionTrainer:
         for name in lin:
             w = self._mat(self.flat_w16, name + ".weight")
             self.wt[name] = self._transpose(w)
+        self.w3 = {}
         for k in range(1, 9):
             self.wt[f"gcn{k}.cat"] = self._transpose(self._gcn_cat(self.flat_w16, k, "weight"))
             self.wt[f"gcn{k}.W0"] = self._transpose(self._mat(self.flat_w16, f"Rs_GCN_{k}.W.0.weight"))
+            # forward operands of the Rs_GCN 1x1 convolutions: bf16x3 split (W_hi | W_hi | W_lo) of the fp32 weights
+            for key, w32 in ((f"gcn{k}.cat", self._gcn_cat(self.flat_p, k, "weight")),
+                             (f"gcn{k}.W0", self._mat(self.flat_p, f"Rs_GCN_{k}.W.0.weight"))):
+                w3 = torch.empty(w32.shape[0], 3 * w32.shape[1], device=self.dev, dtype=torch.bfloat16)
+                _lib.call("mvuld_split3_bf16", w32, w32.shape[1], w3, w32.shape[0], w32.shape[1], 1)
+                self.w3[key] = w3
         self.model.invalidate()
 
     def _transpose(self, x: torch.Tensor) -> torch.Tensor:
-        """bf16 [R, C] (dense) -> [C, Rp] with Rp = R rounded up to 8 (zero filled): the K-major operand of a product
+        """bf16 [R, C] (any row stride) -> [C, Rp] with Rp = R rounded up to 8 (zero filled): the K-major operand of a product
         that reduces over R."""
         R, C = x.shape
+        assert x.stride(1) == 1
         Rp = (R + 7) // 8 * 8
         out = torch.empty(C, Rp, device=self.dev, dtype=torch.bfloat16)
-        _lib.call("mvuld_transpose_bf16", x, out, R, C, Rp)
+        _lib.call("mvuld_transpose_bf16", _lib._Raw(x), x.stride(0), out, R, C, Rp)
         return out
 
     # ----------------------------------------------------------------------------------------------------
@@ -293,6 +302,9 @@ class FusionTrainer:
                       float(mod.negative_slope), zero_deg)
             gat_saved.append((xd, z, el, er, H, F, float(mod.negative_slope)))
             hcur = hout
+            if self.debug_taps is not None:
+                self.debug_taps["gat1" if li == 0 else "gat2"] = hout.clone()
+                self.debug_taps["z1" if li == 0 else "z2"] = z.clone()
         acts = [hcur]                                                     # inputs of fc, hidden.0 ... hidden.7
         for li, name in enumerate(["fc"] + [f"hidden.{i}" for i in range(8)]):
             a = e((N, 512), bf)
@@ -300,6 +312,8 @@ class FusionTrainer:
             if p > 0:                                                     # mlpdropout / hdropout (GraphModel.py:171,176)
                 _lib.call("mvuld_dropout_bf16", a, a, a.numel(), self._seed(8 + li), p)
             acts.append(a)
+            if self.debug_taps is not None and li == 0:
+                self.debug_taps["fc"] = a.clone()
         g.ndata['HGATOUTPUT'] = acts[-1]
         g.ndata['HFGATOUTPUT'] = pos
 
@@ -320,19 +334,22 @@ class FusionTrainer:
         _lib.call("mvuld_pos_branch", pos, offsets, box_scale, box_shift, pv("fc_bbox.weight"), pv("fc_bbox.bias"),
                   z32, zb0, B, n, 32, 512, 480)
 
+        if self.debug_taps is not None:
+            self.debug_taps.update(node_mlp=acts[-1].clone(), gcn_in=z32.clone())
         gcn_saved = []
-        zb = zb0
         for k in range(1, 9):
+            # fp32-class block (bf16x3 split operands, see mvuld_rs_gcn_affinity_f32): Rs_GCN.py:52-73 in train mode
             pre = f"Rs_GCN_{k}."
-            tpg, y, w0 = e((R, 1536), bf), e((R, 512), bf), e((R, 512), f32)
-            _lib.gemm(zb, self._gcn_cat(W16, k, "weight"), bias=self._gcn_cat(P, k, "bias"), out_bf16=tpg)
-            _lib.call("mvuld_rs_gcn_affinity", tpg, y, None, B, n, 512)
-            _lib.gemm(y, w16(pre + "W.0.weight"), bias=pv(pre + "W.0.bias"), out_f32=w0)
-            zb_next = e((R, 512), bf)
+            z3, y3 = e((R, 1536), bf), e((R, 1536), bf)
+            tpg32, tpg, w0 = e((R, 1536), f32), e((R, 1536), bf), e((R, 512), f32)
+            _lib.call("mvuld_split3_bf16", z32, 512, z3, R, 512, 0)
+            _lib.gemm(z3, self.w3[f"gcn{k}.cat"], bias=self._gcn_cat(P, k, "bias"), out_bf16=tpg, out_f32=tpg32)
+            _lib.call("mvuld_rs_gcn_affinity_f32", tpg32, y3, None, B, n, 512)
+            _lib.gemm(y3, self.w3[f"gcn{k}.W0"], bias=pv(pre + "W.0.bias"), out_f32=w0)
             mean, rstd = bn_cols(pre + "W.1", w0, R, 512, res=z32, ldr=512, y32=z32, ldy=512, yb=None)
-            _lib.call("mvuld_f32_to_bf16", z32, zb_next, R * 512)
-            gcn_saved.append((zb, tpg, y, w0, mean, rstd))
-            zb = zb_next
+            gcn_saved.append((z3[:, :512], tpg, y3[:, :512], w0, mean, rstd))
+            if self.debug_taps is not None:
+                self.debug_taps[f"gcn_{k}"] = z32.clone()
         inv_s = e((B, 512), f32)
         _lib.call("mvuld_l2norm_mean_fwd", z32, _lib._Raw(feats[:, 512:1024]), 1536, inv_s, B, n, 512)
         fn = e((B, 1536), f32)
@@ -386,6 +403,8 @@ class FusionTrainer:
             _lib.gemm(dtpg, self.wt[f"gcn{k}.cat"][:, :1536], res=dz32, out_bf16=dzb, out_f32=dz32)   # + residual path
             ready(pre + "g.bias")
 
+        if self.debug_taps is not None:
+            self.debug_taps["d_gcn_in"] = dz32.clone()
         # concat(h_i, pos_i) -> ELU -> fc_gat / fc_bbox -> slot BatchNorms -> unbatch
         dpre = e((R, 512), bf)
         _lib.call("mvuld_elu_bwd", dzb, zb0, dpre, R * 512, 0, 0, 0.0)
@@ -439,7 +458,7 @@ class FusionTrainer:
             while bucket_i < len(self.buckets):
                 on_bucket(self.buckets[bucket_i])
                 bucket_i += 1
-        self.last = dict(zero_deg=zero_deg, graph=g)
+        self.last = dict(zero_deg=zero_deg, graph=g, feats=feats)
         return self.loss_buf, logits
 
     # ----------------------------------------------------------------------------------------------------

@@ -391,3 +391,46 @@ def test_rs_gcn_affinity_and_head(golden):
     torch.cuda.synchronize()
     ref = golden["rs_gcn"]["v_star"].permute(0, 2, 1).reshape(B * n, C)
     assert rel_err(z32, ref) < 1e-2
+
+
+def test_rs_gcn_block_split_precision_matches_reference_golden(golden):
+    """The block as the models run it: bf16x3 split operands (mvuld_split3_bf16, mvuld_rs_gcn_affinity_f32) give the
+    reference Rs_GCN.py output (golden, fp32) to fp32-class accuracy, two orders below the plain bf16 block above."""
+    m = cases.make_rs_gcn()
+    v = cases.rs_gcn_input()
+    B, C, n = v.shape
+    sd = m.state_dict()
+    tok = v.permute(0, 2, 1).reshape(B * n, C).contiguous()
+    wcat = torch.cat([sd["theta.weight"][:, :, 0], sd["phi.weight"][:, :, 0], sd["g.weight"][:, :, 0]], 0).contiguous()
+    bcat = torch.cat([sd["theta.bias"], sd["phi.bias"], sd["g.bias"]], 0)
+    scale = sd["W.1.weight"] / torch.sqrt(sd["W.1.running_var"] + 1e-5)
+    shift = sd["W.1.bias"] - sd["W.1.running_mean"] * scale
+    ww = (sd["W.0.weight"][:, :, 0] * scale[:, None]).contiguous()
+    wb = sd["W.0.bias"] * scale + shift
+
+    def split(x, w_side):
+        x = x.to(DEV).float().contiguous()
+        out = torch.empty(x.shape[0], 3 * x.shape[1], device=DEV, dtype=torch.bfloat16)
+        _lib.call("mvuld_split3_bf16", x, x.shape[1], out, x.shape[0], x.shape[1], w_side)
+        return out
+
+    z3 = split(tok, 0)
+    hi = tok.to(torch.bfloat16)
+    lo = (tok - hi.float()).to(torch.bfloat16)
+    assert torch.equal(z3.cpu(), torch.cat([hi, lo, hi], 1))                 # the split itself is exact bit work
+    w3 = split(wcat, 1)
+    whi = wcat.to(torch.bfloat16)
+    assert torch.equal(w3.cpu(), torch.cat([whi, whi, (wcat - whi.float()).to(torch.bfloat16)], 1))
+    tpg = torch.empty(B * n, 3 * C, device=DEV)
+    _lib.gemm(z3, w3, bias=bcat.to(DEV), out_f32=tpg)
+    ref_tpg = tok @ wcat.t() + bcat
+    assert rel_err(tpg, ref_tpg) < 5e-5
+    y3 = torch.empty(B * n, 3 * C, device=DEV, dtype=torch.bfloat16)
+    R = torch.zeros(B, n, n, device=DEV)
+    _lib.call("mvuld_rs_gcn_affinity_f32", tpg, y3, R, B, n, C)
+    assert rel_err(R, golden["rs_gcn"]["R"]) < 5e-5
+    z32 = tok.to(DEV).contiguous()
+    _lib.gemm(y3, split(ww, 1), bias=wb.to(DEV), res=z32, out_f32=z32)
+    torch.cuda.synchronize()
+    ref = golden["rs_gcn"]["v_star"].permute(0, 2, 1).reshape(B * n, C)
+    assert rel_err(z32, ref) < 1e-4
