@@ -7,7 +7,10 @@
 A "step" is one pass of the composed MVulD forward (SwinV2-B 448/w28 image branch + UniXcoder/RoBERTa-base 512-token
 text branch + GAT/Rs_GCN fusion model, SURVEY.md section 3.4 / BASELINE.json configs[3]) over one batch of synthetic
 functions per GPU.  Functions are independent, so ranks shard the batch with no data-path collective (weak scaling:
-``--batch`` functions per GPU).  ``--workload swin`` / ``ggnn`` time configs[1] / configs[2] instead.
+``--batch`` functions per GPU).  ``--workload swin`` / ``ggnn`` time configs[1] / configs[2] instead, and
+``--workload train`` times configs[4]: the reference-faithful training step (frozen SwinV2 / UniXcoder forward, fusion
+model forward + backward, bucketed NCCL gradient all-reduce over the ranks, clipped AdamW), 32 functions per GPU.  The
+default (``full``) line also carries a ``"train"`` object with that step's throughput at the same N.
 
 One JSON line is printed by rank 0 (contract in the task statement): value = whole-job functions/s with inputs
 resident in HBM, timed with CUDA events on the launching stream and max-reduced over ranks; e2e = the same through
@@ -34,6 +37,9 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 import torch  # noqa: E402
 
 
+METRIC = {"full": "MVulD functions/sec (fwd)", "train": "MVulD functions/sec (train step)"}
+
+
 # --------------------------------------------------------------------------------------------------------
 def parse():
     ap = argparse.ArgumentParser()
@@ -41,12 +47,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "swin", "ggnn"])
+    ap.add_argument("--workload", default="full", choices=["full", "swin", "ggnn", "train"])
     ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (default: 64 functions / 64 images / "
-                                                         "4096 graphs)")
+                                                         "4096 graphs / 32 functions for train)")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step leg of the default workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
+
+
+def captured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from this round's `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path)).get(key)
+    except (OSError, ValueError):
+        return None
 
 
 def peaks():
@@ -171,6 +187,8 @@ def build_workload(args, rank, device):
     from mvuld_b200 import synth
     seed = 12345 + rank
     torch.manual_seed(12345)                       # same weights on every rank
+    if args.workload == "train":
+        return build_train_workload(args, rank, device, int(os.environ.get("WORLD_SIZE", "1")))
     if args.workload == "full":
         B = args.batch or 64
         model = mv.MVulD(mv.default_config()).eval()
@@ -196,7 +214,8 @@ def build_workload(args, rank, device):
         name = (f"MVulD full fused inference (configs[3]): SwinV2-B 448px/w28 + UniXcoder-base 512 tok + GAT x2/"
                 f"Rs_GCN x8 fusion, {B} synthetic functions per GPU per step, avg "
                 f"{host['g'].num_nodes() / B:.0f} CPG nodes")
-        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name, flops_per_unit=262.1e9)
+        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name, flops_per_unit=262.1e9,
+                    model=model)
     if args.workload == "swin":
         B = args.batch or 64
         model = mv.build_model(mv.default_config()).eval()
@@ -224,6 +243,52 @@ def build_workload(args, rank, device):
                      "4 edge types, D=200, 6 steps, segment-sum readout", flops_per_unit=0.0)
 
 
+def build_train_workload(args, rank, device, world, model=None):
+    """configs[4], reference-faithful variant (main_bigvul.py:294-342 trains only the fusion model on vectors from
+    frozen encoders): one step = SwinV2 + UniXcoder forward (eval, no grad), fusion forward + backward, bucketed
+    gradient all-reduce across the ranks, gradient-norm clip, AdamW.  Dropout 0.2 as in the reference."""
+    import mvuld_b200 as mv
+    from mvuld_b200 import synth
+    from mvuld_b200.train import FusionTrainer
+    seed = 22345 + rank
+    B = (args.batch if args.workload == "train" else 0) or 32
+    if model is None:
+        torch.manual_seed(12345)
+        model = mv.MVulD(mv.default_config()).eval()
+        synth.randomize_for_parity(model, seed=777)
+        model = model.to(device)
+    base_lr = 5e-5 * B * world / 512.0                                     # main_bigvul.py:545 linear scaling rule
+    trainer = FusionTrainer(model.fusion, lr=base_lr, weight_decay=0.005, clip_grad=5.0, dropout=0.2, seed=12345 + rank,
+                            world_size=world)
+    host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=synth.token_ids(B, 512, seed=seed).pin_memory(),
+                g=synth.cpg_batch(B, seed=seed),
+                y=torch.randint(0, 2, (B,), generator=torch.Generator().manual_seed(seed)).pin_memory())
+    for k in ("_UNIX_NODE_EMB", "pos_emb"):
+        host["g"].ndata[k] = host["g"].ndata[k].pin_memory()
+    host["g"].ndata.pop("_FUNC_EMB")
+    host["g"]._src, host["g"]._dst = host["g"]._src.pin_memory(), host["g"]._dst.pin_memory()
+
+    def to_dev():
+        return dict(img=host["img"].to(device, non_blocking=True), ids=host["ids"].to(device, non_blocking=True),
+                    g=host["g"].to(device, non_blocking=True), y=host["y"].to(device, non_blocking=True))
+
+    def step(d):
+        d["g"]._csr = d["g"]._ocsr = None          # graph collate (in- and out-CSR build) is part of every step
+        img_embedding = model.swin.forward_features(d["img"])
+        func_text_embedding, _ = model.unix.get_repr(d["ids"])
+        loss, _ = trainer.step(d["g"], img_embedding, func_text_embedding, d["y"], check=False)
+        return loss
+
+    h2d = host["img"].numel() * 4 + host["ids"].numel() * 8 + host["g"]._src.numel() * 16 + B * 8 + \
+        sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
+    name = (f"MVulD fusion training step (configs[4], encoders frozen as in main_bigvul.py): SwinV2-B + UniXcoder "
+            f"forward, fusion fwd+bwd, bucketed NCCL gradient all-reduce ({len(trainer.buckets)} buckets, "
+            f"{trainer.total * 4 / 1e6:.1f} MB fp32), clip 5.0 + AdamW; {B} functions per GPU (global batch {B * world}), "
+            f"avg {host['g'].num_nodes() / B:.0f} CPG nodes")
+    return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name, flops_per_unit=262.1e9 + 3 * 6.4e9,
+                trainer=trainer)
+
+
 def cpu_oracle_runner(workload, sample):
     """The oracle port of the reference forward on the host cores; returns (units, seconds)."""
     import mvuld_b200 as mv
@@ -240,7 +305,7 @@ def cpu_oracle_runner(workload, sample):
         sd = m.state_dict()
         fn = lambda: ofus.ggnn_sum_forward(sd, hb, 200, 6, 4)
     else:
-        model = mv.MVulD(mv.default_config()).eval() if workload == "full" else None
+        model = mv.MVulD(mv.default_config()).eval() if workload in ("full", "train") else None
         swin = model.swin if model is not None else mv.build_model(mv.default_config()).eval()
         synth.randomize_for_parity(model if model is not None else swin, seed=777)
         img = synth.images(sample, 448, seed=1)
@@ -251,10 +316,14 @@ def cpu_oracle_runner(workload, sample):
             ids = synth.token_ids(sample, 512, seed=1)
             hb = to_host_batch(synth.cpg_batch(sample, seed=1))
             sd_u, sd_f = model.unix.state_dict(), model.fusion.state_dict()
+            labels = torch.randint(0, 2, (sample,), generator=torch.Generator().manual_seed(1))
 
             def fn():
                 fi = oswin.forward_features(sd_s, SwinGeometry(), img)
                 ft = orob.get_repr(sd_u, RobertaGeometry(), ids)
+                if workload == "train":                 # fp32 autograd step of the fusion model (no optimiser cost)
+                    from oracle import fusion_train
+                    return fusion_train.loss_and_grads(sd_f, hb, fi, ft, labels)[0]
                 return ofus.fusion_forward(sd_f, hb, fi, ft)
     return fn
 
@@ -265,7 +334,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count())
-    sample = {"full": 2, "swin": 2, "ggnn": 64}[args.workload]
+    sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2}[args.workload]
     fn = cpu_oracle_runner(args.workload, sample)
     for _ in range(max(1, min(args.warmup, 1))):
         fn()
@@ -274,9 +343,9 @@ def run_reference(args, rank):
         fn()
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
-    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s"}[args.workload]
+    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s", "train": "functions/s"}[args.workload]
     print(json.dumps({
-        "impl": "reference", "metric": "MVulD functions/sec (fwd)", "value": v, "unit": unit, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.get(args.workload, f"{args.workload} branch {unit}"), "value": v, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "sample": f"{sample} units per step on the host CPU"},
@@ -303,7 +372,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from mvuld_b200 import _lib
     wl = build_workload(args, rank, device)
-    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s"}[args.workload]
+    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s", "train": "functions/s"}[args.workload]
 
     def barrier():
         if world > 1:
@@ -349,6 +418,41 @@ def main():
     ms_e2e = max_over_ranks(s.elapsed_time(e))
     e2e = wl["units"] * world * args.steps / (ms_e2e / 1e3)
 
+    # ---- train-step leg of the default workload (configs[4]) on the same model, same N ----
+    train_obj = None
+    if args.workload == "full" and not args.no_train:
+        twl = build_train_workload(args, rank, device, world, model=wl["model"])
+        tdev = twl["to_dev"]()
+        tsteps = min(args.steps, 10)
+        for _ in range(3):
+            twl["step"](tdev)
+        barrier()
+        tl0 = _lib.launch_count
+        s.record()
+        for _ in range(tsteps):
+            twl["step"](tdev)
+        e.record()
+        barrier()
+        tms = max_over_ranks(s.elapsed_time(e))
+        tlaunch = _lib.launch_count - tl0
+        for _ in range(2):
+            twl["step"](twl["to_dev"]()).cpu()
+        barrier()
+        s.record()
+        for _ in range(tsteps):
+            loss_host = twl["step"](twl["to_dev"]()).cpu()
+        e.record()
+        barrier()
+        tms_e2e = max_over_ranks(s.elapsed_time(e))
+        train_obj = {"metric": METRIC["train"], "value": twl["units"] * world * tsteps / (tms / 1e3),
+                     "unit": "functions/s", "steps": tsteps, "warmup": 3, "ms_per_step": tms / tsteps,
+                     "per_gpu_batch": twl["units"], "global_batch": twl["units"] * world, "workload": twl["name"],
+                     "e2e": {"value": twl["units"] * world * tsteps / (tms_e2e / 1e3), "unit": "functions/s",
+                             "h2d_bytes_per_step": int(twl["h2d"]), "d2h_bytes_per_step": 4},
+                     "gpu_launches": int(tlaunch), "last_loss": float(loss_host),
+                     "gradient_allreduce": (f"NCCL, {len(twl['trainer'].buckets)} buckets over "
+                                            f"{twl['trainer'].total * 4 / 1e6:.1f} MB fp32" if world > 1 else "none (1 GPU)")}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,17 +460,20 @@ def main():
 
     pk = peaks()
     line = {
-        "metric": "MVulD functions/sec (fwd)" if args.workload == "full" else f"{args.workload} branch {unit}",
+        "metric": METRIC.get(args.workload, f"{args.workload} branch {unit}"),
         "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "per_gpu_batch": wl["units"], "parallelism": f"batch-shard x{world}, no "
-                   "data-path collective", "l2_policy": "per-step inputs + activations exceed the 126 MB L2"},
+                   "data-path collective" if args.workload != "train" else f"data-parallel x{world}, bucketed NCCL "
+                   "gradient all-reduce", "l2_policy": "per-step inputs + activations exceed the 126 MB L2"},
         "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(wl["h2d"]), "d2h_bytes_per_step": int(wl["d2h"])},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if wl["flops_per_unit"]:
         line["model_tflops"] = wl["flops_per_unit"] * value / world / 1e12
+    if train_obj is not None:
+        line["train"] = train_obj
 
     if not args.no_roofline:
         inst = Instrument()
@@ -384,8 +491,10 @@ def main():
             g = dev_in["g"]
             alg = g.num_edges() * 200 * 2 + g.num_edges() * 5 + (g.num_nodes() + 1) * 4 + g.num_nodes() * 200 * 2
             ach = alg / (k["ms"] / k["launches"] / 1e3) / 1e9
+            tr = captured_traffic("ggnn_gather_sum")
             line["roofline"] = {"bound": "hbm", "kernel": "ggnn_gather_sum_kernel", "achieved": ach, "peak": pk["hbm"],
-                                "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                                "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": tr["bytes"] if tr else None,
+                                "algorithmic_bytes_per_launch": alg, "peak_source": pk["src"],
                                 "share_of_step": k["ms"] / total_ms}
         else:
             kname, d = top
@@ -395,8 +504,13 @@ def main():
                                                               "attention": "attn_fwd_kernel",
                                                               "other": "row/graph kernels"}[kname],
                                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                                "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"] +
+                                "frac": ach / pk["bf16_sustained"], "frac_of_burst_peak": ach / pk["bf16"],
+                                "traffic": None, "peak_source": pk["src"] +
                                 " (sustained: kernel timed inside a long step)", "share_of_step": d["ms"] / total_ms}
+            tr = captured_traffic(kname)
+            if tr:
+                line["roofline"]["traffic"] = tr["bytes"]
+                line["roofline"]["traffic_note"] = f"one launch of {tr['kernel']} ({tr['source']})"
         line["kernel_families"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                        "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else 0.0}
                                    for k, v in fam.items()}
@@ -412,7 +526,7 @@ def main():
 
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count())
-        sample = {"full": 2, "swin": 2, "ggnn": 64}[args.workload]
+        sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2}[args.workload]
         fn = cpu_oracle_runner(args.workload, sample)
         fn()
         t0 = time.perf_counter()
