@@ -228,8 +228,9 @@ int mvuld_ce_loss(const float* logits, const long long* labels, float* loss_sum,
                   float scale, mvuld_stream_t stream);
 int mvuld_linear_small_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int M,
                            int N, int K, mvuld_stream_t stream);
-/* out += sum x^2 (global gradient norm of clip_grad_norm_, utils_multi.py:233). */
-int mvuld_sumsq_f32(const float* x, long long n, float* out, mvuld_stream_t stream);
+/* out += sum x^2 (global gradient norm of clip_grad_norm_, utils_multi.py:233).  partials: scratch of 1184 floats; the
+ * reduction order is fixed, so identical (all-reduced) gradients give a bit-identical norm on every rank. */
+int mvuld_sumsq_f32(const float* x, long long n, float* partials, float* out, mvuld_stream_t stream);
 /* clipped AdamW on a flat fp32 buffer with per-segment weight decay (optimizer.py:11-33: decay / no-decay groups). */
 int mvuld_adamw(float* p, const float* g, float* m, float* v, long long n, const long long* seg_end,
                 const float* seg_wd, int nseg, const float* gnorm_sq, float max_norm, float lr, float beta1,

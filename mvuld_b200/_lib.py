@@ -67,14 +67,14 @@ SIGNATURES = {
     "mvuld_l2norm_mean_bwd": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
     "mvuld_ce_loss": [_P, _P, _P, _P, _I, _I, _F, _P],
     "mvuld_linear_small_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
-    "mvuld_sumsq_f32": [_P, _LL, _P, _P],
+    "mvuld_sumsq_f32": [_P, _LL, _P, _P, _P],
     "mvuld_adamw": [_P, _P, _P, _P, _LL, _P, _P, _I, _P, _F, _F, _F, _F, _F, _I, _P],
     "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 13 + [_P, _P],
 }
 
 _lib = None
 launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3}
+_LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3, "mvuld_sumsq_f32": 2}
 
 
 def load() -> C.CDLL:

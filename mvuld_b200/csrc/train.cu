@@ -771,7 +771,17 @@ sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) 
     s += v * v;
   }
   s = block_sum(s, sh);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;       // per-block partial: the final sum runs in a fixed order
+}
+// out[0] += sum of the partials, one block, fixed order: identical gradients give a bit-identical norm on every rank
+// (a float atomicAdd tree would let data-parallel replicas drift apart through the clip factor)
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] += s;
 }
 // AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments) on a flat fp32 parameter
 // buffer; gradients are first scaled by min(1, max_norm / (||g|| + 1e-6)) (clip_grad_norm_, utils_multi.py:233).
@@ -966,11 +976,13 @@ extern "C" int mvuld_linear_small_bwd(const float* x, const float* w, const floa
   MV_LAUNCH_OK();
   return 0;
 }
-extern "C" int mvuld_sumsq_f32(const float* x, long long n, float* out, cudaStream_t stream) {
+extern "C" int mvuld_sumsq_f32(const float* x, long long n, float* partials, float* out, cudaStream_t stream) {
   if (n <= 0) return 0;
   long long blocks = (n + 255) / 256;
   if (blocks > 1184) blocks = 1184;
-  sumsq_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, out);
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n, partials);
+  MV_LAUNCH_OK();
+  sumsq_final_kernel<<<1, 256, 0, stream>>>(partials, (int)blocks, out);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -142,6 +142,7 @@ class FusionTrainer:
         self.seg_wd = torch.tensor(seg_wd, dtype=torch.float32, device=dev)
         self.buckets = plan_buckets(seg_end, int(bucket_mb * (1 << 20) / 4))
         self.gnorm_sq = torch.zeros(1, **f32)
+        self.gnorm_partials = torch.zeros(1184, **f32)
         self.loss_buf = torch.zeros(1, **f32)
         self._refresh_shadows()
         self.last = {}
@@ -479,7 +480,7 @@ class FusionTrainer:
         for w in works:
             w.wait()
         self.gnorm_sq.zero_()
-        _lib.call("mvuld_sumsq_f32", self.flat_g, self.total, self.gnorm_sq)
+        _lib.call("mvuld_sumsq_f32", self.flat_g, self.total, self.gnorm_partials, self.gnorm_sq)
         _lib.call("mvuld_adamw", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.total, self.seg_end,
                   self.seg_wd, int(self.seg_end.numel()), self.gnorm_sq, self.clip, float(self.lr if lr is None else lr),
                   float(self.betas[0]), float(self.betas[1]), self.eps, self.step_count)
