@@ -215,14 +215,14 @@ def build_workload(args, rank, device):
                 f"Rs_GCN x8 fusion, {B} synthetic functions per GPU per step, avg "
                 f"{host['g'].num_nodes() / B:.0f} CPG nodes")
         return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name, flops_per_unit=262.1e9,
-                    model=model)
+                    model=model, host=host)
     if args.workload == "swin":
         B = args.batch or 64
         model = mv.build_model(mv.default_config()).eval()
         synth.randomize_for_parity(model, seed=777)
         model = model.to(device)
         host = dict(img=synth.images(B, 448, seed=seed).pin_memory())
-        return dict(units=B, to_dev=lambda: dict(img=host["img"].to(device, non_blocking=True)),
+        return dict(units=B, to_dev=lambda: dict(img=host["img"].to(device, non_blocking=True)), host=host,
                     step=lambda d: model.forward_features(d["img"]), h2d=host["img"].numel() * 4, d2h=B * 1024 * 4,
                     name=f"SwinV2-B image branch alone (configs[1]), 448px window28, bf16 inference batch={B}",
                     flops_per_unit=159.08e9)
@@ -238,7 +238,9 @@ def build_workload(args, rank, device):
         return model(d["g"])[1]
 
     h2d = g._src.numel() * 16 + g.edata["_ETYPE"].numel() * 8 + g.ndata["_WORD2VEC"].numel() * 4
-    return dict(units=B, to_dev=lambda: dict(g=g.to(device, non_blocking=True)), step=step, h2d=h2d, d2h=B * 4,
+    g._src, g._dst, g.edata["_ETYPE"] = g._src.pin_memory(), g._dst.pin_memory(), g.edata["_ETYPE"].pin_memory()
+    return dict(units=B, to_dev=lambda: dict(g=g.to(device, non_blocking=True)), host=dict(g=g), step=step, h2d=h2d,
+                d2h=B * 4,
                 name=f"GGNN graph branch (configs[2]): {B} batched CPGs, {g.num_nodes()} nodes, {g.num_edges()} edges, "
                      "4 edge types, D=200, 6 steps, segment-sum readout", flops_per_unit=0.0)
 
@@ -286,7 +288,7 @@ def build_train_workload(args, rank, device, world, model=None):
             f"{trainer.total * 4 / 1e6:.1f} MB fp32), clip 5.0 + AdamW; {B} functions per GPU (global batch {B * world}), "
             f"avg {host['g'].num_nodes() / B:.0f} CPG nodes")
     return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name, flops_per_unit=262.1e9 + 3 * 6.4e9,
-                trainer=trainer)
+                trainer=trainer, host=host)
 
 
 def cpu_oracle_runner(workload, sample):
@@ -407,12 +409,20 @@ def main():
     value = wl["units"] * world * args.steps / (ms / 1e3)
 
     # ---- end to end through the public API: pinned host inputs in, logits out, every step ----
-    for _ in range(2):
-        o = wl["step"](wl["to_dev"]()).cpu()
+    # (mvuld_b200.prefetch: batch i+1 is copied on a side stream while batch i computes; every step's inputs are
+    #  copied from pinned host memory and every step's result is read back inside the timed region)
+    from mvuld_b200.prefetch import DevicePrefetcher, ResultSink
+
+    def e2e_pass(w, n):
+        sink = ResultSink(n)
+        for d in DevicePrefetcher((w["host"] for _ in range(n)), device):
+            sink.push(w["step"](d))
+        return sink.results()
+
+    e2e_pass(wl, args.steps)              # also warms the pinned result buffers (cached by torch's host allocator)
     barrier()
     s.record()
-    for _ in range(args.steps):
-        o = wl["step"](wl["to_dev"]()).cpu()
+    e2e_pass(wl, args.steps)
     e.record()
     barrier()
     ms_e2e = max_over_ranks(s.elapsed_time(e))
@@ -435,12 +445,10 @@ def main():
         barrier()
         tms = max_over_ranks(s.elapsed_time(e))
         tlaunch = _lib.launch_count - tl0
-        for _ in range(2):
-            twl["step"](twl["to_dev"]()).cpu()
+        e2e_pass(twl, tsteps)
         barrier()
         s.record()
-        for _ in range(tsteps):
-            loss_host = twl["step"](twl["to_dev"]()).cpu()
+        loss_host = e2e_pass(twl, tsteps)[-1]
         e.record()
         barrier()
         tms_e2e = max_over_ranks(s.elapsed_time(e))

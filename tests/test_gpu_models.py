@@ -159,3 +159,25 @@ def test_composed_forward_matches_oracle():
     torch.cuda.synchronize()
     assert logits_close(out, ref, 2e-2), (out.cpu(), ref)
     assert torch.equal(out.cpu().argmax(1), ref.argmax(1))
+
+
+def test_device_prefetcher_yields_identical_batches_and_results():
+    """mvuld_b200.prefetch: batches staged on the copy stream give the same logits as synchronous staging."""
+    from mvuld_b200.prefetch import DevicePrefetcher, ResultSink
+    fus = cases.make_fusion().to(DEV)
+    batches = []
+    for i in range(3):
+        g = synth.cpg_batch(2, seed=cases.SEED + i)
+        gen = torch.Generator().manual_seed(i)
+        for k in list(g.ndata):
+            g.ndata[k] = g.ndata[k].pin_memory()
+        batches.append(dict(g=g, img=torch.randn(2, 1024, generator=gen).pin_memory(),
+                            txt=torch.randn(2, 768, generator=gen).pin_memory()))
+    want = [fus(b["g"].to(DEV), b["img"].to(DEV), b["txt"].to(DEV)).cpu() for b in batches]
+    sink = ResultSink(3)
+    for d in DevicePrefetcher(batches, DEV):
+        sink.push(fus(d["g"], d["img"], d["txt"]))
+    got = sink.results()
+    assert len(got) == 3 and all(torch.equal(a, b) for a, b in zip(got, want))
+    with pytest.raises(RuntimeError):
+        DevicePrefetcher(batches, "cpu")
