@@ -114,6 +114,9 @@ def work_of(name, args):
     if name == "mvuld_gemm_bf16":
         M, N, K = args["M"], args["N"], args["K"]
         return "gemm", 2.0 * M * N * K, 0.0
+    if name == "mvuld_gemm_gru":
+        M, D, K = args[4], args[5], args[6]
+        return "gemm", 2.0 * M * 4 * D * K, 0.0
     if name == "mvuld_gemm_ln_bf16":
         M, N, K = args[4], args[5], args[6]
         return "gemm", 2.0 * M * N * K, 0.0

@@ -115,14 +115,21 @@ int mvuld_csr_from_coo(const long long* src, const long long* dst, int E, int N,
 /* etype_sorted[i] = uint8(etype[eids[i]]); status[0] = 1 if any etype outside [0, n_etypes) (DGL asserts). */
 int mvuld_gather_etype(const long long* etype, const int* eids, int E, int n_etypes, unsigned char* out, int* status,
                        mvuld_stream_t stream);
-/* a[dst] = sum over in-edges of msgs[src, etype, :]; msgs bf16 [N, T, D], out bf16 [N, D].
+/* a[dst] = sum over in-edges of msgs[src, etype, :]; msgs bf16 [N, T, D], out bf16 [N, D] with row stride ldo.
  * DGL GatedGraphConv message + reduce (baselines/models/reveal/ggnn/model.py:23, devign/model.py:35). */
 int mvuld_ggnn_gather_sum(const void* msgs, const int* indptr, const int* idx_src, const unsigned char* etype,
-                          void* out, int N, int T, int D, mvuld_stream_t stream);
-/* GRUCell gates, in place on h32 (+ bf16 shadow). gi, gh bf16 [N, 3D]. */
+                          void* out, int ldo, int N, int T, int D, mvuld_stream_t stream);
+/* GRUCell gates, in place on h32 (+ bf16 shadow). gi, gh bf16 [N, 3D].  (Unfused form; the models use mvuld_gemm_gru.) */
 int mvuld_gru_gates(const void* gi, const void* gh, float* h32, void* hb, long long N, int D, mvuld_stream_t stream);
-/* h0 = cat(x, 0) zero padding of GatedGraphConv. */
-int mvuld_ggnn_init(const float* x, float* h32, void* hb, long long N, int in_dim, int D, mvuld_stream_t stream);
+/* GRUCell of GatedGraphConv as ONE GEMM with the gates in its epilogue: A = [a | h] bf16 [M, K = 2D] (row stride lda),
+ * Wg bf16 [4D, K] with rows 4j..4j+3 = (W_ir | W_hr), (W_iz | W_hz), (W_in | 0), (0 | W_hn) of feature j, bias4 fp32
+ * [4D] = (b_ir + b_hr, b_iz + b_hz, b_in, b_hn) interleaved; h32 fp32 [M, D] updated in place, the bf16 state is
+ * written to hb_out (row stride ldhb), which must not be the buffer A is read from. */
+int mvuld_gemm_gru(const void* A, int lda, const void* Wg, int ldw, int M, int D, int K, const float* bias4, float* h32,
+                   void* hb_out, int ldhb, mvuld_stream_t stream);
+/* h0 = cat(x, 0) zero padding of GatedGraphConv; hb has row stride ldb. */
+int mvuld_ggnn_init(const float* x, float* h32, void* hb, int ldb, long long N, int in_dim, int D,
+                    mvuld_stream_t stream);
 /* per-graph segment sum (reveal/ggnn/model.py:26-28,46-56): feat fp32 [N, D], offsets int64 [B+1] -> out [B, D]. */
 int mvuld_segment_sum(const float* feat, const long long* offsets, float* out, int B, int D, mvuld_stream_t stream);
 /* GATConv pieces (GraphModel.py:99-105,167-170): el/er scores, then edge-softmax + weighted aggregate + bias. */

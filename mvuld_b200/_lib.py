@@ -35,9 +35,10 @@ SIGNATURES = {
     "mvuld_masked_mean": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_csr_from_coo": [_P, _P, _I, _I, _P, C.POINTER(C.c_size_t), _P, _P, _P, _P, _P],
     "mvuld_gather_etype": [_P, _P, _I, _I, _P, _P, _P],
-    "mvuld_ggnn_gather_sum": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_ggnn_gather_sum": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_gemm_gru": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "mvuld_gru_gates": [_P, _P, _P, _P, _LL, _I, _P],
-    "mvuld_ggnn_init": [_P, _P, _P, _LL, _I, _I, _P],
+    "mvuld_ggnn_init": [_P, _P, _P, _I, _LL, _I, _I, _P],
     "mvuld_segment_sum": [_P, _P, _P, _I, _I, _P],
     "mvuld_gat_scores": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_gat_aggregate": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P],

@@ -91,15 +91,19 @@ rs_gcn_affinity_kernel(const TIn* __restrict__ tpg, bf16* __restrict__ y, float*
       for (int c = 0; c < 10; ++c) {
         const float v = acc[a][c] * inv;
         R[(ti * 5 + a) * (RS_MAXN + 1) + tj * 10 + c] = v;
-        if (r_out && ti * 5 + a < n && tj * 10 + c < n)
+        if (r_out && blockIdx.y == 0 && ti * 5 + a < n && tj * 10 + c < n)
           r_out[((size_t)b * n + ti * 5 + a) * n + tj * 10 + c] = v;
       }
   }
   __syncthreads();
 
   // ---- phase 2: y = R g ; thread (yi, yj) owns rows yi*4..+4, cols yj*8..+8 of each 64-column chunk ----
+  // gridDim.y CTAs share a graph: each recomputes R (phase 1) and produces its own slice of y's columns, so that
+  // 64 graphs fill the 148 SMs
   const int yi = tid / 8, yj = tid % 8;
-  for (int c0 = 0; c0 < C; c0 += 64) {
+  const int c_per = ((C / 64 + gridDim.y - 1) / gridDim.y) * 64;
+  const int c_beg = blockIdx.y * c_per, c_end = min(C, c_beg + c_per);
+  for (int c0 = c_beg; c0 < c_end; c0 += 64) {
     for (int i = tid; i < RS_MAXN * 8; i += 256) {
       const int row = i >> 3, part = i & 7;
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -243,7 +247,7 @@ extern "C" int mvuld_rs_gcn_affinity(const void* tpg, void* y, float* r_out, int
   const int smem = (RS_MAXN * (RS_MAXN + 1) + RS_MAXN * 64 + RS_MAXN * 33) * sizeof(float);
   auto kern = rs_gcn_affinity_kernel<bf16, false>;
   MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<B, 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<bf16*>(y), r_out, n, C);
+  kern<<<dim3(B, B >= 148 ? 2 : 4), 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<bf16*>(y), r_out, n, C);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -256,7 +260,7 @@ extern "C" int mvuld_rs_gcn_affinity_f32(const float* tpg, void* y3, float* r_ou
   const int smem = (RS_MAXN * (RS_MAXN + 1) + RS_MAXN * 64 + RS_MAXN * 33) * sizeof(float);
   auto kern = rs_gcn_affinity_kernel<float, true>;
   MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<B, 256, smem, stream>>>(tpg, reinterpret_cast<bf16*>(y3), r_out, n, C);
+  kern<<<dim3(B, B >= 148 ? 2 : 4), 256, smem, stream>>>(tpg, reinterpret_cast<bf16*>(y3), r_out, n, C);
   MV_LAUNCH_OK();
   return 0;
 }

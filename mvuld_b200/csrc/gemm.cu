@@ -10,6 +10,8 @@
 //   warps 2..9  epilogue       : tcgen05.ld 32 lanes x 32 columns, fused epilogue, 128-bit global stores
 //                                (two warps per TMEM lane quarter, each draining half of the tile's columns)
 //   TMEM        2 x BN fp32 columns: the epilogue of tile i overlaps the mainloop of tile i+1
+#include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "host_util.h"
 
@@ -122,8 +124,13 @@ struct EpiBf16Tma {
       }
     }
     if (act == 1) {
+#ifdef MV_GELU_SCALAR
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+#else
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) gelu_erf2(v[i], v[i + 1]);
+#endif
     } else if (act == 2) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = elu1(v[i]);
@@ -248,34 +255,96 @@ struct EpiQkvHeads {
   }
 };
 
+// GRUCell epilogue of DGL GatedGraphConv (torch.nn.GRUCell, gate order r, z, n): the GEMM computes, for node row n and
+// feature j, the four pre-activations in ADJACENT columns 4j .. 4j+3 of  [a | h] (K = 2D) x Wg^T:
+//   4j   r : W_ir a + W_hr h      4j+1  z : W_iz a + W_hz h      4j+2  i_n : W_in a      4j+3  h_n : W_hn h
+// (bias4 holds b_ir + b_hr, b_iz + b_hz, b_in, b_hn interleaved the same way), so one thread owns all it needs for
+//   h' = (1 - z) * tanh(i_n + r * h_n) + z * h.
+// h32 (fp32 state) is updated in place; the bf16 shadow goes to ANOTHER buffer than the one the A operand is read from
+// (other tiles of the same rows are still loading it).  Replaces two GEMMs writing gi / gh (2 x N x 3D bf16) and the
+// element-wise gate kernel that read them back.
+struct EpiGru {
+  static constexpr bool kStaged = false;
+  static constexpr bool kPrefetch = true;
+  struct Pre { float4 h0, h1; };
+  const float* bias4;  // [4D]
+  float* h32;          // [M, D]
+  bf16* hb;            // [M, ldhb]
+  int ldhb, M, D;
+  // the old state of the 8 features of this chunk, requested BEFORE the wait on the accumulator: the HBM latency of
+  // this read would otherwise sit in the epilogue's critical path twice per tile
+  __device__ __forceinline__ void prefetch(int row, int col0, Pre& p) const {
+    if (row >= M || col0 >= 4 * D) return;
+    const float* hp = h32 + (size_t)row * D + (col0 >> 2);
+    p.h0 = *reinterpret_cast<const float4*>(hp);
+    p.h1 = *reinterpret_cast<const float4*>(hp + 4);
+  }
+  __device__ __forceinline__ void operator()(int row, int col0, const uint32_t (&r)[32], const Pre& p) const {
+    if (row >= M || col0 >= 4 * D) return;
+    const int j0 = col0 >> 2;
+    float* hp = h32 + (size_t)row * D + j0;
+    const float h[8] = {p.h0.x, p.h0.y, p.h0.z, p.h0.w, p.h1.x, p.h1.y, p.h1.z, p.h1.w};
+    float o[8];
+    constexpr float L2E = 1.4426950408889634f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias4 + col0) + q);
+      const float pr = __uint_as_float(r[4 * q]) + b.x, pz = __uint_as_float(r[4 * q + 1]) + b.y;
+      const float pi = __uint_as_float(r[4 * q + 2]) + b.z, ph = __uint_as_float(r[4 * q + 3]) + b.w;
+      const float rg = rcp_approx(1.0f + ex2_approx(-pr * L2E));
+      const float zg = rcp_approx(1.0f + ex2_approx(-pz * L2E));
+      const float nn = 1.0f - 2.0f * rcp_approx(1.0f + ex2_approx(2.0f * L2E * (pi + rg * ph)));   // tanh
+      o[q] = (1.0f - zg) * nn + zg * h[q];
+    }
+    *reinterpret_cast<float4*>(hp) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(hp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(hb + (size_t)row * ldhb + j0) = w;
+  }
+};
+
+// epilogues that want operands fetched before the accumulator is ready declare kPrefetch + Pre + prefetch()
+template <class E, class = void>
+struct epi_prefetch : std::false_type { struct Pre {}; };
+template <class E>
+struct epi_prefetch<E, std::void_t<decltype(E::kPrefetch)>> : std::true_type { using Pre = typename E::Pre; };
+
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// BKB > 0 selects the WEIGHT-STATIONARY schedule for skinny-K problems (K <= 64 BKB): a CTA keeps its BN x K weight
+// panel resident in shared memory (loaded once), owns one column block and walks row blocks, so only A streams through
+// the ring.  With the streaming schedule a 128 x 128 tile at K = 448 pulls 114 KB of A and 114 KB of W through L2 for
+// 32 KB of output; the GGNN GEMMs (M = 825 k, K = 200 / 400) sat at 8.4 TB/s of L2 traffic, not at HBM or MMA limits.
+template <int BN, int STAGES, int BKB = 0>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = BKB > 0 ? A_BYTES : A_BYTES + B_BYTES;    // bytes one ring slot receives
+  static constexpr int B_TOTAL = (BKB > 0 ? BKB : STAGES) * B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SLAB_BYTES = 32 * 128;                                  // [32 rows x 64 bf16] per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_WARPS * SLAB_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * A_BYTES + B_TOTAL + GEMM_EPI_WARPS * SLAB_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;                                    // 256 or 512 (power of two)
 };
 
-template <int BN, int STAGES, class Epi>
+template <int BN, int STAGES, class Epi, int BKB = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
-  using Cfg = GemmCfg<BN, STAGES>;
+  using Cfg = GemmCfg<BN, STAGES, BKB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* sC = smem + STAGES * Cfg::STAGE_BYTES;                       // staged epilogue slabs (kStaged only)
+  uint8_t* sC = smem + STAGES * Cfg::A_BYTES + Cfg::B_TOTAL;            // staged epilogue slabs (kStaged only)
   uint64_t* full = reinterpret_cast<uint64_t*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bfull = tempty + 2;                                          // weight panel resident (BKB > 0)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -283,6 +352,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  // tile walk: streaming = tiles blockIdx.x, + gridDim.x, ... in row-major (m, n) order; weight-stationary = fixed
+  // column block blockIdx.x % n_tiles, row blocks blockIdx.x / n_tiles, + gridDim.x / n_tiles, ... (the host makes
+  // gridDim.x a multiple of n_tiles).  `it` counts this CTA's tiles.
+  const int ws_groups = BKB > 0 ? (int)gridDim.x / n_tiles : 1;
+  const int ws_n = BKB > 0 ? (int)blockIdx.x % n_tiles : 0;
+  auto tile_at = [&](int it, int& m_blk, int& n_blk) -> bool {
+    if (BKB > 0) {
+      m_blk = (int)blockIdx.x / n_tiles + it * ws_groups;
+      n_blk = ws_n;
+      return m_blk < m_tiles;
+    }
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    m_blk = tile / n_tiles;
+    n_blk = tile - m_blk * n_tiles;
+    return tile < num_tiles;
+  };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -295,6 +380,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], GEMM_THREADS - 64);
     }
+    mbar_init(bfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -310,13 +396,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      int m_blk, n_blk;
+      if (BKB > 0 && tile_at(0, m_blk, n_blk)) {                         // the weight panel, once
+        mbar_arrive_expect_tx(bfull, num_kb * Cfg::B_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, bfull, kb * GEMM_BK, n_blk * BN);
+      }
+      for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+          if (BKB == 0) tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -326,8 +417,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      int m_blk, n_blk;
+      if (BKB > 0 && tile_at(0, m_blk, n_blk)) mbar_wait(bfull, 0, 5);
+      for (int local = 0; tile_at(local, m_blk, n_blk); ++local) {
         const int acc = local & 1;
         mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1, 2);
         tc_fence_after();
@@ -336,7 +428,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
           const uint32_t a0 = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b0 = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint32_t b0 = smem_u32(sB + (BKB > 0 ? kb : stage) * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, 2);
@@ -354,13 +446,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int part = (warp - 2) >> 2;    // which slice of the tile's columns this warp drains
     constexpr int PARTS = GEMM_EPI_WARPS / 4;
     constexpr int CPP = (BN / 32) / PARTS;   // 32-column chunks per warp
-    int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+    int m_blk, n_blk;
+    for (int local = 0; tile_at(local, m_blk, n_blk); ++local) {
       const int acc = local & 1;
+      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+      typename epi_prefetch<Epi>::Pre pre[CPP];
+      if constexpr (epi_prefetch<Epi>::value) {
+#pragma unroll
+        for (int i = 0; i < CPP; ++i) epi.prefetch(row, n_blk * BN + (part * CPP + i) * 32, pre[i]);
+      }
       mbar_wait(&tfull[acc], (local >> 1) & 1, 4);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + quarter * 32 + lane;
       const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
       // the TMEM load of the next chunk is in flight while the epilogue math of this one runs
       uint32_t r[2][32];
@@ -399,7 +495,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int c = part * CPP + i;
           tmem_ld_wait();
           if (i + 1 < CPP) tmem_ld32(t0 + (c + 1) * 32, r[(i + 1) & 1]);
-          epi(row, n_blk * BN + c * 32, r[i & 1]);
+          if constexpr (epi_prefetch<Epi>::value) epi(row, n_blk * BN + c * 32, r[i & 1], pre[i]);
+          else epi(row, n_blk * BN + c * 32, r[i & 1]);
         }
       }
       tc_fence_before();
@@ -412,10 +509,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int STAGES, class Epi>
+template <int BN, int STAGES, class Epi, int BKB = 0>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi,
                        cudaStream_t stream, void* out_bf16 = nullptr, int ldc = 0) {
-  using Cfg = GemmCfg<BN, STAGES>;
+  using Cfg = GemmCfg<BN, STAGES, BKB>;
+  static_assert(Cfg::SMEM_BYTES <= 232448, "GEMM configuration exceeds the 227 KB of shared memory per CTA");
+  MV_CHECK_ARG(BKB == 0 || K <= BKB * GEMM_BK, "gemm: weight-stationary schedule holds K <= %d (K=%d)", BKB * GEMM_BK, K);
   MV_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   MV_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements (16 B): %d %d", lda, ldw);
   CUtensorMap tmA, tmB;
@@ -441,14 +540,20 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, in
     int rc = make_tmap_16b(&tmC, out_bf16, 2, dims, str, box, 128);
     if (rc) return rc;
   }
-  auto kern = gemm_tn_kernel<BN, STAGES, Epi>;
+  auto kern = gemm_tn_kernel<BN, STAGES, Epi, BKB>;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int n_tiles_h = (N + BN - 1) / BN;
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * n_tiles_h;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (BKB > 0) {                                   // a multiple of the column blocks, at least one CTA per column block
+    MV_CHECK_ARG(n_tiles_h <= num_sms(), "gemm: weight-stationary schedule needs N / %d <= SM count", BN);
+    grid = (grid / n_tiles_h) * n_tiles_h;
+    if (grid == 0) grid = n_tiles_h;
+  }
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi);
   MV_LAUNCH_OK();
   return 0;
@@ -468,7 +573,11 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   if (out_bf16 && !out_f32 && !res_f32 && ((uintptr_t)out_bf16 % 16) == 0) {
     EpiBf16Tma t;
     t.bias = bias; t.act = act; t.M = M; t.N = N;
+    // skinny-K, tall-M problems keep the weight panel resident (see GemmCfg)
+    const bool ws = K <= 256 && (long long)M >= 128ll * 2 * num_sms() && getenv("MVULD_GEMM_NO_WS") == nullptr;
+    // (measured neutral for the 128 x 256 tiles of the Swin stage-0 / 1 layers, whose GELU epilogue sets the pace)
     if (big) return launch_gemm<256, 4, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
+    if (ws) return launch_gemm<128, 6, EpiBf16Tma, 4>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
     return launch_gemm<128, 6, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
   }
   EpiGeneric e;
@@ -478,6 +587,18 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   if (N % 256 == 0 && (long long)M * N >= 256ll * 256 * 148)
     return launch_gemm<256, 4, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
   return launch_gemm<128, 6, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
+}
+
+extern "C" int mvuld_gemm_gru(const void* A, int lda, const void* Wg, int ldw, int M, int D, int K, const float* bias4,
+                              float* h32, void* hb_out, int ldhb, cudaStream_t stream) {
+  MV_CHECK_ARG(D % 8 == 0 && ldhb % 8 == 0, "gemm_gru: D and ldhb must be multiples of 8 (D=%d ldhb=%d)", D, ldhb);
+  MV_CHECK_ARG(bias4 && h32 && hb_out, "gemm_gru: null pointer");
+  MV_CHECK_ARG((const void*)hb_out != A, "gemm_gru: the bf16 state must be written to another buffer than A");
+  EpiGru e;
+  e.bias4 = bias4; e.h32 = h32; e.hb = reinterpret_cast<bf16*>(hb_out); e.ldhb = ldhb; e.M = M; e.D = D;
+  if (K <= 448 && (long long)M >= 128ll * 2 * num_sms() && getenv("MVULD_GEMM_NO_WS") == nullptr)
+    return launch_gemm<128, 4, EpiGru, 7>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
+  return launch_gemm<128, 6, EpiGru>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
 }
 
 extern "C" int mvuld_swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias,

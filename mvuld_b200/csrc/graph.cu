@@ -47,53 +47,64 @@ __global__ void gather_etype_kernel(const long long* __restrict__ etype, const i
 }
 
 // ------------------------------------------- GGNN aggregation -------------------------------------------
-// msgs: bf16 [N, T, D] (per-etype linear already applied, bias included); one warp per destination node.
-template <int UNROLL>
+// msgs: bf16 [N, T, D] (per-etype linear already applied, bias included).  One warp owns NPW consecutive destination
+// nodes and walks their (contiguous) in-edge range as one flat list, UNROLL gathered rows in flight at a time: a
+// warp-per-node version spent two thirds of its time in the indptr -> (src, etype) -> row dependency chain with
+// nothing in flight (measured 3.1 TB/s DRAM); here the chain is paid once per NPW nodes and row loads of the next
+// node are issued while the previous node is still being summed.  Sums run in edge order per node (fp32).
+template <int UNROLL, int NPW>
 __global__ void __launch_bounds__(256)
 ggnn_gather_sum_kernel(const bf16* __restrict__ msgs, const int* __restrict__ indptr, const int* __restrict__ idx_src,
-                       const unsigned char* __restrict__ etype, bf16* __restrict__ out, int N, int T, int D) {
-  const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (node >= N) return;
+                       const unsigned char* __restrict__ etype, bf16* __restrict__ out, int ldo, int N, int T, int D) {
+  const int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * NPW;
+  if (n0 >= N) return;
   const int lane = threadIdx.x & 31;
   const int units = D >> 3;                 // uint4 per row (25 for D = 200)
   const bool active = lane < units;
-  const int beg = __ldg(indptr + node), end = __ldg(indptr + node + 1);
+  const int n_nodes = min(NPW, N - n0);
+  const int my_ptr = __ldg(indptr + n0 + min(lane, n_nodes));        // lanes 0..n_nodes hold the boundaries
+  const int e_beg = __shfl_sync(0xffffffffu, my_ptr, 0);
+  const int e_end = __shfl_sync(0xffffffffu, my_ptr, n_nodes);
+  int cur = 0;                                                          // node (relative to n0) being summed
+  int boundary = __shfl_sync(0xffffffffu, my_ptr, 1);                   // first edge of the next node
   float acc[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-  for (int base = beg; base < end; base += 32) {
-    const int n_here = min(32, end - base);
+  auto flush = [&]() {
+    if (active) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      reinterpret_cast<uint4*>(out + (size_t)(n0 + cur) * ldo)[lane] = o;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    ++cur;
+    boundary = __shfl_sync(0xffffffffu, my_ptr, min(cur + 1, n_nodes));
+  };
+  for (int base = e_beg; base < e_end; base += 32) {
+    const int n_here = min(32, e_end - base);
     int my_row = 0;
     if (lane < n_here) my_row = __ldg(idx_src + base + lane) * T + (int)__ldg(etype + base + lane);
-    int e = 0;
-    for (; e + UNROLL <= n_here; e += UNROLL) {
+    for (int e = 0; e < n_here; e += UNROLL) {
       uint4 v[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const int row = __shfl_sync(0xffffffffu, my_row, e + u);
-        v[u] = active ? __ldg(reinterpret_cast<const uint4*>(msgs + (size_t)row * D) + lane) : make_uint4(0, 0, 0, 0);
+        const int row = __shfl_sync(0xffffffffu, my_row, (e + u) & 31);
+        v[u] = (active && e + u < n_here) ? __ldg(reinterpret_cast<const uint4*>(msgs + (size_t)row * D) + lane)
+                                          : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
-        acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
-      }
-    }
-    for (; e < n_here; ++e) {
-      const int row = __shfl_sync(0xffffffffu, my_row, e);
-      if (active) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(msgs + (size_t)row * D) + lane);
-        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+        if (e + u < n_here) {
+          while (base + e + u >= boundary && cur < n_nodes - 1) flush();   // (a node without in-edges gets zeros)
+          acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
+          acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
+        }
       }
     }
   }
-  if (active) {
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    reinterpret_cast<uint4*>(out + (size_t)node * D)[lane] = o;
-  }
+  while (cur < n_nodes) flush();            // the last node (and any trailing nodes without in-edges)
 }
 
 // GRUCell gates (torch order r, z, n):  h' = (1 - z) * tanh(i_n + r * h_n) + z * h
@@ -136,7 +147,7 @@ __global__ void gru_gates_kernel(const bf16* __restrict__ gi, const bf16* __rest
 }
 
 // h0 = cat(x, zeros[N, D - in]) (GatedGraphConv zero-pad) -> fp32 state + bf16 shadow
-__global__ void ggnn_init_kernel(const float* __restrict__ x, float* __restrict__ h32, bf16* __restrict__ hb,
+__global__ void ggnn_init_kernel(const float* __restrict__ x, float* __restrict__ h32, bf16* __restrict__ hb, int ldb,
                                  long long N, int in_dim, int D) {
   const long long total = N * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -145,7 +156,7 @@ __global__ void ggnn_init_kernel(const float* __restrict__ x, float* __restrict_
     const int c = (int)(i % D);
     const float v = c < in_dim ? x[n * in_dim + c] : 0.f;
     h32[i] = v;
-    hb[i] = __float2bfloat16(v);
+    hb[n * ldb + c] = __float2bfloat16(v);
   }
 }
 
@@ -440,11 +451,13 @@ extern "C" int mvuld_gather_etype(const long long* etype, const int* eids, int E
 }
 
 extern "C" int mvuld_ggnn_gather_sum(const void* msgs, const int* indptr, const int* idx_src,
-                                     const unsigned char* etype, void* out, int N, int T, int D, cudaStream_t stream) {
+                                     const unsigned char* etype, void* out, int ldo, int N, int T, int D,
+                                     cudaStream_t stream) {
   MV_CHECK_ARG(D % 8 == 0 && D <= 256, "ggnn_gather_sum: D must be a multiple of 8 and <= 256");
+  MV_CHECK_ARG(ldo >= D && ldo % 8 == 0, "ggnn_gather_sum: ldo must be >= D and a multiple of 8");
   if (N <= 0) return 0;
-  ggnn_gather_sum_kernel<4><<<(N + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const bf16*>(msgs), indptr, idx_src,
-                                                            etype, reinterpret_cast<bf16*>(out), N, T, D);
+  ggnn_gather_sum_kernel<8, 8><<<(N + 63) / 64, 256, 0, stream>>>(reinterpret_cast<const bf16*>(msgs), indptr, idx_src,
+                                                            etype, reinterpret_cast<bf16*>(out), ldo, N, T, D);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -460,11 +473,11 @@ extern "C" int mvuld_gru_gates(const void* gi, const void* gh, float* h32, void*
   return 0;
 }
 
-extern "C" int mvuld_ggnn_init(const float* x, float* h32, void* hb, long long N, int in_dim, int D,
+extern "C" int mvuld_ggnn_init(const float* x, float* h32, void* hb, int ldb, long long N, int in_dim, int D,
                                cudaStream_t stream) {
   MV_CHECK_ARG(in_dim <= D, "ggnn_init: in_feats must be <= out_feats");
   if (N <= 0) return 0;
-  ggnn_init_kernel<<<grid_for(N * D, 256), 256, 0, stream>>>(x, h32, reinterpret_cast<bf16*>(hb), N, in_dim, D);
+  ggnn_init_kernel<<<grid_for(N * D, 256), 256, 0, stream>>>(x, h32, reinterpret_cast<bf16*>(hb), ldb, N, in_dim, D);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -98,41 +98,55 @@ patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, c
                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x32,
                    bf16* __restrict__ xb, int B, int Himg, int Wimg, float eps) {
   constexpr int TOK = 16;
-  __shared__ float taps[TOK][48];
+  __shared__ __align__(16) float taps[TOK][48];
   __shared__ float conv[TOK][E + 1];
   const int oc = threadIdx.x;
   const int Hp = Himg / 4, Wp = Wimg / 4;
-  const long long total = (long long)B * Hp * Wp;
+  const int total = B * Hp * Wp;                       // tokens (host checks < 2^31)
   float wr[48];
 #pragma unroll
   for (int i = 0; i < 48; ++i) wr[i] = __ldg(w + oc * 48 + i);
   const float bo = __ldg(bias + oc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (long long t0 = (long long)blockIdx.x * TOK; t0 < total; t0 += (long long)gridDim.x * TOK) {
-    for (int i = threadIdx.x; i < TOK * 48; i += E) {
-      const int tk = i / 48, tap = i % 48;
-      const long long tok = t0 + tk;
-      float val = 0.f;
+  for (int t0 = blockIdx.x * TOK; t0 < total; t0 += gridDim.x * TOK) {
+    // stage the 48 taps of TOK tokens: 12 (channel, kernel-row) segments of 4 contiguous floats per token, one
+    // 128-bit load each (32-bit index math: the per-tap 64-bit divisions used to cost more than the FMAs)
+    for (int j = threadIdx.x; j < TOK * 12; j += E) {
+      const int tk = j / 12, seg = j - tk * 12;
+      const int tok = t0 + tk;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
       if (tok < total) {
-        const int b = (int)(tok / (Hp * Wp));
-        const int rem = (int)(tok % (Hp * Wp));
-        const int ph = rem / Wp, pw = rem % Wp;
-        const int c = tap / 16, kh = (tap % 16) / 4, kw = tap % 4;
-        val = __ldg(img + (((size_t)b * 3 + c) * Himg + ph * 4 + kh) * Wimg + pw * 4 + kw);
+        const int b = tok / (Hp * Wp);
+        const int rem = tok - b * (Hp * Wp);
+        const int ph = rem / Wp, pw = rem - ph * Wp;
+        const int c = seg >> 2, kh = seg & 3;
+        val = __ldg(reinterpret_cast<const float4*>(img + (((size_t)b * 3 + c) * Himg + ph * 4 + kh) * Wimg + pw * 4));
       }
-      taps[tk][tap] = val;
+      *reinterpret_cast<float4*>(&taps[tk][seg * 4]) = val;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int tk = 0; tk < TOK; ++tk) {
-      float acc = bo;
+    // 4 tokens at a time, taps read as 128-bit broadcasts: 4 LDS.128 per 16 FMAs (scalar reads made this loop
+    // LDS-issue bound at one LDS.32 per FMA)
+#pragma unroll 1
+    for (int tk = 0; tk < TOK; tk += 4) {
+      float acc[4] = {bo, bo, bo, bo};
 #pragma unroll
-      for (int i = 0; i < 48; ++i) acc += wr[i] * taps[tk][i];
-      conv[tk][oc] = acc;
+      for (int i = 0; i < 48; i += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(&taps[tk + j][i]);
+          acc[j] = fmaf(wr[i], t.x, acc[j]);
+          acc[j] = fmaf(wr[i + 1], t.y, acc[j]);
+          acc[j] = fmaf(wr[i + 2], t.z, acc[j]);
+          acc[j] = fmaf(wr[i + 3], t.w, acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) conv[tk + j][oc] = acc[j];
     }
     __syncthreads();
     for (int tk = warp; tk < TOK; tk += E / 32) {
-      const long long tok = t0 + tk;
+      const int tok = t0 + tk;
       if (tok >= total) continue;
       float v[E / 32];
       float s = 0.f;
@@ -314,6 +328,8 @@ extern "C" int mvuld_patch_embed(const float* img, const float* w, const float* 
                                  const float* beta, float* x32, void* xb, int B, int Himg, int Wimg, int E, float eps,
                                  cudaStream_t stream) {
   MV_CHECK_ARG(Himg % 4 == 0 && Wimg % 4 == 0, "patch_embed: image size must be a multiple of the 4x4 patch");
+  MV_CHECK_ARG((long long)B * (Himg / 4) * (Wimg / 4) < (1ll << 31) && ((uintptr_t)img % 16) == 0,
+               "patch_embed: too many tokens for 32-bit indexing or image base not 16-byte aligned");
   const long long total = (long long)B * (Himg / 4) * (Wimg / 4);
   long long blocks = (total + 15) / 16;
   const long long cap = (long long)num_sms() * 16;

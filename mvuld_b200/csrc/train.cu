@@ -608,11 +608,11 @@ __device__ void aff_nt(const bf16* __restrict__ X, int ldx, const bf16* __restri
 }
 // out[i, c] = sum_j (TRANS ? S[j][i] : S[i][j]) Y[j, c]   -> bf16 rows (stride ldo)
 template <bool TRANS>
-__device__ void aff_sy(const float* __restrict__ S, const bf16* __restrict__ Y, int ldy, int n, int C,
+__device__ void aff_sy(const float* __restrict__ S, const bf16* __restrict__ Y, int ldy, int n, int c_beg, int c_end,
                        bf16* __restrict__ out, int ldo, float* bufA) {
   const int tid = threadIdx.x;
   const int yi = tid / 8, yj = tid % 8;
-  for (int c0 = 0; c0 < C; c0 += 64) {
+  for (int c0 = c_beg; c0 < c_end; c0 += 64) {
     for (int i = tid; i < AB_N * 8; i += 256) {
       const int row = i >> 3, part = i & 7;
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -673,11 +673,14 @@ rs_gcn_affinity_bwd_kernel(const bf16* __restrict__ tpg, const bf16* __restrict_
   const bf16* dyb = dy + (size_t)b * n * C;
   bf16* dth = dtpg + (size_t)b * n * 3 * C;
   const float inv = 1.0f / (float)n;
+  // gridDim.y CTAs share a graph: each recomputes the two n x n matrices and writes its own slice of the columns
+  const int c_per = ((C / 64 + gridDim.y - 1) / gridDim.y) * 64;
+  const int c_beg = blockIdx.y * c_per, c_end = min(C, c_beg + c_per);
   aff_nt(th, 3 * C, ph, 3 * C, n, C, inv, R, bufA, bufB);     // R  = theta phi^T / n
   aff_nt(dyb, C, gg, 3 * C, n, C, inv, dS, bufA, bufB);       // dS = dy g^T / n
-  aff_sy<true>(R, dyb, C, n, C, dth + 2 * C, 3 * C, bufA);    // dg     = R^T dy
-  aff_sy<false>(dS, ph, 3 * C, n, C, dth, 3 * C, bufA);       // dtheta = dS phi
-  aff_sy<true>(dS, th, 3 * C, n, C, dth + C, 3 * C, bufA);    // dphi   = dS^T theta
+  aff_sy<true>(R, dyb, C, n, c_beg, c_end, dth + 2 * C, 3 * C, bufA);    // dg     = R^T dy
+  aff_sy<false>(dS, ph, 3 * C, n, c_beg, c_end, dth, 3 * C, bufA);       // dtheta = dS phi
+  aff_sy<true>(dS, th, 3 * C, n, c_beg, c_end, dth + C, 3 * C, bufA);    // dphi   = dS^T theta
 }
 
 // --------------------------------------- l2norm over the node axis + node mean ---------------------------------------
@@ -940,7 +943,7 @@ extern "C" int mvuld_rs_gcn_affinity_bwd(const void* tpg, const void* dy, void* 
   if (B <= 0) return 0;
   const int smem = (2 * AB_N * (AB_N + 1) + AB_N * 64 + AB_N * 33) * sizeof(float);
   MV_CUDA_OK(cudaFuncSetAttribute(rs_gcn_affinity_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  rs_gcn_affinity_bwd_kernel<<<B, 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dtpg), n, C);
+  rs_gcn_affinity_bwd_kernel<<<dim3(B, B >= 148 ? 2 : 4), 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dtpg), n, C);
   MV_LAUNCH_OK();
   return 0;
 }

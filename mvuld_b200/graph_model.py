@@ -289,11 +289,25 @@ class GGNNSum(nn.Module):
         f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         b16 = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
         gg = self.ggnn
+        D = self.out_dim
+        # GRUCell as one GEMM over [a | h] with the four pre-activations of feature j in adjacent output columns
+        # (mvuld_gemm_gru): rows 4j .. 4j+3 = (W_ir | W_hr), (W_iz | W_hz), (W_in | 0), (0 | W_hn)
+        wih, whh = gg.gru.weight_ih.detach().float(), gg.gru.weight_hh.detach().float()     # [3D, D], gate order r, z, n
+        wg = torch.zeros(D, 4, 2 * D, device=wih.device)
+        wg[:, 0, :D], wg[:, 0, D:] = wih[:D], whh[:D]
+        wg[:, 1, :D], wg[:, 1, D:] = wih[D:2 * D], whh[D:2 * D]
+        wg[:, 2, :D] = wih[2 * D:]
+        wg[:, 3, D:] = whh[2 * D:]
+        if gg.gru.bias_ih is not None:
+            bih, bhh = gg.gru.bias_ih.detach().float(), gg.gru.bias_hh.detach().float()
+        else:
+            bih = bhh = torch.zeros(3 * D, device=wih.device)
+        b4 = torch.stack([bih[:D] + bhh[:D], bih[D:2 * D] + bhh[D:2 * D], bih[2 * D:], bhh[2 * D:]], 1)
         self._plan = dict(
             dev=dev,
             wmsg=b16(torch.cat([l.weight for l in gg.linears], 0)),     # [T*D, D]: row t*D + o = linears[t].weight[o]
             bmsg=f32(torch.cat([l.bias for l in gg.linears], 0)),
-            wih=b16(gg.gru.weight_ih), bih=f32(gg.gru.bias_ih), whh=b16(gg.gru.weight_hh), bhh=f32(gg.gru.bias_hh),
+            wg=b16(wg.reshape(4 * D, 2 * D)), b4=f32(b4.reshape(-1)),
             wc=f32(self.classifier.weight), bc=f32(self.classifier.bias))
         return self
 
@@ -314,16 +328,18 @@ class GGNNSum(nn.Module):
         et_sorted = torch.empty(et.numel(), device=dev, dtype=torch.uint8)
         _lib.call("mvuld_gather_etype", et, eids, et.numel(), T, et_sorted, status)
         e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
-        h32, hb = e((N, D), torch.float32), e((N, D), torch.bfloat16)
-        _lib.call("mvuld_ggnn_init", feats, h32, hb, N, feats.shape[1], D)
-        msgs, a = e((N, T * D), torch.bfloat16), e((N, D), torch.bfloat16)
-        gi, gh = e((N, 3 * D), torch.bfloat16), e((N, 3 * D), torch.bfloat16)
-        for _ in range(self.num_timesteps):
-            _lib.gemm(hb, p["wmsg"], bias=p["bmsg"], out_bf16=msgs)
-            _lib.call("mvuld_ggnn_gather_sum", msgs, indptr, idx_src, et_sorted, a, N, T, D)
-            _lib.gemm(a, p["wih"], bias=p["bih"], out_bf16=gi)
-            _lib.gemm(hb, p["whh"], bias=p["bhh"], out_bf16=gh)
-            _lib.call("mvuld_gru_gates", gi, gh, h32, hb, N, D)
+        h32 = e((N, D), torch.float32)
+        # two [a | h] operand buffers (bf16 [N, 2D]): step t reads X[t % 2] and writes the new state into the h half of
+        # the other one (tiles of the same rows are still loading the old state while the epilogue runs)
+        X = [e((N, 2 * D), torch.bfloat16), e((N, 2 * D), torch.bfloat16)]
+        _lib.call("mvuld_ggnn_init", feats, h32, _lib._Raw(X[0][:, D:]), 2 * D, N, feats.shape[1], D)
+        msgs = e((N, T * D), torch.bfloat16)
+        for step in range(self.num_timesteps):
+            cur, nxt = X[step % 2], X[(step + 1) % 2]
+            _lib.gemm(cur[:, D:], p["wmsg"], bias=p["bmsg"], out_bf16=msgs)
+            _lib.call("mvuld_ggnn_gather_sum", msgs, indptr, idx_src, et_sorted, cur, 2 * D, N, T, D)
+            _lib.call("mvuld_gemm_gru", cur, 2 * D, p["wg"], 2 * D, N, D, 2 * D, p["b4"], h32,
+                      _lib._Raw(nxt[:, D:]), 2 * D)
         if int(status.item()) != 0:
             raise AssertionError("edge type indices out of range [0, n_etypes)")
         g.check_status()

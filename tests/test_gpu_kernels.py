@@ -359,7 +359,7 @@ def test_gat_and_ggnn_steps():
     st = torch.zeros(1, device=DEV, dtype=torch.int32)
     _lib.call("mvuld_gather_etype", g2d.edata["_ETYPE"], eids, g2.num_edges(), T, ets, st)
     a = torch.zeros(N2, D, device=DEV, dtype=torch.bfloat16)
-    _lib.call("mvuld_ggnn_gather_sum", msgs.to(DEV), indptr, idx_src, ets, a, N2, T, D)
+    _lib.call("mvuld_ggnn_gather_sum", msgs.to(DEV), indptr, idx_src, ets, a, D, N2, T, D)
     torch.cuda.synchronize()
     ref = torch.zeros(N2, D).index_add_(0, torch.from_numpy(h2.dst),
                                         msgs.float()[torch.from_numpy(h2.src), h2.edata["_ETYPE"]])
@@ -434,3 +434,40 @@ def test_rs_gcn_block_split_precision_matches_reference_golden(golden):
     torch.cuda.synchronize()
     ref = golden["rs_gcn"]["v_star"].permute(0, 2, 1).reshape(B * n, C)
     assert rel_err(z32, ref) < 1e-4
+
+
+def test_gemm_gru_matches_torch_grucell():
+    """mvuld_gemm_gru: GRUCell (torch gate order r, z, n) as one GEMM over [a | h] with the gates in the epilogue."""
+    N, D = 1000, 200
+    r = gen(11)
+    cell = torch.nn.GRUCell(D, D)
+    a = (torch.randn(N, D, generator=r) * 0.5).to(torch.bfloat16)
+    h = torch.randn(N, D, generator=r) * 0.5
+    hb = h.to(torch.bfloat16)
+    with torch.no_grad():
+        wih, whh = cell.weight_ih.to(torch.bfloat16).float(), cell.weight_hh.to(torch.bfloat16).float()
+        gi = a.float() @ wih.t() + cell.bias_ih
+        gh = hb.float() @ whh.t() + cell.bias_hh
+        rg = torch.sigmoid(gi[:, :D] + gh[:, :D])
+        zg = torch.sigmoid(gi[:, D:2 * D] + gh[:, D:2 * D])
+        nn_ = torch.tanh(gi[:, 2 * D:] + rg * gh[:, 2 * D:])
+        want = (1 - zg) * nn_ + zg * h
+        wg = torch.zeros(D, 4, 2 * D)
+        wg[:, 0, :D], wg[:, 0, D:] = cell.weight_ih[:D], cell.weight_hh[:D]
+        wg[:, 1, :D], wg[:, 1, D:] = cell.weight_ih[D:2 * D], cell.weight_hh[D:2 * D]
+        wg[:, 2, :D] = cell.weight_ih[2 * D:]
+        wg[:, 3, D:] = cell.weight_hh[2 * D:]
+        b4 = torch.stack([cell.bias_ih[:D] + cell.bias_hh[:D], cell.bias_ih[D:2 * D] + cell.bias_hh[D:2 * D],
+                          cell.bias_ih[2 * D:], cell.bias_hh[2 * D:]], 1).reshape(-1)
+    X = torch.cat([a, hb], 1).to(DEV).contiguous()
+    Xn = torch.zeros_like(X)
+    h32 = h.to(DEV).contiguous()
+    _lib.call("mvuld_gemm_gru", X, 2 * D, wg.reshape(4 * D, 2 * D).to(DEV, torch.bfloat16).contiguous(), 2 * D, N, D, 2 * D,
+              b4.to(DEV).contiguous(), h32, _lib._Raw(Xn[:, D:]), 2 * D)
+    torch.cuda.synchronize()
+    assert rel_err(h32, want) < 1e-4
+    assert torch.equal(Xn[:, D:].cpu(), h32.cpu().to(torch.bfloat16))
+    assert float(Xn[:, :D].float().abs().sum()) == 0.0            # only the h half of the other buffer is written
+    with pytest.raises(RuntimeError):
+        _lib.call("mvuld_gemm_gru", X, 2 * D, wg.reshape(4 * D, 2 * D).to(DEV, torch.bfloat16).contiguous(), 2 * D, N, D,
+                  2 * D, b4.to(DEV).contiguous(), h32, X, 2 * D)   # in-place bf16 state is refused
