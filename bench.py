@@ -37,7 +37,9 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 import torch  # noqa: E402
 
 
-METRIC = {"full": "MVulD functions/sec (fwd)", "train": "MVulD functions/sec (train step)"}
+METRIC = {"full": "MVulD functions/sec (fwd)", "train": "MVulD functions/sec (train step)",
+          "lines": "per-node UniXcoder line vectors, lines/sec"}
+UNIT = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s", "train": "functions/s", "lines": "lines/s"}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -47,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "swin", "ggnn", "train"])
+    ap.add_argument("--workload", default="full", choices=["full", "swin", "ggnn", "train", "lines"])
     ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (default: 64 functions / 64 images / "
                                                          "4096 graphs / 32 functions for train)")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg of the default workload")
@@ -192,6 +194,30 @@ def build_workload(args, rank, device):
     torch.manual_seed(12345)                       # same weights on every rank
     if args.workload == "train":
         return build_train_workload(args, rank, device, int(os.environ.get("WORLD_SIZE", "1")))
+    if args.workload == "lines":
+        # the per-node line encoding the reference runs offline (data_list.py:292-299 ->
+        # unixcoder.py:56-68), every line padded to 512 tokens there; packed rows + block-diagonal attention here
+        n = args.batch or 12800                                       # ~64 functions x 200 CPG nodes
+        model = mv.build_MyUniXcoder().eval()
+        synth.randomize_for_parity(model, seed=777)
+        model = model.to(device)
+        ids = synth.line_token_ids(n, seed=seed)                      # [n, 512] int64, what tokenize(padding=True) gives
+        packed = model.encoder.pack(ids)
+        t0 = time.perf_counter()
+        sample = ids[:256].to(device)
+        for _ in range(2):
+            model.get_repr(sample)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.get_repr(sample)
+        torch.cuda.synchronize()
+        padded_rate = 256 / (time.perf_counter() - t0)
+        name = (f"per-node UniXcoder line encoding (SURVEY 8f.1): {n} code lines, {packed.n_tokens / n:.1f} tokens per "
+                f"line, packed into {packed.n_rows} rows of 512 (fill {packed.fill:.3f}) instead of the reference's {n} "
+                f"padded rows; same kernels on the padded layout: {padded_rate:.0f} lines/s")
+        return dict(units=n, to_dev=lambda: packed, host=ids, step=lambda d: model.encoder.encode_packed(d),
+                    e2e_step=lambda h: model.myEncode_ids(h), h2d=packed.n_rows * 512 * (8 + 4 * 3) + n * 8 + packed.n_rows * 4,
+                    d2h=n * 768 * 4, name=name, flops_per_unit=96.64e9 * packed.n_rows / n)
     if args.workload == "full":
         B = args.batch or 64
         model = mv.MVulD(mv.default_config()).eval()
@@ -303,6 +329,12 @@ def cpu_oracle_runner(workload, sample):
     from oracle.roberta import RobertaGeometry
     from tests.cases import to_host_batch
     torch.manual_seed(12345)
+    if workload == "lines":                       # the reference way: every line padded to 512 tokens (unixcoder.py:56-68)
+        m = mv.build_MyUniXcoder().eval()
+        synth.randomize_for_parity(m, seed=777)
+        ids = synth.line_token_ids(sample, seed=1)
+        sd = m.state_dict()
+        return lambda: orob.get_repr(sd, RobertaGeometry(), ids)
     if workload == "ggnn":
         m = mv.GGNNSum(132, 200, max_edge_types=4, num_steps=6).eval()
         g = synth.ggnn_batch(sample, seed=1, n_etypes=4)
@@ -339,7 +371,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count())
-    sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2}[args.workload]
+    sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2, "lines": 4}[args.workload]
     fn = cpu_oracle_runner(args.workload, sample)
     for _ in range(max(1, min(args.warmup, 1))):
         fn()
@@ -348,7 +380,7 @@ def run_reference(args, rank):
         fn()
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
-    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s", "train": "functions/s"}[args.workload]
+    unit = UNIT[args.workload]
     print(json.dumps({
         "impl": "reference", "metric": METRIC.get(args.workload, f"{args.workload} branch {unit}"), "value": v, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -377,7 +409,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from mvuld_b200 import _lib
     wl = build_workload(args, rank, device)
-    unit = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s", "train": "functions/s"}[args.workload]
+    unit = UNIT[args.workload]
 
     def barrier():
         if world > 1:
@@ -418,6 +450,10 @@ def main():
 
     def e2e_pass(w, n):
         sink = ResultSink(n)
+        if "e2e_step" in w:                     # the public call packs on the host itself (host ids in, vectors out)
+            for _ in range(n):
+                sink.push(w["e2e_step"](w["host"]))
+            return sink.results()
         for d in DevicePrefetcher((w["host"] for _ in range(n)), device):
             sink.push(w["step"](d))
         return sink.results()
@@ -476,7 +512,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "per_gpu_batch": wl["units"], "parallelism": f"batch-shard x{world}, no "
-                   "data-path collective" if args.workload != "train" else f"data-parallel x{world}, bucketed NCCL "
+                   "data-path collective" if args.workload not in ("train",) else f"data-parallel x{world}, bucketed NCCL "
                    "gradient all-reduce", "l2_policy": "per-step inputs + activations exceed the 126 MB L2"},
         "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(wl["h2d"]), "d2h_bytes_per_step": int(wl["d2h"])},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -537,7 +573,7 @@ def main():
 
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count())
-        sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2}[args.workload]
+        sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2, "lines": 4}[args.workload]
         fn = cpu_oracle_runner(args.workload, sample)
         fn()
         t0 = time.perf_counter()

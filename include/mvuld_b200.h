@@ -77,6 +77,18 @@ int mvuld_swin_window_attention(const void* q, const void* k, const void* v, con
  * out bf16 [B*L, nH*64].  unixcoder.py:35-36. */
 int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out, int B, int L,
                         int nH, int hd, mvuld_stream_t stream);
+/* Packed variant (several short sequences per row, block-diagonal attention): token (b, i) attends to keys
+ * [seg_lo[b*L + i], seg_hi[b*L + i]) of row b; padding tokens carry their own position (lo = i, hi = i + 1) so that
+ * they stay finite.  kv_len[b] = tokens in use in row b.  This is what makes the per-node line encoding of
+ * mvuld/data/data_list.py:292-299 / unixcoder.py:56-68 (every line padded to 512 tokens in the reference) affordable.
+ * tile_lo / tile_hi (optional, both or neither): int32 [B, ceil(L / 128)], the range of 128-key tiles that query tile
+ * (b, t) has to visit -- the union of its rows' key ranges; the other key tiles of the row are skipped. */
+int mvuld_seq_attention_packed(const void* q, const void* k, const void* v, const int* kv_len, const int* seg_lo,
+                               const int* seg_hi, const int* tile_lo, const int* tile_hi, void* out, int B, int L,
+                               int nH, int hd, mvuld_stream_t stream);
+/* out[s, :] = mean of token rows [seg_start[s], seg_start[s] + seg_len[s]) of tok fp32 [T, C] (unixcoder.py:37 per line). */
+int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* seg_len, float* out, int n, int C,
+                           mvuld_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row kernels of the image / text branches.

@@ -65,6 +65,14 @@ struct AttnParams {
   int C;                  // channels (= nH * HD)
   // MODE_SEQ
   const int* kv_len;      // [B] valid keys per sequence
+  // packed sequences (several short sequences per row, block-diagonal attention): token (b, i) attends to keys
+  // [seg_lo[b * Nq + i], seg_hi[b * Nq + i]) of its own row; null = one sequence per row
+  const int* seg_lo;
+  const int* seg_hi;
+  // optional, packed only: key-tile range [tile_lo, tile_hi) (units of KT keys) that the 128-row query tile (b, t)
+  // needs, [B, ceil(Nq / 128)]: short lines touch one or two of the four key tiles
+  const int* tile_lo;
+  const int* tile_hi;
   void* out;              // bf16 [tokens, C]
 };
 
@@ -190,6 +198,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     nkt = (kv_valid + KT - 1) / KT;
   }
 
+  // key tiles query tile t has to visit (all of them unless the packed layout narrows it)
+  auto kv_range = [&](int t, int& jlo, int& jhi) {
+    jlo = 0;
+    jhi = nkt;
+    if (MODE == MODE_SEQ && p.tile_lo != nullptr) {
+      jlo = __ldg(p.tile_lo + bwin * nq + t);
+      jhi = __ldg(p.tile_hi + bwin * nq + t);
+      jlo = max(0, min(jlo, nkt - 1));
+      jhi = max(jlo + 1, min(jhi, nkt));
+    }
+  };
+
   uint8_t* sK = smem;
   uint8_t* sV = sK + nkt_all * KT * L::ROW_BYTES;
   uint8_t* sQ = sV + nkt_all * KT * L::ROW_BYTES;
@@ -283,6 +303,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             make_idesc_bf16(ATT_BM, KT, 0, 0) & ~((QK_FP16 ? 1u : 0u) * ((1u << 7) | (1u << 10)));
         const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
         int s_t[2] = {0, 1}, s_j[2] = {0, 0}, s_count[2] = {0, 0};
+        int s_lo[2] = {0, 0}, s_hi[2] = {nkt, nkt};
+        if (nq > 0) kv_range(0, s_lo[0], s_hi[0]);
+        if (nq > 1) kv_range(1, s_lo[1], s_hi[1]);
+        s_j[0] = s_lo[0];
+        s_j[1] = s_lo[1];
         uint32_t ph_q[2] = {0, 0};
         long long t_last = clock64();
         while (s_t[0] < nq || s_t[1] < nq) {
@@ -291,9 +316,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int g = 0; g < 2; ++g) {
             if (s_t[g] >= nq) continue;
             const int j = s_j[g];
-            bool ready = (j != 0) || mbar_test_wait(&q_full[g], ph_q[g]);
+            bool ready = (j != s_lo[g]) || mbar_test_wait(&q_full[g], ph_q[g]);
             if (ready && s_count[g] > 0) ready = mbar_test_wait(&s_free[g], (s_count[g] - 1) & 1);
-            if (ready && s_t[g] == g) ready = mbar_test_wait(&k_full[j], 0);
+            if (ready && (s_t[g] == g || MODE == MODE_SEQ)) ready = mbar_test_wait(&k_full[j], 0);
             if (!ready) continue;
             ATT_TRACE(10, g, s_t[g], j);
             tc_fence_after();
@@ -306,11 +331,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_commit(&s_full[g]);
             ATT_TRACE(11, g, s_t[g], j);
             ++s_count[g];
-            if (j == 0) ph_q[g] ^= 1;
-            if (j + 1 == nkt) {
+            if (j == s_lo[g]) ph_q[g] ^= 1;
+            if (j + 1 == s_hi[g]) {
               umma_commit(&q_empty[g]);          // last read of this Q tile is in flight
-              s_j[g] = 0;
               s_t[g] += 2;
+              if (s_t[g] < nq) kv_range(s_t[g], s_lo[g], s_hi[g]);
+              s_j[g] = s_lo[g];
             } else {
               s_j[g] = j + 1;
             }
@@ -332,21 +358,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t tO = tmem_base + g * 256 + COL_O;
         uint32_t n = 0, ph_o = 0;
         for (int t = g; t < nq; t += 2) {
-          for (int j = 0; j < nkt; ++j, ++n) {
+          int jlo, jhi;
+          kv_range(t, jlo, jhi);
+          for (int j = jlo; j < jhi; ++j, ++n) {
             const int b = n % NPB;
             mbar_wait(&p_full[2 * g + b], (n / NPB) & 1, 22);
-            if (j == 0 && t != g) {
+            if (j == jlo && t != g) {
               mbar_wait(&o_free[g], ph_o, 23);
               ph_o ^= 1;
             }
-            if (t == g) mbar_wait(&v_full[j], 0, 24);
+            if (t == g || MODE == MODE_SEQ) mbar_wait(&v_full[j], 0, 24);
             ATT_TRACE(12, g, t, j);
             tc_fence_after();
             const uint32_t tP = tmem_base + g * 256 + COL_P + b * PW;
 #pragma unroll
             for (int s = 0; s < KT / 16; ++s) {
               const uint64_t bd = make_smem_desc(v0 + (j * KT + s * 16) * L::ROW_BYTES, 16, L::SBO, L::LAYOUT);
-              umma_ts(tO, tP + s * 8, bd, idesc_pv, (j | s) != 0);
+              umma_ts(tO, tP + s * 8, bd, idesc_pv, (j != jlo) || (s != 0));
             }
             umma_commit(&pv_done[2 * g + b]);
             ATT_TRACE(13, g, t, j);
@@ -387,10 +415,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (hi > WS - 1) hi = WS - 1;                        // rows past the window only exist as padding
       }
       const bool ri = hi >= SPLIT, ci = wi >= SPLIT;
+      // packed sequences: this query row's key range (padding rows attend to themselves so that they stay finite)
+      int k_lo = 0, k_hi = 0x7fffffff;
+      if (MODE == MODE_SEQ && p.seg_lo != nullptr) {
+        const int ii = i < p.Nq ? i : p.Nq - 1;
+        k_lo = __ldg(p.seg_lo + (size_t)bwin * p.Nq + ii);
+        k_hi = __ldg(p.seg_hi + (size_t)bwin * p.Nq + ii);
+      }
       float m_run = -INFINITY;
       uint64_t ls[2] = {0ull, 0ull};                         // row sum as two packed fp32x2 accumulators
+      int jlo, jhi;
+      kv_range(t, jlo, jhi);
+      if (MODE == MODE_SEQ && p.seg_lo != nullptr && i >= kv_valid) {   // tail padding: a key this tile does visit
+        k_lo = jlo * KT;
+        k_hi = k_lo + 1;
+      }
 
-      for (int j = 0; j < nkt; ++j, ++n) {
+      for (int j = jlo; j < jhi; ++j, ++n) {
         const int ncols = min(KT, kv_valid - j * KT);        // valid kv columns in this tile
 
         // per-segment additive constants (shift mask) and bias-table row bases
@@ -432,6 +473,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int c = 0; c < KT; ++c) sv[c] = (c < ncols) ? sv[c] : 0xff800000u;   // -inf
         }
+        if (MODE == MODE_SEQ && p.seg_lo != nullptr) {
+          // block-diagonal mask of packed sequences: keys outside [k_lo, k_hi) of this row are -inf
+          const unsigned rel0 = (unsigned)(j * KT - k_lo), span = (unsigned)(k_hi - k_lo);
+#pragma unroll
+          for (int c = 0; c < KT; ++c) sv[c] = (rel0 + (unsigned)c < span) ? sv[c] : 0xff800000u;
+        }
         // sweep 1: reference point of the tile = max over the RAW scores per mask segment + segment constant + the
         // head's largest bias.  It bounds the true row maximum from above by at most (max - min) of the bias table
         // (<= 16 log2 e), so every 2^(.) below is <= 2^8 and the largest term of a row is >= 2^-32: an exact softmax
@@ -448,12 +495,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int s = 0; s < NSEG; ++s) m_tile = fmaxf(m_tile, segmax[s] + ((MODE == MODE_SWIN) ? cseg[s] : 0.f));
         m_tile += bmax;
+        if (MODE == MODE_SEQ) m_tile = fmaxf(m_tile, -1.0e30f);   // a fully masked tile (packed rows): keep the reference finite
 
         // running reference with lazy rescale (only when it moves by more than 2^8)
         const float m_new = fmaxf(m_run, m_tile);
-        const bool need = (j > 0) && (m_new > m_run + 8.0f);
-        if (j == 0) m_run = m_new;
-        if (j > 0 && __any_sync(0xffffffffu, need)) {
+        const bool need = (j > jlo) && (m_new > m_run + 8.0f);
+        if (j == jlo) m_run = m_new;
+        if (j > jlo && __any_sync(0xffffffffu, need)) {
           wait_pv(n - 1);                                    // O holds every PV of this query tile issued so far
           tc_fence_after();
           const float f = need ? ex2_approx(m_run - m_new) : 1.0f;
@@ -546,7 +594,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float l0, l1, l2, l3;
       unpack2f(ls[0], l0, l1);
       unpack2f(ls[1], l2, l3);
-      const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+      const float lsum = (l0 + l1) + (l2 + l3);
+      const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
       size_t orow;
       if (MODE == MODE_SWIN) {
         const int hl = i / WS, wl = i - hl * WS;
@@ -726,8 +775,9 @@ extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const v
   }
 }
 
-extern "C" int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out, int B,
-                                   int L, int nH, int hd, cudaStream_t stream) {
+static int seq_attention(const void* q, const void* k, const void* v, const int* kv_len, const int* seg_lo,
+                         const int* seg_hi, const int* tile_lo, const int* tile_hi, void* out, int B, int L, int nH,
+                         int hd, cudaStream_t stream) {
   MV_CHECK_ARG(hd == 64, "seq attention: head_dim 64 only");
   MV_CHECK_ARG(L <= 512 && L % 8 == 0, "seq attention: L must be <= 512 and a multiple of 8");
   AttnParams p{};
@@ -735,6 +785,21 @@ extern "C" int mvuld_seq_attention(const void* q, const void* k, const void* v, 
   p.nH = nH;
   p.C = nH * hd;
   p.kv_len = kv_len;
+  p.seg_lo = seg_lo;
+  p.seg_hi = seg_hi;
+  p.tile_lo = tile_lo;
+  p.tile_hi = tile_hi;
   p.out = out;
   return launch_attn<MODE_SEQ, 64, 1, 128, false>(q, k, v, B * nH, p, stream);
+}
+extern "C" int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out, int B,
+                                   int L, int nH, int hd, cudaStream_t stream) {
+  return seq_attention(q, k, v, kv_len, nullptr, nullptr, nullptr, nullptr, out, B, L, nH, hd, stream);
+}
+extern "C" int mvuld_seq_attention_packed(const void* q, const void* k, const void* v, const int* kv_len,
+                                          const int* seg_lo, const int* seg_hi, const int* tile_lo, const int* tile_hi,
+                                          void* out, int B, int L, int nH, int hd, cudaStream_t stream) {
+  MV_CHECK_ARG(seg_lo && seg_hi, "packed seq attention: segment bounds are null");
+  MV_CHECK_ARG((tile_lo == nullptr) == (tile_hi == nullptr), "packed seq attention: give both tile bounds or neither");
+  return seq_attention(q, k, v, kv_len, seg_lo, seg_hi, tile_lo, tile_hi, out, B, L, nH, hd, stream);
 }

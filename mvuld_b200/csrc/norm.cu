@@ -390,6 +390,30 @@ extern "C" int mvuld_roberta_embed(const long long* ids, const int* pos, const f
   return 0;
 }
 
+namespace mv {
+// mean over the token rows [start[s], start[s] + len[s]) of tok fp32 [T, C] -> out fp32 [n, C]: the sentence vector
+// of each packed line (unixcoder.py:37 per line).  One block per segment.
+__global__ void __launch_bounds__(256)
+segment_mean_kernel(const float* __restrict__ tok, const int* __restrict__ start, const int* __restrict__ len,
+                    float* __restrict__ out, int C) {
+  const int sgm = blockIdx.x;
+  const long long b = start[sgm];
+  const int n = len[sgm];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < n; ++t) acc += tok[(b + t) * C + c];
+    out[(size_t)sgm * C + c] = acc / (float)n;
+  }
+}
+}  // namespace mv
+extern "C" int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* seg_len, float* out, int n,
+                                      int C, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  mv::segment_mean_kernel<<<n, 256, 0, stream>>>(tok, seg_start, seg_len, out, C);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int mvuld_masked_mean(const float* tok, const int* len, float* out, int B, int L, int C,
                                  cudaStream_t stream) {
   masked_mean_kernel<<<B, 256, 0, stream>>>(tok, len, out, L, C);

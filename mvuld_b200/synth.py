@@ -49,6 +49,20 @@ def token_ids(B: int, L: int = 512, vocab: int = 51416, seed: int = 12345, pad: 
     return ids
 
 
+def line_token_ids(n_lines: int, vocab: int = 51416, seed: int = 12345, pad: int = 1, L: int = 512) -> torch.Tensor:
+    """Token ids of ``n_lines`` code lines as ``tokenize(..., max_length=512, padding=True)`` returns them
+    (unixcoder.py:137-151): ``<s> <encoder-only> </s> tokens </s>`` padded to 512.  Line length (sub-word tokens) is
+    log-normal around 12 (a statement of a C function), clipped to [1, 508]."""
+    g = _gen(seed + 4)
+    body = torch.exp(torch.randn(n_lines, generator=g) * 0.6 + math.log(12.0)).round().clamp(1, L - 4).long()
+    ids = torch.full((n_lines, L), pad, dtype=torch.int64)
+    for i in range(n_lines):
+        nb = int(body[i])
+        ids[i, :nb + 4] = torch.cat([torch.tensor([0, 6, 2]), torch.randint(4, vocab, (nb,), generator=g),
+                                     torch.tensor([2])])
+    return ids
+
+
 def _num_nodes(B: int, g: torch.Generator, lo: int = 2, hi: int = 2000) -> List[int]:
     n = torch.exp(torch.randn(B, generator=g) * 0.6 + math.log(170.0)).round().clamp(lo, hi).long()
     return n.tolist()

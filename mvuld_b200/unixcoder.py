@@ -203,6 +203,160 @@ class RobertaEncoder(nn.Module):
         """HF-style call ``encoder(ids, attention_mask=...)[0]``; the mask is re-derived from the pad id."""
         return (self.encode(input_ids)[0],)
 
+    def pack(self, line_ids, rows_per_pass: int = 64) -> "PackedLines":
+        """Host side of ``encode_lines``: next-fit packing (``pack_lines``) and the per-token arrays the kernels need
+        (ids, position ids restarting per line, the key range [lo, hi) of each token's line), vectorised with numpy and
+        copied to the GPU pass by pass (``rows_per_pass`` rows of 512 tokens per encoder pass)."""
+        import numpy as np
+        if self._plan is None:
+            self.prepare()
+        dev, pad, L = self._plan["dev"], int(self.config.pad_token_id), 512
+        flat, lens = _lines_to_flat(line_ids, pad)
+        n = int(lens.size)
+        row_of, off_of, n_rows = pack_lines(lens.tolist(), L)
+        row_of, off_of = np.asarray(row_of, dtype=np.int64), np.asarray(off_of, dtype=np.int64)
+        first = np.concatenate([[0], np.cumsum(lens)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+        line = np.repeat(np.arange(n), lens)                               # line of every token
+        t = np.arange(flat.size) - np.repeat(first, lens)                  # index inside its line
+        dest = row_of[line] * L + off_of[line] + t
+        ids = np.full(n_rows * L, pad, dtype=np.int64)
+        pos = np.full(n_rows * L, pad, dtype=np.int32)                     # padding_idx of the position table
+        lo = np.zeros(n_rows * L, dtype=np.int32)                          # tail padding: the kernel points it at key 0
+        hi = np.ones(n_rows * L, dtype=np.int32)
+        ids[dest] = flat
+        pos[dest] = t + pad + 1                                            # HF create_position_ids_from_input_ids, per line
+        lo[dest] = off_of[line]
+        hi[dest] = off_of[line] + lens[line]
+        used = np.zeros(n_rows, dtype=np.int32)
+        np.maximum.at(used, row_of, (off_of + lens).astype(np.int32))
+        # key tiles (128 keys) each 128-row query tile must visit: lines are packed in order, so the union of the key
+        # ranges of a tile's valid rows is [lo of its first valid token, hi of its last valid token)
+        QT = 128
+        nqt = L // QT
+        first_tok = np.arange(n_rows * nqt, dtype=np.int64) * QT                           # global token index
+        row_used = np.repeat(used.astype(np.int64), nqt)
+        t_in_row = np.tile(np.arange(nqt, dtype=np.int64) * QT, n_rows)
+        last_tok = first_tok + np.clip(row_used - t_in_row, 1, QT) - 1
+        has = row_used > t_in_row
+        tile_lo = np.where(has, lo[first_tok] // QT, 0).astype(np.int32)
+        tile_hi = np.where(has, (hi[last_tok] + QT - 1) // QT, 1).astype(np.int32)
+        h2d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().to(dev, non_blocking=True)
+        passes = []
+        for r0 in range(0, n_rows, rows_per_pass):
+            r1 = min(n_rows, r0 + rows_per_pass)
+            k0, k1 = int(np.searchsorted(row_of, r0, "left")), int(np.searchsorted(row_of, r1, "left"))
+            sl = slice(r0 * L, r1 * L)
+            passes.append(dict(R=r1 - r0, k0=k0, k1=k1, ids=h2d(ids[sl].reshape(r1 - r0, L)), pos=h2d(pos[sl]),
+                               lo=h2d(lo[sl]), hi=h2d(hi[sl]), used=h2d(used[r0:r1]),
+                               tlo=h2d(tile_lo[r0 * nqt:r1 * nqt]), thi=h2d(tile_hi[r0 * nqt:r1 * nqt]),
+                               start=h2d(((row_of[k0:k1] - r0) * L + off_of[k0:k1]).astype(np.int32)),
+                               len=h2d(lens[k0:k1].astype(np.int32))))
+        return PackedLines(n, n_rows, int(flat.size), passes)
+
+    @torch.no_grad()
+    def encode_packed(self, packed: "PackedLines") -> torch.Tensor:
+        """Device side of ``encode_lines``: the encoder over packed rows with block-diagonal attention, then the mean
+        over each line's tokens (unixcoder.py:37) -> fp32 [n_lines, H]."""
+        if self.training:
+            raise RuntimeError("mvuld_b200 RobertaEncoder implements the eval-mode forward: call model.eval()")
+        if self._plan is None:
+            self.prepare()
+        p, cfg = self._plan, self.config
+        H, nH, L = cfg.hidden_size, cfg.num_attention_heads, 512
+        qmul = LOG2E / math.sqrt(H // nH)
+        eps = float(cfg.layer_norm_eps)
+        out = torch.empty(packed.n_lines, H, device=p["dev"], dtype=torch.float32)
+        for ps in packed.passes:
+            R = ps["R"]
+            M = R * L
+            w = self._workspace(R, L)
+            _lib.call("mvuld_roberta_embed", ps["ids"], ps["pos"], p["word"], p["pos"], p["type0"], p["eg"], p["eb"],
+                      w["x32"], w["xb"], M, H, eps)
+            for lp in p["layers"]:
+                _lib.call("mvuld_heads_qkv", w["xb"], lp["wqkv"], lp["bqkv"], w["q"], w["k"], w["v"], R, L, H, nH, qmul)
+                _lib.call("mvuld_seq_attention_packed", w["q"], w["k"], w["v"], ps["used"], ps["lo"], ps["hi"], ps["tlo"],
+                          ps["thi"], w["ctx"], R, L, nH, H // nH)
+                _lib.gemm(w["ctx"], lp["wo"], bias=lp["bo"], out_bf16=w["y"])
+                _lib.call("mvuld_ln_rows", w["y"], w["x32"], lp["g1"], lp["b1"], w["x32"], w["xb"], M, H, eps, 2)
+                _lib.gemm(w["xb"], lp["wi"], bias=lp["bi"], act=_lib.ACT_GELU, out_bf16=w["h"])
+                _lib.gemm(w["h"], lp["wo2"], bias=lp["bo2"], out_bf16=w["y"])
+                _lib.call("mvuld_ln_rows", w["y"], w["x32"], lp["g2"], lp["b2"], w["x32"], w["xb"], M, H, eps, 2)
+            nl = ps["k1"] - ps["k0"]                                       # lines keep their order: a contiguous slice
+            _lib.call("mvuld_seq_segment_mean", w["x32"], ps["start"], ps["len"], _lib._Raw(out[ps["k0"]:ps["k1"]]), nl, H)
+        return out
+
+    def encode_lines(self, line_ids, rows_per_pass: int = 64) -> torch.Tensor:
+        """Sentence vectors of MANY SHORT sequences (the per-node line encoding of mvuld/data/data_list.py:292-299 via
+        unixcoder.py:56-68, where the reference pads every line to 512 tokens): -> fp32 [n_lines, H] on the GPU.
+
+        ``line_ids``: HOST int64 tensor [n, L <= 512] padded with ``pad_token_id`` (what ``tokenize(..., padding=True)``
+        returns), or a list of token-id lists.  Lines are packed back to back into rows of 512 tokens (``pack``) and run
+        with block-diagonal attention and per-line position ids (``encode_packed``), which is arithmetically what the
+        reference computes for the valid tokens of each padded line; pad tokens are never the key of a valid query."""
+        return self.encode_packed(self.pack(line_ids, rows_per_pass))
+
+
+class PackedLines:
+    """Lines packed into rows of 512 tokens, device resident (see ``RobertaEncoder.pack``)."""
+
+    def __init__(self, n_lines, n_rows, n_tokens, passes):
+        self.n_lines, self.n_rows, self.n_tokens, self.passes = n_lines, n_rows, n_tokens, passes
+
+    @property
+    def fill(self) -> float:
+        """Fraction of the packed rows' token slots that hold real tokens."""
+        return self.n_tokens / max(1, self.n_rows * 512)
+
+
+def _lines_to_flat(line_ids, pad: int):
+    """-> (all valid tokens back to back, int64; length per line, int64).  Pad tokens must form a suffix."""
+    import numpy as np
+    if isinstance(line_ids, torch.Tensor):
+        if line_ids.is_cuda:
+            raise RuntimeError("encode_lines packs on the host: pass the tokenizer's (CPU) ids")
+        a = line_ids.to(torch.int64).numpy()
+        if a.ndim != 2 or a.shape[1] > 512:
+            raise ValueError("line ids must be [n_lines, L <= 512]")
+        valid = a != pad
+        lens = valid.sum(1).astype(np.int64)
+        if not np.array_equal(valid, np.arange(a.shape[1])[None, :] < lens[:, None]):
+            raise ValueError("pad tokens must form a suffix of every line (unixcoder.py:150 tokenisation)")
+        flat = a[valid]
+    else:
+        rows = [np.asarray(r, dtype=np.int64) for r in line_ids]
+        rows = [r[r != pad] for r in rows]
+        lens = np.asarray([r.size for r in rows], dtype=np.int64)
+        flat = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+    if lens.size and (lens.min() < 1 or lens.max() > 512):
+        raise ValueError("every line needs between 1 and 512 tokens (the tokenizer always emits <s> <encoder-only> "
+                         "</s> ... </s>)")
+    return flat, lens
+
+
+def _lines_to_rows(line_ids, pad: int):
+    """-> (list of 1-D int64 numpy rows without padding, list of lengths); helper kept for tests."""
+    import numpy as np
+    flat, lens = _lines_to_flat(line_ids, pad)
+    ends = np.cumsum(lens)
+    return [flat[e - l:e] for e, l in zip(ends, lens)], lens.tolist()
+
+
+def pack_lines(lengths, L: int = 512):
+    """Next-fit packing in input order of sequences of the given lengths into rows of ``L`` tokens.
+    -> (row index per line, token offset per line, number of rows).  Keeping the input order makes each row's lines a
+    contiguous run of nodes, so segment bookkeeping is two integers per line."""
+    row_of, off_of = [], []
+    row, used = 0, 0
+    for ln in lengths:
+        if ln > L:
+            raise ValueError(f"sequence of {ln} tokens does not fit a row of {L}")
+        if used + ln > L:
+            row, used = row + 1, 0
+        row_of.append(row)
+        off_of.append(used)
+        used += ln
+    return row_of, off_of, (row + 1 if len(lengths) else 0)
+
 
 class MyUniXcoder(nn.Module):
     """Mirror of unixcoder.py:20-95."""
@@ -219,6 +373,19 @@ class MyUniXcoder(nn.Module):
     def get_xcode_vec(self, source_ids):
         """unixcoder.py:33-38."""
         return self.encoder.encode(source_ids)
+
+    def myEncode_ids(self, line_ids) -> torch.Tensor:
+        """unixcoder.py:56-68 (``myEncode``) from token ids: one sentence vector per code line, [n_lines, 768].  The
+        reference runs every line padded to 512 tokens through the encoder; here lines are packed (``encode_lines``)."""
+        return self.encoder.encode_lines(line_ids)
+
+    def myEncode(self, sents: list) -> torch.Tensor:
+        """unixcoder.py:56-68: needs the tokenizer callable the reference passes to the constructor."""
+        if self.tokenize is None:
+            raise RuntimeError("MyUniXcoder.myEncode needs the `tokenize` callable (unixcoder.py:137-151); offline use "
+                               "myEncode_ids with token ids")
+        ids = [self.tokenize([' '.join(s.split())], max_length=512, padding=True)[0] for s in sents]
+        return self.myEncode_ids(torch.tensor(ids, dtype=torch.long))
 
     def get_repr(self, input_ids, labels=None):
         """unixcoder.py:91-95."""

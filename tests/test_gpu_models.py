@@ -181,3 +181,33 @@ def test_device_prefetcher_yields_identical_batches_and_results():
     assert len(got) == 3 and all(torch.equal(a, b) for a, b in zip(got, want))
     with pytest.raises(RuntimeError):
         DevicePrefetcher(batches, "cpu")
+
+
+def test_packed_line_encoding_matches_padded_reference_semantics():
+    """per-node line vectors (data_list.py:292-299 -> unixcoder.py:56-68).  The packed,
+    block-diagonal run must give what the reference computes with every line padded to 512 tokens: checked against the
+    fp32 oracle on the padded batch (1e-2, bf16) and against this repo's own padded GPU path."""
+    m = cases.make_roberta()
+    cfg = m.config
+    ids = synth.line_token_ids(37, vocab=cfg.vocab_size, seed=cases.SEED)
+    g = torch.Generator().manual_seed(5)                                   # a few long lines, one full 512-token line
+    for row, n in ((3, 300), (11, 512), (20, 131)):
+        ids[row] = 1
+        ids[row, :n] = torch.cat([torch.tensor([0, 6, 2]), torch.randint(4, cfg.vocab_size, (n - 4,), generator=g),
+                                  torch.tensor([2])])
+    ref = oroberta.get_repr(m.state_dict(), cases.roberta_geometry(cfg), ids)
+    m = m.to(DEV)
+    packed = m.myEncode_ids(ids)
+    padded, _ = m.get_repr(ids.to(DEV))
+    torch.cuda.synchronize()
+    assert packed.shape == (37, cfg.hidden_size)
+    assert rel_err(packed, ref) < 1e-2, rel_err(packed, ref)
+    assert rel_err(packed, padded) < 5e-3, rel_err(packed, padded)
+    # list-of-lists input, small pass size (several passes) -> same vectors
+    as_lists = [r[r != 1].tolist() for r in ids]
+    again = m.encoder.encode_lines(as_lists, rows_per_pass=1)
+    assert rel_err(again, packed) < 2e-3
+    with pytest.raises(RuntimeError):
+        m.myEncode_ids(ids.to(DEV))                                        # packing happens on the host
+    with pytest.raises(RuntimeError):
+        m.myEncode(["int a = 0;"])                                         # no tokenizer offline

@@ -170,3 +170,25 @@ def test_product_path_fails_loudly_without_gpu():
                 "mvuld_b200/unixcoder.py", "mvuld_b200/mvuld.py", "mvuld_b200/graph.py", "mvuld_b200/synth.py"):
         src = open(os.path.join(ROOT, mod)).read()
         assert "import oracle" not in src and "from oracle" not in src, f"{mod} must not use the oracle"
+
+
+def test_pack_lines_next_fit_keeps_order_and_capacity():
+    from mvuld_b200.unixcoder import pack_lines, _lines_to_rows
+    lens = [200, 200, 200, 512, 1, 511, 2, 100]
+    row, off, n = pack_lines(lens, 512)
+    assert row == [0, 0, 1, 2, 3, 3, 4, 4] and off == [0, 200, 0, 0, 0, 1, 0, 2] and n == 5
+    used = {}
+    for r, o, l in zip(row, off, lens):
+        assert o == used.get(r, 0)                      # back to back, input order
+        used[r] = o + l
+        assert used[r] <= 512
+    assert pack_lines([], 512) == ([], [], 0)
+    with pytest.raises(ValueError):
+        pack_lines([513], 512)
+    ids = synth.line_token_ids(5, vocab=1000, seed=3)
+    rows, ln = _lines_to_rows(ids, 1)
+    assert all(len(r) == l and r[0] == 0 and r[1] == 6 and r[2] == 2 and r[-1] == 2 for r, l in zip(rows, ln))
+    bad = ids.clone()
+    bad[0, 2] = 1                                       # a pad token in the middle of a line
+    with pytest.raises(ValueError):
+        _lines_to_rows(bad, 1)
