@@ -124,6 +124,14 @@ int mvuld_masked_mean(const float* tok, const int* len, float* out, int B, int L
 int mvuld_csr_from_coo(const long long* src, const long long* dst, int E, int N, void* workspace,
                        size_t* workspace_bytes, int* indptr, int* idx_src, int* eids, int* status,
                        mvuld_stream_t stream);
+/* dgl.add_self_loop + dgl.batch on the device (mvuld/data/data_list.py:314, mvuld/data/bigvul_dataset.py:177-205):
+ * raw per-graph edge lists with LOCAL int32 node ids concatenated graph by graph (etype_local int64 or null), edge_off /
+ * node_off int64 [B + 1] exclusive prefix sums of the per-graph counts.  Output (int64, DGL order): per graph its edges
+ * in input order shifted by node_off[k], then -- if add_self_loops -- its N_k loops (i, i) with zero edge data.
+ * total_out = E_raw (+ N).  *status is set to 1 if a local id is outside [0, N_k). */
+int mvuld_collate_edges(const int* src_local, const int* dst_local, const long long* etype_local,
+                        const long long* edge_off, const long long* node_off, int B, int add_self_loops, long long* src,
+                        long long* dst, long long* etype, long long total_out, int* status, mvuld_stream_t stream);
 /* etype_sorted[i] = uint8(etype[eids[i]]); status[0] = 1 if any etype outside [0, n_etypes) (DGL asserts). */
 int mvuld_gather_etype(const long long* etype, const int* eids, int E, int n_etypes, unsigned char* out, int* status,
                        mvuld_stream_t stream);

@@ -46,6 +46,42 @@ __global__ void gather_etype_kernel(const long long* __restrict__ etype, const i
   }
 }
 
+// ------------------------------------------- collate (dgl.add_self_loop + dgl.batch) -------------------------------------------
+// Raw per-graph edge lists with LOCAL node ids, concatenated graph by graph (src_l / dst_l int32, etype_l int64 or
+// null), edge_off / node_off = exclusive prefix sums of the per-graph edge / node counts (int64 [B + 1]).
+// Output in DGL order: graph k contributes its E_k edges in input order with ids shifted by
+// node_off[k], then -- when add_loops -- its N_k self loops (i, i) with zero-filled edge data
+// (mvuld/data/data_list.py:314 add_self_loop before mvuld/data/bigvul_dataset.py:177-205 batch).
+__global__ void collate_edges_kernel(const int* __restrict__ src_l, const int* __restrict__ dst_l,
+                                     const long long* __restrict__ etype_l, const long long* __restrict__ edge_off,
+                                     const long long* __restrict__ node_off, int B, int add_loops,
+                                     long long* __restrict__ src, long long* __restrict__ dst,
+                                     long long* __restrict__ etype, long long total, int* __restrict__ bad) {
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = B - 1;                       // graph k with out_off[k] <= o < out_off[k + 1]
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const long long start = edge_off[mid] + (add_loops ? node_off[mid] : 0);
+      if (start <= o) lo = mid; else hi = mid - 1;
+    }
+    const long long nb = node_off[lo], eb = edge_off[lo];
+    const long long ek = edge_off[lo + 1] - eb, nk = node_off[lo + 1] - nb;
+    const long long l = o - (eb + (add_loops ? nb : 0));
+    if (l < ek) {
+      const int sl = src_l[eb + l], dl = dst_l[eb + l];
+      if (sl < 0 || sl >= nk || dl < 0 || dl >= nk) atomicExch(bad, 1);
+      src[o] = nb + sl;
+      dst[o] = nb + dl;
+      if (etype) etype[o] = etype_l ? etype_l[eb + l] : 0;
+    } else {
+      src[o] = nb + (l - ek);
+      dst[o] = nb + (l - ek);
+      if (etype) etype[o] = 0;
+    }
+  }
+}
+
 // ------------------------------------------- GGNN aggregation -------------------------------------------
 // msgs: bf16 [N, T, D] (per-etype linear already applied, bias included).  One warp owns NPW consecutive destination
 // nodes and walks their (contiguous) in-edge range as one flat list, UNROLL gathered rows in flight at a time: a
@@ -439,6 +475,19 @@ extern "C" int mvuld_csr_from_coo(const long long* src, const long long* dst, in
   }
   size_t cb = scan_bytes;
   MV_CUDA_OK(cub::DeviceScan::InclusiveSum(d_tmp, cb, indptr, indptr, N + 1, stream));
+  return 0;
+}
+
+extern "C" int mvuld_collate_edges(const int* src_local, const int* dst_local, const long long* etype_local,
+                                   const long long* edge_off, const long long* node_off, int B, int add_self_loops,
+                                   long long* src, long long* dst, long long* etype, long long total_out, int* status,
+                                   cudaStream_t stream) {
+  MV_CHECK_ARG(B >= 1 && total_out >= 0, "collate: empty batch");
+  if (total_out == 0) return 0;
+  collate_edges_kernel<<<grid_for(total_out, 256), 256, 0, stream>>>(src_local, dst_local, etype_local, edge_off,
+                                                                     node_off, B, add_self_loops, src, dst, etype,
+                                                                     total_out, status);
+  MV_LAUNCH_OK();
   return 0;
 }
 

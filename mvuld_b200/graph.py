@@ -108,6 +108,9 @@ class Graph:
         """Raise if the CSR build saw an endpoint outside [0, N) (one small D2H read)."""
         if self._csr is not None and int(self._csr[3].item()) != 0:
             raise ValueError("edge endpoint outside [0, num_nodes)")
+        st = getattr(self, "_collate_status", None)
+        if st is not None and int(st.item()) != 0:
+            raise ValueError("batch_device: a local node id lies outside its graph")
 
 
 def graph(edges, num_nodes: Optional[int] = None) -> Graph:
@@ -142,6 +145,62 @@ def batch(graphs: Sequence[Graph]) -> Graph:
         out.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0)
     for k in graphs[0].edata:
         out.edata[k] = torch.cat([g.edata[k] for g in graphs], 0)
+    return out
+
+
+def batch_device(graphs: Sequence[Graph], device, add_self_loops: bool = False, pin: bool = True) -> Graph:
+    """``dgl.batch`` (and optionally ``dgl.add_self_loop`` per graph first) with the index arithmetic on the GPU.
+
+    The host only concatenates the graphs' raw LOCAL edge lists (int32) and node data; one kernel
+    (``mvuld_collate_edges``) shifts node ids by the running node count, interleaves each graph's self loops after its
+    own edges and zero-fills their edge data -- the edge order DGL produces, bit-exact with
+    ``batch([add_self_loop(g) for g in graphs])``.  ``ndata`` / other ``edata`` are concatenated on the host
+    (self-loop rows of extra edata are zero-filled there) and copied."""
+    import numpy as np
+    if not graphs:
+        raise ValueError("cannot batch an empty list of graphs")
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("batch_device collates on a CUDA device (no CPU fallback); use graph.batch on the host")
+    B = len(graphs)
+    bnn = torch.tensor([g.num_nodes() for g in graphs], dtype=torch.int64)
+    bne_raw = torch.tensor([g.num_edges() for g in graphs], dtype=torch.int64)
+    node_off = torch.zeros(B + 1, dtype=torch.int64)
+    node_off[1:] = torch.cumsum(bnn, 0)
+    edge_off = torch.zeros(B + 1, dtype=torch.int64)
+    edge_off[1:] = torch.cumsum(bne_raw, 0)
+    N, E_raw = int(node_off[-1]), int(edge_off[-1])
+    total = E_raw + (N if add_self_loops else 0)
+    stage = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+    up = lambda t: stage(t).to(device, non_blocking=True)
+    src_l = up(torch.cat([g._src for g in graphs]).to(torch.int32))
+    dst_l = up(torch.cat([g._dst for g in graphs]).to(torch.int32))
+    has_et = "_ETYPE" in graphs[0].edata
+    et_l = up(torch.cat([g.edata["_ETYPE"] for g in graphs]).to(torch.int64)) if has_et else None
+    src = torch.empty(total, dtype=torch.int64, device=device)
+    dst = torch.empty(total, dtype=torch.int64, device=device)
+    et = torch.empty(total, dtype=torch.int64, device=device) if has_et else None
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    _lib.call("mvuld_collate_edges", src_l, dst_l, et_l, up(edge_off), up(node_off), B, 1 if add_self_loops else 0,
+              src, dst, et, total, status)
+    out = Graph.__new__(Graph)
+    out._src, out._dst, out._num_nodes = src, dst, N
+    out._bnn = bnn
+    out._bne = bne_raw + (bnn if add_self_loops else 0)
+    out.ndata = {k: up(torch.cat([g.ndata[k] for g in graphs], 0)) for k in graphs[0].ndata}
+    out.edata = {"_ETYPE": et} if has_et else {}
+    for k in graphs[0].edata:
+        if k == "_ETYPE":
+            continue
+        parts = []
+        for g in graphs:
+            v = g.edata[k]
+            parts.append(v)
+            if add_self_loops:
+                parts.append(torch.zeros((g.num_nodes(),) + tuple(v.shape[1:]), dtype=v.dtype))
+        out.edata[k] = up(torch.cat(parts, 0))
+    out._csr = out._ocsr = out._offsets = None
+    out._collate_status = status
     return out
 
 

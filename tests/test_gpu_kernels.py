@@ -471,3 +471,43 @@ def test_gemm_gru_matches_torch_grucell():
     with pytest.raises(RuntimeError):
         _lib.call("mvuld_gemm_gru", X, 2 * D, wg.reshape(4 * D, 2 * D).to(DEV, torch.bfloat16).contiguous(), 2 * D, N, D,
                   2 * D, b4.to(DEV).contiguous(), h32, X, 2 * D)   # in-place bf16 state is refused
+
+
+def test_device_collate_is_bit_exact_with_dgl_order():
+    """dgl.add_self_loop + dgl.batch on the device == the host container == the oracle."""
+    r = gen(21)
+    raw, looped, host = [], [], []
+    for n in (5, 1, 130, 2, 64):
+        e = int(torch.randint(0, 3 * n + 1, (1,), generator=r))
+        src, dst = torch.randint(0, n, (e,), generator=r), torch.randint(0, n, (e,), generator=r)
+        g = G.graph((src, dst), num_nodes=n)
+        g.edata["_ETYPE"] = torch.randint(0, 4, (e,), generator=r)
+        g.edata["w"] = torch.randn(e, 2, generator=r)
+        g.ndata["x"] = torch.randn(n, 3, generator=r)
+        raw.append(g)
+        looped.append(G.add_self_loop(g))
+        host.append(dgl_ops.add_self_loop(dgl_ops.graph(src.numpy(), dst.numpy(), n)))
+    for loops, ref_list in ((True, looped), (False, raw)):
+        want = G.batch(ref_list)
+        got = G.batch_device(raw, DEV, add_self_loops=loops)
+        torch.cuda.synchronize()
+        assert torch.equal(got._src.cpu(), want._src) and torch.equal(got._dst.cpu(), want._dst)
+        assert torch.equal(got.edata["_ETYPE"].cpu(), want.edata["_ETYPE"])
+        assert torch.equal(got.edata["w"].cpu(), want.edata["w"]) and torch.equal(got.ndata["x"].cpu(), want.ndata["x"])
+        assert torch.equal(got.batch_num_nodes(), want.batch_num_nodes())
+        assert torch.equal(got.batch_num_edges(), want.batch_num_edges())
+        got.check_status()
+    ob = dgl_ops.batch(host)                                   # the oracle's restatement of DGL, with self loops
+    got = G.batch_device(raw, DEV, add_self_loops=True)
+    assert np.array_equal(got._src.cpu().numpy(), ob.src) and np.array_equal(got._dst.cpu().numpy(), ob.dst)
+    # the in-CSR built from the device-collated edges equals the oracle's
+    indptr, idx_src, eids = got.in_csr()
+    o_indptr, o_idx, o_eids = dgl_ops.in_csr(ob.src, ob.dst, ob.num_nodes)
+    assert np.array_equal(indptr.cpu().numpy(), o_indptr) and np.array_equal(idx_src.cpu().numpy(), o_idx)
+    assert np.array_equal(eids.cpu().numpy(), o_eids)
+    bad = G.graph((torch.tensor([0, 7]), torch.tensor([1, 0])), num_nodes=3)     # local id 7 in a 3-node graph
+    ok = G.graph((torch.tensor([0, 1]), torch.tensor([1, 0])), num_nodes=2)
+    with pytest.raises(ValueError):
+        G.batch_device([ok, bad], DEV).check_status()
+    with pytest.raises(RuntimeError):
+        G.batch_device(raw, "cpu")
