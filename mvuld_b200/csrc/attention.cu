@@ -26,6 +26,9 @@
 
 namespace mv {
 
+#ifndef MV_ATT_POLL_NS
+#define MV_ATT_POLL_NS 40
+#endif
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_BM = 128;          // query rows per tile (= TMEM lanes)
 constexpr int ATT_MAX_KT = 8;        // max kv tiles resident
@@ -344,8 +347,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           if (progress) {
             t_last = clock64();
-          } else if (clock64() - t_last > MV_WATCHDOG_CYCLES) {
-            __trap();
+          } else {
+            __nanosleep(MV_ATT_POLL_NS);          // a hot poll would take issue slots from the softmax warps of this scheduler
+            if (clock64() - t_last > MV_WATCHDOG_CYCLES) __trap();
           }
         }
       }

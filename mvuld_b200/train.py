@@ -494,6 +494,29 @@ class FusionTrainer:
             self.last["graph"].check_status()
         return loss, logits
 
+    def refresh(self):
+        """Re-derive the bf16 / transposed / split weight copies after the parameters were written from outside
+        (``model.load_state_dict`` copies into the flat buffer the parameters are views of)."""
+        self._refresh_shadows()
+
+    def state_dict(self) -> dict:
+        """Optimiser state in the role of ``optimizer.state_dict()`` of utils_multi.py:125-137 (flat AdamW moments)."""
+        return dict(kind="mvuld_b200.FusionTrainer", names=list(self.names), offsets=dict(self.offsets),
+                    exp_avg=self.flat_m.detach().cpu().clone(), exp_avg_sq=self.flat_v.detach().cpu().clone(),
+                    step=self.step_count, lr=self.lr, weight_decay=self.wd, betas=tuple(self.betas), eps=self.eps,
+                    clip_grad=self.clip, dropout=self.p_drop, seed=self.seed)
+
+    def load_state_dict(self, sd: dict):
+        if sd.get("kind") != "mvuld_b200.FusionTrainer" or list(sd["names"]) != list(self.names):
+            raise ValueError("optimizer state does not belong to a FusionTrainer over the same parameters")
+        self.flat_m.copy_(sd["exp_avg"])
+        self.flat_v.copy_(sd["exp_avg_sq"])
+        self.step_count = int(sd["step"])
+        self.lr, self.wd, self.betas, self.eps = float(sd["lr"]), float(sd["weight_decay"]), tuple(sd["betas"]), float(sd["eps"])
+        self.clip, self.p_drop, self.seed = float(sd["clip_grad"]), float(sd["dropout"]), int(sd["seed"])
+        wd = [0.0 if (len(self.shapes[n]) == 1 or n.endswith(".bias")) else self.wd for n in self.names]
+        self.seg_wd.copy_(torch.tensor(wd, dtype=torch.float32))
+
     def grad_norm(self) -> torch.Tensor:
         """Global gradient norm of the last step (what clip_grad_norm_ returns, utils_multi.py:233)."""
         return self.gnorm_sq.sqrt()

@@ -399,3 +399,28 @@ def test_trainer_boundary_errors():
         tr.forward_backward(g.to(DEV), img, txt.to(DEV), labels.to(DEV))       # CPU tensor
     with pytest.raises(ValueError):
         tr.forward_backward(g.to(DEV), img[:1].to(DEV), txt[:1].to(DEV), labels[:1].to(DEV))
+
+
+def test_checkpoint_round_trip_resumes_bit_identically(tmp_path):
+    """save_checkpoint / load_checkpoint (utils_multi.py:7-32,125-137 layout): a resumed trainer takes the same step."""
+    from mvuld_b200 import checkpoint
+    model, sd, tr = _make_trainer(0.0, lr=1e-3)
+    for step in range(2):
+        g, img, txt, labels = _inputs(seed=cases.SEED + step)
+        tr.step(g.to(DEV), img.to(DEV), txt.to(DEV), labels.to(DEV))
+    path = checkpoint.save_checkpoint(str(tmp_path / "ckpt_epoch_0.pth"), 0, model, tr, max_accuracy=61.5)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "lr_scheduler", "max_accuracy", "scaler", "epoch", "config"}
+    model2 = cases.make_fusion().to(DEV)
+    synth.randomize_for_parity(model2, seed=999)                           # different weights before loading
+    tr2 = train.FusionTrainer(model2, dropout=0.0, world_size=1, lr=5e-5)
+    acc, epoch = checkpoint.load_checkpoint(path, model2, tr2)
+    assert acc == 61.5 and epoch == 0 and tr2.step_count == 2 and tr2.lr == 1e-3
+    assert torch.equal(tr2.flat_p, tr.flat_p) and torch.equal(tr2.flat_m, tr.flat_m)
+    g, img, txt, labels = _inputs(seed=cases.SEED + 5)
+    for m in (model, model2):                                               # same BatchNorm running statistics too
+        pass
+    l1, o1 = tr.step(g.to(DEV), img.to(DEV), txt.to(DEV), labels.to(DEV))
+    l2, o2 = tr2.step(g.to(DEV), img.to(DEV), txt.to(DEV), labels.to(DEV))
+    assert abs(float(l1) - float(l2)) < 1e-5 * abs(float(l1))
+    assert rel_err(tr2.flat_p, tr.flat_p) < 1e-6                           # (atomics in bias gradients: not bitwise)

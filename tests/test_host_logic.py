@@ -192,3 +192,28 @@ def test_pack_lines_next_fit_keeps_order_and_capacity():
     bad[0, 2] = 1                                       # a pad token in the middle of a line
     with pytest.raises(ValueError):
         _lines_to_rows(bad, 1)
+
+
+def test_load_pretrained_strips_derived_buffers_and_reinits_head(golden):
+    """utils_multi.py:35-122 on a reference-layout SwinV2 checkpoint: derived buffers never overwrite the rebuilt ones,
+    everything else loads, a head of another width is re-initialised to zero."""
+    from mvuld_b200 import checkpoint
+    kw = dict(cases.SWIN_CASES["small_ws7"])
+    src = cases.make_swin("small_ws7")
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    for k in sd:
+        if "relative_position_index" in k:
+            sd[k] = torch.full_like(sd[k], 123)            # poison: must NOT be loaded
+    dst = mv.SwinTransformerV2(**kw).eval()
+    msg = checkpoint.load_pretrained(dst, {"model": sd})
+    assert not msg.unexpected_keys
+    assert all(any(d in k for d in ("relative_position_index", "relative_coords_table", "attn_mask"))
+               for k in msg.missing_keys)
+    got = dst.state_dict()
+    for k, v in src.state_dict().items():
+        assert torch.equal(got[k], v), k                   # parameters copied, buffers equal the re-derived ones
+    kw5 = dict(kw, num_classes=5)
+    dst5 = mv.SwinTransformerV2(**kw5).eval()
+    checkpoint.load_pretrained(dst5, sd)
+    assert float(dst5.head.weight.abs().sum()) == 0.0 and float(dst5.head.bias.abs().sum()) == 0.0
+    assert torch.equal(dst5.state_dict()["layers.0.blocks.0.attn.qkv.weight"], sd["layers.0.blocks.0.attn.qkv.weight"])
