@@ -99,6 +99,11 @@ class Multi_DefectModel_new_GCN(nn.Module):
         self.final_fc = nn.Linear(hfeat * 3, self.num_classes)
         self.final_fc_bn = nn.BatchNorm1d(hfeat * 3)
         self._plan = None
+        # Input validity (DGL raises on 0-in-degree nodes; edge endpoints must lie in [0, N)) is detected by the kernels
+        # and read back here.  With defer_checks = True the read-back (a host synchronisation per call) is postponed to
+        # raise_if_invalid(), so a pipelined caller (mvuld_b200.prefetch) can keep several steps in flight.
+        self.defer_checks = False
+        self._pending = []
 
     def invalidate(self):
         self._plan = None
@@ -110,6 +115,15 @@ class Multi_DefectModel_new_GCN(nn.Module):
     def _apply(self, fn, *a, **k):
         self._plan = None
         return super()._apply(fn, *a, **k)
+
+    def raise_if_invalid(self):
+        """Raise for any input problem recorded since the last call (one host synchronisation)."""
+        pending, self._pending = self._pending, []
+        for zero_deg, g in pending:
+            if int(zero_deg.item()) != 0:
+                raise RuntimeError("There are 0-in-degree nodes in the graph (GATConv allow_zero_in_degree=False); "
+                                   "add self-loops with mvuld_b200.graph.add_self_loop")
+            g.check_status()
 
     @torch.no_grad()
     def prepare(self):
@@ -234,10 +248,11 @@ class Multi_DefectModel_new_GCN(nn.Module):
         logits = e((B, self.num_classes), f32)
         _lib.call("mvuld_fusion_head", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
                   self.num_classes)
-        if int(zero_deg.item()) != 0:
-            raise RuntimeError("There are 0-in-degree nodes in the graph (GATConv allow_zero_in_degree=False); "
-                               "add self-loops with mvuld_b200.graph.add_self_loop")
-        g.check_status()
+        self._pending.append((zero_deg, g))
+        if not self.defer_checks:
+            self.raise_if_invalid()
+        elif len(self._pending) > 64:
+            self.raise_if_invalid()                      # bound the backlog of a caller that never asks
         return logits
 
 

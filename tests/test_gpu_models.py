@@ -211,3 +211,28 @@ def test_packed_line_encoding_matches_padded_reference_semantics():
         m.myEncode_ids(ids.to(DEV))                                        # packing happens on the host
     with pytest.raises(RuntimeError):
         m.myEncode(["int a = 0;"])                                         # no tokenizer offline
+
+
+def test_deferred_validity_checks_raise_at_the_sync_point():
+    """defer_checks postpones the per-call read-back of the kernels' input-validity flags (pipelined callers)."""
+    from mvuld_b200 import graph as G
+    fus = cases.make_fusion().to(DEV)
+    g = synth.cpg_batch(2, seed=cases.SEED)
+    gen = torch.Generator().manual_seed(1)
+    img, txt = torch.randn(2, 1024, generator=gen).to(DEV), torch.randn(2, 768, generator=gen).to(DEV)
+    want = fus(g.to(DEV), img, txt)
+    fus.defer_checks = True
+    got = fus(g.to(DEV), img, txt)
+    fus.raise_if_invalid()                                     # nothing pending is wrong
+    assert torch.equal(got, want)
+    # a graph whose node 2 has no in-edge (no self loops): the immediate mode raises in forward, the deferred one later
+    bad = G.graph((torch.tensor([0, 1]), torch.tensor([1, 0])), num_nodes=3)
+    bad.ndata["_UNIX_NODE_EMB"] = torch.randn(3, 768, generator=gen)
+    bad.ndata["pos_emb"] = torch.zeros(3, 4)
+    bad = G.batch([bad])
+    fus(bad.to(DEV), img[:1], txt[:1])                         # deferred: returns
+    with pytest.raises(RuntimeError, match="0-in-degree"):
+        fus.raise_if_invalid()
+    fus.defer_checks = False
+    with pytest.raises(RuntimeError, match="0-in-degree"):
+        fus(bad.to(DEV), img[:1], txt[:1])
