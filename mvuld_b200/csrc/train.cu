@@ -98,57 +98,55 @@ __global__ void dropout_bf16_kernel(const bf16* x, bf16* out, long long n,
 
 // ------------------------------------------- BatchNorm over columns -------------------------------------------
 // x fp32 [R, C], statistics per column over the R rows (biased variance, F.batch_norm training semantics).
-// One block per 32 columns; 8 row lanes; two passes (mean, then centred second moment).
-__global__ void __launch_bounds__(256)
+// One block per BN_CL = 8 columns (a 32-byte sector per row), BN_RL = 32 row lanes; two passes (mean, then centred
+// second moment: the Rs_GCN outputs have |mean| >> deviation, a one-pass E[x^2] - E[x]^2 would cancel).  8-column
+// blocks give C / 8 CTAs (64 for C = 512) where 32-column blocks left 16 CTAs on 148 SMs (105 us per launch).
+constexpr int BN_CL = 8, BN_RL = 32;
+// Column sums run in fp64: the Rs_GCN BatchNorms normalise outputs whose batch deviation is small against their
+// magnitude, and their backward pass subtracts nearly equal sums (dy - mean(dy) - xhat mean(dy xhat)); the fp32
+// rounding of those sums was visible (percent level) in the gradients of the deepest block after 8 such stages.
+__device__ __forceinline__ double bn_col_total(double v, double (*part)[BN_CL + 1], int ry, int cl) {
+  part[ry][cl] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < BN_RL; ++k) t += part[k][cl];
+  __syncthreads();
+  return t;                                  // every thread of column cl gets the same fixed-order total
+}
+__global__ void __launch_bounds__(BN_CL * BN_RL)
 bn_cols_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, const float* res, int ldr, float* y32, int ldy, bf16* __restrict__ yb,
-                   float* __restrict__ mean_out,
-                   float* __restrict__ rstd_out, float* __restrict__ run_mean, float* __restrict__ run_var,
-                   float momentum, int R, int C) {
-  __shared__ float part[8][33];
-  __shared__ float stat[2][32];
-  const int cl = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  float s = 0.f;
-  if (c < C)
-    for (int r = ry; r < R; r += 8) s += x[(size_t)r * C + c];
-  part[ry][cl] = s;
-  __syncthreads();
-  if (ry == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][cl];
-    stat[0][cl] = t / (float)R;
-  }
-  __syncthreads();
-  const float mean = stat[0][cl];
-  float q = 0.f;
-  if (c < C)
-    for (int r = ry; r < R; r += 8) {
-      const float d = x[(size_t)r * C + c] - mean;
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ run_mean,
+                   float* __restrict__ run_var, float momentum, int R, int C) {
+  __shared__ double part[BN_RL][BN_CL + 1];
+  const int cl = threadIdx.x % BN_CL, ry = threadIdx.x / BN_CL;
+  const int c = blockIdx.x * BN_CL + cl;
+  const bool ok = c < C;
+  double s = 0.0;
+  if (ok)
+    for (int r = ry; r < R; r += BN_RL) s += (double)x[(size_t)r * C + c];
+  const double mean_d = bn_col_total(s, part, ry, cl) / (double)R;
+  const float mean = (float)mean_d;
+  double q = 0.0;
+  if (ok)
+    for (int r = ry; r < R; r += BN_RL) {
+      const double d = (double)x[(size_t)r * C + c] - mean_d;
       q += d * d;
     }
-  part[ry][cl] = q;
-  __syncthreads();
+  const float var = (float)(bn_col_total(q, part, ry, cl) / (double)R);
+  const float rstd = rsqrtf(var + eps);
+  if (!ok) return;
   if (ry == 0) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][cl];
-    const float var = t / (float)R;
-    stat[1][cl] = rsqrtf(var + eps);
-    if (c < C) {
-      mean_out[c] = mean;
-      rstd_out[c] = stat[1][cl];
-      if (run_mean) {                     // nn.BatchNorm1d running statistics (unbiased variance, momentum 0.1)
-        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
-        run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * ((float)R / (float)max(R - 1, 1));
-      }
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+    if (run_mean) {                       // nn.BatchNorm1d running statistics (unbiased variance, momentum 0.1)
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * ((float)R / (float)max(R - 1, 1));
     }
   }
-  __syncthreads();
-  if (c >= C) return;
-  const float rstd = stat[1][cl], g = gamma[c], b = beta[c];
-  for (int r = ry; r < R; r += 8) {
+  const float g = gamma[c], b = beta[c];
+  for (int r = ry; r < R; r += BN_RL) {
     float v = (x[(size_t)r * C + c] - mean) * rstd * g + b;
     if (res) v += res[(size_t)r * ldr + c];            // Rs_GCN.py:70: W_y + v (res may alias y32)
     if (y32) y32[(size_t)r * ldy + c] = v;
@@ -157,40 +155,32 @@ bn_cols_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 }
 
 // dx = gamma rstd / R * (R dy - sum(dy) - xhat sum(dy xhat));  dgamma += sum(dy xhat);  dbeta += sum(dy)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BN_CL * BN_RL)
 bn_cols_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int ldy, const float* __restrict__ gamma,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx32,
                    bf16* __restrict__ dxb, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int C) {
-  __shared__ float part[2][8][33];
-  __shared__ float tot[2][32];
-  const int cl = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  const float m = c < C ? mean[c] : 0.f, rs = c < C ? rstd[c] : 0.f;
-  float s1 = 0.f, s2 = 0.f;
-  if (c < C)
-    for (int r = ry; r < R; r += 8) {
+  __shared__ double part[BN_RL][BN_CL + 1];
+  const int cl = threadIdx.x % BN_CL, ry = threadIdx.x / BN_CL;
+  const int c = blockIdx.x * BN_CL + cl;
+  const bool ok = c < C;
+  const float m = ok ? mean[c] : 0.f, rs = ok ? rstd[c] : 0.f;
+  double s1 = 0.0, s2 = 0.0;
+  if (ok)
+    for (int r = ry; r < R; r += BN_RL) {
       const float g = dy[(size_t)r * ldy + c];
-      s1 += g;
-      s2 += g * (x[(size_t)r * C + c] - m) * rs;
+      s1 += (double)g;
+      s2 += (double)g * (double)((x[(size_t)r * C + c] - m) * rs);
     }
-  part[0][ry][cl] = s1;
-  part[1][ry][cl] = s2;
-  __syncthreads();
+  const float a = (float)bn_col_total(s1, part, ry, cl);
+  const float b = (float)bn_col_total(s2, part, ry, cl);
+  if (!ok) return;
   if (ry == 0) {
-    float a = 0.f, b = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { a += part[0][k][cl]; b += part[1][k][cl]; }
-    tot[0][cl] = a;
-    tot[1][cl] = b;
-    if (c < C) {
-      dbeta[c] += a;
-      dgamma[c] += b;
-    }
+    dbeta[c] += a;
+    dgamma[c] += b;
   }
-  __syncthreads();
-  if (c >= C || (!dx32 && !dxb)) return;
-  const float a = tot[0][cl], b = tot[1][cl], k = gamma[c] * rs / (float)R;
-  for (int r = ry; r < R; r += 8) {
+  if (!dx32 && !dxb) return;
+  const float k = gamma[c] * rs / (float)R;
+  for (int r = ry; r < R; r += BN_RL) {
     const float xh = (x[(size_t)r * C + c] - m) * rs;
     const float v = k * ((float)R * dy[(size_t)r * ldy + c] - a - xh * b);
     if (dx32) dx32[(size_t)r * C + c] = v;
@@ -861,14 +851,14 @@ extern "C" int mvuld_bn_cols_fwd(const float* x, const float* gamma, const float
                                  int ldr, float* y32, int ldy, void* yb, float* mean, float* rstd, float* run_mean,
                                  float* run_var, float momentum, int R, int C, cudaStream_t stream) {
   MV_CHECK_ARG(R >= 1 && C >= 1, "bn_cols_fwd: empty");
-  bn_cols_fwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, gamma, beta, eps, res, ldr, y32, ldy, reinterpret_cast<bf16*>(yb), mean, rstd, run_mean, run_var, momentum, R, C);
+  bn_cols_fwd_kernel<<<(C + BN_CL - 1) / BN_CL, BN_CL * BN_RL, 0, stream>>>(x, gamma, beta, eps, res, ldr, y32, ldy, reinterpret_cast<bf16*>(yb), mean, rstd, run_mean, run_var, momentum, R, C);
   MV_LAUNCH_OK();
   return 0;
 }
 extern "C" int mvuld_bn_cols_bwd(const float* x, const float* dy, int ldy, const float* gamma, const float* mean,
                                  const float* rstd, float* dx32, void* dxb, float* dgamma, float* dbeta, int R, int C,
                                  cudaStream_t stream) {
-  bn_cols_bwd_kernel<<<(C + 31) / 32, 256, 0, stream>>>(x, dy, ldy, gamma, mean, rstd, dx32, reinterpret_cast<bf16*>(dxb), dgamma, dbeta, R, C);
+  bn_cols_bwd_kernel<<<(C + BN_CL - 1) / BN_CL, BN_CL * BN_RL, 0, stream>>>(x, dy, ldy, gamma, mean, rstd, dx32, reinterpret_cast<bf16*>(dxb), dgamma, dbeta, R, C);
   MV_LAUNCH_OK();
   return 0;
 }
