@@ -263,6 +263,19 @@ struct EpiQkvHeads {
 // h32 (fp32 state) is updated in place; the bf16 shadow goes to ANOTHER buffer than the one the A operand is read from
 // (other tiles of the same rows are still loading it).  Replaces two GEMMs writing gi / gh (2 x N x 3D bf16) and the
 // element-wise gate kernel that read them back.
+// 256-bit global accesses (sm_100 PTX): one full 32-byte sector per lane and instruction.  Two 128-bit stores to the
+// halves of a sector reached L2 as partial writes (ncu: 0.66 GB of extra DRAM reads per launch to fill them).
+__device__ __forceinline__ void ld_global_v8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float* o) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+               "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+               : "memory");
+}
+
 struct EpiGru {
   static constexpr bool kStaged = false;
   static constexpr bool kPrefetch = true;
@@ -275,9 +288,7 @@ struct EpiGru {
   // this read would otherwise sit in the epilogue's critical path twice per tile
   __device__ __forceinline__ void prefetch(int row, int col0, Pre& p) const {
     if (row >= M || col0 >= 4 * D) return;
-    const float* hp = h32 + (size_t)row * D + (col0 >> 2);
-    p.h0 = *reinterpret_cast<const float4*>(hp);
-    p.h1 = *reinterpret_cast<const float4*>(hp + 4);
+    ld_global_v8(h32 + (size_t)row * D + (col0 >> 2), p.h0, p.h1);
   }
   __device__ __forceinline__ void operator()(int row, int col0, const uint32_t (&r)[32], const Pre& p) const {
     if (row >= M || col0 >= 4 * D) return;
@@ -296,8 +307,7 @@ struct EpiGru {
       const float nn = 1.0f - 2.0f * rcp_approx(1.0f + ex2_approx(2.0f * L2E * (pi + rg * ph)));   // tanh
       o[q] = (1.0f - zg) * nn + zg * h[q];
     }
-    *reinterpret_cast<float4*>(hp) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(hp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    st_global_v8(hp, o);
     uint4 w;
     w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
     w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
