@@ -31,8 +31,19 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout; rank 0 prints ONE JSON line there
+# Rank 0 prints ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner to fd 1 at
+# the VERSION and WARN debug levels), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 
 import torch  # noqa: E402
 
@@ -381,14 +392,14 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
     unit = UNIT[args.workload]
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC.get(args.workload, f"{args.workload} branch {unit}"), "value": v, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "sample": f"{sample} units per step on the host CPU"},
         "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} units x {args.steps} steps"},
-        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -594,7 +605,7 @@ def main():
         dt = (time.perf_counter() - t0) / reps
         line["cpu_baseline"] = {"value": sample / dt, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{sample} units, mean of {reps} runs after 1 warm-up, fp32 oracle"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
