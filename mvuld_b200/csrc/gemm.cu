@@ -26,6 +26,14 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // warp 0 TMA, warp 1 M
 // ------------------------------------------------------------------------------------------------
 // Epilogues.  Called once per (row, 32-column chunk) by the thread that owns the row.
 // ------------------------------------------------------------------------------------------------
+// 256-bit global store of eight 32-bit words (sm_100 PTX): one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void st_global_v8_b32(void* p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+                                                 uint32_t w5, uint32_t w6, uint32_t w7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2), "r"(w3),
+               "r"(w4), "r"(w5), "r"(w6), "r"(w7)
+               : "memory");
+}
+
 struct EpiGeneric {
   static constexpr bool kStaged = false;
   const float* bias;   // [N] or null
@@ -190,27 +198,22 @@ struct EpiQkvSwin {
     const int slot = (hh % ws) * ws + (ww % ws);
     const int nW = (H / ws) * nWw;
     const size_t dst = ((((size_t)b * nW + win) * nH + head) * (size_t)(ws * ws) + slot) * 32;
+    // one head of one token = 64 contiguous bytes = two 256-bit stores
+    uint32_t w[16];
     if (which == 2) {
-      bf16* op = v + dst;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(v32[i], v32[i + 1]); u.y = pack_bf16x2(v32[i + 2], v32[i + 3]);
-        u.z = pack_bf16x2(v32[i + 4], v32[i + 5]); u.w = pack_bf16x2(v32[i + 6], v32[i + 7]);
-        *reinterpret_cast<uint4*>(op + i) = u;
-      }
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v32[2 * i], v32[2 * i + 1]);
     } else {
-      __half* op = (which == 0 ? q : k) + dst;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        __half2 h0 = __floats2half2_rn(v32[i], v32[i + 1]), h1 = __floats2half2_rn(v32[i + 2], v32[i + 3]);
-        __half2 h2 = __floats2half2_rn(v32[i + 4], v32[i + 5]), h3 = __floats2half2_rn(v32[i + 6], v32[i + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(op + i) = u;
+      for (int i = 0; i < 16; ++i) {
+        __half2 h = __floats2half2_rn(v32[2 * i], v32[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
       }
     }
+    uint8_t* op = which == 2 ? reinterpret_cast<uint8_t*>(v + dst)
+                             : reinterpret_cast<uint8_t*>((which == 0 ? q : k) + dst);
+    st_global_v8_b32(op, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+    st_global_v8_b32(op + 32, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
   }
 };
 
@@ -244,14 +247,12 @@ struct EpiQkvHeads {
     }
     const int b = row / L, t = row - b * L;
     bf16* base = which == 0 ? q : (which == 1 ? k : v);
-    bf16* op = base + ((((size_t)b * nH + head) * L + t) * hd + d0);
+    uint8_t* op = reinterpret_cast<uint8_t*>(base + ((((size_t)b * nH + head) * L + t) * hd + d0));
+    uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      uint4 u;
-      u.x = pack_bf16x2(v32[i], v32[i + 1]); u.y = pack_bf16x2(v32[i + 2], v32[i + 3]);
-      u.z = pack_bf16x2(v32[i + 4], v32[i + 5]); u.w = pack_bf16x2(v32[i + 6], v32[i + 7]);
-      *reinterpret_cast<uint4*>(op + i) = u;
-    }
+    for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v32[2 * i], v32[2 * i + 1]);
+    st_global_v8_b32(op, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+    st_global_v8_b32(op + 32, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
   }
 };
 
