@@ -1,0 +1,86 @@
+"""GPU: BASELINE.json's full sizes, checked through size-independent properties (the CPU oracle would take hours there):
+sortedness / permutation / stability of the CSR build, independence of graphs and functions inside a batch (the property
+that lets the path shard over GPUs with no collective), linearity of the segment-sum readout."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import mvuld_b200 as mv                     # noqa: E402
+from mvuld_b200 import _lib, synth          # noqa: E402
+from mvuld_b200 import graph as G           # noqa: E402
+from tests import cases                     # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ggnn_full():
+    g = synth.ggnn_batch(4096, seed=cases.SEED, n_etypes=cases.GGNN_T)          # configs[2]: ~825 k nodes, ~4.1 M edges
+    model = cases.make_ggnn().to(DEV)
+    return g, model
+
+
+def test_csr_full_size_is_a_stable_sort_by_destination(ggnn_full):
+    g, _ = ggnn_full
+    gd = g.to(DEV)
+    indptr, idx_src, eids = gd.in_csr()
+    gd.check_status()
+    E, N = g.num_edges(), g.num_nodes()
+    indptr, idx_src, eids = indptr.cpu().long(), idx_src.cpu().long(), eids.cpu().long()
+    assert indptr[0] == 0 and indptr[-1] == E and bool((indptr[1:] >= indptr[:-1]).all())
+    assert torch.equal(torch.sort(eids).values, torch.arange(E))                # a permutation of the edge ids
+    src, dst = g.edges()
+    dst_sorted = dst[eids]
+    assert bool((dst_sorted[1:] >= dst_sorted[:-1]).all())                      # grouped by destination
+    same = dst_sorted[1:] == dst_sorted[:-1]
+    assert bool((eids[1:][same] > eids[:-1][same]).all())                       # stable: edge id increases inside a group
+    assert torch.equal(idx_src, src[eids])
+    assert torch.equal(torch.bincount(dst, minlength=N), indptr[1:] - indptr[:-1])
+
+
+def test_ggnn_full_size_graphs_are_independent_and_readout_is_linear(ggnn_full):
+    g, model = ggnn_full
+    prob, logit = model(g.to(DEV))
+    h = g_states = model._last_sum.clone()                                      # [4096, 200] per-graph sums
+    assert prob.shape == (4096,) and torch.isfinite(logit).all()
+    # the same graphs run as a batch of their own give the same readout (no cross-graph edges; row-wise kernels):
+    # rebuild graphs 100..163 from the batch
+    bnn, bne = g.batch_num_nodes(), g.batch_num_edges()
+    noff = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(bnn, 0)])
+    eoff = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(bne, 0)])
+    lo, hi = 100, 164
+    src, dst = g.edges()
+    sub = G.Graph(src[eoff[lo]:eoff[hi]] - noff[lo], dst[eoff[lo]:eoff[hi]] - noff[lo], int(noff[hi] - noff[lo]),
+                  bnn[lo:hi].clone(), bne[lo:hi].clone())
+    sub.ndata["_WORD2VEC"] = g.ndata["_WORD2VEC"][noff[lo]:noff[hi]]
+    sub.edata["_ETYPE"] = g.edata["_ETYPE"][eoff[lo]:eoff[hi]]
+    prob_s, logit_s = model(sub.to(DEV))
+    assert float((model._last_sum - h[lo:hi]).abs().max()) <= 1e-4 * float(h[lo:hi].abs().max())
+    assert torch.allclose(logit_s, logit[lo:hi], rtol=1e-4, atol=1e-5)
+    # linearity of the segment-sum readout at full size: sum over graphs of the readout == sum over all node states
+    states = model.node_states(g.to(DEV))
+    total = states.double().sum(0)
+    s = torch.empty(4096, states.shape[1], device=DEV)
+    _lib.call("mvuld_segment_sum", states, g.to(DEV).node_offsets(), s, 4096, states.shape[1])
+    assert float((s.double().sum(0) - total).abs().max()) <= 1e-6 * float(states.abs().sum())
+
+
+def test_full_forward_functions_are_independent_of_their_batch():
+    """configs[3] at the benchmark's per-GPU batch: a function's logits do not depend on what else is in the batch --
+    the property behind collective-free batch sharding."""
+    torch.manual_seed(cases.SEED)
+    model = mv.MVulD(mv.default_config()).eval()
+    synth.randomize_for_parity(model, seed=777)
+    model = model.to(DEV)
+    B = 64
+    img, ids = synth.images(B, 448, seed=3), synth.token_ids(B, 512, seed=3)
+    graphs = [synth.cpg_batch(1, seed=1000 + i) for i in range(B)]
+    whole = model(img.to(DEV), ids.to(DEV), G.batch(graphs).to(DEV)).cpu()
+    assert whole.shape == (B, 2) and torch.isfinite(whole).all()
+    lo, hi = 16, 48                                                             # the shard a second rank would take
+    part = model(img[lo:hi].to(DEV), ids[lo:hi].to(DEV), G.batch(graphs[lo:hi]).to(DEV)).cpu()
+    scale = float(whole.abs().max())
+    assert float((part - whole[lo:hi]).abs().max()) <= 2e-3 * scale
+    assert torch.equal(part.argmax(1), whole[lo:hi].argmax(1))
