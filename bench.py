@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (default: 64 functions / 64 images / "
                                                          "4096 graphs / 32 functions for train)")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg of the default workload")
+    ap.add_argument("--padded-text", action="store_true", help="run the text branch on the tokenizer's padded [B, 512] "
+                                                               "rows instead of packing the real tokens")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     return ap.parse_args()
@@ -234,8 +236,11 @@ def build_workload(args, rank, device):
         model = mv.MVulD(mv.default_config()).eval()
         synth.randomize_for_parity(model, seed=777)
         model = model.to(device)
-        host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=synth.token_ids(B, 512, seed=seed).pin_memory(),
-                    g=synth.cpg_batch(B, seed=seed))
+        raw_ids = synth.token_ids(B, 512, seed=seed)
+        # the tokenizer's [B, 512] ids packed at data-loading time (pad tokens dropped, functions back to back in rows
+        # of 512): same sentence vectors, the encoder runs over the real tokens only (mvuld_b200/unixcoder.py)
+        ids = raw_ids.pin_memory() if args.padded_text else model.unix.encoder.pack_host(raw_ids)
+        host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=ids, g=synth.cpg_batch(B, seed=seed))
         for k in ("_UNIX_NODE_EMB", "pos_emb"):
             host["g"].ndata[k] = host["g"].ndata[k].pin_memory()
         host["g"].ndata.pop("_FUNC_EMB")           # feeds only the dead h_func branch (GraphModel.py:172,177)
@@ -249,13 +254,17 @@ def build_workload(args, rank, device):
             d["g"]._csr = None                     # graph collate (CSR build) is part of every step
             return model(d["img"], d["ids"], d["g"])
 
-        h2d = host["img"].numel() * 4 + host["ids"].numel() * 8 + host["g"]._src.numel() * 16 + \
+        ids_bytes = host["ids"].numel() * 8 if args.padded_text else host["ids"].nbytes
+        h2d = host["img"].numel() * 4 + ids_bytes + host["g"]._src.numel() * 16 + \
             sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
-        name = (f"MVulD full fused inference (configs[3]): SwinV2-B 448px/w28 + UniXcoder-base 512 tok + GAT x2/"
+        text = (f"512 tok padded rows" if args.padded_text else
+                f"{int((raw_ids != 1).sum()) / B:.0f} real tokens per function packed into {ids.n_rows} rows of 512")
+        name = (f"MVulD full fused inference (configs[3]): SwinV2-B 448px/w28 + UniXcoder-base ({text}) + GAT x2/"
                 f"Rs_GCN x8 fusion, {B} synthetic functions per GPU per step, avg "
                 f"{host['g'].num_nodes() / B:.0f} CPG nodes")
-        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name, flops_per_unit=262.1e9,
-                    model=model, host=host)
+        text_rows = B if args.padded_text else ids.n_rows            # encoder rows of 512 tokens actually computed
+        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name,
+                    flops_per_unit=159.08e9 + 96.64e9 * text_rows / B + 6.40e9, model=model, host=host)
     if args.workload == "swin":
         B = args.batch or 64
         model = mv.build_model(mv.default_config()).eval()
@@ -302,8 +311,9 @@ def build_train_workload(args, rank, device, world, model=None):
     base_lr = 5e-5 * B * world / 512.0                                     # main_bigvul.py:545 linear scaling rule
     trainer = FusionTrainer(model.fusion, lr=base_lr, weight_decay=0.005, clip_grad=5.0, dropout=0.2, seed=12345 + rank,
                             world_size=world)
-    host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=synth.token_ids(B, 512, seed=seed).pin_memory(),
-                g=synth.cpg_batch(B, seed=seed),
+    raw_ids = synth.token_ids(B, 512, seed=seed)
+    ids = raw_ids.pin_memory() if args.padded_text else model.unix.encoder.pack_host(raw_ids)
+    host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=ids, g=synth.cpg_batch(B, seed=seed),
                 y=torch.randint(0, 2, (B,), generator=torch.Generator().manual_seed(seed)).pin_memory())
     for k in ("_UNIX_NODE_EMB", "pos_emb"):
         host["g"].ndata[k] = host["g"].ndata[k].pin_memory()
@@ -321,14 +331,17 @@ def build_train_workload(args, rank, device, world, model=None):
         loss, _ = trainer.step(d["g"], img_embedding, func_text_embedding, d["y"], check=False)
         return loss
 
-    h2d = host["img"].numel() * 4 + host["ids"].numel() * 8 + host["g"]._src.numel() * 16 + B * 8 + \
+    ids_bytes = host["ids"].numel() * 8 if args.padded_text else host["ids"].nbytes
+    h2d = host["img"].numel() * 4 + ids_bytes + host["g"]._src.numel() * 16 + B * 8 + \
         sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
     name = (f"MVulD fusion training step (configs[4], encoders frozen as in main_bigvul.py): SwinV2-B + UniXcoder "
+            f"({'padded 512-token rows' if args.padded_text else f'real tokens packed into {ids.n_rows} rows of 512'}) "
             f"forward, fusion fwd+bwd, bucketed NCCL gradient all-reduce ({len(trainer.buckets)} buckets, "
             f"{trainer.total * 4 / 1e6:.1f} MB fp32), clip 5.0 + AdamW; {B} functions per GPU (global batch {B * world}), "
             f"avg {host['g'].num_nodes() / B:.0f} CPG nodes")
-    return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name, flops_per_unit=262.1e9 + 3 * 6.4e9,
-                trainer=trainer, host=host)
+    text_rows = B if args.padded_text else ids.n_rows
+    return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name,
+                flops_per_unit=159.08e9 + 96.64e9 * text_rows / B + 4 * 6.4e9, trainer=trainer, host=host)
 
 
 def cpu_oracle_runner(workload, sample):
@@ -576,6 +589,17 @@ def main():
                                 "frac": ach / pk["bf16_sustained"], "frac_of_burst_peak": ach / pk["bf16"],
                                 "traffic": None, "peak_source": pk["src"] +
                                 " (sustained: kernel timed inside a long step)", "share_of_step": d["ms"] / total_ms}
+            if kname == "attention":
+                # the window-attention kernel is bound by the exponentials, not the MMAs (head dim 32: one ex2 per 128
+                # tensor FLOP): report the MUFU roofline next to the tensor one (16 ex2 / clk / SM)
+                sm_hz = (clocks.get("sm_mhz") or 1965) * 1e6
+                peak_exp = 16.0 * 148 * sm_hz
+                swin_fl = sum(work_of(n, a)[1] for n, a, _, _ in inst.records if n == "mvuld_swin_window_attention")
+                swin_ms = per_kernel.get("mvuld_swin_window_attention", {"ms": 0.0})["ms"]
+                if swin_ms > 0:
+                    ach_exp = swin_fl / 128.0 / (swin_ms / 1e3)
+                    line["roofline"]["mufu"] = {"kernel": "attn_fwd_kernel<MODE_SWIN, hd 32>", "achieved_exp_per_s": ach_exp,
+                                                "peak_exp_per_s": peak_exp, "frac": ach_exp / peak_exp}
             tr = captured_traffic(kname)
             if tr:
                 line["roofline"]["traffic"] = tr["bytes"]

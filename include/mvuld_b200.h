@@ -86,9 +86,10 @@ int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* 
 int mvuld_seq_attention_packed(const void* q, const void* k, const void* v, const int* kv_len, const int* seg_lo,
                                const int* seg_hi, const int* tile_lo, const int* tile_hi, void* out, int B, int L,
                                int nH, int hd, mvuld_stream_t stream);
-/* out[s, :] = mean of token rows [seg_start[s], seg_start[s] + seg_len[s]) of tok fp32 [T, C] (unixcoder.py:37 per line). */
-int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* seg_len, float* out, int n, int C,
-                           mvuld_stream_t stream);
+/* out[out_row[s] (or s when null), :] = mean of token rows [seg_start[s], seg_start[s] + seg_len[s]) of tok fp32
+ * [T, C] (unixcoder.py:37 per sequence). */
+int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* seg_len, const int* out_row, float* out,
+                           int n, int C, mvuld_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row kernels of the image / text branches.

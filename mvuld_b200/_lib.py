@@ -47,7 +47,7 @@ SIGNATURES = {
     "mvuld_f32_to_bf16": [_P, _P, _LL, _P],
     "mvuld_collate_edges": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _LL, _P, _P],
     "mvuld_seq_attention_packed": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "mvuld_seq_segment_mean": [_P, _P, _P, _P, _I, _I, _P],
+    "mvuld_seq_segment_mean": [_P, _P, _P, _P, _P, _I, _I, _P],
     "mvuld_rs_gcn_affinity": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_rs_gcn_affinity_f32": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_split3_bf16": [_P, _I, _P, _I, _I, _I, _P],

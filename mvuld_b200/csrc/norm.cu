@@ -395,21 +395,22 @@ namespace mv {
 // of each packed line (unixcoder.py:37 per line).  One block per segment.
 __global__ void __launch_bounds__(256)
 segment_mean_kernel(const float* __restrict__ tok, const int* __restrict__ start, const int* __restrict__ len,
-                    float* __restrict__ out, int C) {
+                    const int* __restrict__ dst, float* __restrict__ out, int C) {
   const int sgm = blockIdx.x;
   const long long b = start[sgm];
   const int n = len[sgm];
+  const size_t orow = dst ? (size_t)dst[sgm] : (size_t)sgm;      // output row of this segment (packing may reorder)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
     for (int t = 0; t < n; ++t) acc += tok[(b + t) * C + c];
-    out[(size_t)sgm * C + c] = acc / (float)n;
+    out[orow * C + c] = acc / (float)n;
   }
 }
 }  // namespace mv
-extern "C" int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* seg_len, float* out, int n,
-                                      int C, cudaStream_t stream) {
+extern "C" int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* seg_len, const int* out_row,
+                                      float* out, int n, int C, cudaStream_t stream) {
   if (n <= 0) return 0;
-  mv::segment_mean_kernel<<<n, 256, 0, stream>>>(tok, seg_start, seg_len, out, C);
+  mv::segment_mean_kernel<<<n, 256, 0, stream>>>(tok, seg_start, seg_len, out_row, out, C);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -27,7 +27,9 @@ class MVulD(nn.Module):
         self.fusion = Multi_DefectModel_new_GCN(config)
 
     @torch.no_grad()
-    def forward(self, image: torch.Tensor, token_ids: torch.Tensor, g) -> torch.Tensor:
+    def forward(self, image: torch.Tensor, token_ids, g) -> torch.Tensor:
+        """``token_ids``: ``[B, 512]`` ids as the reference's tokenizer pads them, or the same batch packed at
+        data-loading time (``self.unix.encoder.pack_host(ids)``), which skips the pad tokens' share of the encoder."""
         img_embedding = self.swin.forward_features(image)
         func_text_embedding, _ = self.unix.get_repr(token_ids)
         return self.fusion(g, img_embedding, func_text_embedding)

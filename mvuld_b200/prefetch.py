@@ -13,6 +13,7 @@ from typing import Callable, Iterable, Iterator, List
 import torch
 
 from .graph import Graph
+from .unixcoder import PackedLines
 
 
 def _tensors(obj):
@@ -23,6 +24,8 @@ def _tensors(obj):
         yield obj._dst
         yield from obj.ndata.values()
         yield from obj.edata.values()
+    elif isinstance(obj, PackedLines):
+        yield from obj.tensors()
     elif isinstance(obj, dict):
         for v in obj.values():
             yield from _tensors(v)
@@ -32,8 +35,8 @@ def _tensors(obj):
 
 
 def to_device(batch, device, non_blocking: bool = True):
-    """Move a batch (tensor / Graph / dict / list of those) to ``device``."""
-    if isinstance(batch, (torch.Tensor, Graph)):
+    """Move a batch (tensor / Graph / PackedLines / dict / list of those) to ``device``."""
+    if isinstance(batch, (torch.Tensor, Graph, PackedLines)):
         return batch.to(device, non_blocking=non_blocking)
     if isinstance(batch, dict):
         return {k: to_device(v, device, non_blocking) for k, v in batch.items()}
@@ -99,6 +102,9 @@ def _allocate_like(host, device):
         g.edata = {k: _allocate_like(v, device) for k, v in host.edata.items()}
         g._csr = g._ocsr = g._offsets = None
         return g
+    if isinstance(host, PackedLines):
+        return PackedLines(host.n_lines, host.n_rows, host.n_tokens,
+                           [{k: _allocate_like(v, device) for k, v in ps.items()} for ps in host.passes])
     if isinstance(host, dict):
         return {k: _allocate_like(v, device) for k, v in host.items()}
     if isinstance(host, (list, tuple)):
@@ -114,6 +120,9 @@ def _fill(dev, host):
         _fill(dev._dst, host._dst)
         _fill(dev.ndata, host.ndata)
         _fill(dev.edata, host.edata)
+    elif isinstance(host, PackedLines):
+        for d, h in zip(dev.passes, host.passes):
+            _fill(d, h)
     elif isinstance(host, dict):
         for k in host:
             _fill(dev[k], host[k])

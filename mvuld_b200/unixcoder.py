@@ -203,17 +203,22 @@ class RobertaEncoder(nn.Module):
         """HF-style call ``encoder(ids, attention_mask=...)[0]``; the mask is re-derived from the pad id."""
         return (self.encode(input_ids)[0],)
 
-    def pack(self, line_ids, rows_per_pass: int = 64) -> "PackedLines":
-        """Host side of ``encode_lines``: next-fit packing (``pack_lines``) and the per-token arrays the kernels need
-        (ids, position ids restarting per line, the key range [lo, hi) of each token's line), vectorised with numpy and
-        copied to the GPU pass by pass (``rows_per_pass`` rows of 512 tokens per encoder pass)."""
-        import numpy as np
+    def pack(self, line_ids, rows_per_pass: int = 64, policy: str = "auto") -> "PackedLines":
+        """``pack_host`` + copy to the encoder's device."""
         if self._plan is None:
             self.prepare()
-        dev, pad, L = self._plan["dev"], int(self.config.pad_token_id), 512
+        return self.pack_host(line_ids, rows_per_pass, policy).to(self._plan["dev"], non_blocking=True)
+
+    def pack_host(self, line_ids, rows_per_pass: int = 64, policy: str = "auto") -> "PackedLines":
+        """Host side of ``encode_lines`` (data-loader work, like the tokenizer's padding it replaces): next-fit packing
+        (``pack_lines``) and the per-token arrays the kernels need (ids, position ids restarting per sequence, the key
+        range [lo, hi) of each token's sequence), vectorised with numpy, as PINNED host tensors grouped in passes of
+        ``rows_per_pass`` rows of 512 tokens."""
+        import numpy as np
+        pad, L = int(self.config.pad_token_id), 512
         flat, lens = _lines_to_flat(line_ids, pad)
         n = int(lens.size)
-        row_of, off_of, n_rows = pack_lines(lens.tolist(), L)
+        row_of, off_of, n_rows = pack_lines(lens.tolist(), L, policy)
         row_of, off_of = np.asarray(row_of, dtype=np.int64), np.asarray(off_of, dtype=np.int64)
         first = np.concatenate([[0], np.cumsum(lens)[:-1]]) if n else np.zeros(0, dtype=np.int64)
         line = np.repeat(np.arange(n), lens)                               # line of every token
@@ -229,8 +234,8 @@ class RobertaEncoder(nn.Module):
         hi[dest] = off_of[line] + lens[line]
         used = np.zeros(n_rows, dtype=np.int32)
         np.maximum.at(used, row_of, (off_of + lens).astype(np.int32))
-        # key tiles (128 keys) each 128-row query tile must visit: lines are packed in order, so the union of the key
-        # ranges of a tile's valid rows is [lo of its first valid token, hi of its last valid token)
+        # key tiles (128 keys) each 128-row query tile must visit: the sequences of a row lie back to back, so the union
+        # of the key ranges of a tile's valid rows is [lo of its first valid token, hi of its last valid token)
         QT = 128
         nqt = L // QT
         first_tok = np.arange(n_rows * nqt, dtype=np.int64) * QT                           # global token index
@@ -240,17 +245,19 @@ class RobertaEncoder(nn.Module):
         has = row_used > t_in_row
         tile_lo = np.where(has, lo[first_tok] // QT, 0).astype(np.int32)
         tile_hi = np.where(has, (hi[last_tok] + QT - 1) // QT, 1).astype(np.int32)
-        h2d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().to(dev, non_blocking=True)
+        pin = torch.cuda.is_available()
+        h2d = lambda x: (torch.from_numpy(np.ascontiguousarray(x)).pin_memory() if pin
+                         else torch.from_numpy(np.ascontiguousarray(x)))
         passes = []
         for r0 in range(0, n_rows, rows_per_pass):
             r1 = min(n_rows, r0 + rows_per_pass)
-            k0, k1 = int(np.searchsorted(row_of, r0, "left")), int(np.searchsorted(row_of, r1, "left"))
+            sel = np.nonzero((row_of >= r0) & (row_of < r1))[0]                # the sequences of this pass
             sl = slice(r0 * L, r1 * L)
-            passes.append(dict(R=r1 - r0, k0=k0, k1=k1, ids=h2d(ids[sl].reshape(r1 - r0, L)), pos=h2d(pos[sl]),
+            passes.append(dict(R=r1 - r0, n=int(sel.size), ids=h2d(ids[sl].reshape(r1 - r0, L)), pos=h2d(pos[sl]),
                                lo=h2d(lo[sl]), hi=h2d(hi[sl]), used=h2d(used[r0:r1]),
                                tlo=h2d(tile_lo[r0 * nqt:r1 * nqt]), thi=h2d(tile_hi[r0 * nqt:r1 * nqt]),
-                               start=h2d(((row_of[k0:k1] - r0) * L + off_of[k0:k1]).astype(np.int32)),
-                               len=h2d(lens[k0:k1].astype(np.int32))))
+                               start=h2d(((row_of[sel] - r0) * L + off_of[sel]).astype(np.int32)),
+                               len=h2d(lens[sel].astype(np.int32)), dst=h2d(sel.astype(np.int32))))
         return PackedLines(n, n_rows, int(flat.size), passes)
 
     @torch.no_grad()
@@ -266,6 +273,8 @@ class RobertaEncoder(nn.Module):
         qmul = LOG2E / math.sqrt(H // nH)
         eps = float(cfg.layer_norm_eps)
         out = torch.empty(packed.n_lines, H, device=p["dev"], dtype=torch.float32)
+        if packed.passes and not packed.passes[0]["ids"].is_cuda:
+            raise RuntimeError("encode_packed takes a device-resident PackedLines: call .to(device) (no CPU fallback)")
         for ps in packed.passes:
             R = ps["R"]
             M = R * L
@@ -281,8 +290,7 @@ class RobertaEncoder(nn.Module):
                 _lib.gemm(w["xb"], lp["wi"], bias=lp["bi"], act=_lib.ACT_GELU, out_bf16=w["h"])
                 _lib.gemm(w["h"], lp["wo2"], bias=lp["bo2"], out_bf16=w["y"])
                 _lib.call("mvuld_ln_rows", w["y"], w["x32"], lp["g2"], lp["b2"], w["x32"], w["xb"], M, H, eps, 2)
-            nl = ps["k1"] - ps["k0"]                                       # lines keep their order: a contiguous slice
-            _lib.call("mvuld_seq_segment_mean", w["x32"], ps["start"], ps["len"], _lib._Raw(out[ps["k0"]:ps["k1"]]), nl, H)
+            _lib.call("mvuld_seq_segment_mean", w["x32"], ps["start"], ps["len"], ps["dst"], out, ps["n"], H)
         return out
 
     def encode_lines(self, line_ids, rows_per_pass: int = 64) -> torch.Tensor:
@@ -297,10 +305,24 @@ class RobertaEncoder(nn.Module):
 
 
 class PackedLines:
-    """Lines packed into rows of 512 tokens, device resident (see ``RobertaEncoder.pack``)."""
+    """Sequences packed into rows of 512 tokens (see ``RobertaEncoder.pack_host``); host (pinned) or device resident."""
 
     def __init__(self, n_lines, n_rows, n_tokens, passes):
         self.n_lines, self.n_rows, self.n_tokens, self.passes = n_lines, n_rows, n_tokens, passes
+
+    def to(self, device, non_blocking: bool = False) -> "PackedLines":
+        mv = lambda v: v.to(device, non_blocking=non_blocking) if isinstance(v, torch.Tensor) else v
+        return PackedLines(self.n_lines, self.n_rows, self.n_tokens, [{k: mv(v) for k, v in ps.items()} for ps in self.passes])
+
+    def tensors(self):
+        for ps in self.passes:
+            for v in ps.values():
+                if isinstance(v, torch.Tensor):
+                    yield v
+
+    @property
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors())
 
     @property
     def fill(self) -> float:
@@ -341,21 +363,47 @@ def _lines_to_rows(line_ids, pad: int):
     return [flat[e - l:e] for e, l in zip(ends, lens)], lens.tolist()
 
 
-def pack_lines(lengths, L: int = 512):
-    """Next-fit packing in input order of sequences of the given lengths into rows of ``L`` tokens.
-    -> (row index per line, token offset per line, number of rows).  Keeping the input order makes each row's lines a
-    contiguous run of nodes, so segment bookkeeping is two integers per line."""
-    row_of, off_of = [], []
-    row, used = 0, 0
-    for ln in lengths:
-        if ln > L:
-            raise ValueError(f"sequence of {ln} tokens does not fit a row of {L}")
-        if used + ln > L:
-            row, used = row + 1, 0
-        row_of.append(row)
-        off_of.append(used)
-        used += ln
-    return row_of, off_of, (row + 1 if len(lengths) else 0)
+def pack_lines(lengths, L: int = 512, policy: str = "next_fit"):
+    """Pack sequences of the given lengths into rows of ``L`` tokens -> (row per sequence, token offset per sequence,
+    number of rows).
+
+    ``next_fit``: input order, a new row whenever the next sequence does not fit (fill ~0.98 for code lines of ~20
+    tokens, O(n)).  ``first_fit_decreasing``: longest first into the first row with room -- for whole functions
+    (hundreds of tokens) next-fit leaves ~20 % of the slots empty, FFD a few per cent.  ``auto`` picks FFD when the mean
+    length exceeds L / 8 and there are at most 8192 sequences."""
+    import numpy as np
+    lengths = [int(x) for x in lengths]
+    if any(ln > L for ln in lengths):
+        raise ValueError(f"a sequence does not fit a row of {L} tokens")
+    n = len(lengths)
+    if policy == "auto":
+        policy = "first_fit_decreasing" if n and n <= 8192 and sum(lengths) / n > L / 8 else "next_fit"
+    if policy == "next_fit":
+        row_of, off_of = [], []
+        row, used = 0, 0
+        for ln in lengths:
+            if used + ln > L:
+                row, used = row + 1, 0
+            row_of.append(row)
+            off_of.append(used)
+            used += ln
+        return row_of, off_of, (row + 1 if n else 0)
+    if policy != "first_fit_decreasing":
+        raise ValueError(f"unknown packing policy {policy!r}")
+    order = sorted(range(n), key=lambda i: -lengths[i])                 # stable: ties keep input order
+    free = np.full(n, L, dtype=np.int64)                                 # at most n rows
+    n_rows = 0
+    row_of, off_of = [0] * n, [0] * n
+    for i in order:
+        ln = lengths[i]
+        fits = free[:n_rows] >= ln
+        r = int(np.argmax(fits)) if fits.any() else n_rows
+        if r == n_rows:
+            n_rows += 1
+        row_of[i] = r
+        off_of[i] = int(L - free[r])
+        free[r] -= ln
+    return row_of, off_of, n_rows
 
 
 class MyUniXcoder(nn.Module):
@@ -388,7 +436,13 @@ class MyUniXcoder(nn.Module):
         return self.myEncode_ids(torch.tensor(ids, dtype=torch.long))
 
     def get_repr(self, input_ids, labels=None):
-        """unixcoder.py:91-95."""
+        """unixcoder.py:91-95.  ``input_ids``: the reference's ``[B, 512]`` ids (CUDA: run as padded rows; CPU: packed on
+        the host first), or a ``PackedLines`` from ``encoder.pack_host(ids)`` made at data-loading time -- the padding
+        of short functions (a Big-Vul function averages well under half of 512 tokens) then costs nothing."""
+        if isinstance(input_ids, PackedLines):
+            return self.encoder.encode_packed(input_ids), labels
+        if not input_ids.is_cuda:
+            return self.encoder.encode_lines(input_ids.view(-1, self.max_source_length)), labels
         source_ids = input_ids.view(-1, self.max_source_length)
         _, vec = self.get_xcode_vec(source_ids)
         return vec, labels

@@ -236,3 +236,22 @@ def test_deferred_validity_checks_raise_at_the_sync_point():
     fus.defer_checks = False
     with pytest.raises(RuntimeError, match="0-in-degree"):
         fus(bad.to(DEV), img[:1], txt[:1])
+
+
+def test_packed_text_branch_gives_the_padded_result_in_the_composed_forward():
+    """get_repr / MVulD.forward with the batch packed at data-loading time (pad tokens dropped, first-fit-decreasing)
+    == the same batch as padded [B, 512] rows; a CPU id tensor is packed on the fly."""
+    m = cases.make_roberta().to(DEV)
+    ids = synth.token_ids(12, 512, vocab=m.config.vocab_size, seed=cases.SEED + 3)
+    packed_host = m.encoder.pack_host(ids)
+    assert packed_host.n_rows < 12 and not packed_host.passes[0]["ids"].is_cuda
+    with pytest.raises(RuntimeError):
+        m.get_repr(packed_host)                                       # must be moved to the device first
+    padded, _ = m.get_repr(ids.to(DEV))
+    packed, _ = m.get_repr(packed_host.to(DEV))
+    from_cpu, _ = m.get_repr(ids)
+    assert rel_err(packed, padded) < 5e-3 and rel_err(from_cpu, padded) < 5e-3
+    # through the prefetcher (PackedLines is a batch element like a tensor or a Graph)
+    from mvuld_b200.prefetch import DevicePrefetcher
+    got = [m.get_repr(d["ids"])[0] for d in DevicePrefetcher([dict(ids=packed_host)] * 2, DEV)]
+    assert torch.equal(got[0], packed) and torch.equal(got[1], packed)

@@ -183,6 +183,17 @@ def test_pack_lines_next_fit_keeps_order_and_capacity():
         used[r] = o + l
         assert used[r] <= 512
     assert pack_lines([], 512) == ([], [], 0)
+    # first-fit-decreasing: whole functions (hundreds of tokens) pack tighter than in input order
+    lens2 = [260, 260, 250, 250, 400, 100, 12]
+    r2, o2, n2 = pack_lines(lens2, 512, "first_fit_decreasing")
+    assert n2 == 3 < pack_lines(lens2, 512, "next_fit")[2]
+    spans = {}
+    for r, o, l in zip(r2, o2, lens2):
+        spans.setdefault(r, []).append((o, o + l))
+    for r, sp in spans.items():
+        sp.sort()
+        assert sp[0][0] == 0 and sp[-1][1] <= 512 and all(a[1] == b[0] for a, b in zip(sp, sp[1:]))   # back to back
+    assert pack_lines(lens2, 512, "auto")[2] == n2 and pack_lines([20] * 100, 512, "auto") == pack_lines([20] * 100, 512)
     with pytest.raises(ValueError):
         pack_lines([513], 512)
     ids = synth.line_token_ids(5, vocab=1000, seed=3)
