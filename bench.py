@@ -566,7 +566,8 @@ def main():
             inst.remove()
         fam, per_kernel = inst.summary()
         total_ms = sum(d["ms"] for d in fam.values())
-        top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        tensor_fams = {k: v for k, v in fam.items() if v["flops"] > 0}
+        top = max((tensor_fams or fam).items(), key=lambda kv: kv[1]["ms"])       # the dominant tensor-pipe family
         if args.workload == "ggnn":
             # HBM-bound path: the segment-reduce kernel (SURVEY.md section 8d row 2, bf16 messages)
             k = per_kernel.get("mvuld_ggnn_gather_sum")
