@@ -166,10 +166,17 @@ def test_product_path_fails_loudly_without_gpu():
         g = synth.cpg_batch(1, seed=1)
         with pytest.raises(RuntimeError, match="CUDA"):
             f(g, torch.zeros(1, 1024), torch.zeros(1, 768))
-    for mod in ("mvuld_b200/_lib.py", "mvuld_b200/swin_transformer_v2.py", "mvuld_b200/graph_model.py",
-                "mvuld_b200/unixcoder.py", "mvuld_b200/mvuld.py", "mvuld_b200/graph.py", "mvuld_b200/synth.py"):
-        src = open(os.path.join(ROOT, mod)).read()
+    import glob
+    mods = sorted(glob.glob(os.path.join(ROOT, "mvuld_b200", "*.py")))
+    assert len(mods) >= 14
+    for mod in mods:                                     # every product module, including train / prefetch / checkpoint
+        src = open(mod).read()
         assert "import oracle" not in src and "from oracle" not in src, f"{mod} must not use the oracle"
+    f = cases.make_fusion()
+    if not torch.cuda.is_available():
+        from mvuld_b200 import train
+        with pytest.raises(RuntimeError, match="CUDA"):
+            train.FusionTrainer(f)                       # training has no CPU path either
 
 
 def test_pack_lines_next_fit_keeps_order_and_capacity():
