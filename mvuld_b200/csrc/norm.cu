@@ -89,86 +89,115 @@ ln_rows_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, c
   }
 }
 
-// PatchEmbed (swin_transformer_v2.py:485-493): Conv2d(3, E, k=4, s=4) as a 48-tap dot per token + LayerNorm.
-// Thread t of a 128-thread half-block keeps the 48 weights of output channel t in registers; a block walks
-// TOK tokens at a time with the 48 input taps of each token staged in shared memory.
+// PatchEmbed (swin_transformer_v2.py:485-493): Conv2d(3, E, k=4, s=4) as a 48-tap dot per token + LayerNorm, fp32.
+// One WARP per group of PE_TOK = 8 consecutive tokens: lane l owns the E / 32 consecutive output channels starting at
+// l * E / 32; the weights sit transposed in shared memory ([tap][channel]) and each 128-bit weight read serves all 8
+// tokens (with 2 tokens per read the kernel was bound by shared-memory bandwidth: 24 KB of weights per pair); the
+// 8 x 48 taps are staged per warp with 96 128-bit loads and read back as broadcasts; LayerNorm is two warp reductions
+// per token and the outputs leave as coalesced 512-byte (fp32) / 256-byte (bf16) rows.
+constexpr int PE_TOK = 8;
 template <int E>
-__global__ void __launch_bounds__(E)
+__global__ void __launch_bounds__(256)
 patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x32,
                    bf16* __restrict__ xb, int B, int Himg, int Wimg, float eps) {
-  constexpr int TOK = 16;
-  __shared__ __align__(16) float taps[TOK][48];
-  __shared__ float conv[TOK][E + 1];
-  const int oc = threadIdx.x;
-  const int Hp = Himg / 4, Wp = Wimg / 4;
-  const int total = B * Hp * Wp;                       // tokens (host checks < 2^31)
-  float wr[48];
-#pragma unroll
-  for (int i = 0; i < 48; ++i) wr[i] = __ldg(w + oc * 48 + i);
-  const float bo = __ldg(bias + oc);
+  constexpr int CPL = E / 32;                               // channels per lane
+  static_assert(E % 32 == 0 && CPL >= 1 && CPL <= 4, "embed dim must be 32, 64, 96 or 128");
+  __shared__ __align__(16) float wT[48][E];                 // wT[tap][channel] = w[channel][tap]
+  __shared__ __align__(16) float taps[8][PE_TOK][48];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t0 = blockIdx.x * TOK; t0 < total; t0 += gridDim.x * TOK) {
-    // stage the 48 taps of TOK tokens: 12 (channel, kernel-row) segments of 4 contiguous floats per token, one
-    // 128-bit load each (32-bit index math: the per-tap 64-bit divisions used to cost more than the FMAs)
-    for (int j = threadIdx.x; j < TOK * 12; j += E) {
-      const int tk = j / 12, seg = j - tk * 12;
-      const int tok = t0 + tk;
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tok < total) {
-        const int b = tok / (Hp * Wp);
-        const int rem = tok - b * (Hp * Wp);
-        const int ph = rem / Wp, pw = rem - ph * Wp;
-        const int c = seg >> 2, kh = seg & 3;
-        val = __ldg(reinterpret_cast<const float4*>(img + (((size_t)b * 3 + c) * Himg + ph * 4 + kh) * Wimg + pw * 4));
+  for (int i = threadIdx.x; i < 48 * E; i += blockDim.x) {
+    const int c = i / 48, tp = i - c * 48;
+    wT[tp][c] = __ldg(w + i);
+  }
+  const int Hp = Himg / 4, Wp = Wimg / 4;
+  const int total = B * Hp * Wp;                            // tokens (host checks < 2^31)
+  float bo[CPL], ga[CPL], be[CPL];
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    bo[q] = __ldg(bias + lane * CPL + q);
+    ga[q] = __ldg(gamma + lane * CPL + q);
+    be[q] = __ldg(beta + lane * CPL + q);
+  }
+  __syncthreads();
+  const int ngroups = (total + PE_TOK - 1) / PE_TOK;
+  for (int gr = blockIdx.x * 8 + warp; gr < ngroups; gr += gridDim.x * 8) {
+    // stage PE_TOK tokens x 12 (channel, kernel-row) segments of 4 contiguous floats, one 128-bit load each
+#pragma unroll
+    for (int it = 0; it < (PE_TOK * 12 + 31) / 32; ++it) {
+      const int j = it * 32 + lane;
+      if (j < PE_TOK * 12) {
+        const int tk = j / 12, seg = j - tk * 12;
+        const int tok = gr * PE_TOK + tk;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tok < total) {
+          const int b = tok / (Hp * Wp);
+          const int rem = tok - b * (Hp * Wp);
+          const int ph = rem / Wp, pw = rem - ph * Wp;
+          const int c = seg >> 2, kh = seg & 3;
+          val = __ldg(reinterpret_cast<const float4*>(img + (((size_t)b * 3 + c) * Himg + ph * 4 + kh) * Wimg + pw * 4));
+        }
+        *reinterpret_cast<float4*>(&taps[warp][tk][seg * 4]) = val;
       }
-      *reinterpret_cast<float4*>(&taps[tk][seg * 4]) = val;
     }
-    __syncthreads();
-    // 4 tokens at a time, taps read as 128-bit broadcasts: 4 LDS.128 per 16 FMAs (scalar reads made this loop
-    // LDS-issue bound at one LDS.32 per FMA)
-#pragma unroll 1
-    for (int tk = 0; tk < TOK; tk += 4) {
-      float acc[4] = {bo, bo, bo, bo};
+    __syncwarp();
+    float acc[PE_TOK][CPL];
 #pragma unroll
-      for (int i = 0; i < 48; i += 4) {
+    for (int tk = 0; tk < PE_TOK; ++tk)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 t = *reinterpret_cast<const float4*>(&taps[tk + j][i]);
-          acc[j] = fmaf(wr[i], t.x, acc[j]);
-          acc[j] = fmaf(wr[i + 1], t.y, acc[j]);
-          acc[j] = fmaf(wr[i + 2], t.z, acc[j]);
-          acc[j] = fmaf(wr[i + 3], t.w, acc[j]);
+      for (int q = 0; q < CPL; ++q) acc[tk][q] = bo[q];
+#pragma unroll 2
+    for (int i = 0; i < 48; i += 4) {
+      float wv[4][CPL];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (CPL == 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&wT[i + k][lane * 4]);
+          wv[k][0] = w4.x; wv[k][1] = w4.y; wv[k][2] = w4.z; wv[k][3] = w4.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) wv[k][q] = wT[i + k][lane * CPL + q];
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) conv[tk + j][oc] = acc[j];
-    }
-    __syncthreads();
-    for (int tk = warp; tk < TOK; tk += E / 32) {
-      const int tok = t0 + tk;
-      if (tok >= total) continue;
-      float v[E / 32];
-      float s = 0.f;
+      for (int tk = 0; tk < PE_TOK; ++tk) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&taps[warp][tk][i]);     // broadcast
+        const float a[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-      for (int q = 0; q < E / 32; ++q) {
-        v[q] = conv[tk][lane + q * 32];
-        s += v[q];
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) acc[tk][q] = fmaf(wv[k][q], a[k], acc[tk][q]);
       }
-      const float mean = warp_sum(s) / (float)E;
+    }
+    __syncwarp();                                            // the taps may be overwritten by the next group
+#pragma unroll
+    for (int tk = 0; tk < PE_TOK; ++tk) {
+      const int tok = gr * PE_TOK + tk;
+      float sm = 0.f;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) sm += acc[tk][q];
+      const float mean = warp_sum(sm) / (float)E;
       float sq = 0.f;
 #pragma unroll
-      for (int q = 0; q < E / 32; ++q) sq += (v[q] - mean) * (v[q] - mean);
+      for (int q = 0; q < CPL; ++q) sq += (acc[tk][q] - mean) * (acc[tk][q] - mean);
       const float rstd = rsqrtf(warp_sum(sq) / (float)E + eps);
+      if (tok >= total) continue;
+      float o[CPL];
 #pragma unroll
-      for (int q = 0; q < E / 32; ++q) {
-        const int ch = lane + q * 32;
-        const float o = (v[q] - mean) * rstd * __ldg(gamma + ch) + __ldg(beta + ch);
-        x32[(size_t)tok * E + ch] = o;
-        xb[(size_t)tok * E + ch] = __float2bfloat16(o);
+      for (int q = 0; q < CPL; ++q) o[q] = (acc[tk][q] - mean) * rstd * ga[q] + be[q];
+      float* op = x32 + (size_t)tok * E + lane * CPL;
+      bf16* ob = xb + (size_t)tok * E + lane * CPL;
+      if constexpr (CPL == 4) {
+        *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint2*>(ob) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          op[q] = o[q];
+          ob[q] = __float2bfloat16(o[q]);
+        }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -331,20 +360,20 @@ extern "C" int mvuld_patch_embed(const float* img, const float* w, const float* 
   MV_CHECK_ARG((long long)B * (Himg / 4) * (Wimg / 4) < (1ll << 31) && ((uintptr_t)img % 16) == 0,
                "patch_embed: too many tokens for 32-bit indexing or image base not 16-byte aligned");
   const long long total = (long long)B * (Himg / 4) * (Wimg / 4);
-  long long blocks = (total + 15) / 16;
-  const long long cap = (long long)num_sms() * 16;
+  long long blocks = (total / PE_TOK + 7) / 8 + 1;            // 8 warps per block, PE_TOK tokens per warp and iteration
+  const long long cap = (long long)num_sms() * 2;           // 100 registers x 256 threads: two resident blocks per SM
   if (blocks > cap) blocks = cap;
   if (E == 128)
-    patch_embed_kernel<128><<<(int)blocks, 128, 0, stream>>>(img, w, bias, gamma, beta, x32,
+    patch_embed_kernel<128><<<(int)blocks, 256, 0, stream>>>(img, w, bias, gamma, beta, x32,
                                                                reinterpret_cast<bf16*>(xb), B, Himg, Wimg, eps);
   else if (E == 96)
-    patch_embed_kernel<96><<<(int)blocks, 96, 0, stream>>>(img, w, bias, gamma, beta, x32, reinterpret_cast<bf16*>(xb),
+    patch_embed_kernel<96><<<(int)blocks, 256, 0, stream>>>(img, w, bias, gamma, beta, x32, reinterpret_cast<bf16*>(xb),
                                                              B, Himg, Wimg, eps);
   else if (E == 32)
-    patch_embed_kernel<32><<<(int)blocks, 32, 0, stream>>>(img, w, bias, gamma, beta, x32, reinterpret_cast<bf16*>(xb),
+    patch_embed_kernel<32><<<(int)blocks, 256, 0, stream>>>(img, w, bias, gamma, beta, x32, reinterpret_cast<bf16*>(xb),
                                                              B, Himg, Wimg, eps);
   else if (E == 64)
-    patch_embed_kernel<64><<<(int)blocks, 64, 0, stream>>>(img, w, bias, gamma, beta, x32, reinterpret_cast<bf16*>(xb),
+    patch_embed_kernel<64><<<(int)blocks, 256, 0, stream>>>(img, w, bias, gamma, beta, x32, reinterpret_cast<bf16*>(xb),
                                                              B, Himg, Wimg, eps);
   else
     return mv::fail(-1, "patch_embed: embed dim %d not instantiated (32, 64, 96, 128)", E);
