@@ -255,3 +255,54 @@ def test_packed_text_branch_gives_the_padded_result_in_the_composed_forward():
     from mvuld_b200.prefetch import DevicePrefetcher
     got = [m.get_repr(d["ids"])[0] for d in DevicePrefetcher([dict(ids=packed_host)] * 2, DEV)]
     assert torch.equal(got[0], packed) and torch.equal(got[1], packed)
+
+
+def test_edge_cases_ragged_and_extreme_sizes():
+    """Ragged / extreme inputs: a 2-node and a 1 500-node CPG in one batch (pad to 100 slots vs truncate,
+    GraphModel.py:30-54), batch size 1, a single GGNN graph, one / zero code lines, a full 512-token line."""
+    from mvuld_b200 import graph as G
+    fus = cases.make_fusion()
+    gen = torch.Generator().manual_seed(3)
+
+    def cpg(n):
+        src = torch.cat([torch.arange(0, n - 1), torch.randint(0, n, (n,), generator=gen)])
+        dst = torch.cat([torch.arange(1, n), torch.randint(0, n, (n,), generator=gen)])
+        g = G.graph((src, dst), num_nodes=n)
+        g.ndata["_UNIX_NODE_EMB"] = torch.randn(n, 768, generator=gen) * 0.5
+        g.ndata["pos_emb"] = torch.rand(n, 4, generator=gen)
+        return G.add_self_loop(g)
+
+    batch = G.batch([cpg(2), cpg(1500), cpg(100), cpg(101)])
+    img, txt = torch.randn(4, 1024, generator=gen), torch.randn(4, 768, generator=gen)
+    ref = ofusion.fusion_forward(fus.state_dict(), cases.to_host_batch(batch), img, txt)
+    fus = fus.to(DEV)
+    out = fus(batch.to(DEV), img.to(DEV), txt.to(DEV))
+    assert logits_close(out, ref, 1e-2) and torch.equal(out.cpu().argmax(1), ref.argmax(1))
+    one = G.batch([cpg(37)])
+    ref1 = ofusion.fusion_forward({k: v.cpu() for k, v in fus.state_dict().items()}, cases.to_host_batch(one), img[:1], txt[:1])
+    out1 = fus(one.to(DEV), img[:1].to(DEV), txt[:1].to(DEV))
+    assert logits_close(out1, ref1, 1e-2)
+    # GGNN: one graph
+    gm = cases.make_ggnn()
+    g1 = synth.ggnn_batch(1, seed=9, n_etypes=cases.GGNN_T)
+    pref, lref, _, _ = ofusion.ggnn_sum_forward(gm.state_dict(), cases.to_host_batch(g1), cases.GGNN_D, cases.GGNN_STEPS,
+                                                cases.GGNN_T)
+    prob, logit = gm.to(DEV)(g1.to(DEV))
+    assert logits_close(logit, lref, 1e-2)
+    # line encoding: one line, a full 512-token line, no lines
+    m = cases.make_roberta().to(DEV)
+    one_line = synth.line_token_ids(1, vocab=m.config.vocab_size, seed=1)
+    full_line = torch.cat([torch.tensor([0, 6, 2]), torch.randint(4, m.config.vocab_size, (508,), generator=gen),
+                           torch.tensor([2])]).view(1, 512)
+    for ids in (one_line, full_line):
+        want, _ = m.get_repr(ids.to(DEV))
+        got = m.myEncode_ids(ids)
+        assert got.shape == (1, m.config.hidden_size) and rel_err(got, want) < 5e-3
+    assert m.myEncode_ids(torch.ones(0, 512, dtype=torch.int64)).shape == (0, m.config.hidden_size)
+    with pytest.raises(ValueError):
+        m.myEncode_ids(torch.ones(1, 512, dtype=torch.int64))              # a line of pad tokens only
+    # Swin: batch of one
+    sw = cases.make_swin("small_ws7")
+    x = synth.images(1, cases.SWIN_CASES["small_ws7"]["img_size"], seed=2)
+    r = oswin.forward_features(sw.state_dict(), cases.swin_geometry("small_ws7"), x)
+    assert rel_err(sw.to(DEV).forward_features(x.to(DEV)), r) < 2e-2
