@@ -142,11 +142,14 @@ def work_of(name, args):
         B, L, Hd = args[6], args[7], args[8]
         return "gemm", 2.0 * B * L * Hd * 3 * Hd, 0.0
     if name == "mvuld_swin_window_attention":
-        B, H, W, C, nH, ws = args[6], args[7], args[8], args[9], args[10], args[11]
+        B, H, W, C, nH, ws = args[7], args[8], args[9], args[10], args[11], args[12]
         n = ws * ws
         return "attention", 4.0 * (B * H * W // n) * nH * n * n * 32, 0.0
     if name == "mvuld_seq_attention":
         B, L, nH, hd = args[5], args[6], args[7], args[8]
+        return "attention", 4.0 * B * nH * L * L * hd, 0.0
+    if name == "mvuld_seq_attention_packed":        # counted as dense rows (the skipped key tiles are the saving)
+        B, L, nH, hd = args[9], args[10], args[11], args[12]
         return "attention", 4.0 * B * nH * L * L * hd, 0.0
     return "other", 0.0, 0.0
 

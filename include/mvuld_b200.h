@@ -68,10 +68,12 @@ int mvuld_cpb_table(const float* w1, const float* b1, const float* w2, int nH, i
 
 /* softmax(q k^T + bias[rel_pos_index] + shift_mask) v, written token-major bf16 [B*H*W, C] with window_reverse and
  * the inverse cyclic shift folded into the store.  ws in {7, 14, 28}; shift in {0, ws/2}.
- * swin_transformer_v2.py:155-176 and :292-299. */
+ * swin_transformer_v2.py:155-176 and :292-299.  q_norm (optional, fp32 [nH]): the norm the qkv epilogue gave each
+ * head's queries (exp(min(logit_scale, ln 100)) * log2 e); heads with 2 q_norm + bias_max <= 100 use a constant softmax
+ * reference (no maximum pass, no rescaling), the others -- and all heads when q_norm is null -- a running maximum. */
 int mvuld_swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
-                                const float* bias_max, void* out, int B, int H, int W, int C, int nH, int ws,
-                                int shift, mvuld_stream_t stream);
+                                const float* bias_max, const float* q_norm, void* out, int B, int H, int W, int C,
+                                int nH, int ws, int shift, mvuld_stream_t stream);
 
 /* Key-padded self-attention for the text encoder: q,k,v bf16 [B, nH, L, 64] (q pre-scaled), kv_len int32 [B];
  * out bf16 [B*L, nH*64].  unixcoder.py:35-36. */

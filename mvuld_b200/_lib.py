@@ -24,7 +24,7 @@ SIGNATURES = {
     "mvuld_swin_qkv": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_heads_qkv": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "mvuld_cpb_table": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
-    "mvuld_swin_window_attention": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mvuld_swin_window_attention": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_seq_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_ln_rows": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
     "mvuld_patch_embed": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],

@@ -64,6 +64,8 @@ struct AttnParams {
   // MODE_SWIN
   const float* bias_rev;  // [nH, (2ws-1)^2] fp32, = 16*sigmoid(.)*log2e, w-axis reversed (see cpb kernel)
   const float* bias_max;  // [nH] max of the head's table (softmax reference bound)
+  const float* q_norm;    // [nH] |q^| of the head (= exp(min(logit_scale, ln 100)) * log2 e), or null: enables the
+                          // fixed softmax reference for heads whose whole logit range fits fp32 (see the kernel)
   int H, W, shift;        // token grid and cyclic shift of this block
   int C;                  // channels (= nH * HD)
   // MODE_SEQ
@@ -406,6 +408,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool colflag = (MODE == MODE_SWIN) && p.shift > 0 && (wc == nWw - 1);
     const float NEG100 = -100.0f * 1.4426950408889634f;
     const float bmax = (MODE == MODE_SWIN) ? __ldg(p.bias_max + head) : 0.f;
+    // Cosine attention bounds every raw score by |q^| |k^| = q_norm, and the bias lies in [0, bmax]: when
+    // 2 q_norm + bmax <= 100 (log2 units) the constant C = q_norm + bmax is a softmax reference under which the largest
+    // term of any row is >= 2^-100 and none exceeds 1 -- exact (the reference cancels in O / l), with no pass over the
+    // scores for a maximum and no rescaling of O, ever.  (Masked terms, -100 log2 e below the rest, flush to 0 either
+    // way.)  Heads with a larger logit scale take the running-maximum path below.  Uniform per CTA.
+    float q_norm = INFINITY;
+    if (MODE == MODE_SWIN && p.q_norm != nullptr) q_norm = __ldg(p.q_norm + head);
+    const bool fixed_ref = (MODE == MODE_SWIN) && (2.0f * q_norm + bmax <= 100.0f);
 
     // PV(m) of this group has retired (its P buffer is free again, O includes it)
     auto wait_pv = [&](uint32_t m) { mbar_wait(&pv_done[2 * g + (m % NPB)], (m / NPB) & 1, 31); };
@@ -487,6 +497,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // head's largest bias.  It bounds the true row maximum from above by at most (max - min) of the bias table
         // (<= 16 log2 e), so every 2^(.) below is <= 2^8 and the largest term of a row is >= 2^-32: an exact softmax
         // (the reference point cancels in O / l) that does not touch the bias table before the exponentials.
+        if (fixed_ref) {
+          m_run = q_norm + bmax;
+        } else {
         float segmax[NSEG];
 #pragma unroll
         for (int s = 0; s < NSEG; ++s) segmax[s] = -INFINITY;
@@ -523,6 +536,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_st32(tO + c0, o);
           }
           tmem_st_wait();
+        }
         }
         if (r == 0) ATT_TRACE(3, g, t, j);
 
@@ -757,8 +771,8 @@ extern "C" int mvuld_debug_att_trace(long long* host_out, int max_records) {
 #endif
 
 extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
-                                           const float* bias_max, void* out, int B, int H, int W, int C, int nH, int ws,
-                                           int shift, cudaStream_t stream) {
+                                           const float* bias_max, const float* q_norm, void* out, int B, int H, int W,
+                                           int C, int nH, int ws, int shift, cudaStream_t stream) {
   MV_CHECK_ARG(C == nH * 32, "swin attention: head_dim must be 32");
   MV_CHECK_ARG(H % ws == 0 && W % ws == 0, "swin attention: window must tile the token grid");
   MV_CHECK_ARG(shift == 0 || shift == ws / 2, "swin attention: shift must be 0 or ws/2");
@@ -767,6 +781,7 @@ extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const v
   p.nH = nH;
   p.bias_rev = bias_rev;
   p.bias_max = bias_max;
+  p.q_norm = q_norm;
   p.H = H; p.W = W; p.shift = shift; p.C = C;
   p.kv_len = nullptr;
   p.out = out;

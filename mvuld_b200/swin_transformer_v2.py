@@ -340,7 +340,7 @@ class SwinTransformerV2(nn.Module):
                 hid = w["h"][:M * blk["wfc1"].shape[0]].view(M, blk["wfc1"].shape[0])
                 _lib.call("mvuld_swin_qkv", xb, blk["wqkv"], blk["qb"], blk["vb"], blk["qscale"], q, k, v, B, H, W, C,
                           nH, ws, shift)
-                _lib.call("mvuld_swin_window_attention", q, k, v, blk["tab_rev"], blk["tab_max"], att, B, H, W, C, nH,
+                _lib.call("mvuld_swin_window_attention", q, k, v, blk["tab_rev"], blk["tab_max"], blk["qscale"], att, B, H, W, C, nH,
                           ws, shift)
                 if C <= 256:      # GEMM + LayerNorm + residual in one kernel; at C = 512 the row fills all 512 TMEM
                                   # columns, the epilogue cannot overlap the next tile, and two kernels are faster

@@ -196,10 +196,13 @@ def test_swin_attention_block(Hres, ws, shift, nH, B):
     assert rel_err(q.view(B_, nH, ws * ws, 32), q_ref) < 2e-3
     assert rel_err(k.view(B_, nH, ws * ws, 32), torch.nn.functional.normalize(qkv[1], dim=-1)) < 2e-3
     assert rel_err(v.view(B_, nH, ws * ws, 32), qkv[2]) < 5e-3
-    _lib.call("mvuld_swin_window_attention", q, k, v, tab_rev, tab_max, out, B, H, W, C, nH, ws, shift)
-    torch.cuda.synchronize()
-    err = rel_err(out, ref)
-    assert err < 1.5e-2, err
+    # both softmax reference policies: constant reference (these heads' logit range is small) and running maximum
+    for qn in (qscale, None):
+        out.zero_()
+        _lib.call("mvuld_swin_window_attention", q, k, v, tab_rev, tab_max, qn, out, B, H, W, C, nH, ws, shift)
+        torch.cuda.synchronize()
+        err = rel_err(out, ref)
+        assert err < 1.5e-2, (err, qn is None)
 
 
 def test_seq_attention():
