@@ -171,33 +171,24 @@ class Multi_DefectModel_new_GCN(nn.Module):
         return self
 
     @torch.no_grad()
-    def forward(self, g: Graph, img_embedding: torch.Tensor, func_text_embedding: torch.Tensor) -> torch.Tensor:
-        """GraphModel.py:150-211."""
+    def graph_features(self, g: Graph) -> torch.Tensor:
+        """The graph half of GraphModel.py:150-211 -- GATConv x2, node MLP, unbatch / pad to ``max_node`` slots, slot
+        BatchNorms, fc_gat | fc_bbox, the eight Rs_GCN blocks -> fp32 [B * max_node, 512].  It needs nothing from the
+        image / text branches, so a caller may run it on another CUDA stream while they compute (``MVulD.forward``)."""
         if self.training:
             raise RuntimeError("mvuld_b200 fusion model implements the eval-mode forward: call model.eval()")
         if not isinstance(g, Graph):
             from .graph import from_dgl
             g = from_dgl(g)
-        if not img_embedding.is_cuda:
-            raise RuntimeError("mvuld_b200 fusion model takes CUDA tensors (no CPU fallback)")
         if self._plan is None:
             self.prepare()
         p = self._plan
         dev = p["dev"]
-        B = img_embedding.shape[0]
-        N = g.num_nodes()
-        if g.batch_size != B:
-            raise ValueError(f"graph batch size {g.batch_size} != embedding batch size {B}")
+        if g.device.type != "cuda":
+            raise RuntimeError("mvuld_b200 fusion model takes CUDA tensors (no CPU fallback)")
+        B, N = g.batch_size, g.num_nodes()
         e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
         bf, f32 = torch.bfloat16, torch.float32
-
-        # image / text projections: ELU(fc(bn(.)))  (GraphModel.py:153-159)
-        img_b, txt_b = e((B, 1024), bf), e((B, 768), bf)
-        _lib.call("mvuld_f32_to_bf16", img_embedding.float().contiguous(), img_b, B * 1024)
-        _lib.call("mvuld_f32_to_bf16", func_text_embedding.float().contiguous(), txt_b, B * 768)
-        ximg, xtxt = e((B, 512), f32), e((B, 512), f32)
-        _lib.gemm(img_b, p["img"][0], bias=p["img"][1], act=_lib.ACT_ELU, out_f32=ximg)
-        _lib.gemm(txt_b, p["txt"][0], bias=p["txt"][1], act=_lib.ACT_ELU, out_f32=xtxt)
 
         # graph branch (GraphModel.py:163-177)
         indptr, idx_src, _ = g.in_csr()
@@ -243,17 +234,50 @@ class Multi_DefectModel_new_GCN(nn.Module):
             _lib.gemm(z3, gc["wcat3"], bias=gc["bcat"], out_f32=tpg)
             _lib.call("mvuld_rs_gcn_affinity_f32", tpg, y3, None, B, n, 512)
             _lib.gemm(y3, gc["ww3"], bias=gc["wb"], res=z32, out_f32=z32)
+        self._pending.append((zero_deg, g))
+        return z32
 
-        # l2norm(dim=1) + mean + concat + BN + final_fc (GraphModel.py:200-209)
+    @torch.no_grad()
+    def head(self, z32: torch.Tensor, img_embedding: torch.Tensor, func_text_embedding: torch.Tensor) -> torch.Tensor:
+        """The rest of GraphModel.py:150-211: image / text projections (:153-159), l2norm over the slot axis + mean +
+        concat + BatchNorm + final_fc (:200-209) -> logits [B, num_classes]."""
+        if not img_embedding.is_cuda:
+            raise RuntimeError("mvuld_b200 fusion model takes CUDA tensors (no CPU fallback)")
+        if self._plan is None:
+            self.prepare()
+        p = self._plan
+        dev = p["dev"]
+        B, n = img_embedding.shape[0], self.max_node
+        if z32.shape[0] != B * n:
+            raise ValueError(f"graph batch size {z32.shape[0] // n} != embedding batch size {B}")
+        e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+        bf, f32 = torch.bfloat16, torch.float32
+        img_b, txt_b = e((B, 1024), bf), e((B, 768), bf)
+        _lib.call("mvuld_f32_to_bf16", img_embedding.float().contiguous(), img_b, B * 1024)
+        _lib.call("mvuld_f32_to_bf16", func_text_embedding.float().contiguous(), txt_b, B * 768)
+        ximg, xtxt = e((B, 512), f32), e((B, 512), f32)
+        _lib.gemm(img_b, p["img"][0], bias=p["img"][1], act=_lib.ACT_ELU, out_f32=ximg)
+        _lib.gemm(txt_b, p["txt"][0], bias=p["txt"][1], act=_lib.ACT_ELU, out_f32=xtxt)
         logits = e((B, self.num_classes), f32)
         _lib.call("mvuld_fusion_head", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
                   self.num_classes)
-        self._pending.append((zero_deg, g))
         if not self.defer_checks:
             self.raise_if_invalid()
         elif len(self._pending) > 64:
             self.raise_if_invalid()                      # bound the backlog of a caller that never asks
         return logits
+
+    @torch.no_grad()
+    def forward(self, g: Graph, img_embedding: torch.Tensor, func_text_embedding: torch.Tensor) -> torch.Tensor:
+        """GraphModel.py:150-211."""
+        if not img_embedding.is_cuda:
+            raise RuntimeError("mvuld_b200 fusion model takes CUDA tensors (no CPU fallback)")
+        if not isinstance(g, Graph):
+            from .graph import from_dgl
+            g = from_dgl(g)
+        if g.batch_size != img_embedding.shape[0]:
+            raise ValueError(f"graph batch size {g.batch_size} != embedding batch size {img_embedding.shape[0]}")
+        return self.head(self.graph_features(g), img_embedding, func_text_embedding)
 
 
 class GatedGraphConv(nn.Module):

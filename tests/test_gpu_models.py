@@ -161,6 +161,22 @@ def test_composed_forward_matches_oracle():
     assert torch.equal(out.cpu().argmax(1), ref.argmax(1))
 
 
+def test_graph_branch_on_a_side_stream_gives_identical_logits():
+    """MVulD.overlap_graph_branch: graph_features on a second stream + head == the single-stream forward."""
+    torch.manual_seed(cases.SEED)
+    model = mv.MVulD(mv.default_config(), cases.roberta_small_config()).eval()
+    synth.randomize_for_parity(model, seed=777)
+    model = model.to(DEV)
+    B = 3
+    img, ids = synth.images(B, 448, seed=5).to(DEV), synth.token_ids(B, 512, vocab=1000, seed=5).to(DEV)
+    g = synth.cpg_batch(B, seed=5).to(DEV)
+    want = model(img, ids, g)
+    model.overlap_graph_branch = True
+    for _ in range(3):
+        got = model(img, ids, g)
+        assert torch.equal(got, want)
+
+
 def test_device_prefetcher_yields_identical_batches_and_results():
     """mvuld_b200.prefetch: batches staged on the copy stream give the same logits as synchronous staging."""
     from mvuld_b200.prefetch import DevicePrefetcher, ResultSink
