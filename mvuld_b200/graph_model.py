@@ -280,6 +280,131 @@ class Multi_DefectModel_new_GCN(nn.Module):
         return self.head(self.graph_features(g), img_embedding, func_text_embedding)
 
 
+class Multi_DefectModel(nn.Module):
+    """The RQ3 "GAT" ablation (mvuld/models/GraphModel.py:214-304, commented alternative at main_bigvul.py:141): the
+    same GATConv x2 + node MLP as the live model, then ``dgl.mean_nodes`` over each graph, ``ELU(hfc(hbn(.)))``, concat
+    with the image / text projections, ``final_fc(final_fc_bn(.))`` -- no slot padding, no Rs_GCN.  Same constructor,
+    ``forward`` signature and state-dict keys as the reference class; eval-mode semantics (BatchNorms folded)."""
+
+    def __init__(self, config, pretrained=True, attention=True):
+        super().__init__()
+        self.num_features = 1024
+        self.config = config
+        self.num_classes = config.MODEL.NUM_CLASSES
+        hfeat, embfeat, numheads = 512, 768, 4
+        self.gat = GATConv(embfeat, hfeat, numheads, feat_drop=0.1)
+        self.gat2 = GATConv(hfeat * numheads, hfeat, numheads, feat_drop=0.1)
+        self.fc = nn.Linear(hfeat * numheads, hfeat)
+        self.fconly = nn.Linear(embfeat, hfeat)
+        self.hidden = nn.ModuleList([nn.Linear(hfeat, hfeat) for _ in range(8)])
+        self.bn_text = nn.BatchNorm1d(embfeat)
+        self.fc_text = nn.Linear(embfeat, hfeat)
+        self.swinbn = nn.BatchNorm1d(self.num_features)
+        self.swinfc = nn.Linear(self.num_features, hfeat)
+        self.hbn = nn.BatchNorm1d(hfeat)
+        self.hfc = nn.Linear(hfeat, hfeat)
+        self.final_fc = nn.Linear(hfeat * 3, self.num_classes)
+        self.final_fc_bn = nn.BatchNorm1d(hfeat * 3)
+        self._plan = None
+
+    def invalidate(self):
+        self._plan = None
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def prepare(self):
+        dev = self.fc.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("mvuld_b200 fusion model runs on CUDA only (no CPU fallback)")
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        b16 = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+        p = dict(dev=dev)
+        for key, bn, lin in (("img", self.swinbn, self.swinfc), ("txt", self.bn_text, self.fc_text),
+                             ("h", self.hbn, self.hfc)):
+            w, b = _fold_bn_into_linear(bn, lin)
+            p[key] = (b16(w), f32(b))
+        for name in ("gat", "gat2"):
+            m = getattr(self, name)
+            p[name] = dict(w=b16(m.fc.weight), al=f32(m.attn_l.view(-1)), ar=f32(m.attn_r.view(-1)), bias=f32(m.bias),
+                           H=m._heads, F=m._out, slope=float(m.negative_slope))
+        p["fc"] = (b16(self.fc.weight), f32(self.fc.bias))
+        p["hidden"] = [(b16(l.weight), f32(l.bias)) for l in self.hidden]
+        scale, shift = _bn_affine(self.final_fc_bn)
+        wf = self.final_fc.weight.detach().float()
+        p["final"] = (f32(wf * scale[None, :]), f32(self.final_fc.bias.detach().float() + wf @ shift))
+        self._plan = p
+        return self
+
+    @torch.no_grad()
+    def forward(self, g: Graph, img_embedding: torch.Tensor, func_text_embedding: torch.Tensor) -> torch.Tensor:
+        """GraphModel.py:263-304."""
+        if self.training:
+            raise RuntimeError("mvuld_b200 fusion model implements the eval-mode forward: call model.eval()")
+        if not isinstance(g, Graph):
+            from .graph import from_dgl
+            g = from_dgl(g)
+        if not img_embedding.is_cuda:
+            raise RuntimeError("mvuld_b200 fusion model takes CUDA tensors (no CPU fallback)")
+        if self._plan is None:
+            self.prepare()
+        p = self._plan
+        dev = p["dev"]
+        B, N = img_embedding.shape[0], g.num_nodes()
+        if g.batch_size != B:
+            raise ValueError(f"graph batch size {g.batch_size} != embedding batch size {B}")
+        e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+        bf, f32 = torch.bfloat16, torch.float32
+        feats = e((B, 1536), f32)                                   # cat(x, h_feature, text) (GraphModel.py:300)
+        img_b, txt_b = e((B, 1024), bf), e((B, 768), bf)
+        _lib.call("mvuld_f32_to_bf16", img_embedding.float().contiguous(), img_b, B * 1024)
+        _lib.call("mvuld_f32_to_bf16", func_text_embedding.float().contiguous(), txt_b, B * 768)
+        _lib.gemm(img_b, p["img"][0], bias=p["img"][1], act=_lib.ACT_ELU, out_f32=feats[:, 0:512])
+        _lib.gemm(txt_b, p["txt"][0], bias=p["txt"][1], act=_lib.ACT_ELU, out_f32=feats[:, 1024:1536])
+        indptr, idx_src, _ = g.in_csr()
+        h_in = g.ndata["_UNIX_NODE_EMB"]
+        hb = e((N, h_in.shape[1]), bf)
+        _lib.call("mvuld_f32_to_bf16", h_in.float().contiguous(), hb, N * h_in.shape[1])
+        zero_deg = torch.zeros(1, device=dev, dtype=torch.int32)
+        for name in ("gat", "gat2"):
+            gp = p[name]
+            H, F = gp["H"], gp["F"]
+            z = e((N, H * F), bf)
+            _lib.gemm(hb, gp["w"], out_bf16=z)
+            el, er = e((N, H), f32), e((N, H), f32)
+            _lib.call("mvuld_gat_scores", z, gp["al"], gp["ar"], el, er, N, H, F)
+            hb = e((N, H * F), bf)
+            _lib.call("mvuld_gat_aggregate", z, el, er, indptr, idx_src, gp["bias"], hb, N, H, F, gp["slope"], zero_deg)
+        a, a2 = e((N, 512), bf), e((N, 512), bf)
+        _lib.gemm(hb, p["fc"][0], bias=p["fc"][1], act=_lib.ACT_ELU, out_bf16=a)
+        a32 = e((N, 512), f32)
+        for i, (w, b) in enumerate(p["hidden"]):
+            last = i == len(p["hidden"]) - 1
+            _lib.gemm(a, w, bias=b, act=_lib.ACT_ELU, out_bf16=a2, out_f32=a32 if last else None)
+            a, a2 = a2, a
+        # dgl.mean_nodes (GraphModel.py:296-298): per-graph mean over its node rows
+        bnn = g.batch_num_nodes().to(torch.int32)
+        start = (torch.cumsum(bnn, 0, dtype=torch.int32) - bnn).to(dev)
+        hmean = e((B, 512), f32)
+        _lib.call("mvuld_seq_segment_mean", a32, start, bnn.to(dev), None, hmean, B, 512)
+        hmean_b = e((B, 512), bf)
+        _lib.call("mvuld_f32_to_bf16", hmean, hmean_b, B * 512)
+        _lib.gemm(hmean_b, p["h"][0], bias=p["h"][1], act=_lib.ACT_ELU, out_f32=feats[:, 512:1024])
+        logits = e((B, self.num_classes), f32)
+        _lib.call("mvuld_linear_small", feats, p["final"][0], p["final"][1], logits, None, B, self.num_classes, 1536)
+        if int(zero_deg.item()) != 0:
+            raise RuntimeError("There are 0-in-degree nodes in the graph (GATConv allow_zero_in_degree=False); "
+                               "add self-loops with mvuld_b200.graph.add_self_loop")
+        g.check_status()
+        return logits
+
+
 class GatedGraphConv(nn.Module):
     """DGL ``GatedGraphConv`` parameters: linears[t] = Linear(out, out), gru = GRUCell(out, out)."""
 

@@ -81,6 +81,26 @@ def fusion_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_
 
 
 @torch.no_grad()
+def gat_variant_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
+                        func_text_embedding: torch.Tensor) -> torch.Tensor:
+    """GraphModel.py:263-304 (``Multi_DefectModel``, the RQ3 GAT ablation): GATConv x2 + node MLP, dgl.mean_nodes,
+    ELU(hfc(hbn(.))), concat, final_fc(final_fc_bn(.)) -> logits [B, 2].  Eval mode."""
+    lin = lambda name, t: F.linear(t, sd[name + ".weight"].float(), sd[name + ".bias"].float())
+    x = F.elu(lin("swinfc", _bn_eval(sd, "swinbn.", img_embedding.float(), 1)))
+    t = F.elu(lin("fc_text", _bn_eval(sd, "bn_text.", func_text_embedding.float(), 1)))
+    h = batch.ndata["_UNIX_NODE_EMB"].float()
+    h = dgl_ops.gat_conv(sd, "gat.", batch.src, batch.dst, h, 4, 512).reshape(h.shape[0], -1)
+    h = dgl_ops.gat_conv(sd, "gat2.", batch.src, batch.dst, h, 4, 512).reshape(h.shape[0], -1)
+    h = F.elu(lin("fc", h))
+    for i in range(8):
+        h = F.elu(lin(f"hidden.{i}", h))
+    hf = dgl_ops.mean_nodes(h, batch.batch_num_nodes)
+    hf = F.elu(lin("hfc", _bn_eval(sd, "hbn.", hf, 1)))
+    feats = torch.cat([x, hf, t], 1)
+    return lin("final_fc", _bn_eval(sd, "final_fc_bn.", feats, 1))
+
+
+@torch.no_grad()
 def ggnn_sum_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", out_dim: int, n_steps: int,
                      n_etypes: int):
     """reveal/ggnn/model.py:20-31 -> (prob [B], logit [B,1], h_i_sum [B,out], node states [N,out])."""

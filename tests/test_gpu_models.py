@@ -99,6 +99,22 @@ def test_fusion_matches_oracle(golden):
     assert torch.equal(logits.cpu().argmax(1), ref.argmax(1))
 
 
+def test_gat_ablation_variant_matches_oracle():
+    """``Multi_DefectModel`` (GraphModel.py:214-304), the dgl.mean_nodes readout variant."""
+    torch.manual_seed(cases.SEED)
+    m = mv.Multi_DefectModel(mv.default_config()).eval()
+    synth.randomize_for_parity(m, seed=cases.SEED)
+    g = synth.cpg_batch(5, seed=cases.SEED + 11)
+    gen = torch.Generator().manual_seed(2)
+    img, txt = torch.randn(5, 1024, generator=gen), torch.randn(5, 768, generator=gen)
+    ref = ofusion.gat_variant_forward(m.state_dict(), cases.to_host_batch(g), img, txt)
+    out = m.to(DEV)(g.to(DEV), img.to(DEV), txt.to(DEV))
+    assert logits_close(out, ref, 1e-2), (out.cpu(), ref)
+    assert torch.equal(out.cpu().argmax(1), ref.argmax(1))
+    keys = set(m.state_dict())
+    assert {"gat.attn_l", "gat2.fc.weight", "hbn.running_mean", "hfc.weight", "final_fc_bn.weight", "fconly.bias"} <= keys
+
+
 def test_fusion_rejects_zero_in_degree():
     model = cases.make_fusion().to(DEV)
     g = mv.graph.graph((torch.tensor([0, 1]), torch.tensor([1, 2])), num_nodes=3)      # node 0 has no in-edge
