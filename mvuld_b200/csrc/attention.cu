@@ -16,6 +16,11 @@
 // group's barriers so a ready P is consumed at once); warp 3 QK^T issuer of both groups; warps 4-7 / 8-11 two softmax
 // warpgroups (thread == query row == TMEM lane, no cross-thread reductions) that work on alternate query tiles.
 // TMEM columns of group g (256 each): S [0, KT) | P buffers [KT, KT + NPB * KT/2) | O [256 - HD, 256).
+// Split remainder tile (ws = 28: 784 tokens = 6 full query tiles + 16 rows): a thread-per-row sweep would spend a whole
+// tile-time on 16 rows, so the 16 queries are REPLICATED over the 8 16-lane groups of the tile and lane group u only
+// exponentiates key tile u (P = 0 elsewhere): O'[16u + q] accumulates key tile u's contribution alone, and the 8 partial
+// (O', l) pairs of a query are summed through shared memory.  Exact under the constant softmax reference (all partials
+// share it), so only heads on that path take it; a warp runs 2 sweeps instead of 7.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -79,6 +84,7 @@ struct AttnParams {
   const int* tile_lo;
   const int* tile_hi;
   void* out;              // bf16 [tokens, C]
+  int no_split;           // debug: disable the split remainder tile (MVULD_ATT_NOSPLIT)
 };
 
 template <int HD>
@@ -90,10 +96,13 @@ struct AttnLayout {
   static constexpr int Q_BYTES = ATT_BM * ROW_BYTES;
 };
 
-__host__ __device__ constexpr int att_smem_bytes(int HD, int KT, int nkt, int table_floats) {
+constexpr int ATT_SPLIT_ROWS = 16;                             // query rows of a split remainder tile
+constexpr int ATT_MERGE_LD = 33;                               // padded row of the merge buffer (floats)
+constexpr int ATT_MERGE_BYTES = ATT_BM * (ATT_MERGE_LD + 1) * 4;   // partial O' [128][33] + partial l [128]
+__host__ __device__ constexpr int att_smem_bytes(int HD, int KT, int nkt, int table_floats, int merge_bytes = 0) {
   return 2 * nkt * KT * HD * 2      // K, V
          + 2 * ATT_BM * HD * 2      // Q x2
-         + ((table_floats * 4 + 1023) / 1024) * 1024 + 512 /*barriers*/ + 1024 /*align*/;
+         + ((table_floats * 4 + 1023) / 1024) * 1024 + 512 /*barriers*/ + merge_bytes + 1024 /*align*/;
 }
 
 // Row stride of the bias table in shared memory.  Lane l of a warp owns query slot i0 + l, i.e. (hi, wi) walks a
@@ -169,7 +178,7 @@ __device__ __forceinline__ void tmem_st8p(uint32_t taddr, const uint32_t* r) {
 template <int MODE, int HD, int WS, int KT, bool QK_FP16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, AttnParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ16, AttnParams p) {
   using L = AttnLayout<HD>;
   constexpr int SIDE = 2 * WS - 1;
   constexpr int TSTRIDE = att_tab_stride(WS);
@@ -181,6 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int PW = KT / 2;                         // 32-bit TMEM columns of one P tile (two bf16 per cell)
   constexpr int NPB = (KT + 2 * PW + HD <= 256) ? 2 : 1;                // P buffers per group
   constexpr int COL_P = KT, COL_O = 256 - HD;
+  constexpr bool CAN_SPLIT = (MODE == MODE_SWIN) && HD == 32 && WS * WS % ATT_BM == ATT_SPLIT_ROWS;
   static_assert(MODE != MODE_SWIN || KT % WS == 0, "kv tile must hold whole window rows");
   static_assert(KT % 16 == 0 && KT <= 128, "kv tile");
   static_assert(KT + NPB * PW + HD <= 256, "TMEM budget of one softmax group");
@@ -215,6 +225,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   };
 
+  // split remainder tile (see the header): last query tile holds <= 16 rows, at most 8 key tiles, constant-reference head
+  bool split = false;
+  if (CAN_SPLIT && p.q_norm != nullptr && !p.no_split) {
+    const int rem = p.Nq - (nq - 1) * ATT_BM;
+    split = nq >= 2 && rem > 0 && rem <= ATT_SPLIT_ROWS && nkt <= ATT_BM / ATT_SPLIT_ROWS &&
+            (2.0f * __ldg(p.q_norm + head) + __ldg(p.bias_max + head) <= 100.0f);
+  }
+
   uint8_t* sK = smem;
   uint8_t* sV = sK + nkt_all * KT * L::ROW_BYTES;
   uint8_t* sQ = sV + nkt_all * KT * L::ROW_BYTES;
@@ -231,6 +249,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* pv_done = p_full + 4;             // [2][2]
   uint64_t* turn = pv_done + 4;               // [2]  exponential sweeps of the two groups alternate (ping-pong)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
+  float* sMerge = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [128][33] O', then [128] l
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -242,6 +261,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
+    if (CAN_SPLIT) prefetch_tmap(&tmQ16);
     for (int i = 0; i < ATT_MAX_KT; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
@@ -281,7 +301,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) {
         auto load_q = [&](int g, int t) {
           mbar_arrive_expect_tx(&q_full[g], L::Q_BYTES);
-          tma_load_3d(sQ + g * L::Q_BYTES, &tmQ, &q_full[g], 0, t * ATT_BM, bh);
+          if (CAN_SPLIT && split && t == nq - 1) {
+            // the 16 remainder queries, once per 16-lane group (1 KB pieces keep the swizzle phase of a 128-row box)
+            for (int u = 0; u < ATT_BM / ATT_SPLIT_ROWS; ++u)
+              tma_load_3d(sQ + g * L::Q_BYTES + u * ATT_SPLIT_ROWS * L::ROW_BYTES, &tmQ16, &q_full[g], 0, t * ATT_BM, bh);
+          } else {
+            tma_load_3d(sQ + g * L::Q_BYTES, &tmQ, &q_full[g], 0, t * ATT_BM, bh);
+          }
         };
         load_q(0, 0);
         for (int j = 0; j < nkt; ++j) {
@@ -421,7 +447,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     auto wait_pv = [&](uint32_t m) { mbar_wait(&pv_done[2 * g + (m % NPB)], (m / NPB) & 1, 31); };
 
     for (int t = g; t < nq; t += 2) {
-      const int i = t * ATT_BM + r;                          // slot inside the window / position in the sequence
+      // split remainder tile: lane group u = r / 16 holds query t * 128 + r % 16 and owns key tile u
+      const bool split_t = CAN_SPLIT && split && (t == nq - 1);
+      const int i = t * ATT_BM + (split_t ? (r & (ATT_SPLIT_ROWS - 1)) : r);   // slot inside the window / position in the sequence
       int hi = 0, wi = 0;
       if (MODE == MODE_SWIN) {
         hi = i / WS;
@@ -447,6 +475,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
       for (int j = jlo; j < jhi; ++j, ++n) {
         const int ncols = min(KT, kv_valid - j * KT);        // valid kv columns in this tile
+        if (CAN_SPLIT && split_t && (j >> 1) != quarter) {
+          // split tile, key tile owned by another warp's lanes: keep the S / P hand-shakes going and contribute P = 0
+          mbar_wait(&s_full[g], ph_s, 30);
+          ph_s ^= 1;
+          mbar_arrive(&s_free[g]);
+          if (n >= (uint32_t)NPB) wait_pv(n - NPB);
+          tc_fence_after();
+          const uint32_t tPz = tS + COL_P + (n % NPB) * PW;
+          uint32_t zero[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) zero[q] = 0u;
+          constexpr int Z32 = (PW / 32) * 32, Z16 = Z32 + ((PW - Z32) / 16) * 16;
+#pragma unroll
+          for (int c0 = 0; c0 < Z32; c0 += 32) tmem_st32p(tPz + c0, zero);
+          if (Z16 > Z32) tmem_st16p(tPz + Z32, zero);
+          if (PW > Z16) tmem_st8p(tPz + Z16, zero);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[2 * g + (n % NPB)]);
+          continue;
+        }
 
         // per-segment additive constants (shift mask) and bias-table row bases
         float cseg[NSEG];
@@ -486,6 +535,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (ncols < KT) {
 #pragma unroll
           for (int c = 0; c < KT; ++c) sv[c] = (c < ncols) ? sv[c] : 0xff800000u;   // -inf
+        }
+        if (CAN_SPLIT && split_t && (r >> 4) != j) {         // the other lane group of this warp owns key tile j
+#pragma unroll
+          for (int c = 0; c < KT; ++c) sv[c] = 0xff800000u;
         }
         if (MODE == MODE_SEQ && p.seg_lo != nullptr) {
           // block-diagonal mask of packed sequences: keys outside [k_lo, k_hi) of this row are -inf
@@ -612,7 +665,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float l0, l1, l2, l3;
       unpack2f(ls[0], l0, l1);
       unpack2f(ls[1], l2, l3);
-      const float lsum = (l0 + l1) + (l2 + l3);
+      float lsum = (l0 + l1) + (l2 + l3);
+      if (CAN_SPLIT && split_t) {
+        // merge the 8 key-tile partials of each query (same softmax reference: plain sums) through shared memory
+        static_assert(!CAN_SPLIT || HD == 32, "split merge assumes one 32-column O load");
+        uint32_t o[32];
+        tmem_ld32(tO, o);
+        tmem_ld_wait();
+        float* mrow = sMerge + r * ATT_MERGE_LD;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) mrow[q] = __uint_as_float(o[q]);
+        sMerge[ATT_BM * ATT_MERGE_LD + r] = lsum;
+        named_bar_sync(1 + g, 128);
+        const int qq = r & (ATT_SPLIT_ROWS - 1), cg = (r >> 4) * 4;     // this thread: query qq, O columns cg .. cg + 3
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        lsum = 0.f;
+#pragma unroll
+        for (int u = 0; u < ATT_BM / ATT_SPLIT_ROWS; ++u) {
+          const float* src = sMerge + (u * ATT_SPLIT_ROWS + qq) * ATT_MERGE_LD + cg;
+          a0 += src[0];
+          a1 += src[1];
+          a2 += src[2];
+          a3 += src[3];
+          lsum += sMerge[ATT_BM * ATT_MERGE_LD + u * ATT_SPLIT_ROWS + qq];
+        }
+        const float invs = lsum > 0.f ? 1.0f / lsum : 0.f;
+        if (i < p.Nq) {
+          const int hl = i / WS, wl = i - hl * WS;
+          int hh = wr * WS + hl + p.shift;
+          if (hh >= p.H) hh -= p.H;
+          int ww = wc * WS + wl + p.shift;
+          if (ww >= p.W) ww -= p.W;
+          const int b = bwin / ((p.H / WS) * nWw);
+          const size_t orow_s = (size_t)b * p.H * p.W + (size_t)hh * p.W + ww;
+          uint2 w2;
+          w2.x = pack_bf16x2(a0 * invs, a1 * invs);
+          w2.y = pack_bf16x2(a2 * invs, a3 * invs);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow_s * p.C + head * HD + cg) = w2;
+        }
+        tc_fence_before();
+        mbar_arrive(&o_free[g]);
+        continue;
+      }
       const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
       size_t orow;
       if (MODE == MODE_SWIN) {
@@ -660,9 +754,9 @@ static int launch_attn(const void* q, const void* k, const void* v, int n_bh, co
   const int nkt = (p.Nkv + KT - 1) / KT;
   MV_CHECK_ARG(nkt <= ATT_MAX_KT, "attention: %d kv tiles exceed the resident maximum %d", nkt, ATT_MAX_KT);
   constexpr int TBL = (MODE == MODE_SWIN) ? (2 * WS - 1) * att_tab_stride(WS) : 0;
-  const int smem = att_smem_bytes(HD, KT, nkt, TBL);
+  const int smem = att_smem_bytes(HD, KT, nkt, TBL, (MODE == MODE_SWIN) ? ATT_MERGE_BYTES : 0);
   MV_CHECK_ARG(smem <= 232448, "attention: %d B shared memory needed, 232448 available", smem);
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmQ16;
   uint64_t dq[3] = {(uint64_t)HD, (uint64_t)p.Nq, (uint64_t)n_bh};
   uint64_t sq[2] = {(uint64_t)HD * 2, (uint64_t)p.Nq * HD * 2};
   uint32_t bq[3] = {(uint32_t)HD, ATT_BM, 1};
@@ -675,9 +769,12 @@ static int launch_attn(const void* q, const void* k, const void* v, int n_bh, co
   if (rc) return rc;
   rc = make_tmap_16b(&tmV, v, 3, dk, sk, bk, L::SWZ);
   if (rc) return rc;
+  uint32_t bq16[3] = {(uint32_t)HD, ATT_SPLIT_ROWS, 1};      // 16-row Q box of the split remainder tile
+  rc = make_tmap_16b(&tmQ16, q, 3, dq, sq, bq16, L::SWZ);
+  if (rc) return rc;
   auto kern = attn_fwd_kernel<MODE, HD, WS, KT, QK_FP16>;
   MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<n_bh, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<n_bh, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmQ16, p);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -785,6 +882,7 @@ extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const v
   p.H = H; p.W = W; p.shift = shift; p.C = C;
   p.kv_len = nullptr;
   p.out = out;
+  p.no_split = getenv("MVULD_ATT_NOSPLIT") != nullptr;
   const int n_bh = B * (H / ws) * (W / ws) * nH;
   switch (ws) {
     case 28: return launch_attn<MODE_SWIN, 32, 28, 112, true>(q, k, v, n_bh, p, stream);
