@@ -66,8 +66,47 @@ def rep(src, dst):
     print(open(dst).read())
 
 
+def table(src, dst):
+    """One row per distinct kernel of a multi-kernel `ncu --set full` capture (first instance of each)."""
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = lambda r, k: r[hdr.index(k)] if k in hdr else ""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    def nbytes(r, k):
+        if k not in hdr or not r[hdr.index(k)]:
+            return 0.0
+        return float(r[hdr.index(k)].replace(",", "")) * scale.get(units[hdr.index(k)], 1.0)
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    seen = OrderedDict()
+    for r in data:
+        name = short(col(r, "Kernel Name"))
+        if name in seen:
+            continue
+        us = float(col(r, "gpu__time_duration.sum").replace(",", "")) * tscale.get(units[hdr.index("gpu__time_duration.sum")], 1.0)
+        rd, wr = nbytes(r, "dram__bytes_read.sum"), nbytes(r, "dram__bytes_write.sum")
+        seen[name] = (us, rd, wr, col(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+                      col(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                      col(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+                      col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                      col(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                      col(r, "launch__registers_per_thread"), col(r, "Grid Size"), col(r, "Block Size"))
+    with open(dst, "w") as fh:
+        fh.write(f"# ncu --set full, one launch of every remaining kernel: {src}\n\n")
+        fh.write("DRAM GB/s = (dram read + write) / duration of that launch (cold-cache, serialised under ncu).\n\n")
+        fh.write("| kernel | us | DRAM read MB | DRAM write MB | DRAM GB/s | dram % | tensor % | sm % | issue % | warps % | regs | grid | block |\n")
+        fh.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---|\n")
+        f2 = lambda x: f"{float(x):.1f}" if x not in ("", "n/a") else ""
+        for name, (us, rd, wr, dp, tp, sp, ip, wp, regs, grid, block) in seen.items():
+            fh.write(f"| `{name}` | {us:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {(rd + wr) / us / 1e3:.0f} | {f2(dp)} | {f2(tp)} | "
+                     f"{f2(sp)} | {f2(ip)} | {f2(wp)} | {regs} | {grid} | {block} |\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "table":
+        table(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else 0)
     else:
         rep(sys.argv[2], sys.argv[3])
