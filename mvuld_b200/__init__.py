@@ -9,9 +9,13 @@ from .swin_transformer_v2 import SwinTransformerV2                  # noqa: F401
 from .unixcoder import MyUniXcoder, RobertaEncoder, build_MyUniXcoder, roberta_base_config   # noqa: F401
 from .graph_model import (Multi_DefectModel_new_GCN, Multi_DefectModel, Rs_GCN, GATConv, GatedGraphConv,  # noqa: F401
                           GGNNSum)
+from .fusion_variants import (Multi_DefectModel_noGraph, Multi_DefectModel_000, Multi_DefectModel_001,   # noqa: F401
+                              Multi_DefectModel_100, Multi_DefectModel_NOGAT2, ABLATIONS)
 from .mvuld import MVulD                                            # noqa: F401
 from . import graph, checkpoint                                     # noqa: F401
 
 __all__ = ["get_config", "default_config", "CfgNode", "build_model", "SwinTransformerV2", "MyUniXcoder",
            "RobertaEncoder", "build_MyUniXcoder", "roberta_base_config", "Multi_DefectModel_new_GCN", "Rs_GCN",
-           "GATConv", "GatedGraphConv", "GGNNSum", "MVulD", "graph", "Multi_DefectModel"]
+           "GATConv", "GatedGraphConv", "GGNNSum", "MVulD", "graph", "Multi_DefectModel",
+           "Multi_DefectModel_noGraph", "Multi_DefectModel_000", "Multi_DefectModel_001", "Multi_DefectModel_100",
+           "Multi_DefectModel_NOGAT2", "ABLATIONS"]

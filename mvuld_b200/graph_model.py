@@ -69,6 +69,45 @@ def _fold_bn_into_linear(bn: nn.BatchNorm1d, lin: nn.Linear):
     return w * scale[None, :], lin.bias.detach().float() + w @ shift
 
 
+@torch.no_grad()
+def plan_rs_gcn_chain(blocks, dev):
+    """Packed weights of a chain of Rs_GCN blocks: (theta | phi | g) as one projection, the BatchNorm after the 1x1
+    convolution W folded on its output side, both as bf16x3 split weights (W_hi | W_hi | W_lo) -- fp32-class 1x1
+    convolutions, see mvuld_rs_gcn_affinity_f32."""
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    plan = []
+    for m in blocks:
+        wcat = torch.cat([m.theta.weight[:, :, 0], m.phi.weight[:, :, 0], m.g.weight[:, :, 0]], 0)
+        bcat = torch.cat([m.theta.bias, m.phi.bias, m.g.bias], 0)
+        scale, shift = _bn_affine(m.W[1])
+        ww = m.W[0].weight.detach().float()[:, :, 0] * scale[:, None]
+        wb = m.W[0].bias.detach().float() * scale + shift
+        split = []
+        for w32 in (f32(wcat), f32(ww)):
+            w3 = torch.empty(w32.shape[0], 3 * w32.shape[1], device=dev, dtype=torch.bfloat16)
+            _lib.call("mvuld_split3_bf16", w32, w32.shape[1], w3, w32.shape[0], w32.shape[1], 1)
+            split.append(w3)
+        plan.append(dict(wcat3=split[0], bcat=f32(bcat), ww3=split[1], wb=f32(wb)))
+    return plan
+
+
+@torch.no_grad()
+def run_rs_gcn_chain(plan, z32: torch.Tensor, B: int, n: int) -> torch.Tensor:
+    """Rs_GCN.py:52-73 applied block after block, in place on the token-major fp32 [B*n, 512] tensor.  The residual
+    stream stays fp32 and every product uses bf16x3 split operands: no softmax bounds the affinity and a BatchNorm
+    follows, so plain bf16 operands cost 1-2 % per block (measured in train mode)."""
+    dev = z32.device
+    z3 = torch.empty((B * n, 1536), device=dev, dtype=torch.bfloat16)
+    y3 = torch.empty((B * n, 1536), device=dev, dtype=torch.bfloat16)
+    tpg = torch.empty((B * n, 1536), device=dev, dtype=torch.float32)
+    for gc in plan:
+        _lib.call("mvuld_split3_bf16", z32, 512, z3, B * n, 512, 0)
+        _lib.gemm(z3, gc["wcat3"], bias=gc["bcat"], out_f32=tpg)
+        _lib.call("mvuld_rs_gcn_affinity_f32", tpg, y3, None, B, n, 512)
+        _lib.gemm(y3, gc["ww3"], bias=gc["wb"], res=z32, out_f32=z32)
+    return z32
+
+
 class Multi_DefectModel_new_GCN(nn.Module):
     def __init__(self, config, pretrained=True, attention=True):
         super().__init__()
@@ -149,21 +188,7 @@ class Multi_DefectModel_new_GCN(nn.Module):
         s, t = _bn_affine(self.bn_bbox)
         p["bn_bbox"] = (f32(s), f32(t))
         p["fc_bbox"] = (f32(self.fc_bbox.weight), f32(self.fc_bbox.bias))
-        p["gcn"] = []
-        for k in range(1, 9):
-            m = getattr(self, f"Rs_GCN_{k}")
-            wcat = torch.cat([m.theta.weight[:, :, 0], m.phi.weight[:, :, 0], m.g.weight[:, :, 0]], 0)
-            bcat = torch.cat([m.theta.bias, m.phi.bias, m.g.bias], 0)
-            scale, shift = _bn_affine(m.W[1])                      # BN after the 1x1 conv: fold on the output side
-            ww = m.W[0].weight.detach().float()[:, :, 0] * scale[:, None]
-            wb = m.W[0].bias.detach().float() * scale + shift
-            # bf16x3 split weights (W_hi | W_hi | W_lo): fp32-class 1x1 convolutions (see mvuld_rs_gcn_affinity_f32)
-            split = []
-            for w32 in (f32(wcat), f32(ww)):
-                w3 = torch.empty(w32.shape[0], 3 * w32.shape[1], device=dev, dtype=torch.bfloat16)
-                _lib.call("mvuld_split3_bf16", w32, w32.shape[1], w3, w32.shape[0], w32.shape[1], 1)
-                split.append(w3)
-            p["gcn"].append(dict(wcat3=split[0], bcat=f32(bcat), ww3=split[1], wb=f32(wb)))
+        p["gcn"] = plan_rs_gcn_chain([getattr(self, f"Rs_GCN_{k}") for k in range(1, 9)], dev)
         scale, shift = _bn_affine(self.final_fc_bn)
         wf = self.final_fc.weight.detach().float()
         p["final"] = (f32(wf * scale[None, :]), f32(self.final_fc.bias.detach().float() + wf @ shift))
@@ -226,14 +251,7 @@ class Multi_DefectModel_new_GCN(nn.Module):
                   p["fc_bbox"][1], z32, zb, B, n, 32, 512, 480)
 
         # 8 x Rs_GCN on the token-major [B*n, 512] tensor (GraphModel.py:190-198)
-        # the residual stream stays fp32 and every product uses bf16x3 split operands: no softmax bounds the affinity
-        # and a BatchNorm follows, so plain bf16 operands cost 1-2 % per block (measured in train mode)
-        z3, y3, tpg = e((B * n, 1536), bf), e((B * n, 1536), bf), e((B * n, 1536), f32)
-        for gc in p["gcn"]:
-            _lib.call("mvuld_split3_bf16", z32, 512, z3, B * n, 512, 0)
-            _lib.gemm(z3, gc["wcat3"], bias=gc["bcat"], out_f32=tpg)
-            _lib.call("mvuld_rs_gcn_affinity_f32", tpg, y3, None, B, n, 512)
-            _lib.gemm(y3, gc["ww3"], bias=gc["wb"], res=z32, out_f32=z32)
+        run_rs_gcn_chain(p["gcn"], z32, B, n)
         self._pending.append((zero_deg, g))
         return z32
 

@@ -110,3 +110,51 @@ def ggnn_sum_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", ou
     s = dgl_ops.segment_sum(h, batch.batch_num_nodes)
     logit = F.linear(s, sd["classifier.weight"].float(), sd["classifier.bias"].float())
     return torch.sigmoid(logit).squeeze(-1), logit, s, h
+
+
+# RQ2 / RQ3 ablation classes without GATConv (GraphModel.py; commented alternatives at main_bigvul.py:126-145).
+#   nodes    : "fconly" = ELU(fconly(h)); "fconly+hidden" adds the eight ELU(hidden[i](.)) layers
+#   readout  : "mean_nodes" = ELU(hfc(hbn(dgl.mean_nodes))); "slots" = unbatch/pad to 100 slots + bn_gat + fc_gat
+#   pos      : slots only -- concat ELU(fc_bbox(bn_bbox(pos slots))) (fc_gat is 512 -> 480) else fc_gat is 512 -> 512
+#   gcn      : slots only -- the eight Rs_GCN blocks + l2norm over the slot axis before the slot mean
+VARIANT_SPECS = {
+    "Multi_DefectModel_noGraph": dict(nodes=None, readout=None),                                   # :306-359
+    "Multi_DefectModel_000": dict(nodes="fconly", readout="mean_nodes"),                           # :362-430
+    "Multi_DefectModel_001": dict(nodes="fconly", readout="slots", pos=False, gcn=True),           # :433-531
+    "Multi_DefectModel_100": dict(nodes="fconly", readout="slots", pos=True, gcn=False),           # :534-615
+    "Multi_DefectModel_NOGAT2": dict(nodes="fconly+hidden", readout="slots", pos=True, gcn=True),  # :1277-1384
+}
+
+
+@torch.no_grad()
+def ablation_forward(name: str, sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
+                     func_text_embedding: torch.Tensor, max_node: int = 100) -> torch.Tensor:
+    """Eval-mode forward of the GATConv-free ablation classes listed in VARIANT_SPECS -> logits [B, num_classes]."""
+    spec = VARIANT_SPECS[name]
+    lin = lambda key, t: F.linear(t, sd[key + ".weight"].float(), sd[key + ".bias"].float())
+    x = F.elu(lin("swinfc", _bn_eval(sd, "swinbn.", img_embedding.float(), 1)))
+    t = F.elu(lin("fc_text", _bn_eval(sd, "bn_text.", func_text_embedding.float(), 1)))
+    if spec["nodes"] is None:
+        feats = torch.cat([x, t], 1)                                            # GraphModel.py:356
+        return lin("final_fc", _bn_eval(sd, "final_fc_bn.", feats, 1))
+    h = F.elu(lin("fconly", batch.ndata["_UNIX_NODE_EMB"].float()))
+    if spec["nodes"] == "fconly+hidden":
+        for i in range(8):
+            h = F.elu(lin(f"hidden.{i}", h))
+    if spec["readout"] == "mean_nodes":
+        hf = dgl_ops.mean_nodes(h, batch.batch_num_nodes)
+        hf = F.elu(lin("hfc", _bn_eval(sd, "hbn.", hf, 1)))
+    else:
+        h_i = dgl_ops.unbatch_pad(h, batch.batch_num_nodes, max_node)          # [B, 100, 512]
+        z = F.elu(lin("fc_gat", _bn_eval(sd, "bn_gat.", h_i, 1)))
+        if spec["pos"]:
+            pos_i = dgl_ops.unbatch_pad(batch.ndata["pos_emb"].float(), batch.batch_num_nodes, max_node)
+            z = torch.cat([z, F.elu(lin("fc_bbox", _bn_eval(sd, "bn_bbox.", pos_i, 1)))], 2)
+        if spec["gcn"]:
+            z = z.permute(0, 2, 1)
+            for k in range(1, 9):
+                z, _ = rs_gcn(sd, f"Rs_GCN_{k}.", z)
+            z = l2norm_dim1(z.permute(0, 2, 1))
+        hf = z.mean(dim=1)
+    feats = torch.cat([x, hf, t], 1)
+    return lin("final_fc", _bn_eval(sd, "final_fc_bn.", feats, 1))

@@ -115,6 +115,25 @@ def test_gat_ablation_variant_matches_oracle():
     assert {"gat.attn_l", "gat2.fc.weight", "hbn.running_mean", "hfc.weight", "final_fc_bn.weight", "fconly.bias"} <= keys
 
 
+@pytest.mark.parametrize("name", ["Multi_DefectModel_noGraph", "Multi_DefectModel_000", "Multi_DefectModel_001",
+                                  "Multi_DefectModel_100", "Multi_DefectModel_NOGAT2"])
+def test_gat_free_ablation_variants_match_oracle(name):
+    """the GATConv-free RQ2 / RQ3 classes (GraphModel.py:306-615, 1277-1384)."""
+    torch.manual_seed(cases.SEED)
+    m = mv.ABLATIONS[name](mv.default_config()).eval()
+    synth.randomize_for_parity(m, seed=cases.SEED)
+    B = 5
+    g = synth.cpg_batch(B, seed=cases.SEED + 13)           # graph sizes on both sides of the 100-slot truncation
+    gen = torch.Generator().manual_seed(3)
+    img, txt = torch.randn(B, 1024, generator=gen), torch.randn(B, 768, generator=gen)
+    ref = ofusion.ablation_forward(name, m.state_dict(), cases.to_host_batch(g), img, txt)
+    out = m.to(DEV)(g.to(DEV), img.to(DEV), txt.to(DEV))
+    torch.cuda.synchronize()
+    assert out.shape == (B, 2) and torch.isfinite(out).all()
+    assert logits_close(out, ref, 1e-2), (name, out.cpu(), ref)
+    assert torch.equal(out.cpu().argmax(1), ref.argmax(1))
+
+
 def test_fusion_rejects_zero_in_degree():
     model = cases.make_fusion().to(DEV)
     g = mv.graph.graph((torch.tensor([0, 1]), torch.tensor([1, 2])), num_nodes=3)      # node 0 has no in-edge

@@ -235,3 +235,71 @@ def test_load_pretrained_strips_derived_buffers_and_reinits_head(golden):
     checkpoint.load_pretrained(dst5, sd)
     assert float(dst5.head.weight.abs().sum()) == 0.0 and float(dst5.head.bias.abs().sum()) == 0.0
     assert torch.equal(dst5.state_dict()["layers.0.blocks.0.attn.qkv.weight"], sd["layers.0.blocks.0.attn.qkv.weight"])
+
+
+def _reference_style_ablation(m, name, g, img, txt):
+    """The reference forward of an ablation class written with the class's own torch modules in eval mode and the
+    reference's Python unbatch loop (GraphModel.py:30-54) -- an independent path to check oracle.fusion.ablation_forward."""
+    import torch.nn.functional as F
+    x = F.elu(m.swinfc(m.swinbn(img)))
+    t = F.elu(m.fc_text(m.bn_text(txt)))
+    if name.endswith("noGraph"):
+        return m.final_fc(m.final_fc_bn(torch.cat((x, t), dim=1)))
+    h = F.elu(m.fconly(g.ndata["_UNIX_NODE_EMB"]))
+    if name.endswith("NOGAT2"):
+        for layer in m.hidden:
+            h = F.elu(layer(h))
+    sizes = [int(v) for v in g.batch_num_nodes()]
+    if name.endswith("000"):
+        hf = torch.stack([c.mean(0) for c in torch.split(h, sizes)])
+        hf = F.elu(m.hfc(m.hbn(hf)))
+    else:
+        def slots(feat):
+            out = []
+            for c in torch.split(feat, sizes):
+                c = c[:100]
+                out.append(torch.cat([c, torch.zeros(100 - c.shape[0], c.shape[1])], 0))
+            return torch.stack(out)
+        z = F.elu(m.fc_gat(m.bn_gat(slots(h))))
+        if hasattr(m, "fc_bbox"):
+            z = torch.cat((z, F.elu(m.fc_bbox(m.bn_bbox(slots(g.ndata["pos_emb"]))))), dim=2)
+        if hasattr(m, "Rs_GCN_1"):
+            from oracle.fusion import rs_gcn, l2norm_dim1
+            sd = m.state_dict()
+            z = z.permute(0, 2, 1)
+            for k in range(1, 9):
+                z, _ = rs_gcn(sd, f"Rs_GCN_{k}.", z)           # pinned against the reference Rs_GCN.py (golden)
+            z = l2norm_dim1(z.permute(0, 2, 1))
+        hf = z.mean(dim=1)
+    return m.final_fc(m.final_fc_bn(torch.cat((x, hf, t), dim=1)))
+
+
+@pytest.mark.parametrize("name", sorted(mv.ABLATIONS))
+def test_ablation_variants_surface_and_oracle(name):
+    from oracle import fusion as ofusion
+    torch.manual_seed(cases.SEED)
+    m = mv.ABLATIONS[name](mv.default_config()).eval()
+    synth.randomize_for_parity(m, seed=cases.SEED)
+    keys = set(m.state_dict())
+    want = {"fconly.weight", "hidden.7.bias", "bn_text.running_var", "ln_text.weight", "fc_text.weight", "swinbn.weight",
+            "swinfc.bias", "hbn.running_mean", "hln.bias", "hfc.weight", "final_fc.weight", "final_fc_bn.running_mean"}
+    spec = ofusion.VARIANT_SPECS[name]
+    if spec["readout"] == "slots":
+        want |= {"bn_gat.running_mean", "fc_gat.weight"}
+        assert m.fc_gat.weight.shape == ((480, 512) if spec["pos"] else (512, 512))
+        if spec["pos"]:
+            want |= {"bn_bbox.weight", "fc_bbox.weight"}
+        if spec["gcn"]:
+            want |= {"Rs_GCN_1.theta.weight", "Rs_GCN_8.W.1.running_var"}
+    assert want <= keys, want - keys
+    assert ("Rs_GCN_1.g.weight" in keys) == bool(spec.get("gcn"))
+    assert m.final_fc.weight.shape == (2, 1024 if spec["nodes"] is None else 1536)
+    g = synth.cpg_batch(4, seed=cases.SEED + 5)
+    gen = torch.Generator().manual_seed(5)
+    img, txt = torch.randn(4, 1024, generator=gen), torch.randn(4, 768, generator=gen)
+    with torch.no_grad():
+        ref = _reference_style_ablation(m, name, g, img, txt)
+    got = ofusion.ablation_forward(name, m.state_dict(), cases.to_host_batch(g), img, txt)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (got, ref)
+    with pytest.raises(RuntimeError):                     # the product path has no CPU fallback
+        m(g, img, txt)
