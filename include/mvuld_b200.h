@@ -186,6 +186,12 @@ int mvuld_split3_bf16(const float* x, int ldx, void* out, int R, int C, int w_si
 /* GraphModel.py:200-209: l2norm(dim=1) + mean + concat + BN(folded) + Linear -> logits fp32 [B, num_classes]. */
 int mvuld_fusion_head(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
                       float* logits, float* feat_out, int B, int n, int D, int num_classes, mvuld_stream_t stream);
+/* Same kernel for the RQ2 ablations (mvuld/models/new_model.py): mode 0 = cat(img, graph, txt) as above; mode 1 =
+ * cat(img, graph), wf [num_classes, 2D] (Multi_DefectModel_noFunc, new_model.py:317-318); mode 2 = txt * graph,
+ * wf [num_classes, D] (Multi_DefectModel_noGlobalImage, new_model.py:196-197).  feat_out (optional) has that width. */
+int mvuld_fusion_head_mode(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
+                           float* logits, float* feat_out, int B, int n, int D, int num_classes, int mode,
+                           mvuld_stream_t stream);
 
 /* Small-N fp32 linear for classification heads (swin_transformer_v2.py:642; reveal/ggnn/model.py:29-30):
  * out[M,N] = x[M,K] w[N,K]^T + b; out_sigmoid (optional) = sigmoid(out). */

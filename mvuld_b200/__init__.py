@@ -10,7 +10,8 @@ from .unixcoder import MyUniXcoder, RobertaEncoder, build_MyUniXcoder, roberta_b
 from .graph_model import (Multi_DefectModel_new_GCN, Multi_DefectModel, Rs_GCN, GATConv, GatedGraphConv,  # noqa: F401
                           GGNNSum)
 from .fusion_variants import (Multi_DefectModel_noGraph, Multi_DefectModel_000, Multi_DefectModel_001,   # noqa: F401
-                              Multi_DefectModel_100, Multi_DefectModel_NOGAT2, ABLATIONS)
+                              Multi_DefectModel_100, Multi_DefectModel_NOGAT2, Multi_DefectModel_noFunc,
+                              Multi_DefectModel_noGlobalImage, ABLATIONS)
 from .mvuld import MVulD                                            # noqa: F401
 from . import graph, checkpoint                                     # noqa: F401
 
@@ -18,4 +19,4 @@ __all__ = ["get_config", "default_config", "CfgNode", "build_model", "SwinTransf
            "RobertaEncoder", "build_MyUniXcoder", "roberta_base_config", "Multi_DefectModel_new_GCN", "Rs_GCN",
            "GATConv", "GatedGraphConv", "GGNNSum", "MVulD", "graph", "Multi_DefectModel",
            "Multi_DefectModel_noGraph", "Multi_DefectModel_000", "Multi_DefectModel_001", "Multi_DefectModel_100",
-           "Multi_DefectModel_NOGAT2", "ABLATIONS"]
+           "Multi_DefectModel_NOGAT2", "Multi_DefectModel_noFunc", "Multi_DefectModel_noGlobalImage", "ABLATIONS"]

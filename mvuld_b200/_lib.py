@@ -52,6 +52,7 @@ SIGNATURES = {
     "mvuld_rs_gcn_affinity_f32": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_split3_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "mvuld_fusion_head": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_fusion_head_mode": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_transpose_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "mvuld_colsum": [_P, _I, _I, _P, _I, _I, _P],

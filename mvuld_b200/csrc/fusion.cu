@@ -176,12 +176,15 @@ __global__ void split3_kernel(const float* __restrict__ x, int ldx, bf16* __rest
 
 // One CTA per function.  z: fp32 [B, n, D] (token-major Rs_GCN output);  img / txt: fp32 [B, D] (already ELU(fc(bn))).
 // feat = cat(img, l2norm_dim1(z).mean(1), txt);  logits = Wf feat + bf with BatchNorm1d(3D) folded into (Wf, bf).
+// mode 1 (new_model.py:317, Multi_DefectModel_noFunc): feat = cat(img, graph) [2D];
+// mode 2 (new_model.py:196, Multi_DefectModel_noGlobalImage): feat = txt * graph [D].
 __global__ void __launch_bounds__(512)
 fusion_head_kernel(const float* __restrict__ z, const float* __restrict__ img, const float* __restrict__ txt,
                    const float* __restrict__ wf, const float* __restrict__ bf, float* __restrict__ logits,
-                   float* __restrict__ feat_out, int n, int D, int num_classes) {
+                   float* __restrict__ feat_out, int n, int D, int num_classes, int mode) {
   extern __shared__ float feat[];                 // [3D]
   const int b = blockIdx.x;
+  const int F = mode == 0 ? 3 * D : (mode == 1 ? 2 * D : D);
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float s = 0.f, sq = 0.f;
     const float* zp = z + (size_t)b * n * D + c;
@@ -190,17 +193,22 @@ fusion_head_kernel(const float* __restrict__ z, const float* __restrict__ img, c
       s += v;
       sq += v * v;
     }
-    feat[c] = __ldg(img + (size_t)b * D + c);
-    feat[D + c] = (s / sqrtf(sq)) / (float)n;     // l2norm has no eps (GraphModel.py:74-79)
-    feat[2 * D + c] = __ldg(txt + (size_t)b * D + c);
+    const float gf = (s / sqrtf(sq)) / (float)n;  // l2norm has no eps (GraphModel.py:74-79)
+    if (mode == 2) {
+      feat[c] = __ldg(txt + (size_t)b * D + c) * gf;
+    } else {
+      feat[c] = __ldg(img + (size_t)b * D + c);
+      feat[D + c] = gf;
+      if (mode == 0) feat[2 * D + c] = __ldg(txt + (size_t)b * D + c);
+    }
   }
   __syncthreads();
   if (feat_out)
-    for (int c = threadIdx.x; c < 3 * D; c += blockDim.x) feat_out[(size_t)b * 3 * D + c] = feat[c];
+    for (int c = threadIdx.x; c < F; c += blockDim.x) feat_out[(size_t)b * F + c] = feat[c];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = warp; k < num_classes; k += blockDim.x >> 5) {
     float acc = 0.f;
-    for (int c = lane; c < 3 * D; c += 32) acc += __ldg(wf + (size_t)k * 3 * D + c) * feat[c];
+    for (int c = lane; c < F; c += 32) acc += __ldg(wf + (size_t)k * F + c) * feat[c];
     acc = warp_sum(acc);
     if (lane == 0) logits[(size_t)b * num_classes + k] = acc + __ldg(bf + k);
   }
@@ -275,12 +283,19 @@ extern "C" int mvuld_split3_bf16(const float* x, int ldx, void* out, int R, int 
   return 0;
 }
 
+extern "C" int mvuld_fusion_head_mode(const float* z, const float* img, const float* txt, const float* wf,
+                                      const float* bf, float* logits, float* feat_out, int B, int n, int D,
+                                      int num_classes, int mode, cudaStream_t stream) {
+  MV_CHECK_ARG(mode >= 0 && mode <= 2, "fusion_head: mode must be 0 (img|graph|txt), 1 (img|graph) or 2 (txt*graph)");
+  if (B <= 0) return 0;
+  fusion_head_kernel<<<B, 512, 3 * D * sizeof(float), stream>>>(z, img, txt, wf, bf, logits, feat_out, n, D,
+                                                               num_classes, mode);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int mvuld_fusion_head(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
                                  float* logits, float* feat_out, int B, int n, int D, int num_classes,
                                  cudaStream_t stream) {
-  if (B <= 0) return 0;
-  fusion_head_kernel<<<B, 512, 3 * D * sizeof(float), stream>>>(z, img, txt, wf, bf, logits, feat_out, n, D,
-                                                               num_classes);
-  MV_LAUNCH_OK();
-  return 0;
+  return mvuld_fusion_head_mode(z, img, txt, wf, bf, logits, feat_out, B, n, D, num_classes, 0, stream);
 }

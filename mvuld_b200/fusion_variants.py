@@ -9,6 +9,11 @@ main_bigvul.py:126-145 keeps next to the live ``Multi_DefectModel_new_GCN``:
     Multi_DefectModel_100       :534-615    ELU(fconly) nodes, 100 slots, fc_gat (480) | fc_bbox (32), slot mean
     Multi_DefectModel_NOGAT2    :1277-1384  fconly + hidden x 8 nodes, fc_gat | fc_bbox, Rs_GCN x 8 ("POS+GCN")
 
+and of /root/reference/mvuld/models/new_model.py -- the live graph branch with one modality removed from the head:
+
+    Multi_DefectModel_noFunc         :202-319   final_fc(final_fc_bn(cat(image, graph)))
+    Multi_DefectModel_noGlobalImage  :81-199    final_fc(final_fc_bn(text * graph))
+
 Same constructor ``(config, pretrained=True, attention=True)``, ``forward(g, img_embedding, func_text_embedding)``
 and state-dict keys as the reference classes (modules a class declares but never runs -- ``hidden`` in _000 / _001 /
 _100, ``ln_text``, ``hln``, ``hfc`` where unused -- are kept so checkpoints load with ``strict=True``).  Eval-mode
@@ -25,7 +30,8 @@ import torch.nn as nn
 
 from . import _lib
 from .graph import Graph
-from .graph_model import Rs_GCN, _bn_affine, _fold_bn_into_linear, plan_rs_gcn_chain, run_rs_gcn_chain
+from .graph_model import (Multi_DefectModel_new_GCN, Rs_GCN, _bn_affine, _fold_bn_into_linear, plan_rs_gcn_chain,
+                          run_rs_gcn_chain)
 
 
 class _AblationBase(nn.Module):
@@ -221,5 +227,18 @@ class Multi_DefectModel_NOGAT2(_AblationBase):
     NODES, READOUT, POS, GCN, FC_GAT = "fconly+hidden", "slots", True, True, (512, 480)
 
 
+class Multi_DefectModel_noFunc(Multi_DefectModel_new_GCN):
+    """new_model.py:202-319 (RQ2: no function text): the live model's GATConv x2 / node MLP / slots / Rs_GCN x 8 graph
+    branch; head = final_fc(final_fc_bn(cat(image, graph))) over 1024 features (one fused kernel, mode 1)."""
+    HEAD_MODE, HEAD_FEATS = 1, 2
+
+
+class Multi_DefectModel_noGlobalImage(Multi_DefectModel_new_GCN):
+    """new_model.py:81-199 (RQ2: no global image): same graph branch; head = final_fc(final_fc_bn(text * graph)) over
+    512 features (elementwise product of the text projection and the graph readout, mode 2)."""
+    HEAD_MODE, HEAD_FEATS = 2, 1
+
+
 ABLATIONS = {c.__name__: c for c in (Multi_DefectModel_noGraph, Multi_DefectModel_000, Multi_DefectModel_001,
-                                     Multi_DefectModel_100, Multi_DefectModel_NOGAT2)}
+                                     Multi_DefectModel_100, Multi_DefectModel_NOGAT2, Multi_DefectModel_noFunc,
+                                     Multi_DefectModel_noGlobalImage)}

@@ -109,6 +109,9 @@ def run_rs_gcn_chain(plan, z32: torch.Tensor, B: int, n: int) -> torch.Tensor:
 
 
 class Multi_DefectModel_new_GCN(nn.Module):
+    HEAD_MODE = 0          # mvuld_fusion_head_mode: 0 cat(img, graph, txt); the RQ2 subclasses in fusion_variants.py use 1 / 2
+    HEAD_FEATS = 3         # width of final_fc / final_fc_bn in units of hfeat
+
     def __init__(self, config, pretrained=True, attention=True):
         super().__init__()
         self.num_features = 1024
@@ -135,8 +138,8 @@ class Multi_DefectModel_new_GCN(nn.Module):
         self.hbn = nn.BatchNorm1d(hfeat)
         self.hln = nn.LayerNorm(hfeat)
         self.hfc = nn.Linear(hfeat, hfeat)
-        self.final_fc = nn.Linear(hfeat * 3, self.num_classes)
-        self.final_fc_bn = nn.BatchNorm1d(hfeat * 3)
+        self.final_fc = nn.Linear(hfeat * self.HEAD_FEATS, self.num_classes)
+        self.final_fc_bn = nn.BatchNorm1d(hfeat * self.HEAD_FEATS)
         self._plan = None
         # Input validity (DGL raises on 0-in-degree nodes; edge endpoints must lie in [0, N)) is detected by the kernels
         # and read back here.  With defer_checks = True the read-back (a host synchronisation per call) is postponed to
@@ -277,8 +280,8 @@ class Multi_DefectModel_new_GCN(nn.Module):
         _lib.gemm(img_b, p["img"][0], bias=p["img"][1], act=_lib.ACT_ELU, out_f32=ximg)
         _lib.gemm(txt_b, p["txt"][0], bias=p["txt"][1], act=_lib.ACT_ELU, out_f32=xtxt)
         logits = e((B, self.num_classes), f32)
-        _lib.call("mvuld_fusion_head", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
-                  self.num_classes)
+        _lib.call("mvuld_fusion_head_mode", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
+                  self.num_classes, self.HEAD_MODE)
         if not self.defer_checks:
             self.raise_if_invalid()
         elif len(self._pending) > 64:

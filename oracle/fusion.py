@@ -45,8 +45,10 @@ def l2norm_dim1(x: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def fusion_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
-                   func_text_embedding: torch.Tensor, max_node: int = 100, taps: dict | None = None) -> torch.Tensor:
-    """GraphModel.py:150-211 -> logits [B, 2]."""
+                   func_text_embedding: torch.Tensor, max_node: int = 100, taps: dict | None = None,
+                   head: str = "all") -> torch.Tensor:
+    """GraphModel.py:150-211 -> logits [B, 2].  ``head``: "all" = the live model; "noFunc" = new_model.py:317-318
+    (cat(image, graph)); "noGlobalImage" = new_model.py:196-197 (text * graph) -- same graph branch."""
     lin = lambda name, t: F.linear(t, sd[name + ".weight"].float(), sd[name + ".bias"].float())
     x = F.elu(lin("swinfc", _bn_eval(sd, "swinbn.", img_embedding.float(), 1)))
     t = F.elu(lin("fc_text", _bn_eval(sd, "bn_text.", func_text_embedding.float(), 1)))
@@ -76,7 +78,8 @@ def fusion_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_
     if taps is not None:
         taps["gcn_out"] = z.clone()
     z = l2norm_dim1(z.permute(0, 2, 1)).mean(dim=1)                           # [B, 512]
-    feats = torch.cat([x, z, t], 1)
+    feats = {"all": lambda: torch.cat([x, z, t], 1), "noFunc": lambda: torch.cat([x, z], 1),
+             "noGlobalImage": lambda: t * z}[head]()
     return lin("final_fc", _bn_eval(sd, "final_fc_bn.", feats, 1))
 
 
@@ -130,6 +133,8 @@ VARIANT_SPECS = {
 def ablation_forward(name: str, sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
                      func_text_embedding: torch.Tensor, max_node: int = 100) -> torch.Tensor:
     """Eval-mode forward of the GATConv-free ablation classes listed in VARIANT_SPECS -> logits [B, num_classes]."""
+    if name in ("Multi_DefectModel_noFunc", "Multi_DefectModel_noGlobalImage"):
+        return fusion_forward(sd, batch, img_embedding, func_text_embedding, max_node, head=name.split("_")[-1])
     spec = VARIANT_SPECS[name]
     lin = lambda key, t: F.linear(t, sd[key + ".weight"].float(), sd[key + ".bias"].float())
     x = F.elu(lin("swinfc", _bn_eval(sd, "swinbn.", img_embedding.float(), 1)))

@@ -116,9 +116,11 @@ def test_gat_ablation_variant_matches_oracle():
 
 
 @pytest.mark.parametrize("name", ["Multi_DefectModel_noGraph", "Multi_DefectModel_000", "Multi_DefectModel_001",
-                                  "Multi_DefectModel_100", "Multi_DefectModel_NOGAT2"])
+                                  "Multi_DefectModel_100", "Multi_DefectModel_NOGAT2", "Multi_DefectModel_noFunc",
+                                  "Multi_DefectModel_noGlobalImage"])
 def test_gat_free_ablation_variants_match_oracle(name):
-    """the GATConv-free RQ2 / RQ3 classes (GraphModel.py:306-615, 1277-1384)."""
+    """the GATConv-free RQ2 / RQ3 classes (GraphModel.py:306-615, 1277-1384) and the two RQ2
+    head variants of the live graph branch (new_model.py:81-319)."""
     torch.manual_seed(cases.SEED)
     m = mv.ABLATIONS[name](mv.default_config()).eval()
     synth.randomize_for_parity(m, seed=cases.SEED)

@@ -274,7 +274,37 @@ def _reference_style_ablation(m, name, g, img, txt):
     return m.final_fc(m.final_fc_bn(torch.cat((x, hf, t), dim=1)))
 
 
-@pytest.mark.parametrize("name", sorted(mv.ABLATIONS))
+@pytest.mark.parametrize("name,width", [("Multi_DefectModel_noFunc", 1024), ("Multi_DefectModel_noGlobalImage", 512)])
+def test_rq2_head_variants_surface_and_oracle(name, width):
+    """new_model.py:81-319: the live graph branch with one modality dropped from the head."""
+    import torch.nn.functional as F
+    from oracle import fusion as ofusion
+    torch.manual_seed(cases.SEED)
+    m = mv.ABLATIONS[name](mv.default_config()).eval()
+    synth.randomize_for_parity(m, seed=cases.SEED)
+    live = set(cases.make_fusion().state_dict())
+    assert set(m.state_dict()) == live                      # same modules as the live model, only the head width differs
+    assert m.final_fc.weight.shape == (2, width) and m.final_fc_bn.weight.shape == (width,)
+    g = synth.cpg_batch(3, seed=cases.SEED + 6)
+    gen = torch.Generator().manual_seed(6)
+    img, txt = torch.randn(3, 1024, generator=gen), torch.randn(3, 768, generator=gen)
+    sd = m.state_dict()
+    taps = {}
+    got = ofusion.ablation_forward(name, sd, cases.to_host_batch(g), img, txt)
+    ofusion.fusion_forward(sd, cases.to_host_batch(g), img, txt, taps=taps, head=name.split("_")[-1])
+    z = taps["gcn_out"].permute(0, 2, 1)
+    z = (z / z.pow(2).sum(1, keepdim=True).sqrt()).mean(1)
+    with torch.no_grad():
+        x, t = F.elu(m.swinfc(m.swinbn(img))), F.elu(m.fc_text(m.bn_text(txt)))
+        feats = torch.cat((x, z), 1) if name.endswith("noFunc") else t * z
+        ref = m.final_fc(m.final_fc_bn(feats))
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (got, ref)
+    with pytest.raises(RuntimeError):
+        m(g, img, txt)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in mv.ABLATIONS if n not in ("Multi_DefectModel_noFunc",
+                                                                             "Multi_DefectModel_noGlobalImage")))
 def test_ablation_variants_surface_and_oracle(name):
     from oracle import fusion as ofusion
     torch.manual_seed(cases.SEED)

@@ -103,8 +103,49 @@ def table(src, dst):
     print(open(dst).read())
 
 
+def table_long(src, dst):
+    """`ncu --metrics ... --csv` (long format: one row per metric per launch) -> one row per distinct kernel, the
+    LARGEST launch of each (by duration), with how many launches of it were measured."""
+    lines = [l for l in open(src) if l.startswith('"')]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    per = OrderedDict()
+    for r in rows:
+        d = per.setdefault(r["ID"], {"name": short(r["Kernel Name"]), "grid": r.get("Grid Size", ""), "block": r.get("Block Size", "")})
+        v = float(r["Metric Value"].replace(",", "")) if r["Metric Value"] not in ("", "n/a") else 0.0
+        unit = r["Metric Unit"]
+        v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "ms": 1e3, "s": 1e6, "msecond": 1e3, "usecond": 1.0,
+              "nsecond": 1e-3, "second": 1e6}.get(unit, 1.0)
+        d[r["Metric Name"]] = v
+    best, count = OrderedDict(), {}
+    for d in per.values():
+        n = d["name"]
+        count[n] = count.get(n, 0) + 1
+        if n not in best or d["gpu__time_duration.sum"] > best[n]["gpu__time_duration.sum"]:
+            best[n] = d
+    g = lambda d, k: d.get(k, 0.0)
+    with open(dst, "w") as fh:
+        fh.write(f"# ncu roofline metrics, every remaining kernel of one full step: {src}\n\n")
+        fh.write("`ncu --metrics <list> --clock-control none` on `bench.py --steps 1 --warmup 1` (cold-cache, serialised). "
+                 "One row per kernel: its longest launch; DRAM GB/s = (read + write) / duration; L2 GB/s = lts__t_bytes / duration.\n\n")
+        fh.write("| kernel | launches seen | us | DRAM read MB | DRAM write MB | DRAM GB/s | dram % | L2 GB/s | tensor % | sm % | issue % | warps % | regs | grid x block |\n")
+        fh.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|\n")
+        for n, d in sorted(best.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"]):
+            us = d["gpu__time_duration.sum"]
+            rd, wr = g(d, "dram__bytes_read.sum"), g(d, "dram__bytes_write.sum")
+            fh.write(f"| `{n}` | {count[n]} | {us:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {(rd + wr) / us / 1e3:.0f} | "
+                     f"{g(d, 'dram__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {g(d, 'lts__t_bytes.sum') / us / 1e3:.0f} | "
+                     f"{g(d, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                     f"{g(d, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                     f"{g(d, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                     f"{g(d, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {g(d, 'launch__registers_per_thread'):.0f} | "
+                     f"{g(d, 'launch__grid_size'):.0f} x {g(d, 'launch__block_size'):.0f} |\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "table":
+    if sys.argv[1] == "table_long":
+        table_long(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "table":
         table(sys.argv[2], sys.argv[3])
     elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else 0)
