@@ -421,25 +421,41 @@ extern "C" int mvuld_roberta_embed(const long long* ids, const int* pos, const f
 
 namespace mv {
 // mean over the token rows [start[s], start[s] + len[s]) of tok fp32 [T, C] -> out fp32 [n, C]: the sentence vector
-// of each packed line (unixcoder.py:37 per line).  One block per segment.
+// of each packed line (unixcoder.py:37 per line).  Grid (segment, 64-column chunk); the 256 threads of a block are 64
+// columns x 4 token phases (phase p sums tokens p, p + 4, ... four loads in flight), combined in a fixed order through
+// shared memory -- 64 function-level segments of ~257 tokens x 768 columns used to run as 64 blocks with one serial
+// chain per column (132 us); this shape gives 768 blocks (deterministic: the summation order depends on n only).
 __global__ void __launch_bounds__(256)
 segment_mean_kernel(const float* __restrict__ tok, const int* __restrict__ start, const int* __restrict__ len,
                     const int* __restrict__ dst, float* __restrict__ out, int C) {
+  __shared__ float part[4][64];
   const int sgm = blockIdx.x;
   const long long b = start[sgm];
   const int n = len[sgm];
   const size_t orow = dst ? (size_t)dst[sgm] : (size_t)sgm;      // output row of this segment (packing may reorder)
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int t = 0; t < n; ++t) acc += tok[(b + t) * C + c];
-    out[orow * C + c] = acc / (float)n;
+  const int cl = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < C) {
+    const float* p = tok + b * C + c;
+    int t = ph;
+    for (; t + 12 < n; t += 16) {
+      a0 += __ldg(p + (size_t)t * C);
+      a1 += __ldg(p + (size_t)(t + 4) * C);
+      a2 += __ldg(p + (size_t)(t + 8) * C);
+      a3 += __ldg(p + (size_t)(t + 12) * C);
+    }
+    for (; t < n; t += 4) a0 += __ldg(p + (size_t)t * C);
   }
+  part[ph][cl] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ph == 0 && c < C) out[orow * C + c] = ((part[0][cl] + part[1][cl]) + (part[2][cl] + part[3][cl])) / (float)n;
 }
 }  // namespace mv
 extern "C" int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* seg_len, const int* out_row,
                                       float* out, int n, int C, cudaStream_t stream) {
   if (n <= 0) return 0;
-  mv::segment_mean_kernel<<<n, 256, 0, stream>>>(tok, seg_start, seg_len, out_row, out, C);
+  mv::segment_mean_kernel<<<dim3(n, (C + 63) / 64), 256, 0, stream>>>(tok, seg_start, seg_len, out_row, out, C);
   MV_LAUNCH_OK();
   return 0;
 }
