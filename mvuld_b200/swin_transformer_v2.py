@@ -20,6 +20,8 @@ from __future__ import annotations
 import math
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -282,10 +284,10 @@ class SwinTransformerV2(nn.Module):
         self._plan = plan
         return self
 
-    def _workspace(self, B: int):
+    def _workspace(self, B: int, slot: int = 0, keep: bool = False):
         p = self._plan
-        if B in p["ws"]:
-            return p["ws"][B]
+        if (B, slot) in p["ws"]:
+            return p["ws"][(B, slot)]
         dev = p["dev"]
         L0 = self.patches_resolution[0] * self.patches_resolution[1]
         n = B * L0 * self.embed_dim                     # elements of the widest [tokens, C] activation
@@ -294,7 +296,9 @@ class SwinTransformerV2(nn.Module):
                   v=e(n, torch.bfloat16), att=e(n, torch.bfloat16), y=e(n, torch.bfloat16),
                   h=e(int(n * self.mlp_ratio), torch.bfloat16), mg=e(n, torch.bfloat16),
                   feat=torch.empty(B, self.num_features, device=dev, dtype=torch.float32))
-        p["ws"] = {B: ws}                                # keep one batch size resident
+        if not keep:
+            p["ws"] = {}                                 # keep one batch size resident
+        p["ws"][(B, slot)] = ws
         return ws
 
     def _check_input(self, x):
@@ -309,13 +313,36 @@ class SwinTransformerV2(nn.Module):
 
     @torch.no_grad()
     def forward_features(self, x: torch.Tensor) -> torch.Tensor:
-        """:623-635 -> fp32 [B, num_features]."""
+        """:623-635 -> fp32 [B, num_features].  ``self.streams`` (or MVULD_SWIN_STREAMS) = k > 1 runs the batch as k
+        independent sub-batches on k CUDA streams, so the HBM-bound row kernels of one sub-batch can share the SMs with
+        the tensor-bound kernels of another (images are independent in eval mode; results are identical)."""
         self._check_input(x)
         if self._plan is None:
             self.prepare()
+        B = x.shape[0]
+        k = int(getattr(self, "streams", 0) or os.environ.get("MVULD_SWIN_STREAMS", "1"))
+        if k <= 1 or B % k != 0 or B // k < 8:
+            return self._forward_features_ws(x, self._workspace(B)).clone()
+        Bk = B // k
+        wss = [self._workspace(Bk, slot=i, keep=i > 0) for i in range(k)]       # allocated on the caller's stream
+        if len(getattr(self, "_side_streams", [])) < k:
+            self._side_streams = [torch.cuda.Stream(device=x.device) for _ in range(k)]
+        main = torch.cuda.current_stream(x.device)
+        x = x.to(torch.float32).contiguous()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for i in range(k):
+            st = self._side_streams[i]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                self._forward_features_ws(x[i * Bk:(i + 1) * Bk], wss[i])
+        for i in range(k):
+            main.wait_stream(self._side_streams[i])
+        return torch.cat([w["feat"] for w in wss], 0)
+
+    def _forward_features_ws(self, x: torch.Tensor, w) -> torch.Tensor:
         p = self._plan
         B = x.shape[0]
-        w = self._workspace(B)
         x = x.to(torch.float32).contiguous()
         E = self.embed_dim
         Hp, Wp = self.patches_resolution
@@ -375,7 +402,7 @@ class SwinTransformerV2(nn.Module):
         x32 = w["x32"][:B * T * C]
         nm = p["norm"]
         _lib.call("mvuld_ln_meanpool", x32, nm["g"], nm["b"], w["feat"], B, T, C, float(nm["eps"]))
-        return w["feat"].clone()
+        return w["feat"]
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:

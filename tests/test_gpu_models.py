@@ -359,3 +359,18 @@ def test_edge_cases_ragged_and_extreme_sizes():
     x = synth.images(1, cases.SWIN_CASES["small_ws7"]["img_size"], seed=2)
     r = oswin.forward_features(sw.state_dict(), cases.swin_geometry("small_ws7"), x)
     assert rel_err(sw.to(DEV).forward_features(x.to(DEV)), r) < 2e-2
+
+
+def test_swin_sub_batches_on_streams_give_identical_features():
+    """forward_features with ``streams = 2``: sub-batches on two CUDA streams, same result as one batch."""
+    name = "small_ws7"
+    model = cases.make_swin(name).to(DEV)
+    x = synth.images(16, cases.SWIN_CASES[name]["img_size"], seed=cases.SEED + 3).to(DEV)
+    one = model.forward_features(x).clone()
+    model.streams = 2
+    two = model.forward_features(x).clone()
+    model.streams = 0
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    again = model.forward_features(x)
+    assert torch.equal(one, again)
