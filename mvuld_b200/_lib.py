@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvuld_b200.so")
+LIB_PATH = os.environ.get("MVULD_LIB") or os.path.join(_HERE, "libmvuld_b200.so")   # MVULD_LIB: an experimental build of the same library
 
 _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
