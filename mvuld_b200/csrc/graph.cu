@@ -9,6 +9,7 @@
 // baselines/models/devign/model.py:15-16,35.  DGL semantics restated in SURVEY.md section 8(c).
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "host_util.h"
 
@@ -88,8 +89,8 @@ __global__ void collate_edges_kernel(const int* __restrict__ src_l, const int* _
 // warp-per-node version spent two thirds of its time in the indptr -> (src, etype) -> row dependency chain with
 // nothing in flight (measured 3.1 TB/s DRAM); here the chain is paid once per NPW nodes and row loads of the next
 // node are issued while the previous node is still being summed.  Sums run in edge order per node (fp32).
-template <int UNROLL, int NPW>
-__global__ void __launch_bounds__(256)
+template <int UNROLL, int NPW, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
 ggnn_gather_sum_kernel(const bf16* __restrict__ msgs, const int* __restrict__ indptr, const int* __restrict__ idx_src,
                        const unsigned char* __restrict__ etype, bf16* __restrict__ out, int ldo, int N, int T, int D) {
   const int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * NPW;
@@ -505,8 +506,14 @@ extern "C" int mvuld_ggnn_gather_sum(const void* msgs, const int* indptr, const 
   MV_CHECK_ARG(D % 8 == 0 && D <= 256, "ggnn_gather_sum: D must be a multiple of 8 and <= 256");
   MV_CHECK_ARG(ldo >= D && ldo % 8 == 0, "ggnn_gather_sum: ldo must be >= D and a multiple of 8");
   if (N <= 0) return 0;
-  ggnn_gather_sum_kernel<8, 8><<<(N + 63) / 64, 256, 0, stream>>>(reinterpret_cast<const bf16*>(msgs), indptr, idx_src,
-                                                            etype, reinterpret_cast<bf16*>(out), ldo, N, T, D);
+  const bf16* mp = reinterpret_cast<const bf16*>(msgs);
+  bf16* op = reinterpret_cast<bf16*>(out);
+  // 4 row loads in flight per lane at 48 registers / 5 blocks per SM: measured 334 us on configs[2] (6.0 TB/s of
+  // algorithmic bytes) against 430 us for 8 in flight at 78 registers / 3 blocks -- occupancy hides the gather latency
+  // better than per-warp depth.  MVULD_GGNN_VARIANT=1 launches the deeper variant for A/B runs.
+  static const bool deep = getenv("MVULD_GGNN_VARIANT") != nullptr && atoi(getenv("MVULD_GGNN_VARIANT")) == 1;
+  if (deep) ggnn_gather_sum_kernel<8, 8><<<(N + 63) / 64, 256, 0, stream>>>(mp, indptr, idx_src, etype, op, ldo, N, T, D);
+  else ggnn_gather_sum_kernel<4, 8, 5><<<(N + 63) / 64, 256, 0, stream>>>(mp, indptr, idx_src, etype, op, ldo, N, T, D);
   MV_LAUNCH_OK();
   return 0;
 }
