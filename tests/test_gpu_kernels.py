@@ -439,6 +439,26 @@ def test_rs_gcn_block_split_precision_matches_reference_golden(golden):
     assert rel_err(z32, ref) < 1e-4
 
 
+@pytest.mark.parametrize("B,n,C", [(3, 100, 512), (5, 37, 256), (2, 1, 128), (4, 76, 512)])
+def test_rs_gcn_affinity_f32_ragged_slot_counts(B, n, C):
+    """mvuld_rs_gcn_affinity_f32 (row-split kernel: 25 rows of R / y per CTA) against the fp32 definition
+    R = theta phi^T / n, y = R g (Rs_GCN.py:57-66) for slot counts that do not fill the last row block."""
+    r = gen(100 * n + C)
+    tpg = torch.randn(B * n, 3 * C, generator=r) * 0.5
+    th, ph, g = (tpg[:, i * C:(i + 1) * C].reshape(B, n, C).double() for i in range(3))
+    R_ref = th @ ph.transpose(1, 2) / n
+    y_ref = (R_ref @ g).reshape(B * n, C)
+    y3 = torch.zeros(B * n, 3 * C, device=DEV, dtype=torch.bfloat16)
+    R = torch.zeros(B, n, n, device=DEV)
+    _lib.call("mvuld_rs_gcn_affinity_f32", tpg.to(DEV), y3, R, B, n, C)
+    torch.cuda.synchronize()
+    assert rel_err(R, R_ref.float()) < 1e-5
+    y3 = y3.float().cpu()
+    assert torch.equal(y3[:, :C], y3[:, 2 * C:])                             # (hi | lo | hi)
+    assert rel_err(y3[:, :C] + y3[:, C:2 * C], y_ref.float()) < 3e-5        # hi + lo carries ~16 mantissa bits
+    assert rel_err(y3[:, :C], y_ref.float()) < 6e-3                          # hi alone is the bf16 rounding
+
+
 def test_gemm_gru_matches_torch_grucell():
     """mvuld_gemm_gru: GRUCell (torch gate order r, z, n) as one GEMM over [a | h] with the gates in the epilogue."""
     N, D = 1000, 200
