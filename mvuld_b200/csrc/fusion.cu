@@ -4,6 +4,7 @@
 //     (folded) + Linear(1536, num_classes) in ONE kernel (GraphModel.py:200-209).
 #include <cstdlib>
 
+#include "affinity_rows.cuh"
 #include "common.cuh"
 #include "host_util.h"
 
@@ -157,124 +158,34 @@ rs_gcn_affinity_kernel(const TIn* __restrict__ tpg, bf16* __restrict__ y, float*
 }
 
 // Row-split variant of the fp32 -> split affinity (what mvuld_rs_gcn_affinity_f32 launches): CTA (b, s) owns the 25 rows
-// [25 s, 25 s + 25) of R and of y, so nothing is computed twice (the column-split kernel above recomputes the whole R in
-// each of its CTAs: 6.4 M FMA per CTA against 2.6 M here).
-//   phase 1  R rows = theta rows . phi^T / n : 200 threads = 4 k-groups x (5 x 10) thread grid, 5 x 10 outputs each
-//            over a quarter of every 32-wide k chunk; the 4 partial sums are combined through shared memory
-//   phase 2  y rows = R rows . g             : 160 threads = 5 row groups x 32 float4 columns of a 128-column g chunk
-constexpr int RS_ROWS = 25;                       // R / y rows per CTA
-constexpr int RS_GCH = 128;                       // g columns staged per pass of phase 2
-constexpr int RS_ROWS_SMEM = (RS_ROWS * RS_MAXN + RS_MAXN * RS_GCH) * 4;     // Rs + max(phase buffers)
+// [25 s, 25 s + 25) of R and of y (affinity_rows.cuh), so nothing is computed twice -- the column-split kernel above
+// recomputes the whole R in each of its CTAs: 6.4 M FMA per CTA against 2.6 M here (138.7 -> 73.0 us at 64 graphs).
 __global__ void __launch_bounds__(256)
 rs_gcn_affinity_rows_kernel(const float* __restrict__ tpg, bf16* __restrict__ y, float* __restrict__ r_out, int n,
                             int C) {
   extern __shared__ __align__(16) float smr[];
-  float* Rs = smr;                                // [RS_ROWS][RS_MAXN]
-  float* U = Rs + RS_ROWS * RS_MAXN;              // phase 1: theta [RS_ROWS][33] | phi [RS_MAXN][33]; then the 4 partial
-                                                  // R tiles [4][RS_ROWS][RS_MAXN]; phase 2: g chunk [RS_MAXN][RS_GCH]
-  float* bufT = U;
-  float* bufP = U + RS_ROWS * 33;
+  float* Rs = smr;                                // [AR_ROWS][AR_MAXN]
+  float* U = Rs + AR_ROWS * AR_MAXN;
   const int b = blockIdx.x;
-  const int r0 = blockIdx.y * RS_ROWS;
-  const int tid = threadIdx.x;
+  const int r0 = blockIdx.y * AR_ROWS;
   const float* base = tpg + (size_t)b * n * 3 * C;
-
-  // ---- phase 1 ----
-  const int kg = tid / 50, t50 = tid % 50;
-  const int ti = t50 / 10, tj = t50 % 10;
-  float acc[5][10];
-#pragma unroll
-  for (int a = 0; a < 5; ++a)
-#pragma unroll
-    for (int c = 0; c < 10; ++c) acc[a][c] = 0.f;
-  for (int k0 = 0; k0 < C; k0 += 32) {
-    for (int i = tid; i < (RS_ROWS + RS_MAXN) * 8; i += 256) {
-      const int row = i >> 3, part = i & 7;       // rows [0, 25) theta (global row r0 + row), [25, 125) phi
-      const bool is_t = row < RS_ROWS;
-      const int grow = is_t ? r0 + row : row - RS_ROWS;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (grow < n) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)grow * 3 * C + (is_t ? 0 : C) + k0) + part);
-      float* dstp = (is_t ? bufT + row * 33 : bufP + (row - RS_ROWS) * 33) + part * 4;
-      dstp[0] = v.x; dstp[1] = v.y; dstp[2] = v.z; dstp[3] = v.w;
-    }
-    __syncthreads();
-    if (tid < 200) {
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const int k = kg * 8 + kk;
-        float th[5], ph[10];
-#pragma unroll
-        for (int a = 0; a < 5; ++a) th[a] = bufT[(ti * 5 + a) * 33 + k];
-#pragma unroll
-        for (int c = 0; c < 10; ++c) ph[c] = bufP[(tj * 10 + c) * 33 + k];
-#pragma unroll
-        for (int a = 0; a < 5; ++a)
-#pragma unroll
-          for (int c = 0; c < 10; ++c) acc[a][c] += th[a] * ph[c];
-      }
-    }
-    __syncthreads();
-  }
-  if (tid < 200) {
-    float* part = U + kg * RS_ROWS * RS_MAXN;
-#pragma unroll
-    for (int a = 0; a < 5; ++a)
-#pragma unroll
-      for (int c = 0; c < 10; ++c) part[(ti * 5 + a) * RS_MAXN + tj * 10 + c] = acc[a][c];
-  }
-  __syncthreads();
-  {
-    const float inv = 1.0f / (float)n;            // R.size(-1) == number of slots
-    for (int i = tid; i < RS_ROWS * RS_MAXN; i += 256) {
-      const float v = ((U[i] + U[RS_ROWS * RS_MAXN + i]) + (U[2 * RS_ROWS * RS_MAXN + i] + U[3 * RS_ROWS * RS_MAXN + i])) * inv;
-      Rs[i] = v;
-      const int row = r0 + i / RS_MAXN, col = i % RS_MAXN;
-      if (r_out && row < n && col < n) r_out[((size_t)b * n + row) * n + col] = v;
+  ar_nt<float>(base, 3 * C, r0, base + C, 3 * C, n, C, 1.0f / (float)n, Rs, U);      // R.size(-1) == number of slots
+  if (r_out) {
+    for (int i = threadIdx.x; i < AR_ROWS * AR_MAXN; i += 256) {
+      const int row = r0 + i / AR_MAXN, col = i % AR_MAXN;
+      if (row < n && col < n) r_out[((size_t)b * n + row) * n + col] = Rs[i];
     }
   }
-  __syncthreads();
-
-  // ---- phase 2 ----
-  const int ri = tid >> 5, cj = tid & 31;
-  for (int c0 = 0; c0 < C; c0 += RS_GCH) {
-    for (int i = tid; i < RS_MAXN * (RS_GCH / 4); i += 256) {
-      const int row = i / (RS_GCH / 4), part = i % (RS_GCH / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < n) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * 3 * C + 2 * C + c0) + part);
-      *reinterpret_cast<float4*>(U + row * RS_GCH + part * 4) = v;
-    }
-    __syncthreads();
-    if (ri < 5) {
-      float o[5][4];
-#pragma unroll
-      for (int a = 0; a < 5; ++a)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[a][q] = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < n; ++j) {
-        const float4 g4 = *reinterpret_cast<const float4*>(U + j * RS_GCH + cj * 4);
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-          const float rv = Rs[(ri * 5 + a) * RS_MAXN + j];
-          o[a][0] += rv * g4.x; o[a][1] += rv * g4.y; o[a][2] += rv * g4.z; o[a][3] += rv * g4.w;
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 5; ++a) {
-        const int row = r0 + ri * 5 + a;
-        if (row < n) {
-          const uint32_t h0 = pack_bf16x2(o[a][0], o[a][1]), h1 = pack_bf16x2(o[a][2], o[a][3]);
-          const uint32_t l0 = pack_bf16x2(o[a][0] - bf16_lo(h0), o[a][1] - bf16_hi(h0));
-          const uint32_t l1 = pack_bf16x2(o[a][2] - bf16_lo(h1), o[a][3] - bf16_hi(h1));
-          bf16* yr = y + ((size_t)b * n + row) * 3 * C + c0 + cj * 4;
-          *reinterpret_cast<uint2*>(yr) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(yr + C) = make_uint2(l0, l1);
-          *reinterpret_cast<uint2*>(yr + 2 * C) = make_uint2(h0, h1);
-        }
-      }
-    }
-    __syncthreads();
-  }
+  bf16* yb = y + (size_t)b * n * 3 * C;
+  ar_sy<float>(Rs, base + 2 * C, 3 * C, r0, n, C, U, [&](int row, int col, const float* o) {
+    const uint32_t h0 = pack_bf16x2(o[0], o[1]), h1 = pack_bf16x2(o[2], o[3]);
+    const uint32_t l0 = pack_bf16x2(o[0] - bf16_lo(h0), o[1] - bf16_hi(h0));
+    const uint32_t l1 = pack_bf16x2(o[2] - bf16_lo(h1), o[3] - bf16_hi(h1));
+    bf16* yr = yb + (size_t)row * 3 * C + col;
+    *reinterpret_cast<uint2*>(yr) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(yr + C) = make_uint2(l0, l1);
+    *reinterpret_cast<uint2*>(yr + 2 * C) = make_uint2(h0, h1);
+  });
 }
 
 // bf16x3 split of an fp32 matrix x [R, C] (row stride ldx) into out bf16 [R, 3C]:
@@ -389,10 +300,10 @@ extern "C" int mvuld_rs_gcn_affinity_f32(const float* tpg, void* y3, float* r_ou
   MV_CHECK_ARG(C % 64 == 0, "rs_gcn_affinity_f32: C %% 64");
   if (B <= 0) return 0;
   static const bool col_split = getenv("MVULD_AFFINITY_COLSPLIT") != nullptr;       // A/B hook: the earlier kernel
-  if (C % RS_GCH == 0 && !col_split) {
+  if (C % AR_GCH == 0 && !col_split) {
     auto kern = rs_gcn_affinity_rows_kernel;
-    MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_ROWS_SMEM));
-    kern<<<dim3(B, (n + RS_ROWS - 1) / RS_ROWS), 256, RS_ROWS_SMEM, stream>>>(tpg, reinterpret_cast<bf16*>(y3), r_out, n, C);
+    MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
+    kern<<<dim3(B, (n + AR_ROWS - 1) / AR_ROWS), 256, AR_SMEM_BYTES, stream>>>(tpg, reinterpret_cast<bf16*>(y3), r_out, n, C);
     MV_LAUNCH_OK();
     return 0;
   }

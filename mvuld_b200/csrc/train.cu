@@ -7,6 +7,9 @@
 // l2norm / mean / cross-entropy head, and the clipped AdamW update (optimizer.py:11-33, config.py:157).
 // Gradients of activations travel in bf16 (GEMM operands) or fp32 (residual stream, BatchNorm), parameter
 // gradients and optimiser state in fp32.
+#include <cstdlib>
+
+#include "affinity_rows.cuh"
 #include "common.cuh"
 #include "host_util.h"
 
@@ -648,6 +651,42 @@ __device__ void aff_sy(const float* __restrict__ S, const bf16* __restrict__ Y, 
     __syncthreads();
   }
 }
+// Row-split backward (affinity_rows.cuh): CTA (b, s) owns rows [25 s, 25 s + 25) of dg, dtheta and dphi and forms the
+// three 25 x n blocks it needs itself -- (R^T) rows = phi rows . theta^T / n, dS rows = dy rows . g^T / n, (dS^T) rows =
+// g rows . dy^T / n -- one product pair per CTA (blockIdx.z), 2.6 M FMA each, where a CTA of the column-split kernel
+// below spends 14.1 M (both n x n matrices in every CTA).
+__global__ void __launch_bounds__(256)
+rs_gcn_affinity_bwd_rows_kernel(const bf16* __restrict__ tpg, const bf16* __restrict__ dy, bf16* __restrict__ dtpg,
+                                int n, int C) {
+  extern __shared__ __align__(16) float smr[];
+  float* Rs = smr;
+  float* U = Rs + AR_ROWS * AR_MAXN;
+  const int b = blockIdx.x;
+  const int r0 = blockIdx.y * AR_ROWS;
+  const bf16* th = tpg + (size_t)b * n * 3 * C;
+  const bf16* ph = th + C;
+  const bf16* gg = th + 2 * C;
+  const bf16* dyb = dy + (size_t)b * n * C;
+  bf16* dth = dtpg + (size_t)b * n * 3 * C;
+  const float inv = 1.0f / (float)n;
+  const int ldo = 3 * C;
+  auto store_to = [&](bf16* outp) {
+    return [=](int row, int col, const float* o) {
+      *reinterpret_cast<uint2*>(outp + (size_t)row * ldo + col) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    };
+  };
+  // blockIdx.z picks one of the three independent products, so that 32 graphs give 384 CTAs instead of 128
+  if (blockIdx.z == 0) {
+    ar_nt<bf16>(ph, 3 * C, r0, th, 3 * C, n, C, inv, Rs, U);           // (R^T)[j][i] = phi_j . theta_i / n
+    ar_sy<bf16>(Rs, dyb, C, r0, n, C, U, store_to(dth + 2 * C));       // dg     = R^T dy
+  } else if (blockIdx.z == 1) {
+    ar_nt<bf16>(dyb, C, r0, gg, 3 * C, n, C, inv, Rs, U);              // dS[i][j] = dy_i . g_j / n
+    ar_sy<bf16>(Rs, ph, 3 * C, r0, n, C, U, store_to(dth));            // dtheta = dS phi
+  } else {
+    ar_nt<bf16>(gg, 3 * C, r0, dyb, C, n, C, inv, Rs, U);              // (dS^T)[j][i] = g_j . dy_i / n
+    ar_sy<bf16>(Rs, th, 3 * C, r0, n, C, U, store_to(dth + C));        // dphi   = dS^T theta
+  }
+}
 __global__ void __launch_bounds__(256)
 rs_gcn_affinity_bwd_kernel(const bf16* __restrict__ tpg, const bf16* __restrict__ dy, bf16* __restrict__ dtpg, int n,
                            int C) {
@@ -931,6 +970,13 @@ extern "C" int mvuld_rs_gcn_affinity_bwd(const void* tpg, const void* dy, void* 
                                          cudaStream_t stream) {
   MV_CHECK_ARG(n >= 1 && n <= AB_N && C % 64 == 0, "rs_gcn_affinity_bwd: n in [1, %d], C %% 64", AB_N);
   if (B <= 0) return 0;
+  static const bool col_split = getenv("MVULD_AFFINITY_COLSPLIT") != nullptr;       // A/B hook: the earlier kernel
+  if (C % AR_GCH == 0 && !col_split) {
+    MV_CUDA_OK(cudaFuncSetAttribute(rs_gcn_affinity_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
+    rs_gcn_affinity_bwd_rows_kernel<<<dim3(B, (n + AR_ROWS - 1) / AR_ROWS, 3), 256, AR_SMEM_BYTES, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dtpg), n, C);
+    MV_LAUNCH_OK();
+    return 0;
+  }
   const int smem = (2 * AB_N * (AB_N + 1) + AB_N * 64 + AB_N * 33) * sizeof(float);
   MV_CUDA_OK(cudaFuncSetAttribute(rs_gcn_affinity_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   rs_gcn_affinity_bwd_kernel<<<dim3(B, B >= 148 ? 2 : 4), 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dtpg), n, C);
