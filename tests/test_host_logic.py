@@ -333,3 +333,27 @@ def test_ablation_variants_surface_and_oracle(name):
     assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (got, ref)
     with pytest.raises(RuntimeError):                     # the product path has no CPU fallback
         m(g, img, txt)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port, no GPU): one JSON line with the base contract's keys, the
+    reference arm's `impl`, `cpu_baseline` and a zero-copy `e2e`; under torchrun only rank 0 prints."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "ggnn", "--steps", "1",
+           "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "graphs/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
