@@ -1,6 +1,8 @@
 // HBM-bound row kernels of the image and text branches: LayerNorm (+ residual, both post- and pre-norm forms),
 // patch embedding, patch-merge gather, final LN + token mean, RoBERTa embeddings, masked mean pooling.
 // One warp owns one row; 128-bit loads/stores; statistics in fp32 (two-pass in registers, like torch).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -22,7 +24,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // mode 0: x = LN(y)                       (PatchMerging.norm, swin_transformer_v2.py:362)
 // mode 1: x = shortcut + LN(y)            (res-post-norm, swin_transformer_v2.py:301,304)
 // mode 2: x = LN(y + shortcut)            (RoBERTa post-LN blocks, HF RobertaSelfOutput / RobertaOutput)
-__global__ void __launch_bounds__(256)
+// UNITS = 8-element units per lane the instantiation holds in registers (C <= 256 UNITS): C = 512 rows need 16 values per
+// lane, not the 32 of the C = 1024 case -- 60 registers and 4 blocks per SM become <= 51 / 5.
+template <int UNITS>
+__global__ void __launch_bounds__(256, UNITS <= 2 ? 5 : 4)
 ln_rows_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, const float* __restrict__ gamma,
                const float* __restrict__ beta, float* __restrict__ x32, bf16* __restrict__ xb, int M, int C, float eps,
                int mode) {
@@ -30,10 +35,10 @@ ln_rows_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, c
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int units = C >> 3;
-  float v[LN_MAX_UNITS][8];
+  float v[UNITS][8];
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_UNITS; ++k) {
+  for (int k = 0; k < UNITS; ++k) {
     const int u = lane + k * 32;
     if (u < units) {
       uint4 raw = __ldg(reinterpret_cast<const uint4*>(y + (size_t)row * C) + u);
@@ -51,7 +56,7 @@ ln_rows_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, c
   const float mean = warp_sum(sum) / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_UNITS; ++k) {
+  for (int k = 0; k < UNITS; ++k) {
     if (lane + k * 32 < units) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -62,7 +67,7 @@ ln_rows_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, c
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
 #pragma unroll
-  for (int k = 0; k < LN_MAX_UNITS; ++k) {
+  for (int k = 0; k < UNITS; ++k) {
     const int u = lane + k * 32;
     if (u < units) {
       const float4* gp = reinterpret_cast<const float4*>(gamma + u * 8);
@@ -347,8 +352,14 @@ extern "C" int mvuld_ln_rows(const void* y, const float* shortcut, const float* 
   MV_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * LN_MAX_UNITS, "ln_rows: C=%d must be a multiple of 8 and <= 1024", C);
   MV_CHECK_ARG(mode == 0 || shortcut, "ln_rows: mode %d needs a shortcut", mode);
   if (M <= 0) return 0;
-  ln_rows_kernel<<<(M + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const bf16*>(y), shortcut, gamma, beta, x32,
-                                                  reinterpret_cast<bf16*>(xb), M, C, eps, mode);
+  const bf16* yp = reinterpret_cast<const bf16*>(y);
+  bf16* xp = reinterpret_cast<bf16*>(xb);
+  const int grid = (M + 7) / 8;
+  static const bool wide = getenv("MVULD_LN_WIDE") != nullptr;                 // A/B hook: the 4-unit instantiation for every C
+  if (C <= 256 && !wide) ln_rows_kernel<1><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
+  else if (C <= 512 && !wide) ln_rows_kernel<2><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
+  else if (C <= 768 && !wide) ln_rows_kernel<3><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
+  else ln_rows_kernel<4><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
   MV_LAUNCH_OK();
   return 0;
 }
