@@ -48,6 +48,23 @@ def position_ids(ids: torch.Tensor, pad: int) -> torch.Tensor:
 def encode(sd: Dict[str, torch.Tensor], geo: RobertaGeometry, ids: torch.Tensor, prefix: str = "",
            key_mask_only: bool = False):
     """-> (token_embeddings [B,L,H], sentence_embeddings [B,H]); unixcoder.py:33-38."""
+    return _encode(sd, geo, ids, prefix, key_mask_only)
+
+
+def sentence_and_grads(sd: Dict[str, torch.Tensor], geo: RobertaGeometry, ids: torch.Tensor, cotangent: torch.Tensor,
+                       prefix: str = "encoder."):
+    """Backward oracle of the text branch (the "whole path trainable" reading of configs[4]): fp32
+    autograd through the restated encoder + masked mean -> (sentence vectors [B, H], {parameter name: gradient of
+    <vectors, cotangent>}).  Dropout 0.  Pinned against autograd through the installed HF RobertaModel
+    (tests/golden/roberta_train.pt); the pooler takes no part in get_repr and gets no gradient."""
+    leaf = {k: v.detach().float().clone().requires_grad_(True) for k, v in sd.items()
+            if k.startswith(prefix) and torch.is_floating_point(v)}
+    sent = _encode(leaf, geo, ids, prefix, False)[1]
+    (sent * cotangent.float()).sum().backward()
+    return sent.detach(), {k: v.grad.detach() for k, v in leaf.items() if v.grad is not None}
+
+
+def _encode(sd, geo, ids, prefix, key_mask_only):
     g = lambda k: sd[prefix + k].float()
     B, L = ids.shape
     Hd, nH = geo.hidden_size, geo.num_attention_heads

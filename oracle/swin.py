@@ -171,11 +171,8 @@ def patch_embed(sd, x, geo: SwinGeometry):
     return F.layer_norm(y, (geo.embed_dim,), sd["patch_embed.norm.weight"], sd["patch_embed.norm.bias"])
 
 
-@torch.no_grad()
-def forward_features(sd: Dict[str, torch.Tensor], geo: SwinGeometry, x: torch.Tensor,
-                     taps: Optional[dict] = None) -> torch.Tensor:
-    """swin_transformer_v2.py:623-635 -> [B, num_features]."""
-    sd = {k: v.float() for k, v in sd.items() if torch.is_floating_point(v)}
+def _forward_features(sd, geo: SwinGeometry, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+    """Differentiable body of forward_features (sd already fp32)."""
     x = patch_embed(sd, x.float(), geo)
     if taps is not None:
         taps["patch_embed"] = x.clone()
@@ -191,6 +188,27 @@ def forward_features(sd: Dict[str, torch.Tensor], geo: SwinGeometry, x: torch.Te
     C = x.shape[-1]
     x = F.layer_norm(x, (C,), sd["norm.weight"], sd["norm.bias"])
     return x.mean(dim=1)
+
+
+@torch.no_grad()
+def forward_features(sd: Dict[str, torch.Tensor], geo: SwinGeometry, x: torch.Tensor,
+                     taps: Optional[dict] = None) -> torch.Tensor:
+    """swin_transformer_v2.py:623-635 -> [B, num_features]."""
+    sd = {k: v.float() for k, v in sd.items() if torch.is_floating_point(v)}
+    return _forward_features(sd, geo, x, taps)
+
+
+def features_and_grads(sd: Dict[str, torch.Tensor], geo: SwinGeometry, x: torch.Tensor, cotangent: torch.Tensor):
+    """Backward oracle of the image branch (the "whole path trainable" reading of configs[4]):
+    fp32 autograd through the restated forward (DropPath / dropout rates 0, as in the pinned test cases) ->
+    (features [B, num_features], {parameter name: d <features, cotangent> / d parameter}, d / d image).
+    Pinned against autograd through the reference module (tests/golden/swin_train.pt)."""
+    leaf = {k: v.detach().float().clone().requires_grad_(True) for k, v in sd.items() if torch.is_floating_point(v)}
+    xin = x.detach().float().clone().requires_grad_(True)
+    feats = _forward_features(leaf, geo, xin)
+    (feats * cotangent.float()).sum().backward()
+    grads = {k: v.grad.detach() for k, v in leaf.items() if v.grad is not None}
+    return feats.detach(), grads, xin.grad.detach()
 
 
 @torch.no_grad()

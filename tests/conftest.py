@@ -28,4 +28,4 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import torch
     return {n: torch.load(os.path.join(GOLDEN, n + ".pt"), weights_only=False)
-            for n in ("swin", "rs_gcn", "roberta", "graph")}
+            for n in ("swin", "rs_gcn", "roberta", "graph", "swin_train", "roberta_train")}

@@ -26,6 +26,57 @@ def test_swin_oracle_matches_reference(golden, name):
     assert torch.allclose(logits, golden["swin"][name]["logits"], rtol=1e-4, atol=2e-5)
 
 
+def test_swin_backward_oracle_matches_reference_autograd(golden):
+    """oracle.swin.features_and_grads (the checker of the encoder-backward kernels to come, SURVEY.md 8d row 4 primary)
+    against autograd through the unmodified reference module (tools/make_golden.py swin_train): every parameter
+    gradient's norm and 32 sampled entries, and the image gradient."""
+    g = golden["swin_train"]
+    name = "small_ws7"
+    model = cases.make_swin(name)
+    x = synth.images(2, cases.SWIN_CASES[name]["img_size"], seed=cases.SEED + 21)
+    feats, grads, dx = swin.features_and_grads(model.state_dict(), cases.swin_geometry(name), x, g["cotangent"])
+    assert torch.allclose(feats, g["features"], rtol=1e-4, atol=2e-5)
+    assert set(grads) == set(g["grads"]), set(grads) ^ set(g["grads"])
+
+    def check(mine, ref, what):
+        f = mine.reshape(-1)
+        assert f.numel() == ref["numel"], what
+        scale = max(ref["norm"] / max(ref["numel"], 1) ** 0.5, 1e-12)              # rms of the reference gradient
+        assert abs(float(f.double().norm()) - ref["norm"]) <= 2e-4 * ref["norm"] + 1e-9, (what, float(f.norm()), ref["norm"])
+        stride = max(1, f.numel() // 16)
+        assert float((f[:16] - ref["head"]).abs().max()) <= 2e-3 * scale + 1e-7, what
+        assert float((f[::stride][:16] - ref["strided"]).abs().max()) <= 2e-3 * scale + 1e-7, what
+
+    for k, r in g["grads"].items():
+        check(grads[k], r, k)
+    check(dx, g["dx"], "d/d image")
+    # the pieces the backward kernels will have to produce are all there and non-trivial
+    for k in ("layers.0.blocks.0.attn.logit_scale", "layers.0.blocks.1.attn.cpb_mlp.2.weight", "layers.1.blocks.0.attn.q_bias",
+              "layers.0.downsample.reduction.weight", "patch_embed.proj.weight"):
+        assert g["grads"][k]["norm"] > 0, k
+
+
+def test_roberta_backward_oracle_matches_hf_autograd(golden):
+    """oracle.roberta.sentence_and_grads against autograd through the installed HF RobertaModel (make_golden.py
+    roberta_train): every encoder parameter that reaches the masked-mean sentence vector."""
+    g = golden["roberta_train"]
+    m = cases.make_roberta()
+    cfg = m.config
+    ids = synth.token_ids(cases.ROBERTA_BATCH, cases.ROBERTA_L, cfg.vocab_size, seed=cases.SEED + 31)
+    sent, grads = roberta.sentence_and_grads(m.state_dict(), cases.roberta_geometry(cfg), ids, g["cotangent"])
+    assert torch.allclose(sent, g["sent"], rtol=1e-4, atol=1e-5)
+    assert set(grads) == set(g["grads"]), set(grads) ^ set(g["grads"])
+    for k, ref in g["grads"].items():
+        f = grads[k].reshape(-1)
+        assert f.numel() == ref["numel"], k
+        scale = max(ref["norm"] / max(ref["numel"], 1) ** 0.5, 1e-12)
+        assert abs(float(f.double().norm()) - ref["norm"]) <= 2e-4 * ref["norm"] + 1e-9, (k, float(f.norm()), ref["norm"])
+        stride = max(1, f.numel() // 16)
+        assert float((f[:16] - ref["head"]).abs().max()) <= 2e-3 * scale + 1e-7, k
+        assert float((f[::stride][:16] - ref["strided"]).abs().max()) <= 2e-3 * scale + 1e-7, k
+    assert not any("pooler" in k for k in grads)
+
+
 def test_swin_integer_artefacts_match_reference(golden):
     g = golden["swin"]
     rpi = swin.relative_position_index(28)

@@ -98,6 +98,35 @@ def golden_swin():
         sys.modules.pop(k, None)
 
 
+def golden_swin_train():
+    """Autograd through the UNMODIFIED reference SwinV2 module (small_ws7 case, DropPath / dropout inactive): pins the
+    backward oracle oracle.swin.features_and_grads that the encoder-backward kernels will be checked against.  Per
+    parameter: gradient norm, the first 16 entries and 16 strided samples; d/d image as norm + samples."""
+    _shim_timm()
+    ref = _load(os.path.join(REF, "mvuld/models/swin_transformer_v2.py"), "ref_swin_v2_train")
+    name = "small_ws7"
+    kw = cases.SWIN_CASES[name]
+    model = cases.make_swin(name)
+    ref_model = ref.SwinTransformerV2(**kw).eval()
+    ref_model.load_state_dict(model.state_dict(), strict=True)
+    x = synth.images(2, kw["img_size"], seed=cases.SEED + 21).requires_grad_(True)
+    feats = ref_model.forward_features(x)
+    cot = torch.randn(feats.shape, generator=torch.Generator().manual_seed(cases.SEED + 22))
+    (feats * cot).sum().backward()
+
+    def pack(g):
+        f = g.detach().reshape(-1)
+        stride = max(1, f.numel() // 16)
+        return dict(norm=float(f.double().norm()), head=f[:16].clone(), strided=f[::stride][:16].clone(), numel=f.numel())
+
+    out = dict(cotangent=cot, features=feats.detach().clone(), dx=pack(x.grad),
+               grads={k: pack(p.grad) for k, p in ref_model.named_parameters() if p.grad is not None})
+    torch.save(out, os.path.join(OUT, "swin_train.pt"))
+    print("swin_train", len(out["grads"]), "parameter gradients; |dx|", out["dx"]["norm"])
+    for k in ("timm", "timm.models", "timm.models.layers"):
+        sys.modules.pop(k, None)
+
+
 @torch.no_grad()
 def golden_rs_gcn():
     ref = _load(os.path.join(REF, "mvuld/models/Rs_GCN.py"), "ref_rs_gcn")
@@ -156,6 +185,39 @@ def golden_roberta():
     print("roberta sent", tuple(sent.shape), float(sent.abs().mean()))
 
 
+def golden_roberta_train():
+    """Autograd through the installed HF RobertaModel (encoder mode, key mask; dropout 0) of <masked-mean sentence
+    vectors, cotangent>: pins oracle.roberta.sentence_and_grads.  Per parameter: norm + 32 samples."""
+    from transformers import RobertaConfig, RobertaModel
+    cfg = cases.roberta_small_config()
+    hf_cfg = RobertaConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
+                           num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                           intermediate_size=cfg.intermediate_size,
+                           max_position_embeddings=cfg.max_position_embeddings, type_vocab_size=cfg.type_vocab_size,
+                           pad_token_id=cfg.pad_token_id, layer_norm_eps=cfg.layer_norm_eps,
+                           hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, is_decoder=False)
+    hf = RobertaModel(hf_cfg, add_pooling_layer=True).eval()
+    mine = cases.make_roberta()
+    sd = {k[len("encoder."):]: v for k, v in mine.state_dict().items() if k.startswith("encoder.")}
+    hf.load_state_dict(sd, strict=False)
+    ids = synth.token_ids(cases.ROBERTA_BATCH, cases.ROBERTA_L, cfg.vocab_size, seed=cases.SEED + 31)
+    mask = ids.ne(cfg.pad_token_id)
+    tok = hf(ids, attention_mask=mask.long())[0]
+    sent = (tok * mask.unsqueeze(-1)).sum(1) / mask.sum(-1).unsqueeze(-1)
+    cot = torch.randn(sent.shape, generator=torch.Generator().manual_seed(cases.SEED + 32))
+    (sent * cot).sum().backward()
+
+    def pack(g):
+        f = g.detach().reshape(-1)
+        stride = max(1, f.numel() // 16)
+        return dict(norm=float(f.double().norm()), head=f[:16].clone(), strided=f[::stride][:16].clone(), numel=f.numel())
+
+    out = dict(cotangent=cot, sent=sent.detach().clone(),
+               grads={"encoder." + k: pack(p.grad) for k, p in hf.named_parameters() if p.grad is not None})
+    torch.save(out, os.path.join(OUT, "roberta_train.pt"))
+    print("roberta_train", len(out["grads"]), "parameter gradients")
+
+
 @torch.no_grad()
 def golden_graph():
     """Oracle-generated (drift guard only): integer artefacts + fusion / GGNN outputs on small seeded batches."""
@@ -189,7 +251,15 @@ if __name__ == "__main__":
     if "rs_gcn_train" in sys.argv[1:]:
         golden_rs_gcn_train()
         sys.exit(0)
+    if "swin_train" in sys.argv[1:] or "roberta_train" in sys.argv[1:]:
+        if "swin_train" in sys.argv[1:]:
+            golden_swin_train()
+        if "roberta_train" in sys.argv[1:]:
+            golden_roberta_train()
+        sys.exit(0)
     golden_rs_gcn_train()
+    golden_swin_train()
+    golden_roberta_train()
     golden_swin()
     golden_rs_gcn()
     golden_roberta()
