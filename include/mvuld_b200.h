@@ -231,6 +231,16 @@ int mvuld_bn_slot_fwd(const void* x, const float* gamma, const float* beta, floa
                       mvuld_stream_t stream);
 int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
                       void* dx, float* dgamma, float* dbeta, int B, int n, int F, mvuld_stream_t stream);
+/* First row kernels of the encoder backward (the "whole path trainable" reading of configs[4]; not yet driven by a
+ * trainer).  LayerNorm backward of the three mvuld_ln_rows forms: dout fp32 [M,C] = gradient of the LN output (mode 1:
+ * the block output's gradient, which is also the shortcut's); the LN input is recomputed from y (bf16) (+ shortcut in
+ * mode 2); dv = gradient of the LN input as bf16 and / or fp32; dgamma / dbeta accumulated.  swin_transformer_v2.py:301,
+ * 304,362; HF RobertaSelfOutput / RobertaOutput. */
+int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const float* gamma, const float* dout, void* dv_bf16,
+                      float* dv_f32, float* dgamma, float* dbeta, int M, int C, float eps, int mode,
+                      mvuld_stream_t stream);
+/* exact (erf) GELU backward: dpre = dh * GELU'(pre), bf16, n %% 8 == 0 (Mlp, swin_transformer_v2.py:26-32). */
+int mvuld_gelu_bwd(const void* pre, const void* dh, void* dpre, long long n, mvuld_stream_t stream);
 /* fp32 strided ELU backward with a bf16 result (image / text projections, GraphModel.py:153-159). */
 int mvuld_elu_bwd_rows(const float* dy, int ldy, const float* y, int ldyy, void* dx, int ldx, int R, int C,
                        mvuld_stream_t stream);

@@ -56,6 +56,8 @@ SIGNATURES = {
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_transpose_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "mvuld_colsum": [_P, _I, _I, _P, _I, _I, _P],
+    "mvuld_ln_rows_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "mvuld_gelu_bwd": [_P, _P, _P, _LL, _P],
     "mvuld_elu_bwd": [_P, _P, _P, _LL, _I, C.c_ulonglong, _F, _P],
     "mvuld_dropout_bf16": [_P, _P, _LL, C.c_ulonglong, _F, _P],
     "mvuld_bn_cols_fwd": [_P, _P, _P, _F, _P, _I, _P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P],

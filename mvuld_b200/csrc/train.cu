@@ -7,6 +7,7 @@
 // l2norm / mean / cross-entropy head, and the clipped AdamW update (optimizer.py:11-33, config.py:157).
 // Gradients of activations travel in bf16 (GEMM operands) or fp32 (residual stream, BatchNorm), parameter
 // gradients and optimiser state in fp32.
+#include <algorithm>
 #include <cstdlib>
 
 #include "affinity_rows.cuh"
@@ -546,6 +547,148 @@ gat_attn_grad_kernel(const bf16* __restrict__ z, const float* __restrict__ del, 
   atomicAdd(dar + col, sr);
 }
 
+// ------------------------------------- encoder backward row kernels (first pieces) -------------------------------------
+// LayerNorm backward of the three forward forms of mvuld_ln_rows (mode 0: x = LN(y); 1: x = shortcut + LN(y), SwinV2
+// res-post-norm, swin_transformer_v2.py:301,304; 2: x = LN(y + shortcut), RoBERTa).  The LN input v (y, or y + shortcut
+// in mode 2) is recomputed from what the forward already keeps (y bf16, shortcut fp32): no saved statistics.
+//   xhat = (v - mean) rstd;  g = dout gamma;  dv = rstd (g - mean(g) - xhat mean(g xhat));
+//   dgamma += sum_rows dout xhat;  dbeta += sum_rows dout
+// One warp walks rows (grid-stride), lane owns 8-element units; the per-lane column sums stay in registers over all
+// rows of the warp, are combined over the 8 warps of the block in shared memory and leave as one atomicAdd per column
+// and block (grid capped at 2 blocks per SM).  dv is written as bf16 (the operand of the dense backward) and / or fp32
+// (mode 2: it is also the shortcut's gradient); the residual gradient of mode 1 is dout itself and needs no kernel.
+template <int UNITS>
+__global__ void __launch_bounds__(256)
+ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, const float* __restrict__ gamma,
+                   const float* __restrict__ dout, bf16* __restrict__ dvb, float* __restrict__ dv32,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C, float eps, int mode) {
+  extern __shared__ float red[];                  // [8 warps][2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = C >> 3;
+  float dg[UNITS][8], db[UNITS][8];
+#pragma unroll
+  for (int k = 0; k < UNITS; ++k)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dg[k][q] = db[k][q] = 0.f;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    float v[UNITS][8], g[UNITS][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < UNITS; ++k) {
+      const int u = lane + k * 32;
+      if (u < units) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(y + (size_t)row * C) + u);
+        v[k][0] = bf16_lo(raw.x); v[k][1] = bf16_hi(raw.x); v[k][2] = bf16_lo(raw.y); v[k][3] = bf16_hi(raw.y);
+        v[k][4] = bf16_lo(raw.z); v[k][5] = bf16_hi(raw.z); v[k][6] = bf16_lo(raw.w); v[k][7] = bf16_hi(raw.w);
+        if (mode == 2) {
+          const float4* sp = reinterpret_cast<const float4*>(shortcut + (size_t)row * C + u * 8);
+          const float4 a = __ldg(sp), b = __ldg(sp + 1);
+          v[k][0] += a.x; v[k][1] += a.y; v[k][2] += a.z; v[k][3] += a.w;
+          v[k][4] += b.x; v[k][5] += b.y; v[k][6] += b.z; v[k][7] += b.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += v[k][q];
+      }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < UNITS; ++k)
+      if (lane + k * 32 < units) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float d = v[k][q] - mean;
+          sq += d * d;
+        }
+      }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < UNITS; ++k) {
+      const int u = lane + k * 32;
+      if (u < units) {
+        const float4* dp = reinterpret_cast<const float4*>(dout + (size_t)row * C + u * 8);
+        const float4* gp = reinterpret_cast<const float4*>(gamma + u * 8);
+        const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), g0 = __ldg(gp), g1 = __ldg(gp + 1);
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float xh = (v[k][q] - mean) * rstd;
+          v[k][q] = xh;
+          g[k][q] = d[q] * gm[q];
+          s1 += g[k][q];
+          s2 += g[k][q] * xh;
+          dg[k][q] += d[q] * xh;
+          db[k][q] += d[q];
+        }
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int k = 0; k < UNITS; ++k) {
+      const int u = lane + k * 32;
+      if (u < units) {
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = rstd * (g[k][q] - m1 - v[k][q] * m2);
+        if (dv32) {
+          float4* op = reinterpret_cast<float4*>(dv32 + (size_t)row * C + u * 8);
+          op[0] = make_float4(o[0], o[1], o[2], o[3]);
+          op[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (dvb) {
+          uint4 w;
+          w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+          w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+          reinterpret_cast<uint4*>(dvb + (size_t)row * C)[u] = w;
+        }
+      }
+    }
+  }
+  // column sums: 8 warps -> shared memory -> one atomicAdd per column and block
+#pragma unroll
+  for (int k = 0; k < UNITS; ++k) {
+    const int u = lane + k * 32;
+    if (u < units) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        red[(warp * 2 + 0) * C + u * 8 + q] = dg[k][q];
+        red[(warp * 2 + 1) * C + u * 8 + q] = db[k][q];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) {
+      a += red[(w8 * 2 + 0) * C + c];
+      b += red[(w8 * 2 + 1) * C + c];
+    }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+// exact (erf) GELU backward, nn.GELU default (swin_transformer_v2.py:26-32 Mlp, HF "gelu"): dpre = dh (Phi(x) + x phi(x))
+__global__ void gelu_bwd_kernel(const bf16* __restrict__ pre, const bf16* __restrict__ dh, bf16* __restrict__ dpre,
+                                long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 xr = __ldg(reinterpret_cast<const uint4*>(pre) + i), dr = __ldg(reinterpret_cast<const uint4*>(dh) + i);
+    const uint32_t xs[4] = {xr.x, xr.y, xr.z, xr.w}, ds[4] = {dr.x, dr.y, dr.z, dr.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x0 = bf16_lo(xs[q]), x1 = bf16_hi(xs[q]);
+      const float c0 = 0.5f * (1.0f + erff(x0 * 0.70710678118654752f)) + x0 * 0.3989422804014327f * __expf(-0.5f * x0 * x0);
+      const float c1 = 0.5f * (1.0f + erff(x1 * 0.70710678118654752f)) + x1 * 0.3989422804014327f * __expf(-0.5f * x1 * x1);
+      o[q] = pack_bf16x2(bf16_lo(ds[q]) * c0, bf16_hi(ds[q]) * c1);
+    }
+    reinterpret_cast<uint4*>(dpre)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // --------------------------------------------- Rs_GCN affinity backward ---------------------------------------------
 // Per graph (n <= 100 slots, C features): theta, phi, g = column blocks of tpg bf16 [n, 3C]; dy bf16 [n, C].
 //   R = theta phi^T / n;  dg = R^T dy;  dS = dy g^T / n;  dtheta = dS phi;  dphi = dS^T theta   -> dtpg bf16 [n, 3C]
@@ -912,6 +1055,37 @@ extern "C" int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gam
                                  const float* rstd, void* dx, float* dgamma, float* dbeta, int B, int n, int F,
                                  cudaStream_t stream) {
   bn_slot_bwd_kernel<<<n, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dy), gamma, mean, rstd, reinterpret_cast<bf16*>(dx), dgamma, dbeta, B, n, F);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const float* gamma, const float* dout, void* dv_bf16,
+                                 float* dv_f32, float* dgamma, float* dbeta, int M, int C, float eps, int mode,
+                                 cudaStream_t stream) {
+  MV_CHECK_ARG(C % 8 == 0 && C <= 1024, "ln_rows_bwd: C=%d must be a multiple of 8 and <= 1024", C);
+  MV_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || shortcut), "ln_rows_bwd: mode %d (mode 2 needs the shortcut)", mode);
+  MV_CHECK_ARG(dgamma && dbeta && (dv_bf16 || dv_f32), "ln_rows_bwd: dgamma / dbeta and one of the dv outputs are required");
+  if (M <= 0) return 0;
+  const int grid = std::min((M + 7) / 8, 2 * num_sms());
+  const size_t smem = (size_t)16 * C * sizeof(float);
+  const bf16* yp = reinterpret_cast<const bf16*>(y);
+  bf16* dvp = reinterpret_cast<bf16*>(dv_bf16);
+#define MV_LN_BWD(U)                                                                                                   \
+  do {                                                                                                                 \
+    MV_CUDA_OK(cudaFuncSetAttribute(ln_rows_bwd_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    ln_rows_bwd_kernel<U><<<grid, 256, smem, stream>>>(yp, shortcut, gamma, dout, dvp, dv_f32, dgamma, dbeta, M, C, eps, mode); \
+  } while (0)
+  if (C <= 256) MV_LN_BWD(1);
+  else if (C <= 512) MV_LN_BWD(2);
+  else if (C <= 768) MV_LN_BWD(3);
+  else MV_LN_BWD(4);
+#undef MV_LN_BWD
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_gelu_bwd(const void* pre, const void* dh, void* dpre, long long n, cudaStream_t stream) {
+  MV_CHECK_ARG(n % 8 == 0, "gelu_bwd: n %% 8");
+  if (n <= 0) return 0;
+  gelu_bwd_kernel<<<GRID1(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(pre), reinterpret_cast<const bf16*>(dh), reinterpret_cast<bf16*>(dpre), n / 8);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -182,6 +182,50 @@ def test_rs_gcn_affinity_backward(B, n, C):
     assert rel_err(out, t.grad) < 1e-2
 
 
+@pytest.mark.parametrize("M,C,mode", [(300, 512, 1), (77, 128, 0), (500, 768, 2), (64, 1024, 1), (9, 256, 2)])
+def test_ln_rows_backward_matches_autograd(M, C, mode):
+    """mvuld_ln_rows_bwd against autograd of the three forward forms of mvuld_ln_rows (first encoder-backward piece)."""
+    r = gen(50 + C + mode)
+    y = (torch.randn(M, C, generator=r) * 1.5 + 0.3).to(torch.bfloat16)
+    sc = torch.randn(M, C, generator=r)
+    gamma, beta = torch.randn(C, generator=r) * 0.3 + 1.0, torch.randn(C, generator=r) * 0.1
+    dout = torch.randn(M, C, generator=r)
+    yr = y.float().requires_grad_(True)
+    scr = sc.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ln = lambda t: torch.nn.functional.layer_norm(t, (C,), gr, br, 1e-5)
+    out = ln(yr) if mode == 0 else (scr + ln(yr) if mode == 1 else ln(yr + scr))
+    out.backward(dout)
+    dvb = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    dv32 = torch.empty(M, C, device=DEV)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    _lib.call("mvuld_ln_rows_bwd", y.to(DEV), sc.to(DEV) if mode else None, gamma.to(DEV), dout.to(DEV), dvb, dv32, dg, db,
+              M, C, 1e-5, mode)
+    torch.cuda.synchronize()
+    assert rel_err(dv32, yr.grad) < 1e-4
+    assert rel_err(dvb, yr.grad) < 6e-3                     # bf16 rounding of the same values
+    assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    if mode == 2:
+        assert rel_err(dv32, scr.grad) < 1e-4               # LN(y + shortcut): the shortcut's gradient is dv
+    # accumulation semantics: a second call adds to dgamma / dbeta
+    _lib.call("mvuld_ln_rows_bwd", y.to(DEV), sc.to(DEV) if mode else None, gamma.to(DEV), dout.to(DEV), dvb, None, dg, db,
+              M, C, 1e-5, mode)
+    assert rel_err(dg, 2 * gr.grad) < 1e-4
+
+
+def test_gelu_backward_matches_autograd():
+    r = gen(61)
+    n = 8 * 1000
+    pre = (torch.randn(n, generator=r) * 2.0).to(torch.bfloat16)
+    dh = torch.randn(n, generator=r).to(torch.bfloat16)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(dh.float())
+    dpre = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    _lib.call("mvuld_gelu_bwd", pre.to(DEV), dh.to(DEV), dpre, n)
+    torch.cuda.synchronize()
+    assert rel_err(dpre, x.grad) < 5e-3
+
+
 def test_head_kernels_l2norm_ce_linear():
     B, n, D = 5, 100, 512
     r = gen(8)
