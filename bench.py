@@ -10,11 +10,15 @@ functions per GPU.  Functions are independent, so ranks shard the batch with no 
 ``--batch`` functions per GPU).  ``--workload swin`` / ``ggnn`` time configs[1] / configs[2] instead, and
 ``--workload train`` times configs[4]: the reference-faithful training step (frozen SwinV2 / UniXcoder forward, fusion
 model forward + backward, bucketed NCCL gradient all-reduce over the ranks, clipped AdamW), 32 functions per GPU.  The
-default (``full``) line also carries a ``"train"`` object with that step's throughput at the same N.
+default (``full``) line also carries sub-objects measured in the same run at the same N: ``"train"`` (configs[4]),
+``"swin"`` (configs[1]) and ``"ggnn"`` (configs[2]) with their own roofline, ``"padded_text"`` (the text branch on the
+tokenizer's padded [B, 512] rows) and ``"job"`` (configs[3] as written: 25 816 functions sharded over the ranks by
+cost with a short last batch, strong scaling).  ``--workload job`` prints the job as its own line.
 
 One JSON line is printed by rank 0 (contract in the task statement): value = whole-job functions/s with inputs
 resident in HBM, timed with CUDA events on the launching stream and max-reduced over ranks; e2e = the same through
-``MVulD.forward`` with pinned host inputs copied in and logits copied out inside the timed region; roofline = the
+``MVulD.forward`` from the reference interface's HOST inputs -- pinned image, the tokenizer's raw [B, 512] ids (packed
+on the host inside the timed region), the collated CPG -- copied in, and logits copied out, every step; roofline = the
 dominant kernel family's achieved TFLOP/s (algorithmic FLOPs / CUDA-event time of every launch of that family in an
 instrumented pass) against MEASURED_PEAKS.json; cpu_baseline = the oracle port timed on the host cores on a bounded
 sample.
@@ -49,14 +53,17 @@ import torch  # noqa: E402
 
 
 METRIC = {"full": "MVulD functions/sec (fwd)", "train": "MVulD functions/sec (train step)",
+          "job": "MVulD functions/sec (fwd), whole 25 816-function job",
           "lines": "per-node UniXcoder line vectors, lines/sec"}
 REF_WORKLOAD = {      # what the reference arm runs (the B200 arm's config.workload adds the per-run packing figures)
     "full": "MVulD full fused inference (configs[3]): SwinV2-B 448px/w28 + UniXcoder-base 512 tok + GAT x2/Rs_GCN x8 fusion",
     "train": "MVulD fusion training step (configs[4], encoders frozen as in main_bigvul.py): forward + fusion backward (autograd)",
     "swin": "SwinV2-B image branch (configs[1]), 448px window 28",
     "ggnn": "GGNN graph branch (configs[2]): 4 edge types, D 200, 6 steps, segment-sum readout",
+    "job": "MVulD full fused inference over a sharded job (configs[3])",
     "lines": "per-node UniXcoder line encoding (SURVEY 8f.1), every line padded to 512 tokens as the reference runs it"}
-UNIT = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s", "train": "functions/s", "lines": "lines/s"}
+UNIT = {"full": "functions/s", "swin": "images/s", "ggnn": "graphs/s", "train": "functions/s", "lines": "lines/s",
+        "job": "functions/s"}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -66,7 +73,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "swin", "ggnn", "train", "lines"])
+    ap.add_argument("--workload", default="full", choices=["full", "swin", "ggnn", "train", "lines", "job"])
+    ap.add_argument("--functions", type=int, default=25816, help="size of the inference job (configs[3]: 25 816)")
+    ap.add_argument("--no-sub", action="store_true", help="default workload: skip the swin / ggnn / padded_text / job "
+                                                          "sub-objects")
     ap.add_argument("--batch", type=int, default=0, help="units per GPU per step (default: 64 functions / 64 images / "
                                                          "4096 graphs / 32 functions for train)")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step leg of the default workload")
@@ -79,7 +89,9 @@ def parse():
 
 def captured_traffic(key):
     """DRAM bytes per launch of the dominant kernel from this round's `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
         return json.load(open(path)).get(key)
     except (OSError, ValueError):
@@ -209,14 +221,32 @@ class Instrument:
 
 
 # --------------------------------------------------------------------------------------------------------
-def build_workload(args, rank, device):
+def _pin_graph(g):
+    for k in list(g.ndata):
+        g.ndata[k] = g.ndata[k].pin_memory()
+    g._src, g._dst = g._src.pin_memory(), g._dst.pin_memory()
+    return g
+
+
+def build_full_model(device):
     import mvuld_b200 as mv
     from mvuld_b200 import synth
+    torch.manual_seed(12345)                       # same weights on every rank
+    model = mv.MVulD(mv.default_config()).eval()
+    synth.randomize_for_parity(model, seed=777)
+    return model.to(device)
+
+
+def build_workload(args, rank, device, workload=None, model=None, padded_text=None):
+    import mvuld_b200 as mv
+    from mvuld_b200 import synth
+    workload = workload or args.workload
+    padded_text = args.padded_text if padded_text is None else padded_text
     seed = 12345 + rank
     torch.manual_seed(12345)                       # same weights on every rank
-    if args.workload == "train":
-        return build_train_workload(args, rank, device, int(os.environ.get("WORLD_SIZE", "1")))
-    if args.workload == "lines":
+    if workload == "train":
+        return build_train_workload(args, rank, device, int(os.environ.get("WORLD_SIZE", "1")), model=model)
+    if workload == "lines":
         # the per-node line encoding the reference runs offline (data_list.py:292-299 ->
         # unixcoder.py:56-68), every line padded to 512 tokens there; packed rows + block-diagonal attention here
         n = args.batch or 12800                                       # ~64 functions x 200 CPG nodes
@@ -225,7 +255,6 @@ def build_workload(args, rank, device):
         model = model.to(device)
         ids = synth.line_token_ids(n, seed=seed)                      # [n, 512] int64, what tokenize(padding=True) gives
         packed = model.encoder.pack(ids)
-        t0 = time.perf_counter()
         sample = ids[:256].to(device)
         for _ in range(2):
             model.get_repr(sample)
@@ -240,20 +269,16 @@ def build_workload(args, rank, device):
         return dict(units=n, to_dev=lambda: packed, host=ids, step=lambda d: model.encoder.encode_packed(d),
                     e2e_step=lambda h: model.myEncode_ids(h), h2d=packed.n_rows * 512 * (8 + 4 * 3) + n * 8 + packed.n_rows * 4,
                     d2h=n * 768 * 4, name=name, flops_per_unit=96.64e9 * packed.n_rows / n)
-    if args.workload == "full":
+    if workload == "full":
         B = args.batch or 64
-        model = mv.MVulD(mv.default_config()).eval()
-        synth.randomize_for_parity(model, seed=777)
-        model = model.to(device)
-        raw_ids = synth.token_ids(B, 512, seed=seed)
-        # the tokenizer's [B, 512] ids packed at data-loading time (pad tokens dropped, functions back to back in rows
-        # of 512): same sentence vectors, the encoder runs over the real tokens only (mvuld_b200/unixcoder.py)
-        ids = raw_ids.pin_memory() if args.padded_text else model.unix.encoder.pack_host(raw_ids)
-        host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=ids, g=synth.cpg_batch(B, seed=seed))
-        for k in ("_UNIX_NODE_EMB", "pos_emb"):
-            host["g"].ndata[k] = host["g"].ndata[k].pin_memory()
+        model = model or build_full_model(device)
+        raw_ids = synth.token_ids(B, 512, seed=seed).pin_memory()    # what the reference's tokenizer hands over
+        enc = model.unix.encoder
+        # device-resident leg: the batch as the data loader stages it (pad tokens dropped, functions back to back in
+        # rows of 512: same sentence vectors, the encoder runs over the real tokens only, mvuld_b200/unixcoder.py)
+        ids = raw_ids if padded_text else enc.pack_host(raw_ids)
+        host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=ids, g=_pin_graph(synth.cpg_batch(B, seed=seed)))
         host["g"].ndata.pop("_FUNC_EMB")           # feeds only the dead h_func branch (GraphModel.py:172,177)
-        host["g"]._src, host["g"]._dst = host["g"]._src.pin_memory(), host["g"]._dst.pin_memory()
 
         def to_dev():
             return dict(img=host["img"].to(device, non_blocking=True), ids=host["ids"].to(device, non_blocking=True),
@@ -263,37 +288,45 @@ def build_workload(args, rank, device):
             d["g"]._csr = None                     # graph collate (CSR build) is part of every step
             return model(d["img"], d["ids"], d["g"])
 
-        ids_bytes = host["ids"].numel() * 8 if args.padded_text else host["ids"].nbytes
+        def host_iter(n):
+            """e2e: every step starts from the reference interface's host inputs -- the raw [B, 512] ids are packed on
+            the host INSIDE the timed region (numpy, ~1 ms, overlapping the previous step's kernels)."""
+            for _ in range(n):
+                yield dict(img=host["img"], g=host["g"], ids=raw_ids if padded_text else enc.pack_host(raw_ids))
+
+        ids_bytes = raw_ids.numel() * 8 if padded_text else ids.nbytes
         h2d = host["img"].numel() * 4 + ids_bytes + host["g"]._src.numel() * 16 + \
             sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
-        text = (f"512 tok padded rows" if args.padded_text else
+        text = (f"512 tok padded rows" if padded_text else
                 f"{int((raw_ids != 1).sum()) / B:.0f} real tokens per function packed into {ids.n_rows} rows of 512")
         name = (f"MVulD full fused inference (configs[3]): SwinV2-B 448px/w28 + UniXcoder-base ({text}) + GAT x2/"
                 f"Rs_GCN x8 fusion, {B} synthetic functions per GPU per step, avg "
                 f"{host['g'].num_nodes() / B:.0f} CPG nodes")
-        text_rows = B if args.padded_text else ids.n_rows            # encoder rows of 512 tokens actually computed
-        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name,
+        text_rows = B if padded_text else ids.n_rows            # encoder rows of 512 tokens actually computed
+        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=B * 2 * 4, name=name, host_iter=host_iter,
                     flops_per_unit=159.08e9 + 96.64e9 * text_rows / B + 6.40e9, model=model, host=host)
-    if args.workload == "swin":
+    if workload == "swin":
         B = args.batch or 64
-        model = mv.build_model(mv.default_config()).eval()
-        synth.randomize_for_parity(model, seed=777)
-        model = model.to(device)
+        swin = model.swin if model is not None else None
+        if swin is None:
+            swin = mv.build_model(mv.default_config()).eval()
+            synth.randomize_for_parity(swin, seed=777)
+            swin = swin.to(device)
         host = dict(img=synth.images(B, 448, seed=seed).pin_memory())
         return dict(units=B, to_dev=lambda: dict(img=host["img"].to(device, non_blocking=True)), host=host,
-                    step=lambda d: model.forward_features(d["img"]), h2d=host["img"].numel() * 4, d2h=B * 1024 * 4,
+                    step=lambda d: swin.forward_features(d["img"]), h2d=host["img"].numel() * 4, d2h=B * 1024 * 4,
                     name=f"SwinV2-B image branch alone (configs[1]), 448px window28, bf16 inference batch={B}",
                     flops_per_unit=159.08e9)
-    B = args.batch or 4096
-    model = mv.GGNNSum(132, 200, max_edge_types=4, num_steps=6).eval()
-    synth.randomize_for_parity(model, seed=777)
-    model = model.to(device)
+    B = (args.batch if args.workload == "ggnn" else 0) or 4096
+    gm = mv.GGNNSum(132, 200, max_edge_types=4, num_steps=6).eval()
+    synth.randomize_for_parity(gm, seed=777)
+    gm = gm.to(device)
     g = synth.ggnn_batch(B, seed=seed, n_etypes=4)
     g.ndata["_WORD2VEC"] = g.ndata["_WORD2VEC"].pin_memory()
 
     def step(d):
         d["g"]._csr = None
-        return model(d["g"])[1]
+        return gm(d["g"])[1]
 
     h2d = g._src.numel() * 16 + g.edata["_ETYPE"].numel() * 8 + g.ndata["_WORD2VEC"].numel() * 4
     g._src, g._dst, g.edata["_ETYPE"] = g._src.pin_memory(), g._dst.pin_memory(), g.edata["_ETYPE"].pin_memory()
@@ -307,27 +340,20 @@ def build_train_workload(args, rank, device, world, model=None):
     """configs[4], reference-faithful variant (main_bigvul.py:294-342 trains only the fusion model on vectors from
     frozen encoders): one step = SwinV2 + UniXcoder forward (eval, no grad), fusion forward + backward, bucketed
     gradient all-reduce across the ranks, gradient-norm clip, AdamW.  Dropout 0.2 as in the reference."""
-    import mvuld_b200 as mv
     from mvuld_b200 import synth
     from mvuld_b200.train import FusionTrainer
     seed = 22345 + rank
     B = (args.batch if args.workload == "train" else 0) or 32
-    if model is None:
-        torch.manual_seed(12345)
-        model = mv.MVulD(mv.default_config()).eval()
-        synth.randomize_for_parity(model, seed=777)
-        model = model.to(device)
+    model = model or build_full_model(device)
     base_lr = 5e-5 * B * world / 512.0                                     # main_bigvul.py:545 linear scaling rule
     trainer = FusionTrainer(model.fusion, lr=base_lr, weight_decay=0.005, clip_grad=5.0, dropout=0.2, seed=12345 + rank,
                             world_size=world)
-    raw_ids = synth.token_ids(B, 512, seed=seed)
-    ids = raw_ids.pin_memory() if args.padded_text else model.unix.encoder.pack_host(raw_ids)
-    host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=ids, g=synth.cpg_batch(B, seed=seed),
+    raw_ids = synth.token_ids(B, 512, seed=seed).pin_memory()
+    enc = model.unix.encoder
+    ids = raw_ids if args.padded_text else enc.pack_host(raw_ids)
+    host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=ids, g=_pin_graph(synth.cpg_batch(B, seed=seed)),
                 y=torch.randint(0, 2, (B,), generator=torch.Generator().manual_seed(seed)).pin_memory())
-    for k in ("_UNIX_NODE_EMB", "pos_emb"):
-        host["g"].ndata[k] = host["g"].ndata[k].pin_memory()
     host["g"].ndata.pop("_FUNC_EMB")
-    host["g"]._src, host["g"]._dst = host["g"]._src.pin_memory(), host["g"]._dst.pin_memory()
 
     def to_dev():
         return dict(img=host["img"].to(device, non_blocking=True), ids=host["ids"].to(device, non_blocking=True),
@@ -340,7 +366,12 @@ def build_train_workload(args, rank, device, world, model=None):
         loss, _ = trainer.step(d["g"], img_embedding, func_text_embedding, d["y"], check=False)
         return loss
 
-    ids_bytes = host["ids"].numel() * 8 if args.padded_text else host["ids"].nbytes
+    def host_iter(n):
+        for _ in range(n):
+            yield dict(img=host["img"], g=host["g"], y=host["y"],
+                       ids=raw_ids if args.padded_text else enc.pack_host(raw_ids))
+
+    ids_bytes = raw_ids.numel() * 8 if args.padded_text else ids.nbytes
     h2d = host["img"].numel() * 4 + ids_bytes + host["g"]._src.numel() * 16 + B * 8 + \
         sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
     name = (f"MVulD fusion training step (configs[4], encoders frozen as in main_bigvul.py): SwinV2-B + UniXcoder "
@@ -349,15 +380,19 @@ def build_train_workload(args, rank, device, world, model=None):
             f"{trainer.total * 4 / 1e6:.1f} MB fp32), clip 5.0 + AdamW; {B} functions per GPU (global batch {B * world}), "
             f"avg {host['g'].num_nodes() / B:.0f} CPG nodes")
     text_rows = B if args.padded_text else ids.n_rows
-    return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name,
-                flops_per_unit=159.08e9 + 96.64e9 * text_rows / B + 4 * 6.4e9, trainer=trainer, host=host)
+    return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name, host_iter=host_iter,
+                flops_per_unit=159.08e9 + 96.64e9 * text_rows / B + 4 * 6.4e9, trainer=trainer, host=host, model=model)
 
 
+# --------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own modules where they run here (oracle/_ref: SwinTransformerV2, Rs_GCN), the oracle port
+# for the parts whose arithmetic lives in absent third-party code (HF 4.18 RobertaModel, DGL 0.8.1)
+# --------------------------------------------------------------------------------------------------------
 def cpu_oracle_runner(workload, sample):
-    """The oracle port of the reference forward on the host cores; returns (units, seconds)."""
+    """-> (callable running ``sample`` units on the host cores, kind, description)."""
     import mvuld_b200 as mv
     from mvuld_b200 import synth
-    from oracle import swin as oswin, roberta as orob, fusion as ofus
+    from oracle import swin as oswin, roberta as orob, fusion as ofus, ref_build
     from oracle.swin import SwinGeometry
     from oracle.roberta import RobertaGeometry
     from tests.cases import to_host_batch
@@ -367,62 +402,314 @@ def cpu_oracle_runner(workload, sample):
         synth.randomize_for_parity(m, seed=777)
         ids = synth.line_token_ids(sample, seed=1)
         sd = m.state_dict()
-        return lambda: orob.get_repr(sd, RobertaGeometry(), ids)
+        return (lambda: orob.get_repr(sd, RobertaGeometry(), ids)), "port", "HF-4.18 RobertaModel restatement (oracle)"
     if workload == "ggnn":
         m = mv.GGNNSum(132, 200, max_edge_types=4, num_steps=6).eval()
         g = synth.ggnn_batch(sample, seed=1, n_etypes=4)
         hb = to_host_batch(g)
         sd = m.state_dict()
-        fn = lambda: ofus.ggnn_sum_forward(sd, hb, 200, 6, 4)
-    else:
-        model = mv.MVulD(mv.default_config()).eval() if workload in ("full", "train") else None
-        swin = model.swin if model is not None else mv.build_model(mv.default_config()).eval()
-        synth.randomize_for_parity(model if model is not None else swin, seed=777)
-        img = synth.images(sample, 448, seed=1)
-        sd_s = swin.state_dict()
-        if workload == "swin":
-            fn = lambda: oswin.forward_features(sd_s, SwinGeometry(), img)
-        else:
-            ids = synth.token_ids(sample, 512, seed=1)
-            hb = to_host_batch(synth.cpg_batch(sample, seed=1))
-            sd_u, sd_f = model.unix.state_dict(), model.fusion.state_dict()
-            labels = torch.randint(0, 2, (sample,), generator=torch.Generator().manual_seed(1))
+        return (lambda: ofus.ggnn_sum_forward(sd, hb, 200, 6, 4)), "port", "DGL GatedGraphConv restatement (oracle)"
+    model = mv.MVulD(mv.default_config()).eval() if workload in ("full", "train", "job") else None
+    swin = model.swin if model is not None else mv.build_model(mv.default_config()).eval()
+    synth.randomize_for_parity(model if model is not None else swin, seed=777)
+    img = synth.images(sample, 448, seed=1)
+    sd_s = swin.state_dict()
+    kind, what = "port", "SwinV2 = oracle restatement"
+    swin_fn = lambda: oswin.forward_features(sd_s, SwinGeometry(), img)
+    rs_mods = None
+    if ref_build.available():
+        try:
+            cfg = mv.default_config()
+            sw = cfg.MODEL.SWINV2
+            ref = ref_build.load("swin_transformer_v2").SwinTransformerV2(
+                img_size=cfg.DATA.IMG_SIZE, patch_size=sw.PATCH_SIZE, in_chans=sw.IN_CHANS, num_classes=cfg.MODEL.NUM_CLASSES,
+                embed_dim=sw.EMBED_DIM, depths=sw.DEPTHS, num_heads=sw.NUM_HEADS, window_size=sw.WINDOW_SIZE,
+                mlp_ratio=sw.MLP_RATIO, qkv_bias=sw.QKV_BIAS, drop_rate=cfg.MODEL.DROP_RATE,
+                drop_path_rate=cfg.MODEL.DROP_PATH_RATE, ape=sw.APE, patch_norm=sw.PATCH_NORM,
+                pretrained_window_sizes=sw.PRETRAINED_WINDOW_SIZES).eval()
+            ref.load_state_dict(sd_s, strict=True)
+            with torch.no_grad():
+                swin_fn = lambda: ref.forward_features(img)
+            kind, what = "reference", "SwinV2 = the reference's own swin_transformer_v2.py module (oracle/_ref)"
+            if model is not None:
+                rs = ref_build.load("Rs_GCN")
+                rs_mods = []
+                for k in range(1, 9):
+                    mod = rs.Rs_GCN(512, 512).eval()
+                    mod.load_state_dict({n[len(f"Rs_GCN_{k}."):]: v for n, v in model.fusion.state_dict().items()
+                                         if n.startswith(f"Rs_GCN_{k}.")}, strict=True)
+                    rs_mods.append(mod)
+                what += " + its Rs_GCN.py module"
+        except Exception as exc:                                   # the staged files are a convenience, never required
+            kind, what = "port", f"SwinV2 = oracle restatement (oracle/_ref unusable: {type(exc).__name__})"
+            swin_fn = lambda: oswin.forward_features(sd_s, SwinGeometry(), img)
+            rs_mods = None
+    if workload == "swin":
+        return (lambda: _no_grad(swin_fn)), kind, what
+    ids = synth.token_ids(sample, 512, seed=1)
+    hb = to_host_batch(synth.cpg_batch(sample, seed=1))
+    sd_u, sd_f = model.unix.state_dict(), model.fusion.state_dict()
+    labels = torch.randint(0, 2, (sample,), generator=torch.Generator().manual_seed(1))
+    what += "; UniXcoder = HF-4.18 RobertaModel restatement, GATConv / unbatch = DGL restatement (oracle port)"
 
-            def fn():
-                fi = oswin.forward_features(sd_s, SwinGeometry(), img)
-                ft = orob.get_repr(sd_u, RobertaGeometry(), ids)
-                if workload == "train":                 # fp32 autograd step of the fusion model (no optimiser cost)
-                    from oracle import fusion_train
-                    return fusion_train.loss_and_grads(sd_f, hb, fi, ft, labels)[0]
-                return ofus.fusion_forward(sd_f, hb, fi, ft)
-    return fn
+    def fn():
+        fi = _no_grad(swin_fn)
+        ft = orob.get_repr(sd_u, RobertaGeometry(), ids)
+        if workload == "train":                 # fp32 autograd step of the fusion model (no optimiser cost)
+            from oracle import fusion_train
+            return fusion_train.loss_and_grads(sd_f, hb, fi, ft, labels)[0]
+        return ofus.fusion_forward(sd_f, hb, fi, ft, rs_gcn_modules=rs_mods)
+    return fn, kind, what
+
+
+def _no_grad(fn):
+    with torch.no_grad():
+        return fn()
+
+
+CPU_SAMPLE = {"full": 4, "job": 4, "swin": 4, "ggnn": 64, "train": 4, "lines": 4}    # units per CPU step (configs[0]: batch 4)
+
+
+def time_cpu(workload, reps, warm=1):
+    """Median of ``reps`` timed runs after ``warm`` warm-ups, all host threads -> cpu_baseline object."""
+    torch.set_num_threads(os.cpu_count())
+    sample = CPU_SAMPLE[workload]
+    fn, kind, what = cpu_oracle_runner(workload, sample)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": sample / med, "unit": UNIT[workload], "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"batch {sample}, median of {reps} runs after {warm} warm-up, fp32, torch.no_grad; {what}"}, med
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference's own entry
-    points cannot run: no dgl/timm/yacs), all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores (its own SwinV2 / Rs_GCN
+    modules from oracle/_ref where staged, the oracle port for the HF / DGL parts: the reference's entry points cannot
+    run, no dgl / timm / yacs), all host threads, each step a bounded sample (batch 4)."""
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count())
-    sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2, "lines": 4}[args.workload]
-    fn = cpu_oracle_runner(args.workload, sample)
-    for _ in range(max(1, min(args.warmup, 1))):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fn()
-    dt = time.perf_counter() - t0
-    v = sample * args.steps / dt
+    wlname = "full" if args.workload == "job" else args.workload
+    reps = max(1, min(args.steps, 5))                  # bounded: a few minutes at most whatever --steps says
+    cb, med = time_cpu(wlname, reps, warm=max(1, min(args.warmup, 1)))
     unit = UNIT[args.workload]
     emit({
-        "impl": "reference", "metric": METRIC.get(args.workload, f"{args.workload} branch {unit}"), "value": v, "unit": unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": REF_WORKLOAD[args.workload], "per_step_sample": sample, "parallelism": "host CPU, all threads",
-                   "note": "same model and synthetic input distribution as the B200 arm; each step is a bounded sample"},
-        "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample} units x {args.steps} steps"},
-        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        "impl": "reference", "metric": METRIC.get(args.workload, f"{args.workload} branch {unit}"), "value": cb["value"],
+        "unit": unit, "n_gpus": args.gpus, "steps": reps, "warmup": 1, "ms_per_step": med * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": REF_WORKLOAD[args.workload], "per_step_sample": CPU_SAMPLE[wlname],
+                   "parallelism": "host CPU, all threads",
+                   "note": "same model and synthetic input distribution as the B200 arm; each step is a bounded sample "
+                           f"(batch {CPU_SAMPLE[wlname]}), median of {reps} steps"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+# --------------------------------------------------------------------------------------------------------
+# measurement helpers
+# --------------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, device, local_rank, rank, world):
+        self.device, self.local_rank, self.rank, self.world = device, local_rank, rank, world
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(ctx, wl, steps, warmup, sample_clocks=False):
+    """Device-resident and end-to-end timing of one workload -> dict."""
+    from mvuld_b200 import _lib
+    from mvuld_b200.prefetch import DevicePrefetcher, ResultSink
+    dev_in = wl["to_dev"]()
+    torch.cuda.synchronize()
+    for _ in range(max(warmup, 3)):
+        wl["step"](dev_in)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank) if sample_clocks else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        wl["step"](dev_in)
+    e.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(s.elapsed_time(e))
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the public API: host inputs in, result out, every step ----
+    # (mvuld_b200.prefetch: batch i+1 is staged -- ids packed on the host, everything copied from pinned memory on a
+    #  side stream -- while batch i computes; every step's result is read back inside the timed region)
+    def e2e_pass(n):
+        sink = ResultSink(n)
+        fusion = getattr(wl.get("model"), "fusion", None)
+        if fusion is not None:
+            fusion.defer_checks = True          # input-validity flags are read back once per pass, not once per step
+        try:
+            if "e2e_step" in wl:                # the public call packs on the host itself (host ids in, vectors out)
+                for _ in range(n):
+                    sink.push(wl["e2e_step"](wl["host"]))
+                return sink.results()
+            batches = wl["host_iter"](n) if "host_iter" in wl else (wl["host"] for _ in range(n))
+            for d in DevicePrefetcher(batches, ctx.device):
+                sink.push(wl["step"](d))
+            return sink.results()
+        finally:
+            if fusion is not None:
+                fusion.raise_if_invalid()
+                fusion.defer_checks = False
+
+    e2e_pass(steps)                       # also warms the pinned result buffers (cached by torch's host allocator)
+    ctx.barrier()
+    s.record()
+    last = e2e_pass(steps)[-1]
+    e.record()
+    ctx.barrier()
+    ms_e2e = ctx.max_over_ranks(s.elapsed_time(e))
+    n_units = wl["units"] * ctx.world * steps
+    return dict(value=n_units / (ms / 1e3), ms_per_step=ms / steps, e2e=n_units / (ms_e2e / 1e3), launches=int(launches),
+                clocks=clocks, dev_in=dev_in, last=last)
+
+
+def roofline_of(wl, dev_in, workload, clocks, pk, detail_path=None):
+    """One instrumented step: every C-ABI call bracketed with CUDA events on the launching stream."""
+    inst = Instrument()
+    inst.install()
+    try:
+        wl["step"](dev_in)
+    finally:
+        inst.remove()
+    fam, per_kernel = inst.summary()
+    total_ms = sum(d["ms"] for d in fam.values())
+    out = {}
+    if workload == "ggnn":
+        # HBM-bound path: the segment-reduce kernel (SURVEY.md section 8d row 2, bf16 messages)
+        k = per_kernel.get("mvuld_ggnn_gather_sum")
+        g = dev_in["g"]
+        alg = g.num_edges() * 200 * 2 + g.num_edges() * 5 + (g.num_nodes() + 1) * 4 + g.num_nodes() * 200 * 2
+        ach = alg / (k["ms"] / k["launches"] / 1e3) / 1e9
+        tr = captured_traffic("ggnn_gather_sum")
+        out["roofline"] = {"bound": "hbm", "kernel": "ggnn_gather_sum_kernel", "achieved": ach, "peak": pk["hbm"],
+                           "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": tr["bytes"] if tr else None,
+                           "algorithmic_bytes_per_launch": alg, "peak_source": pk["src"],
+                           "share_of_step": k["ms"] / total_ms}
+    else:
+        tensor_fams = {k: v for k, v in fam.items() if v["flops"] > 0}
+        kname, d = max((tensor_fams or fam).items(), key=lambda kv: kv[1]["ms"])       # the dominant tensor-pipe family
+        fl = d["flops"] if d["flops"] else 0.0
+        ach = fl / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
+        out["roofline"] = {"bound": "tensor", "kernel": {"gemm": "gemm_tn_kernel / gemm_ln_kernel (all epilogues)",
+                                                         "attention": "attn_fwd_kernel",
+                                                         "other": "row/graph kernels"}[kname],
+                           "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                           "frac": ach / pk["bf16_sustained"], "frac_of_burst_peak": ach / pk["bf16"],
+                           "traffic": None, "peak_source": pk["src"] +
+                           " (sustained: kernel timed inside a long step)", "share_of_step": d["ms"] / total_ms}
+        tr = captured_traffic(kname)
+        if tr:
+            out["roofline"]["traffic"] = tr["bytes"]
+            out["roofline"]["traffic_note"] = f"one launch of {tr['kernel']} ({tr['source']})"
+        # the window-attention kernel next to it: tensor fraction and the exponential (MUFU) roof of head dim 32
+        swin_fl = sum(work_of(n, a)[1] for n, a, _, _ in inst.records if n == "mvuld_swin_window_attention")
+        swin_ms = per_kernel.get("mvuld_swin_window_attention", {"ms": 0.0})["ms"]
+        if swin_ms > 0:
+            sm_hz = ((clocks or {}).get("sm_mhz") or 1965) * 1e6
+            a_t = swin_fl / (swin_ms / 1e3) / 1e12
+            out["window_attention"] = {"kernel": "attn_fwd_kernel<MODE_SWIN, hd 32>", "ms": round(swin_ms, 3),
+                                       "achieved": a_t, "unit": "TFLOP/s", "frac": a_t / pk["bf16_sustained"],
+                                       "frac_of_burst_peak": a_t / pk["bf16"], "share_of_step": swin_ms / total_ms,
+                                       "exp_per_s": swin_fl / 128.0 / (swin_ms / 1e3),
+                                       "mufu_peak_exp_per_s": 16.0 * 148 * sm_hz}
+    out["kernel_families"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                  "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else 0.0}
+                              for k, v in fam.items()}
+    out["entry_points_ms"] = {k: [round(v["ms"], 3), v["launches"]] for k, v in
+                              sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])[:12]}
+    if detail_path:
+        rows = []
+        for name, a, s_, e_ in inst.records:
+            shape = a if isinstance(a, dict) else [x for x in a if isinstance(x, (int, float))]
+            rows.append({"name": name, "shape": shape, "ms": round(s_.elapsed_time(e_), 4)})
+        with open(detail_path, "w") as fh:
+            json.dump(rows, fh)
+    return out
+
+
+def run_job(ctx, args, model):
+    """configs[3] as written: ``args.functions`` (25 816) synthetic functions, sharded over the ranks by cost
+    (mvuld_b200.sharding.shard_by_cost: every function scored exactly once, unlike DistributedSampler's padding,
+    bigvul_dataset.py:170-175), each rank walking its shard in batches of 64 with a short last batch.  The rank's whole
+    shard is staged in HBM first (62 GB of fp32 images + 16 GB of node vectors at one GPU; SURVEY.md section 8d row 3);
+    the timed region is the inference over the whole shard; value = functions of the JOB / max-over-ranks time, so the
+    number scales strongly with N and the slowest shard sets it."""
+    from mvuld_b200 import synth, _lib
+    from mvuld_b200.sharding import shard_by_cost, batches
+    n, B = int(args.functions), args.batch or 64
+    nodes = synth.job_node_counts(n, seed=12345)
+    # cost of a function in CPG-node equivalents: the image + text branches are constant (256 GFLOP), the graph branch
+    # is ~6.4 GFLOP per 200 nodes
+    cost = (nodes + int(200 * 255.7 / 6.4)).tolist()
+    shards = shard_by_cost(cost, ctx.world)
+    lo, hi = shards[ctx.rank]
+    fs = synth.function_set(hi - lo, ctx.device, seed=777 + ctx.rank, node_counts=nodes[lo:hi])
+    enc = model.unix.encoder
+    steps = [(a, b, enc.pack_host(fs.ids[a:b]).to(ctx.device)) for a, b in batches(0, hi - lo, B)]
+    out = torch.empty(hi - lo, 2, device=ctx.device, dtype=torch.float32)
+    model.fusion.defer_checks = True
+
+    def run(sel):
+        for a, b, ids in sel:
+            out[a:b] = model(fs.images[a:b], ids, fs.graph(a, b))
+    run(steps[:3] + steps[-1:])                                    # warm-up incl. the short last batch's shapes
+    model.fusion.raise_if_invalid()
+    ctx.barrier()
+    l0 = _lib.launch_count
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    run(steps)
+    e.record()
+    ctx.barrier()
+    model.fusion.raise_if_invalid()
+    model.fusion.defer_checks = False
+    mine = s.elapsed_time(e)
+    ms = ctx.max_over_ranks(mine)
+    per_rank = [mine]
+    if ctx.world > 1:
+        import torch.distributed as dist
+        t = torch.zeros(ctx.world, device=ctx.device)
+        t[ctx.rank] = mine
+        dist.all_reduce(t)
+        per_rank = [float(x) for x in t.tolist()]
+    finite = bool(torch.isfinite(out).all())
+    res = {"metric": METRIC["job"], "value": n / (ms / 1e3), "unit": "functions/s", "functions": n, "seconds": ms / 1e3,
+           "scaling": "strong", "per_gpu_batch": B, "steps_on_rank0": len(steps), "last_batch_on_rank0": steps[-1][1] - steps[-1][0],
+           "shards": [b - a for a, b in shards], "shard_seconds": [round(x / 1e3, 3) for x in per_rank],
+           "tail_imbalance": max(per_rank) / (sum(per_rank) / len(per_rank)), "gpu_launches_rank0": int(_lib.launch_count - l0),
+           "logits_finite": finite,
+           "workload": f"MVulD full fused inference, {n} synthetic functions batch-sharded over {ctx.world} GPU(s) by cost "
+                       f"(sharding.shard_by_cost), batches of {B} with a short last batch, inputs staged in HBM, text "
+                       "packed at data-loading time"}
+    del fs, steps, out
+    torch.cuda.empty_cache()
+    return res
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -441,205 +728,99 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    from mvuld_b200 import _lib
+    ctx = Ctx(device, local_rank, rank, world)
+    pk = peaks()
+
+    if args.workload == "job":
+        model = build_full_model(device)
+        job = run_job(ctx, args, model)
+        if rank == 0:
+            line = {"metric": job["metric"], "value": job["value"], "unit": job["unit"], "n_gpus": world, "steps": job["steps_on_rank0"],
+                    "warmup": 4, "ms_per_step": job["seconds"] * 1e3 / max(1, job["steps_on_rank0"]), "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": job["workload"], "per_gpu_batch": job["per_gpu_batch"],
+                               "parallelism": f"cost-sharded x{world}, no data-path collective"},
+                    "gpu_launches": job["gpu_launches_rank0"], "job": job}
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     wl = build_workload(args, rank, device)
     unit = UNIT[args.workload]
+    m = measure(ctx, wl, args.steps, args.warmup, sample_clocks=True)
+    clocks = m["clocks"]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident timing ----
-    dev_in = wl["to_dev"]()
-    torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
-        out = wl["step"](dev_in)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = _lib.launch_count
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(args.steps):
-        out = wl["step"](dev_in)
-    e.record()
-    barrier()
-    ms = max_over_ranks(s.elapsed_time(e))
-    launches = _lib.launch_count - launches0
-    clocks = sampler.stop()
-    value = wl["units"] * world * args.steps / (ms / 1e3)
-
-    # ---- end to end through the public API: pinned host inputs in, logits out, every step ----
-    # (mvuld_b200.prefetch: batch i+1 is copied on a side stream while batch i computes; every step's inputs are
-    #  copied from pinned host memory and every step's result is read back inside the timed region)
-    from mvuld_b200.prefetch import DevicePrefetcher, ResultSink
-
-    def e2e_pass(w, n):
-        sink = ResultSink(n)
-        fusion = getattr(w.get("model"), "fusion", None)
-        if fusion is not None:
-            fusion.defer_checks = True          # input-validity flags are read back once per pass, not once per step
-        try:
-            return _e2e_pass(w, n, sink)
-        finally:
-            if fusion is not None:
-                fusion.raise_if_invalid()
-                fusion.defer_checks = False
-
-    def _e2e_pass(w, n, sink):
-        if "e2e_step" in w:                     # the public call packs on the host itself (host ids in, vectors out)
-            for _ in range(n):
-                sink.push(w["e2e_step"](w["host"]))
-            return sink.results()
-        for d in DevicePrefetcher((w["host"] for _ in range(n)), device):
-            sink.push(w["step"](d))
-        return sink.results()
-
-    e2e_pass(wl, args.steps)              # also warms the pinned result buffers (cached by torch's host allocator)
-    barrier()
-    s.record()
-    e2e_pass(wl, args.steps)
-    e.record()
-    barrier()
-    ms_e2e = max_over_ranks(s.elapsed_time(e))
-    e2e = wl["units"] * world * args.steps / (ms_e2e / 1e3)
-
-    # ---- train-step leg of the default workload (configs[4]) on the same model, same N ----
-    train_obj = None
-    if args.workload == "full" and not args.no_train:
-        twl = build_train_workload(args, rank, device, world, model=wl["model"])
-        tdev = twl["to_dev"]()
+    sub = {}
+    if args.workload == "full":
+        model = wl["model"]
         tsteps = min(args.steps, 10)
-        for _ in range(3):
-            twl["step"](tdev)
-        barrier()
-        tl0 = _lib.launch_count
-        s.record()
-        for _ in range(tsteps):
-            twl["step"](tdev)
-        e.record()
-        barrier()
-        tms = max_over_ranks(s.elapsed_time(e))
-        tlaunch = _lib.launch_count - tl0
-        e2e_pass(twl, tsteps)
-        barrier()
-        s.record()
-        loss_host = e2e_pass(twl, tsteps)[-1]
-        e.record()
-        barrier()
-        tms_e2e = max_over_ranks(s.elapsed_time(e))
-        train_obj = {"metric": METRIC["train"], "value": twl["units"] * world * tsteps / (tms / 1e3),
-                     "unit": "functions/s", "steps": tsteps, "warmup": 3, "ms_per_step": tms / tsteps,
-                     "per_gpu_batch": twl["units"], "global_batch": twl["units"] * world, "workload": twl["name"],
-                     "e2e": {"value": twl["units"] * world * tsteps / (tms_e2e / 1e3), "unit": "functions/s",
-                             "h2d_bytes_per_step": int(twl["h2d"]), "d2h_bytes_per_step": 4},
-                     "gpu_launches": int(tlaunch), "last_loss": float(loss_host),
-                     "gradient_allreduce": (f"NCCL, {len(twl['trainer'].buckets)} buckets over "
-                                            f"{twl['trainer'].total * 4 / 1e6:.1f} MB fp32" if world > 1 else "none (1 GPU)")}
+        if not args.no_train:
+            # train-step leg (configs[4]) on the same model, same N
+            twl = build_train_workload(args, rank, device, world, model=model)
+            tm = measure(ctx, twl, tsteps, 3)
+            sub["train"] = {"metric": METRIC["train"], "value": tm["value"], "unit": "functions/s", "steps": tsteps, "warmup": 3,
+                            "ms_per_step": tm["ms_per_step"], "per_gpu_batch": twl["units"],
+                            "global_batch": twl["units"] * world, "workload": twl["name"],
+                            "e2e": {"value": tm["e2e"], "unit": "functions/s", "h2d_bytes_per_step": int(twl["h2d"]),
+                                    "d2h_bytes_per_step": 4},
+                            "gpu_launches": tm["launches"], "last_loss": float(tm["last"]),
+                            "gradient_allreduce": (f"NCCL, {len(twl['trainer'].buckets)} buckets over "
+                                                   f"{twl['trainer'].total * 4 / 1e6:.1f} MB fp32" if world > 1 else "none (1 GPU)")}
+            del twl, tm
+        if not args.no_sub:
+            if not args.padded_text:
+                # the literal "512 tok" reading of configs[3]: the text branch on the tokenizer's padded rows
+                pwl = build_workload(args, rank, device, "full", model=model, padded_text=True)
+                pm = measure(ctx, pwl, tsteps, 3)
+                sub["padded_text"] = {"value": pm["value"], "unit": "functions/s", "ms_per_step": pm["ms_per_step"],
+                                      "steps": tsteps, "e2e": {"value": pm["e2e"], "unit": "functions/s",
+                                                               "h2d_bytes_per_step": int(pwl["h2d"]), "d2h_bytes_per_step": int(pwl["d2h"])},
+                                      "workload": pwl["name"]}
+                del pwl, pm
+            for name in ("swin", "ggnn"):
+                # configs[1] / configs[2] in the driver-run line, each with its own roofline
+                swl = build_workload(args, rank, device, name, model=model)
+                sm = measure(ctx, swl, tsteps, 3)
+                obj = {"metric": f"{name} branch {UNIT[name]}", "value": sm["value"], "unit": UNIT[name], "steps": tsteps,
+                       "warmup": 3, "ms_per_step": sm["ms_per_step"], "workload": swl["name"], "gpu_launches": sm["launches"],
+                       "e2e": {"value": sm["e2e"], "unit": UNIT[name], "h2d_bytes_per_step": int(swl["h2d"]),
+                               "d2h_bytes_per_step": int(swl["d2h"])}}
+                if swl["flops_per_unit"]:
+                    obj["model_tflops"] = swl["flops_per_unit"] * sm["value"] / world / 1e12
+                if rank == 0 and not args.no_roofline:
+                    obj.update(roofline_of(swl, sm["dev_in"], name, clocks, pk))
+                sub[name] = obj
+                del swl, sm
+                torch.cuda.empty_cache()
+            sub["job"] = run_job(ctx, args, model)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
     line = {
         "metric": METRIC.get(args.workload, f"{args.workload} branch {unit}"),
-        "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "value": m["value"], "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["name"], "per_gpu_batch": wl["units"], "parallelism": f"batch-shard x{world}, no "
                    "data-path collective" if args.workload not in ("train",) else f"data-parallel x{world}, bucketed NCCL "
                    "gradient all-reduce", "l2_policy": "per-step inputs + activations exceed the 126 MB L2"},
-        "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(wl["h2d"]), "d2h_bytes_per_step": int(wl["d2h"])},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": {"value": m["e2e"], "unit": unit, "h2d_bytes_per_step": int(wl["h2d"]), "d2h_bytes_per_step": int(wl["d2h"]),
+                "note": "host inputs of the reference interface every step: pinned image + raw [B,512] ids (packed on the "
+                        "host inside the timed region) + collated CPG in, logits out" if args.workload in ("full", "train")
+                        else "pinned host inputs in, result out, every step"},
+        "gpu_launches": m["launches"], "clocks": clocks,
     }
     if wl["flops_per_unit"]:
-        line["model_tflops"] = wl["flops_per_unit"] * value / world / 1e12
-    if train_obj is not None:
-        line["train"] = train_obj
-
+        line["model_tflops"] = wl["flops_per_unit"] * m["value"] / world / 1e12
+    line.update(sub)
     if not args.no_roofline:
-        inst = Instrument()
-        inst.install()
-        try:
-            wl["step"](dev_in)
-        finally:
-            inst.remove()
-        fam, per_kernel = inst.summary()
-        total_ms = sum(d["ms"] for d in fam.values())
-        tensor_fams = {k: v for k, v in fam.items() if v["flops"] > 0}
-        top = max((tensor_fams or fam).items(), key=lambda kv: kv[1]["ms"])       # the dominant tensor-pipe family
-        if args.workload == "ggnn":
-            # HBM-bound path: the segment-reduce kernel (SURVEY.md section 8d row 2, bf16 messages)
-            k = per_kernel.get("mvuld_ggnn_gather_sum")
-            g = dev_in["g"]
-            alg = g.num_edges() * 200 * 2 + g.num_edges() * 5 + (g.num_nodes() + 1) * 4 + g.num_nodes() * 200 * 2
-            ach = alg / (k["ms"] / k["launches"] / 1e3) / 1e9
-            tr = captured_traffic("ggnn_gather_sum")
-            line["roofline"] = {"bound": "hbm", "kernel": "ggnn_gather_sum_kernel", "achieved": ach, "peak": pk["hbm"],
-                                "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": tr["bytes"] if tr else None,
-                                "algorithmic_bytes_per_launch": alg, "peak_source": pk["src"],
-                                "share_of_step": k["ms"] / total_ms}
-        else:
-            kname, d = top
-            fl = d["flops"] if d["flops"] else 0.0
-            ach = fl / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
-            line["roofline"] = {"bound": "tensor", "kernel": {"gemm": "gemm_tn_kernel (all epilogues)",
-                                                              "attention": "attn_fwd_kernel",
-                                                              "other": "row/graph kernels"}[kname],
-                                "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                                "frac": ach / pk["bf16_sustained"], "frac_of_burst_peak": ach / pk["bf16"],
-                                "traffic": None, "peak_source": pk["src"] +
-                                " (sustained: kernel timed inside a long step)", "share_of_step": d["ms"] / total_ms}
-            if kname == "attention":
-                # the window-attention kernel is bound by the exponentials, not the MMAs (head dim 32: one ex2 per 128
-                # tensor FLOP): report the MUFU roofline next to the tensor one (16 ex2 / clk / SM)
-                sm_hz = (clocks.get("sm_mhz") or 1965) * 1e6
-                peak_exp = 16.0 * 148 * sm_hz
-                swin_fl = sum(work_of(n, a)[1] for n, a, _, _ in inst.records if n == "mvuld_swin_window_attention")
-                swin_ms = per_kernel.get("mvuld_swin_window_attention", {"ms": 0.0})["ms"]
-                if swin_ms > 0:
-                    ach_exp = swin_fl / 128.0 / (swin_ms / 1e3)
-                    line["roofline"]["mufu"] = {"kernel": "attn_fwd_kernel<MODE_SWIN, hd 32>", "achieved_exp_per_s": ach_exp,
-                                                "peak_exp_per_s": peak_exp, "frac": ach_exp / peak_exp}
-            tr = captured_traffic(kname)
-            if tr:
-                line["roofline"]["traffic"] = tr["bytes"]
-                line["roofline"]["traffic_note"] = f"one launch of {tr['kernel']} ({tr['source']})"
-        line["kernel_families"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
-                                       "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else 0.0}
-                                   for k, v in fam.items()}
-        line["entry_points_ms"] = {k: [round(v["ms"], 3), v["launches"]] for k, v in
-                                   sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])[:12]}
-        if os.environ.get("MVULD_BENCH_DETAIL"):
-            rows = []
-            for name, a, s_, e_ in inst.records:
-                shape = a if isinstance(a, dict) else [x for x in a if isinstance(x, (int, float))]
-                rows.append({"name": name, "shape": shape, "ms": round(s_.elapsed_time(e_), 4)})
-            with open(os.environ["MVULD_BENCH_DETAIL"], "w") as fh:
-                json.dump(rows, fh)
-
+        line.update(roofline_of(wl, m["dev_in"], args.workload, clocks, pk, os.environ.get("MVULD_BENCH_DETAIL")))
     if not args.no_cpu_baseline and world == 1:
-        torch.set_num_threads(os.cpu_count())
-        sample = {"full": 2, "swin": 2, "ggnn": 64, "train": 2, "lines": 4}[args.workload]
-        fn = cpu_oracle_runner(args.workload, sample)
-        fn()
-        t0 = time.perf_counter()
-        reps = 2
-        for _ in range(reps):
-            fn()
-        dt = (time.perf_counter() - t0) / reps
-        line["cpu_baseline"] = {"value": sample / dt, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{sample} units, mean of {reps} runs after 1 warm-up, fp32 oracle"}
+        line["cpu_baseline"], _ = time_cpu(args.workload, reps=5)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

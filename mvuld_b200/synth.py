@@ -131,6 +131,99 @@ def ggnn_batch(B: int, seed: int = 12345, in_dim: int = 132, n_etypes: int = 4) 
     return out
 
 
+class FunctionSet:
+    """A whole inference job's worth of synthetic functions (BASELINE.json configs[3]: 25 816 functions), staged on ONE
+    device: images fp32 [n, 3, S, S], the tokenizer's [n, 512] ids (host), and all CPGs as one edge / node-data store
+    with per-function offsets.  ``graph(a, b)`` is the batched CPG of functions [a, b) (``dgl.batch`` order: node ids
+    shifted by the running node count, each graph's self loops after its own edges) without copying node data."""
+
+    def __init__(self, images, ids, src, dst, n_off, e_off, nodes, emb, pos):
+        self.images, self.ids = images, ids
+        self._src, self._dst, self._n_off, self._e_off, self.nodes = src, dst, n_off, e_off, nodes
+        self._emb, self._pos = emb, pos
+
+    def __len__(self):
+        return int(self.nodes.numel())
+
+    def graph(self, a: int, b: int) -> G.Graph:
+        n0, n1, e0, e1 = int(self._n_off[a]), int(self._n_off[b]), int(self._e_off[a]), int(self._e_off[b])
+        g = G.Graph.__new__(G.Graph)
+        g._src, g._dst = self._src[e0:e1] - n0, self._dst[e0:e1] - n0
+        g._num_nodes = n1 - n0
+        g._bnn = self.nodes[a:b]
+        g._bne = (self._e_off[a + 1:b + 1] - self._e_off[a:b])
+        g.ndata = {"_UNIX_NODE_EMB": self._emb[n0:n1], "pos_emb": self._pos[n0:n1]}
+        g.edata = {}
+        g._csr = g._ocsr = g._offsets = None
+        return g
+
+
+def function_set(n: int, device, seed: int = 12345, img_size: int = 448, node_dim: int = 768,
+                 node_counts=None) -> FunctionSet:
+    """``n`` synthetic functions resident on ``device`` (same laws as ``images`` / ``token_ids`` / ``cpg_batch``; the
+    structure is built vectorised on the host, the dense payloads -- 2.4 MB of image and ~0.6 MB of node vectors per
+    function -- are drawn on the device, since the set is far too large to ship from the host: SURVEY.md section 8d
+    row 3).  ``node_counts`` (int64 [n]) fixes the CPG sizes, e.g. a slice of the job-wide draw used for sharding."""
+    dev = torch.device(device)
+    g = _gen(seed + 7)
+    nn_ = torch.as_tensor(node_counts, dtype=torch.int64) if node_counts is not None else \
+        torch.tensor(_num_nodes(n, g), dtype=torch.int64)
+    assert nn_.numel() == n
+    n_off = torch.zeros(n + 1, dtype=torch.int64)
+    n_off[1:] = torch.cumsum(nn_, 0)
+    N = int(n_off[-1])
+    e_cnt = 4 * nn_                                        # (N-1) tree + (N-1) chain + (N+2) random + N self loops
+    e_off = torch.zeros(n + 1, dtype=torch.int64)
+    e_off[1:] = torch.cumsum(e_cnt, 0)
+    E = int(e_off[-1])
+    src = torch.empty(E, dtype=torch.int64)
+    dst = torch.empty(E, dtype=torch.int64)
+    nid = torch.arange(N)
+    gid = torch.repeat_interleave(torch.arange(n), nn_)
+    loc = nid - n_off[gid]                                 # local node id
+    nz = loc > 0
+    # tree: node i > 0 gets a random parent < i; chain: i-1 -> i   (edge slots 0..N_k-2 and N_k-1..2N_k-3 of the graph)
+    par = (torch.rand(N, generator=g) * loc).long()
+    p_tree = e_off[gid] + loc - 1
+    src[p_tree[nz]], dst[p_tree[nz]] = (par + n_off[gid])[nz], nid[nz]
+    p_chain = p_tree + nn_[gid] - 1
+    src[p_chain[nz]], dst[p_chain[nz]] = nid[nz] - 1, nid[nz]
+    # N_k + 2 random pairs
+    rgid = torch.repeat_interleave(torch.arange(n), nn_ + 2)
+    rk = torch.arange(rgid.numel()) - torch.repeat_interleave(torch.cumsum(nn_ + 2, 0) - (nn_ + 2), nn_ + 2)
+    p_rnd = e_off[rgid] + 2 * (nn_[rgid] - 1) + rk
+    src[p_rnd] = (torch.rand(rgid.numel(), generator=g) * nn_[rgid]).long() + n_off[rgid]
+    dst[p_rnd] = (torch.rand(rgid.numel(), generator=g) * nn_[rgid]).long() + n_off[rgid]
+    # self loops last (dgl.add_self_loop)
+    p_loop = e_off[gid] + 3 * nn_[gid] + loc
+    src[p_loop], dst[p_loop] = nid, nid
+    dg = torch.Generator(device=dev)
+    dg.manual_seed(int(seed) + 11)
+    emb = torch.randn(N, node_dim, device=dev, generator=dg) * 0.5
+    have = (torch.rand(N, 1, device=dev, generator=dg) < 0.7).float()
+    r = torch.rand(N, 4, device=dev, generator=dg)
+    x0, y0 = r[:, 0] * 0.9, r[:, 1] * 0.9
+    pos = torch.stack([x0, y0, x0 + 0.02 + r[:, 2] * 0.08, y0 + 0.01 + r[:, 3] * 0.04], 1) * have
+    pos = (pos * 1e5).round() / 1e5
+    imgs = torch.empty(n, 3, img_size, img_size, device=dev, dtype=torch.float32)
+    mean = torch.tensor(IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, device=dev).view(1, 3, 1, 1)
+    for a in range(0, n, 256):                             # chunks bound the temporaries
+        b = min(n, a + 256)
+        white = torch.rand(b - a, 1, img_size, img_size, device=dev, generator=dg) < 0.9
+        dark = torch.rand(b - a, 1, img_size, img_size, device=dev, generator=dg) * 0.3
+        base = torch.where(white, torch.ones_like(dark), dark)
+        x = (base + (torch.rand(b - a, 3, img_size, img_size, device=dev, generator=dg) - 0.5) * 0.04).clamp_(0, 1)
+        imgs[a:b] = (x - mean) / std
+    ids = token_ids(n, 512, seed=seed)
+    return FunctionSet(imgs, ids, src.to(dev), dst.to(dev), n_off, e_off, nn_, emb, pos)
+
+
+def job_node_counts(n: int, seed: int = 12345) -> torch.Tensor:
+    """CPG node counts of a whole job (the law of ``cpg_batch``), drawn once so every rank shards the same list."""
+    return torch.tensor(_num_nodes(n, _gen(seed + 8)), dtype=torch.int64)
+
+
 @torch.no_grad()
 def randomize_for_parity(model: nn.Module, seed: int = 777) -> nn.Module:
     """Make a random-init comparison non-vacuous: the reference zero-initialises the

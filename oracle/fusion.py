@@ -46,9 +46,11 @@ def l2norm_dim1(x: torch.Tensor) -> torch.Tensor:
 @torch.no_grad()
 def fusion_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
                    func_text_embedding: torch.Tensor, max_node: int = 100, taps: dict | None = None,
-                   head: str = "all") -> torch.Tensor:
+                   head: str = "all", rs_gcn_modules=None) -> torch.Tensor:
     """GraphModel.py:150-211 -> logits [B, 2].  ``head``: "all" = the live model; "noFunc" = new_model.py:317-318
-    (cat(image, graph)); "noGlobalImage" = new_model.py:196-197 (text * graph) -- same graph branch."""
+    (cat(image, graph)); "noGlobalImage" = new_model.py:196-197 (text * graph) -- same graph branch.
+    ``rs_gcn_modules``: eight instances of the REFERENCE ``Rs_GCN`` module (oracle/_ref) to run in place of the
+    restatement ``rs_gcn`` (bench.py's CPU arm)."""
     lin = lambda name, t: F.linear(t, sd[name + ".weight"].float(), sd[name + ".bias"].float())
     x = F.elu(lin("swinfc", _bn_eval(sd, "swinbn.", img_embedding.float(), 1)))
     t = F.elu(lin("fc_text", _bn_eval(sd, "bn_text.", func_text_embedding.float(), 1)))
@@ -74,7 +76,7 @@ def fusion_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_
     if taps is not None:
         taps["gcn_in"] = z.clone()
     for k in range(1, 9):
-        z, _ = rs_gcn(sd, f"Rs_GCN_{k}.", z)
+        z, _ = rs_gcn(sd, f"Rs_GCN_{k}.", z) if rs_gcn_modules is None else rs_gcn_modules[k - 1](z)
     if taps is not None:
         taps["gcn_out"] = z.clone()
     z = l2norm_dim1(z.permute(0, 2, 1)).mean(dim=1)                           # [B, 512]

@@ -1,6 +1,8 @@
-"""GPU: BASELINE.json's full sizes, checked through size-independent properties (the CPU oracle would take hours there):
-sortedness / permutation / stability of the CSR build, independence of graphs and functions inside a batch (the property
-that lets the path shard over GPUs with no collective), linearity of the segment-sum readout."""
+"""GPU: BASELINE.json's full sizes.  The composed forward (SwinV2-B 448/w28 + 12-layer RoBERTa-base + fusion) is
+compared with the fp32 CPU oracle on 4 functions (a few seconds of CPU); the 4 096-graph GGNN batch and the 64-function
+batch are checked through size-independent properties: sortedness / permutation / stability of the CSR build,
+independence of graphs and functions inside a batch (the property that lets the path shard over GPUs with no
+collective), linearity of the segment-sum readout."""
 import numpy as np
 import pytest
 import torch
@@ -84,3 +86,37 @@ def test_full_forward_functions_are_independent_of_their_batch():
     scale = float(whole.abs().max())
     assert float((part - whole[lo:hi]).abs().max()) <= 2e-3 * scale
     assert torch.equal(part.argmax(1), whole[lo:hi].argmax(1))
+
+
+def test_full_size_composed_forward_matches_oracle():
+    """configs[0] / configs[3] geometry, B = 4: image + padded ids + CPG -> logits on the B200 path against the fp32
+    oracle (reference SwinV2 restatement + HF-4.18 RoBERTa restatement + fusion), north_star's 1e-2 and identical argmax.
+    Both text layouts (padded rows as the reference tokenizer gives them, and packed at data-loading time) are checked."""
+    from oracle import fusion as ofusion, roberta as oroberta, swin as oswin
+    from oracle.swin import SwinGeometry
+    from oracle.roberta import RobertaGeometry
+    from tests.conftest import record_parity
+    torch.manual_seed(cases.SEED)
+    model = mv.MVulD(mv.default_config()).eval()
+    synth.randomize_for_parity(model, seed=777)
+    B = 4
+    img, ids = synth.images(B, 448, seed=11), synth.token_ids(B, 512, seed=11)
+    g = synth.cpg_batch(B, seed=11)
+    f_img = oswin.forward_features(model.swin.state_dict(), SwinGeometry(), img)
+    f_txt = oroberta.get_repr(model.unix.state_dict(), RobertaGeometry(), ids)
+    ref = ofusion.fusion_forward(model.fusion.state_dict(), cases.to_host_batch(g), f_img, f_txt)
+    model = model.to(DEV)
+    img_d, g_d = img.to(DEV), g.to(DEV)
+    out = model(img_d, ids.to(DEV), g_d).cpu()
+    f_img_d = model.swin.forward_features(img_d).cpu()
+    f_txt_d = model.unix.get_repr(ids.to(DEV))[0].cpu()
+    out_packed = model(img_d, model.unix.encoder.pack_host(ids).to(DEV), g.to(DEV)).cpu()
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    lerr = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    e_img = record_parity("fullsize.swin448w28.features rel-L2 vs oracle", rel(f_img_d, f_img), 1e-2)
+    e_txt = record_parity("fullsize.roberta12L.sentence rel-L2 vs oracle", rel(f_txt_d, f_txt), 1e-2)
+    e_out = record_parity("fullsize.composed.logits max-rel vs oracle (padded text)", lerr(out, ref), 1e-2)
+    e_pk = record_parity("fullsize.composed.logits max-rel vs oracle (packed text)", lerr(out_packed, ref), 1e-2)
+    assert e_img < 1e-2 and e_txt < 1e-2, (e_img, e_txt)
+    assert e_out < 1e-2 and e_pk < 1e-2, (e_out, e_pk, out, ref)
+    assert torch.equal(out.argmax(1), ref.argmax(1)) and torch.equal(out_packed.argmax(1), ref.argmax(1))

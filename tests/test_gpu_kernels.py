@@ -202,7 +202,10 @@ def test_swin_attention_block(Hres, ws, shift, nH, B):
         _lib.call("mvuld_swin_window_attention", q, k, v, tab_rev, tab_max, qn, out, B, H, W, C, nH, ws, shift)
         torch.cuda.synchronize()
         err = rel_err(out, ref)
-        assert err < 1.5e-2, (err, qn is None)
+        from tests.conftest import record_parity
+        record_parity(f"swin_window_attention[H{Hres} ws{ws} shift{shift}, {'constant' if qn is not None else 'running-max'} reference] rel-L2",
+                      err, 1e-2)
+        assert err < 1e-2, (err, qn is None)
 
 
 def test_seq_attention():

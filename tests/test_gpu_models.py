@@ -22,10 +22,23 @@ def rel_err(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def logits_close(a, b, tol=1e-2):
+def logits_err(a, b):
     a, b = a.float().cpu(), b.float().cpu()
-    scale = b.abs().max().clamp(min=1e-6)
-    return float((a - b).abs().max() / scale) < tol
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-6))
+
+
+def logits_close(a, b, tol=1e-2):
+    return logits_err(a, b) < tol
+
+
+TOL = 1e-2          # north_star: bf16 results within 1e-2 relative of the fp32 reference
+
+
+def check(name, measured, tol=TOL):
+    """Assert against north_star's tolerance and record the measured error (gpurun_out/parity_errors.json)."""
+    from tests.conftest import record_parity
+    record_parity(name, measured, tol)
+    assert measured < tol, (name, measured, tol)
 
 
 @pytest.mark.parametrize("name", ["small_ws7", "mid_ws14", "full"])
@@ -37,9 +50,8 @@ def test_swin_matches_reference_golden(golden, name):
     logits = model(x.to(DEV))
     torch.cuda.synchronize()
     ref = golden["swin"][name]
-    e = rel_err(feats, ref["features"])
-    assert e < 2e-2, e
-    assert logits_close(logits, ref["logits"], 2e-2), (logits.cpu(), ref["logits"])
+    check(f"swin[{name}].features rel-L2 vs reference-module golden", rel_err(feats, ref["features"]))
+    check(f"swin[{name}].logits max-rel vs reference-module golden", logits_err(logits, ref["logits"]))
     assert torch.equal(logits.cpu().argmax(1), ref["logits"].argmax(1))
 
 
@@ -52,7 +64,7 @@ def test_swin_block_taps_against_oracle():
     ref = oswin.forward_features(model.state_dict(), cases.swin_geometry(name), x, taps=taps)
     feats = model.to(DEV).forward_features(x.to(DEV))
     torch.cuda.synchronize()
-    assert rel_err(feats, ref) < 2e-2
+    check("swin[small_ws7].features rel-L2 vs oracle", rel_err(feats, ref))
 
 
 def test_swin_boundary_errors():
@@ -78,11 +90,12 @@ def test_unixcoder_matches_oracle(golden, full):
     vec, _ = md.get_repr(ids.to(DEV))
     tok, _ = md.get_xcode_vec(ids.to(DEV))
     torch.cuda.synchronize()
-    assert rel_err(vec, sent_ref) < 1.5e-2, rel_err(vec, sent_ref)
+    tag = "full" if full else "small"
+    check(f"unixcoder[{tag}].sentence rel-L2 vs oracle", rel_err(vec, sent_ref))
     if not full:
-        assert rel_err(vec, golden["roberta"]["sent"]) < 1.5e-2
+        check("unixcoder[small].sentence rel-L2 vs HF golden", rel_err(vec, golden["roberta"]["sent"]))
     mask = ids.ne(cfg.pad_token_id).unsqueeze(-1).float()
-    assert rel_err(tok.cpu() * mask, tok_ref * mask) < 2e-2
+    check(f"unixcoder[{tag}].tokens rel-L2 vs oracle", rel_err(tok.cpu() * mask, tok_ref * mask))
     assert torch.isfinite(tok).all()
 
 
@@ -95,7 +108,7 @@ def test_fusion_matches_oracle(golden):
     ref = golden["graph"]["fusion_logits"]
     logits = model.to(DEV)(g.to(DEV), img.to(DEV), txt.to(DEV))
     torch.cuda.synchronize()
-    assert logits_close(logits, ref, 2e-2), (logits.cpu(), ref)
+    check("fusion.logits max-rel vs oracle golden", logits_err(logits, ref))
     assert torch.equal(logits.cpu().argmax(1), ref.argmax(1))
 
 
@@ -157,9 +170,9 @@ def test_ggnn_matches_oracle(golden):
     h = md.node_states(gd)
     prob, logit = md(gd)
     torch.cuda.synchronize()
-    assert rel_err(h, h_r) < 2e-2, rel_err(h, h_r)
-    assert rel_err(md._last_sum, sum_r) < 2e-2
-    assert logits_close(logit, logit_r, 2e-2)
+    check("ggnn.node_states rel-L2 vs oracle", rel_err(h, h_r))
+    check("ggnn.graph_sums rel-L2 vs oracle", rel_err(md._last_sum, sum_r))
+    check("ggnn.logits max-rel vs oracle", logits_err(logit, logit_r))
     # edge types outside [0, n_etypes) are rejected like DGL's assert
     gd.edata["_ETYPE"] = gd.edata["_ETYPE"] + 10
     with pytest.raises(AssertionError):
@@ -194,7 +207,7 @@ def test_composed_forward_matches_oracle():
     ref = ofusion.fusion_forward(model.fusion.state_dict(), cases.to_host_batch(g), f_img, f_txt)
     out = model.to(DEV)(img.to(DEV), ids.to(DEV), g.to(DEV))
     torch.cuda.synchronize()
-    assert logits_close(out, ref, 2e-2), (out.cpu(), ref)
+    check("composed[small].logits max-rel vs oracle", logits_err(out, ref))
     assert torch.equal(out.cpu().argmax(1), ref.argmax(1))
 
 
@@ -358,7 +371,7 @@ def test_edge_cases_ragged_and_extreme_sizes():
     sw = cases.make_swin("small_ws7")
     x = synth.images(1, cases.SWIN_CASES["small_ws7"]["img_size"], seed=2)
     r = oswin.forward_features(sw.state_dict(), cases.swin_geometry("small_ws7"), x)
-    assert rel_err(sw.to(DEV).forward_features(x.to(DEV)), r) < 2e-2
+    check("swin[small_ws7, batch 1].features rel-L2 vs oracle", rel_err(sw.to(DEV).forward_features(x.to(DEV)), r))
 
 
 def test_swin_sub_batches_on_streams_give_identical_features():
