@@ -79,6 +79,7 @@ SIGNATURES = {
     "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 13 + [_P, _P],
 }
 
+_SYNC_EACH = bool(os.environ.get("MVULD_SYNC_EACH"))     # debug: synchronise after every call and name the one that faulted
 _lib = None
 launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
 _LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3, "mvuld_sumsq_f32": 2}
@@ -143,7 +144,16 @@ def call(name: str, *args):
         msg = lib.mvuld_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{name} failed (code {rc}): {msg}")
     launch_count += _LAUNCHES_PER_CALL.get(name, 1)
+    if _SYNC_EACH:
+        _sync_check(name)
     return rc
+
+
+def _sync_check(name: str):
+    try:
+        torch.cuda.synchronize()
+    except Exception as exc:                                  # noqa: BLE001
+        raise RuntimeError(f"{name}: device fault surfaced after this call: {exc}") from exc
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -176,6 +186,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act=ACT_NONE, res=None, ou
     if rc != 0:
         raise RuntimeError(f"mvuld_gemm_bf16 failed (code {rc}): {lib.mvuld_last_error().decode()}")
     launch_count += 1
+    if _SYNC_EACH:
+        _sync_check(f"mvuld_gemm_bf16[M={M},N={N},K={K}]")
 
 
 def gemm_ln(a: torch.Tensor, w: torch.Tensor, gamma, beta, eps: float, bias=None, shortcut=None, x32=None, xb=None):

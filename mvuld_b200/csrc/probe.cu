@@ -74,7 +74,8 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 using namespace mv;
 
 // A: 16-bit [a_rows, a_inner] row-major, B: 16-bit [b_rows, b_inner] row-major; each loaded as ONE box with the given
-// swizzle.  fmt: 0 = fp16, 1 = bf16.  a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
+// swizzle.  fmt: 0 = fp16, 1 = bf16 (both operands: a bf16 A with an fp16 B, tried here on a B200, raises an illegal
+// instruction -- kind::f16 wants one format for A and B).  a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
 extern "C" int mvuld_probe_umma(const void* A, int a_inner, int a_rows, int a_swizzle, const void* B, int b_inner,
                                 int b_rows, int b_swizzle, int N, int nk, int a_step, int b_step, int a_lbo, int a_sbo,
                                 int a_layout, int b_lbo, int b_sbo, int b_layout, int a_mn, int b_mn, int fmt,

@@ -156,6 +156,7 @@ class Multi_DefectModel_new_GCN(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._plan = None
+        self._engine = None                 # the flat training buffers belong to the old device / dtype
         return super()._apply(fn, *a, **k)
 
     def raise_if_invalid(self):
@@ -288,9 +289,28 @@ class Multi_DefectModel_new_GCN(nn.Module):
             self.raise_if_invalid()                      # bound the backlog of a caller that never asks
         return logits
 
-    @torch.no_grad()
+    def train(self, mode: bool = True):
+        """Switching between train and eval drops the packed eval-mode plan: an optimiser may have changed the
+        parameters, and train-mode forwards move the BatchNorm running statistics the plan folds in."""
+        self._plan = None
+        return super().train(mode)
+
+    def train_engine(self):
+        """The flat-buffer training engine behind the train-mode ``forward`` (``mvuld_b200.train.FusionTrainer`` used
+        for its forward / backward launch sequences only; created on first use, re-created when the model moves)."""
+        eng = getattr(self, "_engine", None)
+        if eng is None or eng.flat_p.device != self.fc.weight.device:
+            from .train import FusionTrainer
+            eng = FusionTrainer(self, world_size=1)
+            self._engine = eng
+        return eng
+
     def forward(self, g: Graph, img_embedding: torch.Tensor, func_text_embedding: torch.Tensor) -> torch.Tensor:
-        """GraphModel.py:150-211."""
+        """GraphModel.py:150-211.  ``model.eval()``: the folded inference path, no autograd graph.  ``model.train()``:
+        the train-mode forward (dropout, BatchNorm on batch statistics) as ONE autograd node whose backward is the
+        hand-written backward launch sequence, so the reference loop body (main_bigvul.py:328-342:
+        ``outputs = model(...)``, ``loss_scaler(loss, optimizer, ...)`` with ``ACCUMULATION_STEPS``, any
+        ``torch.optim`` optimiser, DDP) runs against this module unchanged."""
         if not img_embedding.is_cuda:
             raise RuntimeError("mvuld_b200 fusion model takes CUDA tensors (no CPU fallback)")
         if not isinstance(g, Graph):
@@ -298,7 +318,13 @@ class Multi_DefectModel_new_GCN(nn.Module):
             g = from_dgl(g)
         if g.batch_size != img_embedding.shape[0]:
             raise ValueError(f"graph batch size {g.batch_size} != embedding batch size {img_embedding.shape[0]}")
-        return self.head(self.graph_features(g), img_embedding, func_text_embedding)
+        if self.training:
+            if type(self).HEAD_MODE != 0 or type(self).HEAD_FEATS != 3:
+                raise RuntimeError("mvuld_b200: train-mode forward is built for Multi_DefectModel_new_GCN only")
+            from .autograd import fusion_train_forward
+            return fusion_train_forward(self, g, img_embedding, func_text_embedding)
+        with torch.no_grad():
+            return self.head(self.graph_features(g), img_embedding, func_text_embedding)
 
 
 class Multi_DefectModel(nn.Module):

@@ -205,13 +205,13 @@ class FusionTrainer:
 
     # ----------------------------------------------------------------------------------------------------
     def _grad_w(self, dy: torch.Tensor, x: torch.Tensor, gname: str, rows_out: Optional[int] = None,
-                out: Optional[torch.Tensor] = None):
+                out: Optional[torch.Tensor] = None, G: Optional[torch.Tensor] = None):
         """dW [out, in] = dY^T X on the tensor cores, fp32 straight into the flat gradient buffer.  Both operands are
         transposed to K-major ([out, Rp] and [in, Rp], zero filled past the R real rows)."""
         dyT, xT = self._transpose(dy), self._transpose(x)
         if rows_out is not None:
             dyT = dyT[:rows_out]
-        _lib.gemm(dyT, xT, out_f32=self._mat(self.flat_g, gname) if out is None else out)
+        _lib.gemm(dyT, xT, out_f32=self._mat(self.flat_g if G is None else G, gname) if out is None else out)
 
     def _seed(self, layer: int) -> int:
         return (self.seed * 1000003 + self.step_count * 257 + layer) & 0x7FFFFFFFFFFFFFFF
@@ -222,10 +222,28 @@ class FusionTrainer:
                          targets: torch.Tensor, on_bucket=None):
         """Train-mode forward (GraphModel.py:150-211) + backward of the mean cross-entropy; fills ``flat_g`` (scaled
         by 1 / world so that a SUM all-reduce yields DDP's mean).  Returns (loss [1] fp32 device tensor, logits)."""
+        if not targets.is_cuda:
+            raise RuntimeError("mvuld_b200 FusionTrainer takes CUDA tensors (no CPU fallback)")
+        logits, ctx = self.forward_train(g, img_embedding, func_text_embedding)
+        B, C = logits.shape
+        dlogits = torch.empty((B, C), device=self.dev, dtype=torch.float32)
+        self.loss_buf.zero_()
+        _lib.call("mvuld_ce_loss", logits, targets.to(torch.int64).contiguous(), self.loss_buf, dlogits, B, C,
+                  1.0 / (B * self.world))
+        self.flat_g.zero_()
+        self.backward_train(ctx, dlogits, self.flat_g, on_bucket)
+        return self.loss_buf, logits
+
+    @torch.no_grad()
+    def forward_train(self, g: Graph, img_embedding: torch.Tensor, func_text_embedding: torch.Tensor,
+                      seed_index: Optional[int] = None):
+        """Train-mode forward of GraphModel.py:150-211 (dropout on, BatchNorm on batch statistics with the running
+        statistics updated).  Returns (logits [B, num_classes] fp32, ctx): ``ctx`` holds what ``backward_train`` needs.
+        ``seed_index`` selects the dropout masks of this pass (default: the optimiser step count)."""
         if not isinstance(g, Graph):
             from .graph import from_dgl
             g = from_dgl(g)
-        if not (img_embedding.is_cuda and func_text_embedding.is_cuda and targets.is_cuda):
+        if not (img_embedding.is_cuda and func_text_embedding.is_cuda):
             raise RuntimeError("mvuld_b200 FusionTrainer takes CUDA tensors (no CPU fallback)")
         m, dev = self.model, self.dev
         B, N, n = img_embedding.shape[0], g.num_nodes(), m.max_node
@@ -235,25 +253,13 @@ class FusionTrainer:
             raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d)")
         bf, f32 = torch.bfloat16, torch.float32
         e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
-        P, G, W16 = self.flat_p, self.flat_g, self.flat_w16
+        P, W16 = self.flat_p, self.flat_w16
         pv = lambda name: self._view(P, name)
-        gv = lambda name: self._view(G, name)
         w16 = lambda name: self._mat(W16, name)
         p, mom = self.p_drop, self.momentum
         R = B * n
-        G.zero_()
-        self.loss_buf.zero_()
-        bucket_i = 0
-
-        def ready(name):
-            """Every gradient up to and including ``name`` is final: hand closed buckets to the reducer."""
-            nonlocal bucket_i
-            if on_bucket is None:
-                return
-            end = self.offsets[name] + (self._view(P, name).numel() + _ALIGN - 1) // _ALIGN * _ALIGN
-            while bucket_i < len(self.buckets) and self.buckets[bucket_i][1] <= end:
-                on_bucket(self.buckets[bucket_i])
-                bucket_i += 1
+        seed_base = self.seed * 1000003 + (self.step_count if seed_index is None else int(seed_index)) * 257
+        _seed = lambda layer: (seed_base + layer) & 0x7FFFFFFFFFFFFFFF
 
         def bn_cols(prefix, x, R_, C_, res=None, ldr=0, y32=None, ldy=None, yb=None):
             bn = getattr(m, prefix) if "." not in prefix else m.get_submodule(prefix)
@@ -291,7 +297,7 @@ class FusionTrainer:
             H, F = mod._heads, mod._out
             if p > 0:                                                     # GATConv feat_drop on the input features
                 xd = e(hcur.shape, bf)
-                _lib.call("mvuld_dropout_bf16", hcur, xd, hcur.numel(), self._seed(li), p)
+                _lib.call("mvuld_dropout_bf16", hcur, xd, hcur.numel(), _seed(li), p)
             else:
                 xd = hcur
             z = e((N, H * F), bf)
@@ -311,7 +317,7 @@ class FusionTrainer:
             a = e((N, 512), bf)
             _lib.gemm(acts[-1], w16(name + ".weight"), bias=pv(name + ".bias"), act=_lib.ACT_ELU, out_bf16=a)
             if p > 0:                                                     # mlpdropout / hdropout (GraphModel.py:171,176)
-                _lib.call("mvuld_dropout_bf16", a, a, a.numel(), self._seed(8 + li), p)
+                _lib.call("mvuld_dropout_bf16", a, a, a.numel(), _seed(8 + li), p)
             acts.append(a)
             if self.debug_taps is not None and li == 0:
                 self.debug_taps["fc"] = a.clone()
@@ -356,12 +362,50 @@ class FusionTrainer:
         fn = e((B, 1536), f32)
         fin_mean, fin_rstd = bn_cols("final_fc_bn", feats, B, 1536, y32=fn)
         C = m.num_classes
-        logits, dlogits = e((B, C), f32), e((B, C), f32)
+        logits = e((B, C), f32)
         _lib.call("mvuld_linear_small", fn, pv("final_fc.weight"), pv("final_fc.bias"), logits, None, B, C, 1536)
-        _lib.call("mvuld_ce_loss", logits, targets.to(torch.int64).contiguous(), self.loss_buf, dlogits, B, C,
-                  1.0 / (B * self.world))
+        self.last = dict(zero_deg=zero_deg, graph=g, feats=feats)
+        ctx = dict(B=B, N=N, n=n, R=R, E=E, C=C, seed_base=seed_base, p=p, feats=feats, fn=fn, fin=(fin_mean, fin_rstd),
+                   img=(img32, img_n, img_stat), txt=(txt32, txt_n, txt_stat), z32=z32, inv_s=inv_s, gcn_saved=gcn_saved,
+                   zb0=zb0, hpn=hpn, hp=hp, gat_stat=(gat_mean, gat_rstd), pos=pos, offsets=offsets,
+                   box_stat=(box_mean, box_rstd), acts=acts, gat_saved=gat_saved, csr=(indptr, idx_src),
+                   out_csr=(out_indptr, out_dst, pos_in))
+        return logits, ctx
 
-        # ---------------- backward ----------------
+    @torch.no_grad()
+    def backward_train(self, ctx: dict, dlogits: torch.Tensor, G: torch.Tensor, on_bucket=None,
+                       input_grads: bool = False):
+        """Backward of ``forward_train`` from ``dlogits`` [B, num_classes] fp32: parameter gradients are WRITTEN into
+        the flat buffer ``G`` (same layout as ``flat_p``; it must be zero on entry).  With ``input_grads`` also returns
+        (d img_embedding [B, 1024], d func_text_embedding [B, 768]) fp32 -- what trainable encoders consume."""
+        m, dev = self.model, self.dev
+        B, N, n, R, E, C = ctx["B"], ctx["N"], ctx["n"], ctx["R"], ctx["E"], ctx["C"]
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+        P = self.flat_p
+        pv = lambda name: self._view(P, name)
+        gv = lambda name: self._view(G, name)
+        p = ctx["p"]
+        _seed = lambda layer: (ctx["seed_base"] + layer) & 0x7FFFFFFFFFFFFFFF
+        feats, fn, (fin_mean, fin_rstd) = ctx["feats"], ctx["fn"], ctx["fin"]
+        (img32, img_n, img_stat), (txt32, txt_n, txt_stat) = ctx["img"], ctx["txt"]
+        z32, inv_s, gcn_saved, zb0, hpn, hp = ctx["z32"], ctx["inv_s"], ctx["gcn_saved"], ctx["zb0"], ctx["hpn"], ctx["hp"]
+        (gat_mean, gat_rstd), pos, offsets, (box_mean, box_rstd) = ctx["gat_stat"], ctx["pos"], ctx["offsets"], ctx["box_stat"]
+        acts, gat_saved, (indptr, idx_src), (out_indptr, out_dst, pos_in) = ctx["acts"], ctx["gat_saved"], ctx["csr"], ctx["out_csr"]
+        dlogits = dlogits.to(torch.float32).contiguous()
+        bucket_i = 0
+        d_inputs = []
+
+        def ready(name):
+            """Every gradient up to and including ``name`` is final: hand closed buckets to the reducer."""
+            nonlocal bucket_i
+            if on_bucket is None:
+                return
+            end = self.offsets[name] + (self._view(P, name).numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            while bucket_i < len(self.buckets) and self.buckets[bucket_i][1] <= end:
+                on_bucket(self.buckets[bucket_i])
+                bucket_i += 1
+
         dfn = e((B, 1536), f32)
         _lib.call("mvuld_linear_small_bwd", fn, pv("final_fc.weight"), dlogits, dfn, gv("final_fc.weight"),
                   gv("final_fc.bias"), B, C, 1536)
@@ -376,12 +420,14 @@ class FusionTrainer:
             dpre = e((B, 512), bf)
             _lib.call("mvuld_elu_bwd_rows", _lib._Raw(dfeats[:, col0:col0 + 512]), 1536,
                       _lib._Raw(feats[:, col0:col0 + 512]), 1536, dpre, 512, B, 512)
-            self._grad_w(dpre, xn, lin + ".weight")
+            self._grad_w(dpre, xn, lin + ".weight", G=G)
             _lib.call("mvuld_colsum", dpre, 1, 512, gv(lin + ".bias"), B, 512)
             dxn = e((B, K), f32)
             _lib.gemm(dpre, self.wt[lin][:, :512], out_f32=dxn)
-            _lib.call("mvuld_bn_cols_bwd", xin, dxn, K, pv(bnname + ".weight"), stat[0], stat[1], None, None,
+            dxin = e((B, K), f32) if input_grads else None
+            _lib.call("mvuld_bn_cols_bwd", xin, dxn, K, pv(bnname + ".weight"), stat[0], stat[1], dxin, None,
                       gv(bnname + ".weight"), gv(bnname + ".bias"), B, K)
+            d_inputs.append(dxin)
         ready("bn_text.bias")
 
         # l2norm + mean, then the eight Rs_GCN blocks in reverse
@@ -393,13 +439,13 @@ class FusionTrainer:
             dw0 = e((R, 512), bf)
             _lib.call("mvuld_bn_cols_bwd", w0, dz32, 512, pv(pre + "W.1.weight"), mean, rstd, None, dw0,
                       gv(pre + "W.1.weight"), gv(pre + "W.1.bias"), R, 512)
-            self._grad_w(dw0, y, pre + "W.0.weight")
+            self._grad_w(dw0, y, pre + "W.0.weight", G=G)
             _lib.call("mvuld_colsum", dw0, 1, 512, gv(pre + "W.0.bias"), R, 512)
             dy = e((R, 512), bf)
             _lib.gemm(dw0, self.wt[f"gcn{k}.W0"][:, :512], out_bf16=dy)
             dtpg = e((R, 1536), bf)
             _lib.call("mvuld_rs_gcn_affinity_bwd", tpg, dy, dtpg, B, n, 512)
-            self._grad_w(dtpg, zin, "", out=self._gcn_cat(G, k, "weight"))
+            self._grad_w(dtpg, zin, "", out=self._gcn_cat(G, k, "weight"), G=G)
             _lib.call("mvuld_colsum", dtpg, 1, 1536, self._gcn_cat(G, k, "bias"), R, 1536)
             _lib.gemm(dtpg, self.wt[f"gcn{k}.cat"][:, :1536], res=dz32, out_bf16=dzb, out_f32=dz32)   # + residual path
             ready(pre + "g.bias")
@@ -409,7 +455,7 @@ class FusionTrainer:
         # concat(h_i, pos_i) -> ELU -> fc_gat / fc_bbox -> slot BatchNorms -> unbatch
         dpre = e((R, 512), bf)
         _lib.call("mvuld_elu_bwd", dzb, zb0, dpre, R * 512, 0, 0, 0.0)
-        self._grad_w(dpre, hpn, "fc_gat.weight", rows_out=480)
+        self._grad_w(dpre, hpn, "fc_gat.weight", rows_out=480, G=G)
         _lib.call("mvuld_colsum", dpre, 1, 512, gv("fc_gat.bias"), R, 480)
         dhpn = e((R, 512), bf)
         _lib.gemm(dpre[:, :480], self.wt["fc_gat"][:, :480], out_bf16=dhpn)
@@ -428,8 +474,8 @@ class FusionTrainer:
         for li in range(8, -1, -1):
             name = mlp[li]
             dpre = e((N, 512), bf)
-            _lib.call("mvuld_elu_bwd", dh, acts[li + 1], dpre, N * 512, 0, self._seed(8 + li), p)
-            self._grad_w(dpre, acts[li], name + ".weight")
+            _lib.call("mvuld_elu_bwd", dh, acts[li + 1], dpre, N * 512, 0, _seed(8 + li), p)
+            self._grad_w(dpre, acts[li], name + ".weight", G=G)
             _lib.call("mvuld_colsum", dpre, 1, 512, gv(name + ".bias"), N, 512)
             K = acts[li].shape[1]
             dh = e((N, K), bf)
@@ -447,20 +493,21 @@ class FusionTrainer:
             _lib.call("mvuld_gat_bwd", z, dh, el, er, indptr, idx_src, out_indptr, out_dst, pos_in,
                       pv(name + ".attn_l").view(-1), pv(name + ".attn_r").view(-1), alpha_e, ds_e, dl, dr, dz,
                       gv(name + ".attn_l").view(-1), gv(name + ".attn_r").view(-1), N, H, F, slope)
-            self._grad_w(dz, xd, name + ".fc.weight")
+            self._grad_w(dz, xd, name + ".fc.weight", G=G)
             if li == 1:
                 dxd = e((N, xd.shape[1]), bf)
                 _lib.gemm(dz, self.wt["gat2.fc"][:, :H * F], out_bf16=dxd)
                 if p > 0:
-                    _lib.call("mvuld_dropout_bf16", dxd, dxd, dxd.numel(), self._seed(li), p)
+                    _lib.call("mvuld_dropout_bf16", dxd, dxd, dxd.numel(), _seed(li), p)
                 dh = dxd
             ready(name + ".fc.weight")
         if on_bucket is not None:
             while bucket_i < len(self.buckets):
                 on_bucket(self.buckets[bucket_i])
                 bucket_i += 1
-        self.last = dict(zero_deg=zero_deg, graph=g, feats=feats)
-        return self.loss_buf, logits
+        if input_grads:
+            return d_inputs[0], d_inputs[1]
+        return None
 
     # ----------------------------------------------------------------------------------------------------
     @torch.no_grad()

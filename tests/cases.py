@@ -22,10 +22,23 @@ SWIN_CASES = {
 SWIN_BATCH = {"small_ws7": 3, "mid_ws14": 2, "full": 2}
 
 
+@torch.no_grad()
+def round_matrices_to_bf16(model):
+    """Make every weight MATRIX of ``model`` bf16-representable (values a bf16 checkpoint would hold), in place: the
+    B200 path packs matrices as bf16 GEMM operands, so with such weights the oracle and the path compute with
+    identical numbers and a parity test measures arithmetic, not weight quantisation.  Vectors (biases, norms) stay.
+    Every model-level parity case uses such weights (north_star: "identical random-init weights"); the effect of
+    quantising fp32 weights to bf16 is measured separately (tests/test_gpu_fullsize.py)."""
+    for p in model.parameters():
+        if p.dim() >= 2:
+            p.copy_(p.to(torch.bfloat16).to(p.dtype))
+    return model
+
+
 def make_swin(name: str) -> mv.SwinTransformerV2:
     torch.manual_seed(SEED)
     m = mv.SwinTransformerV2(**SWIN_CASES[name]).eval()
-    return synth.randomize_for_parity(m, seed=SEED)
+    return round_matrices_to_bf16(synth.randomize_for_parity(m, seed=SEED))
 
 
 def swin_geometry(name: str):
@@ -47,7 +60,7 @@ def roberta_small_config():
 def make_roberta(full: bool = False) -> mv.MyUniXcoder:
     torch.manual_seed(SEED)
     m = mv.build_MyUniXcoder(None if full else roberta_small_config()).eval()
-    return synth.randomize_for_parity(m, seed=SEED)
+    return round_matrices_to_bf16(synth.randomize_for_parity(m, seed=SEED))
 
 
 def roberta_geometry(cfg):
@@ -76,7 +89,7 @@ FUSION_BATCH = 4
 def make_fusion() -> mv.Multi_DefectModel_new_GCN:
     torch.manual_seed(SEED)
     m = mv.Multi_DefectModel_new_GCN(mv.default_config()).eval()
-    return synth.randomize_for_parity(m, seed=SEED)
+    return round_matrices_to_bf16(synth.randomize_for_parity(m, seed=SEED))
 
 
 GGNN_BATCH, GGNN_D, GGNN_T, GGNN_STEPS, GGNN_IN = 6, 200, 4, 6, 132
@@ -85,7 +98,7 @@ GGNN_BATCH, GGNN_D, GGNN_T, GGNN_STEPS, GGNN_IN = 6, 200, 4, 6, 132
 def make_ggnn() -> mv.GGNNSum:
     torch.manual_seed(SEED)
     m = mv.GGNNSum(GGNN_IN, GGNN_D, max_edge_types=GGNN_T, num_steps=GGNN_STEPS).eval()
-    return synth.randomize_for_parity(m, seed=SEED)
+    return round_matrices_to_bf16(synth.randomize_for_parity(m, seed=SEED))
 
 
 def to_host_batch(g):

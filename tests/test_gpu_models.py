@@ -116,7 +116,7 @@ def test_gat_ablation_variant_matches_oracle():
     """``Multi_DefectModel`` (GraphModel.py:214-304), the dgl.mean_nodes readout variant."""
     torch.manual_seed(cases.SEED)
     m = mv.Multi_DefectModel(mv.default_config()).eval()
-    synth.randomize_for_parity(m, seed=cases.SEED)
+    cases.round_matrices_to_bf16(synth.randomize_for_parity(m, seed=cases.SEED))
     g = synth.cpg_batch(5, seed=cases.SEED + 11)
     gen = torch.Generator().manual_seed(2)
     img, txt = torch.randn(5, 1024, generator=gen), torch.randn(5, 768, generator=gen)
@@ -136,7 +136,7 @@ def test_gat_free_ablation_variants_match_oracle(name):
     head variants of the live graph branch (new_model.py:81-319)."""
     torch.manual_seed(cases.SEED)
     m = mv.ABLATIONS[name](mv.default_config()).eval()
-    synth.randomize_for_parity(m, seed=cases.SEED)
+    cases.round_matrices_to_bf16(synth.randomize_for_parity(m, seed=cases.SEED))
     B = 5
     g = synth.cpg_batch(B, seed=cases.SEED + 13)           # graph sizes on both sides of the 100-slot truncation
     gen = torch.Generator().manual_seed(3)
@@ -192,7 +192,7 @@ def test_composed_forward_matches_oracle():
     cfg.freeze()
     rcfg = mv.roberta_base_config(vocab_size=1000, num_hidden_layers=2)
     model = mv.MVulD(cfg, rcfg).eval()
-    synth.randomize_for_parity(model, seed=cases.SEED)
+    cases.round_matrices_to_bf16(synth.randomize_for_parity(model, seed=cases.SEED))
     B = 3
     img = synth.images(B, 224, seed=1)
     ids = synth.token_ids(B, 512, 1000, seed=1)
