@@ -74,6 +74,12 @@ int mvuld_cpb_table(const float* w1, const float* b1, const float* w2, int nH, i
 int mvuld_swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
                                 const float* bias_max, const float* q_norm, void* out, int B, int H, int W, int C,
                                 int nH, int ws, int shift, mvuld_stream_t stream);
+/* The same operation for launches in which EVERY head meets the constant-reference condition 2 q_norm + bias_max <= 100
+ * (checked by the caller once per weight version; a violating head traps) and ws == 28: three softmax warpgroups on
+ * (query tile, key tile) units, P aliased onto S in TMEM, the row sum taken by the PV product (N = 48). */
+int mvuld_swin_window_attention_fixed(const void* q, const void* k, const void* v, const float* bias_rev,
+                                      const float* bias_max, const float* q_norm, void* out, int B, int H, int W,
+                                      int C, int nH, int ws, int shift, mvuld_stream_t stream);
 
 /* Key-padded self-attention for the text encoder: q,k,v bf16 [B, nH, L, 64] (q pre-scaled), kv_len int32 [B];
  * out bf16 [B*L, nH*64].  unixcoder.py:35-36. */
@@ -237,8 +243,11 @@ int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gamma, const f
  * mode 2); dv = gradient of the LN input as bf16 and / or fp32; dgamma / dbeta accumulated.  swin_transformer_v2.py:301,
  * 304,362; HF RobertaSelfOutput / RobertaOutput. */
 int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const float* gamma, const float* dout, void* dv_bf16,
-                      float* dv_f32, float* dgamma, float* dbeta, int M, int C, float eps, int mode,
+                      float* dv_f32, float* dgamma, float* dbeta, float* partials, int M, int C, float eps, int mode,
                       mvuld_stream_t stream);
+/* rows of the fp32 [rows, 2, C] partials workspace mvuld_ln_rows_bwd needs for M rows: dgamma / dbeta are summed over
+ * the blocks in a fixed order (bit-reproducible gradients, no atomics). */
+int mvuld_ln_rows_bwd_blocks(int M);
 /* exact (erf) GELU backward: dpre = dh * GELU'(pre), bf16, n %% 8 == 0 (Mlp, swin_transformer_v2.py:26-32). */
 int mvuld_gelu_bwd(const void* pre, const void* dh, void* dpre, long long n, mvuld_stream_t stream);
 /* fp32 strided ELU backward with a bf16 result (image / text projections, GraphModel.py:153-159). */
@@ -252,7 +261,8 @@ int mvuld_pos_slot_stats(const float* pos, const long long* offsets, const float
                          float momentum, int B, int n, mvuld_stream_t stream);
 int mvuld_pos_branch_bwd(const float* pos, const long long* offsets, const float* mean, const float* rstd,
                          const float* gamma, const float* beta, const float* w, const void* dpre, float* dw, float* db,
-                         float* dgamma, float* dbeta, int B, int n, int OUT, int ld, int col0, mvuld_stream_t stream);
+                         float* dgamma, float* dbeta, float* partials /* fp32 [n, 160] workspace */, int B, int n, int OUT,
+                         int ld, int col0, mvuld_stream_t stream);
 /* backward of unbatch_features pad / truncate (GraphModel.py:30-54). */
 int mvuld_unbatch_pad_bwd(const void* dhp, const long long* offsets, void* dh, int B, int max_node, int F,
                           mvuld_stream_t stream);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mvuld_heads_qkv": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "mvuld_cpb_table": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "mvuld_swin_window_attention": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mvuld_swin_window_attention_fixed": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_seq_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_ln_rows": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
     "mvuld_patch_embed": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
@@ -56,7 +57,8 @@ SIGNATURES = {
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_transpose_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "mvuld_colsum": [_P, _I, _I, _P, _I, _I, _P],
-    "mvuld_ln_rows_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "mvuld_ln_rows_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "mvuld_ln_rows_bwd_blocks": [_I],
     "mvuld_gelu_bwd": [_P, _P, _P, _LL, _P],
     "mvuld_elu_bwd": [_P, _P, _P, _LL, _I, C.c_ulonglong, _F, _P],
     "mvuld_dropout_bf16": [_P, _P, _LL, C.c_ulonglong, _F, _P],
@@ -64,7 +66,7 @@ SIGNATURES = {
     "mvuld_bn_cols_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "mvuld_elu_bwd_rows": [_P, _I, _P, _I, _P, _I, _I, _I, _P],
     "mvuld_pos_slot_stats": [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _I, _I, _P],
-    "mvuld_pos_branch_bwd": [_P] * 12 + [_I, _I, _I, _I, _I, _P],
+    "mvuld_pos_branch_bwd": [_P] * 13 + [_I, _I, _I, _I, _I, _P],
     "mvuld_bn_slot_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P],
     "mvuld_bn_slot_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_unbatch_pad_bwd": [_P, _P, _P, _I, _I, _I, _P],
@@ -82,7 +84,8 @@ SIGNATURES = {
 _SYNC_EACH = bool(os.environ.get("MVULD_SYNC_EACH"))     # debug: synchronise after every call and name the one that faulted
 _lib = None
 launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3, "mvuld_sumsq_f32": 2}
+_LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3, "mvuld_sumsq_f32": 2,
+                      "mvuld_ln_rows_bwd": 2, "mvuld_pos_branch_bwd": 2}
 
 
 def load() -> C.CDLL:
@@ -147,6 +150,11 @@ def call(name: str, *args):
     if _SYNC_EACH:
         _sync_check(name)
     return rc
+
+
+def ln_rows_bwd_partials(M: int, C: int, device) -> torch.Tensor:
+    """Workspace of ``mvuld_ln_rows_bwd`` for M rows of C columns (fixed-order dgamma / dbeta reduction)."""
+    return torch.empty(load().mvuld_ln_rows_bwd_blocks(int(M)) * 2 * C, device=device, dtype=torch.float32)
 
 
 def _sync_check(name: str):

@@ -5,8 +5,12 @@
   geometry, a v1 ``relative_position_bias_table`` / ``absolute_pos_embed`` of another size is bicubically resized, a
   classifier head of another width is re-initialised to zero -- then ``load_state_dict(strict=False)``.
 * ``save_checkpoint`` / ``load_checkpoint``: the reference's file layout ``{model, optimizer, lr_scheduler,
-  max_accuracy, scaler, epoch, config}``.  ``optimizer`` holds the ``FusionTrainer`` state (flat AdamW moments, step
-  count, hyper-parameters) instead of ``torch.optim.AdamW``'s per-parameter dict.
+  max_accuracy, scaler, epoch, config}``.  ``optimizer`` is in ``torch.optim.AdamW.state_dict()``'s own layout
+  (``FusionTrainer.state_dict`` converts its flat moments to per-parameter ``{step, exp_avg, exp_avg_sq}`` entries in
+  ``build_optimizer``'s group order, optimizer.py:35-50, and back), ``scaler`` in ``torch.amp.GradScaler.state_dict()``'s
+  (scale 1: the bf16 step needs no loss scaling), so a checkpoint written here resumes in ``utils_multi.load_checkpoint``
+  and a reference checkpoint resumes here.  Files are read with ``weights_only=True`` first (tensors and plain
+  containers); a reference checkpoint that pickles its yacs ``config`` node needs ``trusted=True``.
 
 State-dict KEYS are the reference's own (tests load this package's weights into the reference classes with
 ``strict=True``), so reference checkpoints load into these models and vice versa.
@@ -20,10 +24,26 @@ import torch
 _DERIVED = ("relative_position_index", "relative_coords_table", "attn_mask")
 
 
-def load_pretrained(model, checkpoint, logger=None):
+def _read(path: str, trusted: bool = False):
+    """``torch.load`` restricted to tensors / plain containers unless the caller vouches for the file (a pickled yacs
+    node, as the reference's ``save_checkpoint`` writes under ``config``, executes code on load)."""
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:                                  # noqa: BLE001 -- the unpickler's error types vary by version
+        if not trusted:
+            raise RuntimeError(f"{path} holds objects beyond tensors and plain containers ({type(e).__name__}: {e}); "
+                               "pass trusted=True to unpickle it if you trust its origin") from e
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
+#: ``torch.amp.GradScaler().state_dict()`` keys; scale 1 = no loss scaling (bf16 step), loadable by the reference's scaler
+SCALER_STATE = {"scale": 1.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 0}
+
+
+def load_pretrained(model, checkpoint, logger=None, trusted: bool = False):
     """utils_multi.py:35-122.  ``checkpoint``: a path, a ``{'model': state_dict}`` dict or a bare state dict."""
     if isinstance(checkpoint, str):
-        checkpoint = torch.load(checkpoint, map_location="cpu", weights_only=False)
+        checkpoint = _read(checkpoint, trusted)
     state_dict = dict(checkpoint["model"] if "model" in checkpoint else checkpoint)
     for k in [k for k in state_dict if any(d in k for d in _DERIVED)]:
         del state_dict[k]                                          # always re-derived (utils_multi.py:40-53)
@@ -71,15 +91,18 @@ def save_checkpoint(path: str, epoch: int, model, trainer=None, max_accuracy: fl
     """utils_multi.py:125-137 file layout."""
     state = {"model": {k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
              "optimizer": trainer.state_dict() if trainer is not None else None,
-             "lr_scheduler": lr_scheduler or {}, "max_accuracy": max_accuracy, "scaler": {}, "epoch": epoch,
+             "lr_scheduler": lr_scheduler or {}, "max_accuracy": max_accuracy, "scaler": dict(SCALER_STATE),
+             "epoch": epoch,
+             # the yaml text of the node: a pickled CfgNode would make the file unreadable under weights_only=True
              "config": config.dump() if hasattr(config, "dump") else config}
     torch.save(state, path)
     return path
 
 
-def load_checkpoint(path_or_dict, model, trainer=None, eval_mode: bool = False):
-    """utils_multi.py:7-32 -> (max_accuracy, epoch).  Optimiser state is restored unless ``eval_mode``."""
-    ck = torch.load(path_or_dict, map_location="cpu", weights_only=False) if isinstance(path_or_dict, str) else path_or_dict
+def load_checkpoint(path_or_dict, model, trainer=None, eval_mode: bool = False, trusted: bool = False):
+    """utils_multi.py:7-32 -> (max_accuracy, epoch).  Optimiser state (this package's or a reference
+    ``torch.optim.AdamW`` one) is restored unless ``eval_mode``."""
+    ck = _read(path_or_dict, trusted) if isinstance(path_or_dict, str) else path_or_dict
     model.load_state_dict(ck["model"], strict=False)      # copies INTO the trainer's flat buffer when one owns the weights
     if hasattr(model, "invalidate"):
         model.invalidate()

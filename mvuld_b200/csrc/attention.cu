@@ -686,6 +686,410 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =========================================================================================================
+// attn_swin3_kernel: SwinV2 window attention for 28x28 windows (784 tokens, head dim 32) on heads whose softmax can
+// use the CONSTANT reference |q^| + max bias (2 |q^| + max bias <= 100, see attn_fwd_kernel) -- every head of a model
+// whose logit scales stay below ~ln 27, the initialisation (ln 10) included.  Same arithmetic per score as
+// attn_fwd_kernel<MODE_SWIN>, different schedule:
+//  * THREE softmax warpgroups (12 warps, 3 per SM sub-partition instead of 2) hide the TMEM / mbarrier hand-offs that
+//    left the MUFU pipe idle half of the time with two (profiles/r1_ncu_attn.md: XU 52 %, issue 49 %).
+//  * Work units are (query tile t, key tile j), dealt round-robin to the groups: the 49 units of a head split 17/16/16
+//    instead of 4/3 query tiles.  A constant reference needs no per-row state between key tiles, so the groups that
+//    share a query tile just accumulate into the SAME O accumulator (two O buffers, alternating by query tile).
+//  * P (bf16) overwrites the S columns it was computed from (the sweep reads S in pieces ahead of the P stores), so a
+//    group owns ONE 112-column TMEM buffer: 3 x 128 + 2 x 64 columns.
+//  * The row sum comes out of the tensor core: the PV product runs with N = 48, the extra 16 columns of the B operand
+//    are a [1, 0, ..] block in shared memory (second MN atom of the descriptor, reached through its leading byte
+//    offset), so O[:, 32] = sum_k P[q, k] of exactly the bf16 P the numerator used -- no FADD chain in the sweep and
+//    no cross-group merge of partial sums.
+// Warp roles: 0 TMA producer, 1 QK^T issuer, 2 PV issuer (+ TMEM owner), 3 idle, 4-15 softmax groups 0-2 (thread ==
+// query row == TMEM lane).  The group that sweeps unit (t, 6) also writes tile t's output.
+// =========================================================================================================
+constexpr int A3_THREADS = 512;
+constexpr int A3_G = 3;
+constexpr int A3_KT = 112;
+constexpr int A3_NT = 7;                    // query tiles == key tiles of a 784-token window
+constexpr int A3_NU = A3_NT * A3_NT;
+constexpr int A3_NO = 48;                   // PV accumulator columns: 32 head dims + the row-sum column (+ 15 unused)
+constexpr int A3_REGS_CTRL = 80;
+constexpr int A3_REGS_SOFTMAX = 144;        // 128 * 80 + 384 * 144 = 65536 = 512 threads * 128 registers at launch
+
+__host__ __device__ constexpr int a3_smem_bytes(int table_floats) {
+  return 2 * A3_NT * A3_KT * 64 + 1024 /*ones*/ + 2 * ATT_BM * 64 + ((table_floats * 4 + 1023) / 1024) * 1024 +
+         512 /*barriers*/ + ATT_MERGE_BYTES + 1024 /*align*/;
+}
+
+template <int WS>
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQ16, AttnParams p) {
+  constexpr int HD = 32, KT = A3_KT;
+  using L = AttnLayout<HD>;
+  constexpr int SIDE = 2 * WS - 1;
+  constexpr int TSTRIDE = att_tab_stride(WS);
+  constexpr int TBL = SIDE * TSTRIDE;
+  constexpr int ROWS_PER_TILE = KT / WS;
+  constexpr int SPLIT = WS - WS / 2;
+  constexpr int NSEG = ROWS_PER_TILE * 2;
+  constexpr int NCH = KT / 8;
+  constexpr int PW = KT / 2;
+  static_assert(WS * WS == A3_NT * KT && WS * WS == (A3_NT - 1) * ATT_BM + ATT_SPLIT_ROWS, "784-token windows only");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + A3_NT * KT * 64;
+  uint8_t* sOnes = sV + A3_NT * KT * 64;                       // 16 keys x 64 B: column 0 = 1.0 (64 B swizzle applied)
+  uint8_t* sQ = sOnes + 1024;
+  float* sTab = reinterpret_cast<float*>(sQ + 2 * L::Q_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sTab) + ((TBL * 4 + 1023) / 1024) * 1024);
+  uint64_t* k_full = bars;                    // [7]
+  uint64_t* v_full = k_full + A3_NT;          // [7]
+  uint64_t* q_full = v_full + A3_NT;          // [2]
+  uint64_t* q_empty = q_full + 2;             // [2]
+  uint64_t* s_full = q_empty + 2;             // [3]  S of the group's current unit is in TMEM
+  uint64_t* p_full = s_full + A3_G;           // [3]  P of the group's current unit is in TMEM
+  uint64_t* pv_done = p_full + A3_G;          // [3]  PV of the group's current unit retired: its buffer is free
+  uint64_t* tile_done = pv_done + A3_G;       // [2]  all seven PV products of a query tile retired
+  uint64_t* o_free = tile_done + 2;           // [2]  the tile's output has been read out of its O buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  float* sMerge = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [128][33]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.x;
+  const int head = bh % p.nH;
+  const int bwin = bh / p.nH;
+
+  const float bmax = __ldg(p.bias_max + head);
+  const float q_norm = __ldg(p.q_norm + head);
+  if (!(2.0f * q_norm + bmax <= 100.0f)) __trap();   // the host promised constant-reference heads (entry point contract)
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmQ16);
+    for (int i = 0; i < A3_NT; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+      mbar_init(&tile_done[b], 1);
+      mbar_init(&o_free[b], 4);
+    }
+    for (int g = 0; g < A3_G; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&pv_done[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  {
+    const float* src = p.bias_rev + (size_t)head * SIDE * SIDE;
+    for (int i = threadIdx.x; i < SIDE * SIDE; i += A3_THREADS) sTab[(i / SIDE) * TSTRIDE + (i % SIDE)] = __ldg(src + i);
+    // ones block: key row k, logical 16-byte chunk 0 sits at physical chunk (k >> 1) & 3 under the 64 B swizzle
+    if (threadIdx.x < 64) {
+      const int k = threadIdx.x >> 2, c = threadIdx.x & 3;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (c == ((k >> 1) & 3)) val.x = 0x3f80u;                // bf16 1.0 in element 0
+      *reinterpret_cast<uint4*>(sOnes + k * 64 + c * 16) = val;
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    reg_dec<A3_REGS_CTRL>();
+    if (warp == 0) {
+      // =========================================== TMA producer ===========================================
+      if (lane == 0) {
+        auto load_q = [&](int t) {
+          const int b = t & 1;
+          mbar_arrive_expect_tx(&q_full[b], L::Q_BYTES);
+          if (t == A3_NT - 1) {
+            for (int u = 0; u < ATT_BM / ATT_SPLIT_ROWS; ++u)
+              tma_load_3d(sQ + b * L::Q_BYTES + u * ATT_SPLIT_ROWS * L::ROW_BYTES, &tmQ16, &q_full[b], 0, t * ATT_BM, bh);
+          } else {
+            tma_load_3d(sQ + b * L::Q_BYTES, &tmQ, &q_full[b], 0, t * ATT_BM, bh);
+          }
+        };
+        load_q(0);
+        for (int j = 0; j < A3_NT; ++j) {
+          mbar_arrive_expect_tx(&k_full[j], KT * 64);
+          tma_load_3d(sK + j * KT * 64, &tmK, &k_full[j], 0, j * KT, bh);
+          if (j == 0) load_q(1);
+          mbar_arrive_expect_tx(&v_full[j], KT * 64);
+          tma_load_3d(sV + j * KT * 64, &tmV, &v_full[j], 0, j * KT, bh);
+        }
+        for (int t = 2; t < A3_NT; ++t) {
+          mbar_wait(&q_empty[t & 1], ((t - 2) >> 1) & 1, 10);
+          load_q(t);
+        }
+      }
+    } else if (warp == 1) {
+      // ============================================ QK^T issuer ============================================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, KT, 0, 0) & ~((1u << 7) | (1u << 10));   // fp16 operands
+        const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
+        for (int u = 0; u < A3_NU; ++u) {
+          const int t = u / A3_NT, j = u - t * A3_NT, g = u % A3_G, n = u / A3_G;
+          if (j == 0) mbar_wait(&q_full[t & 1], (t >> 1) & 1, 20);
+          if (t == 0) mbar_wait(&k_full[j], 0, 21);
+          if (n > 0) mbar_wait(&pv_done[g], (n - 1) & 1, 22);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint64_t ad = make_smem_desc(q0 + (t & 1) * L::Q_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
+            const uint64_t bd = make_smem_desc(k0 + j * KT * 64 + k * 32, 16, L::SBO, L::LAYOUT);
+            umma_ss(tmem_base + g * 128, ad, bd, idesc_s, k != 0);
+          }
+          umma_commit(&s_full[g]);
+          if (j == A3_NT - 1) umma_commit(&q_empty[t & 1]);
+        }
+      }
+    } else if (warp == 2) {
+      // ============================================= PV issuer =============================================
+      if (lane == 0) {
+        constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, A3_NO, 0, 1);
+        const uint32_t v0 = smem_u32(sV), ones = smem_u32(sOnes);
+        for (int u = 0; u < A3_NU; ++u) {
+          const int t = u / A3_NT, j = u - t * A3_NT, g = u % A3_G, n = u / A3_G;
+          mbar_wait(&p_full[g], n & 1, 23);
+          if (j == 0 && t >= 2) mbar_wait(&o_free[t & 1], ((t - 2) >> 1) & 1, 24);
+          if (t == 0) mbar_wait(&v_full[j], 0, 25);
+          tc_fence_after();
+          const uint32_t tO = tmem_base + 3 * 128 + (t & 1) * 64;
+          const uint32_t tP = tmem_base + g * 128;
+#pragma unroll
+          for (int s = 0; s < KT / 16; ++s) {
+            const uint32_t b0 = v0 + (j * KT + s * 16) * 64;
+            // MN-major B: first MN atom = the 32 head dims of V, second atom (leading byte offset) = the ones block
+            const uint64_t bd = make_smem_desc(b0, ones - b0, L::SBO, L::LAYOUT);
+            umma_ts(tO, tP + s * 8, bd, idesc_pv, (j != 0) || (s != 0));
+          }
+          umma_commit(&pv_done[g]);
+          if (j == A3_NT - 1) umma_commit(&tile_done[t & 1]);
+        }
+      }
+    }
+  } else {
+    // ========================================= softmax warpgroups =========================================
+    reg_inc<A3_REGS_SOFTMAX>();
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + g * 128 + lane_off;
+
+    const int nWw = p.W / WS;
+    const int wr = (bwin % ((p.H / WS) * nWw)) / nWw;
+    const int wc = (bwin % ((p.H / WS) * nWw)) % nWw;
+    const bool rowflag = p.shift > 0 && (wr == p.H / WS - 1);
+    const bool colflag = p.shift > 0 && (wc == nWw - 1);
+    const float NEG100 = -100.0f * 1.4426950408889634f;
+    const float m_ref = q_norm + bmax;
+
+    int n = 0;
+    for (int u = g; u < A3_NU; u += A3_G, ++n) {
+      const int t = u / A3_NT, j = u - t * A3_NT;
+      const bool split_t = (t == A3_NT - 1);
+      const int i = t * ATT_BM + (split_t ? (r & (ATT_SPLIT_ROWS - 1)) : r);
+      int hi = i / WS;
+      const int wi = i - hi * WS;
+      if (hi > WS - 1) hi = WS - 1;
+      const bool ri = hi >= SPLIT, ci = wi >= SPLIT;
+
+      if (split_t && (j >> 1) != quarter) {
+        // split remainder tile, key tile owned by another warp's lanes: P = 0
+        mbar_wait(&s_full[g], n & 1, 30);
+        tc_fence_after();
+        uint32_t zero[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) zero[q] = 0u;
+        tmem_st32p(tS, zero);
+        tmem_st16p(tS + 32, zero);
+        tmem_st8p(tS + 48, zero);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      } else {
+        float csm[NSEG];
+        const float* tb[ROWS_PER_TILE];
+#pragma unroll
+        for (int rr = 0; rr < ROWS_PER_TILE; ++rr) {
+          const int hj = j * ROWS_PER_TILE + rr;
+          const bool rdiff = rowflag && ((hj >= SPLIT) != ri);
+          csm[2 * rr] = ((rdiff || (colflag && ci)) ? NEG100 : 0.f) - m_ref;          // wj <  SPLIT
+          csm[2 * rr + 1] = ((rdiff || (colflag && !ci)) ? NEG100 : 0.f) - m_ref;     // wj >= SPLIT
+          tb[rr] = sTab + (hi - hj + WS - 1) * TSTRIDE + (WS - 1 - wi);
+        }
+        if (split_t && (r >> 4) != j) {
+          // the other 16-lane group of this warp owns key tile j: every term flushes to 0
+#pragma unroll
+          for (int s = 0; s < NSEG; ++s) csm[s] = -INFINITY;
+        }
+
+        mbar_wait(&s_full[g], n & 1, 30);
+        tc_fence_after();
+        uint32_t sv[KT];
+        float bb[3][8];
+        uint32_t pw[PW];
+        tmem_ld32p(tS, sv);
+        tmem_ld32p(tS + 32, sv + 32);
+        tmem_ld_wait();
+        // Software pipeline over 8-column chunks (see attn_fwd_kernel): A bias LDS | B adds | C ex2 | D bf16 pack.
+        // S columns 64.. are pulled in while the first chunks are in flight; P words go back to TMEM eight at a time,
+        // always into columns whose S values are already in registers.
+#pragma unroll
+        for (int st = 0; st < NCH + 3; ++st) {
+          if (st == 4) tmem_ld32p(tS + 64, sv + 64);
+          if (st == 8) {
+            tmem_ld_wait();
+            tmem_ld16p(tS + 96, sv + 96);
+          }
+          if (st == 12) tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (st >= 2 && st < NCH + 2) {                   // stage C
+              const int c = (st - 2) * 8 + q;
+              sv[c] = __float_as_uint(ex2_approx(__uint_as_float(sv[c])));
+            }
+            if (st < NCH) {                                  // stage A
+              const int c = st * 8 + q;
+              bb[st % 3][q] = tb[c / WS][c % WS];
+            }
+            if (st >= 1 && st < NCH + 1 && (q & 1) == 0) {   // stage B
+              const int k = st - 1;
+              const int c = k * 8 + q;
+              const int seg = (c / WS) * 2 + ((c % WS) >= SPLIT ? 1 : 0);
+              const int seg1 = ((c + 1) / WS) * 2 + (((c + 1) % WS) >= SPLIT ? 1 : 0);
+              uint64_t x = add2(pack2u(sv[c], sv[c + 1]), pack2f(csm[seg], csm[seg1]));
+              x = add2(x, pack2f(bb[k % 3][q], bb[k % 3][q + 1]));
+              unpack2u(x, sv[c], sv[c + 1]);
+            }
+            if (st >= 3 && (q & 1) == 1) {                   // stage D
+              const int c = (st - 3) * 8 + q - 1;
+              pw[c >> 1] = pack_bf16x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+            }
+          }
+          if (st >= 4 && (st & 1) == 0) tmem_st8p(tS + 4 * (st - 2) - 8, pw + 4 * (st - 2) - 8);   // words [4(st-2)-8, 4(st-2))
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+
+      if (j == A3_NT - 1) {
+        // ---- output of query tile t: O / l -> bf16, token-major store (window_reverse + inverse shift folded in) ----
+        mbar_wait(&tile_done[t & 1], (t >> 1) & 1, 31);
+        tc_fence_after();
+        const uint32_t tO = tmem_base + 3 * 128 + (t & 1) * 64 + lane_off;
+        uint32_t o[32], o2[16];
+        tmem_ld32(tO, o);
+        tmem_ld16(tO + 32, o2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t & 1]);
+        const int b = bwin / ((p.H / WS) * nWw);
+        if (split_t) {
+          float* mrow = sMerge + r * ATT_MERGE_LD;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) mrow[q] = __uint_as_float(o[q]);
+          mrow[32] = __uint_as_float(o2[0]);
+          named_bar_sync(1 + g, 128);
+          const int qq = r & (ATT_SPLIT_ROWS - 1), cg = (r >> 4) * 4;   // this thread: query qq, O columns cg .. cg + 3
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, lsum = 0.f;
+#pragma unroll
+          for (int v8 = 0; v8 < ATT_BM / ATT_SPLIT_ROWS; ++v8) {
+            const float* src = sMerge + (v8 * ATT_SPLIT_ROWS + qq) * ATT_MERGE_LD;
+            a0 += src[cg];
+            a1 += src[cg + 1];
+            a2 += src[cg + 2];
+            a3 += src[cg + 3];
+            lsum += src[32];
+          }
+          const float invs = lsum > 0.f ? 1.0f / lsum : 0.f;
+          const int hl = i / WS, wl = i - hl * WS;
+          int hh = wr * WS + hl + p.shift;
+          if (hh >= p.H) hh -= p.H;
+          int ww = wc * WS + wl + p.shift;
+          if (ww >= p.W) ww -= p.W;
+          const size_t orow_s = (size_t)b * p.H * p.W + (size_t)hh * p.W + ww;
+          uint2 w2;
+          w2.x = pack_bf16x2(a0 * invs, a1 * invs);
+          w2.y = pack_bf16x2(a2 * invs, a3 * invs);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow_s * p.C + head * HD + cg) = w2;
+        } else {
+          const float lsum = __uint_as_float(o2[0]);
+          const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+          const int hl = i / WS, wl = i - hl * WS;
+          int hh = wr * WS + hl + p.shift;
+          if (hh >= p.H) hh -= p.H;
+          int ww = wc * WS + wl + p.shift;
+          if (ww >= p.W) ww -= p.W;
+          const size_t orow = (size_t)b * p.H * p.W + (size_t)hh * p.W + ww;
+          bf16* op = reinterpret_cast<bf16*>(p.out) + orow * p.C + head * HD;
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[q]) * inv, __uint_as_float(o[q + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[q + 2]) * inv, __uint_as_float(o[q + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[q + 4]) * inv, __uint_as_float(o[q + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[q + 6]) * inv, __uint_as_float(o[q + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + q) = w;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int WS>
+static int launch_attn_swin3(const void* q, const void* k, const void* v, int n_bh, const AttnParams& p,
+                             cudaStream_t stream) {
+  using L = AttnLayout<32>;
+  constexpr int TBL = (2 * WS - 1) * att_tab_stride(WS);
+  const int smem = a3_smem_bytes(TBL);
+  MV_CHECK_ARG(smem <= 232448, "attention: %d B shared memory needed, 232448 available", smem);
+  CUtensorMap tmQ, tmK, tmV, tmQ16;
+  uint64_t dq[3] = {32, (uint64_t)p.Nq, (uint64_t)n_bh};
+  uint64_t sq[2] = {64, (uint64_t)p.Nq * 64};
+  uint32_t bq[3] = {32, ATT_BM, 1};
+  int rc = make_tmap_16b(&tmQ, q, 3, dq, sq, bq, L::SWZ);
+  if (rc) return rc;
+  uint32_t bk[3] = {32, (uint32_t)A3_KT, 1};
+  rc = make_tmap_16b(&tmK, k, 3, dq, sq, bk, L::SWZ);
+  if (rc) return rc;
+  rc = make_tmap_16b(&tmV, v, 3, dq, sq, bk, L::SWZ);
+  if (rc) return rc;
+  uint32_t bq16[3] = {32, ATT_SPLIT_ROWS, 1};
+  rc = make_tmap_16b(&tmQ16, q, 3, dq, sq, bq16, L::SWZ);
+  if (rc) return rc;
+  auto kern = attn_swin3_kernel<WS>;
+  MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<n_bh, A3_THREADS, smem, stream>>>(tmQ, tmK, tmV, tmQ16, p);
+  MV_LAUNCH_OK();
+  return 0;
+}
+
 template <int MODE, int HD, int WS, int KT, bool QK_FP16>
 static int launch_attn(const void* q, const void* k, const void* v, int n_bh, const AttnParams& p,
                        cudaStream_t stream) {
@@ -829,6 +1233,28 @@ extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const v
     case 7: return launch_attn<MODE_SWIN, 32, 7, 112, true>(q, k, v, n_bh, p, stream);
     default: return mv::fail(-1, "swin attention: window %d not instantiated (7, 14, 28)", ws);
   }
+}
+
+// Same operation for launches whose heads ALL satisfy the constant-reference condition 2 |q^| + max bias <= 100 (log2
+// units; the caller checks it once per weight version -- a violating head traps): the three-group kernel above.
+extern "C" int mvuld_swin_window_attention_fixed(const void* q, const void* k, const void* v, const float* bias_rev,
+                                                 const float* bias_max, const float* q_norm, void* out, int B, int H,
+                                                 int W, int C, int nH, int ws, int shift, cudaStream_t stream) {
+  MV_CHECK_ARG(C == nH * 32, "swin attention: head_dim must be 32");
+  MV_CHECK_ARG(ws == 28, "swin attention (constant reference): 28x28 windows only, use mvuld_swin_window_attention");
+  MV_CHECK_ARG(H % ws == 0 && W % ws == 0, "swin attention: window must tile the token grid");
+  MV_CHECK_ARG(shift == 0 || shift == ws / 2, "swin attention: shift must be 0 or ws/2");
+  MV_CHECK_ARG(q_norm != nullptr && bias_max != nullptr, "swin attention (constant reference): q_norm / bias_max are null");
+  AttnParams p{};
+  p.Nq = p.Nkv = ws * ws;
+  p.nH = nH;
+  p.bias_rev = bias_rev;
+  p.bias_max = bias_max;
+  p.q_norm = q_norm;
+  p.H = H; p.W = W; p.shift = shift; p.C = C;
+  p.out = out;
+  const int n_bh = B * (H / ws) * (W / ws) * nH;
+  return launch_attn_swin3<28>(q, k, v, n_bh, p, stream);
 }
 
 static int seq_attention(const void* q, const void* k, const void* v, const int* kv_len, const int* seg_lo,

@@ -48,25 +48,58 @@ __device__ __forceinline__ float ldf<float>(const float* p, size_t i) { return p
 template <>
 __device__ __forceinline__ float ldf<bf16>(const bf16* p, size_t i) { return __bfloat162float(p[i]); }
 
-// out[c] (+)= sum_r x[r, c]; grid (C/32 column groups, row slabs), atomics across slabs
+// Fixed-order block reduction of NV per-thread values (256 threads): xor-shuffle tree inside each warp, then the 8 warp
+// results in warp order.  Thread t < NV returns the total of value t; every run adds in the same order, so the column
+// sums below (bias / attention-vector / LayerNorm gradients) are bit-reproducible -- a float atomicAdd across blocks is
+// not, and its noise, amplified by the batch-statistics BatchNorms, moved the training loss by 4e-3 after two steps.
+template <int NV>
+__device__ __forceinline__ float block_reduce_fixed(float (&acc)[NV], float (*part)[NV]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) part[warp][k] = acc[k];
+  }
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < NV) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+  }
+  return t;
+}
+
+// out[c] += sum_r x[r, c].  One block owns 8 columns over ALL rows (thread = row lane, one 16 / 32-byte load per row),
+// so no sum crosses a block: deterministic, no atomics.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, int R, int C, int rows_per_block) {
-  __shared__ float part[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ry = threadIdx.x >> 5;
-  const int rbeg = blockIdx.y * rows_per_block, rend = min(R, rbeg + rows_per_block);
-  float s = 0.f;
-  if (c < C)
-    for (int r = rbeg + ry; r < rend; r += 8) s += ldf<T>(x, (size_t)r * ldx + c);
-  part[ry][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (ry == 0 && c < C) {
-    float t = 0.f;
+colsum_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, int R, int C) {
+  __shared__ float part[8][8];
+  const int c0 = blockIdx.x * 8;
+  const int nc = min(8, C - c0);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool vec = nc == 8 && (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 31) == 0;
+  for (int r = threadIdx.x; r < R; r += 256) {
+    const T* p = x + (size_t)r * ldx + c0;
+    if (vec) {
+      if (sizeof(T) == 2) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+      } else {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(p)), b4 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        acc[0] += a4.x; acc[1] += a4.y; acc[2] += a4.z; acc[3] += a4.w;
+        acc[4] += b4.x; acc[5] += b4.y; acc[6] += b4.z; acc[7] += b4.w;
+      }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
-    atomicAdd(out + c, t);
+      for (int k = 0; k < 8; ++k)
+        if (k < nc) acc[k] += ldf<T>(p, k);
+    }
   }
+  const float t = block_reduce_fixed<8>(acc, part);
+  if (threadIdx.x < nc) out[c0 + threadIdx.x] += t;
 }
 
 // activation backward through y = dropout(elu(pre)):  kept elements carry elu(pre) / (1 - p)
@@ -322,9 +355,9 @@ pos_slot_stats_kernel(const float* __restrict__ pos, const long long* __restrict
 __global__ void __launch_bounds__(128)
 pos_branch_bwd_kernel(const float* __restrict__ pos, const long long* __restrict__ off, const float* __restrict__ mean,
                       const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      const float* __restrict__ w, const bf16* __restrict__ dpre, float* __restrict__ dw,
-                      float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int n,
-                      int ld, int col0) {
+                      const float* __restrict__ w, const bf16* __restrict__ dpre,
+                      float* __restrict__ partials, float* __restrict__ dgamma, float* __restrict__ dbeta, int B,
+                      int n, int ld, int col0) {
   const int r = blockIdx.x;
   const int o = threadIdx.x & 31, q = threadIdx.x >> 5;
   const float m = mean[r], rs = rstd[r], ga = gamma[r], be = beta[r];
@@ -349,13 +382,31 @@ pos_branch_bwd_kernel(const float* __restrict__ pos, const long long* __restrict
       abt += dxn;
     }
   }
+  // this slot's contribution: the 4 warps in warp order (fixed), then one row of the partials buffer; the sum over slots
+  // is taken in slot order by pos_branch_bwd_final_kernel -- bit-reproducible, no atomics
+  __shared__ float sh[4][162];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) atomicAdd(dw + o * 4 + k, aw[k]);
-  atomicAdd(db + o, ab);
+  for (int k = 0; k < 4; ++k) sh[q][o * 4 + k] = aw[k];
+  sh[q][128 + o] = ab;
   if (o == 0) {
-    atomicAdd(dgamma + r, ag);
-    atomicAdd(dbeta + r, abt);
+    sh[q][160] = ag;
+    sh[q][161] = abt;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 162; i += 128) {
+    const float t = ((sh[0][i] + sh[1][i]) + sh[2][i]) + sh[3][i];
+    if (i < 160) partials[(size_t)r * 160 + i] = t;
+    else if (i == 160) dgamma[r] += t;
+    else dbeta[r] += t;
+  }
+}
+__global__ void pos_branch_bwd_final_kernel(const float* __restrict__ partials, float* __restrict__ dw,
+                                            float* __restrict__ db, int n) {
+  const int i = threadIdx.x;                                 // 160 threads: dW [32, 4] then db [32]
+  float t = 0.f;
+  for (int r = 0; r < n; ++r) t += partials[(size_t)r * 160 + i];
+  if (i < 128) dw[i] += t;
+  else db[i - 128] += t;
 }
 
 // backward of unbatch_features pad / truncate (GraphModel.py:30-54): dh[node] = dhp[b, r] for r < max_node, else 0
@@ -529,22 +580,31 @@ gat_bwd_src_kernel(const bf16* __restrict__ dout, const float* __restrict__ alph
   }
 }
 
-// dattn_l[h,f] += sum_n del[n,h] z[n,h,f];  dattn_r likewise with der.  grid (H*F/256 chunks, node slabs)
+// dattn_l[h,f] += sum_n del[n,h] z[n,h,f];  dattn_r likewise with der.  One block owns 8 columns of the H*F row over
+// ALL nodes (thread = node lane, one 16-byte load per node); fixed-order block reduction, no atomics.
 __global__ void __launch_bounds__(256)
 gat_attn_grad_kernel(const bf16* __restrict__ z, const float* __restrict__ del, const float* __restrict__ der,
-                     float* __restrict__ dal, float* __restrict__ dar, int N, int H, int F, int nodes_per_block) {
-  const int col = blockIdx.x * 256 + threadIdx.x;          // column of the H*F row
-  if (col >= H * F) return;
-  const int h = col / F;
-  const int nbeg = blockIdx.y * nodes_per_block, nend = min(N, nbeg + nodes_per_block);
-  float sl = 0.f, sr = 0.f;
-  for (int n = nbeg; n < nend; ++n) {
-    const float zv = __bfloat162float(z[(size_t)n * H * F + col]);
-    sl += __ldg(del + (size_t)n * H + h) * zv;
-    sr += __ldg(der + (size_t)n * H + h) * zv;
+                     float* __restrict__ dal, float* __restrict__ dar, int N, int H, int F) {
+  __shared__ float part[8][16];
+  const int col0 = blockIdx.x * 8;                          // F % 8 == 0: the 8 columns share a head
+  const int h = col0 / F;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (int n = threadIdx.x; n < N; n += 256) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(z + (size_t)n * H * F + col0));
+    const float zl[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                         bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+    const float a = __ldg(del + (size_t)n * H + h), b = __ldg(der + (size_t)n * H + h);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k] += a * zl[k];
+      acc[8 + k] += b * zl[k];
+    }
   }
-  atomicAdd(dal + col, sl);
-  atomicAdd(dar + col, sr);
+  const float t = block_reduce_fixed<16>(acc, part);
+  if (threadIdx.x < 8) dal[col0 + threadIdx.x] += t;
+  else if (threadIdx.x < 16) dar[col0 + threadIdx.x - 8] += t;
 }
 
 // ------------------------------------- encoder backward row kernels (first pieces) -------------------------------------
@@ -554,14 +614,15 @@ gat_attn_grad_kernel(const bf16* __restrict__ z, const float* __restrict__ del, 
 //   xhat = (v - mean) rstd;  g = dout gamma;  dv = rstd (g - mean(g) - xhat mean(g xhat));
 //   dgamma += sum_rows dout xhat;  dbeta += sum_rows dout
 // One warp walks rows (grid-stride), lane owns 8-element units; the per-lane column sums stay in registers over all
-// rows of the warp, are combined over the 8 warps of the block in shared memory and leave as one atomicAdd per column
-// and block (grid capped at 2 blocks per SM).  dv is written as bf16 (the operand of the dense backward) and / or fp32
+// rows of the warp, are combined over the 8 warps of the block in shared memory and leave as one row of the partials
+// workspace per block (grid capped at 2 blocks per SM), which ln_rows_bwd_final_kernel sums in block order: no atomics,
+// bit-reproducible gradients.  dv is written as bf16 (the operand of the dense backward) and / or fp32
 // (mode 2: it is also the shortcut's gradient); the residual gradient of mode 1 is dout itself and needs no kernel.
 template <int UNITS>
 __global__ void __launch_bounds__(256)
 ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, const float* __restrict__ gamma,
                    const float* __restrict__ dout, bf16* __restrict__ dvb, float* __restrict__ dv32,
-                   float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C, float eps, int mode) {
+                   float* __restrict__ partials, int M, int C, float eps, int mode) {
   extern __shared__ float red[];                  // [8 warps][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int units = C >> 3;
@@ -666,9 +727,21 @@ ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcu
       a += red[(w8 * 2 + 0) * C + c];
       b += red[(w8 * 2 + 1) * C + c];
     }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, b);
+    partials[((size_t)blockIdx.x * 2 + 0) * C + c] = a;      // block order is fixed by ln_rows_bwd_final_kernel
+    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = b;
   }
+}
+__global__ void ln_rows_bwd_final_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta, int nblocks, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int k = 0; k < nblocks; ++k) {
+    a += partials[((size_t)k * 2 + 0) * C + c];
+    b += partials[((size_t)k * 2 + 1) * C + c];
+  }
+  dgamma[c] += a;
+  dbeta[c] += b;
 }
 
 // exact (erf) GELU backward, nn.GELU default (swin_transformer_v2.py:26-32 Mlp, HF "gelu"): dpre = dh (Phi(x) + x phi(x))
@@ -896,19 +969,26 @@ __global__ void l2norm_mean_bwd_kernel(const float* __restrict__ z, const float*
 
 // ------------------------------------------- cross entropy (mean) fwd + bwd -------------------------------------------
 // logits fp32 [B, C<=8], labels int64; loss_sum += sum_b CE_b * scale; dlogits = (softmax - onehot) * scale
-__global__ void ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
-                               float* __restrict__ loss_sum, float* __restrict__ dlogits, int B, int C, float scale) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float m = -INFINITY;
-  for (int c = 0; c < C; ++c) m = fmaxf(m, logits[(size_t)b * C + c]);
-  float s = 0.f;
-  for (int c = 0; c < C; ++c) s += expf(logits[(size_t)b * C + c] - m);
-  const int y = (int)labels[b];
-  const float lse = m + logf(s);
-  atomicAdd(loss_sum, (lse - logits[(size_t)b * C + y]) * scale);
-  for (int c = 0; c < C; ++c)
-    dlogits[(size_t)b * C + c] = (expf(logits[(size_t)b * C + c] - lse) - (c == y ? 1.f : 0.f)) * scale;
+// One block walks the batch: the per-row losses are summed in a fixed order (shared-memory tree), so the reported loss
+// is bit-reproducible (a float atomicAdd per row was not).
+__global__ void __launch_bounds__(256)
+ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, float* __restrict__ loss_sum,
+               float* __restrict__ dlogits, int B, int C, float scale) {
+  __shared__ float part[8][1];
+  float acc[1] = {0.f};
+  for (int b = threadIdx.x; b < B; b += 256) {
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, logits[(size_t)b * C + c]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(logits[(size_t)b * C + c] - m);
+    const int y = (int)labels[b];
+    const float lse = m + logf(s);
+    acc[0] += (lse - logits[(size_t)b * C + y]) * scale;
+    for (int c = 0; c < C; ++c)
+      dlogits[(size_t)b * C + c] = (expf(logits[(size_t)b * C + c] - lse) - (c == y ? 1.f : 0.f)) * scale;
+  }
+  const float t = block_reduce_fixed<1>(acc, part);
+  if (threadIdx.x == 0) loss_sum[0] += t;
 }
 
 // small fp32 linear backward (heads): dX[M,K] = dY[M,N] W[N,K];  dW[N,K] += dY^T X;  db[N] += sum dY.   N <= 8
@@ -1006,10 +1086,9 @@ extern "C" int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, i
 extern "C" int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, int R, int C, cudaStream_t stream) {
   MV_CHECK_ARG(ldx >= C, "colsum: ldx < C");
   if (R <= 0 || C <= 0) return 0;
-  const int rpb = 512;
-  dim3 grid((C + 31) / 32, (R + rpb - 1) / rpb);
-  if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, R, C, rpb);
-  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, out, R, C, rpb);
+  const int grid = (C + 7) / 8;
+  if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, R, C);
+  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, out, R, C);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -1059,8 +1138,9 @@ extern "C" int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gam
   return 0;
 }
 extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const float* gamma, const float* dout, void* dv_bf16,
-                                 float* dv_f32, float* dgamma, float* dbeta, int M, int C, float eps, int mode,
-                                 cudaStream_t stream) {
+                                 float* dv_f32, float* dgamma, float* dbeta, float* partials, int M, int C, float eps,
+                                 int mode, cudaStream_t stream) {
+  MV_CHECK_ARG(partials != nullptr, "ln_rows_bwd: the [mvuld_ln_rows_bwd_blocks(M), 2, C] partials workspace is null");
   MV_CHECK_ARG(C % 8 == 0 && C <= 1024, "ln_rows_bwd: C=%d must be a multiple of 8 and <= 1024", C);
   MV_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || shortcut), "ln_rows_bwd: mode %d (mode 2 needs the shortcut)", mode);
   MV_CHECK_ARG(dgamma && dbeta && (dv_bf16 || dv_f32), "ln_rows_bwd: dgamma / dbeta and one of the dv outputs are required");
@@ -1072,7 +1152,7 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
 #define MV_LN_BWD(U)                                                                                                   \
   do {                                                                                                                 \
     MV_CUDA_OK(cudaFuncSetAttribute(ln_rows_bwd_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    ln_rows_bwd_kernel<U><<<grid, 256, smem, stream>>>(yp, shortcut, gamma, dout, dvp, dv_f32, dgamma, dbeta, M, C, eps, mode); \
+    ln_rows_bwd_kernel<U><<<grid, 256, smem, stream>>>(yp, shortcut, gamma, dout, dvp, dv_f32, partials, M, C, eps, mode); \
   } while (0)
   if (C <= 256) MV_LN_BWD(1);
   else if (C <= 512) MV_LN_BWD(2);
@@ -1080,8 +1160,12 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
   else MV_LN_BWD(4);
 #undef MV_LN_BWD
   MV_LAUNCH_OK();
+  ln_rows_bwd_final_kernel<<<(C + 255) / 256, 256, 0, stream>>>(partials, dgamma, dbeta, grid, C);
+  MV_LAUNCH_OK();
   return 0;
 }
+// rows of the partials workspace mvuld_ln_rows_bwd needs for M rows ([blocks, 2, C] floats)
+extern "C" int mvuld_ln_rows_bwd_blocks(int M) { return std::min((M + 7) / 8, 2 * num_sms()); }
 extern "C" int mvuld_gelu_bwd(const void* pre, const void* dh, void* dpre, long long n, cudaStream_t stream) {
   MV_CHECK_ARG(n % 8 == 0, "gelu_bwd: n %% 8");
   if (n <= 0) return 0;
@@ -1106,11 +1190,14 @@ extern "C" int mvuld_pos_slot_stats(const float* pos, const long long* offsets, 
 }
 extern "C" int mvuld_pos_branch_bwd(const float* pos, const long long* offsets, const float* mean, const float* rstd,
                                     const float* gamma, const float* beta, const float* w, const void* dpre, float* dw,
-                                    float* db, float* dgamma, float* dbeta, int B, int n, int OUT, int ld, int col0,
-                                    cudaStream_t stream) {
+                                    float* db, float* dgamma, float* dbeta, float* partials, int B, int n, int OUT,
+                                    int ld, int col0, cudaStream_t stream) {
   MV_CHECK_ARG(OUT == 32, "pos_branch_bwd: fc_bbox has 32 outputs (got %d)", OUT);
+  MV_CHECK_ARG(partials != nullptr, "pos_branch_bwd: the [n, 160] partials workspace is null");
   if (B <= 0) return 0;
-  pos_branch_bwd_kernel<<<n, 128, 0, stream>>>(pos, offsets, mean, rstd, gamma, beta, w, reinterpret_cast<const bf16*>(dpre), dw, db, dgamma, dbeta, B, n, ld, col0);
+  pos_branch_bwd_kernel<<<n, 128, 0, stream>>>(pos, offsets, mean, rstd, gamma, beta, w, reinterpret_cast<const bf16*>(dpre), partials, dgamma, dbeta, B, n, ld, col0);
+  MV_LAUNCH_OK();
+  pos_branch_bwd_final_kernel<<<1, 160, 0, stream>>>(partials, dw, db, n);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -1134,9 +1221,7 @@ extern "C" int mvuld_gat_bwd(const void* z, const void* dout, const float* el, c
   MV_LAUNCH_OK();
   gat_bwd_src_kernel<4><<<(N + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const bf16*>(dout), alpha_e, ds_e, der, out_indptr, out_dst, pos_in, attn_l, attn_r, reinterpret_cast<bf16*>(dz), del, N, F);
   MV_LAUNCH_OK();
-  const int npb = 256;
-  dim3 grid((H * F + 255) / 256, (N + npb - 1) / npb);
-  gat_attn_grad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(z), del, der, dattn_l, dattn_r, N, H, F, npb);
+  gat_attn_grad_kernel<<<H * F / 8, 256, 0, stream>>>(reinterpret_cast<const bf16*>(z), del, der, dattn_l, dattn_r, N, H, F);
   MV_LAUNCH_OK();
   return 0;
 }
@@ -1177,7 +1262,7 @@ extern "C" int mvuld_ce_loss(const float* logits, const long long* labels, float
                              int C, float scale, cudaStream_t stream) {
   MV_CHECK_ARG(C >= 1 && C <= 64, "ce_loss: C in [1, 64]");
   if (B <= 0) return 0;
-  ce_loss_kernel<<<GRID1(B, 128), 128, 0, stream>>>(logits, labels, loss_sum, dlogits, B, C, scale);
+  ce_loss_kernel<<<1, 256, 0, stream>>>(logits, labels, loss_sum, dlogits, B, C, scale);
   MV_LAUNCH_OK();
   return 0;
 }

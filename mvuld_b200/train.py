@@ -144,7 +144,10 @@ class FusionTrainer:
         self.gnorm_sq = torch.zeros(1, **f32)
         self.gnorm_partials = torch.zeros(1184, **f32)
         self.loss_buf = torch.zeros(1, **f32)
-        self._refresh_shadows()
+        if self.world > 1:
+            self.sync_replicas()               # DDP broadcasts rank 0's module state at construction
+        else:
+            self._refresh_shadows()
         self.last = {}
         self.debug_taps = None      # tests set this to a dict to receive intermediate activations
 
@@ -464,7 +467,7 @@ class FusionTrainer:
                   gv("bn_gat.bias"), B, n, 512)
         _lib.call("mvuld_pos_branch_bwd", pos, offsets, box_mean, box_rstd, pv("bn_bbox.weight"), pv("bn_bbox.bias"),
                   pv("fc_bbox.weight"), dpre, gv("fc_bbox.weight"), gv("fc_bbox.bias"), gv("bn_bbox.weight"),
-                  gv("bn_bbox.bias"), B, n, 32, 512, 480)
+                  gv("bn_bbox.bias"), e((n, 160), f32), B, n, 32, 512, 480)
         dh = e((N, 512), bf)
         _lib.call("mvuld_unbatch_pad_bwd", dhp, offsets, dh, B, n, 512)
         ready("bn_bbox.bias")
@@ -515,7 +518,7 @@ class FusionTrainer:
              lr: Optional[float] = None, check: bool = True):
         """One optimiser step of main_bigvul.py:306-342.  Returns (loss, logits): loss is a [1] fp32 device tensor
         holding this rank's mean cross-entropy (no host synchronisation unless ``check``)."""
-        self.step_count += 1
+        self.step_count += 1                   # counts THIS step: dropout seeds and AdamW's bias correction use it
         works = []
         if self.world > 1:
             import torch.distributed as dist
@@ -523,15 +526,14 @@ class FusionTrainer:
                                                                group=self.group, async_op=True))
         else:
             on_bucket = None
-        loss, logits = self.forward_backward(g, img_embedding, func_text_embedding, targets, on_bucket)
+        try:
+            loss, logits = self.forward_backward(g, img_embedding, func_text_embedding, targets, on_bucket)
+        except Exception:
+            self.step_count -= 1               # a rejected batch must not advance the schedule or the seeds
+            raise
         for w in works:
             w.wait()
-        self.gnorm_sq.zero_()
-        _lib.call("mvuld_sumsq_f32", self.flat_g, self.total, self.gnorm_partials, self.gnorm_sq)
-        _lib.call("mvuld_adamw", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.total, self.seg_end,
-                  self.seg_wd, int(self.seg_end.numel()), self.gnorm_sq, self.clip, float(self.lr if lr is None else lr),
-                  float(self.betas[0]), float(self.betas[1]), self.eps, self.step_count)
-        self._refresh_shadows()
+        self.apply_update(lr, advance=False)
         if self.world > 1:
             loss = loss * self.world           # forward_backward scaled the cross-entropy by 1 / world
         if check:
@@ -541,26 +543,111 @@ class FusionTrainer:
             self.last["graph"].check_status()
         return loss, logits
 
-    def refresh(self):
-        """Re-derive the bf16 / transposed / split weight copies after the parameters were written from outside
-        (``model.load_state_dict`` copies into the flat buffer the parameters are views of)."""
+    @torch.no_grad()
+    def apply_update(self, lr: Optional[float] = None, advance: bool = True):
+        """``clip_grad_norm_(clip)`` + AdamW on whatever ``flat_g`` holds (utils_multi.py:225-240, optimizer.py:28-30), then
+        the bf16 / transposed weight copies.  ``advance``: count a new optimiser step first (``step`` has already)."""
+        if advance:
+            self.step_count += 1
+        self.gnorm_sq.zero_()
+        _lib.call("mvuld_sumsq_f32", self.flat_g, self.total, self.gnorm_partials, self.gnorm_sq)
+        _lib.call("mvuld_adamw", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.total, self.seg_end,
+                  self.seg_wd, int(self.seg_end.numel()), self.gnorm_sq, self.clip, float(self.lr if lr is None else lr),
+                  float(self.betas[0]), float(self.betas[1]), self.eps, self.step_count)
         self._refresh_shadows()
 
+    @torch.no_grad()
+    def sync_replicas(self, src: int = 0):
+        """Data-parallel start-up / resume: every rank takes rank ``src``'s parameters, AdamW moments, step count and
+        BatchNorm running statistics, as DDP's constructor broadcast does for the module state
+        (main_bigvul.py:162-164).  A no-op on one GPU."""
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        meta = torch.tensor([float(self.step_count)], device=self.dev, dtype=torch.float64)
+        for t in (self.flat_p, self.flat_m, self.flat_v, meta):
+            dist.broadcast(t, src=src, group=self.group)
+        self.step_count = int(meta.item())
+        for b in self.model.buffers():
+            if b.is_floating_point() or b.dtype in (torch.int64, torch.int32):
+                dist.broadcast(b, src=src, group=self.group)
+        self._refresh_shadows()
+
+    def refresh(self):
+        """Re-derive the bf16 / transposed / split weight copies after the parameters were written from outside
+        (``model.load_state_dict`` copies into the flat buffer the parameters are views of); under data parallelism the
+        replicas are re-synchronised from rank 0 first (a checkpoint loaded on one rank only must not fork the replicas)."""
+        if self.world > 1:
+            self.sync_replicas()
+        else:
+            self._refresh_shadows()
+
+    # ------------------------------------------------------------------------------------------------
+    # optimiser state in torch.optim.AdamW's own layout, so checkpoints move both ways between this trainer and the
+    # reference's ``optimizer.state_dict()`` / ``optimizer.load_state_dict()`` (utils_multi.py:7-32,125-137)
+    # ------------------------------------------------------------------------------------------------
+    def _torch_param_index(self) -> Tuple[Dict[str, int], int, int]:
+        """Parameter name -> index in ``build_optimizer``'s groups (optimizer.py:35-50): every ``requires_grad``
+        parameter in ``named_parameters()`` order, the decayed group first, then the 1-D / bias group."""
+        decay, no_decay = [], []
+        for n, prm in self.model.named_parameters():
+            if not prm.requires_grad:
+                continue
+            (no_decay if (prm.dim() == 1 or n.endswith(".bias")) else decay).append(n)
+        return {n: i for i, n in enumerate(decay + no_decay)}, len(decay), len(no_decay)
+
     def state_dict(self) -> dict:
-        """Optimiser state in the role of ``optimizer.state_dict()`` of utils_multi.py:125-137 (flat AdamW moments)."""
-        return dict(kind="mvuld_b200.FusionTrainer", names=list(self.names), offsets=dict(self.offsets),
-                    exp_avg=self.flat_m.detach().cpu().clone(), exp_avg_sq=self.flat_v.detach().cpu().clone(),
-                    step=self.step_count, lr=self.lr, weight_decay=self.wd, betas=tuple(self.betas), eps=self.eps,
-                    clip_grad=self.clip, dropout=self.p_drop, seed=self.seed)
+        """``torch.optim.AdamW.state_dict()`` layout: ``state[idx] = {step, exp_avg, exp_avg_sq}`` for every parameter that
+        has received a gradient, ``param_groups`` = [decayed, not decayed].  Trainer-only settings ride along under the
+        extra key ``mvuld_b200`` (``Optimizer.load_state_dict`` reads ``state`` and ``param_groups`` only)."""
+        index, n_decay, n_no = self._torch_param_index()
+        state = {}
+        if self.step_count > 0:
+            m, v = self.flat_m.detach().cpu(), self.flat_v.detach().cpu()
+            for n in self.names:
+                state[index[n]] = {"step": torch.tensor(float(self.step_count)),
+                                   "exp_avg": self._view(m, n).clone(), "exp_avg_sq": self._view(v, n).clone()}
+        common = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, amsgrad=False, maximize=False, foreach=None,
+                      capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True)
+        groups = [dict(common, weight_decay=self.wd, params=list(range(n_decay))),
+                  dict(common, weight_decay=0.0, params=list(range(n_decay, n_decay + n_no)))]
+        return {"state": state, "param_groups": groups,
+                "mvuld_b200": dict(kind="mvuld_b200.FusionTrainer", step=self.step_count, clip_grad=self.clip,
+                                   dropout=self.p_drop, seed=self.seed)}
 
     def load_state_dict(self, sd: dict):
-        if sd.get("kind") != "mvuld_b200.FusionTrainer" or list(sd["names"]) != list(self.names):
-            raise ValueError("optimizer state does not belong to a FusionTrainer over the same parameters")
-        self.flat_m.copy_(sd["exp_avg"])
-        self.flat_v.copy_(sd["exp_avg_sq"])
-        self.step_count = int(sd["step"])
-        self.lr, self.wd, self.betas, self.eps = float(sd["lr"]), float(sd["weight_decay"]), tuple(sd["betas"]), float(sd["eps"])
-        self.clip, self.p_drop, self.seed = float(sd["clip_grad"]), float(sd["dropout"]), int(sd["seed"])
+        """Accepts a ``torch.optim.AdamW`` state dict over the same model (the reference's checkpoints) or one written
+        by ``state_dict()`` above."""
+        if "param_groups" not in sd or "state" not in sd:
+            raise ValueError("optimizer state is not a torch.optim.AdamW state dict ({'state', 'param_groups'})")
+        index, n_decay, n_no = self._torch_param_index()
+        groups = sd["param_groups"]
+        if len(groups) != 2 or len(groups[0]["params"]) != n_decay or len(groups[1]["params"]) != n_no:
+            raise ValueError("optimizer state does not belong to an AdamW over this model's parameter groups "
+                             f"(expected {n_decay} decayed + {n_no} non-decayed parameters)")
+        ids = list(groups[0]["params"]) + list(groups[1]["params"])          # position -> saved id
+        g0 = groups[0]
+        self.lr, self.wd, self.betas, self.eps = float(g0["lr"]), float(g0["weight_decay"]), tuple(g0["betas"]), float(g0["eps"])
+        self.flat_m.zero_()
+        self.flat_v.zero_()
+        steps = set()
+        for n in self.names:
+            st = sd["state"].get(ids[index[n]])
+            if st is None:
+                continue
+            if tuple(st["exp_avg"].shape) != self.shapes[n]:
+                raise ValueError(f"optimizer state of {n}: shape {tuple(st['exp_avg'].shape)} != {self.shapes[n]}")
+            self._view(self.flat_m, n).copy_(st["exp_avg"].to(torch.float32))
+            self._view(self.flat_v, n).copy_(st["exp_avg_sq"].to(torch.float32))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"optimizer state holds different step counts per parameter ({sorted(steps)}); the flat "
+                             "AdamW launch applies one bias correction")
+        extra = sd.get("mvuld_b200", {})
+        self.step_count = int(extra.get("step", steps.pop() if steps else 0))
+        self.clip = float(extra.get("clip_grad", self.clip))
+        self.p_drop = float(extra.get("dropout", self.p_drop))
+        self.seed = int(extra.get("seed", self.seed))
         wd = [0.0 if (len(self.shapes[n]) == 1 or n.endswith(".bias")) else self.wd for n in self.names]
         self.seg_wd.copy_(torch.tensor(wd, dtype=torch.float32))
 

@@ -197,15 +197,20 @@ def test_swin_attention_block(Hres, ws, shift, nH, B):
     assert rel_err(k.view(B_, nH, ws * ws, 32), torch.nn.functional.normalize(qkv[1], dim=-1)) < 2e-3
     assert rel_err(v.view(B_, nH, ws * ws, 32), qkv[2]) < 5e-3
     # both softmax reference policies: constant reference (these heads' logit range is small) and running maximum
-    for qn in (qscale, None):
+    # plus, for 28x28 windows, the three-group kernel that the model uses when every head is on the constant reference
+    fixed_ok = ws == 28 and bool((2 * qscale + tab_max <= 100).all())
+    for entry, qn in (("mvuld_swin_window_attention", qscale), ("mvuld_swin_window_attention", None),
+                      ("mvuld_swin_window_attention_fixed", qscale)):
+        if entry.endswith("_fixed") and not fixed_ok:
+            continue
         out.zero_()
-        _lib.call("mvuld_swin_window_attention", q, k, v, tab_rev, tab_max, qn, out, B, H, W, C, nH, ws, shift)
+        _lib.call(entry, q, k, v, tab_rev, tab_max, qn, out, B, H, W, C, nH, ws, shift)
         torch.cuda.synchronize()
         err = rel_err(out, ref)
         from tests.conftest import record_parity
-        record_parity(f"swin_window_attention[H{Hres} ws{ws} shift{shift}, {'constant' if qn is not None else 'running-max'} reference] rel-L2",
-                      err, 1e-2)
-        assert err < 1e-2, (err, qn is None)
+        kind = "three-group constant" if entry.endswith("_fixed") else ("constant" if qn is not None else "running-max")
+        record_parity(f"swin_window_attention[H{Hres} ws{ws} shift{shift}, {kind} reference] rel-L2", err, 1e-2)
+        assert err < 1e-2, (err, kind)
 
 
 def test_seq_attention():

@@ -14,8 +14,20 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["L
 dev = "cuda"
 g, img, txt, labels = _inputs(B=8, seed=100 + rank)           # each rank its own shard
 model = cases.make_fusion().to(dev)
+if rank != 0:
+    # ranks that built / loaded different weights must end up on rank 0's (DDP's constructor broadcast)
+    from mvuld_b200 import synth
+    synth.randomize_for_parity(model, seed=4242 + rank)
+    model.swinbn.running_mean.add_(1.0)
 tr = train.FusionTrainer(model, dropout=0.0, lr=1e-3, bucket_mb=4.0)
 assert tr.world == world and len(tr.buckets) > 3
+p0 = [torch.empty_like(tr.flat_p) for _ in range(world)]
+dist.all_gather(p0, tr.flat_p.clone())
+rm = [torch.empty_like(model.swinbn.running_mean) for _ in range(world)]
+dist.all_gather(rm, model.swinbn.running_mean.clone())
+ref0 = cases.make_fusion().to(dev)
+assert all(torch.equal(p0[0], q) for q in p0[1:]) and all(torch.equal(rm[0], q) for q in rm[1:]), "replicas not synchronised at construction"
+assert torch.equal(model.fc.weight.detach(), ref0.fc.weight.detach()), "rank 0's weights did not win"
 loss, _ = tr.step(g.to(dev), img.to(dev), txt.to(dev), labels.to(dev))
 gsum = tr.flat_g.clone()                                      # SUM over ranks of (local grad / world) = mean gradient
 # local gradient of this rank alone

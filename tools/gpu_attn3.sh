@@ -1,0 +1,6 @@
+#!/bin/bash
+# new three-group window attention: parity + timing against the two-group kernel
+mkdir -p gpurun_out
+timeout 200 python -m pytest tests/test_gpu_kernels.py -q -x -m gpu -k swin_attention 2>&1 | tail -15 | tee gpurun_out/attn3_test.log
+PB=64 timeout 60 python tools/prof_attn.py 2>&1 | tee gpurun_out/attn3_time.log
+ENTRY=mvuld_swin_window_attention_fixed PB=64 timeout 60 python tools/prof_attn.py 2>&1 | tee -a gpurun_out/attn3_time.log

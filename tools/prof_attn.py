@@ -13,13 +13,14 @@ tab = (torch.rand(nH, side * side, generator=g) * 16 * 1.4427).cuda()
 tmax = tab.max(1).values.contiguous()
 qn = torch.full((nH,), 14.0, device="cuda") if os.environ.get("FIXED_REF", "1") == "1" else None
 out = torch.empty(B * H * W, C, device="cuda", dtype=torch.bfloat16)
+ENTRY = os.environ.get("ENTRY", "mvuld_swin_window_attention")
 for _ in range(3):
-    _lib.call("mvuld_swin_window_attention", q, k, v, tab, tmax, qn, out, B, H, W, C, nH, ws, shift)
+    _lib.call(ENTRY, q, k, v, tab, tmax, qn, out, B, H, W, C, nH, ws, shift)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(10):
-    _lib.call("mvuld_swin_window_attention", q, k, v, tab, tmax, qn, out, B, H, W, C, nH, ws, shift)
+    _lib.call(ENTRY, q, k, v, tab, tmax, qn, out, B, H, W, C, nH, ws, shift)
 e.record()
 torch.cuda.synchronize()
-print("attention ms per launch", s.elapsed_time(e) / 10, "B", B)
+print(ENTRY, "ms per launch", s.elapsed_time(e) / 10, "B", B)
