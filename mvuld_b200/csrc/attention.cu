@@ -59,8 +59,21 @@ __device__ __forceinline__ void att_trace(unsigned int& i, int tag, int g, int t
   g_att_trace_n[w] = i;
 }
 #define ATT_TRACE(tag, g, t, j) att_trace(trace_i, tag, g, t, j)
+// three-group kernel: writer slot = group (0..2), 3 = QK^T issuer, 4 = PV issuer
+__device__ __forceinline__ void att_trace3(unsigned int& i, int slot, int tag, int g, int t, int j) {
+  const long long clk = clock64();
+  if (blockIdx.x != 0) return;
+  if (i < 4096u) {
+    g_att_trace[(slot * 4096 + i) * 2] = ((long long)tag << 48) | ((long long)g << 32) | ((long long)t << 16) | j;
+    g_att_trace[(slot * 4096 + i) * 2 + 1] = clk;
+  }
+  ++i;
+  g_att_trace_n[slot] = i;
+}
+#define ATT_TRACE3(slot, tag, g, t, j) att_trace3(trace_i, slot, tag, g, t, j)
 #else
 #define ATT_TRACE(tag, g, t, j)
+#define ATT_TRACE3(slot, tag, g, t, j)
 #endif
 
 struct AttnParams {
@@ -696,9 +709,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //    left the MUFU pipe idle half of the time with two (profiles/r1_ncu_attn.md: XU 52 %, issue 49 %).
 //  * Work units are (query tile t, key tile j), dealt round-robin to the groups: the 49 units of a head split 17/16/16
 //    instead of 4/3 query tiles.  A constant reference needs no per-row state between key tiles, so the groups that
-//    share a query tile just accumulate into the SAME O accumulator (two O buffers, alternating by query tile).
+//    share a query tile just accumulate into the SAME O accumulator (one O buffer: the tile's writer drains it while
+//    the first units of the next tile are still in their sweeps).
 //  * P (bf16) overwrites the S columns it was computed from (the sweep reads S in pieces ahead of the P stores), so a
-//    group owns ONE 112-column TMEM buffer: 3 x 128 + 2 x 64 columns.
+//    unit needs ONE 112-column TMEM buffer; FOUR of them rotate over the units (unit u -> buffer u % 4, group u % 3),
+//    so QK^T of unit u + 3 is issued into the spare buffer while the PV product of unit u is still pending and a group
+//    finds its next S waiting (with one buffer per group a third of the softmax warps' time went into that wait).
+//    TMEM: 4 x 112 (S / P) + 48 (O).
 //  * The row sum comes out of the tensor core: the PV product runs with N = 48, the extra 16 columns of the B operand
 //    are a [1, 0, ..] block in shared memory (second MN atom of the descriptor, reached through its leading byte
 //    offset), so O[:, 32] = sum_k P[q, k] of exactly the bf16 P the numerator used -- no FADD chain in the sweep and
@@ -706,15 +723,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // Warp roles: 0 TMA producer, 1 QK^T issuer, 2 PV issuer (+ TMEM owner), 3 idle, 4-15 softmax groups 0-2 (thread ==
 // query row == TMEM lane).  The group that sweeps unit (t, 6) also writes tile t's output.
 // =========================================================================================================
-constexpr int A3_THREADS = 512;
-constexpr int A3_G = 3;
+constexpr int A3_THREADS = 640;
+constexpr int A3_G = 4;
 constexpr int A3_KT = 112;
 constexpr int A3_NT = 7;                    // query tiles == key tiles of a 784-token window
 constexpr int A3_NU = A3_NT * A3_NT;
+constexpr int A3_NB = 4;                    // rotating S / P buffers
 constexpr int A3_NO = 48;                   // PV accumulator columns: 32 head dims + the row-sum column (+ 15 unused)
-constexpr int A3_REGS_CTRL = 80;
-constexpr int A3_REGS_SOFTMAX = 144;        // 128 * 80 + 384 * 144 = 65536 = 512 threads * 128 registers at launch
+constexpr int A3_REGS_CTRL = 64;
+constexpr int A3_REGS_SOFTMAX = 104;        // 128 * 64 + 512 * 104 = 61440 = 640 threads * 96 registers at launch
 
+// processing order of the query tiles: the 16-row remainder tile first, then tiles 0 .. 5
+__host__ __device__ constexpr int a3_tile(int pt) { return pt == 0 ? A3_NT - 1 : pt - 1; }
 __host__ __device__ constexpr int a3_smem_bytes(int table_floats) {
   return 2 * A3_NT * A3_KT * 64 + 1024 /*ones*/ + 2 * ATT_BM * 64 + ((table_floats * 4 + 1023) / 1024) * 1024 +
          512 /*barriers*/ + ATT_MERGE_BYTES + 1024 /*align*/;
@@ -749,12 +769,12 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* v_full = k_full + A3_NT;          // [7]
   uint64_t* q_full = v_full + A3_NT;          // [2]
   uint64_t* q_empty = q_full + 2;             // [2]
-  uint64_t* s_full = q_empty + 2;             // [3]  S of the group's current unit is in TMEM
-  uint64_t* p_full = s_full + A3_G;           // [3]  P of the group's current unit is in TMEM
-  uint64_t* pv_done = p_full + A3_G;          // [3]  PV of the group's current unit retired: its buffer is free
-  uint64_t* tile_done = pv_done + A3_G;       // [2]  all seven PV products of a query tile retired
-  uint64_t* o_free = tile_done + 2;           // [2]  the tile's output has been read out of its O buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* s_full = q_empty + 2;             // [4]  S of the unit using this buffer is in TMEM
+  uint64_t* p_full = s_full + A3_NB;          // [4]  P of that unit is in TMEM
+  uint64_t* pv_done = p_full + A3_NB;         // [4]  its PV product retired: the buffer is free
+  uint64_t* tile_done = pv_done + A3_NB;      // all seven PV products of a query tile retired
+  uint64_t* o_free = tile_done + 1;           // the tile's output has been read out of the O accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
   float* sMerge = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [128][33]
 
   const int warp = threadIdx.x >> 5;
@@ -762,6 +782,9 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int bh = blockIdx.x;
   const int head = bh % p.nH;
   const int bwin = bh / p.nH;
+#ifdef MV_ATT_TRACE
+  unsigned int trace_i = 0;
+#endif
 
   const float bmax = __ldg(p.bias_max + head);
   const float q_norm = __ldg(p.q_norm + head);
@@ -779,13 +802,13 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int b = 0; b < 2; ++b) {
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
-      mbar_init(&tile_done[b], 1);
-      mbar_init(&o_free[b], 4);
     }
-    for (int g = 0; g < A3_G; ++g) {
-      mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 4);
-      mbar_init(&pv_done[g], 1);
+    mbar_init(tile_done, 1);
+    mbar_init(o_free, 4);
+    for (int b = 0; b < A3_NB; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 4);
+      mbar_init(&pv_done[b], 1);
     }
     fence_barrier_init();
   }
@@ -815,8 +838,10 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (warp == 0) {
       // =========================================== TMA producer ===========================================
       if (lane == 0) {
-        auto load_q = [&](int t) {
-          const int b = t & 1;
+        // query tiles are processed remainder tile first (a3_tile): its seven one-warp units overlap the K / V loads
+        // instead of forming a tail in which two thirds of the softmax warps idle
+        auto load_q = [&](int pt) {
+          const int b = pt & 1, t = a3_tile(pt);
           mbar_arrive_expect_tx(&q_full[b], L::Q_BYTES);
           if (t == A3_NT - 1) {
             for (int u = 0; u < ATT_BM / ATT_SPLIT_ROWS; ++u)
@@ -833,55 +858,69 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           mbar_arrive_expect_tx(&v_full[j], KT * 64);
           tma_load_3d(sV + j * KT * 64, &tmV, &v_full[j], 0, j * KT, bh);
         }
-        for (int t = 2; t < A3_NT; ++t) {
-          mbar_wait(&q_empty[t & 1], ((t - 2) >> 1) & 1, 10);
-          load_q(t);
+        for (int pt = 2; pt < A3_NT; ++pt) {
+          mbar_wait(&q_empty[pt & 1], ((pt - 2) >> 1) & 1, 10);
+          load_q(pt);
         }
       }
     } else if (warp == 1) {
       // ============================================ QK^T issuer ============================================
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, KT, 0, 0) & ~((1u << 7) | (1u << 10));   // fp16 operands
-        const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
-        for (int u = 0; u < A3_NU; ++u) {
-          const int t = u / A3_NT, j = u - t * A3_NT, g = u % A3_G, n = u / A3_G;
-          if (j == 0) mbar_wait(&q_full[t & 1], (t >> 1) & 1, 20);
-          if (t == 0) mbar_wait(&k_full[j], 0, 21);
-          if (n > 0) mbar_wait(&pv_done[g], (n - 1) & 1, 22);
-          tc_fence_after();
+      // The whole warp runs the (uniform) control flow and one elected lane issues: descriptors are then built on the
+      // uniform datapath, and incrementally -- a descriptor assembled from scratch in a one-lane branch cost ~100
+      // cycles per MMA (VIADD / SHF / LOP3 chain + R2UR), 700 cycles per unit on the serial issue path.
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, KT, 0, 0) & ~((1u << 7) | (1u << 10));   // fp16 operands
+      const uint32_t hi = (uint32_t)(make_smem_desc(0, 16, L::SBO, L::LAYOUT) >> 32);
+      const uint32_t q_lo = (uint32_t)make_smem_desc(smem_u32(sQ), 16, L::SBO, L::LAYOUT);
+      const uint32_t k_lo = (uint32_t)make_smem_desc(smem_u32(sK), 16, L::SBO, L::LAYOUT);
+      const bool leader = elect_one();
+      for (int u = 0; u < A3_NU; ++u) {
+        const int t = u / A3_NT, j = u - t * A3_NT, b = u % A3_NB, n = u / A3_NB;      // t: processing index of the tile
+        if (j == 0) mbar_wait(&q_full[t & 1], (t >> 1) & 1, 20);
+        if (t == 0) mbar_wait(&k_full[j], 0, 21);
+        if (n > 0) mbar_wait(&pv_done[b], (n - 1) & 1, 22);
+        ATT_TRACE3(3, 10, u % A3_G, t, j);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a0 = q_lo + (uint32_t)(t & 1) * (L::Q_BYTES >> 4);
+          const uint32_t b0 = k_lo + (uint32_t)j * (KT * 64 >> 4);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) {
-            const uint64_t ad = make_smem_desc(q0 + (t & 1) * L::Q_BYTES + k * 32, 16, L::SBO, L::LAYOUT);
-            const uint64_t bd = make_smem_desc(k0 + j * KT * 64 + k * 32, 16, L::SBO, L::LAYOUT);
-            umma_ss(tmem_base + g * 128, ad, bd, idesc_s, k != 0);
-          }
-          umma_commit(&s_full[g]);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_ss(tmem_base + b * KT, ((uint64_t)hi << 32) | (a0 + k * 2), ((uint64_t)hi << 32) | (b0 + k * 2), idesc_s,
+                    k != 0);
+          umma_commit(&s_full[b]);
           if (j == A3_NT - 1) umma_commit(&q_empty[t & 1]);
         }
+        __syncwarp();
       }
     } else if (warp == 2) {
       // ============================================= PV issuer =============================================
-      if (lane == 0) {
-        constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, A3_NO, 0, 1);
-        const uint32_t v0 = smem_u32(sV), ones = smem_u32(sOnes);
-        for (int u = 0; u < A3_NU; ++u) {
-          const int t = u / A3_NT, j = u - t * A3_NT, g = u % A3_G, n = u / A3_G;
-          mbar_wait(&p_full[g], n & 1, 23);
-          if (j == 0 && t >= 2) mbar_wait(&o_free[t & 1], ((t - 2) >> 1) & 1, 24);
-          if (t == 0) mbar_wait(&v_full[j], 0, 25);
-          tc_fence_after();
-          const uint32_t tO = tmem_base + 3 * 128 + (t & 1) * 64;
-          const uint32_t tP = tmem_base + g * 128;
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, A3_NO, 0, 1);
+      // MN-major B: first MN atom = the 32 head dims of V, second atom (leading byte offset) = the ones block.
+      // Low word = address | LBO << 16 with LBO = ones - address: moving the tile by d (16-byte units) adds
+      // d * (1 - 65536) (no field overflows: shared-memory offsets stay below 2^18 bytes).
+      const uint32_t hi = (uint32_t)(make_smem_desc(0, 0, L::SBO, L::LAYOUT) >> 32);
+      const uint32_t v_lo = (uint32_t)make_smem_desc(smem_u32(sV), smem_u32(sOnes) - smem_u32(sV), L::SBO, L::LAYOUT);
+      constexpr uint32_t STEP = 1u - 65536u;
+      const bool leader = elect_one();
+      for (int u = 0; u < A3_NU; ++u) {
+        const int t = u / A3_NT, j = u - t * A3_NT, b = u % A3_NB, n = u / A3_NB;      // t: processing index of the tile
+        mbar_wait(&p_full[b], n & 1, 23);
+        if (j == 0 && t >= 1) mbar_wait(o_free, (t - 1) & 1, 24);
+        if (t == 0) mbar_wait(&v_full[j], 0, 25);
+        ATT_TRACE3(4, 12, u % A3_G, t, j);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t tO = tmem_base + A3_NB * KT;
+          const uint32_t tP = tmem_base + b * KT;
+          const uint32_t lo_j = v_lo + (uint32_t)j * (KT * 64 >> 4) * STEP;
 #pragma unroll
-          for (int s = 0; s < KT / 16; ++s) {
-            const uint32_t b0 = v0 + (j * KT + s * 16) * 64;
-            // MN-major B: first MN atom = the 32 head dims of V, second atom (leading byte offset) = the ones block
-            const uint64_t bd = make_smem_desc(b0, ones - b0, L::SBO, L::LAYOUT);
-            umma_ts(tO, tP + s * 8, bd, idesc_pv, (j != 0) || (s != 0));
-          }
-          umma_commit(&pv_done[g]);
-          if (j == A3_NT - 1) umma_commit(&tile_done[t & 1]);
+          for (int s = 0; s < KT / 16; ++s)
+            umma_ts(tO, tP + s * 8, ((uint64_t)hi << 32) | (lo_j + (uint32_t)s * (16 * 64 >> 4) * STEP), idesc_pv,
+                    (j != 0) || (s != 0));
+          umma_commit(&pv_done[b]);
+          if (j == A3_NT - 1) umma_commit(tile_done);
         }
+        __syncwarp();
       }
     }
   } else {
@@ -891,7 +930,6 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + g * 128 + lane_off;
 
     const int nWw = p.W / WS;
     const int wr = (bwin % ((p.H / WS) * nWw)) / nWw;
@@ -901,9 +939,12 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float NEG100 = -100.0f * 1.4426950408889634f;
     const float m_ref = q_norm + bmax;
 
-    int n = 0;
-    for (int u = g; u < A3_NU; u += A3_G, ++n) {
-      const int t = u / A3_NT, j = u - t * A3_NT;
+    for (int u = g; u < A3_NU; u += A3_G) {
+      const int pt = u / A3_NT, j = u - pt * A3_NT;
+      const int t = a3_tile(pt);
+      const int buf = u % A3_NB;
+      const uint32_t par = (uint32_t)(u / A3_NB) & 1u;
+      const uint32_t tS = tmem_base + buf * KT + lane_off;
       const bool split_t = (t == A3_NT - 1);
       const int i = t * ATT_BM + (split_t ? (r & (ATT_SPLIT_ROWS - 1)) : r);
       int hi = i / WS;
@@ -913,7 +954,7 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
       if (split_t && (j >> 1) != quarter) {
         // split remainder tile, key tile owned by another warp's lanes: P = 0
-        mbar_wait(&s_full[g], n & 1, 30);
+        mbar_wait(&s_full[buf], par, 30);
         tc_fence_after();
         uint32_t zero[32];
 #pragma unroll
@@ -924,7 +965,7 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
+        if (lane == 0) mbar_arrive(&p_full[buf]);
       } else {
         float csm[NSEG];
         const float* tb[ROWS_PER_TILE];
@@ -942,14 +983,17 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int s = 0; s < NSEG; ++s) csm[s] = -INFINITY;
         }
 
-        mbar_wait(&s_full[g], n & 1, 30);
+        if (r == 0) ATT_TRACE3(g, 0, g, t, j);
+        mbar_wait(&s_full[buf], par, 30);
         tc_fence_after();
+        if (r == 0) ATT_TRACE3(g, 1, g, t, j);
         uint32_t sv[KT];
         float bb[3][8];
         uint32_t pw[PW];
         tmem_ld32p(tS, sv);
         tmem_ld32p(tS + 32, sv + 32);
         tmem_ld_wait();
+        if (r == 0) ATT_TRACE3(g, 6, g, t, j);
         // Software pipeline over 8-column chunks (see attn_fwd_kernel): A bias LDS | B adds | C ex2 | D bf16 pack.
         // S columns 64.. are pulled in while the first chunks are in flight; P words go back to TMEM eight at a time,
         // always into columns whose S values are already in registers.
@@ -987,24 +1031,26 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
           if (st >= 4 && (st & 1) == 0) tmem_st8p(tS + 4 * (st - 2) - 8, pw + 4 * (st - 2) - 8);   // words [4(st-2)-8, 4(st-2))
         }
+        if (r == 0) ATT_TRACE3(g, 4, g, t, j);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
+        if (lane == 0) mbar_arrive(&p_full[buf]);
+        if (r == 0) ATT_TRACE3(g, 7, g, t, j);
       }
 
       if (j == A3_NT - 1) {
         // ---- output of query tile t: O / l -> bf16, token-major store (window_reverse + inverse shift folded in) ----
-        mbar_wait(&tile_done[t & 1], (t >> 1) & 1, 31);
+        mbar_wait(tile_done, pt & 1, 31);
         tc_fence_after();
-        const uint32_t tO = tmem_base + 3 * 128 + (t & 1) * 64 + lane_off;
+        const uint32_t tO = tmem_base + A3_NB * KT + lane_off;
         uint32_t o[32], o2[16];
         tmem_ld32(tO, o);
         tmem_ld16(tO + 32, o2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free[t & 1]);
+        if (lane == 0) mbar_arrive(o_free);
         const int b = bwin / ((p.H / WS) * nWw);
         if (split_t) {
           float* mrow = sMerge + r * ATT_MERGE_LD;

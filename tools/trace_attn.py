@@ -15,7 +15,7 @@ out = torch.empty(B * H * W, C, device="cuda", dtype=torch.bfloat16)
 lib = _lib.load()
 buf = (ctypes.c_longlong * (4 * 16384))()
 for it in range(2):
-    _lib.call("mvuld_swin_window_attention", q, k, v, tab, tmax, qn, out, B, H, W, C, nH, ws, shift)
+    _lib.call(os.environ.get("ENTRY", "mvuld_swin_window_attention"), q, k, v, tab, tmax, qn, out, B, H, W, C, nH, ws, shift)
     n = lib.mvuld_debug_att_trace(buf, 16384)
 recs = []
 for i in range(n):
