@@ -159,7 +159,7 @@ def work_of(name, args):
     if name == "mvuld_heads_qkv":
         B, L, Hd = args[6], args[7], args[8]
         return "gemm", 2.0 * B * L * Hd * 3 * Hd, 0.0
-    if name == "mvuld_swin_window_attention":
+    if name in ("mvuld_swin_window_attention", "mvuld_swin_window_attention_fixed"):
         B, H, W, C, nH, ws = args[7], args[8], args[9], args[10], args[11], args[12]
         n = ws * ws
         return "attention", 4.0 * (B * H * W // n) * nH * n * n * 32, 0.0
@@ -628,12 +628,13 @@ def roofline_of(wl, dev_in, workload, clocks, pk, detail_path=None):
             out["roofline"]["traffic"] = tr["bytes"]
             out["roofline"]["traffic_note"] = f"one launch of {tr['kernel']} ({tr['source']})"
         # the window-attention kernel next to it: tensor fraction and the exponential (MUFU) roof of head dim 32
-        swin_fl = sum(work_of(n, a)[1] for n, a, _, _ in inst.records if n == "mvuld_swin_window_attention")
-        swin_ms = per_kernel.get("mvuld_swin_window_attention", {"ms": 0.0})["ms"]
+        _wa = ("mvuld_swin_window_attention", "mvuld_swin_window_attention_fixed")
+        swin_fl = sum(work_of(n, a)[1] for n, a, _, _ in inst.records if n in _wa)
+        swin_ms = sum(per_kernel.get(n, {"ms": 0.0})["ms"] for n in _wa)
         if swin_ms > 0:
             sm_hz = ((clocks or {}).get("sm_mhz") or 1965) * 1e6
             a_t = swin_fl / (swin_ms / 1e3) / 1e12
-            out["window_attention"] = {"kernel": "attn_fwd_kernel<MODE_SWIN, hd 32>", "ms": round(swin_ms, 3),
+            out["window_attention"] = {"kernel": "attn_swin3_kernel (28x28 windows) / attn_fwd_kernel<MODE_SWIN> (14x14), hd 32", "ms": round(swin_ms, 3),
                                        "achieved": a_t, "unit": "TFLOP/s", "frac": a_t / pk["bf16_sustained"],
                                        "frac_of_burst_peak": a_t / pk["bf16"], "share_of_step": swin_ms / total_ms,
                                        "exp_per_s": swin_fl / 128.0 / (swin_ms / 1e3),

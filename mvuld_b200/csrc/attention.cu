@@ -335,34 +335,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     } else {
       // ========================================= PV issuer of group g =========================================
-      if (lane == 0) {
-        const int g = warp - 1;
-        constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, HD, 0, 1);
-        const uint32_t v0 = smem_u32(sV);
-        const uint32_t tO = tmem_base + g * 256 + COL_O;
-        uint32_t n = 0, ph_o = 0;
-        for (int t = g; t < nq; t += 2) {
-          int jlo, jhi;
-          kv_range(t, jlo, jhi);
-          for (int j = jlo; j < jhi; ++j, ++n) {
-            const int b = n % NPB;
-            mbar_wait(&p_full[2 * g + b], (n / NPB) & 1, 22);
-            if (j == jlo && t != g) {
-              mbar_wait(&o_free[g], ph_o, 23);
-              ph_o ^= 1;
-            }
-            if (t == g || MODE == MODE_SEQ) mbar_wait(&v_full[j], 0, 24);
-            ATT_TRACE(12, g, t, j);
-            tc_fence_after();
-            const uint32_t tP = tmem_base + g * 256 + COL_P + b * PW;
-#pragma unroll
-            for (int s = 0; s < KT / 16; ++s) {
-              const uint64_t bd = make_smem_desc(v0 + (j * KT + s * 16) * L::ROW_BYTES, 16, L::SBO, L::LAYOUT);
-              umma_ts(tO, tP + s * 8, bd, idesc_pv, (j != jlo) || (s != 0));
-            }
-            umma_commit(&pv_done[2 * g + b]);
-            ATT_TRACE(13, g, t, j);
+      // uniform control flow, one elected lane issues, descriptor low word advanced by adds (see attn_swin3_kernel)
+      const int g = warp - 1;
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, HD, 0, 1);
+      const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, 16, L::SBO, L::LAYOUT) >> 32);
+      const uint32_t v_lo0 = (uint32_t)make_smem_desc(smem_u32(sV), 16, L::SBO, L::LAYOUT);
+      const uint32_t tO = tmem_base + g * 256 + COL_O;
+      const bool leader = elect_one();
+      uint32_t n = 0, ph_o = 0;
+      for (int t = g; t < nq; t += 2) {
+        int jlo, jhi;
+        kv_range(t, jlo, jhi);
+        for (int j = jlo; j < jhi; ++j, ++n) {
+          const int b = n % NPB;
+          mbar_wait(&p_full[2 * g + b], (n / NPB) & 1, 22);
+          if (j == jlo && t != g) {
+            mbar_wait(&o_free[g], ph_o, 23);
+            ph_o ^= 1;
           }
+          if (t == g || MODE == MODE_SEQ) mbar_wait(&v_full[j], 0, 24);
+          ATT_TRACE(12, g, t, j);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t tP = tmem_base + g * 256 + COL_P + b * PW;
+            const uint32_t v_lo = v_lo0 + (uint32_t)j * (KT * L::ROW_BYTES >> 4);
+#pragma unroll
+            for (int s = 0; s < KT / 16; ++s)
+              umma_ts(tO, tP + s * 8, ((uint64_t)desc_hi << 32) | (v_lo + s * (16 * L::ROW_BYTES >> 4)), idesc_pv,
+                      (j != jlo) || (s != 0));
+            umma_commit(&pv_done[2 * g + b]);
+          }
+          __syncwarp();
+          ATT_TRACE(13, g, t, j);
         }
       }
     }

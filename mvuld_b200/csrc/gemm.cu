@@ -424,33 +424,41 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int m_blk, n_blk;
-      if (BKB > 0 && tile_at(0, m_blk, n_blk)) mbar_wait(bfull, 0, 5);
-      for (int local = 0; tile_at(local, m_blk, n_blk); ++local) {
-        const int acc = local & 1;
-        mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1, 2);
+    // The whole warp runs the (uniform) control flow and one elected lane issues.  Descriptors: the high word is a
+    // constant, the low word (address >> 4 | LBO << 16) advances by plain adds -- assembling each descriptor from
+    // scratch inside a one-lane branch put a ~100-cycle dependent chain (shift / mask / or / elect loop) in front of
+    // every MMA, as long as a 128 x 128 x 16 MMA takes in the tensor pipe.
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, 16, 1024, 2) >> 32);
+    const uint32_t a_lo0 = (uint32_t)make_smem_desc(smem_u32(sA), 16, 1024, 2);
+    const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB), 16, 1024, 2);
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int m_blk, n_blk;
+    if (BKB > 0 && tile_at(0, m_blk, n_blk)) mbar_wait(bfull, 0, 5);
+    for (int local = 0; tile_at(local, m_blk, n_blk); ++local) {
+      const int acc = local & 1;
+      mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase, 3);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase, 3);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b0 = smem_u32(sB + (BKB > 0 ? kb : stage) * Cfg::B_BYTES);
+        if (leader) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (Cfg::A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)(BKB > 0 ? kb : stage) * (Cfg::B_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a0 + k * 32, 16, 1024, 2);
-            const uint64_t bd = make_smem_desc(b0 + k * 32, 16, 1024, 2);
-            umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_ss(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + k * 2), ((uint64_t)desc_hi << 32) | (b_lo + k * 2), idesc,
+                    (kb | k) != 0);
           umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);       // accumulator ready for the epilogue
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tfull[acc]);       // accumulator ready for the epilogue
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access

@@ -111,36 +111,42 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GLN_BM, Cfg::NI, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int acc = (Cfg::NACC == 2) ? (local & 1) : 0;
-        const uint32_t par = (Cfg::NACC == 2) ? ((local >> 1) & 1) : (local & 1);
-        mbar_wait(&tempty[acc], par ^ 1, 2);
+    // uniform control flow, one elected lane issues, descriptors advanced by adds (see gemm.cu)
+    constexpr uint32_t idesc = make_idesc_bf16(GLN_BM, Cfg::NI, 0, 0);
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, 16, Cfg::SBO, Cfg::LAYOUT) >> 32);
+    const uint32_t a_lo0 = (uint32_t)make_smem_desc(smem_u32(sA), 16, Cfg::SBO, Cfg::LAYOUT);
+    const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB), 16, Cfg::SBO, Cfg::LAYOUT);
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = (Cfg::NACC == 2) ? (local & 1) : 0;
+      const uint32_t par = (Cfg::NACC == 2) ? ((local >> 1) & 1) : (local & 1);
+      mbar_wait(&tempty[acc], par ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase, 3);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase, 3);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b0 = smem_u32(sB + stage * Cfg::B_BYTES);
+        if (leader) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (Cfg::A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)stage * (Cfg::B_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a0 + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
 #pragma unroll
-            for (int h = 0; h < N / Cfg::NI; ++h) {
-              const uint64_t bd = make_smem_desc(b0 + h * Cfg::NI * Cfg::ROW_BYTES + k * 32, 16, Cfg::SBO, Cfg::LAYOUT);
-              umma_ss(d_tmem + h * Cfg::NI, ad, bd, idesc, (kb | k) != 0);
-            }
+            for (int h = 0; h < N / Cfg::NI; ++h)
+              umma_ss(d_tmem + h * Cfg::NI, ((uint64_t)desc_hi << 32) | (a_lo + k * 2),
+                      ((uint64_t)desc_hi << 32) | (b_lo + ((h * Cfg::NI * Cfg::ROW_BYTES) >> 4) + k * 2), idesc,
+                      (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tfull[acc]);
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
