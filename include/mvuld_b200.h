@@ -52,6 +52,11 @@ int mvuld_swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const f
                    void* q, void* k, void* v, int B, int H, int W, int C, int nH, int ws, int shift,
                    mvuld_stream_t stream);
 
+/* Training variant of mvuld_swin_qkv: also keeps rq / rk = 1 / max(|q|, eps), 1 / max(|k|, eps) per (token, head), fp32
+ * in the window-major order of q / k, for the backward of F.normalize (swin_transformer_v2.py:155). */
+int mvuld_swin_qkv_train(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias, const float* qscale,
+                         void* q, void* k, void* v, float* rq, float* rk, int B, int H, int W, int C, int nH, int ws,
+                         int shift, mvuld_stream_t stream);
 /* RoBERTa qkv projection, head-major outputs bf16 [B, nH, L, hd]; q multiplied by qmul (= log2 e / sqrt(hd)).
  * Wqkv = cat(query.weight, key.weight, value.weight) [3*Hd, Hd].  HF RobertaSelfAttention via unixcoder.py:36. */
 int mvuld_heads_qkv(const void* X, const void* Wqkv, const float* bias, void* q, void* k, void* v, int B, int L,
@@ -80,6 +85,27 @@ int mvuld_swin_window_attention(const void* q, const void* k, const void* v, con
 int mvuld_swin_window_attention_fixed(const void* q, const void* k, const void* v, const float* bias_rev,
                                       const float* bias_max, const float* q_norm, void* out, int B, int H, int W,
                                       int C, int nH, int ws, int shift, mvuld_stream_t stream);
+
+/* Training forward of the two entry points above: also writes lse, the log2-domain log-sum-exp of every score row
+ * (fp32 [windows * nH, ws^2], window-major like q), which mvuld_swin_attention_bwd recomputes the probabilities from.
+ * fixed != 0: the constant-reference kernel (ws == 28, every head checked by the caller). */
+int mvuld_swin_window_attention_train(const void* q, const void* k, const void* v, const float* bias_rev,
+                                      const float* bias_max, const float* q_norm, void* out, float* lse, int fixed,
+                                      int B, int H, int W, int C, int nH, int ws, int shift, mvuld_stream_t stream);
+/* Backward of the window attention (autograd through swin_transformer_v2.py:155-176, trained by mvuld/main.py:251-300).
+ * prep: gathers dO (bf16 token-major [B*H*W, C], gradient of the attention output before proj) into the window-major
+ * head-major order of q / k / v (dOw), packs ld[row] = (lse, D = rowsum(dO o O)) and makes bf16 copies qb / kb of the
+ * fp16 q^ / k^.  bwd: per (window, head) recomputes P from lse, G = P o (dO V^T - D), and writes fp32 [windows*nH, ws^2, 32]
+ *   dq = G k^,  dk = G^T q^ (q^ as stored: logit scale and log2 e folded in),  dv = P^T dO,
+ * plus gt = G^T as bf16 [windows*nH, ws^2, ntok_pad] (key major; ntok_pad = ws^2 rounded up to 8; null to skip) for
+ * mvuld_swin_bias_grad.  G = dL / d(natural-unit logits).  ws in {7, 14, 28}.  Deterministic (no atomics). */
+int mvuld_swin_attention_bwd_prep(const void* dO, const void* O, const float* lse, const void* qh, const void* kh,
+                                  void* dOw, void* ld, void* qb, void* kb, int B, int H, int W, int C, int nH, int ws,
+                                  int shift, mvuld_stream_t stream);
+int mvuld_swin_attention_bwd(const void* qh, const void* qb, const void* kh, const void* kb, const void* v,
+                             const void* dOw, const void* ld, const float* bias_rev, float* dq, float* dk, float* dv,
+                             void* gt, int ntok_pad, int B, int H, int W, int nH, int ws, int shift,
+                             mvuld_stream_t stream);
 
 /* Key-padded self-attention for the text encoder: q,k,v bf16 [B, nH, L, 64] (q pre-scaled), kv_len int32 [B];
  * out bf16 [B*L, nH*64].  unixcoder.py:35-36. */

@@ -97,6 +97,7 @@ struct AttnParams {
   const int* tile_lo;
   const int* tile_hi;
   void* out;              // bf16 [tokens, C]
+  float* lse;             // optional (training): log2-domain log-sum-exp of every row, [windows * nH, Nq]
   int no_split;           // debug: disable the split remainder tile (MVULD_ATT_NOSPLIT)
 };
 
@@ -646,6 +647,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           lsum += sMerge[ATT_BM * ATT_MERGE_LD + u * ATT_SPLIT_ROWS + qq];
         }
         const float invs = lsum > 0.f ? 1.0f / lsum : 0.f;
+        if (p.lse != nullptr && cg == 0 && i < p.Nq) p.lse[(size_t)bh * p.Nq + i] = m_run + log2f(lsum);
         if (i < p.Nq) {
           const int hl = i / WS, wl = i - hl * WS;
           int hh = wr * WS + hl + p.shift;
@@ -664,6 +666,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         continue;
       }
       const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+      if (p.lse != nullptr && i < p.Nq) p.lse[(size_t)bh * p.Nq + i] = m_run + log2f(lsum);
       size_t orow;
       if (MODE == MODE_SWIN) {
         const int hl = i / WS, wl = i - hl * WS;
@@ -1074,6 +1077,7 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             lsum += src[32];
           }
           const float invs = lsum > 0.f ? 1.0f / lsum : 0.f;
+          if (p.lse != nullptr && cg == 0) p.lse[(size_t)bh * p.Nq + i] = m_ref + log2f(lsum);
           const int hl = i / WS, wl = i - hl * WS;
           int hh = wr * WS + hl + p.shift;
           if (hh >= p.H) hh -= p.H;
@@ -1087,6 +1091,7 @@ attn_swin3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         } else {
           const float lsum = __uint_as_float(o2[0]);
           const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+          if (p.lse != nullptr) p.lse[(size_t)bh * p.Nq + i] = m_ref + log2f(lsum);
           const int hl = i / WS, wl = i - hl * WS;
           int hh = wr * WS + hl + p.shift;
           if (hh >= p.H) hh -= p.H;
@@ -1260,9 +1265,9 @@ extern "C" int mvuld_debug_att_trace(long long* host_out, int max_records) {
 }
 #endif
 
-extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
-                                           const float* bias_max, const float* q_norm, void* out, int B, int H, int W,
-                                           int C, int nH, int ws, int shift, cudaStream_t stream) {
+static int swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
+                                 const float* bias_max, const float* q_norm, void* out, float* lse, int B, int H, int W,
+                                 int C, int nH, int ws, int shift, cudaStream_t stream) {
   MV_CHECK_ARG(C == nH * 32, "swin attention: head_dim must be 32");
   MV_CHECK_ARG(H % ws == 0 && W % ws == 0, "swin attention: window must tile the token grid");
   MV_CHECK_ARG(shift == 0 || shift == ws / 2, "swin attention: shift must be 0 or ws/2");
@@ -1275,6 +1280,7 @@ extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const v
   p.H = H; p.W = W; p.shift = shift; p.C = C;
   p.kv_len = nullptr;
   p.out = out;
+  p.lse = lse;
   p.no_split = getenv("MVULD_ATT_NOSPLIT") != nullptr;
   const int n_bh = B * (H / ws) * (W / ws) * nH;
   switch (ws) {
@@ -1284,12 +1290,32 @@ extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const v
     default: return mv::fail(-1, "swin attention: window %d not instantiated (7, 14, 28)", ws);
   }
 }
+extern "C" int mvuld_swin_window_attention(const void* q, const void* k, const void* v, const float* bias_rev,
+                                           const float* bias_max, const float* q_norm, void* out, int B, int H, int W,
+                                           int C, int nH, int ws, int shift, cudaStream_t stream) {
+  return swin_window_attention(q, k, v, bias_rev, bias_max, q_norm, out, nullptr, B, H, W, C, nH, ws, shift, stream);
+}
+
+static int swin_window_attention_fixed(const void* q, const void* k, const void* v, const float* bias_rev,
+                                       const float* bias_max, const float* q_norm, void* out, float* lse, int B, int H,
+                                       int W, int C, int nH, int ws, int shift, cudaStream_t stream);
+// Training forward: the same kernels, plus the log2-domain log-sum-exp of every score row (fp32 [windows * nH, ws^2],
+// window-major like q) that mvuld_swin_attention_bwd recomputes the probabilities from.  fixed != 0 selects the
+// constant-reference kernel (ws == 28, caller-checked as for mvuld_swin_window_attention_fixed).
+extern "C" int mvuld_swin_window_attention_train(const void* q, const void* k, const void* v, const float* bias_rev,
+                                                 const float* bias_max, const float* q_norm, void* out, float* lse,
+                                                 int fixed, int B, int H, int W, int C, int nH, int ws, int shift,
+                                                 cudaStream_t stream) {
+  MV_CHECK_ARG(lse != nullptr, "swin attention (train): lse is null");
+  if (fixed) return swin_window_attention_fixed(q, k, v, bias_rev, bias_max, q_norm, out, lse, B, H, W, C, nH, ws, shift, stream);
+  return swin_window_attention(q, k, v, bias_rev, bias_max, q_norm, out, lse, B, H, W, C, nH, ws, shift, stream);
+}
 
 // Same operation for launches whose heads ALL satisfy the constant-reference condition 2 |q^| + max bias <= 100 (log2
 // units; the caller checks it once per weight version -- a violating head traps): the three-group kernel above.
-extern "C" int mvuld_swin_window_attention_fixed(const void* q, const void* k, const void* v, const float* bias_rev,
-                                                 const float* bias_max, const float* q_norm, void* out, int B, int H,
-                                                 int W, int C, int nH, int ws, int shift, cudaStream_t stream) {
+static int swin_window_attention_fixed(const void* q, const void* k, const void* v, const float* bias_rev,
+                                       const float* bias_max, const float* q_norm, void* out, float* lse, int B, int H,
+                                       int W, int C, int nH, int ws, int shift, cudaStream_t stream) {
   MV_CHECK_ARG(C == nH * 32, "swin attention: head_dim must be 32");
   MV_CHECK_ARG(ws == 28, "swin attention (constant reference): 28x28 windows only, use mvuld_swin_window_attention");
   MV_CHECK_ARG(H % ws == 0 && W % ws == 0, "swin attention: window must tile the token grid");
@@ -1303,8 +1329,14 @@ extern "C" int mvuld_swin_window_attention_fixed(const void* q, const void* k, c
   p.q_norm = q_norm;
   p.H = H; p.W = W; p.shift = shift; p.C = C;
   p.out = out;
+  p.lse = lse;
   const int n_bh = B * (H / ws) * (W / ws) * nH;
   return launch_attn_swin3<28>(q, k, v, n_bh, p, stream);
+}
+extern "C" int mvuld_swin_window_attention_fixed(const void* q, const void* k, const void* v, const float* bias_rev,
+                                                 const float* bias_max, const float* q_norm, void* out, int B, int H,
+                                                 int W, int C, int nH, int ws, int shift, cudaStream_t stream) {
+  return swin_window_attention_fixed(q, k, v, bias_rev, bias_max, q_norm, out, nullptr, B, H, W, C, nH, ws, shift, stream);
 }
 
 static int seq_attention(const void* q, const void* k, const void* v, const int* kv_len, const int* seg_lo,

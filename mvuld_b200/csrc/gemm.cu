@@ -160,6 +160,8 @@ struct EpiQkvSwin {
   __half* q;
   __half* k;
   bf16* v;
+  float* rq = nullptr;   // training: 1 / max(|q|, eps) of every (token, head) in the window-major order of q (or null)
+  float* rk = nullptr;
   int C, nH, H, W, ws, shift, M;
   __device__ __forceinline__ void operator()(int row, int col0, const uint32_t (&r)[32]) const {
     if (row >= M) return;
@@ -177,11 +179,13 @@ struct EpiQkvSwin {
         v32[i] += b.x; v32[i + 1] += b.y; v32[i + 2] += b.z; v32[i + 3] += b.w;
       }
     }
+    float rnorm = 0.f;
     if (which < 2) {
       float ss = 0.f;
 #pragma unroll
       for (int i = 0; i < 32; ++i) ss += v32[i] * v32[i];
       float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      rnorm = inv;
       if (which == 0) inv *= __ldg(qscale + head);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v32[i] *= inv;
@@ -198,6 +202,8 @@ struct EpiQkvSwin {
     const int slot = (hh % ws) * ws + (ww % ws);
     const int nW = (H / ws) * nWw;
     const size_t dst = ((((size_t)b * nW + win) * nH + head) * (size_t)(ws * ws) + slot) * 32;
+    if (which == 0 && rq) rq[dst >> 5] = rnorm;
+    if (which == 1 && rk) rk[dst >> 5] = rnorm;
     // one head of one token = 64 contiguous bytes = two 256-bit stores
     uint32_t w[16];
     if (which == 2) {
@@ -620,17 +626,31 @@ extern "C" int mvuld_gemm_gru(const void* A, int lda, const void* Wg, int ldw, i
   return launch_gemm<128, 6, EpiGru>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
 }
 
-extern "C" int mvuld_swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias,
-                              const float* qscale, void* q, void* k, void* v, int B, int H, int W, int C, int nH,
-                              int ws, int shift, cudaStream_t stream) {
+static int swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias, const float* qscale,
+                    void* q, void* k, void* v, float* rq, float* rk, int B, int H, int W, int C, int nH, int ws,
+                    int shift, cudaStream_t stream) {
   MV_CHECK_ARG(C % 128 == 0 && C / nH == 32, "swin_qkv: need C %% 128 == 0 and head_dim 32 (C=%d nH=%d)", C, nH);
   MV_CHECK_ARG(H % ws == 0 && W % ws == 0 && shift >= 0 && shift < ws, "swin_qkv: bad window geometry");
   EpiQkvSwin e;
   e.q_bias = q_bias; e.v_bias = v_bias; e.qscale = qscale;
   e.q = reinterpret_cast<__half*>(q); e.k = reinterpret_cast<__half*>(k); e.v = reinterpret_cast<bf16*>(v);
+  e.rq = rq; e.rk = rk;
   e.C = C; e.nH = nH; e.H = H; e.W = W; e.ws = ws; e.shift = shift; e.M = B * H * W;
   if ((3 * C) % 256 == 0) return launch_gemm<256, 4, EpiQkvSwin>(X, C, Wqkv, C, B * H * W, 3 * C, C, e, stream);
   return launch_gemm<128, 6, EpiQkvSwin>(X, C, Wqkv, C, B * H * W, 3 * C, C, e, stream);
+}
+extern "C" int mvuld_swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias,
+                              const float* qscale, void* q, void* k, void* v, int B, int H, int W, int C, int nH,
+                              int ws, int shift, cudaStream_t stream) {
+  return swin_qkv(X, Wqkv, q_bias, v_bias, qscale, q, k, v, nullptr, nullptr, B, H, W, C, nH, ws, shift, stream);
+}
+// training forward: also keeps 1 / max(|q|, eps) and 1 / max(|k|, eps) per (token, head) (fp32, window-major like q / k)
+// for the backward of F.normalize (swin_transformer_v2.py:155)
+extern "C" int mvuld_swin_qkv_train(const void* X, const void* Wqkv, const float* q_bias, const float* v_bias,
+                                    const float* qscale, void* q, void* k, void* v, float* rq, float* rk, int B, int H,
+                                    int W, int C, int nH, int ws, int shift, cudaStream_t stream) {
+  MV_CHECK_ARG(rq && rk, "swin_qkv_train: rq / rk are null");
+  return swin_qkv(X, Wqkv, q_bias, v_bias, qscale, q, k, v, rq, rk, B, H, W, C, nH, ws, shift, stream);
 }
 
 extern "C" int mvuld_heads_qkv(const void* X, const void* Wqkv, const float* bias, void* q, void* k, void* v, int B,
