@@ -107,6 +107,29 @@ int mvuld_swin_attention_bwd(const void* qh, const void* qb, const void* kh, con
                              void* gt, int ntok_pad, int B, int H, int W, int nH, int ws, int shift,
                              mvuld_stream_t stream);
 
+/* Bias-table gradient from the G^T matrices of mvuld_swin_attention_bwd: dtab[h, (qy-ky+ws-1) * (2ws-1) + (qx-kx+ws-1)]
+ * += sum over the n_win window instances and all (query, key) pairs of that offset (the reference's table order,
+ * natural units).  partial: fp32 workspace [nH, ws, ws, 2ws-1].  Fixed summation order. */
+int mvuld_swin_bias_grad(const void* gt, int n_win, int nH, int ws, int npad, float* partial, float* dtab,
+                         mvuld_stream_t stream);
+/* cpb_mlp backward (swin_transformer_v2.py:98-111,159,163): tab = table_ref of mvuld_cpb_table, dtab as above;
+ * accumulates dw1 [512,2], db1 [512], dw2 [nH,512]. */
+int mvuld_cpb_mlp_bwd(const float* w1, const float* b1, const float* w2, const float* tab, const float* dtab, int nH,
+                      int ws, int pretrained_ws, float* dw1, float* db1, float* dw2, mvuld_stream_t stream);
+/* (dq, dk, dv) of mvuld_swin_attention_bwd -> d qkv, bf16 token-major [B*H*W, 3C] (q | k | v columns): backward of
+ * F.normalize with the saved inverse norms rq / rk, window_reverse and the inverse cyclic shift; accumulates
+ * dlogit_scale [nH] (zero past the clamp at ln 100).  ls_partial: fp32 [mvuld_swin_qkv_bwd_blocks(...), nH]. */
+int mvuld_swin_qkv_bwd_blocks(int B, int H, int W, int nH);
+int mvuld_swin_qkv_bwd(const float* dq, const float* dk, const float* dv, const void* qh, const void* kh, const float* rq,
+                       const float* rk, const float* qscale, const float* logit_scale, void* dqkv, float* dlogit_scale,
+                       float* ls_partial, int B, int H, int W, int C, int nH, int ws, int shift, mvuld_stream_t stream);
+/* Training-mode plumbing: erf GELU bf16 -> bf16 (the pre-activation is kept for mvuld_gelu_bwd); the inverse of
+ * mvuld_patch_merge_gather for fp32 gradients; PatchEmbed's 4x4 patches as a bf16 [tokens, 48] matrix (tap order of
+ * proj.weight.view(E, 48)) so that the projection and its weight gradient run on the GEMM. */
+int mvuld_gelu_fwd(const void* x, void* y, long long n, mvuld_stream_t stream);
+int mvuld_patch_merge_scatter(const float* dg, float* dx, int B, int H, int W, int C, mvuld_stream_t stream);
+int mvuld_patch_im2col(const float* img, void* out, int B, int Hi, int Wi, mvuld_stream_t stream);
+
 /* Key-padded self-attention for the text encoder: q,k,v bf16 [B, nH, L, 64] (q pre-scaled), kv_len int32 [B];
  * out bf16 [B*L, nH*64].  unixcoder.py:35-36. */
 int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out, int B, int L,

@@ -29,6 +29,13 @@ SIGNATURES = {
     "mvuld_swin_window_attention_train": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_swin_attention_bwd_prep": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_swin_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mvuld_swin_bias_grad": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "mvuld_cpb_mlp_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "mvuld_swin_qkv_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mvuld_swin_qkv_bwd_blocks": [_I, _I, _I, _I],
+    "mvuld_gelu_fwd": [_P, _P, _LL, _P],
+    "mvuld_patch_merge_scatter": [_P, _P, _I, _I, _I, _I, _P],
+    "mvuld_patch_im2col": [_P, _P, _I, _I, _I, _P],
     "mvuld_swin_qkv_train": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_seq_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_ln_rows": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
@@ -89,7 +96,8 @@ _SYNC_EACH = bool(os.environ.get("MVULD_SYNC_EACH"))     # debug: synchronise af
 _lib = None
 launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
 _LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3, "mvuld_sumsq_f32": 2,
-                      "mvuld_ln_rows_bwd": 2, "mvuld_pos_branch_bwd": 2}
+                      "mvuld_ln_rows_bwd": 2, "mvuld_pos_branch_bwd": 2, "mvuld_swin_bias_grad": 2,
+                      "mvuld_swin_qkv_bwd": 2}
 
 
 def load() -> C.CDLL:

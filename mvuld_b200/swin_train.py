@@ -1,0 +1,416 @@
+"""Training step of the image encoder: SwinV2 forward + backward + AdamW as fixed sequences of C-ABI launches.
+
+Reference: /root/reference/mvuld/main.py:251-300 (``outputs = model(samples)``; ``loss = criterion(outputs, targets)``;
+``loss_scaler(loss, optimizer, clip_grad=..., parameters=model.parameters())``) training
+``mvuld/models/swin_transformer_v2.py`` under autograd -- BASELINE.json configs[4] in its primary reading (the encoder
+trains, not only the fusion head).  Here the backward pass is hand written:
+
+* dense products (forward, ``dX = dY W``, ``dW = dY^T X``) on ``gemm_tn_kernel`` (tcgen05), weight gradients written by
+  the GEMM epilogue straight into ONE flat fp32 gradient buffer (= the all-reduce buckets of data parallelism);
+* scaled-cosine window attention backward on tcgen05 (``csrc/attention_bwd.cu``), bias-table gradient ->
+  ``cpb_mlp`` gradients, ``F.normalize`` / ``logit_scale`` backward (``csrc/swin_bwd.cu``);
+* res-post-norm LayerNorm / GELU backward row kernels (``csrc/train.cu``), patch merging / patch embedding as products.
+
+The residual-stream gradient stays fp32; GEMM operands are bf16 (as the forward's).  Every reduction has a fixed order:
+a step is bit-reproducible.  Stochastic depth / dropout are not applied (rates 0, as in the pinned oracle cases).
+No CPU path: CUDA tensors only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .swin_transformer_v2 import LOG2E, SwinTransformerV2
+from .train import _ALIGN, plan_buckets, plan_layout
+
+_NO_DECAY_KEYWORDS = ("cpb_mlp", "logit_scale", "relative_position_bias_table")      # swin_transformer_v2.py:596-598
+
+
+class SwinTrainer:
+    """Owns flat parameter / gradient / AdamW buffers of a ``SwinTransformerV2`` and runs training steps on it."""
+
+    def __init__(self, model: SwinTransformerV2, lr: float = 5e-5, weight_decay: float = 0.05,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, clip_grad: float = 5.0,
+                 process_group=None, world_size: Optional[int] = None, bucket_mb: float = 25.0):
+        dev = model.patch_embed.proj.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("mvuld_b200 SwinTrainer runs on CUDA only (no CPU fallback): move the model to the GPU")
+        _lib.load()
+        self.model, self.dev = model, dev
+        self.lr, self.wd, self.betas, self.eps, self.clip = float(lr), float(weight_decay), betas, float(eps), float(clip_grad)
+        self.group = process_group
+        if world_size is None:
+            import torch.distributed as dist
+            world_size = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = int(world_size)
+        self.step_count = 0
+
+        params = dict(model.named_parameters())
+        self.names: List[str] = [n for n, p in reversed(list(model.named_parameters())) if p.requires_grad]
+        self.offsets, self.total = plan_layout([(n, params[n].numel()) for n in self.names])
+        self.shapes = {n: tuple(params[n].shape) for n in self.names}
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.flat_p = torch.zeros(self.total, **f32)
+        self.flat_g = torch.zeros(self.total, **f32)
+        self.flat_m = torch.zeros(self.total, **f32)
+        self.flat_v = torch.zeros(self.total, **f32)
+        self.flat_w16 = torch.zeros(self.total, device=dev, dtype=torch.bfloat16)
+        with torch.no_grad():
+            for n in self.names:                       # re-point the module parameters at the flat buffer
+                view = self._view(self.flat_p, n)
+                view.copy_(params[n].detach().float())
+                params[n].data = view
+        seg_end, seg_wd = [], []
+        for n in self.names:                           # optimizer.py:35-50 + no_weight_decay_keywords
+            no_decay = len(self.shapes[n]) == 1 or n.endswith(".bias") or any(k in n for k in _NO_DECAY_KEYWORDS)
+            seg_end.append(self.offsets[n] + (params[n].numel() + _ALIGN - 1) // _ALIGN * _ALIGN)
+            seg_wd.append(0.0 if no_decay else self.wd)
+        self.seg_end = torch.tensor(seg_end, dtype=torch.int64, device=dev)
+        self.seg_wd = torch.tensor(seg_wd, dtype=torch.float32, device=dev)
+        self.buckets = plan_buckets(seg_end, int(bucket_mb * (1 << 20) / 4))
+        self.gnorm_sq = torch.zeros(1, **f32)
+        self.gnorm_partials = torch.zeros(1184, **f32)
+        self.loss_buf = torch.zeros(1, **f32)
+        self._geometry()
+        if self.world > 1:
+            self.sync_replicas()
+        else:
+            self._refresh()
+
+    # ------------------------------------------------------------------------------------------------
+    def _view(self, flat: torch.Tensor, name: str, shape=None) -> torch.Tensor:
+        shp = self.shapes[name] if shape is None else shape
+        o = self.offsets[name]
+        return flat[o:o + math.prod(shp)].view(shp)
+
+    def _geometry(self):
+        m = self.model
+        self.blocks = []
+        for li, layer in enumerate(m.layers):
+            for bi, blk in enumerate(layer.blocks):
+                a = blk.attn
+                self.blocks.append(dict(prefix=f"layers.{li}.blocks.{bi}.", stage=li, H=blk.input_resolution[0],
+                                        W=blk.input_resolution[1], C=blk.dim, nH=blk.num_heads, ws=blk.window_size,
+                                        shift=blk.shift_size, pws=int(a.pretrained_window_size[0]),
+                                        eps1=blk.norm1.eps, eps2=blk.norm2.eps))
+        self.merges = {}
+        for li, layer in enumerate(m.layers):
+            if layer.downsample is not None:
+                d = layer.downsample
+                self.merges[li] = dict(prefix=f"layers.{li}.downsample.", H=d.input_resolution[0],
+                                       W=d.input_resolution[1], C=d.dim, eps=d.norm.eps)
+        self.has_head = isinstance(m.head, torch.nn.Linear)
+
+    @torch.no_grad()
+    def _refresh(self):
+        """bf16 copies of every weight matrix (GEMM operands), their transposes (dX = dY W), the CPB tables."""
+        _lib.call("mvuld_f32_to_bf16", self.flat_p, self.flat_w16, self.total)
+        p32 = lambda n: self._view(self.flat_p, n)
+        w16 = lambda n, shape=None: self._view(self.flat_w16, n, shape)
+        self.w, self.wt = {}, {}
+        E = self.model.embed_dim
+        mats = [("patch_embed.proj.weight", (E, 48))]
+        for b in self.blocks:
+            mats += [(b["prefix"] + s, None) for s in ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")]
+        mats += [(mg["prefix"] + "reduction.weight", None) for mg in self.merges.values()]
+        for n, shape in mats:
+            self.w[n] = w16(n, shape)
+            self.wt[n] = self._transpose(self.w[n])
+        for b in self.blocks:
+            pre, nH, ws = b["prefix"] + "attn.", b["nH"], b["ws"]
+            side = 2 * ws - 1
+            tab_rev = torch.empty(nH, side * side, device=self.dev, dtype=torch.float32)
+            tab_ref = torch.empty(nH, side * side, device=self.dev, dtype=torch.float32)
+            tab_max = torch.empty(nH, device=self.dev, dtype=torch.float32)
+            _lib.call("mvuld_cpb_table", p32(pre + "cpb_mlp.0.weight"), p32(pre + "cpb_mlp.0.bias"),
+                      p32(pre + "cpb_mlp.2.weight"), nH, ws, b["pws"], tab_rev, tab_ref, tab_max)
+            qscale = (torch.clamp(p32(pre + "logit_scale").view(-1), max=math.log(100.0)).exp() * LOG2E).contiguous()
+            fixed = ws == 28 and bool((2.0 * qscale + tab_max <= 100.0).all().item())
+            b.update(tab_rev=tab_rev, tab_ref=tab_ref, tab_max=tab_max, qscale=qscale, fixed=int(fixed))
+        self.model.invalidate()
+
+    def refresh(self):
+        if self.world > 1:
+            self.sync_replicas()
+        else:
+            self._refresh()
+
+    @torch.no_grad()
+    def sync_replicas(self, src: int = 0):
+        """Every rank takes rank ``src``'s parameters / AdamW state (DDP's constructor broadcast, main.py:119-121)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            meta = torch.tensor([float(self.step_count)], device=self.dev, dtype=torch.float64)
+            for t in (self.flat_p, self.flat_m, self.flat_v, meta):
+                dist.broadcast(t, src=src, group=self.group)
+            self.step_count = int(meta.item())
+        self._refresh()
+
+    def _transpose(self, x: torch.Tensor) -> torch.Tensor:
+        """bf16 [R, C] -> [C, Rp], Rp = R rounded up to 8 (zero filled): the K-major operand of a product over R."""
+        R, C = x.shape
+        assert x.stride(1) == 1
+        Rp = (R + 7) // 8 * 8
+        out = torch.empty(C, Rp, device=self.dev, dtype=torch.bfloat16)
+        _lib.call("mvuld_transpose_bf16", _lib._Raw(x), x.stride(0), out, R, C, Rp)
+        return out
+
+    def _grad_w(self, dy: torch.Tensor, x: torch.Tensor, name: str, shape=None):
+        """dW [out, in] = dY^T X on the tensor cores, fp32 straight into the flat gradient buffer."""
+        _lib.gemm(self._transpose(dy), self._transpose(x), out_f32=self._view(self.flat_g, name, shape))
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_train(self, x: torch.Tensor):
+        """Training-mode ``forward_features`` (swin_transformer_v2.py:623-635) -> (features fp32 [B, num_features], ctx)."""
+        if not x.is_cuda:
+            raise RuntimeError("mvuld_b200 SwinTrainer takes CUDA tensors (no CPU fallback)")
+        m, dev = self.model, self.dev
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+        pv = lambda n: self._view(self.flat_p, n)
+        x = x.to(f32).contiguous()
+        B, E = x.shape[0], m.embed_dim
+        Hp, Wp = m.patches_resolution
+        if x.shape[2] != Hp * 4 or x.shape[3] != Wp * 4:
+            raise ValueError(f"Input image size ({x.shape[2]}*{x.shape[3]}) doesn't match model ({Hp * 4}*{Wp * 4}).")
+        ctx = dict(B=B, blocks=[], merges={})
+        M = B * Hp * Wp
+        a0 = e((M, 48), bf)
+        _lib.call("mvuld_patch_im2col", x, a0, B, x.shape[2], x.shape[3])
+        y_pe = e((M, E), bf)
+        _lib.gemm(a0, self.w["patch_embed.proj.weight"], bias=pv("patch_embed.proj.bias"), out_bf16=y_pe)
+        x32, xb = e((M, E), f32), e((M, E), bf)
+        _lib.call("mvuld_ln_rows", y_pe, None, pv("patch_embed.norm.weight"), pv("patch_embed.norm.bias"), x32, xb, M, E,
+                  float(m.patch_embed.norm.eps), 0)
+        ctx["pe"] = dict(a0=a0, y=y_pe)
+        for bi, b in enumerate(self.blocks):
+            P, H, W, C, nH, ws, shift = b["prefix"], b["H"], b["W"], b["C"], b["nH"], b["ws"], b["shift"]
+            M, N = B * H * W, ws * ws
+            n_bh = M // N * nH
+            q, k, v = e((n_bh, N, 32), torch.float16), e((n_bh, N, 32), torch.float16), e((n_bh, N, 32), bf)
+            rq, rk, lse = e((n_bh, N), f32), e((n_bh, N), f32), e((n_bh, N), f32)
+            _lib.call("mvuld_swin_qkv_train", xb, self.w[P + "attn.qkv.weight"], pv(P + "attn.q_bias"), pv(P + "attn.v_bias"),
+                      b["qscale"], q, k, v, rq, rk, B, H, W, C, nH, ws, shift)
+            att = e((M, C), bf)
+            _lib.call("mvuld_swin_window_attention_train", q, k, v, b["tab_rev"], b["tab_max"], b["qscale"], att, lse,
+                      b["fixed"], B, H, W, C, nH, ws, shift)
+            y1 = e((M, C), bf)
+            _lib.gemm(att, self.w[P + "attn.proj.weight"], bias=pv(P + "attn.proj.bias"), out_bf16=y1)
+            xb1 = e((M, C), bf)
+            _lib.call("mvuld_ln_rows", y1, x32, pv(P + "norm1.weight"), pv(P + "norm1.bias"), x32, xb1, M, C, float(b["eps1"]), 1)
+            hdim = self.shapes[P + "mlp.fc1.weight"][0]
+            pre = e((M, hdim), bf)
+            _lib.gemm(xb1, self.w[P + "mlp.fc1.weight"], bias=pv(P + "mlp.fc1.bias"), out_bf16=pre)
+            hid = e((M, hdim), bf)
+            _lib.call("mvuld_gelu_fwd", pre, hid, M * hdim)
+            y2 = e((M, C), bf)
+            _lib.gemm(hid, self.w[P + "mlp.fc2.weight"], bias=pv(P + "mlp.fc2.bias"), out_bf16=y2)
+            xb2 = e((M, C), bf)
+            _lib.call("mvuld_ln_rows", y2, x32, pv(P + "norm2.weight"), pv(P + "norm2.bias"), x32, xb2, M, C, float(b["eps2"]), 1)
+            ctx["blocks"].append(dict(xb_in=xb, q=q, k=k, v=v, rq=rq, rk=rk, lse=lse, att=att, y1=y1, xb1=xb1, pre=pre,
+                                      hid=hid, y2=y2))
+            xb = xb2
+            last_of_stage = bi + 1 == len(self.blocks) or self.blocks[bi + 1]["stage"] != b["stage"]
+            if last_of_stage and b["stage"] in self.merges:
+                mg = self.merges[b["stage"]]
+                Pm = mg["prefix"]
+                M2 = B * (H // 2) * (W // 2)
+                gathered = e((M2, 4 * C), bf)
+                _lib.call("mvuld_patch_merge_gather", xb, gathered, B, H, W, C)
+                y = e((M2, 2 * C), bf)
+                _lib.gemm(gathered, self.w[Pm + "reduction.weight"], out_bf16=y)
+                x32, xb = e((M2, 2 * C), f32), e((M2, 2 * C), bf)
+                _lib.call("mvuld_ln_rows", y, None, pv(Pm + "norm.weight"), pv(Pm + "norm.bias"), x32, xb, M2, 2 * C,
+                          float(mg["eps"]), 0)
+                ctx["merges"][b["stage"]] = dict(gathered=gathered, y=y)
+        last = self.blocks[-1]
+        T, C = last["H"] * last["W"], last["C"]
+        feat = e((B, C), f32)
+        _lib.call("mvuld_ln_meanpool", x32, pv("norm.weight"), pv("norm.bias"), feat, B, T, C, float(m.norm.eps))
+        ctx.update(xb_last=xb, T=T, feat=feat)
+        return feat, ctx
+
+    @torch.no_grad()
+    def backward_train(self, ctx: dict, dfeat: torch.Tensor, on_bucket=None):
+        """Backward of ``forward_train`` for the cotangent ``dfeat`` [B, num_features]; fills ``flat_g`` (call
+        ``flat_g.zero_()`` first: vector gradients accumulate).  ``on_bucket``: called with each gradient bucket as soon
+        as it is complete (data-parallel all-reduce overlap)."""
+        m, dev, G = self.model, self.dev, self.flat_g
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
+        pv = lambda n: self._view(self.flat_p, n)
+        gv = lambda n: self._view(G, n)
+        B = ctx["B"]
+        done, bucket_i = set(), 0
+
+        def ready(*names):
+            nonlocal bucket_i
+            if on_bucket is None:
+                return
+            done.update(names)
+            while bucket_i < len(self.buckets):
+                lo, hi = self.buckets[bucket_i]
+                need = [n for n in self.names if lo <= self.offsets[n] < hi]
+                if not all(n in done for n in need):
+                    break
+                on_bucket(self.buckets[bucket_i])
+                bucket_i += 1
+
+        def ln_bwd(y, gamma_name, beta_name, dout, M, C, eps, mode, want_f32=False):
+            dvb = None if want_f32 else e((M, C), bf)
+            dv32 = e((M, C), f32) if want_f32 else None
+            _lib.call("mvuld_ln_rows_bwd", y, None, pv(gamma_name), dout, dvb, dv32, gv(gamma_name), gv(beta_name),
+                      _lib.ln_rows_bwd_partials(M, C, dev), M, C, float(eps), mode)
+            return dv32 if want_f32 else dvb
+
+        last = self.blocks[-1]
+        T, C = ctx["T"], last["C"]
+        M = B * T
+        dln = (dfeat.to(f32) / T).repeat_interleave(T, dim=0).contiguous()                  # AdaptiveAvgPool1d(1) backward
+        dx = ln_bwd(ctx["xb_last"], "norm.weight", "norm.bias", dln, M, C, m.norm.eps, 0, want_f32=True)
+        ready("norm.weight", "norm.bias")
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            b, s = self.blocks[bi], ctx["blocks"][bi]
+            P, H, W, C, nH, ws, shift = b["prefix"], b["H"], b["W"], b["C"], b["nH"], b["ws"], b["shift"]
+            M, N = B * H * W, ws * ws
+            n_bh = M // N * nH
+            last_of_stage = bi + 1 == len(self.blocks) or self.blocks[bi + 1]["stage"] != b["stage"]
+            if last_of_stage and b["stage"] in self.merges:
+                # ---- PatchMerging backward (the merge FOLLOWS this block in the forward pass) ----
+                mg, sm = self.merges[b["stage"]], ctx["merges"][b["stage"]]
+                Pm = mg["prefix"]
+                M2 = B * (H // 2) * (W // 2)
+                dy = ln_bwd(sm["y"], Pm + "norm.weight", Pm + "norm.bias", dx, M2, 2 * C, mg["eps"], 0)
+                self._grad_w(dy, sm["gathered"], Pm + "reduction.weight")
+                dg = e((M2, 4 * C), f32)
+                _lib.gemm(dy, self.wt[Pm + "reduction.weight"], out_f32=dg)
+                dx = e((M, C), f32)
+                _lib.call("mvuld_patch_merge_scatter", dg, dx, B, H, W, C)
+                ready(Pm + "norm.weight", Pm + "norm.bias", Pm + "reduction.weight")
+            # ---- x2 = x1 + LN2(fc2(gelu(fc1(x1)))) ----
+            hdim = self.shapes[P + "mlp.fc1.weight"][0]
+            dy2 = ln_bwd(s["y2"], P + "norm2.weight", P + "norm2.bias", dx, M, C, b["eps2"], 1)
+            self._grad_w(dy2, s["hid"], P + "mlp.fc2.weight")
+            _lib.call("mvuld_colsum", dy2, 1, C, gv(P + "mlp.fc2.bias"), M, C)
+            dhid = e((M, hdim), bf)
+            _lib.gemm(dy2, self.wt[P + "mlp.fc2.weight"], out_bf16=dhid)
+            dpre = e((M, hdim), bf)
+            _lib.call("mvuld_gelu_bwd", s["pre"], dhid, dpre, M * hdim)
+            self._grad_w(dpre, s["xb1"], P + "mlp.fc1.weight")
+            _lib.call("mvuld_colsum", dpre, 1, hdim, gv(P + "mlp.fc1.bias"), M, hdim)
+            _lib.gemm(dpre, self.wt[P + "mlp.fc1.weight"], res=dx, out_f32=dx)              # dx1 = dx2 + dpre W_fc1
+            del dhid, dpre
+            # ---- x1 = x0 + LN1(proj(attention(x0))) ----
+            dy1 = ln_bwd(s["y1"], P + "norm1.weight", P + "norm1.bias", dx, M, C, b["eps1"], 1)
+            self._grad_w(dy1, s["att"], P + "attn.proj.weight")
+            _lib.call("mvuld_colsum", dy1, 1, C, gv(P + "attn.proj.bias"), M, C)
+            datt = e((M, C), bf)
+            _lib.gemm(dy1, self.wt[P + "attn.proj.weight"], out_bf16=datt)
+            dOw, ld = e((n_bh, N, 32), bf), e((n_bh, N, 2), f32)
+            qb, kb = e((n_bh, N, 32), bf), e((n_bh, N, 32), bf)
+            _lib.call("mvuld_swin_attention_bwd_prep", datt, s["att"], s["lse"], s["q"], s["k"], dOw, ld, qb, kb, B, H, W, C,
+                      nH, ws, shift)
+            npad = (N + 7) // 8 * 8
+            dq, dk, dv = e((n_bh, N, 32), f32), e((n_bh, N, 32), f32), e((n_bh, N, 32), f32)
+            gt = e((n_bh, N, npad), bf)
+            _lib.call("mvuld_swin_attention_bwd", s["q"], qb, s["k"], kb, s["v"], dOw, ld, b["tab_rev"], dq, dk, dv, gt,
+                      npad, B, H, W, nH, ws, shift)
+            side = 2 * ws - 1
+            dtab = torch.zeros(nH, side * side, device=dev, dtype=f32)
+            _lib.call("mvuld_swin_bias_grad", gt, n_bh // nH, nH, ws, npad, e((nH, ws, ws, side), f32), dtab)
+            A = P + "attn."
+            _lib.call("mvuld_cpb_mlp_bwd", pv(A + "cpb_mlp.0.weight"), pv(A + "cpb_mlp.0.bias"), pv(A + "cpb_mlp.2.weight"),
+                      b["tab_ref"], dtab, nH, ws, b["pws"], gv(A + "cpb_mlp.0.weight"), gv(A + "cpb_mlp.0.bias"),
+                      gv(A + "cpb_mlp.2.weight"))
+            del gt, dOw, qb, kb
+            dqkv = e((M, 3 * C), bf)
+            nblk = _lib.load().mvuld_swin_qkv_bwd_blocks(B, H, W, nH)
+            _lib.call("mvuld_swin_qkv_bwd", dq, dk, dv, s["q"], s["k"], s["rq"], s["rk"], b["qscale"],
+                      pv(A + "logit_scale").view(-1), dqkv, gv(A + "logit_scale").view(-1), e((nblk, nH), f32), B, H, W, C,
+                      nH, ws, shift)
+            del dq, dk, dv
+            self._grad_w(dqkv, s["xb_in"], A + "qkv.weight")
+            _lib.call("mvuld_colsum", _lib._Raw(dqkv), 1, 3 * C, gv(A + "q_bias"), M, C)
+            _lib.call("mvuld_colsum", _lib._Raw(dqkv[:, 2 * C:]), 1, 3 * C, gv(A + "v_bias"), M, C)
+            _lib.gemm(dqkv, self.wt[A + "qkv.weight"], res=dx, out_f32=dx)                  # dx0 = dx1 + dqkv W_qkv
+            del dqkv, datt
+            ctx["blocks"][bi] = None                                                         # release the saved activations
+            ready(*[n for n in self.names if n.startswith(P)])
+        # ---- PatchEmbed: LayerNorm(conv 4x4 / 4) ----
+        E = m.embed_dim
+        Hp, Wp = m.patches_resolution
+        M = B * Hp * Wp
+        dy = ln_bwd(ctx["pe"]["y"], "patch_embed.norm.weight", "patch_embed.norm.bias", dx, M, E, m.patch_embed.norm.eps, 0)
+        self._grad_w(dy, ctx["pe"]["a0"], "patch_embed.proj.weight", (E, 48))
+        _lib.call("mvuld_colsum", dy, 1, E, gv("patch_embed.proj.bias"), M, E)
+        ready(*[n for n in self.names if n.startswith("patch_embed.")])
+        if on_bucket is not None:
+            while bucket_i < len(self.buckets):
+                on_bucket(self.buckets[bucket_i])
+                bucket_i += 1
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_backward(self, x: torch.Tensor, targets: torch.Tensor, on_bucket=None):
+        """main.py:262-276: logits = head(forward_features(x)), mean cross-entropy, backward.  Returns (loss [1], logits)."""
+        if not self.has_head:
+            raise RuntimeError("SwinTrainer.forward_backward needs a classification head (num_classes > 0)")
+        feat, ctx = self.forward_train(x)
+        B, Cf = feat.shape
+        ncls = self.shapes["head.weight"][0]
+        logits = torch.empty(B, ncls, device=self.dev, dtype=torch.float32)
+        _lib.call("mvuld_linear_small", feat, self._view(self.flat_p, "head.weight"), self._view(self.flat_p, "head.bias"),
+                  logits, None, B, ncls, Cf)
+        dlogits = torch.empty_like(logits)
+        self.loss_buf.zero_()
+        _lib.call("mvuld_ce_loss", logits, targets.to(torch.int64).contiguous(), self.loss_buf, dlogits, B, ncls,
+                  1.0 / (B * self.world))
+        self.flat_g.zero_()
+        dfeat = torch.empty_like(feat)
+        _lib.call("mvuld_linear_small_bwd", feat, self._view(self.flat_p, "head.weight"), dlogits, dfeat,
+                  self._view(self.flat_g, "head.weight"), self._view(self.flat_g, "head.bias"), B, ncls, Cf)
+        self.backward_train(ctx, dfeat, on_bucket)
+        return self.loss_buf, logits
+
+    @torch.no_grad()
+    def step(self, x: torch.Tensor, targets: torch.Tensor, lr: Optional[float] = None):
+        """One optimiser step of main.py:251-300 (clip_grad_norm_ + AdamW; bucketed gradient all-reduce when data
+        parallel).  Returns (loss [1] fp32 device tensor of this rank, logits)."""
+        self.step_count += 1
+        works = []
+        if self.world > 1:
+            import torch.distributed as dist
+            on_bucket = lambda b: works.append(dist.all_reduce(self.flat_g[b[0]:b[1]], op=dist.ReduceOp.SUM,
+                                                               group=self.group, async_op=True))
+        else:
+            on_bucket = None
+        try:
+            loss, logits = self.forward_backward(x, targets, on_bucket)
+        except Exception:
+            self.step_count -= 1
+            raise
+        for w in works:
+            w.wait()
+        self.apply_update(lr, advance=False)
+        return (loss * self.world if self.world > 1 else loss), logits
+
+    @torch.no_grad()
+    def apply_update(self, lr: Optional[float] = None, advance: bool = True):
+        if advance:
+            self.step_count += 1
+        self.gnorm_sq.zero_()
+        _lib.call("mvuld_sumsq_f32", self.flat_g, self.total, self.gnorm_partials, self.gnorm_sq)
+        _lib.call("mvuld_adamw", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.total, self.seg_end,
+                  self.seg_wd, int(self.seg_end.numel()), self.gnorm_sq, self.clip, float(self.lr if lr is None else lr),
+                  float(self.betas[0]), float(self.betas[1]), self.eps, self.step_count)
+        self._refresh()
+
+    def grad_norm(self) -> torch.Tensor:
+        return self.gnorm_sq.sqrt()
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        return {n: self._view(self.flat_g, n) for n in self.names}

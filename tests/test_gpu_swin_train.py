@@ -115,3 +115,112 @@ def test_window_attention_backward_matches_autograd(Hres, ws, shift, nH, B, fixe
     for name, e in errs.items():
         record_parity(f"swin_attention_bwd[H{Hres} ws{ws} shift{shift} fixed{fixed}] {name} rel-L2", e, 1e-2)
     assert max(errs.values()) < 1e-2, errs
+
+
+# --------------------------------------------------------------------------------------------------------
+# the whole encoder: forward_train + backward_train against the backward oracle (fp32 autograd through the restated
+# forward, pinned to autograd through the UNMODIFIED reference module by tests/golden/swin_train.pt)
+# --------------------------------------------------------------------------------------------------------
+def _encoder_case(name, B, seed_x, cot=None):
+    import os
+    from mvuld_b200 import swin_train, synth
+    from tests import cases
+    model = cases.make_swin(name)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    geo = cases.swin_geometry(name)
+    x = synth.images(B, cases.SWIN_CASES[name]["img_size"], seed=seed_x)
+    tr = swin_train.SwinTrainer(model.to(DEV), world_size=1)
+    feat, ctx = tr.forward_train(x.to(DEV))
+    if cot is None:
+        cot = torch.randn(feat.shape, generator=gen(seed_x + 1))
+    tr.flat_g.zero_()
+    tr.backward_train(ctx, cot.to(DEV))
+    torch.cuda.synchronize()
+    feats_ref, gref, _ = oswin.features_and_grads(sd, geo, x, cot)
+    grads = {k: v.detach().cpu().clone() for k, v in tr.named_grads().items()}
+    return tr, feat.cpu(), feats_ref, grads, gref
+
+
+def _check_grads(tag, grads, gref, worst_tol, flat_tol, floor=1e-3):
+    """Flat relative L2 error over all parameters, and per tensor |g - ref| <= worst_tol * max(|ref|, floor * |ref_flat|).
+    The floor matters for a handful of tiny gradients that are sums with near-total cancellation (logit_scale, q_bias and
+    the cpb_mlp of late stages, whose keys / queries are almost collinear on these synthetic weights: |ref| ~ 1e-1 next
+    to a flat norm of 5e3): bf16 G / k^ operands leave an ABSOLUTE error of ~4e-2 there, i.e. 1e-5 of the gradient."""
+    names = [n for n in gref if n in grads]
+    assert set(n for n in grads if not n.startswith("head.")) == set(names), "every trained parameter needs a reference gradient"
+    a = torch.cat([grads[n].reshape(-1).float() for n in names])
+    b = torch.cat([gref[n].reshape(-1).float() for n in names])
+    flat, flat_norm = rel_err(a, b), float(b.norm())
+    errs = {}
+    for n in names:
+        ref = gref[n].float()
+        errs[n] = float((grads[n].reshape(ref.shape).float() - ref).norm()) / max(float(ref.norm()), floor * flat_norm)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    dense = ("qkv.weight", "proj.weight", "fc1.weight", "fc2.weight", "reduction.weight")       # the GEMM weights
+    big = {n: rel_err(grads[n].reshape(gref[n].shape), gref[n]) for n in names if n.endswith(dense)}
+    worst_big = max(big.items(), key=lambda kv: kv[1])
+    record_parity(f"swin_train[{tag}] flat gradient rel-L2", flat, flat_tol)
+    record_parity(f"swin_train[{tag}] worst tensor, error / max(|ref|, 1e-3 |flat|) ({worst[0][0]})", worst[0][1], worst_tol)
+    record_parity(f"swin_train[{tag}] worst weight matrix rel-L2 ({worst_big[0]})", worst_big[1], worst_tol)
+    assert flat < flat_tol, (flat, worst)
+    assert worst[0][1] < worst_tol, worst
+    assert worst_big[1] < worst_tol, worst_big
+    return errs
+
+
+def test_swin_encoder_backward_matches_reference_autograd_golden():
+    """small_ws7 (three stages, shifted windows, two patch mergings), batch 2, the golden file's image and cotangent:
+    gradients of EVERY parameter vs the oracle, and the oracle's own pin (norm + samples of the reference module's
+    autograd gradients) re-checked on the same run."""
+    import os
+    from tests import cases
+    from tests.conftest import GOLDEN
+    gold = torch.load(os.path.join(GOLDEN, "swin_train.pt"), weights_only=False)
+    tr, feat, feats_ref, grads, gref = _encoder_case("small_ws7", 2, cases.SEED + 21, gold["cotangent"])
+    assert rel_err(feats_ref, gold["features"]) < 1e-5                          # same inputs as the golden run
+    assert rel_err(feat, feats_ref) < 1e-2
+    for k, g in gold["grads"].items():                                          # the oracle against the reference module
+        f = gref[k].reshape(-1)
+        assert abs(float(f.double().norm()) - g["norm"]) <= 1e-3 * max(g["norm"], 1e-6), k
+    errs = _check_grads("small_ws7", grads, gref, worst_tol=5e-2, flat_tol=1e-2)
+    # against the reference module's own numbers: norms of the CUDA gradients
+    flat_norm = math.sqrt(sum(g["norm"] ** 2 for g in gold["grads"].values()))
+    for k, g in gold["grads"].items():                                         # (same floor as _check_grads)
+        tol = 5e-2 * max(g["norm"], 1e-3 * flat_norm)
+        assert abs(float(grads[k].double().norm()) - g["norm"]) <= tol, (k, float(grads[k].norm()), g["norm"])
+        stride = max(1, g["numel"] // 16)
+        mine = grads[k].reshape(-1)[::stride][:16].float()
+        assert float((mine - g["strided"]).norm()) <= 5e-2 * max(float(g["strided"].norm()), 1e-3 * flat_norm / math.sqrt(max(1, g["numel"] / 16))) + 1e-6, k
+
+
+def test_swin_encoder_backward_ws14_matches_oracle():
+    """mid_ws14: 14x14 windows (two key / query tiles per window in the attention backward), shift 7, one merging."""
+    from tests import cases
+    tr, feat, feats_ref, grads, gref = _encoder_case("mid_ws14", 2, cases.SEED + 31)
+    assert rel_err(feat, feats_ref) < 1e-2
+    _check_grads("mid_ws14", grads, gref, worst_tol=5e-2, flat_tol=1e-2)
+
+
+def test_swin_trainer_step_updates_and_is_reproducible():
+    """step(): cross-entropy through the head, clip + AdamW on the flat buffer, bit-identical when repeated."""
+    from mvuld_b200 import swin_train, synth
+    from tests import cases
+    outs = []
+    for _ in range(2):
+        model = cases.make_swin("small_ws7").to(DEV)
+        tr = swin_train.SwinTrainer(model, lr=2e-5, world_size=1)
+        x = synth.images(3, 112, seed=cases.SEED + 41).to(DEV)
+        y = torch.tensor([0, 1, 1], device=DEV)
+        p0 = tr.flat_p.clone()
+        losses = []
+        for _s in range(2):
+            loss, logits = tr.step(x, y)
+            losses.append(float(loss))
+        assert all(math.isfinite(v) for v in losses) and float(tr.grad_norm()) > 0
+        assert not torch.equal(p0, tr.flat_p)
+        outs.append((losses, tr.flat_p.cpu().clone()))
+        # the eval-mode module sees the updated weights
+        f = model.eval()(x)
+        assert torch.isfinite(f).all()
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][0][-1] < outs[0][0][0], outs[0][0]                          # the repeated batch is fitted better
