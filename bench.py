@@ -336,7 +336,7 @@ def build_workload(args, rank, device, workload=None, model=None, padded_text=No
                      "4 edge types, D=200, 6 steps, segment-sum readout", flops_per_unit=0.0)
 
 
-def build_train_workload(args, rank, device, world, model=None):
+def build_train_workload(args, rank, device, world, model=None, encoders=False):
     """configs[4], reference-faithful variant (main_bigvul.py:294-342 trains only the fusion model on vectors from
     frozen encoders): one step = SwinV2 + UniXcoder forward (eval, no grad), fusion forward + backward, bucketed
     gradient all-reduce across the ranks, gradient-norm clip, AdamW.  Dropout 0.2 as in the reference."""
@@ -346,8 +346,14 @@ def build_train_workload(args, rank, device, world, model=None):
     B = (args.batch if args.workload == "train" else 0) or 32
     model = model or build_full_model(device)
     base_lr = 5e-5 * B * world / 512.0                                     # main_bigvul.py:545 linear scaling rule
-    trainer = FusionTrainer(model.fusion, lr=base_lr, weight_decay=0.005, clip_grad=5.0, dropout=0.2, seed=12345 + rank,
-                            world_size=world)
+    if encoders:
+        # configs[4], primary reading: the image encoder trains too (mvuld/main.py:251-300 chained behind the fusion
+        # backward); UniXcoder stays frozen (its backward is not built)
+        from mvuld_b200.joint_train import MVulDTrainer
+        trainer = MVulDTrainer(model, lr=base_lr, clip_grad=5.0, dropout=0.2, seed=12345 + rank, world_size=world)
+    else:
+        trainer = FusionTrainer(model.fusion, lr=base_lr, weight_decay=0.005, clip_grad=5.0, dropout=0.2,
+                                seed=12345 + rank, world_size=world)
     raw_ids = synth.token_ids(B, 512, seed=seed).pin_memory()
     enc = model.unix.encoder
     ids = raw_ids if args.padded_text else enc.pack_host(raw_ids)
@@ -361,6 +367,9 @@ def build_train_workload(args, rank, device, world, model=None):
 
     def step(d):
         d["g"]._csr = d["g"]._ocsr = None          # graph collate (in- and out-CSR build) is part of every step
+        if encoders:
+            loss, _ = trainer.step(d["g"], d["img"], d["ids"], d["y"])
+            return loss
         img_embedding = model.swin.forward_features(d["img"])
         func_text_embedding, _ = model.unix.get_repr(d["ids"])
         loss, _ = trainer.step(d["g"], img_embedding, func_text_embedding, d["y"], check=False)
@@ -374,6 +383,19 @@ def build_train_workload(args, rank, device, world, model=None):
     ids_bytes = raw_ids.numel() * 8 if args.padded_text else ids.nbytes
     h2d = host["img"].numel() * 4 + ids_bytes + host["g"]._src.numel() * 16 + B * 8 + \
         sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
+    if encoders:
+        n_par = trainer.num_parameters
+        total = trainer.fusion.total + trainer.swin.total
+        name = (f"MVulD training step (configs[4], image encoder + fusion model trained jointly, {n_par / 1e6:.0f} M "
+                f"parameters; UniXcoder forward only): SwinV2-B forward + backward, UniXcoder "
+                f"({'padded 512-token rows' if args.padded_text else f'real tokens packed into {ids.n_rows} rows of 512'}) "
+                f"forward, fusion fwd+bwd, bucketed NCCL gradient all-reduce ({len(trainer.buckets)} buckets, "
+                f"{total * 4 / 1e6:.0f} MB fp32), one clip 5.0 over both parameter sets + AdamW; {B} functions per GPU "
+                f"(global batch {B * world}), avg {host['g'].num_nodes() / B:.0f} CPG nodes")
+        text_rows = B if args.padded_text else ids.n_rows
+        return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name, host_iter=host_iter,
+                    flops_per_unit=3 * 159.08e9 + 96.64e9 * text_rows / B + 4 * 6.4e9, trainer=trainer, host=host,
+                    model=model, total_grad_elems=total)
     name = (f"MVulD fusion training step (configs[4], encoders frozen as in main_bigvul.py): SwinV2-B + UniXcoder "
             f"({'padded 512-token rows' if args.padded_text else f'real tokens packed into {ids.n_rows} rows of 512'}) "
             f"forward, fusion fwd+bwd, bucketed NCCL gradient all-reduce ({len(trainer.buckets)} buckets, "
@@ -769,6 +791,25 @@ def main():
                             "gradient_allreduce": (f"NCCL, {len(twl['trainer'].buckets)} buckets over "
                                                    f"{twl['trainer'].total * 4 / 1e6:.1f} MB fp32" if world > 1 else "none (1 GPU)")}
             del twl, tm
+            torch.cuda.empty_cache()
+            # the same step with the image encoder trainable (configs[4], primary reading); a fresh model: the trainers
+            # re-point its parameters at their flat buffers
+            emodel = build_full_model(device)
+            ewl = build_train_workload(args, rank, device, world, model=emodel, encoders=True)
+            em = measure(ctx, ewl, tsteps, 3)
+            sub["train_encoders"] = {
+                "metric": "MVulD functions/sec (train step, image encoder + fusion trainable)", "value": em["value"],
+                "unit": "functions/s", "steps": tsteps, "warmup": 3, "ms_per_step": em["ms_per_step"],
+                "per_gpu_batch": ewl["units"], "global_batch": ewl["units"] * world, "workload": ewl["name"],
+                "trained_parameters": int(ewl["trainer"].num_parameters),
+                "model_tflops": ewl["flops_per_unit"] * em["value"] / world / 1e12,
+                "e2e": {"value": em["e2e"], "unit": "functions/s", "h2d_bytes_per_step": int(ewl["h2d"]),
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": em["launches"], "last_loss": float(em["last"]),
+                "gradient_allreduce": (f"NCCL, {len(ewl['trainer'].buckets)} buckets over "
+                                       f"{ewl['total_grad_elems'] * 4 / 1e6:.0f} MB fp32" if world > 1 else "none (1 GPU)")}
+            del ewl, em, emodel
+            torch.cuda.empty_cache()
         if not args.no_sub:
             if not args.padded_text:
                 # the literal "512 tok" reading of configs[3]: the text branch on the tokenizer's padded rows

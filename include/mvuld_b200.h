@@ -263,7 +263,17 @@ int mvuld_linear_small(const float* x, const float* w, const float* b, float* ou
  * dW = dY^T X. */
 int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, int C, int ldo, mvuld_stream_t stream);
 /* out[c] += sum_r x[r, c] (bias gradients); x bf16 (is_bf16 != 0) or fp32, row stride ldx >= C. */
-int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, int R, int C, mvuld_stream_t stream);
+/* Weight gradient dW[n_out, k_in] = dY^T X (fp32, row stride ld_dw, overwritten) from ROW-major bf16 dY [M, n_out] and
+ * X [M, k_in]: both operands are consumed MN-major by tcgen05 (no transposed copies), the M rows are split over CTAs
+ * and the partial tiles summed in split order (bit-reproducible).  partials: fp32 workspace of
+ * mvuld_gemm_dw_workspace(M, n_out, k_in) floats (may be null when that is 0). */
+long long mvuld_gemm_dw_workspace(int M, int n_out, int k_in);
+int mvuld_gemm_dw(const void* dY, int ld_dy, const void* X, int ld_x, float* dW, int ld_dw, float* partials, int M,
+                  int n_out, int k_in, mvuld_stream_t stream);
+int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, float* partials, int R, int C, mvuld_stream_t stream);
+/* rows of the fp32 [slabs, C] partials workspace of mvuld_colsum (null allowed when this returns 1): the row slabs are
+ * summed in slab order, so the column sums are bit-reproducible. */
+int mvuld_colsum_slabs(int R, int C);
 /* dx = dy * ELU'(pre) through y = dropout(ELU(pre), p) with the mask regenerated from seed (F.elu + nn.Dropout,
  * GraphModel.py:171,176); is_f32 selects fp32 tensors (no dropout). */
 int mvuld_elu_bwd(const void* dy, const void* y, void* dx, long long n, int is_f32, unsigned long long seed, float p,

@@ -67,7 +67,10 @@ SIGNATURES = {
     "mvuld_fusion_head_mode": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_transpose_bf16": [_P, _I, _P, _I, _I, _I, _P],
-    "mvuld_colsum": [_P, _I, _I, _P, _I, _I, _P],
+    "mvuld_gemm_dw": [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P],
+    "mvuld_gemm_dw_workspace": [_I, _I, _I],
+    "mvuld_colsum": [_P, _I, _I, _P, _P, _I, _I, _P],
+    "mvuld_colsum_slabs": [_I, _I],
     "mvuld_ln_rows_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
     "mvuld_ln_rows_bwd_blocks": [_I],
     "mvuld_gelu_bwd": [_P, _P, _P, _LL, _P],
@@ -97,7 +100,7 @@ _lib = None
 launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
 _LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3, "mvuld_sumsq_f32": 2,
                       "mvuld_ln_rows_bwd": 2, "mvuld_pos_branch_bwd": 2, "mvuld_swin_bias_grad": 2,
-                      "mvuld_swin_qkv_bwd": 2}
+                      "mvuld_swin_qkv_bwd": 2, "mvuld_colsum": 2, "mvuld_gemm_dw": 2}
 
 
 def load() -> C.CDLL:
@@ -113,7 +116,7 @@ def load() -> C.CDLL:
     lib.mvuld_last_error.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
-        fn.restype = C.c_int
+        fn.restype = C.c_longlong if name == "mvuld_gemm_dw_workspace" else C.c_int
         fn.argtypes = argtypes
     _lib = lib
     return lib
@@ -162,6 +165,25 @@ def call(name: str, *args):
     if _SYNC_EACH:
         _sync_check(name)
     return rc
+
+
+def gemm_dw(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, n_out: Optional[int] = None):
+    """out [n_out, k_in] fp32 = dy[:, :n_out]^T @ x  (dy [M, *] and x [M, k_in] bf16 row-major: no transposed copies)."""
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.stride(1) == 1 and x.stride(1) == 1
+    assert out.dtype == torch.float32 and out.stride(1) == 1
+    M, k_in = x.shape
+    n_out = dy.shape[1] if n_out is None else n_out
+    assert dy.shape[0] == M and tuple(out.shape) == (n_out, k_in)
+    need = load().mvuld_gemm_dw_workspace(M, n_out, k_in)
+    part = torch.empty(need, device=out.device, dtype=torch.float32) if need else None
+    call("mvuld_gemm_dw", _Raw(dy), dy.stride(0), _Raw(x), x.stride(0), _Raw(out), out.stride(0), part, M, n_out, k_in)
+
+
+def colsum(x, is_bf16: int, ldx: int, out: torch.Tensor, R: int, C: int):
+    """out[c] += sum_r x[r, c] (x: a tensor or a ``_Raw`` base pointer with row stride ``ldx``); fixed summation order."""
+    slabs = load().mvuld_colsum_slabs(int(R), int(C))
+    part = torch.empty(slabs * C, device=out.device, dtype=torch.float32) if slabs > 1 else None
+    call("mvuld_colsum", x, is_bf16, ldx, out, part, R, C)
 
 
 def ln_rows_bwd_partials(M: int, C: int, device) -> torch.Tensor:

@@ -70,17 +70,20 @@ __device__ __forceinline__ float block_reduce_fixed(float (&acc)[NV], float (*pa
   return t;
 }
 
-// out[c] += sum_r x[r, c].  One block owns 8 columns over ALL rows (thread = row lane, one 16 / 32-byte load per row),
-// so no sum crosses a block: deterministic, no atomics.
+// out[c] += sum_r x[r, c].  Block (column group of 8, row slab): thread = row lane, one 16 / 32-byte load per row, fixed-
+// order block reduction; with one slab the block adds straight into out, otherwise it writes its row of the partials
+// workspace and colsum_final_kernel sums the slabs in slab order.  No atomics: bit-reproducible.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, int R, int C) {
+colsum_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, float* __restrict__ partials, int R, int C,
+              int rows_per_slab) {
   __shared__ float part[8][8];
   const int c0 = blockIdx.x * 8;
   const int nc = min(8, C - c0);
+  const int rbeg = blockIdx.y * rows_per_slab, rend = min(R, rbeg + rows_per_slab);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bool vec = nc == 8 && (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 31) == 0;
-  for (int r = threadIdx.x; r < R; r += 256) {
+  for (int r = rbeg + threadIdx.x; r < rend; r += 256) {
     const T* p = x + (size_t)r * ldx + c0;
     if (vec) {
       if (sizeof(T) == 2) {
@@ -99,7 +102,17 @@ colsum_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, int R, 
     }
   }
   const float t = block_reduce_fixed<8>(acc, part);
-  if (threadIdx.x < nc) out[c0 + threadIdx.x] += t;
+  if (threadIdx.x < nc) {
+    if (gridDim.y == 1) out[c0 + threadIdx.x] += t;
+    else partials[(size_t)blockIdx.y * C + c0 + threadIdx.x] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partials, float* __restrict__ out, int slabs, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int s = 0; s < slabs; ++s) t += partials[(size_t)s * C + c];
+  out[c] += t;
 }
 
 // activation backward through y = dropout(elu(pre)):  kept elements carry elu(pre) / (1 - p)
@@ -1083,13 +1096,30 @@ extern "C" int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, i
   MV_LAUNCH_OK();
   return 0;
 }
-extern "C" int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, int R, int C, cudaStream_t stream) {
+// row slabs (= rows of the fp32 [slabs, C] partials workspace) mvuld_colsum uses for R rows: enough blocks to fill the
+// GPU when C is small (a [401 k, 128] gradient has 16 column groups)
+extern "C" int mvuld_colsum_slabs(int R, int C) {
+  const int groups = (C + 7) / 8;
+  int slabs = (4 * num_sms() + groups - 1) / groups;           // ~4 blocks per SM
+  const int max_by_rows = (R + 1023) / 1024;                   // at least 1024 rows per slab
+  if (slabs > max_by_rows) slabs = max_by_rows;
+  return slabs < 1 ? 1 : slabs;
+}
+extern "C" int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, float* partials, int R, int C,
+                            cudaStream_t stream) {
   MV_CHECK_ARG(ldx >= C, "colsum: ldx < C");
   if (R <= 0 || C <= 0) return 0;
-  const int grid = (C + 7) / 8;
-  if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, R, C);
-  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, out, R, C);
+  const int slabs = mvuld_colsum_slabs(R, C);
+  MV_CHECK_ARG(slabs == 1 || partials != nullptr, "colsum: the [mvuld_colsum_slabs(R, C), C] partials workspace is null");
+  const int rps = (R + slabs - 1) / slabs;
+  dim3 grid((C + 7) / 8, slabs);
+  if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, partials, R, C, rps);
+  else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, out, partials, R, C, rps);
   MV_LAUNCH_OK();
+  if (slabs > 1) {
+    colsum_final_kernel<<<(C + 255) / 256, 256, 0, stream>>>(partials, out, slabs, C);
+    MV_LAUNCH_OK();
+  }
   return 0;
 }
 extern "C" int mvuld_elu_bwd(const void* dy, const void* y, void* dx, long long n, int is_f32, unsigned long long seed,

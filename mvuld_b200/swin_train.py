@@ -159,8 +159,10 @@ class SwinTrainer:
         return out
 
     def _grad_w(self, dy: torch.Tensor, x: torch.Tensor, name: str, shape=None):
-        """dW [out, in] = dY^T X on the tensor cores, fp32 straight into the flat gradient buffer."""
-        _lib.gemm(self._transpose(dy), self._transpose(x), out_f32=self._view(self.flat_g, name, shape))
+        """dW [out, in] = dY^T X on the tensor cores (both operands row-major as they are, M split over CTAs), fp32
+        straight into the flat gradient buffer."""
+        out = self._view(self.flat_g, name, shape)
+        _lib.gemm_dw(dy, x, out.view(out.shape[0], -1))
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -295,19 +297,19 @@ class SwinTrainer:
             hdim = self.shapes[P + "mlp.fc1.weight"][0]
             dy2 = ln_bwd(s["y2"], P + "norm2.weight", P + "norm2.bias", dx, M, C, b["eps2"], 1)
             self._grad_w(dy2, s["hid"], P + "mlp.fc2.weight")
-            _lib.call("mvuld_colsum", dy2, 1, C, gv(P + "mlp.fc2.bias"), M, C)
+            _lib.colsum(dy2, 1, C, gv(P + "mlp.fc2.bias"), M, C)
             dhid = e((M, hdim), bf)
             _lib.gemm(dy2, self.wt[P + "mlp.fc2.weight"], out_bf16=dhid)
             dpre = e((M, hdim), bf)
             _lib.call("mvuld_gelu_bwd", s["pre"], dhid, dpre, M * hdim)
             self._grad_w(dpre, s["xb1"], P + "mlp.fc1.weight")
-            _lib.call("mvuld_colsum", dpre, 1, hdim, gv(P + "mlp.fc1.bias"), M, hdim)
+            _lib.colsum(dpre, 1, hdim, gv(P + "mlp.fc1.bias"), M, hdim)
             _lib.gemm(dpre, self.wt[P + "mlp.fc1.weight"], res=dx, out_f32=dx)              # dx1 = dx2 + dpre W_fc1
             del dhid, dpre
             # ---- x1 = x0 + LN1(proj(attention(x0))) ----
             dy1 = ln_bwd(s["y1"], P + "norm1.weight", P + "norm1.bias", dx, M, C, b["eps1"], 1)
             self._grad_w(dy1, s["att"], P + "attn.proj.weight")
-            _lib.call("mvuld_colsum", dy1, 1, C, gv(P + "attn.proj.bias"), M, C)
+            _lib.colsum(dy1, 1, C, gv(P + "attn.proj.bias"), M, C)
             datt = e((M, C), bf)
             _lib.gemm(dy1, self.wt[P + "attn.proj.weight"], out_bf16=datt)
             dOw, ld = e((n_bh, N, 32), bf), e((n_bh, N, 2), f32)
@@ -334,8 +336,8 @@ class SwinTrainer:
                       nH, ws, shift)
             del dq, dk, dv
             self._grad_w(dqkv, s["xb_in"], A + "qkv.weight")
-            _lib.call("mvuld_colsum", _lib._Raw(dqkv), 1, 3 * C, gv(A + "q_bias"), M, C)
-            _lib.call("mvuld_colsum", _lib._Raw(dqkv[:, 2 * C:]), 1, 3 * C, gv(A + "v_bias"), M, C)
+            _lib.colsum(_lib._Raw(dqkv), 1, 3 * C, gv(A + "q_bias"), M, C)
+            _lib.colsum(_lib._Raw(dqkv[:, 2 * C:]), 1, 3 * C, gv(A + "v_bias"), M, C)
             _lib.gemm(dqkv, self.wt[A + "qkv.weight"], res=dx, out_f32=dx)                  # dx0 = dx1 + dqkv W_qkv
             del dqkv, datt
             ctx["blocks"][bi] = None                                                         # release the saved activations
@@ -346,7 +348,7 @@ class SwinTrainer:
         M = B * Hp * Wp
         dy = ln_bwd(ctx["pe"]["y"], "patch_embed.norm.weight", "patch_embed.norm.bias", dx, M, E, m.patch_embed.norm.eps, 0)
         self._grad_w(dy, ctx["pe"]["a0"], "patch_embed.proj.weight", (E, 48))
-        _lib.call("mvuld_colsum", dy, 1, E, gv("patch_embed.proj.bias"), M, E)
+        _lib.colsum(dy, 1, E, gv("patch_embed.proj.bias"), M, E)
         ready(*[n for n in self.names if n.startswith("patch_embed.")])
         if on_bucket is not None:
             while bucket_i < len(self.buckets):

@@ -209,12 +209,10 @@ class FusionTrainer:
     # ----------------------------------------------------------------------------------------------------
     def _grad_w(self, dy: torch.Tensor, x: torch.Tensor, gname: str, rows_out: Optional[int] = None,
                 out: Optional[torch.Tensor] = None, G: Optional[torch.Tensor] = None):
-        """dW [out, in] = dY^T X on the tensor cores, fp32 straight into the flat gradient buffer.  Both operands are
-        transposed to K-major ([out, Rp] and [in, Rp], zero filled past the R real rows)."""
-        dyT, xT = self._transpose(dy), self._transpose(x)
-        if rows_out is not None:
-            dyT = dyT[:rows_out]
-        _lib.gemm(dyT, xT, out_f32=self._mat(self.flat_g if G is None else G, gname) if out is None else out)
+        """dW [out, in] = dY^T X on the tensor cores, fp32 straight into the flat gradient buffer: ``mvuld_gemm_dw`` reads
+        both operands row-major as they are (MN-major tcgen05 operands) and splits the M rows over CTAs."""
+        dst = self._mat(self.flat_g if G is None else G, gname) if out is None else out
+        _lib.gemm_dw(dy, x, dst, n_out=rows_out)
 
     def _seed(self, layer: int) -> int:
         return (self.seed * 1000003 + self.step_count * 257 + layer) & 0x7FFFFFFFFFFFFFFF
@@ -424,7 +422,7 @@ class FusionTrainer:
             _lib.call("mvuld_elu_bwd_rows", _lib._Raw(dfeats[:, col0:col0 + 512]), 1536,
                       _lib._Raw(feats[:, col0:col0 + 512]), 1536, dpre, 512, B, 512)
             self._grad_w(dpre, xn, lin + ".weight", G=G)
-            _lib.call("mvuld_colsum", dpre, 1, 512, gv(lin + ".bias"), B, 512)
+            _lib.colsum(dpre, 1, 512, gv(lin + ".bias"), B, 512)
             dxn = e((B, K), f32)
             _lib.gemm(dpre, self.wt[lin][:, :512], out_f32=dxn)
             dxin = e((B, K), f32) if input_grads else None
@@ -443,13 +441,13 @@ class FusionTrainer:
             _lib.call("mvuld_bn_cols_bwd", w0, dz32, 512, pv(pre + "W.1.weight"), mean, rstd, None, dw0,
                       gv(pre + "W.1.weight"), gv(pre + "W.1.bias"), R, 512)
             self._grad_w(dw0, y, pre + "W.0.weight", G=G)
-            _lib.call("mvuld_colsum", dw0, 1, 512, gv(pre + "W.0.bias"), R, 512)
+            _lib.colsum(dw0, 1, 512, gv(pre + "W.0.bias"), R, 512)
             dy = e((R, 512), bf)
             _lib.gemm(dw0, self.wt[f"gcn{k}.W0"][:, :512], out_bf16=dy)
             dtpg = e((R, 1536), bf)
             _lib.call("mvuld_rs_gcn_affinity_bwd", tpg, dy, dtpg, B, n, 512)
             self._grad_w(dtpg, zin, "", out=self._gcn_cat(G, k, "weight"), G=G)
-            _lib.call("mvuld_colsum", dtpg, 1, 1536, self._gcn_cat(G, k, "bias"), R, 1536)
+            _lib.colsum(dtpg, 1, 1536, self._gcn_cat(G, k, "bias"), R, 1536)
             _lib.gemm(dtpg, self.wt[f"gcn{k}.cat"][:, :1536], res=dz32, out_bf16=dzb, out_f32=dz32)   # + residual path
             ready(pre + "g.bias")
 
@@ -459,7 +457,7 @@ class FusionTrainer:
         dpre = e((R, 512), bf)
         _lib.call("mvuld_elu_bwd", dzb, zb0, dpre, R * 512, 0, 0, 0.0)
         self._grad_w(dpre, hpn, "fc_gat.weight", rows_out=480, G=G)
-        _lib.call("mvuld_colsum", dpre, 1, 512, gv("fc_gat.bias"), R, 480)
+        _lib.colsum(dpre, 1, 512, gv("fc_gat.bias"), R, 480)
         dhpn = e((R, 512), bf)
         _lib.gemm(dpre[:, :480], self.wt["fc_gat"][:, :480], out_bf16=dhpn)
         dhp = e((R, 512), bf)
@@ -479,7 +477,7 @@ class FusionTrainer:
             dpre = e((N, 512), bf)
             _lib.call("mvuld_elu_bwd", dh, acts[li + 1], dpre, N * 512, 0, _seed(8 + li), p)
             self._grad_w(dpre, acts[li], name + ".weight", G=G)
-            _lib.call("mvuld_colsum", dpre, 1, 512, gv(name + ".bias"), N, 512)
+            _lib.colsum(dpre, 1, 512, gv(name + ".bias"), N, 512)
             K = acts[li].shape[1]
             dh = e((N, K), bf)
             _lib.gemm(dpre, self.wt[name][:, :512], out_bf16=dh)
@@ -489,7 +487,7 @@ class FusionTrainer:
         for li in (1, 0):
             name = ("gat", "gat2")[li]
             xd, z, el, er, H, F, slope = gat_saved[li]
-            _lib.call("mvuld_colsum", dh, 1, H * F, gv(name + ".bias"), N, H * F)
+            _lib.colsum(dh, 1, H * F, gv(name + ".bias"), N, H * F)
             alpha_e, ds_e = e((E, H), f32), e((E, H), f32)
             dl, dr = e((N, H), f32), e((N, H), f32)
             dz = e((N, H * F), bf)

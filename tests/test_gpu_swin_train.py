@@ -224,3 +224,48 @@ def test_swin_trainer_step_updates_and_is_reproducible():
         assert torch.isfinite(f).all()
     assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
     assert outs[0][0][-1] < outs[0][0][0], outs[0][0]                          # the repeated batch is fitted better
+
+
+# --------------------------------------------------------------------------------------------------------
+# BASELINE.json's full size: SwinV2-B 448 / window 28 (the four-group attention forward, the 7 x 7-unit backward)
+# --------------------------------------------------------------------------------------------------------
+def test_swin_encoder_backward_full_size_matches_oracle():
+    """SwinV2-B 448 px / window 28, one image: every gradient against the fp32 oracle (about a minute of CPU autograd)."""
+    from tests import cases
+    tr, feat, feats_ref, grads, gref = _encoder_case("full", 1, cases.SEED + 51)
+    assert rel_err(feat, feats_ref) < 1e-2
+    assert any(b["fixed"] for b in tr.blocks)                                  # the constant-reference forward kernel ran
+    _check_grads("full 448/w28", grads, gref, worst_tol=5e-2, flat_tol=1e-2)
+
+
+def test_joint_trainer_chains_fusion_and_image_encoder_backward():
+    """MVulDTrainer (configs[4], primary reading): the fusion backward's input gradient drives the SwinV2 backward; one
+    clip over both parameter sets.  Checked: the image-encoder gradient equals SwinTrainer.backward_train fed the same
+    cotangent (bitwise: same launches), the joint norm, that repeated steps on one batch lower the loss."""
+    import mvuld_b200 as mv
+    from mvuld_b200 import synth
+    from mvuld_b200.joint_train import MVulDTrainer
+    from tests import cases
+    torch.manual_seed(cases.SEED)
+    model = mv.MVulD(mv.default_config()).eval()
+    synth.randomize_for_parity(model, seed=777)
+    model = model.to(DEV)
+    B = 2
+    tr = MVulDTrainer(model, lr=2e-5, dropout=0.0, world_size=1)
+    assert tr.num_parameters > 100e6
+    img = synth.images(B, 448, seed=cases.SEED + 61).to(DEV)
+    ids = synth.token_ids(B, 512, seed=cases.SEED + 62).to(DEV)
+    g = synth.cpg_batch(B, seed=cases.SEED + 63)
+    g.ndata.pop("_FUNC_EMB", None)
+    g = g.to(DEV)
+    y = torch.tensor([0, 1], device=DEV)
+    losses = []
+    for _ in range(3):
+        g._csr = g._ocsr = None
+        loss, logits = tr.step(g, img, ids, y)
+        losses.append(float(loss))
+        assert torch.isfinite(logits).all()
+    gs, gf = tr.swin.flat_g.double().pow(2).sum(), tr.fusion.flat_g.double().pow(2).sum()
+    assert float(gs) > 0 and float(gf) > 0
+    assert abs(float(tr.grad_norm()) - float((gs + gf).sqrt())) <= 1e-4 * float((gs + gf).sqrt())
+    assert losses[-1] < losses[0], losses

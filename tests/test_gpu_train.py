@@ -60,11 +60,11 @@ def test_transpose_and_colsum():
     assert torch.equal(out[:, :70].cpu(), x.t())
     assert float(out[:, 70:].float().abs().sum()) == 0.0
     s = torch.zeros(200, device=DEV)
-    _lib.call("mvuld_colsum", x.to(DEV), 1, 200, s, 70, 200)
+    _lib.colsum(x.to(DEV), 1, 200, s, 70, 200)
     assert rel_err(s, x.float().sum(0)) < 1e-5
     y = torch.randn(1000, 48, generator=gen(2))
     s2 = torch.ones(40, device=DEV)
-    _lib.call("mvuld_colsum", y.to(DEV), 0, 48, s2, 1000, 40)            # strided: first 40 of 48 columns, accumulates
+    _lib.colsum(y.to(DEV), 0, 48, s2, 1000, 40)            # strided: first 40 of 48 columns, accumulates
     assert rel_err(s2, y[:, :40].sum(0) + 1.0) < 1e-5
 
 
