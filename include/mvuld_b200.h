@@ -134,6 +134,20 @@ int mvuld_patch_im2col(const float* img, void* out, int B, int Hi, int Wi, mvuld
  * out bf16 [B*L, nH*64].  unixcoder.py:35-36. */
 int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out, int B, int L,
                         int nH, int hd, mvuld_stream_t stream);
+/* Training forward of mvuld_seq_attention: also writes lse (log2-domain log-sum-exp of every row, fp32 [B*nH, L]). */
+int mvuld_seq_attention_train(const void* q, const void* k, const void* v, const int* kv_len, void* out, float* lse,
+                              int B, int L, int nH, int hd, mvuld_stream_t stream);
+/* Backward of the RoBERTa self-attention (HF RobertaSelfAttention under autograd, unixcoder.py:33-38): prep gathers dO
+ * (bf16 token-major [B*L, nH*64]) head-major and packs ld = (lse, rowsum(dO o O)); bwd writes fp32 [B*nH, L, 64]
+ * dq = G k, dk = G^T q_stored, dv = P^T dO (G = dL / d natural logits; rows / key tiles past kv_len are skipped: the
+ * caller zero-fills); qkv_bwd turns them into d(x Wqkv^T + b), bf16 token-major [B*L, 3*nH*64] (q | k | v). */
+int mvuld_seq_attention_bwd_prep(const void* dO, const void* O, const float* lse, void* dOh, void* ld, int B, int L,
+                                 int nH, mvuld_stream_t stream);
+int mvuld_seq_attention_bwd(const void* q, const void* k, const void* v, const void* dOh, const void* ld,
+                            const int* kv_len, float* dq, float* dk, float* dv, int B, int L, int nH, int hd,
+                            mvuld_stream_t stream);
+int mvuld_seq_qkv_bwd(const float* dq, const float* dk, const float* dv, void* dqkv, int B, int L, int nH, int hd,
+                      mvuld_stream_t stream);
 /* Packed variant (several short sequences per row, block-diagonal attention): token (b, i) attends to keys
  * [seg_lo[b*L + i], seg_hi[b*L + i]) of row b; padding tokens carry their own position (lo = i, hi = i + 1) so that
  * they stay finite.  kv_len[b] = tokens in use in row b.  This is what makes the per-node line encoding of
@@ -155,6 +169,17 @@ int mvuld_seq_segment_mean(const float* tok, const int* seg_start, const int* se
  * 2: x = LN(y + shortcut) (RoBERTa).  y bf16 [M,C]; shortcut fp32; outputs fp32 x32 and/or bf16 xb. */
 int mvuld_ln_rows(const void* y, const float* shortcut, const float* gamma, const float* beta, float* x32, void* xb,
                   int M, int C, float eps, int mode, mvuld_stream_t stream);
+/* Training variant of mvuld_roberta_embed: also keeps ysum = word + position + type rows (bf16 [M, C], the LayerNorm
+ * input).  Backward: mvuld_ln_rows_bwd (mode 0) on ysum, then mvuld_embed_grad_rows per table. */
+int mvuld_roberta_embed_train(const long long* ids, const int* pos, const float* word, const float* posemb,
+                              const float* type0, const float* gamma, const float* beta, float* x32, void* xb, void* ysum,
+                              int M, int C, float eps, mvuld_stream_t stream);
+/* Backward of the masked mean (unixcoder.py:37): dtok[b, t] = dsent[b] / len[b] for t < len[b], else 0. */
+int mvuld_masked_mean_bwd(const float* dsent, const int* len, float* dtok, int B, int L, int C, mvuld_stream_t stream);
+/* nn.Embedding backward: dtab[v] += sum of the rows d[rows[k]], k in [indptr[v], indptr[v+1]) (rows grouped by index
+ * with mvuld_csr_from_coo, token order kept: fixed summation order); index skip_index (padding_idx) gets nothing. */
+int mvuld_embed_grad_rows(const float* d, const int* indptr, const int* rows, float* dtab, int n_index, int C,
+                          int skip_index, mvuld_stream_t stream);
 /* PatchEmbed: Conv2d(3,E,4,4) + LayerNorm, img fp32 NCHW -> x32 / xb [B*(H/4)*(W/4), E]. swin_transformer_v2.py:485-493 */
 int mvuld_patch_embed(const float* img, const float* w, const float* bias, const float* gamma, const float* beta,
                       float* x32, void* xb, int B, int Himg, int Wimg, int E, float eps, mvuld_stream_t stream);

@@ -29,6 +29,13 @@ SIGNATURES = {
     "mvuld_swin_window_attention_train": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_swin_attention_bwd_prep": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_swin_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "mvuld_seq_attention_train": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_seq_attention_bwd_prep": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_seq_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_seq_qkv_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_roberta_embed_train": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "mvuld_masked_mean_bwd": [_P, _P, _P, _I, _I, _I, _P],
+    "mvuld_embed_grad_rows": [_P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_swin_bias_grad": [_P, _I, _I, _I, _I, _P, _P, _P],
     "mvuld_cpb_mlp_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "mvuld_swin_qkv_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

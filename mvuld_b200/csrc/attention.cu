@@ -1340,8 +1340,8 @@ extern "C" int mvuld_swin_window_attention_fixed(const void* q, const void* k, c
 }
 
 static int seq_attention(const void* q, const void* k, const void* v, const int* kv_len, const int* seg_lo,
-                         const int* seg_hi, const int* tile_lo, const int* tile_hi, void* out, int B, int L, int nH,
-                         int hd, cudaStream_t stream) {
+                         const int* seg_hi, const int* tile_lo, const int* tile_hi, void* out, float* lse, int B, int L,
+                         int nH, int hd, cudaStream_t stream) {
   MV_CHECK_ARG(hd == 64, "seq attention: head_dim 64 only");
   MV_CHECK_ARG(L <= 512 && L % 8 == 0, "seq attention: L must be <= 512 and a multiple of 8");
   AttnParams p{};
@@ -1354,16 +1354,24 @@ static int seq_attention(const void* q, const void* k, const void* v, const int*
   p.tile_lo = tile_lo;
   p.tile_hi = tile_hi;
   p.out = out;
+  p.lse = lse;
   return launch_attn<MODE_SEQ, 64, 1, 128, false>(q, k, v, B * nH, p, stream);
 }
 extern "C" int mvuld_seq_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out, int B,
                                    int L, int nH, int hd, cudaStream_t stream) {
-  return seq_attention(q, k, v, kv_len, nullptr, nullptr, nullptr, nullptr, out, B, L, nH, hd, stream);
+  return seq_attention(q, k, v, kv_len, nullptr, nullptr, nullptr, nullptr, out, nullptr, B, L, nH, hd, stream);
+}
+// training forward: also writes the log2-domain log-sum-exp of every score row (fp32 [B * nH, L]) for
+// mvuld_seq_attention_bwd
+extern "C" int mvuld_seq_attention_train(const void* q, const void* k, const void* v, const int* kv_len, void* out,
+                                         float* lse, int B, int L, int nH, int hd, cudaStream_t stream) {
+  MV_CHECK_ARG(lse != nullptr, "seq attention (train): lse is null");
+  return seq_attention(q, k, v, kv_len, nullptr, nullptr, nullptr, nullptr, out, lse, B, L, nH, hd, stream);
 }
 extern "C" int mvuld_seq_attention_packed(const void* q, const void* k, const void* v, const int* kv_len,
                                           const int* seg_lo, const int* seg_hi, const int* tile_lo, const int* tile_hi,
                                           void* out, int B, int L, int nH, int hd, cudaStream_t stream) {
   MV_CHECK_ARG(seg_lo && seg_hi, "packed seq attention: segment bounds are null");
   MV_CHECK_ARG((tile_lo == nullptr) == (tile_hi == nullptr), "packed seq attention: give both tile bounds or neither");
-  return seq_attention(q, k, v, kv_len, seg_lo, seg_hi, tile_lo, tile_hi, out, B, L, nH, hd, stream);
+  return seq_attention(q, k, v, kv_len, seg_lo, seg_hi, tile_lo, tile_hi, out, nullptr, B, L, nH, hd, stream);
 }

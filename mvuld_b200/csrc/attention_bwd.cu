@@ -459,3 +459,358 @@ extern "C" int mvuld_swin_attention_bwd(const void* qh, const void* qb, const vo
     default: return mv::fail(-1, "attention_bwd: window %d not instantiated (7, 14, 28)", ws);
   }
 }
+
+// =========================================================================================================
+// Backward of the RoBERTa self-attention of the text encoder (HF RobertaSelfAttention under autograd, as fine-tuned
+// through mvuld/models/unixcoder.py:33-54): head dim 64, sequences of up to 512 tokens, keys past kv_len masked.
+// Same structure as attn_bwd_kernel (transposed score tiles, P^T / G^T as TMEM A operands, G^T once through shared
+// memory for dQ), with 128-query tiles and without a bias table.  dQ of all query tiles does not fit TMEM next to the
+// 64-wide accumulators, so each unit's dQ contribution is added to the fp32 dq rows in global memory by the CTA that
+// owns the (sequence, head) -- sequential over the key tiles, hence still deterministic.
+// q is stored pre-scaled by log2(e) / sqrt(hd) (mvuld_heads_qkv): outputs dq = G k, dk = G^T q_stored, dv = P^T dO with
+// G = dL / d(natural logits).
+// =========================================================================================================
+namespace mv {
+
+constexpr int SB_T = 128;            // keys per tile (TMEM lanes) and queries per tile (TMEM columns)
+constexpr int SB_HD = 64;
+constexpr int SB_TILE = SB_T * SB_HD * 2;        // 16 KB operand tile, 128-byte rows
+struct SeqBwdParams {
+  int nH, L;
+  const int* kv_len;       // [B]
+  const float2* ld;        // [B * nH, L] (LSE log2 units, D)
+  float* dq;               // [B * nH, L, 64] fp32 (zero-filled by the caller: tiles past kv_len are skipped)
+  float* dk;
+  float* dv;
+};
+constexpr int SB_SMEM = 2 * SB_T * 128 /*G: 2 atoms of 64 queries*/ + 2 * SB_TILE /*K, V*/ + 4 * SB_TILE /*Q, dO x2*/ +
+                        4096 /*LD*/ + 256 + 1024;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+seq_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, SeqBwdParams p) {
+  constexpr int COL_ST = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
+  constexpr int NSTEP = SB_T / 16;                   // 8 query steps per tile, 4 per math warpgroup
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sG = smem;
+  uint8_t* sK = sG + 2 * SB_T * 128;
+  uint8_t* sV = sK + SB_TILE;
+  uint8_t* sQ = sV + SB_TILE;                        // [2]
+  uint8_t* sdO = sQ + 2 * SB_TILE;                   // [2]
+  float2* sLD = reinterpret_cast<float2*>(sdO + 2 * SB_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sLD) + 4096);
+  uint64_t* kv_full = bars;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* q_full = bars + 2;       // [2]
+  uint64_t* q_empty = bars + 4;      // [2]
+  uint64_t* sdp_full = bars + 6;
+  uint64_t* pg_full = bars + 7;
+  uint64_t* unit_done = bars + 8;    // the unit's dV / dK / dQ products retired (dQ of the unit is readable)
+  uint64_t* dq_free = bars + 9;      // ... and its dQ tile has been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x;
+  const int b = bh / p.nH;
+  int len = __ldg(p.kv_len + b);
+  len = len < 1 ? 1 : (len > p.L ? p.L : len);
+  const int nt = (len + SB_T - 1) / SB_T;            // key tiles == query tiles that hold valid tokens
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pg_full, 8);
+    mbar_init(unit_done, 1);
+    mbar_init(dq_free, 8);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  {
+    const float2* ldg = p.ld + (size_t)bh * p.L;
+    for (int i = threadIdx.x; i < 512; i += AB_THREADS) sLD[i] = i < p.L ? __ldg(ldg + i) : make_float2(1.0e30f, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int j = 0; j < nt; ++j) {
+        if (j > 0) mbar_wait(kv_empty, (j - 1) & 1, 1);
+        mbar_arrive_expect_tx(kv_full, 2 * SB_TILE);
+        tma_load_3d(sK, &tmK, kv_full, 0, j * SB_T, bh);
+        tma_load_3d(sV, &tmV, kv_full, 0, j * SB_T, bh);
+        for (int i = 0; i < nt; ++i, ++n) {
+          const int st = n & 1;
+          if (n >= 2) mbar_wait(&q_empty[st], ((n >> 1) - 1) & 1, 2);
+          mbar_arrive_expect_tx(&q_full[st], 2 * SB_TILE);
+          tma_load_3d(sQ + st * SB_TILE, &tmQ, &q_full[st], 0, i * SB_T, bh);
+          tma_load_3d(sdO + st * SB_TILE, &tmdO, &q_full[st], 0, i * SB_T, bh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_st = make_idesc_bf16(SB_T, SB_T, 0, 0);
+    constexpr uint32_t idesc_dv = make_idesc_bf16(SB_T, SB_HD, 0, 1);        // A from TMEM, B MN-major
+    constexpr uint32_t idesc_dq = make_idesc_bf16(SB_T, SB_HD, 1, 1);        // A MN-major (shared memory), B MN-major
+    // 128-byte-swizzle tiles with 128-byte rows: K-major = MN-major atom layout, 8-row groups 1 KB apart
+    const uint32_t hi = (uint32_t)(make_smem_desc(0, 16, 1024, 2) >> 32);
+    const uint32_t g_lo = (uint32_t)make_smem_desc(smem_u32(sG), SB_T * 128, 1024, 2);
+    const uint32_t k_lo = (uint32_t)make_smem_desc(smem_u32(sK), 16, 1024, 2);
+    const uint32_t v_lo = (uint32_t)make_smem_desc(smem_u32(sV), 16, 1024, 2);
+    const uint32_t q_lo = (uint32_t)make_smem_desc(smem_u32(sQ), 16, 1024, 2);
+    const uint32_t do_lo = (uint32_t)make_smem_desc(smem_u32(sdO), 16, 1024, 2);
+    const bool leader = elect_one();
+    auto d = [&](uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+    int n = 0;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(kv_full, j & 1, 3);
+      for (int i = 0; i < nt; ++i, ++n) {
+        const int st = n & 1;
+        mbar_wait(&q_full[st], (n >> 1) & 1, 4);
+        tc_fence_after();
+        const uint32_t qoff = (uint32_t)st * (SB_TILE >> 4);
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < SB_HD / 16; ++k)
+            umma_ss(tmem_base + COL_ST, d(k_lo + k * 2), d(q_lo + qoff + k * 2), idesc_st, k != 0);
+#pragma unroll
+          for (int k = 0; k < SB_HD / 16; ++k)
+            umma_ss(tmem_base + COL_DP, d(v_lo + k * 2), d(do_lo + qoff + k * 2), idesc_st, k != 0);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
+        mbar_wait(pg_full, n & 1, 6);
+        if (n > 0) mbar_wait(dq_free, (n - 1) & 1, 7);        // the previous unit's dQ tile has left TMEM
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int s = 0; s < NSTEP; ++s)
+            umma_ts(tmem_base + COL_DV, tmem_base + COL_ST + 16 * s, d(do_lo + qoff + s * (16 * 128 >> 4)), idesc_dv,
+                    (i != 0) || (s != 0));
+#pragma unroll
+          for (int s = 0; s < NSTEP; ++s)
+            umma_ts(tmem_base + COL_DK, tmem_base + COL_DP + 16 * s, d(q_lo + qoff + s * (16 * 128 >> 4)), idesc_dv,
+                    (i != 0) || (s != 0));
+#pragma unroll
+          for (int s = 0; s < SB_T / 16; ++s)
+            umma_ss(tmem_base + COL_DQ, d(g_lo + s * (16 * 128 >> 4)), d(k_lo + s * (16 * 128 >> 4)), idesc_dq, s != 0);
+          umma_commit(&q_empty[st]);
+          umma_commit(unit_done);
+          if (i == nt - 1) umma_commit(kv_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    const int wg = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int s_lo = wg * (NSTEP / 2), s_hi = s_lo + NSTEP / 2;
+    int n = 0;
+    for (int j = 0; j < nt; ++j) {
+      const int kk = j * SB_T + r;
+      const bool kvalid = kk < len;
+      uint8_t* srow = sG + (r >> 3) * 1024 + (r & 7) * 128;
+      for (int i = 0; i < nt; ++i, ++n) {
+        mbar_wait(sdp_full, n & 1, 10);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < NSTEP; ++s) {
+          if (s < s_lo || s >= s_hi) continue;
+          uint32_t sv[16], dp[16];
+          tmem_ld16(tmem_base + lane_off + COL_ST + 16 * s, sv);
+          tmem_ld16(tmem_base + lane_off + COL_DP + 16 * s, dp);
+          tmem_ld_wait();
+          uint32_t pw[8], gw[8];
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            float pv[2], gv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float2 ldq = sLD[i * SB_T + 16 * s + c + e];
+              const float pe = kvalid ? ex2_approx(__uint_as_float(sv[c + e]) - ldq.x) : 0.f;
+              pv[e] = pe;
+              gv[e] = pe * (__uint_as_float(dp[c + e]) - ldq.y);
+            }
+            pw[c >> 1] = pack_bf16x2(pv[0], pv[1]);
+            gw[c >> 1] = pack_bf16x2(gv[0], gv[1]);
+          }
+          tmem_st8p(tmem_base + lane_off + COL_ST + 16 * s, pw);
+          tmem_st8p(tmem_base + lane_off + COL_DP + 16 * s, gw);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = 2 * s + h;
+            *reinterpret_cast<uint4*>(srow + (c >> 3) * (SB_T * 128) + (((c & 7) ^ (r & 7)) << 4)) =
+                make_uint4(gw[4 * h], gw[4 * h + 1], gw[4 * h + 2], gw[4 * h + 3]);
+          }
+        }
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pg_full);
+        // ---- this unit's dQ tile (rows = queries): add into the fp32 rows of query tile i (warpgroup = column half) ----
+        mbar_wait(unit_done, n & 1, 11);
+        tc_fence_after();
+        {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + lane_off + COL_DQ + 32 * wg, o);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
+          const int q = i * SB_T + r;
+          if (q < len) {
+            float4* dst = reinterpret_cast<float4*>(p.dq + ((size_t)bh * p.L + q) * SB_HD + 32 * wg);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 a = make_float4(__uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]),
+                                     __uint_as_float(o[4 * c + 2]), __uint_as_float(o[4 * c + 3]));
+              if (j > 0) {
+                const float4 old = dst[c];
+                a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
+              }
+              dst[c] = a;
+            }
+          }
+        }
+      }
+      // ---- dV (warpgroup 0) / dK (warpgroup 1) of key tile j: the last unit_done wait above covered these products ----
+      {
+        float* base = (wg == 0 ? p.dv : p.dk) + ((size_t)bh * p.L + kk) * SB_HD;
+#pragma unroll
+        for (int c0 = 0; c0 < SB_HD; c0 += 32) {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + lane_off + (wg == 0 ? COL_DV : COL_DK) + c0, o);
+          tmem_ld_wait();
+          if (kvalid) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              *reinterpret_cast<uint4*>(base + c0 + q) = make_uint4(o[q], o[q + 1], o[q + 2], o[q + 3]);
+          }
+        }
+        tc_fence_before();
+      }
+      // the next key tile's first dV / dK products must not start before every warp has read these accumulators: the
+      // issuer's next pg_full wait needs all eight warps, and each arrives only after this point
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// one thread per (token, head): dO token-major [B*L, nH*64] -> head-major [B, nH, L, 64]; ld = (lse, rowsum(dO o O))
+__global__ void __launch_bounds__(256)
+seq_attn_bwd_prep_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, const float* __restrict__ lse,
+                         bf16* __restrict__ dOh, float2* __restrict__ ld, int B, int L, int nH) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * L * nH) return;
+  const int head = (int)(idx % nH);
+  const long long row = idx / nH;
+  const int b = (int)(row / L), t = (int)(row - (long long)b * L);
+  const size_t hrow = ((size_t)b * nH + head) * L + t;
+  const uint4* dp = reinterpret_cast<const uint4*>(dO + (size_t)row * nH * SB_HD + head * SB_HD);
+  const uint4* op = reinterpret_cast<const uint4*>(O + (size_t)row * nH * SB_HD + head * SB_HD);
+  uint4* dst = reinterpret_cast<uint4*>(dOh + hrow * SB_HD);
+  float d = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 a = __ldg(dp + i), o = __ldg(op + i);
+    d += bf16_lo(a.x) * bf16_lo(o.x) + bf16_hi(a.x) * bf16_hi(o.x) + bf16_lo(a.y) * bf16_lo(o.y) +
+         bf16_hi(a.y) * bf16_hi(o.y) + bf16_lo(a.z) * bf16_lo(o.z) + bf16_hi(a.z) * bf16_hi(o.z) +
+         bf16_lo(a.w) * bf16_lo(o.w) + bf16_hi(a.w) * bf16_hi(o.w);
+    dst[i] = a;
+  }
+  ld[hrow] = make_float2(lse[hrow], d);
+}
+
+// (dq, dk, dv) fp32 head-major -> d(x Wqkv^T + b) bf16 token-major [B*L, 3*Hd] (q | k | v): dq / sqrt(hd), ln2 dk, dv
+__global__ void __launch_bounds__(256)
+seq_qkv_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ dk, const float* __restrict__ dv,
+                   bf16* __restrict__ dqkv, int B, int L, int nH, float q_mul, float k_mul) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * L * nH) return;
+  const int head = (int)(idx % nH);
+  const long long row = idx / nH;
+  const int b = (int)(row / L), t = (int)(row - (long long)b * L);
+  const size_t hrow = ((size_t)b * nH + head) * L + t;
+  const int Hd = nH * SB_HD;
+  const float* src[3] = {dq + hrow * SB_HD, dk + hrow * SB_HD, dv + hrow * SB_HD};
+  const float mul[3] = {q_mul, k_mul, 1.0f};
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    uint4* o = reinterpret_cast<uint4*>(dqkv + (size_t)row * 3 * Hd + w * Hd + head * SB_HD);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src[w]) + 2 * i);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(src[w]) + 2 * i + 1);
+      o[i] = make_uint4(pack_bf16x2(a.x * mul[w], a.y * mul[w]), pack_bf16x2(a.z * mul[w], a.w * mul[w]),
+                        pack_bf16x2(c.x * mul[w], c.y * mul[w]), pack_bf16x2(c.z * mul[w], c.w * mul[w]));
+    }
+  }
+}
+
+}  // namespace mv
+
+extern "C" int mvuld_seq_attention_bwd_prep(const void* dO, const void* O, const float* lse, void* dOh, void* ld, int B,
+                                            int L, int nH, cudaStream_t stream) {
+  const long long total = (long long)B * L * nH;
+  if (total <= 0) return 0;
+  seq_attn_bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dO), reinterpret_cast<const bf16*>(O), lse, reinterpret_cast<bf16*>(dOh),
+      reinterpret_cast<float2*>(ld), B, L, nH);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_seq_attention_bwd(const void* q, const void* k, const void* v, const void* dOh, const void* ld,
+                                       const int* kv_len, float* dq, float* dk, float* dv, int B, int L, int nH, int hd,
+                                       cudaStream_t stream) {
+  MV_CHECK_ARG(hd == SB_HD, "seq attention backward: head_dim 64 only");
+  MV_CHECK_ARG(L <= 512 && L % 8 == 0, "seq attention backward: L must be <= 512 and a multiple of 8");
+  SeqBwdParams p{};
+  p.nH = nH; p.L = L; p.kv_len = kv_len;
+  p.ld = reinterpret_cast<const float2*>(ld);
+  p.dq = dq; p.dk = dk; p.dv = dv;
+  const int n_bh = B * nH;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  uint64_t dims[3] = {SB_HD, (uint64_t)L, (uint64_t)n_bh};
+  uint64_t str[2] = {SB_HD * 2, (uint64_t)L * SB_HD * 2};
+  uint32_t box[3] = {SB_HD, SB_T, 1};
+  int rc;
+  if ((rc = make_tmap_16b(&tmQ, q, 3, dims, str, box, 128))) return rc;
+  if ((rc = make_tmap_16b(&tmK, k, 3, dims, str, box, 128))) return rc;
+  if ((rc = make_tmap_16b(&tmV, v, 3, dims, str, box, 128))) return rc;
+  if ((rc = make_tmap_16b(&tmdO, dOh, 3, dims, str, box, 128))) return rc;
+  MV_CUDA_OK(cudaFuncSetAttribute(seq_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+  seq_attn_bwd_kernel<<<n_bh, AB_THREADS, SB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  MV_LAUNCH_OK();
+  return 0;
+}
+extern "C" int mvuld_seq_qkv_bwd(const float* dq, const float* dk, const float* dv, void* dqkv, int B, int L, int nH,
+                                 int hd, cudaStream_t stream) {
+  MV_CHECK_ARG(hd == SB_HD, "seq_qkv_bwd: head_dim 64 only");
+  const long long total = (long long)B * L * nH;
+  if (total <= 0) return 0;
+  // q is stored as (x Wq + b) log2e / sqrt(hd): d(x Wq + b) = ln2 (G k) log2e / sqrt(hd) = dq / sqrt(hd); d k = ln2 G^T q_stored
+  seq_qkv_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dq, dk, dv, reinterpret_cast<bf16*>(dqkv), B,
+                                                                         L, nH, 1.0f / sqrtf((float)hd),
+                                                                         0.6931471805599453f);
+  MV_LAUNCH_OK();
+  return 0;
+}

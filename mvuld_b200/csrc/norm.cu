@@ -296,8 +296,8 @@ seq_positions_kernel(const long long* __restrict__ ids, int L, int pad, int* __r
 __global__ void __launch_bounds__(256)
 roberta_embed_kernel(const long long* __restrict__ ids, const int* __restrict__ pos, const float* __restrict__ word,
                      const float* __restrict__ posemb, const float* __restrict__ type0, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float* __restrict__ x32, bf16* __restrict__ xb, int M, int C,
-                     float eps) {
+                     const float* __restrict__ beta, float* __restrict__ x32, bf16* __restrict__ xb,
+                     bf16* __restrict__ ysum, int M, int C, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -311,6 +311,10 @@ roberta_embed_kernel(const long long* __restrict__ ids, const int* __restrict__ 
     if (q < per) {
       const int c = lane + q * 32;
       v[q] = __ldg(wp + c) + __ldg(pp + c) + __ldg(type0 + c);
+      if (ysum) {                                  // training: the LayerNorm input as the backward pass will see it
+        ysum[(size_t)row * C + c] = __float2bfloat16(v[q]);
+        v[q] = __bfloat162float(__float2bfloat16(v[q]));
+      }
       s += v[q];
     }
   }
@@ -425,7 +429,19 @@ extern "C" int mvuld_roberta_embed(const long long* ids, const int* pos, const f
                                    int M, int C, float eps, cudaStream_t stream) {
   MV_CHECK_ARG(C % 32 == 0 && C <= 1024, "roberta_embed: C");
   roberta_embed_kernel<<<(M + 7) / 8, 256, 0, stream>>>(ids, pos, word, posemb, type0, gamma, beta, x32,
-                                                        reinterpret_cast<bf16*>(xb), M, C, eps);
+                                                        reinterpret_cast<bf16*>(xb), nullptr, M, C, eps);
+  MV_LAUNCH_OK();
+  return 0;
+}
+// training forward: also keeps ysum = word + position + type embeddings (bf16 [M, C], the LayerNorm input; the
+// normalisation then runs on exactly these rounded values so that mvuld_ln_rows_bwd recomputes the same statistics)
+extern "C" int mvuld_roberta_embed_train(const long long* ids, const int* pos, const float* word, const float* posemb,
+                                         const float* type0, const float* gamma, const float* beta, float* x32, void* xb,
+                                         void* ysum, int M, int C, float eps, cudaStream_t stream) {
+  MV_CHECK_ARG(C % 32 == 0 && C <= 1024 && ysum != nullptr, "roberta_embed_train: C %% 32, C <= 1024, ysum non-null");
+  roberta_embed_kernel<<<(M + 7) / 8, 256, 0, stream>>>(ids, pos, word, posemb, type0, gamma, beta, x32,
+                                                        reinterpret_cast<bf16*>(xb), reinterpret_cast<bf16*>(ysum), M, C,
+                                                        eps);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -1167,6 +1167,7 @@ extern "C" int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gam
   MV_LAUNCH_OK();
   return 0;
 }
+extern "C" int mvuld_ln_rows_bwd_blocks(int M);
 extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const float* gamma, const float* dout, void* dv_bf16,
                                  float* dv_f32, float* dgamma, float* dbeta, float* partials, int M, int C, float eps,
                                  int mode, cudaStream_t stream) {
@@ -1175,7 +1176,7 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
   MV_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || shortcut), "ln_rows_bwd: mode %d (mode 2 needs the shortcut)", mode);
   MV_CHECK_ARG(dgamma && dbeta && (dv_bf16 || dv_f32), "ln_rows_bwd: dgamma / dbeta and one of the dv outputs are required");
   if (M <= 0) return 0;
-  const int grid = std::min((M + 7) / 8, 2 * num_sms());
+  const int grid = mvuld_ln_rows_bwd_blocks(M);
   const size_t smem = (size_t)16 * C * sizeof(float);
   const bf16* yp = reinterpret_cast<const bf16*>(y);
   bf16* dvp = reinterpret_cast<bf16*>(dv_bf16);
@@ -1195,7 +1196,7 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
   return 0;
 }
 // rows of the partials workspace mvuld_ln_rows_bwd needs for M rows ([blocks, 2, C] floats)
-extern "C" int mvuld_ln_rows_bwd_blocks(int M) { return std::min((M + 7) / 8, 2 * num_sms()); }
+extern "C" int mvuld_ln_rows_bwd_blocks(int M) { return std::min((M + 7) / 8, 6 * num_sms()); }   // 2 blocks per SM left the row loop latency bound (5.6 ms of a 66 ms SwinV2 step)
 extern "C" int mvuld_gelu_bwd(const void* pre, const void* dh, void* dpre, long long n, cudaStream_t stream) {
   MV_CHECK_ARG(n % 8 == 0, "gelu_bwd: n %% 8");
   if (n <= 0) return 0;
