@@ -347,8 +347,8 @@ def build_train_workload(args, rank, device, world, model=None, encoders=False):
     model = model or build_full_model(device)
     base_lr = 5e-5 * B * world / 512.0                                     # main_bigvul.py:545 linear scaling rule
     if encoders:
-        # configs[4], primary reading: the image encoder trains too (mvuld/main.py:251-300 chained behind the fusion
-        # backward); UniXcoder stays frozen (its backward is not built)
+        # configs[4], primary reading: both encoders train too (mvuld/main.py:251-300 and autograd through
+        # unixcoder.py:33-38 chained behind the fusion backward)
         from mvuld_b200.joint_train import MVulDTrainer
         trainer = MVulDTrainer(model, lr=base_lr, clip_grad=5.0, dropout=0.2, seed=12345 + rank, world_size=world)
     else:
@@ -356,7 +356,8 @@ def build_train_workload(args, rank, device, world, model=None, encoders=False):
                                 seed=12345 + rank, world_size=world)
     raw_ids = synth.token_ids(B, 512, seed=seed).pin_memory()
     enc = model.unix.encoder
-    ids = raw_ids if args.padded_text else enc.pack_host(raw_ids)
+    padded = args.padded_text or encoders        # the trained text encoder takes the tokenizer's padded [B, 512] rows
+    ids = raw_ids if padded else enc.pack_host(raw_ids)
     host = dict(img=synth.images(B, 448, seed=seed).pin_memory(), ids=ids, g=_pin_graph(synth.cpg_batch(B, seed=seed)),
                 y=torch.randint(0, 2, (B,), generator=torch.Generator().manual_seed(seed)).pin_memory())
     host["g"].ndata.pop("_FUNC_EMB")
@@ -378,23 +379,21 @@ def build_train_workload(args, rank, device, world, model=None, encoders=False):
     def host_iter(n):
         for _ in range(n):
             yield dict(img=host["img"], g=host["g"], y=host["y"],
-                       ids=raw_ids if args.padded_text else enc.pack_host(raw_ids))
+                       ids=raw_ids if padded else enc.pack_host(raw_ids))
 
-    ids_bytes = raw_ids.numel() * 8 if args.padded_text else ids.nbytes
+    ids_bytes = raw_ids.numel() * 8 if padded else ids.nbytes
     h2d = host["img"].numel() * 4 + ids_bytes + host["g"]._src.numel() * 16 + B * 8 + \
         sum(v.numel() * v.element_size() for v in host["g"].ndata.values())
     if encoders:
         n_par = trainer.num_parameters
-        total = trainer.fusion.total + trainer.swin.total
-        name = (f"MVulD training step (configs[4], image encoder + fusion model trained jointly, {n_par / 1e6:.0f} M "
-                f"parameters; UniXcoder forward only): SwinV2-B forward + backward, UniXcoder "
-                f"({'padded 512-token rows' if args.padded_text else f'real tokens packed into {ids.n_rows} rows of 512'}) "
-                f"forward, fusion fwd+bwd, bucketed NCCL gradient all-reduce ({len(trainer.buckets)} buckets, "
-                f"{total * 4 / 1e6:.0f} MB fp32), one clip 5.0 over both parameter sets + AdamW; {B} functions per GPU "
+        total = sum(t.total for t in trainer.trainers)
+        name = (f"MVulD training step (configs[4], image encoder + text encoder + fusion model trained jointly, "
+                f"{n_par / 1e6:.0f} M parameters): SwinV2-B forward + backward, UniXcoder (padded 512-token rows) forward "
+                f"+ backward, fusion fwd+bwd, bucketed NCCL gradient all-reduce ({len(trainer.buckets)} buckets, "
+                f"{total * 4 / 1e6:.0f} MB fp32), one clip 5.0 over the three parameter sets + AdamW; {B} functions per GPU "
                 f"(global batch {B * world}), avg {host['g'].num_nodes() / B:.0f} CPG nodes")
-        text_rows = B if args.padded_text else ids.n_rows
         return dict(units=B, to_dev=to_dev, step=step, h2d=h2d, d2h=4, name=name, host_iter=host_iter,
-                    flops_per_unit=3 * 159.08e9 + 96.64e9 * text_rows / B + 4 * 6.4e9, trainer=trainer, host=host,
+                    flops_per_unit=3 * 159.08e9 + 3 * 96.64e9 + 4 * 6.4e9, trainer=trainer, host=host,
                     model=model, total_grad_elems=total)
     name = (f"MVulD fusion training step (configs[4], encoders frozen as in main_bigvul.py): SwinV2-B + UniXcoder "
             f"({'padded 512-token rows' if args.padded_text else f'real tokens packed into {ids.n_rows} rows of 512'}) "
@@ -792,13 +791,13 @@ def main():
                                                    f"{twl['trainer'].total * 4 / 1e6:.1f} MB fp32" if world > 1 else "none (1 GPU)")}
             del twl, tm
             torch.cuda.empty_cache()
-            # the same step with the image encoder trainable (configs[4], primary reading); a fresh model: the trainers
+            # the same step with both encoders trainable (configs[4], primary reading); a fresh model: the trainers
             # re-point its parameters at their flat buffers
             emodel = build_full_model(device)
             ewl = build_train_workload(args, rank, device, world, model=emodel, encoders=True)
             em = measure(ctx, ewl, tsteps, 3)
             sub["train_encoders"] = {
-                "metric": "MVulD functions/sec (train step, image encoder + fusion trainable)", "value": em["value"],
+                "metric": "MVulD functions/sec (train step, image + text encoders + fusion trainable)", "value": em["value"],
                 "unit": "functions/s", "steps": tsteps, "warmup": 3, "ms_per_step": em["ms_per_step"],
                 "per_gpu_batch": ewl["units"], "global_batch": ewl["units"] * world, "workload": ewl["name"],
                 "trained_parameters": int(ewl["trainer"].num_parameters),

@@ -239,9 +239,10 @@ def test_swin_encoder_backward_full_size_matches_oracle():
 
 
 def test_joint_trainer_chains_fusion_and_image_encoder_backward():
-    """MVulDTrainer (configs[4], primary reading): the fusion backward's input gradient drives the SwinV2 backward; one
-    clip over both parameter sets.  Checked: the image-encoder gradient equals SwinTrainer.backward_train fed the same
-    cotangent (bitwise: same launches), the joint norm, that repeated steps on one batch lower the loss."""
+    """MVulDTrainer (configs[4], primary reading): the fusion backward's input gradients drive the SwinV2 and RoBERTa
+    backward passes; one clip over the three parameter sets (232 M parameters).  Checked: every parameter set
+    receives a gradient, the joint norm is the norm over the three flat buffers, repeated steps on one batch lower the
+    loss (each encoder's own gradient parity is pinned in test_gpu_swin_train / test_gpu_roberta_train)."""
     import mvuld_b200 as mv
     from mvuld_b200 import synth
     from mvuld_b200.joint_train import MVulDTrainer
@@ -252,7 +253,7 @@ def test_joint_trainer_chains_fusion_and_image_encoder_backward():
     model = model.to(DEV)
     B = 2
     tr = MVulDTrainer(model, lr=2e-5, dropout=0.0, world_size=1)
-    assert tr.num_parameters > 100e6
+    assert tr.num_parameters > 225e6                                           # SwinV2-B 87 M + RoBERTa-base 125 M + fusion 19 M
     img = synth.images(B, 448, seed=cases.SEED + 61).to(DEV)
     ids = synth.token_ids(B, 512, seed=cases.SEED + 62).to(DEV)
     g = synth.cpg_batch(B, seed=cases.SEED + 63)
@@ -266,6 +267,7 @@ def test_joint_trainer_chains_fusion_and_image_encoder_backward():
         losses.append(float(loss))
         assert torch.isfinite(logits).all()
     gs, gf = tr.swin.flat_g.double().pow(2).sum(), tr.fusion.flat_g.double().pow(2).sum()
-    assert float(gs) > 0 and float(gf) > 0
-    assert abs(float(tr.grad_norm()) - float((gs + gf).sqrt())) <= 1e-4 * float((gs + gf).sqrt())
+    gt = tr.text.flat_g.double().pow(2).sum()
+    assert float(gs) > 0 and float(gf) > 0 and float(gt) > 0
+    assert abs(float(tr.grad_norm()) - float((gs + gf + gt).sqrt())) <= 1e-4 * float((gs + gf + gt).sqrt())
     assert losses[-1] < losses[0], losses
