@@ -279,6 +279,27 @@ int mvuld_linear_small(const float* x, const float* w, const float* b, float* ou
                        int K, mvuld_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Fusion ablation classes (mvuld/models/GraphModel.py:618-1274, mvuld/models/myModels.py:280-428).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Per-node ELU(Linear(4, OUT)(pos_emb)) into bf16 columns [col0, col0 + OUT) of a [N, ld] buffer
+ * (GraphModel.py:791 _GATPOS fc_bbox, :1132 _NOGAT3, :1242 _NOGAT4).  pos fp32 [N, 4], w fp32 [OUT, 4]. */
+int mvuld_node_linear4(const float* pos, const float* w, const float* bias, void* out_bf16, int N, int OUT, int ld,
+                       int col0, mvuld_stream_t stream);
+/* ELU(bn_gat(pad(h))) -> fp32 + bf16 [B * max_node, F] (GraphModel.py:923-928, _011: no fc_gat behind the slot BN). */
+int mvuld_unbatch_pad_bn_elu(const void* feat, const long long* offsets, const float* bn_scale, const float* bn_shift,
+                             float* z32, void* zb, int B, int max_node, int F, mvuld_stream_t stream);
+/* nn.GRU(H, H, 1, batch_first=True) recurrence, h_0 = 0, -> last hidden state fp32 [B, H] (myModels.py:324,385-387).
+ * gi fp32 [B, T, 3H] = x_t W_ih^T + b_ih (gate order r | z | n); w_hh fp32 [3H, H]; b_hh fp32 [3H];
+ * workspace: mvuld_gru_sequence_workspace(B, H) bytes.  Cooperative launch (one grid barrier per step). */
+long long mvuld_gru_sequence_workspace(int B, int H);
+int mvuld_gru_sequence(const float* gi, const float* w_hh, const float* b_hh, float* h_out, void* workspace, int B,
+                       int T, int H, mvuld_stream_t stream);
+/* mode 0: out[b, col0 + c] = softmax_c(tanh(x[b, c] * h[b, c])) * h[b, c]  (myModels.py:407-413, fusion 'attention');
+ * mode 1: out[b, col0 + c] = x[b, c] * h[b, c] (myModels.py:419, fusion 'dot').  fp32, C <= 1024. */
+int mvuld_gate_fusion(const float* x, const float* h, float* out, int B, int C, int ld, int col0, int mode,
+                      mvuld_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Training step of the fusion model (mvuld/main_bigvul.py:294-342 drives GraphModel.py:150-211 in train mode with
  * CrossEntropyLoss, clip_grad_norm_(5.0) and AdamW).  Dense backward passes reuse mvuld_gemm_bf16 on transposed
  * operands; these entry points are the non-GEMM pieces.  Activation gradients bf16 / fp32, parameter gradients fp32

@@ -11,7 +11,10 @@ from .graph_model import (Multi_DefectModel_new_GCN, Multi_DefectModel, Rs_GCN, 
                           GGNNSum)
 from .fusion_variants import (Multi_DefectModel_noGraph, Multi_DefectModel_000, Multi_DefectModel_001,   # noqa: F401
                               Multi_DefectModel_100, Multi_DefectModel_NOGAT2, Multi_DefectModel_noFunc,
-                              Multi_DefectModel_noGlobalImage, ABLATIONS)
+                              Multi_DefectModel_noGlobalImage, ABLATIONS, Multi_DefectModel_110,
+                              Multi_DefectModel_GATPOS, Multi_DefectModel_011, Multi_DefectModel_NOGAT,
+                              Multi_DefectModel_NOGAT3, Multi_DefectModel_NOGAT4, GRID_VARIANTS)
+from . import my_models                                             # noqa: F401
 from .mvuld import MVulD                                            # noqa: F401
 from . import graph, checkpoint                                     # noqa: F401
 
@@ -19,4 +22,6 @@ __all__ = ["get_config", "default_config", "CfgNode", "build_model", "SwinTransf
            "RobertaEncoder", "build_MyUniXcoder", "roberta_base_config", "Multi_DefectModel_new_GCN", "Rs_GCN",
            "GATConv", "GatedGraphConv", "GGNNSum", "MVulD", "graph", "Multi_DefectModel",
            "Multi_DefectModel_noGraph", "Multi_DefectModel_000", "Multi_DefectModel_001", "Multi_DefectModel_100",
-           "Multi_DefectModel_NOGAT2", "Multi_DefectModel_noFunc", "Multi_DefectModel_noGlobalImage", "ABLATIONS"]
+           "Multi_DefectModel_NOGAT2", "Multi_DefectModel_noFunc", "Multi_DefectModel_noGlobalImage", "ABLATIONS",
+           "Multi_DefectModel_110", "Multi_DefectModel_GATPOS", "Multi_DefectModel_011", "Multi_DefectModel_NOGAT",
+           "Multi_DefectModel_NOGAT3", "Multi_DefectModel_NOGAT4", "GRID_VARIANTS", "my_models"]

@@ -99,6 +99,11 @@ SIGNATURES = {
     "mvuld_linear_small_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_sumsq_f32": [_P, _LL, _P, _P, _P],
     "mvuld_adamw": [_P, _P, _P, _P, _LL, _P, _P, _I, _P, _F, _F, _F, _F, _F, _I, _P],
+    "mvuld_node_linear4": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvuld_unbatch_pad_bn_elu": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_gru_sequence_workspace": [_I, _I],
+    "mvuld_gru_sequence": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvuld_gate_fusion": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 13 + [_P, _P],
 }
 
@@ -123,7 +128,7 @@ def load() -> C.CDLL:
     lib.mvuld_last_error.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
-        fn.restype = C.c_longlong if name == "mvuld_gemm_dw_workspace" else C.c_int
+        fn.restype = C.c_longlong if name.endswith("_workspace") else C.c_int
         fn.argtypes = argtypes
     _lib = lib
     return lib

@@ -165,3 +165,137 @@ def ablation_forward(name: str, sd: Dict[str, torch.Tensor], batch: "dgl_ops.Hos
         hf = z.mean(dim=1)
     feats = torch.cat([x, hf, t], 1)
     return lin("final_fc", _bn_eval(sd, "final_fc_bn.", feats, 1))
+
+
+# The remaining classes of GraphModel.py (RQ3 "position / GAT / GCN on-off" grid) and the gating-fusion class of
+# myModels.py.  Every one returns final_fc(final_fc_bn(.)) logits (the reference names the tensor ``all_feats``).
+#   pre      : "gatpos" = per-node ELU(fc_gat 768->720) | ELU(fc_bbox 4->48) in front of the GATConvs (:790-792)
+#   nodes    : "gat" = GATConv x2 + fc + hidden x 8; "raw" = the 768-wide line vectors go to the slots unchanged (:1014-1019);
+#              "fconly+hidden" (:1130-1136); "fconly480|pos+hidden" = cat(ELU(fconly 768->480), ELU(fc_bbox 4->32)) +
+#              hidden x 8 (:1241-1246)
+#   posnodes : per-node ELU(fc_bbox 4->128) + eight ELU(pos_hidden[i]) layers (:1132,1138-1139)
+#   slot     : what follows bn_gat on the [B, 100, F] slots: "fc_gat" | "hfc" (:815) | "elu" (:928)
+#   pos      : None | "fc_bbox" (bn_bbox + fc_bbox 4->32 on the padded boxes) | "fc_bbox2" (bn_bbox + fc_bbox2 128->32, :1148)
+#   gcn      : Rs_GCN x 8 + l2norm over the slot axis before the slot mean
+VARIANT_SPECS2 = {
+    "Multi_DefectModel_110": dict(nodes="gat", slot="fc_gat", pos="fc_bbox", gcn=False),                       # :618-718
+    "Multi_DefectModel_GATPOS": dict(pre="gatpos", nodes="gat", slot="hfc", pos=None, gcn=False),              # :721-826
+    "Multi_DefectModel_011": dict(nodes="gat", slot="elu", pos=None, gcn=True),                                # :830-948
+    "Multi_DefectModel_NOGAT": dict(nodes="raw", slot="fc_gat", pos="fc_bbox", gcn=True),                      # :950-1050
+    "Multi_DefectModel_NOGAT3": dict(nodes="fconly+hidden", posnodes=True, slot="fc_gat", pos="fc_bbox2", gcn=True),  # :1053-1170
+    "Multi_DefectModel_NOGAT4": dict(nodes="fconly480|pos+hidden", slot="fc_gat", pos=None, gcn=True),         # :1173-1273
+}
+
+
+@torch.no_grad()
+def variant2_forward(name: str, sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
+                     func_text_embedding: torch.Tensor, max_node: int = 100) -> torch.Tensor:
+    """Eval-mode forward of the classes listed in VARIANT_SPECS2 -> logits [B, num_classes]."""
+    spec = VARIANT_SPECS2[name]
+    lin = lambda key, t: F.linear(t, sd[key + ".weight"].float(), sd[key + ".bias"].float())
+    x = F.elu(lin("swinfc", _bn_eval(sd, "swinbn.", img_embedding.float(), 1)))
+    t = F.elu(lin("fc_text", _bn_eval(sd, "bn_text.", func_text_embedding.float(), 1)))
+    h = batch.ndata["_UNIX_NODE_EMB"].float()
+    pos = batch.ndata["pos_emb"].float()
+    pos_n = None
+    if spec.get("pre") == "gatpos":
+        h = torch.cat([F.elu(lin("fc_gat", h)), F.elu(lin("fc_bbox", pos))], 1)
+    if spec["nodes"] == "gat":
+        h = dgl_ops.gat_conv(sd, "gat.", batch.src, batch.dst, h, 4, 512).reshape(h.shape[0], -1)
+        h = dgl_ops.gat_conv(sd, "gat2.", batch.src, batch.dst, h, 4, 512).reshape(h.shape[0], -1)
+        h = F.elu(lin("fc", h))
+    elif spec["nodes"] == "fconly+hidden":
+        h = F.elu(lin("fconly", h))
+    elif spec["nodes"] == "fconly480|pos+hidden":
+        h = torch.cat([F.elu(lin("fconly", h)), F.elu(lin("fc_bbox", pos))], 1)
+    if spec["nodes"] != "raw":
+        for i in range(8):
+            h = F.elu(lin(f"hidden.{i}", h))
+    if spec.get("posnodes"):
+        pos_n = F.elu(lin("fc_bbox", pos))
+        for i in range(8):
+            pos_n = F.elu(lin(f"pos_hidden.{i}", pos_n))
+    h_i = _bn_eval(sd, "bn_gat.", dgl_ops.unbatch_pad(h, batch.batch_num_nodes, max_node), 1)
+    z = F.elu({"fc_gat": lambda: lin("fc_gat", h_i), "hfc": lambda: lin("hfc", h_i), "elu": lambda: h_i}[spec["slot"]]())
+    if spec["pos"] == "fc_bbox":
+        pos_i = dgl_ops.unbatch_pad(pos, batch.batch_num_nodes, max_node)
+        z = torch.cat([z, F.elu(lin("fc_bbox", _bn_eval(sd, "bn_bbox.", pos_i, 1)))], 2)
+    elif spec["pos"] == "fc_bbox2":
+        pos_i = dgl_ops.unbatch_pad(pos_n, batch.batch_num_nodes, max_node)
+        z = torch.cat([z, F.elu(lin("fc_bbox2", _bn_eval(sd, "bn_bbox.", pos_i, 1)))], 2)
+    if spec["gcn"]:
+        z = z.permute(0, 2, 1)
+        for k in range(1, 9):
+            z, _ = rs_gcn(sd, f"Rs_GCN_{k}.", z)
+        z = l2norm_dim1(z.permute(0, 2, 1))
+    feats = torch.cat([x, z.mean(dim=1), t], 1)
+    return lin("final_fc", _bn_eval(sd, "final_fc_bn.", feats, 1))
+
+
+@torch.no_grad()
+def gru_last_state(sd: Dict[str, torch.Tensor], prefix: str, seq: torch.Tensor) -> torch.Tensor:
+    """torch.nn.GRU(batch_first=True, 1 layer), h_0 = 0 -> hidden state after the last step [B, H] (restated; pinned
+    against torch.nn.GRU in tests/test_host_logic.py)."""
+    w_ih, w_hh = sd[prefix + "weight_ih_l0"].float(), sd[prefix + "weight_hh_l0"].float()
+    b_ih, b_hh = sd[prefix + "bias_ih_l0"].float(), sd[prefix + "bias_hh_l0"].float()
+    B, T, _ = seq.shape
+    H = w_hh.shape[1]
+    h = seq.new_zeros(B, H)
+    gi_all = seq.float() @ w_ih.t() + b_ih
+    for step in range(T):
+        gi, gh = gi_all[:, step], h @ w_hh.t() + b_hh
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        zg = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - zg) * n + zg * h
+    return h
+
+
+@torch.no_grad()
+def gating_forward(sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
+                   func_text_embedding: torch.Tensor, projection: str = "gru", fusion: str = "attention") -> torch.Tensor:
+    """myModels.py:343-428 (``Multi_DefectModel`` of that file; as shipped: projection_layer 'gru', fusion 'attention'):
+    GATConv x2 + node MLP, unbatch padded to the LONGEST graph of the batch (:430-446, no truncation), projection over the
+    node axis, ELU(hfc(hbn(.))), then the tanh / softmax gate of the image vector on the graph vector (:407-413)."""
+    lin = lambda name, t: F.linear(t, sd[name + ".weight"].float(), sd[name + ".bias"].float())
+    x = F.elu(lin("swinfc", _bn_eval(sd, "swinbn.", img_embedding.float(), 1)))
+    t = F.elu(lin("fc_text", _bn_eval(sd, "bn_text.", func_text_embedding.float(), 1)))
+    h = batch.ndata["_UNIX_NODE_EMB"].float()
+    h = dgl_ops.gat_conv(sd, "gat.", batch.src, batch.dst, h, 4, 512).reshape(h.shape[0], -1)
+    h = dgl_ops.gat_conv(sd, "gat2.", batch.src, batch.dst, h, 4, 512).reshape(h.shape[0], -1)
+    h = F.elu(lin("fc", h))
+    for i in range(8):
+        h = F.elu(lin(f"hidden.{i}", h))
+    max_len = int(max(batch.batch_num_nodes))
+    h_i = dgl_ops.unbatch_pad(h, batch.batch_num_nodes, max_len)                 # [B, max_len, 512]
+    B = x.shape[0]
+    if projection == "gru":
+        hv = gru_last_state(sd, "gru_local.", h_i)
+    elif projection == "attention":
+        a = F.softmax(F.leaky_relu(torch.bmm(x.reshape(B, 1, 512), h_i.permute(0, 2, 1))), dim=2)
+        hv = torch.bmm(a, h_i).reshape(B, -1)
+    else:
+        hv = h_i.mean(dim=1)
+    hv = F.elu(lin("hfc", _bn_eval(sd, "hbn.", hv, 1)))
+    if fusion == "attention":
+        feats = torch.cat([F.softmax(torch.tanh(x * hv), dim=1) * hv, t], 1)
+    elif fusion == "dot":
+        feats = torch.cat([x * hv, t], 1)
+    else:
+        feats = torch.cat([x, hv, t], 1)
+    return lin("final_fc", _bn_eval(sd, "final_bn.", feats, 1))
+
+
+def class_forward(key: str, sd: Dict[str, torch.Tensor], batch: "dgl_ops.HostBatch", img_embedding: torch.Tensor,
+                  func_text_embedding: torch.Tensor) -> torch.Tensor:
+    """Oracle forward of the fusion class ``key`` (keys of tests/golden/fusion_classes.pt, which holds the logits of
+    the reference's own classes run with ``dgl`` stubbed by oracle.dgl_ops: tools/make_golden.py fusion_classes)."""
+    if key == "Multi_DefectModel_new_GCN":
+        return fusion_forward(sd, batch, img_embedding, func_text_embedding)
+    if key == "Multi_DefectModel":
+        return gat_variant_forward(sd, batch, img_embedding, func_text_embedding)
+    if key == "myModels.Multi_DefectModel":
+        return gating_forward(sd, batch, img_embedding, func_text_embedding)
+    if key in VARIANT_SPECS2:
+        return variant2_forward(key, sd, batch, img_embedding, func_text_embedding)
+    return ablation_forward(key, sd, batch, img_embedding, func_text_embedding)

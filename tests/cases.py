@@ -109,3 +109,37 @@ def to_host_batch(g):
                      g.batch_num_nodes().cpu().numpy().astype(np.int64),
                      g.batch_num_edges().cpu().numpy().astype(np.int64),
                      {k: v.cpu() for k, v in g.ndata.items()}, {k: v.cpu() for k, v in g.edata.items()})
+
+
+# ---- every fusion class against the reference's own class code (tests/golden/fusion_classes.pt) ----
+def fusion_class_cases():
+    """(golden key, reference module, class name, mirror class) of every fusion class."""
+    import mvuld_b200 as mv
+    from mvuld_b200 import my_models
+    out = [("Multi_DefectModel_new_GCN", "GraphModel", "Multi_DefectModel_new_GCN", mv.Multi_DefectModel_new_GCN),
+           ("Multi_DefectModel", "GraphModel", "Multi_DefectModel", mv.Multi_DefectModel),
+           ("myModels.Multi_DefectModel", "myModels", "Multi_DefectModel", my_models.Multi_DefectModel)]
+    for n, c in {**mv.ABLATIONS, **mv.GRID_VARIANTS}.items():
+        out.append((n, "new_model" if n in ("Multi_DefectModel_noFunc", "Multi_DefectModel_noGlobalImage") else "GraphModel",
+                    n, c))
+    return out
+
+
+FUSION_CLASS_BATCH = 5
+
+
+def fusion_class_inputs():
+    from mvuld_b200 import synth
+    g = synth.cpg_batch(FUSION_CLASS_BATCH, seed=SEED + 13)       # graph sizes on both sides of the 100-slot truncation
+    gen = torch.Generator().manual_seed(3)
+    img, txt = torch.randn(FUSION_CLASS_BATCH, 1024, generator=gen), torch.randn(FUSION_CLASS_BATCH, 768, generator=gen)
+    return g, img, txt
+
+
+def fusion_class_model(key, cls):
+    import mvuld_b200 as mv
+    from mvuld_b200 import synth
+    torch.manual_seed(SEED)
+    m = cls(mv.default_config()).eval()
+    round_matrices_to_bf16(synth.randomize_for_parity(m, seed=SEED))
+    return m

@@ -28,7 +28,7 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import torch
     return {n: torch.load(os.path.join(GOLDEN, n + ".pt"), weights_only=False)
-            for n in ("swin", "rs_gcn", "roberta", "graph", "swin_train", "roberta_train")}
+            for n in ("swin", "rs_gcn", "roberta", "graph", "swin_train", "roberta_train", "fusion_classes")}
 
 
 # measured parity errors of the -m gpu run: every model-level assert records (name, measured, tolerance) here and the

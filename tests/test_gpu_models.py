@@ -149,6 +149,44 @@ def test_gat_free_ablation_variants_match_oracle(name):
     assert torch.equal(out.cpu().argmax(1), ref.argmax(1))
 
 
+@pytest.mark.parametrize("key", ["Multi_DefectModel_110", "Multi_DefectModel_GATPOS", "Multi_DefectModel_011",
+                                 "Multi_DefectModel_NOGAT", "Multi_DefectModel_NOGAT3", "Multi_DefectModel_NOGAT4",
+                                 "myModels.Multi_DefectModel"])
+def test_grid_and_gating_fusion_classes_match_oracle_and_reference_class(golden, key):
+    """SURVEY.md section 8f.3, the remaining classes: the RQ3 grid of GraphModel.py:618-1273 and the GRU-projection /
+    gating-attention class of myModels.py:280-428 -- CUDA mirror vs the oracle AND vs the logits of the reference's own
+    class (tests/golden/fusion_classes.pt)."""
+    mirror = {k: c for k, _, _, c in cases.fusion_class_cases()}[key]
+    m = cases.fusion_class_model(key, mirror)
+    g, img, txt = cases.fusion_class_inputs()
+    ref = ofusion.class_forward(key, m.state_dict(), cases.to_host_batch(g), img, txt)
+    gold = golden["fusion_classes"][key]["logits"]
+    out = m.to(DEV)(g.to(DEV), img.to(DEV), txt.to(DEV))
+    torch.cuda.synchronize()
+    assert out.shape == gold.shape and torch.isfinite(out).all()
+    check(f"{key} logits max-rel vs oracle", logits_err(out, ref))
+    check(f"{key} logits max-rel vs the reference class", logits_err(out, gold))
+    assert torch.equal(out.cpu().argmax(1), gold.argmax(1))
+
+
+def test_gru_sequence_kernel_matches_gru_oracle():
+    """mvuld_gru_sequence (myModels.py:324,385-387) vs oracle.fusion.gru_last_state (itself pinned against torch.nn.GRU
+    on the CPU): 64 rows, 333 steps, hidden 512, fp32."""
+    from mvuld_b200 import _lib
+    torch.manual_seed(5)
+    B, T, H = 64, 333, 512
+    gru = torch.nn.GRU(H, H, 1, batch_first=True)
+    x = torch.randn(B, T, H) * 0.5
+    ref = ofusion.gru_last_state({"g." + k: v for k, v in gru.state_dict().items()}, "g.", x)
+    gi = (x.reshape(B * T, H) @ gru.weight_ih_l0.detach().t() + gru.bias_ih_l0.detach()).contiguous().to(DEV)
+    out = torch.empty(B, H, device=DEV)
+    ws = torch.empty(int(_lib.load().mvuld_gru_sequence_workspace(B, H)), device=DEV, dtype=torch.uint8)
+    _lib.call("mvuld_gru_sequence", gi, gru.weight_hh_l0.detach().to(DEV).contiguous(),
+              gru.bias_hh_l0.detach().to(DEV).contiguous(), out, ws, B, T, H)
+    torch.cuda.synchronize()
+    check("gru_sequence max abs error vs oracle (|h| <= 1)", float((out.cpu() - ref).abs().max()), 1e-4)
+
+
 def test_fusion_rejects_zero_in_degree():
     model = cases.make_fusion().to(DEV)
     g = mv.graph.graph((torch.tensor([0, 1]), torch.tensor([1, 2])), num_nodes=3)      # node 0 has no in-edge

@@ -169,3 +169,110 @@ def test_gat_softmax_is_per_destination():
     out = dgl_ops.gat_conv(sd, "", [0, 1, 2, 0, 1], [2, 2, 2, 0, 1], x, 2, 4)
     z = (x @ sd["fc.weight"].T).view(3, 2, 4)
     assert torch.allclose(out[0], z[0], atol=1e-6) and torch.allclose(out[1], z[1], atol=1e-6)
+
+
+FUSION_KEYS = ["Multi_DefectModel_new_GCN", "Multi_DefectModel", "myModels.Multi_DefectModel", "Multi_DefectModel_noGraph",
+               "Multi_DefectModel_000", "Multi_DefectModel_001", "Multi_DefectModel_100", "Multi_DefectModel_NOGAT2",
+               "Multi_DefectModel_noFunc", "Multi_DefectModel_noGlobalImage", "Multi_DefectModel_110",
+               "Multi_DefectModel_GATPOS", "Multi_DefectModel_011", "Multi_DefectModel_NOGAT", "Multi_DefectModel_NOGAT3",
+               "Multi_DefectModel_NOGAT4"]
+
+
+def test_fusion_class_golden_covers_every_class(golden):
+    assert sorted(golden["fusion_classes"]) == sorted(FUSION_KEYS) == sorted(k for k, *_ in cases.fusion_class_cases())
+
+
+@pytest.mark.parametrize("key", FUSION_KEYS)
+def test_fusion_class_oracle_matches_reference_class(golden, key):
+    """oracle.fusion.class_forward against the logits of the reference's OWN class (GraphModel.py / new_model.py /
+    myModels.py loaded unmodified from /root/reference by tools/make_golden.py fusion_classes, `dgl` stubbed with the
+    restated GATConv / unbatch / mean_nodes); the mirror class's state-dict keys are the ones the reference class
+    loaded with strict=True."""
+    ref = golden["fusion_classes"][key]
+    mirror = {k: c for k, _, _, c in cases.fusion_class_cases()}[key]
+    m = cases.fusion_class_model(key, mirror)
+    assert sorted(m.state_dict().keys()) == ref["keys"]
+    g, img, txt = cases.fusion_class_inputs()
+    got = fusion.class_forward(key, m.state_dict(), cases.to_host_batch(g), img, txt)
+    assert torch.allclose(got, ref["logits"], rtol=1e-4, atol=1e-4), (got, ref["logits"])
+
+
+def test_gru_restatement_matches_torch_gru():
+    """oracle.fusion.gru_last_state (checker of mvuld_gru_sequence) against torch.nn.GRU."""
+    torch.manual_seed(3)
+    gru = torch.nn.GRU(64, 64, 1, batch_first=True)
+    x = torch.randn(3, 37, 64)
+    with torch.no_grad():
+        _, hn = gru(x)
+    got = fusion.gru_last_state({"g." + k: v for k, v in gru.state_dict().items()}, "g.", x)
+    assert torch.allclose(got, hn[0], rtol=1e-5, atol=1e-5)
+
+
+# ---- second, independently written DGL restatement (oracle/dgl_ops_alt.py) against the first ----
+def _small_multigraph(seed):
+    """A small graph with parallel edges, self loops appended last and every node with an in-edge."""
+    g = torch.Generator().manual_seed(seed)
+    n = 23
+    src = torch.randint(0, n, (70,), generator=g)
+    dst = torch.randint(0, n, (70,), generator=g)
+    src = torch.cat([src, src[:9], torch.arange(n)])          # 9 duplicated (parallel) edges + the self loops
+    dst = torch.cat([dst, dst[:9], torch.arange(n)])
+    return src.numpy().astype(np.int64), dst.numpy().astype(np.int64), n
+
+
+def test_second_dgl_restatement_gatconv_dense_adjacency():
+    from oracle import dgl_ops_alt
+    src, dst, n = _small_multigraph(1)
+    torch.manual_seed(2)
+    H, Fo, Fi = 4, 24, 40
+    sd = {"fc.weight": torch.randn(H * Fo, Fi) * 0.2, "attn_l": torch.randn(1, H, Fo), "attn_r": torch.randn(1, H, Fo),
+          "bias": torch.randn(H * Fo)}
+    x = torch.randn(n, Fi)
+    a = dgl_ops.gat_conv(sd, "", src, dst, x, H, Fo)
+    b = dgl_ops_alt.gat_conv_dense(sd, "", src, dst, x, H, Fo)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-5), float((a - b).abs().max())
+    with pytest.raises(RuntimeError):                                      # a node without in-edges: both raise
+        dgl_ops_alt.gat_conv_dense(sd, "", src[:20], dst[:20], x, H, Fo)
+    with pytest.raises(RuntimeError):
+        dgl_ops.gat_conv(sd, "", src[:20], dst[:20], x, H, Fo)
+
+
+def test_second_dgl_restatement_gated_graph_conv_edge_loop():
+    from oracle import dgl_ops_alt
+    src, dst, n = _small_multigraph(3)
+    torch.manual_seed(4)
+    D, T, steps, Fi = 16, 3, 4, 10
+    et = torch.randint(0, T, (len(src),))
+    sd = {f"linears.{t}.weight": torch.randn(D, D) * 0.3 for t in range(T)}
+    sd.update({f"linears.{t}.bias": torch.randn(D) * 0.1 for t in range(T)})
+    cell = torch.nn.GRUCell(D, D)
+    sd.update({"gru.weight_ih": cell.weight_ih.detach(), "gru.weight_hh": cell.weight_hh.detach(),
+               "gru.bias_ih": cell.bias_ih.detach(), "gru.bias_hh": cell.bias_hh.detach()})
+    x = torch.randn(n, Fi)
+    a = dgl_ops.gated_graph_conv(sd, "", src, dst, et, x, D, steps, T)
+    b = dgl_ops_alt.gated_graph_conv_loop(sd, "", src, dst, et, x, D, steps, T)
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), float((a - b).abs().max())
+
+
+def test_second_dgl_restatement_index_artefacts_bit_exact():
+    from oracle import dgl_ops_alt
+    rng = np.random.default_rng(5)
+    raw = []
+    for n in (1, 7, 130, 2):                                                # one-node graph, one above the 100-slot cut
+        e = int(rng.integers(0, 3 * n + 1))
+        raw.append((rng.integers(0, n, e), rng.integers(0, n, e), n, torch.from_numpy(rng.integers(0, 4, e))))
+    graphs = []
+    for s, d, n, et in raw:
+        hg = dgl_ops.graph(s, d, n)
+        hg.edata["_ETYPE"] = et
+        hg.ndata["f"] = torch.from_numpy(rng.standard_normal((n, 6)).astype(np.float32))
+        graphs.append(dgl_ops.add_self_loop(hg))
+    hb = dgl_ops.batch(graphs)
+    S, D, T, bnn, bne = dgl_ops_alt.batch_with_self_loops_loop(raw)
+    assert np.array_equal(hb.src, S) and np.array_equal(hb.dst, D) and np.array_equal(hb.edata["_ETYPE"].numpy(), T)
+    assert np.array_equal(hb.batch_num_nodes, bnn) and np.array_equal(hb.batch_num_edges, bne)
+    ip, idx, eid = dgl_ops.in_csr(hb.src, hb.dst, hb.num_nodes)
+    ip2, idx2, eid2 = dgl_ops_alt.in_edges_loop(S, D, hb.num_nodes)
+    assert np.array_equal(ip, ip2) and np.array_equal(idx, idx2) and np.array_equal(eid, eid2)
+    a = dgl_ops.unbatch_pad(hb.ndata["f"], hb.batch_num_nodes, 100)
+    assert torch.equal(a, dgl_ops_alt.unbatch_pad_loop(hb.ndata["f"], bnn, 100))

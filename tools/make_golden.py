@@ -245,11 +245,117 @@ def golden_graph():
     print("ggnn prob", prob[:4])
 
 
+
+# --------------------------------------------------------------------------------------------------------
+# The reference's OWN fusion classes (GraphModel.py, new_model.py, myModels.py) run on CPU.  Their third-party
+# graph library is absent (dgl 0.8.1), so `dgl` is stubbed with the oracle's restatement of the
+# three calls the classes make (GATConv.forward, dgl.unbatch, dgl.mean_nodes); everything else -- the class
+# constructors, the Python unbatch / pad loops, the Rs_GCN module, the order and wiring of every layer -- is the
+# reference's code, unmodified, loaded from /root/reference.  Pins oracle.fusion.{fusion_forward, gat_variant_forward,
+# ablation_forward, variant2_forward, gating_forward} and the mirror classes' state-dict keys (strict load).
+# --------------------------------------------------------------------------------------------------------
+def _stub_dgl():
+    import contextlib
+    from oracle import dgl_ops
+
+    class _Sub:
+        def __init__(self, ndata):
+            self.ndata = ndata
+
+        def number_of_nodes(self):
+            return next(iter(self.ndata.values())).shape[0]
+
+    class RefGraph:
+        """What the reference forwards touch of a batched DGLGraph: ndata, local_scope, unbatch, mean_nodes."""
+
+        def __init__(self, hb):
+            self.hb = hb
+            self.ndata = dict(hb.ndata)
+
+        @contextlib.contextmanager
+        def local_scope(self):
+            saved = dict(self.ndata)
+            try:
+                yield
+            finally:
+                self.ndata = saved
+
+    def unbatch(g):
+        off = dgl_ops.node_offsets(g.hb.batch_num_nodes)
+        return [_Sub({k: v[off[i]:off[i + 1]] for k, v in g.ndata.items()}) for i in range(len(off) - 1)]
+
+    def mean_nodes(g, key):
+        return dgl_ops.mean_nodes(g.ndata[key], g.hb.batch_num_nodes)
+
+    class GATConv(nn.Module):
+        def __init__(self, in_feats, out_feats, num_heads, feat_drop=0., attn_drop=0., negative_slope=0.2):
+            super().__init__()
+            self.h, self.o, self.slope = num_heads, out_feats, negative_slope
+            self.fc = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+            self.attn_l = nn.Parameter(torch.zeros(1, num_heads, out_feats))
+            self.attn_r = nn.Parameter(torch.zeros(1, num_heads, out_feats))
+            self.bias = nn.Parameter(torch.zeros(num_heads * out_feats))
+
+        def forward(self, g, feat):
+            assert not self.training
+            return dgl_ops.gat_conv(self.state_dict(), "", g.hb.src, g.hb.dst, feat, self.h, self.o, self.slope)
+
+    dgl = types.ModuleType("dgl")
+    dgl.unbatch, dgl.mean_nodes = unbatch, mean_nodes
+    dnn = types.ModuleType("dgl.nn")
+    dpt = types.ModuleType("dgl.nn.pytorch")
+    dpt.GATConv, dpt.GraphConv, dpt.GatedGraphConv = GATConv, None, None
+    dgl.nn, dnn.pytorch = dnn, dpt
+    utils = types.ModuleType("utils")
+    for n in ("load_checkpoint", "auto_resume_helper", "reduce_tensor", "resume_bestf1_helper", "save_bestf1_checkpoint"):
+        setattr(utils, n, None)
+    sys.modules.update({"dgl": dgl, "dgl.nn": dnn, "dgl.nn.pytorch": dpt, "utils": utils})
+    return RefGraph
+
+
+def _load_ref_models():
+    """GraphModel / new_model / myModels of the reference as submodules of a synthetic package whose unrelated
+    siblings (`.build`, `.fusion`, the other Swin files) are empty stubs."""
+    RefGraph = _stub_dgl()
+    _shim_timm()
+    pkg = types.ModuleType("refmodels")
+    pkg.__path__ = [os.path.join(REF, "mvuld", "models")]
+    sys.modules["refmodels"] = pkg
+    for stub in ("build", "fusion", "swin_transformer_v2"):
+        sys.modules[f"refmodels.{stub}"] = types.ModuleType(f"refmodels.{stub}")
+    mods = {}
+    for name in ("GraphModel", "new_model", "myModels"):
+        mods[name] = importlib.import_module(f"refmodels.{name}")
+    return RefGraph, mods
+
+
+@torch.no_grad()
+def golden_fusion_classes():
+    from tests.cases import to_host_batch, fusion_class_cases, fusion_class_inputs, fusion_class_model, FUSION_CLASS_BATCH
+    RefGraph, mods = _load_ref_models()
+    g, img, txt = fusion_class_inputs()
+    hb = to_host_batch(g)
+    out = {}
+    for key, modname, clsname, mirror in fusion_class_cases():
+        m = fusion_class_model(key, mirror)
+        ref = getattr(mods[modname], clsname)(mv.default_config()).eval()
+        ref.load_state_dict(m.state_dict(), strict=True)                # pins the mirror's key set and shapes
+        rg = RefGraph(hb)
+        rg.ndata["_ALL_NODE_EMB"] = torch.zeros(hb.num_nodes, 800)     # read and never used by myModels.py:357
+        logits = ref(rg, img.clone(), txt.clone())
+        assert logits.shape == (FUSION_CLASS_BATCH, 2) and torch.isfinite(logits).all(), key
+        out[key] = dict(logits=logits.clone(), keys=sorted(m.state_dict().keys()))
+        print(f"{key:36s}", logits[0].tolist())
+    torch.save(out, os.path.join(OUT, "fusion_classes.pt"))
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     if "rs_gcn_train" in sys.argv[1:]:
         golden_rs_gcn_train()
+        sys.exit(0)
+    if "fusion_classes" in sys.argv[1:]:
+        golden_fusion_classes()
         sys.exit(0)
     if "swin_train" in sys.argv[1:] or "roberta_train" in sys.argv[1:]:
         if "swin_train" in sys.argv[1:]:
