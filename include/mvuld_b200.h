@@ -43,6 +43,12 @@ int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N
 int mvuld_gemm_ln_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                        const float* gamma, const float* beta, float eps, const float* shortcut_f32, float* x32,
                        void* xb, mvuld_stream_t stream);
+/* Same contract for rows wider than one CTA can double-buffer in TMEM: N in {512, 768, 1024}; a thread-block cluster of
+ * N / 256 CTAs owns a 128-row tile, each CTA one 256-column block, row statistics exchanged through distributed shared
+ * memory (swin_transformer_v2.py:301,304; shortcut may be null: PatchMerging :361-362). */
+int mvuld_gemm_ln_wide_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                            const float* gamma, const float* beta, float eps, const float* shortcut_f32, float* x32,
+                            void* xb, mvuld_stream_t stream);
 
 /* SwinV2 qkv projection fused with: cat(q_bias, 0, v_bias), per-head L2 normalisation of q and k, the learnable
  * logit scale (qscale[h] = exp(min(logit_scale_h, ln 100)) * log2 e, folded into q), window partition and cyclic
@@ -222,8 +228,6 @@ int mvuld_gather_etype(const long long* etype, const int* eids, int E, int n_ety
  * DGL GatedGraphConv message + reduce (baselines/models/reveal/ggnn/model.py:23, devign/model.py:35). */
 int mvuld_ggnn_gather_sum(const void* msgs, const int* indptr, const int* idx_src, const unsigned char* etype,
                           void* out, int ldo, int N, int T, int D, mvuld_stream_t stream);
-/* GRUCell gates, in place on h32 (+ bf16 shadow). gi, gh bf16 [N, 3D].  (Unfused form; the models use mvuld_gemm_gru.) */
-int mvuld_gru_gates(const void* gi, const void* gh, float* h32, void* hb, long long N, int D, mvuld_stream_t stream);
 /* GRUCell of GatedGraphConv as ONE GEMM with the gates in its epilogue: A = [a | h] bf16 [M, K = 2D] (row stride lda),
  * Wg bf16 [4D, K] with rows 4j..4j+3 = (W_ir | W_hr), (W_iz | W_hz), (W_in | 0), (0 | W_hn) of feature j, bias4 fp32
  * [4D] = (b_ir + b_hr, b_iz + b_hz, b_in, b_hn) interleaved; h32 fp32 [M, D] updated in place, the bf16 state is
@@ -254,19 +258,15 @@ int mvuld_f32_to_bf16(const float* in, void* out, long long n, mvuld_stream_t st
 /* ------------------------------------------------------------------------------------------------------------
  * Fusion branch.
  * ---------------------------------------------------------------------------------------------------------- */
-/* Rs_GCN.py:57-66: tpg bf16 [B*n, 3C] = (theta | phi | g); y = (theta phi^T / n) g, bf16 [B*n, C]; r_out optional
- * fp32 [B, n, n] (the affinity the reference returns). */
-int mvuld_rs_gcn_affinity(const void* tpg, void* y, float* r_out, int B, int n, int C, mvuld_stream_t stream);
-/* The variant the models use: tpg fp32 [B*n, 3C]; y3 = bf16x3 split operand [B*n, 3C] = (hi | lo | hi) of the fp32 y,
+/* Rs_GCN.py:57-66: tpg fp32 [B*n, 3C] = (theta | phi | g); y = (theta phi^T / n) g; r_out optional fp32 [B, n, n] (the
+ * affinity the reference returns).  y3 = bf16x3 split operand [B*n, 3C] = (hi | lo | hi) of the fp32 y,
  * to be multiplied against a (W_hi | W_hi | W_lo) weight (mvuld_split3_bf16, w_side = 1): fp32-class products on the
  * bf16 tensor-core GEMM.  Rs_GCN has no softmax and feeds a BatchNorm: plain bf16 operands cost 1-2 % per block. */
 int mvuld_rs_gcn_affinity_f32(const float* tpg, void* y3, float* r_out, int B, int n, int C, mvuld_stream_t stream);
 /* x fp32 [R, C] (row stride ldx) -> out bf16 [R, 3C]: (hi | lo | hi) for w_side == 0, (hi | hi | lo) otherwise. */
 int mvuld_split3_bf16(const float* x, int ldx, void* out, int R, int C, int w_side, mvuld_stream_t stream);
-/* GraphModel.py:200-209: l2norm(dim=1) + mean + concat + BN(folded) + Linear -> logits fp32 [B, num_classes]. */
-int mvuld_fusion_head(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
-                      float* logits, float* feat_out, int B, int n, int D, int num_classes, mvuld_stream_t stream);
-/* Same kernel for the RQ2 ablations (mvuld/models/new_model.py): mode 0 = cat(img, graph, txt) as above; mode 1 =
+/* GraphModel.py:200-209: l2norm(dim=1) + mean + concat + BN(folded) + Linear -> logits fp32 [B, num_classes].
+ * Same kernel for the RQ2 ablations (mvuld/models/new_model.py): mode 0 = cat(img, graph, txt) as above; mode 1 =
  * cat(img, graph), wf [num_classes, 2D] (Multi_DefectModel_noFunc, new_model.py:317-318); mode 2 = txt * graph,
  * wf [num_classes, D] (Multi_DefectModel_noGlobalImage, new_model.py:196-197).  feat_out (optional) has that width. */
 int mvuld_fusion_head_mode(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
@@ -396,12 +396,6 @@ int mvuld_sumsq_f32(const float* x, long long n, float* partials, float* out, mv
 int mvuld_adamw(float* p, const float* g, float* m, float* v, long long n, const long long* seg_end,
                 const float* seg_wd, int nseg, const float* gnorm_sq, float max_norm, float lr, float beta1,
                 float beta2, float eps, int step, mvuld_stream_t stream);
-
-/* Test hook: one TMA box per operand, nk tcgen05.mma K-steps, accumulator dumped (see csrc/probe.cu). */
-int mvuld_probe_umma(const void* A, int a_inner, int a_rows, int a_swizzle, const void* B, int b_inner, int b_rows,
-                     int b_swizzle, int N, int nk, int a_step, int b_step, int a_lbo, int a_sbo, int a_layout,
-                     int b_lbo, int b_sbo, int b_layout, int a_mn, int b_mn, int fmt, float* out,
-                     mvuld_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libmvuld_b200.so")
+PROBE_LIB = os.path.join(HERE, "libmvuld_probe.so")          # test fixture (csrc/testlib), not part of the product library
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -81,7 +82,19 @@ def build(verbose: bool = False, force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    _build_probe(digest, verbose, os.path.join(OBJDIR, "host_util.o"))
     return LIB
+
+
+def _build_probe(digest: str, verbose: bool, host_util_obj: str) -> str:
+    """The UMMA / TMA layout probe the kernel tests use: one more .so next to the product library."""
+    obj = _compile_one(os.path.join(CSRC, "testlib", "probe.cu"), digest, verbose)
+    if not os.path.exists(PROBE_LIB) or os.path.getmtime(PROBE_LIB) < max(os.path.getmtime(obj), os.path.getmtime(host_util_obj)):
+        cmd = [_nvcc(), "-shared", "-o", PROBE_LIB, obj, host_util_obj, "-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return PROBE_LIB
 
 
 if __name__ == "__main__":

@@ -21,6 +21,7 @@ _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "mvuld_gemm_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P],
     "mvuld_gemm_ln_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
+    "mvuld_gemm_ln_wide_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
     "mvuld_swin_qkv": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_heads_qkv": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "mvuld_cpb_table": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
@@ -56,7 +57,6 @@ SIGNATURES = {
     "mvuld_gather_etype": [_P, _P, _I, _I, _P, _P, _P],
     "mvuld_ggnn_gather_sum": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_gemm_gru": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
-    "mvuld_gru_gates": [_P, _P, _P, _P, _LL, _I, _P],
     "mvuld_ggnn_init": [_P, _P, _P, _I, _LL, _I, _I, _P],
     "mvuld_segment_sum": [_P, _P, _P, _I, _I, _P],
     "mvuld_gat_scores": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
@@ -67,10 +67,8 @@ SIGNATURES = {
     "mvuld_collate_edges": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _LL, _P, _P],
     "mvuld_seq_attention_packed": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_seq_segment_mean": [_P, _P, _P, _P, _P, _I, _I, _P],
-    "mvuld_rs_gcn_affinity": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_rs_gcn_affinity_f32": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_split3_bf16": [_P, _I, _P, _I, _I, _I, _P],
-    "mvuld_fusion_head": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvuld_fusion_head_mode": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_transpose_bf16": [_P, _I, _P, _I, _I, _I, _P],
@@ -104,7 +102,6 @@ SIGNATURES = {
     "mvuld_gru_sequence_workspace": [_I, _I],
     "mvuld_gru_sequence": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_gate_fusion": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "mvuld_probe_umma": [_P, _I, _I, _I, _P, _I, _I, _I] + [_I] * 13 + [_P, _P],
 }
 
 _SYNC_EACH = bool(os.environ.get("MVULD_SYNC_EACH"))     # debug: synchronise after every call and name the one that faulted
@@ -252,6 +249,18 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, gamma, beta, eps: float, bias=None
     for t in (shortcut, x32, xb):
         assert t is None or (t.is_contiguous() and t.shape == (M, N))
     call("mvuld_gemm_ln_bf16", _Raw(a), a.stride(0), _Raw(w), w.stride(0), M, N, K, bias, gamma, beta, float(eps),
+         shortcut, x32, xb)
+
+
+def gemm_ln_wide(a: torch.Tensor, w: torch.Tensor, gamma, beta, eps: float, bias=None, shortcut=None, x32=None, xb=None):
+    """N = w.shape[0] in {512, 768, 1024}: x = shortcut + LayerNorm(a @ w.T + bias) * gamma + beta in one cluster launch
+    (csrc/gemm_ln_cluster.cu)."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    for t in (shortcut, x32, xb):
+        assert t is None or (t.is_contiguous() and t.shape == (M, N))
+    call("mvuld_gemm_ln_wide_bf16", _Raw(a), a.stride(0), _Raw(w), w.stride(0), M, N, K, bias, gamma, beta, float(eps),
          shortcut, x32, xb)
 
 

@@ -1281,7 +1281,7 @@ static int swin_window_attention(const void* q, const void* k, const void* v, co
   p.kv_len = nullptr;
   p.out = out;
   p.lse = lse;
-  p.no_split = getenv("MVULD_ATT_NOSPLIT") != nullptr;
+  p.no_split = false;
   const int n_bh = B * (H / ws) * (W / ws) * nH;
   switch (ws) {
     case 28: return launch_attn<MODE_SWIN, 32, 28, 112, true>(q, k, v, n_bh, p, stream);

@@ -281,26 +281,12 @@ extern "C" int mvuld_linear_small(const float* x, const float* w, const float* b
   return 0;
 }
 
-extern "C" int mvuld_rs_gcn_affinity(const void* tpg, void* y, float* r_out, int B, int n, int C,
-                                     cudaStream_t stream) {
-  MV_CHECK_ARG(n >= 1 && n <= RS_MAXN, "rs_gcn_affinity: n must be in [1, %d]", RS_MAXN);
-  MV_CHECK_ARG(C % 64 == 0, "rs_gcn_affinity: C %% 64");
-  if (B <= 0) return 0;
-  const int smem = (RS_MAXN * (RS_MAXN + 1) + RS_MAXN * 64 + RS_MAXN * 33) * sizeof(float);
-  auto kern = rs_gcn_affinity_kernel<bf16, false>;
-  MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<dim3(B, B >= 148 ? 2 : 4), 256, smem, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<bf16*>(y), r_out, n, C);
-  MV_LAUNCH_OK();
-  return 0;
-}
-
 extern "C" int mvuld_rs_gcn_affinity_f32(const float* tpg, void* y3, float* r_out, int B, int n, int C,
                                          cudaStream_t stream) {
   MV_CHECK_ARG(n >= 1 && n <= RS_MAXN, "rs_gcn_affinity_f32: n must be in [1, %d]", RS_MAXN);
   MV_CHECK_ARG(C % 64 == 0, "rs_gcn_affinity_f32: C %% 64");
   if (B <= 0) return 0;
-  static const bool col_split = getenv("MVULD_AFFINITY_COLSPLIT") != nullptr;       // A/B hook: the earlier kernel
-  if (C % AR_GCH == 0 && !col_split) {
+  if (C % AR_GCH == 0) {
     auto kern = rs_gcn_affinity_rows_kernel;
     MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
     kern<<<dim3(B, (n + AR_ROWS - 1) / AR_ROWS), 256, AR_SMEM_BYTES, stream>>>(tpg, reinterpret_cast<bf16*>(y3), r_out, n, C);
@@ -334,10 +320,4 @@ extern "C" int mvuld_fusion_head_mode(const float* z, const float* img, const fl
                                                                num_classes, mode);
   MV_LAUNCH_OK();
   return 0;
-}
-
-extern "C" int mvuld_fusion_head(const float* z, const float* img, const float* txt, const float* wf, const float* bf,
-                                 float* logits, float* feat_out, int B, int n, int D, int num_classes,
-                                 cudaStream_t stream) {
-  return mvuld_fusion_head_mode(z, img, txt, wf, bf, logits, feat_out, B, n, D, num_classes, 0, stream);
 }

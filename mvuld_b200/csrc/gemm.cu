@@ -599,7 +599,7 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
     EpiBf16Tma t;
     t.bias = bias; t.act = act; t.M = M; t.N = N;
     // skinny-K, tall-M problems keep the weight panel resident (see GemmCfg)
-    const bool ws = K <= 256 && (long long)M >= 128ll * 2 * num_sms() && getenv("MVULD_GEMM_NO_WS") == nullptr;
+    const bool ws = K <= 256 && (long long)M >= 128ll * 2 * num_sms();
     // (measured neutral for the 128 x 256 tiles of the Swin stage-0 / 1 layers, whose GELU epilogue sets the pace)
     if (big) return launch_gemm<256, 4, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
     if (ws) return launch_gemm<128, 6, EpiBf16Tma, 4>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
@@ -621,7 +621,7 @@ extern "C" int mvuld_gemm_gru(const void* A, int lda, const void* Wg, int ldw, i
   MV_CHECK_ARG((const void*)hb_out != A, "gemm_gru: the bf16 state must be written to another buffer than A");
   EpiGru e;
   e.bias4 = bias4; e.h32 = h32; e.hb = reinterpret_cast<bf16*>(hb_out); e.ldhb = ldhb; e.M = M; e.D = D;
-  if (K <= 448 && (long long)M >= 128ll * 2 * num_sms() && getenv("MVULD_GEMM_NO_WS") == nullptr)
+  if (K <= 448 && (long long)M >= 128ll * 2 * num_sms())
     return launch_gemm<128, 4, EpiGru, 7>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
   return launch_gemm<128, 6, EpiGru>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
 }

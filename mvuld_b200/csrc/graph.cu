@@ -144,45 +144,6 @@ ggnn_gather_sum_kernel(const bf16* __restrict__ msgs, const int* __restrict__ in
   while (cur < n_nodes) flush();            // the last node (and any trailing nodes without in-edges)
 }
 
-// GRUCell gates (torch order r, z, n):  h' = (1 - z) * tanh(i_n + r * h_n) + z * h
-__global__ void gru_gates_kernel(const bf16* __restrict__ gi, const bf16* __restrict__ gh, float* __restrict__ h32,
-                                 bf16* __restrict__ hb, long long N, int D) {
-  const int units = D >> 3;
-  const long long total = N * units;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long n = i / units;
-    const int u = (int)(i % units);
-    const uint4* gip = reinterpret_cast<const uint4*>(gi + n * 3 * D);
-    const uint4* ghp = reinterpret_cast<const uint4*>(gh + n * 3 * D);
-    const uint4 ir = __ldg(gip + u), iz = __ldg(gip + units + u), in_ = __ldg(gip + 2 * units + u);
-    const uint4 hr = __ldg(ghp + u), hz = __ldg(ghp + units + u), hn = __ldg(ghp + 2 * units + u);
-    float4* hp = reinterpret_cast<float4*>(h32 + n * D + u * 8);
-    float4 h0 = hp[0], h1 = hp[1];
-    float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    const uint32_t a_ir[4] = {ir.x, ir.y, ir.z, ir.w}, a_iz[4] = {iz.x, iz.y, iz.z, iz.w};
-    const uint32_t a_in[4] = {in_.x, in_.y, in_.z, in_.w}, a_hr[4] = {hr.x, hr.y, hr.z, hr.w};
-    const uint32_t a_hz[4] = {hz.x, hz.y, hz.z, hz.w}, a_hn[4] = {hn.x, hn.y, hn.z, hn.w};
-    float o[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int w = q >> 1;
-      const bool hi = q & 1;
-      auto get = [&](const uint32_t* a) { return hi ? bf16_hi(a[w]) : bf16_lo(a[w]); };
-      const float r = 1.f / (1.f + __expf(-(get(a_ir) + get(a_hr))));
-      const float z = 1.f / (1.f + __expf(-(get(a_iz) + get(a_hz))));
-      const float nn = tanhf(get(a_in) + r * get(a_hn));
-      o[q] = (1.f - z) * nn + z * h[q];
-    }
-    hp[0] = make_float4(o[0], o[1], o[2], o[3]);
-    hp[1] = make_float4(o[4], o[5], o[6], o[7]);
-    uint4 ob;
-    ob.x = pack_bf16x2(o[0], o[1]); ob.y = pack_bf16x2(o[2], o[3]);
-    ob.z = pack_bf16x2(o[4], o[5]); ob.w = pack_bf16x2(o[6], o[7]);
-    reinterpret_cast<uint4*>(hb + n * D)[u] = ob;
-  }
-}
-
 // h0 = cat(x, zeros[N, D - in]) (GatedGraphConv zero-pad) -> fp32 state + bf16 shadow
 __global__ void ggnn_init_kernel(const float* __restrict__ x, float* __restrict__ h32, bf16* __restrict__ hb, int ldb,
                                  long long N, int in_dim, int D) {
@@ -510,21 +471,8 @@ extern "C" int mvuld_ggnn_gather_sum(const void* msgs, const int* indptr, const 
   bf16* op = reinterpret_cast<bf16*>(out);
   // 4 row loads in flight per lane at 48 registers / 5 blocks per SM: measured 334 us on configs[2] (6.0 TB/s of
   // algorithmic bytes) against 430 us for 8 in flight at 78 registers / 3 blocks -- occupancy hides the gather latency
-  // better than per-warp depth.  MVULD_GGNN_VARIANT=1 launches the deeper variant for A/B runs.
-  static const bool deep = getenv("MVULD_GGNN_VARIANT") != nullptr && atoi(getenv("MVULD_GGNN_VARIANT")) == 1;
-  if (deep) ggnn_gather_sum_kernel<8, 8><<<(N + 63) / 64, 256, 0, stream>>>(mp, indptr, idx_src, etype, op, ldo, N, T, D);
-  else ggnn_gather_sum_kernel<4, 8, 5><<<(N + 63) / 64, 256, 0, stream>>>(mp, indptr, idx_src, etype, op, ldo, N, T, D);
-  MV_LAUNCH_OK();
-  return 0;
-}
-
-extern "C" int mvuld_gru_gates(const void* gi, const void* gh, float* h32, void* hb, long long N, int D,
-                               cudaStream_t stream) {
-  MV_CHECK_ARG(D % 8 == 0, "gru_gates: D %% 8");
-  if (N <= 0) return 0;
-  gru_gates_kernel<<<grid_for(N * (D / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(gi),
-                                                                    reinterpret_cast<const bf16*>(gh), h32,
-                                                                    reinterpret_cast<bf16*>(hb), N, D);
+  // better than per-warp depth.
+  ggnn_gather_sum_kernel<4, 8, 5><<<(N + 63) / 64, 256, 0, stream>>>(mp, indptr, idx_src, etype, op, ldo, N, T, D);
   MV_LAUNCH_OK();
   return 0;
 }

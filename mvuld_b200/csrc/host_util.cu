@@ -2,6 +2,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -37,8 +38,64 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Encoded tensor maps are pure functions of (pointer, geometry): a forward pass re-launches the same few hundred
+// (buffer, shape) pairs every step (workspaces and weights keep their addresses), so the encodings are kept in a small
+// per-thread direct-mapped cache instead of going through the driver on every launch.
+namespace {
+struct TmapKey {
+  const void* ptr;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  int rank, swizzle;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int kTmapSlots = 2048;
+}  // namespace
+
+static int encode_tmap_16b(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
 int make_tmap_16b(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int swizzle_bytes) {
+  if (rank < 1 || rank > 5) return fail(-1, "TMA rank %d out of range", rank);
+  static thread_local TmapSlot* cache = nullptr;
+  if (!cache) cache = static_cast<TmapSlot*>(calloc(kTmapSlots, sizeof(TmapSlot)));
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.rank = rank; key.swizzle = swizzle_bytes;
+  uint64_t h = reinterpret_cast<uintptr_t>(ptr) * 0x9E3779B97F4A7C15ull + (uint64_t)swizzle_bytes * 31 + rank;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    h = (h ^ dims[i]) * 0x100000001B3ull;
+    h = (h ^ box[i]) * 0x100000001B3ull;
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    key.strides[i] = strides_bytes[i];
+    h = (h ^ strides_bytes[i]) * 0x100000001B3ull;
+  }
+  TmapSlot* slot = cache ? &cache[(h >> 20) % kTmapSlots] : nullptr;
+  if (slot && slot->valid && slot->key == key) {
+    *out = slot->map;
+    return 0;
+  }
+  int rc = encode_tmap_16b(out, ptr, rank, dims, strides_bytes, box, swizzle_bytes);
+  if (rc == 0 && slot) {
+    slot->key = key;
+    slot->map = *out;
+    slot->valid = true;
+  }
+  return rc;
+}
+
+static int encode_tmap_16b(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(-2, "cuTensorMapEncodeTiled not available from the driver");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-1, "TMA base pointer not 16-byte aligned");

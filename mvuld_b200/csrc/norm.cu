@@ -359,10 +359,9 @@ extern "C" int mvuld_ln_rows(const void* y, const float* shortcut, const float* 
   const bf16* yp = reinterpret_cast<const bf16*>(y);
   bf16* xp = reinterpret_cast<bf16*>(xb);
   const int grid = (M + 7) / 8;
-  static const bool wide = getenv("MVULD_LN_WIDE") != nullptr;                 // A/B hook: the 4-unit instantiation for every C
-  if (C <= 256 && !wide) ln_rows_kernel<1><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
-  else if (C <= 512 && !wide) ln_rows_kernel<2><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
-  else if (C <= 768 && !wide) ln_rows_kernel<3><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
+  if (C <= 256) ln_rows_kernel<1><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
+  else if (C <= 512) ln_rows_kernel<2><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
+  else if (C <= 768) ln_rows_kernel<3><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
   else ln_rows_kernel<4><<<grid, 256, 0, stream>>>(yp, shortcut, gamma, beta, x32, xp, M, C, eps, mode);
   MV_LAUNCH_OK();
   return 0;

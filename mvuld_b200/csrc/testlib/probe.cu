@@ -1,9 +1,10 @@
 // Single-tile UMMA probe: one TMA box for A, one for B, `nk` tcgen05.mma K-steps with caller-chosen descriptor
 // parameters, accumulator dumped as fp32 [128, N].  Used by tests/ to pin every shared-memory layout the GEMM
 // and attention kernels rely on (K-major SW128 / SW64, MN-major SW64 / SW128, fp16 and bf16 operands)
-// independently of the big kernels.
-#include "common.cuh"
-#include "host_util.h"
+// independently of the big kernels.  Test fixture: built into its own library (libmvuld_probe.so), not into the product
+// libmvuld_b200.so.
+#include "../common.cuh"
+#include "../host_util.h"
 
 namespace mv {
 

@@ -1260,8 +1260,7 @@ extern "C" int mvuld_rs_gcn_affinity_bwd(const void* tpg, const void* dy, void* 
                                          cudaStream_t stream) {
   MV_CHECK_ARG(n >= 1 && n <= AB_N && C % 64 == 0, "rs_gcn_affinity_bwd: n in [1, %d], C %% 64", AB_N);
   if (B <= 0) return 0;
-  static const bool col_split = getenv("MVULD_AFFINITY_COLSPLIT") != nullptr;       // A/B hook: the earlier kernel
-  if (C % AR_GCH == 0 && !col_split) {
+  if (C % AR_GCH == 0) {
     MV_CUDA_OK(cudaFuncSetAttribute(rs_gcn_affinity_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM_BYTES));
     rs_gcn_affinity_bwd_rows_kernel<<<dim3(B, (n + AR_ROWS - 1) / AR_ROWS, 3), 256, AR_SMEM_BYTES, stream>>>(reinterpret_cast<const bf16*>(tpg), reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(dtpg), n, C);
     MV_LAUNCH_OK();

@@ -201,8 +201,8 @@ class _AblationBase(nn.Module):
                       p["fc_bbox"][1], z32, zb, B, n, 32, 512, 480)
         if self.GCN:                                                   # Rs_GCN x 8, l2norm over slots, mean, head
             run_rs_gcn_chain(p["gcn"], z32, B, n)
-            _lib.call("mvuld_fusion_head", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
-                      self.num_classes)
+            _lib.call("mvuld_fusion_head_mode", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
+                      self.num_classes, 0)
         else:                                                          # plain mean over the slots (GraphModel.py:610)
             start = torch.arange(B, device=dev, dtype=torch.int32) * n
             length = torch.full((B,), n, device=dev, dtype=torch.int32)
@@ -473,8 +473,8 @@ class _GridBase(nn.Module):
         logits = e((B, self.num_classes), f32)
         if self.GCN:
             run_rs_gcn_chain(p["gcn"], z32, B, n)
-            _lib.call("mvuld_fusion_head", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
-                      self.num_classes)
+            _lib.call("mvuld_fusion_head_mode", z32, ximg, xtxt, p["final"][0], p["final"][1], logits, None, B, n, 512,
+                      self.num_classes, 0)
         else:
             start = torch.arange(B, device=dev, dtype=torch.int32) * n
             length = torch.full((B,), n, device=dev, dtype=torch.int32)

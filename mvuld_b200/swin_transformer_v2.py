@@ -382,11 +382,18 @@ class SwinTransformerV2(nn.Module):
                     _lib.gemm_ln(hid, blk["wfc2"], blk["g2"], blk["b2"], blk["eps2"], bias=blk["bfc2"], shortcut=x32,
                                  x32=x32, xb=xb)
                 else:
+                    # C = 512 / 1024: proj (K = C) stays GEMM + LayerNorm pass (the fused epilogue is the longer pole at
+                    # short K: 92 vs 87 us at 64 images); fc2 (K = 4 C) runs on the cluster kernel -- a 2 / 4 CTA cluster
+                    # per 128-row tile, row statistics over distributed shared memory (127 vs 142 us)
                     _lib.gemm(att, blk["wproj"], bias=blk["bproj"], out_bf16=y)
                     _lib.call("mvuld_ln_rows", y, x32, blk["g1"], blk["b1"], x32, xb, M, C, float(blk["eps1"]), 1)
                     _lib.gemm(xb, blk["wfc1"], bias=blk["bfc1"], act=_lib.ACT_GELU, out_bf16=hid)
-                    _lib.gemm(hid, blk["wfc2"], bias=blk["bfc2"], out_bf16=y)
-                    _lib.call("mvuld_ln_rows", y, x32, blk["g2"], blk["b2"], x32, xb, M, C, float(blk["eps2"]), 1)
+                    if C in (512, 1024):
+                        _lib.gemm_ln_wide(hid, blk["wfc2"], blk["g2"], blk["b2"], blk["eps2"], bias=blk["bfc2"],
+                                          shortcut=x32, x32=x32, xb=xb)
+                    else:
+                        _lib.gemm(hid, blk["wfc2"], bias=blk["bfc2"], out_bf16=y)
+                        _lib.call("mvuld_ln_rows", y, x32, blk["g2"], blk["b2"], x32, xb, M, C, float(blk["eps2"]), 1)
             if layer.downsample is not None:
                 mg = p["merge"][li]
                 H, W, C = mg["H"], mg["W"], mg["C"]
@@ -398,6 +405,8 @@ class SwinTransformerV2(nn.Module):
                 xb = w["xb"][:M2 * 2 * C].view(M2, 2 * C)
                 if 2 * C <= 512:
                     _lib.gemm_ln(gathered, mg["w"], mg["g"], mg["b"], mg["eps"], x32=x32, xb=xb)
+                elif 2 * C == 1024:
+                    _lib.gemm_ln_wide(gathered, mg["w"], mg["g"], mg["b"], mg["eps"], x32=x32, xb=xb)
                 else:
                     y = w["y"][:M2 * 2 * C].view(M2, 2 * C)
                     _lib.gemm(gathered, mg["w"], out_bf16=y)
