@@ -276,7 +276,6 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint8_t* box = sSc + (half * GLC_SC_SLOTS + slot) * GLC_SC_BYTES + quarter * 32 * 64;
 #pragma unroll
           for (int k = 0; k < 4; ++k) sc[k] = *reinterpret_cast<const float4*>(box + (8 * k + rsub) * 64 + c4 * 16);
-          mbar_arrive(&sc_empty[half * GLC_SC_SLOTS + slot]);
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k) sc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -297,6 +296,11 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (ep.xb) *reinterpret_cast<uint2*>(ep.xb + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
           }
         }
+        // The ring slot is released only HERE, after the values read from it have been consumed by the stores above.
+        // Arriving right after issuing the ld.shared let the TMA refill the slot before the loads had read it (an
+        // mbarrier arrive does not wait for the thread's outstanding shared-memory loads): under memory pressure from
+        // another stream a few rows then received the residual of a later chunk.
+        if (ep.shortcut) mbar_arrive(&sc_empty[half * GLC_SC_SLOTS + nsc % GLC_SC_SLOTS]);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);

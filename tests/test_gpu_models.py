@@ -425,3 +425,26 @@ def test_swin_sub_batches_on_streams_give_identical_features():
     assert torch.equal(one, two)
     again = model.forward_features(x)
     assert torch.equal(one, again)
+
+
+@pytest.mark.parametrize("B", [4, 16])
+def test_cuda_graph_replay_with_concurrent_branches_is_bit_identical(B):
+    """mvuld_b200.graphs.GraphedMVulD: the image and padded-text branches replayed from CUDA graphs on two side streams
+    while the graph branch runs eagerly -- same launches, so the logits equal the single-stream eager forward bit for
+    bit, on every replay.  (At 16 functions the SwinV2 cluster kernels run next to the text encoder's kernels: the case
+    that exposed an early release of the residual ring in csrc/gemm_ln_cluster.cu.)"""
+    from mvuld_b200.graphs import GraphedMVulD
+    torch.manual_seed(cases.SEED)
+    model = mv.MVulD(mv.default_config()).eval()
+    synth.randomize_for_parity(model, seed=777)
+    model = model.to(DEV)
+    img, ids = synth.images(B, 448, seed=B).to(DEV), synth.token_ids(B, 512, seed=B).to(DEV)
+    g = synth.cpg_batch(B, seed=B)
+    g.ndata.pop("_FUNC_EMB", None)
+    g = g.to(DEV)
+    want = model(img, ids, g).clone()
+    fast = GraphedMVulD(model, concurrent_below=64)
+    for _ in range(6):
+        assert torch.equal(fast(img, ids, g), want)
+    seq = GraphedMVulD(model, concurrent_below=0)
+    assert torch.equal(seq(img, ids, g), want)
