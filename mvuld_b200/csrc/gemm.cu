@@ -333,7 +333,7 @@ struct epi_prefetch<E, std::void_t<decltype(E::kPrefetch)>> : std::true_type { u
 // panel resident in shared memory (loaded once), owns one column block and walks row blocks, so only A streams through
 // the ring.  With the streaming schedule a 128 x 128 tile at K = 448 pulls 114 KB of A and 114 KB of W through L2 for
 // 32 KB of output; the GGNN GEMMs (M = 825 k, K = 200 / 400) sat at 8.4 TB/s of L2 traffic, not at HBM or MMA limits.
-template <int BN, int STAGES, int BKB = 0>
+template <int BN, int STAGES, int BKB = 0, bool STAGED_C = true>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
@@ -341,7 +341,8 @@ struct GemmCfg {
   static constexpr int B_TOTAL = (BKB > 0 ? BKB : STAGES) * B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SLAB_BYTES = 32 * 128;                                  // [32 rows x 64 bf16] per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * A_BYTES + B_TOTAL + GEMM_EPI_WARPS * SLAB_BYTES + BAR_BYTES + 1024;
+  static constexpr int SLABS_BYTES = STAGED_C ? GEMM_EPI_WARPS * SLAB_BYTES : 0;   // only the TMA-store epilogues stage C
+  static constexpr int SMEM_BYTES = STAGES * A_BYTES + B_TOTAL + SLABS_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;                                    // 256 or 512 (power of two)
 };
 
@@ -349,14 +350,14 @@ template <int BN, int STAGES, class Epi, int BKB = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
-  using Cfg = GemmCfg<BN, STAGES, BKB>;
+  using Cfg = GemmCfg<BN, STAGES, BKB, Epi::kStaged>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* sC = smem + STAGES * Cfg::A_BYTES + Cfg::B_TOTAL;            // staged epilogue slabs (kStaged only)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sC + GEMM_EPI_WARPS * Cfg::SLAB_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sC + Cfg::SLABS_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -537,7 +538,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int STAGES, class Epi, int BKB = 0>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi,
                        cudaStream_t stream, void* out_bf16 = nullptr, int ldc = 0) {
-  using Cfg = GemmCfg<BN, STAGES, BKB>;
+  using Cfg = GemmCfg<BN, STAGES, BKB, Epi::kStaged>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "GEMM configuration exceeds the 227 KB of shared memory per CTA");
   MV_CHECK_ARG(BKB == 0 || K <= BKB * GEMM_BK, "gemm: weight-stationary schedule holds K <= %d (K=%d)", BKB * GEMM_BK, K);
   MV_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -602,7 +603,7 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
     const bool ws = K <= 256 && (long long)M >= 128ll * 2 * num_sms();
     // (measured neutral for the 128 x 256 tiles of the Swin stage-0 / 1 layers, whose GELU epilogue sets the pace)
     if (big) return launch_gemm<256, 4, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
-    if (ws) return launch_gemm<128, 6, EpiBf16Tma, 4>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
+    if (ws) return launch_gemm<128, 8, EpiBf16Tma, 4>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
     return launch_gemm<128, 6, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
   }
   EpiGeneric e;
@@ -622,7 +623,7 @@ extern "C" int mvuld_gemm_gru(const void* A, int lda, const void* Wg, int ldw, i
   EpiGru e;
   e.bias4 = bias4; e.h32 = h32; e.hb = reinterpret_cast<bf16*>(hb_out); e.ldhb = ldhb; e.M = M; e.D = D;
   if (K <= 448 && (long long)M >= 128ll * 2 * num_sms())
-    return launch_gemm<128, 4, EpiGru, 7>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
+    return launch_gemm<128, 6, EpiGru, 7>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
   return launch_gemm<128, 6, EpiGru>(A, lda, Wg, ldw, M, 4 * D, K, e, stream);
 }
 

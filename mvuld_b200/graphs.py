@@ -26,8 +26,11 @@ from .unixcoder import PackedLines
 
 
 class _Captured:
-    def __init__(self, graph, static_in, static_out):
+    def __init__(self, graph, static_in, static_out, plan, keep):
         self.graph, self.static_in, self.static_out = graph, static_in, static_out
+        # the graph holds raw pointers into the packed weights (`plan`) and the workspace (`keep`): both stay referenced
+        # here for the graph's lifetime, and a re-packed plan (weights changed, model moved) invalidates the capture
+        self.plan, self.keep = plan, keep
 
 
 class GraphedMVulD:
@@ -43,7 +46,7 @@ class GraphedMVulD:
         self._text: Dict[Tuple[int, int], _Captured] = {}
 
     # ------------------------------------------------------------------------------------------------
-    def _capture(self, fn, example: torch.Tensor) -> _Captured:
+    def _capture(self, fn, example: torch.Tensor, plan_of, keep_of) -> _Captured:
         static_in = example.clone()
         side = torch.cuda.Stream(device=example.device)
         side.wait_stream(torch.cuda.current_stream(example.device))
@@ -55,7 +58,7 @@ class GraphedMVulD:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_out = fn(static_in)
-        return _Captured(graph, static_in, static_out)
+        return _Captured(graph, static_in, static_out, plan_of(), keep_of())
 
     def image_features(self, image: torch.Tensor) -> torch.Tensor:
         swin = self.model.swin
@@ -64,10 +67,10 @@ class GraphedMVulD:
             swin.prepare()
         B = image.shape[0]
         cap = self._swin.get(B)
-        if cap is None:
+        if cap is None or cap.plan is not swin._plan:
             x = image.to(torch.float32).contiguous()
             ws = swin._workspace(B)
-            cap = self._capture(lambda t: swin._forward_features_ws(t, ws), x)
+            cap = self._capture(lambda t: swin._forward_features_ws(t, ws), x, lambda: swin._plan, lambda: ws)
             self._swin[B] = cap
         cap.static_in.copy_(image, non_blocking=True)
         cap.graph.replay()
@@ -80,8 +83,9 @@ class GraphedMVulD:
         ids = token_ids.view(-1, unix.max_source_length).to(torch.int64).contiguous()
         key = tuple(ids.shape)
         cap = self._text.get(key)
-        if cap is None:
-            cap = self._capture(lambda t: unix.get_repr(t)[0], ids)
+        enc = unix.encoder
+        if cap is None or cap.plan is not enc._plan:
+            cap = self._capture(lambda t: unix.get_repr(t)[0], ids, lambda: enc._plan, lambda: enc._plan["ws"].get(key))
             self._text[key] = cap
         cap.static_in.copy_(ids, non_blocking=True)
         cap.graph.replay()

@@ -164,7 +164,7 @@ class RobertaEncoder(nn.Module):
         return ws
 
     @torch.no_grad()
-    def encode(self, source_ids: torch.Tensor, check_suffix_padding: bool = False):
+    def encode(self, source_ids: torch.Tensor, check_suffix_padding: bool = False, clone_tokens: bool = True):
         """-> (token_embeddings fp32 [B, L, H], sentence_embeddings fp32 [B, H]); unixcoder.py:33-38."""
         if self.training:
             raise RuntimeError("mvuld_b200 RobertaEncoder implements the eval-mode forward: call model.eval()")
@@ -197,7 +197,10 @@ class RobertaEncoder(nn.Module):
         _lib.call("mvuld_masked_mean", w["x32"], w["len"], w["sent"], B, L, H)
         if check_suffix_padding and int(w["ok"].item()) != 1:
             raise ValueError("pad tokens must form a suffix of every sequence (unixcoder.py:150 tokenisation)")
-        return w["x32"].view(B, L, H), w["sent"].clone()
+        # the token embeddings live in the cached per-(B, L) workspace: callers get their own copy unless they ask for
+        # the view (internal fast paths that only use the sentence vector)
+        tok = w["x32"].view(B, L, H)
+        return (tok.clone() if clone_tokens else tok), w["sent"].clone()
 
     def forward(self, input_ids, attention_mask=None):
         """HF-style call ``encoder(ids, attention_mask=...)[0]``; the mask is re-derived from the pad id."""
@@ -444,7 +447,7 @@ class MyUniXcoder(nn.Module):
         if not input_ids.is_cuda:
             return self.encoder.encode_lines(input_ids.view(-1, self.max_source_length)), labels
         source_ids = input_ids.view(-1, self.max_source_length)
-        _, vec = self.get_xcode_vec(source_ids)
+        _, vec = self.encoder.encode(source_ids, clone_tokens=False)
         return vec, labels
 
     @torch.no_grad()
