@@ -567,10 +567,9 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, in
     if (rc) return rc;
   }
   auto kern = gemm_tn_kernel<BN, STAGES, Epi, BKB>;
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // per template instantiation, one bit per device
+  if (first_use_on_current_device(&attr_set)) {
     MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int n_tiles_h = (N + BN - 1) / BN;
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * n_tiles_h;

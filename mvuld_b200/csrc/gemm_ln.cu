@@ -281,10 +281,9 @@ static int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M,
     if (rc) return rc;
   }
   auto kern = gemm_ln_kernel<N, BK, STAGES>;
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // per template instantiation, one bit per device
+  if (first_use_on_current_device(&attr_set)) {
     MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles = (M + GLN_BM - 1) / GLN_BM;
   const int grid = tiles < num_sms() ? tiles : num_sms();

@@ -342,7 +342,11 @@ static int launch_gemm_ln_cluster(const void* A, int lda, const void* W, int ldw
     if (rc) return rc;
   }
   auto kern = gemm_ln_cluster_kernel<CL>;
-  static int max_clusters = 0;         // per template instantiation
+  static int max_clusters_dev[64] = {0};   // per template instantiation and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int& max_clusters = max_clusters_dev[dev];
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -128,14 +128,25 @@ static int encode_tmap_16b(CUtensorMap* out, const void* ptr, int rank, const ui
 }
 
 int num_sms() {
-  static int n = 0;
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    __atomic_store_n(&cached[dev], n, __ATOMIC_RELAXED);
   }
   return n;
+}
+
+bool first_use_on_current_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;                      // beyond the mask: just set the attribute every time
+  const unsigned long long bit = 1ull << dev;
+  return (__atomic_fetch_or(mask, bit, __ATOMIC_ACQ_REL) & bit) == 0;
 }
 
 }  // namespace mv

@@ -33,6 +33,11 @@ int fail(int code, const char* fmt, ...);
 int make_tmap_16b(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int swizzle_bytes);
 
+// SM count of the CURRENT device (cached per device ordinal).
 int num_sms();
+
+// Per-device once-flag for function attributes (cudaFuncSetAttribute is per device): `mask` is a function-local static;
+// returns true the first time it is asked on the current device.  Thread safe.
+bool first_use_on_current_device(unsigned long long* mask);
 
 }  // namespace mv
