@@ -333,10 +333,17 @@ struct epi_prefetch<E, std::void_t<decltype(E::kPrefetch)>> : std::true_type { u
 // panel resident in shared memory (loaded once), owns one column block and walks row blocks, so only A streams through
 // the ring.  With the streaming schedule a 128 x 128 tile at K = 448 pulls 114 KB of A and 114 KB of W through L2 for
 // 32 KB of output; the GGNN GEMMs (M = 825 k, K = 200 / 400) sat at 8.4 TB/s of L2 traffic, not at HBM or MMA limits.
-template <int BN, int STAGES, int BKB = 0, bool STAGED_C = true>
+//
+// CG = 2 is the CTA-PAIR form (tcgen05 cta_group::2): the two CTAs of a cluster (= the two SMs of a TPC) own one
+// 256 x BN tile; each CTA loads its own 128 rows of A and HALF of the tile's weight rows, the leader issues one
+// M = 256 MMA over both shared memories, each CTA drains its own 128 accumulator rows.  Why: these GEMMs are bound by
+// the L2 -> SM path, not by the tensor pipe or the epilogue -- a 128 x 256 tile pulls 48 KB per 64-wide k block through
+// L2 for 512 cycles of MMA = 96 B/clk/SM, the chip's L2 delivers ~43 B/clk/SM (profiles/r2_ncu_gemm_fc1.md: 8.4 k cycles
+// per tile against 4.1 k of MMA, = 384 KB / 45 B/clk).  The pair form moves 32 KB per CTA for the same MMA time.
+template <int BN, int STAGES, int BKB = 0, bool STAGED_C = true, int CG = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN / CG * GEMM_BK * 2;   // this CTA's share of the weight rows
   static constexpr int STAGE_BYTES = BKB > 0 ? A_BYTES : A_BYTES + B_BYTES;    // bytes one ring slot receives
   static constexpr int B_TOTAL = (BKB > 0 ? BKB : STAGES) * B_BYTES;
   static constexpr int BAR_BYTES = 256;
@@ -346,11 +353,12 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;                                    // 256 or 512 (power of two)
 };
 
-template <int BN, int STAGES, class Epi, int BKB = 0>
+template <int BN, int STAGES, class Epi, int BKB = 0, int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
-  using Cfg = GemmCfg<BN, STAGES, BKB, Epi::kStaged>;
+  static_assert(CG == 1 || (CG == 2 && BKB == 0), "the pair form uses the streaming schedule");
+  using Cfg = GemmCfg<BN, STAGES, BKB, Epi::kStaged, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -366,7 +374,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = CG == 2 ? (int)blockIdx.x >> 1 : (int)blockIdx.x;      // a CTA, or a CTA pair
+  const int units = CG == 2 ? (int)gridDim.x >> 1 : (int)gridDim.x;
+  const int m_tiles = (M + GEMM_BM * CG - 1) / (GEMM_BM * CG);            // row blocks of 128 * CG rows
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
@@ -381,9 +392,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       n_blk = ws_n;
       return m_blk < m_tiles;
     }
-    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-    m_blk = tile / n_tiles;
-    n_blk = tile - m_blk * n_tiles;
+    const int tile = unit + it * units;
+    const int mb = tile / n_tiles;
+    n_blk = tile - mb * n_tiles;
+    m_blk = mb * CG + cta_rank;                                           // in 128-row blocks
     return tile < num_tiles;
   };
 
@@ -396,17 +408,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], GEMM_THREADS - 64);
+      mbar_init(&tempty[a], (GEMM_THREADS - 64) * CG);       // pair form: both CTAs' epilogues arrive on the leader's
     }
     mbar_init(bfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -420,22 +438,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb)
           tma_load_2d(sB + kb * Cfg::B_BYTES, &tmB, bfull, kb * GEMM_BK, n_blk * BN);
       }
+      const uint32_t lead_full = CG == 2 ? mapa_u32(smem_u32(full), 0) : 0;   // the leader CTA's full[] barriers
       for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          if (BKB == 0) tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+          if (CG == 2) {
+            // both halves of the stage complete on the LEADER's barrier, which expects the pair's bytes
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_cg2(sA + stage * Cfg::A_BYTES, &tmA, lead_full + stage * 8, kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d_cg2(sB + stage * Cfg::B_BYTES, &tmB, lead_full + stage * 8, kb * GEMM_BK,
+                            n_blk * BN + cta_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            if (BKB == 0) tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && cta_rank == 0) {
     // The whole warp runs the (uniform) control flow and one elected lane issues.  Descriptors: the high word is a
     // constant, the low word (address >> 4 | LBO << 16) advances by plain adds -- assembling each descriptor from
     // scratch inside a one-lane branch put a ~100-cycle dependent chain (shift / mask / or / elect loop) in front of
     // every MMA, as long as a 128 x 128 x 16 MMA takes in the tensor pipe.
-    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, BN, 0, 0);
     const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, 16, 1024, 2) >> 32);
     const uint32_t a_lo0 = (uint32_t)make_smem_desc(smem_u32(sA), 16, 1024, 2);
     const uint32_t b_lo0 = (uint32_t)make_smem_desc(smem_u32(sB), 16, 1024, 2);
@@ -446,7 +473,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (BKB > 0 && tile_at(0, m_blk, n_blk)) mbar_wait(bfull, 0, 5);
     for (int local = 0; tile_at(local, m_blk, n_blk); ++local) {
       const int acc = local & 1;
-      mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1, 2);
+      if (CG == 2) mbar_wait_cluster(&tempty[acc], ((local >> 1) & 1) ^ 1, 2);
+      else mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -456,23 +484,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * (Cfg::A_BYTES >> 4);
           const uint32_t b_lo = b_lo0 + (uint32_t)(BKB > 0 ? kb : stage) * (Cfg::B_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_ss(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + k * 2), ((uint64_t)desc_hi << 32) | (b_lo + k * 2), idesc,
-                    (kb | k) != 0);
-          umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (CG == 2)
+              umma_ss2(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + k * 2), ((uint64_t)desc_hi << 32) | (b_lo + k * 2),
+                       idesc, (kb | k) != 0);
+            else
+              umma_ss(d_tmem, ((uint64_t)desc_hi << 32) | (a_lo + k * 2), ((uint64_t)desc_hi << 32) | (b_lo + k * 2),
+                      idesc, (kb | k) != 0);
+          }
+          if (CG == 2) umma_commit2_mc(&empty[stage], 3);   // frees the slot in BOTH CTAs when these MMAs retire
+          else umma_commit(&empty[stage]);                  // frees the smem slot when these MMAs retire
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (leader) umma_commit(&tfull[acc]);       // accumulator ready for the epilogue
+      if (leader) {                               // accumulator ready for the epilogue (of both CTAs)
+        if (CG == 2) umma_commit2_mc(&tfull[acc], 3);
+        else umma_commit(&tfull[acc]);
+      }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2) {
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;    // which slice of the tile's columns this warp drains
     constexpr int PARTS = GEMM_EPI_WARPS / 4;
     constexpr int CPP = (BN / 32) / PARTS;   // 32-column chunks per warp
     int m_blk, n_blk;
+    const uint32_t lead_tempty = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : 0;
     for (int local = 0; tile_at(local, m_blk, n_blk); ++local) {
       const int acc = local & 1;
       const int row = m_blk * GEMM_BM + quarter * 32 + lane;
@@ -526,19 +564,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      if (CG == 2) mbar_arrive_cluster(lead_tempty + acc * 8);
+      else mbar_arrive(&tempty[acc]);
     }
     if (Epi::kStaged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (CG == 2) {
+    cluster_sync_all();                   // no CTA leaves (or frees TMEM) while its peer can still reach it
+    if (warp == 1) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
-template <int BN, int STAGES, class Epi, int BKB = 0>
+template <int BN, int STAGES, class Epi, int BKB = 0, int CG = 1>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi,
                        cudaStream_t stream, void* out_bf16 = nullptr, int ldc = 0) {
-  using Cfg = GemmCfg<BN, STAGES, BKB, Epi::kStaged>;
+  using Cfg = GemmCfg<BN, STAGES, BKB, Epi::kStaged, CG>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "GEMM configuration exceeds the 227 KB of shared memory per CTA");
   MV_CHECK_ARG(BKB == 0 || K <= BKB * GEMM_BK, "gemm: weight-stationary schedule holds K <= %d (K=%d)", BKB * GEMM_BK, K);
   MV_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -554,7 +598,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, in
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t str[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)(BN / CG)};
     int rc = make_tmap_16b(&tmB, W, 2, dims, str, box, 128);
     if (rc) return rc;
   }
@@ -566,13 +610,31 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, in
     int rc = make_tmap_16b(&tmC, out_bf16, 2, dims, str, box, 128);
     if (rc) return rc;
   }
-  auto kern = gemm_tn_kernel<BN, STAGES, Epi, BKB>;
+  auto kern = gemm_tn_kernel<BN, STAGES, Epi, BKB, CG>;
   static unsigned long long attr_set = 0;   // per template instantiation, one bit per device
   if (first_use_on_current_device(&attr_set)) {
     MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   }
   const int n_tiles_h = (N + BN - 1) / BN;
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * n_tiles_h;
+  const int tiles = ((M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * n_tiles_h;
+  if (CG == 2) {                                   // one CTA pair per TPC, persistent over 256 x BN tiles
+    const int pairs_max = num_sms() / 2;
+    const int pairs = tiles < pairs_max ? tiles : pairs_max;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, M, N, K, epi));
+    return 0;
+  }
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (BKB > 0) {                                   // a multiple of the column blocks, at least one CTA per column block
     MV_CHECK_ARG(n_tiles_h <= num_sms(), "gemm: weight-stationary schedule needs N / %d <= SM count", BN);
@@ -588,6 +650,11 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, in
 
 using namespace mv;
 
+// The pair form (CG = 2) pays above K = 512 (tools/time_gemm_ksweep.py, M = 50 176, N = 2 048: K = 1 024 162 -> 150 us,
+// K = 2 048 297 -> 281 us); at K <= 512 a tile's time is its epilogue and HBM writes, and coupling two CTAs' epilogues
+// to one accumulator hand-off costs more than the halved weight traffic returns (K = 256: 61 -> 82 us).
+static inline bool pair_form(int K) { return K >= 1024; }
+
 extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                                int act, const float* res_f32, int ldr, void* out_bf16, float* out_f32, int ldc,
                                cudaStream_t stream) {
@@ -601,6 +668,7 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
     // skinny-K, tall-M problems keep the weight panel resident (see GemmCfg)
     const bool ws = K <= 256 && (long long)M >= 128ll * 2 * num_sms();
     // (measured neutral for the 128 x 256 tiles of the Swin stage-0 / 1 layers, whose GELU epilogue sets the pace)
+    if (big && pair_form(K)) return launch_gemm<256, 6, EpiBf16Tma, 0, 2>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
     if (big) return launch_gemm<256, 4, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
     if (ws) return launch_gemm<128, 8, EpiBf16Tma, 4>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
     return launch_gemm<128, 6, EpiBf16Tma>(A, lda, W, ldw, M, N, K, t, stream, out_bf16, ldc);
@@ -609,8 +677,8 @@ extern "C" int mvuld_gemm_bf16(const void* A, int lda, const void* W, int ldw, i
   e.bias = bias; e.res = res_f32; e.out_b = reinterpret_cast<bf16*>(out_bf16); e.out_f = out_f32;
   e.ldr = ldr; e.ldc = ldc; e.act = act; e.M = M; e.N = N;
   // 128x256 tiles move 27 % fewer operand bytes per MAC through L2 than 128x128; use them when N fills them
-  if (N % 256 == 0 && (long long)M * N >= 256ll * 256 * 148)
-    return launch_gemm<256, 4, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
+  if (big && pair_form(K)) return launch_gemm<256, 7, EpiGeneric, 0, 2>(A, lda, W, ldw, M, N, K, e, stream);
+  if (big) return launch_gemm<256, 4, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
   return launch_gemm<128, 6, EpiGeneric>(A, lda, W, ldw, M, N, K, e, stream);
 }
 

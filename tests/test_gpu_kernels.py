@@ -109,6 +109,34 @@ def test_gemm_plain(M, N, K):
     assert rel_err(ob, ref) < 5e-3
 
 
+@pytest.mark.parametrize("M,N,K,act", [(50176, 2048, 1024, 1), (40000 + 129, 512, 1024, 0), (38000 + 77, 768, 3072, 0),
+                                       (50176 - 128, 1536, 1024, 1), (25000, 1024, 2048, 2)])
+def test_gemm_pair_tiles(M, N, K, act):
+    """Shapes that take the CTA-pair form (cta_group::2, 256 x 256 tiles): full tiles, a last row block whose second
+    CTA is entirely / partly out of range, both epilogues (bf16 through TMA stores; fp32 + bf16 + residual)."""
+    g = gen(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    fn = {0: lambda t: t, 1: torch.nn.functional.gelu, 2: torch.nn.functional.elu}[act]
+    ref = fn(A.float() @ W.float().T + bias)
+    ob = torch.zeros(M + 3, N, device=DEV, dtype=torch.bfloat16)              # rows past M must stay untouched
+    _lib.gemm(A, W, bias=bias, act=act, out_bf16=ob[:M])
+    torch.cuda.synchronize()
+    assert rel_err(ob[:M], ref) < 5e-3 and float(ob[M:].abs().sum()) == 0.0
+    res = torch.randn(M, N, generator=g).to(DEV)
+    of = torch.zeros(M + 3, N, device=DEV)
+    ob.zero_()
+    _lib.gemm(A, W, bias=bias, act=act, res=res, out_f32=of[:M], out_bf16=ob[:M])
+    torch.cuda.synchronize()
+    assert rel_err(of[:M], ref + res) < 1e-5 and float(of[M:].abs().sum()) == 0.0
+    assert rel_err(ob[:M], ref + res) < 5e-3 and float(ob[M:].abs().sum()) == 0.0
+    ob2 = torch.zeros_like(ob)
+    _lib.gemm(A, W, bias=bias, act=act, res=res, out_f32=of[:M], out_bf16=ob2[:M])
+    torch.cuda.synchronize()
+    assert torch.equal(ob, ob2)
+
+
 def test_gemm_epilogues():
     g = gen(11)
     M, N, K = 300, 256, 256
