@@ -50,6 +50,16 @@ int mvuld_gemm_ln_wide_bf16(const void* A, int lda, const void* W, int ldw, int 
                             const float* gamma, const float* beta, float eps, const float* shortcut_f32, float* x32,
                             void* xb, mvuld_stream_t stream);
 
+/* SwinV2 Mlp + res-post-norm in ONE kernel for the narrow stages (C in {128, 256}):
+ *   x = shortcut + LayerNorm(fc2(GELU(fc1(X) + b1)) + b2) * gamma + beta
+ * X bf16 [M, C] contiguous, W1 bf16 [4C, C], W2 bf16 [C, 4C]; shortcut fp32 [M, C] (may alias x32); outputs fp32 x32
+ * and/or bf16 xb (xb may alias X).  The hidden activation [M, 4C] stays in shared memory / TMEM (csrc/mlp_ln.cu);
+ * bit-identical to mvuld_gemm_bf16(act = GELU) followed by mvuld_gemm_ln_bf16.
+ * Replaces mvuld/models/swin_transformer_v2.py:26-32 (Mlp.forward) + :304 (norm2 + residual). */
+int mvuld_mlp_ln_bf16(const void* X, const void* W1, const float* b1, const void* W2, const float* b2,
+                      const float* gamma, const float* beta, float eps, const float* shortcut_f32, float* x32, void* xb,
+                      int M, int C, mvuld_stream_t stream);
+
 /* SwinV2 qkv projection fused with: cat(q_bias, 0, v_bias), per-head L2 normalisation of q and k, the learnable
  * logit scale (qscale[h] = exp(min(logit_scale_h, ln 100)) * log2 e, folded into q), window partition and cyclic
  * shift (pure index math).  X bf16 [B*H*W, C]; q,k fp16 and v bf16, each [B*nW, nH, ws*ws, 32].
@@ -115,9 +125,11 @@ int mvuld_swin_attention_bwd(const void* qh, const void* qb, const void* kh, con
 
 /* Bias-table gradient from the G^T matrices of mvuld_swin_attention_bwd: dtab[h, (qy-ky+ws-1) * (2ws-1) + (qx-kx+ws-1)]
  * += sum over the n_win window instances and all (query, key) pairs of that offset (the reference's table order,
- * natural units).  partial: fp32 workspace [nH, ws, ws, 2ws-1].  Fixed summation order. */
+ * natural units).  partial: fp32 workspace [mvuld_swin_bias_grad_splits(n_win, nH, ws), nH, ws, ws, 2ws-1] (the window
+ * instances are split over blocks; splits are summed in split order).  Fixed summation order. */
 int mvuld_swin_bias_grad(const void* gt, int n_win, int nH, int ws, int npad, float* partial, float* dtab,
                          mvuld_stream_t stream);
+int mvuld_swin_bias_grad_splits(int n_win, int nH, int ws);
 /* cpb_mlp backward (swin_transformer_v2.py:98-111,159,163): tab = table_ref of mvuld_cpb_table, dtab as above;
  * accumulates dw1 [512,2], db1 [512], dw2 [nH,512]. */
 int mvuld_cpb_mlp_bwd(const float* w1, const float* b1, const float* w2, const float* tab, const float* dtab, int nH,

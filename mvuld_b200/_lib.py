@@ -22,6 +22,7 @@ SIGNATURES = {
     "mvuld_gemm_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P],
     "mvuld_gemm_ln_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
     "mvuld_gemm_ln_wide_bf16": [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P],
+    "mvuld_mlp_ln_bf16": [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _P],
     "mvuld_swin_qkv": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_heads_qkv": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "mvuld_cpb_table": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
@@ -38,6 +39,7 @@ SIGNATURES = {
     "mvuld_masked_mean_bwd": [_P, _P, _P, _I, _I, _I, _P],
     "mvuld_embed_grad_rows": [_P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_swin_bias_grad": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "mvuld_swin_bias_grad_splits": [_I, _I, _I],
     "mvuld_cpb_mlp_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "mvuld_swin_qkv_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "mvuld_swin_qkv_bwd_blocks": [_I, _I, _I, _I],
@@ -250,6 +252,19 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, gamma, beta, eps: float, bias=None
         assert t is None or (t.is_contiguous() and t.shape == (M, N))
     call("mvuld_gemm_ln_bf16", _Raw(a), a.stride(0), _Raw(w), w.stride(0), M, N, K, bias, gamma, beta, float(eps),
          shortcut, x32, xb)
+
+
+def mlp_ln(x: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor, b2, gamma, beta, eps: float, shortcut=None, x32=None,
+           xb=None):
+    """x = shortcut + LayerNorm(fc2(GELU(fc1(x) + b1)) + b2) * gamma + beta in one launch (C = x.shape[1] in {128, 256};
+    csrc/mlp_ln.cu).  ``xb`` may be ``x`` itself."""
+    M, Cc = x.shape
+    assert x.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert x.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()
+    assert w1.shape == (4 * Cc, Cc) and w2.shape == (Cc, 4 * Cc)
+    for t in (shortcut, x32, xb):
+        assert t is None or (t.is_contiguous() and t.shape == (M, Cc))
+    call("mvuld_mlp_ln_bf16", _Raw(x), _Raw(w1), b1, _Raw(w2), b2, gamma, beta, float(eps), shortcut, x32, xb, M, Cc)
 
 
 def gemm_ln_wide(a: torch.Tensor, w: torch.Tensor, gamma, beta, eps: float, bias=None, shortcut=None, x32=None, xb=None):

@@ -17,10 +17,12 @@ namespace mv {
 // Bias-table gradient.  gt: bf16 [n_win * nH, N, npad] = G^T (key major) of every window instance; the table entry of
 // (query (qy, qx), key (ky, kx)) is [(qy - ky + ws - 1), (qx - kx + ws - 1)].  Block (head, ky) reads the WHOLE rows of
 // its ws keys (contiguous) for every window instance, sums over the instances in registers, then reduces over kx along
-// the diagonals qx - kx = const through shared memory: partial[head][ky][qy][dx].  The final kernel sums the ws
-// partials of a table row in ky order.
+// the diagonals qx - kx = const through shared memory: partial[split][head][ky][qy][dx].  The window instances are split
+// over blockIdx.z so that nH * ws blocks of a 4-head stage do not leave SMs idle (stage 0 of a 32-image batch: 112 blocks
+// walking 512 windows each ran at 2 TB/s).  The final kernel sums the ws partials of a table row in ky order within a split,
+// then the splits in split order: a fixed order.
 // ---------------------------------------------------------------------------------------------------------
-template <int WS>
+template <int WS, bool SPLIT>
 __global__ void __launch_bounds__(256)
 bias_grad_partial_kernel(const bf16* __restrict__ gt, int n_win, int nH, int npad, float* __restrict__ partial) {
   constexpr int N = WS * WS, SIDE = 2 * WS - 1;
@@ -34,7 +36,17 @@ bias_grad_partial_kernel(const bf16* __restrict__ gt, int n_win, int nH, int npa
   for (int t = 0; t < IPT; ++t)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
-  for (int w = 0; w < n_win; ++w) {
+  // Code generation of this loop is fragile (measured on the 16-head stage / the 4-head stage): the plain 0 .. n_win loop
+  // 179 us; the same kernel with computed bounds [w_beg, w_end) 237 us / 743 us in five splits; a 0 .. count loop from an
+  // offset base pointer 2 323 us.  So the unsplit instantiation keeps the plain loop and only the stages with fewer
+  // blocks than SMs (four heads: 1 236 us unsplit) take the split form.
+  int w_beg = 0, w_end = n_win;
+  if (SPLIT) {
+    const int per = (n_win + (int)gridDim.z - 1) / (int)gridDim.z;
+    w_beg = blockIdx.z * per;
+    w_end = min(n_win, w_beg + per);
+  }
+  for (int w = w_beg; w < w_end; ++w) {
     const bf16* base = gt + ((size_t)(w * nH + head) * N + ky * WS) * npad;
 #pragma unroll
     for (int t = 0; t < IPT; ++t) {
@@ -57,7 +69,7 @@ bias_grad_partial_kernel(const bf16* __restrict__ gt, int n_win, int nH, int npa
     }
   }
   __syncthreads();
-  float* out = partial + ((size_t)head * WS + ky) * WS * SIDE;      // [qy][dx]
+  float* out = partial + (((size_t)(SPLIT ? blockIdx.z : 0) * nH + head) * WS + ky) * WS * SIDE;      // [qy][dx]
   for (int o = threadIdx.x; o < WS * SIDE; o += 256) {
     const int qy = o / SIDE, dx = o - qy * SIDE;
     float s = 0.f;
@@ -69,16 +81,21 @@ bias_grad_partial_kernel(const bf16* __restrict__ gt, int n_win, int nH, int npa
   }
 }
 template <int WS>
-__global__ void bias_grad_final_kernel(const float* __restrict__ partial, float* __restrict__ dtab, int nH) {
+__global__ void bias_grad_final_kernel(const float* __restrict__ partial, float* __restrict__ dtab, int nH, int splits) {
   constexpr int SIDE = 2 * WS - 1;
   const int o = blockIdx.x * blockDim.x + threadIdx.x;   // (head, dy, dx)
   if (o >= nH * SIDE * SIDE) return;
   const int head = o / (SIDE * SIDE), e = o - head * SIDE * SIDE;
   const int dy = e / SIDE, dx = e - dy * SIDE;
   float s = 0.f;
-  for (int ky = 0; ky < WS; ++ky) {
-    const int qy = dy - (WS - 1) + ky;
-    if (qy >= 0 && qy < WS) s += partial[(((size_t)head * WS + ky) * WS + qy) * SIDE + dx];
+  for (int z = 0; z < splits; ++z) {
+    float t = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < WS; ++ky) {
+      const int qy = dy - (WS - 1) + ky;
+      if (qy >= 0 && qy < WS) t += partial[((((size_t)z * nH + head) * WS + ky) * WS + qy) * SIDE + dx];
+    }
+    s += t;
   }
   dtab[o] += s;
 }
@@ -341,16 +358,37 @@ __global__ void patch_im2col_kernel(const float* __restrict__ img, bf16* __restr
 
 using namespace mv;
 
+// Window splits of mvuld_swin_bias_grad.  A block's cost is its window instances plus a fixed epilogue (~11 instances'
+// worth, measured: splitting the 224 blocks of an 8-head stage five ways was slower than not splitting); the SM holds `per_sm` blocks (the [ws][ws^2] fp32 tile: 88 KB at ws = 28), so a launch runs in
+// ceil(blocks / capacity) waves: take the split count that minimises waves x (instances per split + epilogue).  The
+// partial workspace holds splits * nH * ws * ws * (2 ws - 1) floats.
+extern "C" int mvuld_swin_bias_grad_splits(int n_win, int nH, int ws) {
+  const int smem = ws * ((ws * ws + 7) / 8) * 8 * 4;
+  int per_sm = (227 * 1024) / (smem + 1024);
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const long long cap = (long long)per_sm * num_sms();
+  const long long blocks = (long long)nH * ws;
+  int best = 1;
+  long long best_cost = -1;
+  for (int sp = 1; sp <= 32 && sp <= n_win; ++sp) {
+    const long long waves = (blocks * sp + cap - 1) / cap;
+    const long long cost = waves * ((n_win + sp - 1) / sp + 11);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+  }
+  return best;
+}
 template <int WS>
 static int bias_grad(const void* gt, int n_win, int nH, int npad, float* partial, float* dtab, cudaStream_t stream) {
   constexpr int VPR = (WS * WS + 7) / 8;
   const int smem = WS * VPR * 8 * sizeof(float);
-  auto kern = bias_grad_partial_kernel<WS>;
+  const int splits = mvuld_swin_bias_grad_splits(n_win, nH, WS);
+  auto kern = splits > 1 ? bias_grad_partial_kernel<WS, true> : bias_grad_partial_kernel<WS, false>;
   MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<dim3(nH, WS), 256, smem, stream>>>(reinterpret_cast<const bf16*>(gt), n_win, nH, npad, partial);
+  kern<<<dim3(nH, WS, splits), 256, smem, stream>>>(reinterpret_cast<const bf16*>(gt), n_win, nH, npad, partial);
   MV_LAUNCH_OK();
   constexpr int SIDE = 2 * WS - 1;
-  bias_grad_final_kernel<WS><<<(nH * SIDE * SIDE + 255) / 256, 256, 0, stream>>>(partial, dtab, nH);
+  bias_grad_final_kernel<WS><<<(nH * SIDE * SIDE + 255) / 256, 256, 0, stream>>>(partial, dtab, nH, splits);
   MV_LAUNCH_OK();
   return 0;
 }

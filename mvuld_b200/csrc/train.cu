@@ -70,49 +70,111 @@ __device__ __forceinline__ float block_reduce_fixed(float (&acc)[NV], float (*pa
   return t;
 }
 
-// out[c] += sum_r x[r, c].  Block (column group of 8, row slab): thread = row lane, one 16 / 32-byte load per row, fixed-
-// order block reduction; with one slab the block adds straight into out, otherwise it writes its row of the partials
-// workspace and colsum_final_kernel sums the slabs in slab order.  No atomics: bit-reproducible.
+// out[c] += sum_r x[r, c].  Block (column segment of up to 256 eight-column units, row slab): thread = (row lane, unit),
+// so a warp reads 32 consecutive 16 / 32-byte units of a row (the first version gave a thread one unit of 256 different
+// rows: 32 half-used sectors per warp load, and a [25 088, 512] gradient took 21 us against 4 us of HBM time); the row
+// lanes of a unit are summed in lane order through shared memory; with one slab the block adds straight into out,
+// otherwise it writes its row of the partials workspace and colsum_final_kernel sums the slabs in a fixed order.
+// No atomics: bit-reproducible.
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, float* __restrict__ partials, int R, int C,
               int rows_per_slab) {
-  __shared__ float part[8][8];
-  const int c0 = blockIdx.x * 8;
+  __shared__ float red[256 * 8];
+  const int units_total = (C + 7) >> 3;
+  const int u0 = blockIdx.x * 256;
+  const int upr = min(256, units_total - u0);          // units of a row this block covers
+  const int rpp = 256 / upr;                           // rows per pass
+  const int tr = threadIdx.x / upr, tu = threadIdx.x - tr * upr;
+  const bool active = tr < rpp;
+  const int c0 = (u0 + tu) * 8;
   const int nc = min(8, C - c0);
   const int rbeg = blockIdx.y * rows_per_slab, rend = min(R, rbeg + rows_per_slab);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bool vec = nc == 8 && (ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 31) == 0;
-  for (int r = rbeg + threadIdx.x; r < rend; r += 256) {
-    const T* p = x + (size_t)r * ldx + c0;
+  if (active) {
     if (vec) {
-      if (sizeof(T) == 2) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
-      } else {
-        const float4 a4 = __ldg(reinterpret_cast<const float4*>(p)), b4 = __ldg(reinterpret_cast<const float4*>(p) + 1);
-        acc[0] += a4.x; acc[1] += a4.y; acc[2] += a4.z; acc[3] += a4.w;
-        acc[4] += b4.x; acc[5] += b4.y; acc[6] += b4.z; acc[7] += b4.w;
+      // four rows in flight per thread: the loop carries only the adds
+      int r = rbeg + tr;
+      for (; r + 3 * rpp < rend; r += 4 * rpp) {
+        if (sizeof(T) == 2) {
+          uint4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(r + j * rpp) * ldx + c0));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[0] += bf16_lo(v[j].x); acc[1] += bf16_hi(v[j].x); acc[2] += bf16_lo(v[j].y); acc[3] += bf16_hi(v[j].y);
+            acc[4] += bf16_lo(v[j].z); acc[5] += bf16_hi(v[j].z); acc[6] += bf16_lo(v[j].w); acc[7] += bf16_hi(v[j].w);
+          }
+        } else {
+          float4 a4[4], b4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4* p = reinterpret_cast<const float4*>(x + (size_t)(r + j * rpp) * ldx + c0);
+            a4[j] = __ldg(p);
+            b4[j] = __ldg(p + 1);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[0] += a4[j].x; acc[1] += a4[j].y; acc[2] += a4[j].z; acc[3] += a4[j].w;
+            acc[4] += b4[j].x; acc[5] += b4[j].y; acc[6] += b4[j].z; acc[7] += b4[j].w;
+          }
+        }
+      }
+      for (; r < rend; r += rpp) {
+        const T* p = x + (size_t)r * ldx + c0;
+        if (sizeof(T) == 2) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+          acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+          acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+        } else {
+          const float4 a4 = __ldg(reinterpret_cast<const float4*>(p)), b4 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+          acc[0] += a4.x; acc[1] += a4.y; acc[2] += a4.z; acc[3] += a4.w;
+          acc[4] += b4.x; acc[5] += b4.y; acc[6] += b4.z; acc[7] += b4.w;
+        }
       }
     } else {
+      for (int r = rbeg + tr; r < rend; r += rpp) {
+        const T* p = x + (size_t)r * ldx + c0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (k < nc) acc[k] += ldf<T>(p, k);
+        for (int k = 0; k < 8; ++k)
+          if (k < nc) acc[k] += ldf<T>(p, k);
+      }
     }
   }
-  const float t = block_reduce_fixed<8>(acc, part);
-  if (threadIdx.x < nc) {
-    if (gridDim.y == 1) out[c0 + threadIdx.x] += t;
-    else partials[(size_t)blockIdx.y * C + c0 + threadIdx.x] = t;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  if (active && tr == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = 0.f;
+      for (int q = 0; q < rpp; ++q) t += red[(q * upr + tu) * 8 + k];
+      if (k < nc) {
+        if (gridDim.y == 1) out[c0 + k] += t;
+        else partials[(size_t)blockIdx.y * C + c0 + k] = t;
+      }
+    }
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partials, float* __restrict__ out, int slabs, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float t = 0.f;
-  for (int s = 0; s < slabs; ++s) t += partials[(size_t)s * C + c];
-  out[c] += t;
+// slabs summed in a fixed order, split over 32 thread rows (see ln_rows_bwd_final_kernel)
+__global__ void __launch_bounds__(1024)
+colsum_final_kernel(const float* __restrict__ partials, float* __restrict__ out, int slabs, int C) {
+  __shared__ float sa[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, slice = threadIdx.y;
+  const int per = (slabs + 31) / 32;
+  const int k0 = slice * per, k1 = min(slabs, k0 + per);
+  float a = 0.f;
+  if (c < C)
+    for (int k = k0; k < k1; ++k) a += partials[(size_t)k * C + c];
+  sa[slice][threadIdx.x] = a;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 32; ++s2) t += sa[s2][threadIdx.x];
+    out[c] += t;
+  }
 }
 
 // activation backward through y = dropout(elu(pre)):  kept elements carry elu(pre) / (1 - p)
@@ -631,104 +693,132 @@ gat_attn_grad_kernel(const bf16* __restrict__ z, const float* __restrict__ del, 
 // workspace per block (grid capped at 2 blocks per SM), which ln_rows_bwd_final_kernel sums in block order: no atomics,
 // bit-reproducible gradients.  dv is written as bf16 (the operand of the dense backward) and / or fp32
 // (mode 2: it is also the shortcut's gradient); the residual gradient of mode 1 is dout itself and needs no kernel.
-template <int UNITS>
+// Latency: a warp keeps RPW = NR * (32 / LPR) rows in flight (LPR = 16 lanes per row when a row has <= 16 units, so a
+// C = 128 row does not idle half the warp), and y, the shortcut and dout of all of them are requested before the first
+// reduction (one row per warp with dout loaded after two shuffle reductions ran the C = 128 launches at 1.8 TB/s).
+template <int UNITS, int LPR, int NR>
 __global__ void __launch_bounds__(256)
 ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, const float* __restrict__ gamma,
                    const float* __restrict__ dout, bf16* __restrict__ dvb, float* __restrict__ dv32,
                    float* __restrict__ partials, int M, int C, float eps, int mode) {
-  extern __shared__ float red[];                  // [8 warps][2][C]
+  extern __shared__ float red[];                  // [8 warps][32 / LPR][2][C]
+  constexpr int RPP = 32 / LPR;                   // rows per pass of a warp
+  constexpr int RPW = RPP * NR;                   // rows a warp has in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
   const int units = C >> 3;
+  const float invC = 1.0f / (float)C;
+  auto seg_sum = [](float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
   float dg[UNITS][8], db[UNITS][8];
 #pragma unroll
   for (int k = 0; k < UNITS; ++k)
 #pragma unroll
     for (int q = 0; q < 8; ++q) dg[k][q] = db[k][q] = 0.f;
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    float v[UNITS][8], g[UNITS][8];
-    float sum = 0.f;
+  for (int row0 = (blockIdx.x * 8 + warp) * RPW; row0 < M; row0 += gridDim.x * 8 * RPW) {
+    float v[NR][UNITS][8], d[NR][UNITS][8];
 #pragma unroll
-    for (int k = 0; k < UNITS; ++k) {
-      const int u = lane + k * 32;
-      if (u < units) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(y + (size_t)row * C) + u);
-        v[k][0] = bf16_lo(raw.x); v[k][1] = bf16_hi(raw.x); v[k][2] = bf16_lo(raw.y); v[k][3] = bf16_hi(raw.y);
-        v[k][4] = bf16_lo(raw.z); v[k][5] = bf16_hi(raw.z); v[k][6] = bf16_lo(raw.w); v[k][7] = bf16_hi(raw.w);
-        if (mode == 2) {
-          const float4* sp = reinterpret_cast<const float4*>(shortcut + (size_t)row * C + u * 8);
-          const float4 a = __ldg(sp), b = __ldg(sp + 1);
-          v[k][0] += a.x; v[k][1] += a.y; v[k][2] += a.z; v[k][3] += a.w;
-          v[k][4] += b.x; v[k][5] += b.y; v[k][6] += b.z; v[k][7] += b.w;
-        }
+    for (int n = 0; n < NR; ++n) {
+      const int row = row0 + n * RPP + sub;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sum += v[k][q];
-      }
-    }
-    const float mean = warp_sum(sum) / (float)C;
-    float sq = 0.f;
+      for (int k = 0; k < UNITS; ++k) {
+        const int u = l + k * LPR;
+        if (row < M && u < units) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(y + (size_t)row * C) + u);
+          v[n][k][0] = bf16_lo(raw.x); v[n][k][1] = bf16_hi(raw.x); v[n][k][2] = bf16_lo(raw.y); v[n][k][3] = bf16_hi(raw.y);
+          v[n][k][4] = bf16_lo(raw.z); v[n][k][5] = bf16_hi(raw.z); v[n][k][6] = bf16_lo(raw.w); v[n][k][7] = bf16_hi(raw.w);
+          if (mode == 2) {
+            const float4* sp = reinterpret_cast<const float4*>(shortcut + (size_t)row * C + u * 8);
+            const float4 a = __ldg(sp), b = __ldg(sp + 1);
+            v[n][k][0] += a.x; v[n][k][1] += a.y; v[n][k][2] += a.z; v[n][k][3] += a.w;
+            v[n][k][4] += b.x; v[n][k][5] += b.y; v[n][k][6] += b.z; v[n][k][7] += b.w;
+          }
+          const float4* dp = reinterpret_cast<const float4*>(dout + (size_t)row * C + u * 8);
+          const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+          d[n][k][0] = d0.x; d[n][k][1] = d0.y; d[n][k][2] = d0.z; d[n][k][3] = d0.w;
+          d[n][k][4] = d1.x; d[n][k][5] = d1.y; d[n][k][6] = d1.z; d[n][k][7] = d1.w;
+        } else {
 #pragma unroll
-    for (int k = 0; k < UNITS; ++k)
-      if (lane + k * 32 < units) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float d = v[k][q] - mean;
-          sq += d * d;
-        }
-      }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < UNITS; ++k) {
-      const int u = lane + k * 32;
-      if (u < units) {
-        const float4* dp = reinterpret_cast<const float4*>(dout + (size_t)row * C + u * 8);
-        const float4* gp = reinterpret_cast<const float4*>(gamma + u * 8);
-        const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1), g0 = __ldg(gp), g1 = __ldg(gp + 1);
-        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float xh = (v[k][q] - mean) * rstd;
-          v[k][q] = xh;
-          g[k][q] = d[q] * gm[q];
-          s1 += g[k][q];
-          s2 += g[k][q] * xh;
-          dg[k][q] += d[q] * xh;
-          db[k][q] += d[q];
+          for (int q = 0; q < 8; ++q) v[n][k][q] = d[n][k][q] = 0.f;
         }
       }
     }
-    const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
 #pragma unroll
-    for (int k = 0; k < UNITS; ++k) {
-      const int u = lane + k * 32;
-      if (u < units) {
-        float o[8];
+    for (int n = 0; n < NR; ++n) {
+      const int row = row0 + n * RPP + sub;
+      float sum = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = rstd * (g[k][q] - m1 - v[k][q] * m2);
-        if (dv32) {
-          float4* op = reinterpret_cast<float4*>(dv32 + (size_t)row * C + u * 8);
-          op[0] = make_float4(o[0], o[1], o[2], o[3]);
-          op[1] = make_float4(o[4], o[5], o[6], o[7]);
+      for (int k = 0; k < UNITS; ++k)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += v[n][k][q];
+      const float mean = seg_sum(sum) * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < UNITS; ++k)
+        if (l + k * LPR < units) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float dd = v[n][k][q] - mean;
+            sq += dd * dd;
+          }
         }
-        if (dvb) {
-          uint4 w;
-          w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-          w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-          reinterpret_cast<uint4*>(dvb + (size_t)row * C)[u] = w;
+      const float rstd = rsqrtf(seg_sum(sq) * invC + eps);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < UNITS; ++k) {
+        const int u = l + k * LPR;
+        if (u < units) {
+          const float4* gp = reinterpret_cast<const float4*>(gamma + u * 8);
+          const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float xh = (v[n][k][q] - mean) * rstd;
+            const float dq = d[n][k][q];
+            v[n][k][q] = xh;
+            dg[k][q] += dq * xh;                     // rows past M contribute dq = 0
+            db[k][q] += dq;
+            d[n][k][q] = dq * gm[q];
+            s1 += d[n][k][q];
+            s2 += d[n][k][q] * xh;
+          }
+        }
+      }
+      const float m1 = seg_sum(s1) * invC, m2 = seg_sum(s2) * invC;
+#pragma unroll
+      for (int k = 0; k < UNITS; ++k) {
+        const int u = l + k * LPR;
+        if (row < M && u < units) {
+          float o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = rstd * (d[n][k][q] - m1 - v[n][k][q] * m2);
+          if (dv32) {
+            float4* op = reinterpret_cast<float4*>(dv32 + (size_t)row * C + u * 8);
+            op[0] = make_float4(o[0], o[1], o[2], o[3]);
+            op[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          if (dvb) {
+            uint4 w;
+            w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+            w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+            reinterpret_cast<uint4*>(dvb + (size_t)row * C)[u] = w;
+          }
         }
       }
     }
   }
-  // column sums: 8 warps -> shared memory -> one atomicAdd per column and block
+  // column sums: 8 warps x RPP row lanes -> shared memory -> one row of the partials workspace per block (fixed order)
 #pragma unroll
   for (int k = 0; k < UNITS; ++k) {
-    const int u = lane + k * 32;
+    const int u = l + k * LPR;
     if (u < units) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        red[(warp * 2 + 0) * C + u * 8 + q] = dg[k][q];
-        red[(warp * 2 + 1) * C + u * 8 + q] = db[k][q];
+        red[((warp * RPP + sub) * 2 + 0) * C + u * 8 + q] = dg[k][q];
+        red[((warp * RPP + sub) * 2 + 1) * C + u * 8 + q] = db[k][q];
       }
     }
   }
@@ -736,7 +826,7 @@ ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcu
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) {
+    for (int w8 = 0; w8 < 8 * RPP; ++w8) {
       a += red[(w8 * 2 + 0) * C + c];
       b += red[(w8 * 2 + 1) * C + c];
     }
@@ -744,17 +834,37 @@ ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcu
     partials[((size_t)blockIdx.x * 2 + 1) * C + c] = b;
   }
 }
-__global__ void ln_rows_bwd_final_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta, int nblocks, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// Sum of the per-block partials in a FIXED order with the blocks split over 32 thread rows: thread (slice, column) adds
+// its contiguous run of blocks in ascending order, the 32 slice sums are added in slice order.  (One thread per column
+// walking all ~900 blocks was a serial chain of dependent L2 round trips on two SMs: ~100 us of the 133 us a C = 512
+// LayerNorm backward took.)
+__global__ void __launch_bounds__(1024)
+ln_rows_bwd_final_kernel(const float* __restrict__ partials, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         int nblocks, int C) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, slice = threadIdx.y;
+  const int per = (nblocks + 31) / 32;
+  const int k0 = slice * per, k1 = min(nblocks, k0 + per);
   float a = 0.f, b = 0.f;
-  for (int k = 0; k < nblocks; ++k) {
-    a += partials[((size_t)k * 2 + 0) * C + c];
-    b += partials[((size_t)k * 2 + 1) * C + c];
+  if (c < C) {
+    for (int k = k0; k < k1; ++k) {
+      a += partials[((size_t)k * 2 + 0) * C + c];
+      b += partials[((size_t)k * 2 + 1) * C + c];
+    }
   }
-  dgamma[c] += a;
-  dbeta[c] += b;
+  sa[slice][threadIdx.x] = a;
+  sb[slice][threadIdx.x] = b;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+      ta += sa[s][threadIdx.x];
+      tb += sb[s][threadIdx.x];
+    }
+    dgamma[c] += ta;
+    dbeta[c] += tb;
+  }
 }
 
 // exact (erf) GELU backward, nn.GELU default (swin_transformer_v2.py:26-32 Mlp, HF "gelu"): dpre = dh (Phi(x) + x phi(x))
@@ -767,8 +877,7 @@ __global__ void gelu_bwd_kernel(const bf16* __restrict__ pre, const bf16* __rest
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float x0 = bf16_lo(xs[q]), x1 = bf16_hi(xs[q]);
-      const float c0 = 0.5f * (1.0f + erff(x0 * 0.70710678118654752f)) + x0 * 0.3989422804014327f * __expf(-0.5f * x0 * x0);
-      const float c1 = 0.5f * (1.0f + erff(x1 * 0.70710678118654752f)) + x1 * 0.3989422804014327f * __expf(-0.5f * x1 * x1);
+      const float c0 = gelu_erf_grad(x0), c1 = gelu_erf_grad(x1);
       o[q] = pack_bf16x2(bf16_lo(ds[q]) * c0, bf16_hi(ds[q]) * c1);
     }
     reinterpret_cast<uint4*>(dpre)[i] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1096,12 +1205,15 @@ extern "C" int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, i
   MV_LAUNCH_OK();
   return 0;
 }
-// row slabs (= rows of the fp32 [slabs, C] partials workspace) mvuld_colsum uses for R rows: enough blocks to fill the
-// GPU when C is small (a [401 k, 128] gradient has 16 column groups)
+// row slabs (= rows of the fp32 [slabs, C] partials workspace) mvuld_colsum uses for R rows: 8 blocks per SM (the
+// kernel is a pure stream: it needs the SM's full thread count to keep enough loads in flight), at least four passes of
+// the block's row lanes per slab
 extern "C" int mvuld_colsum_slabs(int R, int C) {
-  const int groups = (C + 7) / 8;
-  int slabs = (4 * num_sms() + groups - 1) / groups;           // ~4 blocks per SM
-  const int max_by_rows = (R + 1023) / 1024;                   // at least 1024 rows per slab
+  const int units = (C + 7) / 8;
+  const int segs = (units + 255) / 256;
+  const int rpp = 256 / (units < 256 ? units : 256);
+  int slabs = (8 * num_sms() + segs - 1) / segs;
+  const int max_by_rows = (R + 4 * rpp - 1) / (4 * rpp);
   if (slabs > max_by_rows) slabs = max_by_rows;
   return slabs < 1 ? 1 : slabs;
 }
@@ -1112,12 +1224,12 @@ extern "C" int mvuld_colsum(const void* x, int is_bf16, int ldx, float* out, flo
   const int slabs = mvuld_colsum_slabs(R, C);
   MV_CHECK_ARG(slabs == 1 || partials != nullptr, "colsum: the [mvuld_colsum_slabs(R, C), C] partials workspace is null");
   const int rps = (R + slabs - 1) / slabs;
-  dim3 grid((C + 7) / 8, slabs);
+  dim3 grid(((C + 7) / 8 + 255) / 256, slabs);
   if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, partials, R, C, rps);
   else colsum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, out, partials, R, C, rps);
   MV_LAUNCH_OK();
   if (slabs > 1) {
-    colsum_final_kernel<<<(C + 255) / 256, 256, 0, stream>>>(partials, out, slabs, C);
+    colsum_final_kernel<<<(C + 31) / 32, dim3(32, 32), 0, stream>>>(partials, out, slabs, C);
     MV_LAUNCH_OK();
   }
   return 0;
@@ -1176,22 +1288,32 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
   MV_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || shortcut), "ln_rows_bwd: mode %d (mode 2 needs the shortcut)", mode);
   MV_CHECK_ARG(dgamma && dbeta && (dv_bf16 || dv_f32), "ln_rows_bwd: dgamma / dbeta and one of the dv outputs are required");
   if (M <= 0) return 0;
-  const int grid = mvuld_ln_rows_bwd_blocks(M);
-  const size_t smem = (size_t)16 * C * sizeof(float);
   const bf16* yp = reinterpret_cast<const bf16*>(y);
   bf16* dvp = reinterpret_cast<bf16*>(dv_bf16);
-#define MV_LN_BWD(U)                                                                                                   \
+  int grid = 0;
+#define MV_LN_BWD(U, LPR, NR)                                                                                          \
   do {                                                                                                                 \
-    MV_CUDA_OK(cudaFuncSetAttribute(ln_rows_bwd_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    ln_rows_bwd_kernel<U><<<grid, 256, smem, stream>>>(yp, shortcut, gamma, dout, dvp, dv_f32, partials, M, C, eps, mode); \
+    constexpr int RPW = (32 / (LPR)) * (NR);                                                                           \
+    const size_t smem = (size_t)16 * (32 / (LPR)) * C * sizeof(float);                                                 \
+    auto kern = ln_rows_bwd_kernel<U, LPR, NR>;                                                                        \
+    static unsigned long long attr_set = 0;                                                                            \
+    if (first_use_on_current_device(&attr_set))                                                                        \
+      MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (32 / (LPR)) * 1024 * 4)); \
+    /* exactly the blocks the GPU holds at once: a second wave would serialise one more load -> reduce -> store chain */ \
+    int per_sm = 1;                                                                                                    \
+    MV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                               \
+    per_sm = std::max(1, std::min(per_sm, 6));                                                                         \
+    grid = std::min((M + 8 * RPW - 1) / (8 * RPW), std::min(per_sm * num_sms(), mvuld_ln_rows_bwd_blocks(M)));         \
+    kern<<<grid, 256, smem, stream>>>(yp, shortcut, gamma, dout, dvp, dv_f32, partials, M, C, eps, mode);              \
   } while (0)
-  if (C <= 256) MV_LN_BWD(1);
-  else if (C <= 512) MV_LN_BWD(2);
-  else if (C <= 768) MV_LN_BWD(3);
-  else MV_LN_BWD(4);
+  if (C <= 128) MV_LN_BWD(1, 16, 2);
+  else if (C <= 256) MV_LN_BWD(1, 32, 2);
+  else if (C <= 512) MV_LN_BWD(2, 32, 2);
+  else if (C <= 768) MV_LN_BWD(3, 32, 1);
+  else MV_LN_BWD(4, 32, 1);
 #undef MV_LN_BWD
   MV_LAUNCH_OK();
-  ln_rows_bwd_final_kernel<<<(C + 255) / 256, 256, 0, stream>>>(partials, dgamma, dbeta, grid, C);
+  ln_rows_bwd_final_kernel<<<(C + 31) / 32, dim3(32, 32), 0, stream>>>(partials, dgamma, dbeta, grid, C);
   MV_LAUNCH_OK();
   return 0;
 }

@@ -323,7 +323,8 @@ class SwinTrainer:
                       npad, B, H, W, nH, ws, shift)
             side = 2 * ws - 1
             dtab = torch.zeros(nH, side * side, device=dev, dtype=f32)
-            _lib.call("mvuld_swin_bias_grad", gt, n_bh // nH, nH, ws, npad, e((nH, ws, ws, side), f32), dtab)
+            splits = _lib.load().mvuld_swin_bias_grad_splits(n_bh // nH, nH, ws)
+            _lib.call("mvuld_swin_bias_grad", gt, n_bh // nH, nH, ws, npad, e((splits, nH, ws, ws, side), f32), dtab)
             A = P + "attn."
             _lib.call("mvuld_cpb_mlp_bwd", pv(A + "cpb_mlp.0.weight"), pv(A + "cpb_mlp.0.bias"), pv(A + "cpb_mlp.2.weight"),
                       b["tab_ref"], dtab, nH, ws, b["pws"], gv(A + "cpb_mlp.0.weight"), gv(A + "cpb_mlp.0.bias"),

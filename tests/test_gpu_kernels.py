@@ -236,6 +236,40 @@ def test_gemm_ln_wide_repeated_launches_are_bit_identical(M, N, K):
             assert torch.equal(first, x32)
 
 
+@pytest.mark.parametrize("M,C", [(128 * 148 * 2 + 77, 128), (300, 128), (128 * 151 + 5, 256), (64, 256),
+                                 (802816 // 8, 128)])
+def test_mlp_ln_fused_matches_reference_and_two_kernel_path(M, C):
+    """Fused SwinV2 Mlp + norm2 + residual (csrc/mlp_ln.cu, swin_transformer_v2.py:26-32,304): against the fp32 torch
+    restatement (hidden rounded to bf16 as on every bf16 path) and BIT-identical to fc1-GEMM(GELU) + gemm_ln (same k
+    order, same epilogue arithmetic).  More row tiles than SMs, ragged last tile, xb output aliasing the operand, and
+    repeated launches bit-identical (the H / accumulator hand-offs are the places a race would show)."""
+    g = torch.Generator(device=DEV).manual_seed(M + C)
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    X = (rn(M, C) * 0.7).to(torch.bfloat16)
+    W1, b1 = (rn(4 * C, C) * 0.08).to(torch.bfloat16), rn(4 * C) * 0.3
+    W2, b2 = (rn(C, 4 * C) * 0.05).to(torch.bfloat16), rn(C) * 0.3
+    gamma, beta, res = 1 + 0.1 * rn(C), 0.1 * rn(C), rn(M, C)
+    hid_ref = torch.nn.functional.gelu(X.float() @ W1.float().T + b1).to(torch.bfloat16)
+    ref = torch.nn.functional.layer_norm(hid_ref.float() @ W2.float().T + b2, (C,), gamma, beta, 1e-5) + res
+    # two-kernel path
+    hid = torch.empty(M, 4 * C, device=DEV, dtype=torch.bfloat16)
+    x32_a, xb_a = res.clone(), torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    _lib.gemm(X, W1, bias=b1, act=_lib.ACT_GELU, out_bf16=hid)
+    _lib.gemm_ln(hid, W2, gamma, beta, 1e-5, bias=b2, shortcut=x32_a, x32=x32_a, xb=xb_a)
+    first = None
+    for it in range(6):
+        x32, xb = res.clone(), X.clone()                             # xb aliases the operand, shortcut aliases x32
+        _lib.mlp_ln(xb, W1, b1, W2, b2, gamma, beta, 1e-5, shortcut=x32, x32=x32, xb=xb)
+        if first is None:
+            first = (x32, xb)
+            torch.cuda.synchronize()
+            assert float((x32 - ref).abs().max()) < 5e-3, float((x32 - ref).abs().max())   # bf16 hidden rounding flips
+            assert rel_err(x32, ref) < 1e-4, rel_err(x32, ref)
+            assert torch.equal(x32, x32_a) and torch.equal(xb, xb_a)
+        else:
+            assert torch.equal(first[0], x32) and torch.equal(first[1], xb)
+
+
 # --------------------------------------------------------------------------------------------------------
 # Swin qkv + window attention against the oracle's window_attention
 # --------------------------------------------------------------------------------------------------------

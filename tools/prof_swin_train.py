@@ -39,3 +39,13 @@ for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:14]:
     fl = 2.0 * k[0] * k[1] * k[2] * v[1]
     print(f"gemm M={k[0]:7d} N={k[1]:5d} K={k[2]:7d}: {v[0]:8.3f} ms x{v[1]:3d}  {fl / v[0] / 1e9:7.1f} TFLOP/s")
 print("max memory GB", torch.cuda.max_memory_allocated() / 1e9)
+# row / reduction kernels by their integer arguments (shape signature)
+for ent in ("mvuld_ln_rows_bwd", "mvuld_colsum", "mvuld_swin_bias_grad", "mvuld_swin_attention_bwd", "mvuld_swin_attention_bwd_prep",
+            "mvuld_gelu_bwd", "mvuld_swin_qkv_bwd", "mvuld_gemm_dw", "mvuld_transpose_bf16", "mvuld_ln_rows"):
+    sig = {}
+    for name, a, s_, e_ in inst.records:
+        if name == ent:
+            key = tuple(int(v) for v in a if isinstance(v, int) and not isinstance(v, bool))
+            d = sig.setdefault(key, [0.0, 0]); d[0] += s_.elapsed_time(e_); d[1] += 1
+    for k, v in sorted(sig.items(), key=lambda kv: -kv[1][0])[:6]:
+        print(f"{ent} {k}: {v[0]:8.3f} ms x{v[1]:3d}  ({1e3 * v[0] / v[1]:7.1f} us each)")
