@@ -153,6 +153,9 @@ def work_of(name, args):
     if name in ("mvuld_gemm_ln_bf16", "mvuld_gemm_ln_wide_bf16"):
         M, N, K = args[4], args[5], args[6]
         return "gemm", 2.0 * M * N * K, 0.0
+    if name == "mvuld_mlp_ln_bf16":                 # fc1 + fc2 of one Mlp: 2 * M * C * 4C each
+        M, C = args[11], args[12]
+        return "gemm", 16.0 * M * C * C, 0.0
     if name == "mvuld_swin_qkv":
         B, H, W, C = args[8], args[9], args[10], args[11]
         return "gemm", 2.0 * B * H * W * C * 3 * C, 0.0

@@ -18,8 +18,11 @@
 //                              [128 rows x 64 k] through an NW-deep ring, in the order the MMA warp consumes them
 //   warp 1      MMA issuer   : issues G1(g + 1) BEFORE G2(g), so the tensor pipe works on the next chunk while the
 //                              epilogue warps run the GELU of this one
-//   warps 2..9  epilogue     : GELU of every chunk; the LayerNorm epilogue of row tile t - 1 is run after the first GELU
-//                              of row tile t (its accumulator is long complete by then: no wait on the tensor pipe)
+//   warps 2..9  GELU warps   : acc1 -> bias + GELU -> bf16 -> H, one chunk after the other
+//   warps 10..17 LN warps    : the LayerNorm + residual epilogue of row tile t while the GELU warps are already on row
+//                              tile t + 1 (with one set of eight warps doing both, every phase -- each latency bound on
+//                              two warps per scheduler -- added up: 31 k cycles per row tile against 27 k for the two
+//                              kernels)
 //
 // The accumulation order over K is that of the two-kernel path (k blocks of 64 in ascending order), and the GELU / LN
 // arithmetic is the same code, so the result is bit-identical to gemm + gemm_ln (tests/test_gpu_kernels.py).
@@ -32,7 +35,7 @@ namespace mv {
 
 constexpr int ML_BM = 128;
 constexpr int ML_HC = 128;                     // hidden columns per chunk
-constexpr int ML_THREADS = 320;
+constexpr int ML_THREADS = 64 + 256 + 256;     // TMA, MMA, 8 GELU warps, 8 LayerNorm warps
 constexpr int ML_UNIT = 128 * 64 * 2;          // 16 KB: [128 rows x 64 k] bf16, K-major, 128B swizzle
 
 template <int C>
@@ -95,7 +98,7 @@ mlp_ln_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int num_tiles = (M + ML_BM - 1) / ML_BM;
   const int nt = ((int)blockIdx.x < num_tiles) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int G = nt * NCH;                       // chunks this CTA runs
-  constexpr int EPI_THREADS = ML_THREADS - 64;
+  constexpr int EPI_THREADS = 256;              // GELU threads = LayerNorm threads
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
@@ -225,13 +228,13 @@ mlp_ln_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       if (g + 1 < G) issue_g1(g + 1);
       issue_g2(g);
     }
-  } else {
+  } else if (warp < 10) {
+    // ---- GELU warps: acc1[g & 1] (this thread's row, 64 columns) -> H[g & 1] ----
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;            // row within the tile
-
-    // ---- GELU of chunk g: acc1[g & 1] (this thread's row, 64 columns) -> H[g & 1] ----
-    auto gelu_chunk = [&](int g) {
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
       const int b = g & 1;
       const int j = g % NCH;
       const float* bias = ep.b1 + j * ML_HC + half * 64;
@@ -248,62 +251,70 @@ mlp_ln_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       mbar_arrive(&a1_empty[b]);                       // both halves are in registers: G1(g + 2) may overwrite
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        float x[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + hh * 32 + i));
-          x[i] = __uint_as_float(v[hh][i]) + bb.x;
-          x[i + 1] = __uint_as_float(v[hh][i + 1]) + bb.y;
-          x[i + 2] = __uint_as_float(v[hh][i + 2]) + bb.z;
-          x[i + 3] = __uint_as_float(v[hh][i + 3]) + bb.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) gelu_erf2(x[i], x[i + 1]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)                    // 16-byte unit hh * 4 + u of the 128-byte row
+        for (int u = 0; u < 4; ++u) {                  // 16-byte unit hh * 4 + u of the 128-byte row: 8 columns
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + hh * 32 + u * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hh * 32 + u * 8 + 4));
+          float x0 = __uint_as_float(v[hh][8 * u]) + b0.x, x1 = __uint_as_float(v[hh][8 * u + 1]) + b0.y;
+          float x2 = __uint_as_float(v[hh][8 * u + 2]) + b0.z, x3 = __uint_as_float(v[hh][8 * u + 3]) + b0.w;
+          float x4 = __uint_as_float(v[hh][8 * u + 4]) + b1.x, x5 = __uint_as_float(v[hh][8 * u + 5]) + b1.y;
+          float x6 = __uint_as_float(v[hh][8 * u + 6]) + b1.z, x7 = __uint_as_float(v[hh][8 * u + 7]) + b1.w;
+          gelu_erf2(x0, x1);
+          gelu_erf2(x2, x3);
+          gelu_erf2(x4, x5);
+          gelu_erf2(x6, x7);
           *reinterpret_cast<uint4*>(dst + ((((hh << 2) + u) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2(x[8 * u], x[8 * u + 1]), pack_bf16x2(x[8 * u + 2], x[8 * u + 3]),
-                         pack_bf16x2(x[8 * u + 4], x[8 * u + 5]), pack_bf16x2(x[8 * u + 6], x[8 * u + 7]));
+              make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3), pack_bf16x2(x4, x5), pack_bf16x2(x6, x7));
+        }
       }
       fence_proxy_async_smem();                        // generic-proxy writes -> visible to the tensor core's reads
       mbar_arrive(&h_full[b]);
+    }
+  } else {
+    // ---- LayerNorm warps: LayerNorm + residual epilogue of row tile tl (the epilogue of gemm_ln_kernel, N = C) ----
+    const int quarter = warp & 3;
+    const int half = (warp - 10) >> 2;
+    const int r = quarter * 32 + lane;
+    constexpr int HCOLS = C / 2;                       // columns per thread
+    const float invN = 1.0f / (float)C;
+    // lane l handles float4 column c4 = l % 8 of rows rl = 4 k + l / 8, k = 0..7, of this warp's 32 rows
+    const int c4 = lane & 7, rsub = lane >> 3;
+    uint8_t* myT = sT + (warp - 10) * 4096;
+    const int colbase = half * HCOLS;
+    // The residual rows are the only HBM operand of this epilogue and do not depend on the MMAs: the lines of row tile
+    // tl + 1 are pulled into L2 while the warps wait for the accumulator of row tile tl (no registers held; the loads
+    // under the TMEM read then cost an L2 hit instead of a DRAM round trip per 32-column chunk).
+    auto prefetch_shortcut = [&](int tl) {
+      if (!ep.shortcut || tl >= nt || c4 != 0) return;
+      const int row0 = ((int)blockIdx.x + tl * (int)gridDim.x) * ML_BM + quarter * 32;
+#pragma unroll
+      for (int cc = 0; cc < HCOLS / 32; ++cc)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int grow = row0 + 4 * k + rsub;
+          if (grow < M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.shortcut + (size_t)grow * C + colbase + cc * 32));
+        }
     };
-
-    // ---- LayerNorm + residual epilogue of row tile tl (the epilogue of gemm_ln_kernel, N = C) ----
-    auto ln_tile = [&](int tl) {
-      constexpr int HCOLS = C / 2;                     // columns per epilogue thread
+    prefetch_shortcut(0);
+#pragma unroll 1
+    for (int tl = 0; tl < nt; ++tl) {
       const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+      prefetch_shortcut(tl + 1);
       const int a = Cfg::NACC2 == 2 ? (tl & 1) : 0;
       const uint32_t apar = Cfg::NACC2 == 2 ? ((tl >> 1) & 1) : (tl & 1);
-      const float invN = 1.0f / (float)C;
+      const int wrow0 = tile * ML_BM + quarter * 32;
       mbar_wait(&a2_full[a], apar, 10);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::ACC2_COL + a * C + half * HCOLS;
-      const int colbase = half * HCOLS;
-      // lane l handles float4 column c4 = l % 8 of rows rl = 4 k + l / 8, k = 0..7, of this warp's 32 rows
-      const int c4 = lane & 7, rsub = lane >> 3;
-      const int wrow0 = tile * ML_BM + quarter * 32;
-      uint8_t* myT = sT + (warp - 2) * 4096;
-      float4 sc[2][8];
-      auto load_sc = [&](int buf, int c) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int grow = wrow0 + 4 * k + rsub;
-          sc[buf][k] = (ep.shortcut && grow < M)
-                           ? *reinterpret_cast<const float4*>(ep.shortcut + (size_t)grow * C + colbase + c + 4 * c4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      load_sc(0, 0);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < HCOLS; c += 64) {
-        uint32_t v[64];
-        tmem_ld32p(t0 + c, v);
-        tmem_ld32p(t0 + c + 32, v + 32);
+      for (int c = 0; c < HCOLS; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t0 + c, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
+        for (int i = 0; i < 32; i += 4) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(ep.b2 + colbase + c + i));
           const float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
           const float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
@@ -315,33 +326,38 @@ mlp_ln_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       st[half * ML_BM + r] = make_float2(s1, s2);
       named_bar_sync(1 + quarter, 64);
       const float2 other = st[(half ^ 1) * ML_BM + r];
-      const float mean = (s1 + other.x) * invN;
-      const float var = fmaxf((s2 + other.y) * invN - mean * mean, 0.f);
+      // half 0 adds (own, other), half 1 (other, own): the same order in both threads of a row
+      const float t1 = half == 0 ? s1 + other.x : other.x + s1, t2 = half == 0 ? s2 + other.y : other.y + s2;
+      const float mean = t1 * invN;
+      const float var = fmaxf(t2 * invN - mean * mean, 0.f);
       const float rstd = rsqrtf(var + ep.eps);
       const float nmr = -mean * rstd;
-      uint32_t v[2][32];
-      tmem_ld32(t0, v[0]);
-#pragma unroll
+#pragma unroll 1
       for (int cc = 0; cc < HCOLS / 32; ++cc) {
-        const int c = cc * 32;
-        const int col = colbase + c;
+        const int col = colbase + cc * 32;
+        uint32_t v[32];
+        tmem_ld32(t0 + cc * 32, v);
+        float4 sc[8];                                  // the residual rows, requested under the TMEM load
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int grow = wrow0 + 4 * k + rsub;
+          sc[k] = (ep.shortcut && grow < M) ? *reinterpret_cast<const float4*>(ep.shortcut + (size_t)grow * C + col + 4 * c4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
-        if (cc + 1 < HCOLS / 32) {
-          tmem_ld32(t0 + c + 32, v[(cc + 1) & 1]);
-          load_sc((cc + 1) & 1, c + 32);
-        } else {
+        if (cc + 1 == HCOLS / 32) {
           tc_fence_before();
-          mbar_arrive(&a2_empty[a]);                   // the accumulator is in registers: the next tile's G2 may start
+          mbar_arrive(&a2_empty[a]);                   // the accumulator is in registers: a later tile's G2 may start
         }
         __syncwarp();                                  // previous chunk's reads of myT are done
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(ep.b2 + col + 4 * i));
           float4 o;
-          o.x = fmaf(__uint_as_float(v[cc & 1][4 * i]) + b.x, rstd, nmr);
-          o.y = fmaf(__uint_as_float(v[cc & 1][4 * i + 1]) + b.y, rstd, nmr);
-          o.z = fmaf(__uint_as_float(v[cc & 1][4 * i + 2]) + b.z, rstd, nmr);
-          o.w = fmaf(__uint_as_float(v[cc & 1][4 * i + 3]) + b.w, rstd, nmr);
+          o.x = fmaf(__uint_as_float(v[4 * i]) + b.x, rstd, nmr);
+          o.y = fmaf(__uint_as_float(v[4 * i + 1]) + b.y, rstd, nmr);
+          o.z = fmaf(__uint_as_float(v[4 * i + 2]) + b.z, rstd, nmr);
+          o.w = fmaf(__uint_as_float(v[4 * i + 3]) + b.w, rstd, nmr);
           *reinterpret_cast<float4*>(myT + lane * 128 + ((i ^ (lane & 7)) << 4)) = o;
         }
         __syncwarp();
@@ -354,24 +370,14 @@ mlp_ln_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const float4 a4 = *reinterpret_cast<const float4*>(myT + rl * 128 + ((c4 ^ (rl & 7)) << 4));
           if (grow < M) {
             const size_t off = (size_t)grow * C + col + 4 * c4;
-            const float4 s = sc[cc & 1][k];
-            const float4 o = make_float4(fmaf(a4.x, g.x, be.x) + s.x, fmaf(a4.y, g.y, be.y) + s.y,
-                                         fmaf(a4.z, g.z, be.z) + s.z, fmaf(a4.w, g.w, be.w) + s.w);
+            const float4 o = make_float4(fmaf(a4.x, g.x, be.x) + sc[k].x, fmaf(a4.y, g.y, be.y) + sc[k].y,
+                                         fmaf(a4.z, g.z, be.z) + sc[k].z, fmaf(a4.w, g.w, be.w) + sc[k].w);
             if (ep.x32) *reinterpret_cast<float4*>(ep.x32 + off) = o;
             if (ep.xb) *reinterpret_cast<uint2*>(ep.xb + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
           }
         }
       }
-    };
-
-    for (int tl = 0; tl < nt; ++tl) {
-#pragma unroll 1
-      for (int j = 0; j < NCH; ++j) {
-        gelu_chunk(tl * NCH + j);
-        if (j == 0 && tl > 0) ln_tile(tl - 1);
-      }
     }
-    if (nt > 0) ln_tile(nt - 1);
   }
   tc_fence_before();
   __syncthreads();
