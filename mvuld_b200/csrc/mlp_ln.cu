@@ -24,6 +24,14 @@
 //                              two warps per scheduler -- added up: 31 k cycles per row tile against 27 k for the two
 //                              kernels)
 //
+// Measured (64 images; tools/time_mlp.py): C = 128 454 us against 624 us for the two kernels, C = 256 302 against 350.
+// What bounds it (variant builds): with the GELU arithmetic removed 317 us, with the LayerNorm stores removed 421, with
+// both 258 -- the skeleton itself (TMEM reads, H hand-off through the proxy fence, and 256 KB of weights per row tile
+// streamed from L2 by every SM = 6 TB/s of L2 -> SM traffic against the ~12 TB/s the fabric gives) is the floor, and the
+// GELU warps' time adds to it because G2(g) cannot be issued before GELU(g) is done.  Tried and not kept: the GELU warps
+// as two groups of four on alternate chunks (each group then waits for a G1 that sits behind the other group's G2 in the
+// MMA warp's in-order issue: 505 us); one set of eight warps for GELU and LayerNorm (667 us).
+//
 // The accumulation order over K is that of the two-kernel path (k blocks of 64 in ascending order), and the GELU / LN
 // arithmetic is the same code, so the result is bit-identical to gemm + gemm_ln (tests/test_gpu_kernels.py).
 // Algorithmic HBM bytes per row: 2 C (xb in) + 4 C (shortcut) + 4 C (x32 out) + 2 C (xb out) = 12 C, against
