@@ -384,15 +384,21 @@ attn_bwd_prep_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, co
     dst[i] = a;
   }
   ld[wrow] = make_float2(lse[wrow], d);
-  const __half2* qs = reinterpret_cast<const __half2*>(qh + wrow * 32);
-  const __half2* ks = reinterpret_cast<const __half2*>(kh + wrow * 32);
-  uint32_t* qd = reinterpret_cast<uint32_t*>(qb + wrow * 32);
-  uint32_t* kd = reinterpret_cast<uint32_t*>(kb + wrow * 32);
+  // fp16 -> bf16 copies of this (token, head)'s 32 q^ and 32 k^ values: four 16-byte loads and stores per tensor (as 16
+  // half2 accesses per thread every warp instruction touched 32 sectors for 4 bytes each)
+  const uint4* qs = reinterpret_cast<const uint4*>(qh + wrow * 32);
+  const uint4* ks = reinterpret_cast<const uint4*>(kh + wrow * 32);
+  uint4* qd = reinterpret_cast<uint4*>(qb + wrow * 32);
+  uint4* kd = reinterpret_cast<uint4*>(kb + wrow * 32);
+  auto cvt = [](uint32_t h2) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+    return pack_bf16x2(f.x, f.y);
+  };
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float2 a = __half22float2(qs[i]), c = __half22float2(ks[i]);
-    qd[i] = pack_bf16x2(a.x, a.y);
-    kd[i] = pack_bf16x2(c.x, c.y);
+  for (int i = 0; i < 4; ++i) {
+    const uint4 a = __ldg(qs + i), c = __ldg(ks + i);
+    qd[i] = make_uint4(cvt(a.x), cvt(a.y), cvt(a.z), cvt(a.w));
+    kd[i] = make_uint4(cvt(c.x), cvt(c.y), cvt(c.z), cvt(c.w));
   }
 }
 

@@ -201,7 +201,7 @@ swin_qkv_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ dk, 
     {
       float g[32], u[32];
       const float4* gp = reinterpret_cast<const float4*>(dq + wrow * 32);
-      const __half2* qp = reinterpret_cast<const __half2*>(qh + wrow * 32);
+      const uint4* qp = reinterpret_cast<const uint4*>(qh + wrow * 32);     // four 16-byte loads, not 16 half2 loads
       float dot = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -209,10 +209,15 @@ swin_qkv_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ dk, 
         g[4 * i] = a.x; g[4 * i + 1] = a.y; g[4 * i + 2] = a.z; g[4 * i + 3] = a.w;
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 a = __half22float2(qp[i]);
-        u[2 * i] = a.x * inv_qs;
-        u[2 * i + 1] = a.y * inv_qs;
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = __ldg(qp + i);
+        const uint32_t h2[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2[j]));
+          u[8 * i + 2 * j] = f.x * inv_qs;
+          u[8 * i + 2 * j + 1] = f.y * inv_qs;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) dot += u[i] * g[i];      // q~ . dq
@@ -230,7 +235,7 @@ swin_qkv_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ dk, 
     {
       float g[32], u[32];
       const float4* gp = reinterpret_cast<const float4*>(dk + wrow * 32);
-      const __half2* kp = reinterpret_cast<const __half2*>(kh + wrow * 32);
+      const uint4* kp = reinterpret_cast<const uint4*>(kh + wrow * 32);
       float dot = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -238,10 +243,15 @@ swin_qkv_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ dk, 
         g[4 * i] = a.x; g[4 * i + 1] = a.y; g[4 * i + 2] = a.z; g[4 * i + 3] = a.w;
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 a = __half22float2(kp[i]);
-        u[2 * i] = a.x;
-        u[2 * i + 1] = a.y;
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = __ldg(kp + i);
+        const uint32_t h2[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2[j]));
+          u[8 * i + 2 * j] = f.x;
+          u[8 * i + 2 * j + 1] = f.y;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) dot += u[i] * g[i];
