@@ -360,11 +360,18 @@ int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gamma, const f
  * mode 2); dv = gradient of the LN input as bf16 and / or fp32; dgamma / dbeta accumulated.  swin_transformer_v2.py:301,
  * 304,362; HF RobertaSelfOutput / RobertaOutput. */
 int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const float* gamma, const float* dout, void* dv_bf16,
-                      float* dv_f32, float* dgamma, float* dbeta, float* partials, int M, int C, float eps, int mode,
-                      mvuld_stream_t stream);
-/* rows of the fp32 [rows, 2, C] partials workspace mvuld_ln_rows_bwd needs for M rows: dgamma / dbeta are summed over
+                      float* dv_f32, float* dgamma, float* dbeta, float* dbias, float* partials, int M, int C, float eps,
+                      int mode, mvuld_stream_t stream);
+/* dbias (may be null): += column sums of dv, i.e. the bias gradient of the dense layer whose output the LayerNorm
+ * normalises (proj / fc2, RoBERTa output.dense) -- saves a separate pass over dv.
+ * rows of the fp32 [rows, 3, C] partials workspace mvuld_ln_rows_bwd needs for M rows: dgamma / dbeta are summed over
  * the blocks in a fixed order (bit-reproducible gradients, no atomics). */
 int mvuld_ln_rows_bwd_blocks(int M);
+/* GELU backward fused with the column sums of its result (fc1's bias gradient): dpre [M, C] bf16 = dh * GELU'(pre),
+ * dbias[c] += sum_rows dpre[:, c] (fixed summation order).  partials: fp32 [mvuld_colsum_slabs(M, C), C] (may be null
+ * when that is 1).  C %% 8 == 0. */
+int mvuld_gelu_bwd_colsum(const void* pre, const void* dh, void* dpre, float* dbias, float* partials, int M, int C,
+                          mvuld_stream_t stream);
 /* exact (erf) GELU backward: dpre = dh * GELU'(pre), bf16, n %% 8 == 0 (Mlp, swin_transformer_v2.py:26-32). */
 int mvuld_gelu_bwd(const void* pre, const void* dh, void* dpre, long long n, mvuld_stream_t stream);
 /* fp32 strided ELU backward with a bf16 result (image / text projections, GraphModel.py:153-159). */

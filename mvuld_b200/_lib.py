@@ -78,9 +78,10 @@ SIGNATURES = {
     "mvuld_gemm_dw_workspace": [_I, _I, _I],
     "mvuld_colsum": [_P, _I, _I, _P, _P, _I, _I, _P],
     "mvuld_colsum_slabs": [_I, _I],
-    "mvuld_ln_rows_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "mvuld_ln_rows_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
     "mvuld_ln_rows_bwd_blocks": [_I],
     "mvuld_gelu_bwd": [_P, _P, _P, _LL, _P],
+    "mvuld_gelu_bwd_colsum": [_P, _P, _P, _P, _P, _I, _I, _P],
     "mvuld_elu_bwd": [_P, _P, _P, _LL, _I, C.c_ulonglong, _F, _P],
     "mvuld_dropout_bf16": [_P, _P, _LL, C.c_ulonglong, _F, _P],
     "mvuld_bn_cols_fwd": [_P, _P, _P, _F, _P, _I, _P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P],
@@ -110,7 +111,7 @@ _SYNC_EACH = bool(os.environ.get("MVULD_SYNC_EACH"))     # debug: synchronise af
 _lib = None
 launch_count = 0     # kernels launched through this binding (bench.py reports it as gpu_launches)
 _LAUNCHES_PER_CALL = {"mvuld_cpb_table": 2, "mvuld_csr_from_coo": 5, "mvuld_gat_bwd": 3, "mvuld_sumsq_f32": 2,
-                      "mvuld_ln_rows_bwd": 2, "mvuld_pos_branch_bwd": 2, "mvuld_swin_bias_grad": 2,
+                      "mvuld_ln_rows_bwd": 2, "mvuld_gelu_bwd_colsum": 2, "mvuld_pos_branch_bwd": 2, "mvuld_swin_bias_grad": 2,
                       "mvuld_swin_qkv_bwd": 2, "mvuld_colsum": 2, "mvuld_gemm_dw": 2}
 
 
@@ -197,9 +198,18 @@ def colsum(x, is_bf16: int, ldx: int, out: torch.Tensor, R: int, C: int):
     call("mvuld_colsum", x, is_bf16, ldx, out, part, R, C)
 
 
+def gelu_bwd_colsum(pre: torch.Tensor, dh: torch.Tensor, dpre: torch.Tensor, dbias: torch.Tensor):
+    """dpre = dh * GELU'(pre) (bf16 [M, C]) and dbias += column sums of dpre, one pass (fixed summation order)."""
+    M, Cc = pre.shape
+    assert pre.is_contiguous() and dh.is_contiguous() and dpre.is_contiguous() and dh.shape == pre.shape == dpre.shape
+    slabs = load().mvuld_colsum_slabs(int(M), int(Cc))
+    part = torch.empty(slabs * Cc, device=pre.device, dtype=torch.float32) if slabs > 1 else None
+    call("mvuld_gelu_bwd_colsum", pre, dh, dpre, dbias, part, M, Cc)
+
+
 def ln_rows_bwd_partials(M: int, C: int, device) -> torch.Tensor:
     """Workspace of ``mvuld_ln_rows_bwd`` for M rows of C columns (fixed-order dgamma / dbeta reduction)."""
-    return torch.empty(load().mvuld_ln_rows_bwd_blocks(int(M)) * 2 * C, device=device, dtype=torch.float32)
+    return torch.empty(load().mvuld_ln_rows_bwd_blocks(int(M)) * 3 * C, device=device, dtype=torch.float32)
 
 
 def _sync_check(name: str):

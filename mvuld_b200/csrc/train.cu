@@ -696,12 +696,15 @@ gat_attn_grad_kernel(const bf16* __restrict__ z, const float* __restrict__ del, 
 // Latency: a warp keeps RPW = NR * (32 / LPR) rows in flight (LPR = 16 lanes per row when a row has <= 16 units, so a
 // C = 128 row does not idle half the warp), and y, the shortcut and dout of all of them are requested before the first
 // reduction (one row per warp with dout loaded after two shuffle reductions ran the C = 128 launches at 1.8 TB/s).
-template <int UNITS, int LPR, int NR>
+// DB: also the column sums of dv (= the bias gradient of the dense layer in front of the LayerNorm) as a third row of the
+// block's partials: saves a separate pass over dv.
+template <int UNITS, int LPR, int NR, bool DB>
 __global__ void __launch_bounds__(256)
 ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, const float* __restrict__ gamma,
                    const float* __restrict__ dout, bf16* __restrict__ dvb, float* __restrict__ dv32,
                    float* __restrict__ partials, int M, int C, float eps, int mode) {
-  extern __shared__ float red[];                  // [8 warps][32 / LPR][2][C]
+  extern __shared__ float red[];                  // [8 warps][32 / LPR][NP][C]
+  constexpr int NP = DB ? 3 : 2;                  // rows of a block's partials: dgamma, dbeta (, dbias)
   constexpr int RPP = 32 / LPR;                   // rows per pass of a warp
   constexpr int RPW = RPP * NR;                   // rows a warp has in flight
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -713,11 +716,15 @@ ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcu
     for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
-  float dg[UNITS][8], db[UNITS][8];
+  float dg[UNITS][8], db[UNITS][8], dbi[DB ? UNITS : 1][8];
 #pragma unroll
   for (int k = 0; k < UNITS; ++k)
 #pragma unroll
     for (int q = 0; q < 8; ++q) dg[k][q] = db[k][q] = 0.f;
+#pragma unroll
+  for (int k = 0; k < (DB ? UNITS : 1); ++k)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dbi[k][q] = 0.f;
   for (int row0 = (blockIdx.x * 8 + warp) * RPW; row0 < M; row0 += gridDim.x * 8 * RPW) {
     float v[NR][UNITS][8], d[NR][UNITS][8];
 #pragma unroll
@@ -795,6 +802,10 @@ ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcu
           float o[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) o[q] = rstd * (d[n][k][q] - m1 - v[n][k][q] * m2);
+          if (DB) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dbi[k][q] += o[q];
+          }
           if (dv32) {
             float4* op = reinterpret_cast<float4*>(dv32 + (size_t)row * C + u * 8);
             op[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -817,21 +828,24 @@ ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcu
     if (u < units) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        red[((warp * RPP + sub) * 2 + 0) * C + u * 8 + q] = dg[k][q];
-        red[((warp * RPP + sub) * 2 + 1) * C + u * 8 + q] = db[k][q];
+        red[((warp * RPP + sub) * NP + 0) * C + u * 8 + q] = dg[k][q];
+        red[((warp * RPP + sub) * NP + 1) * C + u * 8 + q] = db[k][q];
+        if (DB) red[((warp * RPP + sub) * NP + 2) * C + u * 8 + q] = dbi[k][q];
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    float a[NP];
 #pragma unroll
-    for (int w8 = 0; w8 < 8 * RPP; ++w8) {
-      a += red[(w8 * 2 + 0) * C + c];
-      b += red[(w8 * 2 + 1) * C + c];
-    }
-    partials[((size_t)blockIdx.x * 2 + 0) * C + c] = a;      // block order is fixed by ln_rows_bwd_final_kernel
-    partials[((size_t)blockIdx.x * 2 + 1) * C + c] = b;
+    for (int j = 0; j < NP; ++j) a[j] = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8 * RPP; ++w8)
+#pragma unroll
+      for (int j = 0; j < NP; ++j) a[j] += red[(w8 * NP + j) * C + c];
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+      partials[((size_t)blockIdx.x * NP + j) * C + c] = a[j];   // block order is fixed by ln_rows_bwd_final_kernel
   }
 }
 // Sum of the per-block partials in a FIXED order with the blocks split over 32 thread rows: thread (slice, column) adds
@@ -840,30 +854,25 @@ ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcu
 // LayerNorm backward took.)
 __global__ void __launch_bounds__(1024)
 ln_rows_bwd_final_kernel(const float* __restrict__ partials, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                         int nblocks, int C) {
-  __shared__ float sa[32][33], sb[32][33];
+                         float* __restrict__ dbias, int nblocks, int C) {
+  __shared__ float sa[3][32][33];
+  const int NP = dbias ? 3 : 2;
   const int c = blockIdx.x * 32 + threadIdx.x, slice = threadIdx.y;
   const int per = (nblocks + 31) / 32;
   const int k0 = slice * per, k1 = min(nblocks, k0 + per);
-  float a = 0.f, b = 0.f;
+  float a[3] = {0.f, 0.f, 0.f};
   if (c < C) {
-    for (int k = k0; k < k1; ++k) {
-      a += partials[((size_t)k * 2 + 0) * C + c];
-      b += partials[((size_t)k * 2 + 1) * C + c];
-    }
+    for (int k = k0; k < k1; ++k)
+      for (int j = 0; j < NP; ++j) a[j] += partials[((size_t)k * NP + j) * C + c];
   }
-  sa[slice][threadIdx.x] = a;
-  sb[slice][threadIdx.x] = b;
+  for (int j = 0; j < NP; ++j) sa[j][slice][threadIdx.x] = a[j];
   __syncthreads();
-  if (slice == 0 && c < C) {
-    float ta = 0.f, tb = 0.f;
+  if (slice < NP && c < C) {                       // thread row j finishes output j
+    float t = 0.f;
 #pragma unroll
-    for (int s = 0; s < 32; ++s) {
-      ta += sa[s][threadIdx.x];
-      tb += sb[s][threadIdx.x];
-    }
-    dgamma[c] += ta;
-    dbeta[c] += tb;
+    for (int s2 = 0; s2 < 32; ++s2) t += sa[slice][s2][threadIdx.x];
+    float* out = slice == 0 ? dgamma : (slice == 1 ? dbeta : dbias);
+    out[c] += t;
   }
 }
 
@@ -1281,9 +1290,9 @@ extern "C" int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gam
 }
 extern "C" int mvuld_ln_rows_bwd_blocks(int M);
 extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const float* gamma, const float* dout, void* dv_bf16,
-                                 float* dv_f32, float* dgamma, float* dbeta, float* partials, int M, int C, float eps,
-                                 int mode, cudaStream_t stream) {
-  MV_CHECK_ARG(partials != nullptr, "ln_rows_bwd: the [mvuld_ln_rows_bwd_blocks(M), 2, C] partials workspace is null");
+                                 float* dv_f32, float* dgamma, float* dbeta, float* dbias, float* partials, int M, int C,
+                                 float eps, int mode, cudaStream_t stream) {
+  MV_CHECK_ARG(partials != nullptr, "ln_rows_bwd: the [mvuld_ln_rows_bwd_blocks(M), 3, C] partials workspace is null");
   MV_CHECK_ARG(C % 8 == 0 && C <= 1024, "ln_rows_bwd: C=%d must be a multiple of 8 and <= 1024", C);
   MV_CHECK_ARG(mode >= 0 && mode <= 2 && (mode != 2 || shortcut), "ln_rows_bwd: mode %d (mode 2 needs the shortcut)", mode);
   MV_CHECK_ARG(dgamma && dbeta && (dv_bf16 || dv_f32), "ln_rows_bwd: dgamma / dbeta and one of the dv outputs are required");
@@ -1291,14 +1300,14 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
   const bf16* yp = reinterpret_cast<const bf16*>(y);
   bf16* dvp = reinterpret_cast<bf16*>(dv_bf16);
   int grid = 0;
-#define MV_LN_BWD(U, LPR, NR)                                                                                          \
+#define MV_LN_BWD(U, LPR, NR, DB)                                                                                      \
   do {                                                                                                                 \
     constexpr int RPW = (32 / (LPR)) * (NR);                                                                           \
-    const size_t smem = (size_t)16 * (32 / (LPR)) * C * sizeof(float);                                                 \
-    auto kern = ln_rows_bwd_kernel<U, LPR, NR>;                                                                        \
+    const size_t smem = (size_t)8 * ((DB) ? 3 : 2) * (32 / (LPR)) * C * sizeof(float);                                 \
+    auto kern = ln_rows_bwd_kernel<U, LPR, NR, DB>;                                                                    \
     static unsigned long long attr_set = 0;                                                                            \
     if (first_use_on_current_device(&attr_set))                                                                        \
-      MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (32 / (LPR)) * 1024 * 4)); \
+      MV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * (32 / (LPR)) * 1024 * 4)); \
     /* exactly the blocks the GPU holds at once: a second wave would serialise one more load -> reduce -> store chain */ \
     int per_sm = 1;                                                                                                    \
     MV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                               \
@@ -1306,19 +1315,100 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
     grid = std::min((M + 8 * RPW - 1) / (8 * RPW), std::min(per_sm * num_sms(), mvuld_ln_rows_bwd_blocks(M)));         \
     kern<<<grid, 256, smem, stream>>>(yp, shortcut, gamma, dout, dvp, dv_f32, partials, M, C, eps, mode);              \
   } while (0)
-  if (C <= 128) MV_LN_BWD(1, 16, 2);
-  else if (C <= 256) MV_LN_BWD(1, 32, 2);
-  else if (C <= 512) MV_LN_BWD(2, 32, 2);
-  else if (C <= 768) MV_LN_BWD(3, 32, 1);
-  else MV_LN_BWD(4, 32, 1);
+  if (dbias) {        // one row per warp pass where the third accumulator would cost a resident block
+    if (C <= 128) MV_LN_BWD(1, 16, 2, true);
+    else if (C <= 256) MV_LN_BWD(1, 32, 2, true);
+    else if (C <= 512) MV_LN_BWD(2, 32, 1, true);
+    else if (C <= 768) MV_LN_BWD(3, 32, 1, true);
+    else MV_LN_BWD(4, 32, 1, true);
+  } else {
+    if (C <= 128) MV_LN_BWD(1, 16, 2, false);
+    else if (C <= 256) MV_LN_BWD(1, 32, 2, false);
+    else if (C <= 512) MV_LN_BWD(2, 32, 2, false);
+    else if (C <= 768) MV_LN_BWD(3, 32, 1, false);
+    else MV_LN_BWD(4, 32, 1, false);
+  }
 #undef MV_LN_BWD
   MV_LAUNCH_OK();
-  ln_rows_bwd_final_kernel<<<(C + 31) / 32, dim3(32, 32), 0, stream>>>(partials, dgamma, dbeta, grid, C);
+  ln_rows_bwd_final_kernel<<<(C + 31) / 32, dim3(32, 32), 0, stream>>>(partials, dgamma, dbeta, dbias, grid, C);
   MV_LAUNCH_OK();
   return 0;
 }
-// rows of the partials workspace mvuld_ln_rows_bwd needs for M rows ([blocks, 2, C] floats)
+// rows of the partials workspace mvuld_ln_rows_bwd needs for M rows ([blocks, 3, C] floats)
 extern "C" int mvuld_ln_rows_bwd_blocks(int M) { return std::min((M + 7) / 8, 6 * num_sms()); }   // 2 blocks per SM left the row loop latency bound (5.6 ms of a 66 ms SwinV2 step)
+// GELU backward + the column sums of its result in one pass (dpre = dh GELU'(pre) is the gradient of fc1's output: its
+// column sums are fc1's bias gradient).  Thread = (row lane, 8-column unit) as in colsum_kernel; two rows in flight.
+namespace mv {
+__global__ void __launch_bounds__(256)
+gelu_bwd_colsum_kernel(const bf16* __restrict__ pre, const bf16* __restrict__ dh, bf16* __restrict__ dpre,
+                       float* __restrict__ out, float* __restrict__ partials, int R, int C, int rows_per_slab) {
+  __shared__ float red[256 * 8];
+  const int units_total = C >> 3;
+  const int u0 = blockIdx.x * 256;
+  const int upr = min(256, units_total - u0);
+  const int rpp = 256 / upr;
+  const int tr = threadIdx.x / upr, tu = threadIdx.x - tr * upr;
+  const bool active = tr < rpp;
+  const int c0 = (u0 + tu) * 8;
+  const int rbeg = blockIdx.y * rows_per_slab, rend = min(R, rbeg + rows_per_slab);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto one = [&](const uint4& xr, const uint4& dr, size_t off) {
+    const uint32_t xs[4] = {xr.x, xr.y, xr.z, xr.w}, ds[4] = {dr.x, dr.y, dr.z, dr.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float g0 = bf16_lo(ds[q]) * gelu_erf_grad(bf16_lo(xs[q])), g1 = bf16_hi(ds[q]) * gelu_erf_grad(bf16_hi(xs[q]));
+      acc[2 * q] += g0;
+      acc[2 * q + 1] += g1;
+      o[q] = pack_bf16x2(g0, g1);
+    }
+    *reinterpret_cast<uint4*>(dpre + off) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  if (active) {
+    int r = rbeg + tr;
+    for (; r + rpp < rend; r += 2 * rpp) {
+      const size_t o0 = (size_t)r * C + c0, o1 = (size_t)(r + rpp) * C + c0;
+      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(pre + o0)), d0 = __ldg(reinterpret_cast<const uint4*>(dh + o0));
+      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(pre + o1)), d1 = __ldg(reinterpret_cast<const uint4*>(dh + o1));
+      one(x0, d0, o0);
+      one(x1, d1, o1);
+    }
+    for (; r < rend; r += rpp) {
+      const size_t o0 = (size_t)r * C + c0;
+      one(__ldg(reinterpret_cast<const uint4*>(pre + o0)), __ldg(reinterpret_cast<const uint4*>(dh + o0)), o0);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  if (active && tr == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = 0.f;
+      for (int q = 0; q < rpp; ++q) t += red[(q * upr + tu) * 8 + k];
+      if (gridDim.y == 1) out[c0 + k] += t;
+      else partials[(size_t)blockIdx.y * C + c0 + k] = t;
+    }
+  }
+}
+}  // namespace mv
+extern "C" int mvuld_gelu_bwd_colsum(const void* pre, const void* dh, void* dpre, float* dbias, float* partials, int M,
+                                     int C, cudaStream_t stream) {
+  MV_CHECK_ARG(C % 8 == 0 && pre && dh && dpre && dbias, "gelu_bwd_colsum: C %% 8 and non-null pointers");
+  if (M <= 0) return 0;
+  const int slabs = mvuld_colsum_slabs(M, C);
+  MV_CHECK_ARG(slabs == 1 || partials != nullptr, "gelu_bwd_colsum: the [mvuld_colsum_slabs(M, C), C] partials workspace is null");
+  const int rps = (M + slabs - 1) / slabs;
+  dim3 grid((C / 8 + 255) / 256, slabs);
+  gelu_bwd_colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(pre), reinterpret_cast<const bf16*>(dh),
+                                                   reinterpret_cast<bf16*>(dpre), dbias, partials, M, C, rps);
+  MV_LAUNCH_OK();
+  if (slabs > 1) {
+    colsum_final_kernel<<<(C + 31) / 32, dim3(32, 32), 0, stream>>>(partials, dbias, slabs, C);
+    MV_LAUNCH_OK();
+  }
+  return 0;
+}
 extern "C" int mvuld_gelu_bwd(const void* pre, const void* dh, void* dpre, long long n, cudaStream_t stream) {
   MV_CHECK_ARG(n % 8 == 0, "gelu_bwd: n %% 8");
   if (n <= 0) return 0;

@@ -219,11 +219,13 @@ class RobertaTrainer:
                 on_bucket(self.buckets[bucket_i])
                 bucket_i += 1
 
-        def ln_bwd(y, shortcut, gname, bname, dout):
-            """LN(y + shortcut) backward -> (dv fp32: gradient of the sum, i.e. of both addends; dv bf16)."""
+        def ln_bwd(y, shortcut, gname, bname, dout, bias_name=None):
+            """LN(y + shortcut) backward -> (dv fp32: gradient of the sum, i.e. of both addends; dv bf16); the gradient
+            of the dense bias in front of the LayerNorm (column sums of dv) comes out of the same kernel."""
             dvb, dv32 = e((M, H), bf), e((M, H), f32)
             _lib.call("mvuld_ln_rows_bwd", y, shortcut, pv(gname), dout, dvb, dv32, gv(gname), gv(bname),
-                      _lib.ln_rows_bwd_partials(M, H, dev), M, H, eps, 2 if shortcut is not None else 0)
+                      gv(bias_name) if bias_name else None, _lib.ln_rows_bwd_partials(M, H, dev), M, H, eps,
+                      2 if shortcut is not None else 0)
             return dv32, dvb
 
         dx = e((M, H), f32)
@@ -231,22 +233,20 @@ class RobertaTrainer:
         for i in range(len(self.enc.encoder.layer) - 1, -1, -1):
             p, s, wt = f"encoder.layer.{i}.", ctx["layers"][i], self.wt[i]
             # ---- x2 = LN(dense2(gelu(dense1(x1))) + x1) ----
-            d32, db16 = ln_bwd(s["y2"], s["x32_1"], p + "output.LayerNorm.weight", p + "output.LayerNorm.bias", dx)
+            d32, db16 = ln_bwd(s["y2"], s["x32_1"], p + "output.LayerNorm.weight", p + "output.LayerNorm.bias", dx,
+                               bias_name=p + "output.dense.bias")
             _lib.gemm_dw(db16, s["hid"], gv(p + "output.dense.weight"))
-            _lib.colsum(db16, 1, H, gv(p + "output.dense.bias"), M, H)
             dhid = e((M, I), bf)
             _lib.gemm(db16, wt["o2"], out_bf16=dhid)
             dpre = e((M, I), bf)
-            _lib.call("mvuld_gelu_bwd", s["pre"], dhid, dpre, M * I)
+            _lib.gelu_bwd_colsum(s["pre"].view(M, I), dhid, dpre, gv(p + "intermediate.dense.bias"))
             _lib.gemm_dw(dpre, s["xb1"], gv(p + "intermediate.dense.weight"))
-            _lib.colsum(dpre, 1, I, gv(p + "intermediate.dense.bias"), M, I)
             _lib.gemm(dpre, wt["i"], res=d32, out_f32=d32)                      # dx1 = d(sum) + dpre W_i
             del dhid, dpre
             # ---- x1 = LN(dense(attention(x0)) + x0) ----
             d32b, db16 = ln_bwd(s["y1"], s["x32_in"], p + "attention.output.LayerNorm.weight",
-                                p + "attention.output.LayerNorm.bias", d32)
+                                p + "attention.output.LayerNorm.bias", d32, bias_name=p + "attention.output.dense.bias")
             _lib.gemm_dw(db16, s["att"], gv(p + "attention.output.dense.weight"))
-            _lib.colsum(db16, 1, H, gv(p + "attention.output.dense.bias"), M, H)
             datt = e((M, H), bf)
             _lib.gemm(db16, wt["o"], out_bf16=datt)
             dOh, ld = e((M, H), bf), e((B * nH, L, 2), f32)

@@ -262,11 +262,13 @@ class SwinTrainer:
                 on_bucket(self.buckets[bucket_i])
                 bucket_i += 1
 
-        def ln_bwd(y, gamma_name, beta_name, dout, M, C, eps, mode, want_f32=False):
+        def ln_bwd(y, gamma_name, beta_name, dout, M, C, eps, mode, want_f32=False, bias_name=None):
+            """bias_name: the bias of the dense layer in front of the LayerNorm; its gradient (column sums of dv) comes
+            out of the same kernel."""
             dvb = None if want_f32 else e((M, C), bf)
             dv32 = e((M, C), f32) if want_f32 else None
             _lib.call("mvuld_ln_rows_bwd", y, None, pv(gamma_name), dout, dvb, dv32, gv(gamma_name), gv(beta_name),
-                      _lib.ln_rows_bwd_partials(M, C, dev), M, C, float(eps), mode)
+                      gv(bias_name) if bias_name else None, _lib.ln_rows_bwd_partials(M, C, dev), M, C, float(eps), mode)
             return dv32 if want_f32 else dvb
 
         last = self.blocks[-1]
@@ -295,21 +297,19 @@ class SwinTrainer:
                 ready(Pm + "norm.weight", Pm + "norm.bias", Pm + "reduction.weight")
             # ---- x2 = x1 + LN2(fc2(gelu(fc1(x1)))) ----
             hdim = self.shapes[P + "mlp.fc1.weight"][0]
-            dy2 = ln_bwd(s["y2"], P + "norm2.weight", P + "norm2.bias", dx, M, C, b["eps2"], 1)
+            dy2 = ln_bwd(s["y2"], P + "norm2.weight", P + "norm2.bias", dx, M, C, b["eps2"], 1, bias_name=P + "mlp.fc2.bias")
             self._grad_w(dy2, s["hid"], P + "mlp.fc2.weight")
-            _lib.colsum(dy2, 1, C, gv(P + "mlp.fc2.bias"), M, C)
             dhid = e((M, hdim), bf)
             _lib.gemm(dy2, self.wt[P + "mlp.fc2.weight"], out_bf16=dhid)
             dpre = e((M, hdim), bf)
-            _lib.call("mvuld_gelu_bwd", s["pre"], dhid, dpre, M * hdim)
+            _lib.gelu_bwd_colsum(s["pre"].view(M, hdim), dhid, dpre, gv(P + "mlp.fc1.bias"))   # + fc1's bias gradient
             self._grad_w(dpre, s["xb1"], P + "mlp.fc1.weight")
-            _lib.colsum(dpre, 1, hdim, gv(P + "mlp.fc1.bias"), M, hdim)
             _lib.gemm(dpre, self.wt[P + "mlp.fc1.weight"], res=dx, out_f32=dx)              # dx1 = dx2 + dpre W_fc1
             del dhid, dpre
             # ---- x1 = x0 + LN1(proj(attention(x0))) ----
-            dy1 = ln_bwd(s["y1"], P + "norm1.weight", P + "norm1.bias", dx, M, C, b["eps1"], 1)
+            dy1 = ln_bwd(s["y1"], P + "norm1.weight", P + "norm1.bias", dx, M, C, b["eps1"], 1,
+                         bias_name=P + "attn.proj.bias")
             self._grad_w(dy1, s["att"], P + "attn.proj.weight")
-            _lib.colsum(dy1, 1, C, gv(P + "attn.proj.bias"), M, C)
             datt = e((M, C), bf)
             _lib.gemm(dy1, self.wt[P + "attn.proj.weight"], out_bf16=datt)
             dOw, ld = e((n_bh, N, 32), bf), e((n_bh, N, 2), f32)
@@ -347,9 +347,9 @@ class SwinTrainer:
         E = m.embed_dim
         Hp, Wp = m.patches_resolution
         M = B * Hp * Wp
-        dy = ln_bwd(ctx["pe"]["y"], "patch_embed.norm.weight", "patch_embed.norm.bias", dx, M, E, m.patch_embed.norm.eps, 0)
+        dy = ln_bwd(ctx["pe"]["y"], "patch_embed.norm.weight", "patch_embed.norm.bias", dx, M, E, m.patch_embed.norm.eps, 0,
+                    bias_name="patch_embed.proj.bias")
         self._grad_w(dy, ctx["pe"]["a0"], "patch_embed.proj.weight", (E, 48))
-        _lib.colsum(dy, 1, E, gv("patch_embed.proj.bias"), M, E)
         ready(*[n for n in self.names if n.startswith("patch_embed.")])
         if on_bucket is not None:
             while bucket_i < len(self.buckets):

@@ -198,19 +198,42 @@ def test_ln_rows_backward_matches_autograd(M, C, mode):
     out.backward(dout)
     dvb = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
     dv32 = torch.empty(M, C, device=DEV)
-    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dg, db, dbi = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     _lib.call("mvuld_ln_rows_bwd", y.to(DEV), sc.to(DEV) if mode else None, gamma.to(DEV), dout.to(DEV), dvb, dv32, dg, db,
-              _lib.ln_rows_bwd_partials(M, C, DEV), M, C, 1e-5, mode)
+              dbi, _lib.ln_rows_bwd_partials(M, C, DEV), M, C, 1e-5, mode)
     torch.cuda.synchronize()
     assert rel_err(dv32, yr.grad) < 1e-4
     assert rel_err(dvb, yr.grad) < 6e-3                     # bf16 rounding of the same values
     assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    # bias gradient of the dense layer in front of the LayerNorm = column sums of dv (sums cancel: compare in absolute terms)
+    assert float((dbi.cpu() - yr.grad.sum(0)).abs().max()) < 1e-3 * float(yr.grad.abs().sum(0).max())
     if mode == 2:
         assert rel_err(dv32, scr.grad) < 1e-4               # LN(y + shortcut): the shortcut's gradient is dv
     # accumulation semantics: a second call adds to dgamma / dbeta
     _lib.call("mvuld_ln_rows_bwd", y.to(DEV), sc.to(DEV) if mode else None, gamma.to(DEV), dout.to(DEV), dvb, None, dg, db,
-              _lib.ln_rows_bwd_partials(M, C, DEV), M, C, 1e-5, mode)
+              None, _lib.ln_rows_bwd_partials(M, C, DEV), M, C, 1e-5, mode)
     assert rel_err(dg, 2 * gr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("M,C", [(3000, 512), (77, 3072), (25088, 2048), (5, 4096)])
+def test_gelu_backward_with_bias_gradient(M, C):
+    """mvuld_gelu_bwd_colsum: the same dpre as mvuld_gelu_bwd, bit for bit, plus its column sums (fc1's bias gradient);
+    rows not divisible by the row lanes, two column segments (C > 2048), accumulation into dbias, repeatable."""
+    r = torch.Generator(device=DEV).manual_seed(M + C)
+    pre = (torch.randn(M, C, device=DEV, generator=r) * 2.0).to(torch.bfloat16)
+    dh = torch.randn(M, C, device=DEV, generator=r).to(torch.bfloat16)
+    ref = torch.empty_like(pre)
+    _lib.call("mvuld_gelu_bwd", pre, dh, ref, M * C)
+    dpre, dbias = torch.empty_like(pre), torch.ones(C, device=DEV)
+    _lib.gelu_bwd_colsum(pre, dh, dpre, dbias)
+    assert torch.equal(dpre, ref)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).backward(dh.float())
+    want = 1.0 + x.grad.sum(0)
+    assert float((dbias - want).abs().max()) < 2e-3 * max(1.0, float(x.grad.abs().sum(0).max()))
+    dbias2 = torch.ones(C, device=DEV)
+    _lib.gelu_bwd_colsum(pre, dh, dpre, dbias2)
+    assert torch.equal(dbias, dbias2)
 
 
 def test_gelu_backward_matches_autograd():

@@ -27,7 +27,7 @@ for M, C in ((25088, 512), (401408, 128), (100352, 256), (6272, 1024)):
     dvb = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
     dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     part = _lib.ln_rows_bwd_partials(M, C, dev)
-    t = timed(lambda: _lib.call("mvuld_ln_rows_bwd", y, None, gamma, dout, dvb, None, dg, db, part, M, C, 1e-5, 1))
+    t = timed(lambda: _lib.call("mvuld_ln_rows_bwd", y, None, gamma, dout, dvb, None, dg, db, dg, part, M, C, 1e-5, 1))
     by = M * C * (2 + 4 + 2)
     print(f"ln_rows_bwd M={M} C={C}: {t:7.1f} us  {by / t / 1e6:5.2f} TB/s", flush=True)
 for R, C in ((25088, 512), (25088, 1536), (25088, 2048), (401408, 128), (401408, 512), (401408, 384)):
