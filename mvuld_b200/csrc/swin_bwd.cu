@@ -40,6 +40,10 @@ bias_grad_partial_kernel(const bf16* __restrict__ gt, int n_win, int nH, int npa
   // 179 us; the same kernel with computed bounds [w_beg, w_end) 237 us / 743 us in five splits; a 0 .. count loop from an
   // offset base pointer 2 323 us.  So the unsplit instantiation keeps the plain loop and only the stages with fewer
   // blocks than SMs (four heads: 1 236 us unsplit) take the split form.
+  // ncu (16-head stage, profiles/r2_ncu_biasgrad.md): 174 us, 3.6 TB/s of DRAM reads, 21 % warps active (two blocks per SM:
+  // 128 registers and 88 KB of shared memory each), every stall a long scoreboard, 1.51 waves.  Tried and not kept:
+  // the sums in thread-owned shared-memory slots instead of 88 registers (54 registers, all loads of a window in flight:
+  // 230 us, the LDS / STS round trip per load costs more than the occupancy returns).
   int w_beg = 0, w_end = n_win;
   if (SPLIT) {
     const int per = (n_win + (int)gridDim.z - 1) / (int)gridDim.z;
