@@ -106,31 +106,72 @@ class SwinTrainer:
 
     @torch.no_grad()
     def _refresh(self):
-        """bf16 copies of every weight matrix (GEMM operands), their transposes (dX = dY W), the CPB tables."""
+        """bf16 copies of every weight matrix (GEMM operands), their transposes (dX = dY W), the CPB tables.
+
+        Runs at the end of every step, so nothing here may wait for the GPU: the transposes land in buffers allocated
+        once, the logit scales of all blocks are converted in three launches, and the per-block choice of the
+        constant-reference attention kernel (one flag per block) is read back LAZILY -- the only host read, taken at the
+        start of the next forward (``_resolve_fixed``).  (Reading 24 flags with ``.item()`` here drained the queue 24
+        times per step while the host still had ~200 launches of this function to issue.)"""
         _lib.call("mvuld_f32_to_bf16", self.flat_p, self.flat_w16, self.total)
         p32 = lambda n: self._view(self.flat_p, n)
         w16 = lambda n, shape=None: self._view(self.flat_w16, n, shape)
-        self.w, self.wt = {}, {}
-        E = self.model.embed_dim
-        mats = [("patch_embed.proj.weight", (E, 48))]
-        for b in self.blocks:
-            mats += [(b["prefix"] + s, None) for s in ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")]
-        mats += [(mg["prefix"] + "reduction.weight", None) for mg in self.merges.values()]
-        for n, shape in mats:
+        first = not hasattr(self, "_wt_buf")
+        if first:
+            self._wt_buf = {}
+            E = self.model.embed_dim
+            self._mats = [("patch_embed.proj.weight", (E, 48))]
+            for b in self.blocks:
+                self._mats += [(b["prefix"] + s, None) for s in ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight",
+                                                                 "mlp.fc2.weight")]
+            self._mats += [(mg["prefix"] + "reduction.weight", None) for mg in self.merges.values()]
+            # one index over the logit scales of every block, one buffer for every block's table maximum
+            idx, blk_of, off = [], [], 0
+            for i, b in enumerate(self.blocks):
+                o = self.offsets[b["prefix"] + "attn.logit_scale"]
+                idx += list(range(o, o + b["nH"]))
+                blk_of += [i] * b["nH"]
+                b["_hs"] = (off, off + b["nH"])
+                off += b["nH"]
+            self._ls_index = torch.tensor(idx, dtype=torch.int64, device=self.dev)
+            self._blk_of = torch.tensor(blk_of, dtype=torch.int64, device=self.dev)
+            self._tab_max_all = torch.zeros(off, device=self.dev, dtype=torch.float32)
+            self._fixed_host = torch.zeros(len(self.blocks), dtype=torch.float32).pin_memory()
+            self.w, self.wt = {}, {}
+        for n, shape in self._mats:
             self.w[n] = w16(n, shape)
-            self.wt[n] = self._transpose(self.w[n])
+            if first:
+                R, C = self.w[n].shape
+                self._wt_buf[n] = torch.empty(C, (R + 7) // 8 * 8, device=self.dev, dtype=torch.bfloat16)
+            self.wt[n] = self._transpose(self.w[n], out=self._wt_buf[n])
+        qs_all = torch.clamp(self.flat_p[self._ls_index], max=math.log(100.0)).exp() * LOG2E
         for b in self.blocks:
             pre, nH, ws = b["prefix"] + "attn.", b["nH"], b["ws"]
             side = 2 * ws - 1
-            tab_rev = torch.empty(nH, side * side, device=self.dev, dtype=torch.float32)
-            tab_ref = torch.empty(nH, side * side, device=self.dev, dtype=torch.float32)
-            tab_max = torch.empty(nH, device=self.dev, dtype=torch.float32)
+            if first:
+                b["tab_rev"] = torch.empty(nH, side * side, device=self.dev, dtype=torch.float32)
+                b["tab_ref"] = torch.empty(nH, side * side, device=self.dev, dtype=torch.float32)
+            lo, hi = b["_hs"]
+            tab_max = self._tab_max_all[lo:hi]
             _lib.call("mvuld_cpb_table", p32(pre + "cpb_mlp.0.weight"), p32(pre + "cpb_mlp.0.bias"),
-                      p32(pre + "cpb_mlp.2.weight"), nH, ws, b["pws"], tab_rev, tab_ref, tab_max)
-            qscale = (torch.clamp(p32(pre + "logit_scale").view(-1), max=math.log(100.0)).exp() * LOG2E).contiguous()
-            fixed = ws == 28 and bool((2.0 * qscale + tab_max <= 100.0).all().item())
-            b.update(tab_rev=tab_rev, tab_ref=tab_ref, tab_max=tab_max, qscale=qscale, fixed=int(fixed))
+                      p32(pre + "cpb_mlp.2.weight"), nH, ws, b["pws"], b["tab_rev"], b["tab_ref"], tab_max)
+            b.update(tab_max=tab_max, qscale=qs_all[lo:hi])
+        # constant softmax reference allowed for a block iff 2 |q^| + max bias <= 100 on every head (DESIGN 3.2)
+        viol = (2.0 * qs_all + self._tab_max_all > 100.0).to(torch.float32)
+        per_block = torch.zeros(len(self.blocks), device=self.dev, dtype=torch.float32).index_add_(0, self._blk_of, viol)
+        self._fixed_host.copy_(per_block, non_blocking=True)
+        self._fixed_event = torch.cuda.Event()
+        self._fixed_event.record()
+        self._fixed_pending = True
         self.model.invalidate()
+
+    def _resolve_fixed(self):
+        """Host side of the lazy flag read of ``_refresh`` (one wait per step, at the start of the forward)."""
+        if getattr(self, "_fixed_pending", False):
+            self._fixed_event.synchronize()
+            for b, v in zip(self.blocks, self._fixed_host.tolist()):
+                b["fixed"] = int(b["ws"] == 28 and v == 0.0)
+            self._fixed_pending = False
 
     def refresh(self):
         if self.world > 1:
@@ -149,12 +190,13 @@ class SwinTrainer:
             self.step_count = int(meta.item())
         self._refresh()
 
-    def _transpose(self, x: torch.Tensor) -> torch.Tensor:
+    def _transpose(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """bf16 [R, C] -> [C, Rp], Rp = R rounded up to 8 (zero filled): the K-major operand of a product over R."""
         R, C = x.shape
         assert x.stride(1) == 1
         Rp = (R + 7) // 8 * 8
-        out = torch.empty(C, Rp, device=self.dev, dtype=torch.bfloat16)
+        if out is None:
+            out = torch.empty(C, Rp, device=self.dev, dtype=torch.bfloat16)
         _lib.call("mvuld_transpose_bf16", _lib._Raw(x), x.stride(0), out, R, C, Rp)
         return out
 
@@ -171,6 +213,7 @@ class SwinTrainer:
         if not x.is_cuda:
             raise RuntimeError("mvuld_b200 SwinTrainer takes CUDA tensors (no CPU fallback)")
         m, dev = self.model, self.dev
+        self._resolve_fixed()
         bf, f32 = torch.bfloat16, torch.float32
         e = lambda shape, dt: torch.empty(shape, device=dev, dtype=dt)
         pv = lambda n: self._view(self.flat_p, n)
