@@ -699,7 +699,7 @@ gat_attn_grad_kernel(const bf16* __restrict__ z, const float* __restrict__ del, 
 // DB: also the column sums of dv (= the bias gradient of the dense layer in front of the LayerNorm) as a third row of the
 // block's partials: saves a separate pass over dv.
 template <int UNITS, int LPR, int NR, bool DB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)          // two resident blocks: the C = 768 / 1024 forms would take 151+ registers
 ln_rows_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ shortcut, const float* __restrict__ gamma,
                    const float* __restrict__ dout, bf16* __restrict__ dvb, float* __restrict__ dv32,
                    float* __restrict__ partials, int M, int C, float eps, int mode) {
@@ -1177,27 +1177,59 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
              long long n, const long long* __restrict__ seg_end, const float* __restrict__ seg_wd, int nseg,
              const float* __restrict__ gnorm_sq, float max_norm, float lr, float beta1, float beta2, float eps,
              float bc1, float bc2) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  // four elements per thread (128-bit accesses; the flat buffers are 256-byte aligned), ONE segment search per thread:
+  // one element per thread with a nine-step dependent search each ran the 231 M-parameter update at half the HBM rate
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= n) return;
   float clip = 1.0f;
   if (max_norm > 0.f) {
     const float gn = sqrtf(*gnorm_sq);
     clip = fminf(1.0f, max_norm / (gn + 1e-6f));
   }
-  int lo = 0, hi = nseg - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (i < seg_end[mid]) hi = mid; else lo = mid + 1;
+  auto seg_of = [&](long long i) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (i < seg_end[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  int sg = seg_of(i0);
+  long long end = seg_end[sg];
+  float wd = seg_wd[sg];
+  auto update = [&](long long i, float& pi, float gi, float& mi, float& vi) {
+    if (i >= end && sg < nseg - 1) {                  // crossed into the next segment (rare)
+      sg = seg_of(i);
+      end = seg_end[sg];
+      wd = seg_wd[sg];
+    }
+    // (the statements of the one-element-per-thread form, kept verbatim: the trainer tests pin the trajectory)
+    gi *= clip;
+    mi = beta1 * mi + (1.f - beta1) * gi;
+    vi = beta2 * vi + (1.f - beta2) * gi * gi;
+    pi = pi * (1.f - lr * wd);
+    pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  };
+  const bool vec = i0 + 3 < n && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                                  reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (vec) {
+    float4 p4 = *reinterpret_cast<float4*>(p + i0), m4 = *reinterpret_cast<float4*>(m + i0);
+    float4 v4 = *reinterpret_cast<float4*>(v + i0);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + i0));
+    update(i0, p4.x, g4.x, m4.x, v4.x);
+    update(i0 + 1, p4.y, g4.y, m4.y, v4.y);
+    update(i0 + 2, p4.z, g4.z, m4.z, v4.z);
+    update(i0 + 3, p4.w, g4.w, m4.w, v4.w);
+    *reinterpret_cast<float4*>(p + i0) = p4;
+    *reinterpret_cast<float4*>(m + i0) = m4;
+    *reinterpret_cast<float4*>(v + i0) = v4;
+  } else {
+    for (long long i = i0; i < n && i < i0 + 4; ++i) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      update(i, pi, g[i], mi, vi);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+    }
   }
-  const float wd = seg_wd[lo];
-  const float gi = g[i] * clip;
-  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  float pi = p[i] * (1.f - lr * wd);
-  pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
-  p[i] = pi;
 }
 
 }  // namespace mv
@@ -1337,7 +1369,7 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
 // rows of the partials workspace mvuld_ln_rows_bwd needs for M rows ([blocks, 3, C] floats)
 extern "C" int mvuld_ln_rows_bwd_blocks(int M) { return std::min((M + 7) / 8, 6 * num_sms()); }   // 2 blocks per SM left the row loop latency bound (5.6 ms of a 66 ms SwinV2 step)
 // GELU backward + the column sums of its result in one pass (dpre = dh GELU'(pre) is the gradient of fc1's output: its
-// column sums are fc1's bias gradient).  Thread = (row lane, 8-column unit) as in colsum_kernel; two rows in flight.
+// column sums are fc1's bias gradient).  Thread = (row lane, 8-column unit) as in colsum_kernel; four rows in flight.
 namespace mv {
 __global__ void __launch_bounds__(256)
 gelu_bwd_colsum_kernel(const bf16* __restrict__ pre, const bf16* __restrict__ dh, bf16* __restrict__ dpre,
@@ -1366,12 +1398,16 @@ gelu_bwd_colsum_kernel(const bf16* __restrict__ pre, const bf16* __restrict__ dh
   };
   if (active) {
     int r = rbeg + tr;
-    for (; r + rpp < rend; r += 2 * rpp) {
-      const size_t o0 = (size_t)r * C + c0, o1 = (size_t)(r + rpp) * C + c0;
-      const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(pre + o0)), d0 = __ldg(reinterpret_cast<const uint4*>(dh + o0));
-      const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(pre + o1)), d1 = __ldg(reinterpret_cast<const uint4*>(dh + o1));
-      one(x0, d0, o0);
-      one(x1, d1, o1);
+    for (; r + 3 * rpp < rend; r += 4 * rpp) {         // four rows (eight 16-byte loads) in flight per thread
+      uint4 x[4], d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t o = (size_t)(r + j * rpp) * C + c0;
+        x[j] = __ldg(reinterpret_cast<const uint4*>(pre + o));
+        d[j] = __ldg(reinterpret_cast<const uint4*>(dh + o));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) one(x[j], d[j], (size_t)(r + j * rpp) * C + c0);
     }
     for (; r < rend; r += rpp) {
       const size_t o0 = (size_t)r * C + c0;
@@ -1532,7 +1568,7 @@ extern "C" int mvuld_adamw(float* p, const float* g, float* m, float* v, long lo
   MV_CHECK_ARG(nseg >= 1 && step >= 1, "adamw: nseg >= 1 and step >= 1");
   if (n <= 0) return 0;
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
-  adamw_kernel<<<GRID1(n, 256), 256, 0, stream>>>(p, g, m, v, n, seg_end, seg_wd, nseg, gnorm_sq, max_norm, lr, beta1, beta2, eps, bc1, bc2);
+  adamw_kernel<<<GRID1((n + 3) / 4, 256), 256, 0, stream>>>(p, g, m, v, n, seg_end, seg_wd, nseg, gnorm_sq, max_norm, lr, beta1, beta2, eps, bc1, bc2);
   MV_LAUNCH_OK();
   return 0;
 }

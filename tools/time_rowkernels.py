@@ -30,6 +30,21 @@ for M, C in ((25088, 512), (401408, 128), (100352, 256), (6272, 1024)):
     t = timed(lambda: _lib.call("mvuld_ln_rows_bwd", y, None, gamma, dout, dvb, None, dg, db, dg, part, M, C, 1e-5, 1))
     by = M * C * (2 + 4 + 2)
     print(f"ln_rows_bwd M={M} C={C}: {t:7.1f} us  {by / t / 1e6:5.2f} TB/s", flush=True)
+for M, C, mode in ((25088, 512, 1), (16384, 768, 2), (401408, 128, 1)):      # with the dense bias gradient (third column sum)
+    y = rn(M, C).to(torch.bfloat16)
+    dout, gamma, sc = rn(M, C), 1 + 0.1 * rn(C), rn(M, C)
+    dvb, dv32 = torch.empty(M, C, device=dev, dtype=torch.bfloat16), torch.empty(M, C, device=dev)
+    dg, db, dbi = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    part = _lib.ln_rows_bwd_partials(M, C, dev)
+    t = timed(lambda: _lib.call("mvuld_ln_rows_bwd", y, sc if mode == 2 else None, gamma, dout, dvb, dv32 if mode == 2 else None,
+                                dg, db, dbi, part, M, C, 1e-5, mode))
+    by = M * C * (2 + 4 + 2 + (8 if mode == 2 else 0))
+    print(f"ln_rows_bwd+dbias M={M} C={C} mode={mode}: {t:7.1f} us  {by / t / 1e6:5.2f} TB/s", flush=True)
+for M, C in ((25088, 2048), (16384, 3072), (401408, 512)):
+    pre, dh = rn(M, C).to(torch.bfloat16), rn(M, C).to(torch.bfloat16)
+    dpre, dbias = torch.empty_like(pre), torch.zeros(C, device=dev)
+    t = timed(lambda: _lib.gelu_bwd_colsum(pre, dh, dpre, dbias))
+    print(f"gelu_bwd_colsum M={M} C={C}: {t:7.1f} us  {M * C * 6 / t / 1e6:5.2f} TB/s", flush=True)
 for R, C in ((25088, 512), (25088, 1536), (25088, 2048), (401408, 128), (401408, 512), (401408, 384)):
     x = rn(R, C).to(torch.bfloat16)
     out = torch.zeros(C, device=dev)
