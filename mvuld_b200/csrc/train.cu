@@ -1432,8 +1432,17 @@ extern "C" int mvuld_gelu_bwd_colsum(const void* pre, const void* dh, void* dpre
                                      int C, cudaStream_t stream) {
   MV_CHECK_ARG(C % 8 == 0 && pre && dh && dpre && dbias, "gelu_bwd_colsum: C %% 8 and non-null pointers");
   if (M <= 0) return 0;
-  const int slabs = mvuld_colsum_slabs(M, C);
+  int slabs = mvuld_colsum_slabs(M, C);
   MV_CHECK_ARG(slabs == 1 || partials != nullptr, "gelu_bwd_colsum: the [mvuld_colsum_slabs(M, C), C] partials workspace is null");
+  // no more blocks than are resident at once (40 registers: 6 per SM, not the 8 the slab count assumes -- a second,
+  // one-third-full wave cost a third of the kernel's time); the workspace bound stays mvuld_colsum_slabs
+  {
+    int per_sm = 1;
+    MV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gelu_bwd_colsum_kernel, 256, 0));
+    const int segs = (C / 8 + 255) / 256;
+    const int cap = std::max(1, per_sm * num_sms() / segs);
+    if (slabs > cap) slabs = cap;
+  }
   const int rps = (M + slabs - 1) / slabs;
   dim3 grid((C / 8 + 255) / 256, slabs);
   gelu_bwd_colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(pre), reinterpret_cast<const bf16*>(dh),
