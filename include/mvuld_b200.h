@@ -319,6 +319,11 @@ int mvuld_gate_fusion(const float* x, const float* h, float* out, int B, int C, 
  * ---------------------------------------------------------------------------------------------------------- */
 /* out[c, r] = in[r, c] (bf16, in row stride ldi), out row stride ldo >= R with zero fill: operand transposes of
  * dW = dY^T X. */
+/* The same for a table of matrices in ONE launch: desc = nmat x {in, out, R, C, ldi, ldo} (six 64-bit words each, device
+ * memory), tile_end[k] = exclusive end of matrix k's 32 x 32 tiles (ceil(ldo / 32) x ceil(C / 32) per matrix) in the
+ * flattened grid, total_tiles = tile_end[nmat - 1]. */
+int mvuld_transpose_bf16_batched(const long long* desc, const int* tile_end, int nmat, int total_tiles,
+                                 mvuld_stream_t stream);
 int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, int C, int ldo, mvuld_stream_t stream);
 /* out[c] += sum_r x[r, c] (bias gradients); x bf16 (is_bf16 != 0) or fp32, row stride ldx >= C. */
 /* Weight gradient dW[n_out, k_in] = dY^T X (fp32, row stride ld_dw, overwritten) from ROW-major bf16 dY [M, n_out] and

@@ -74,6 +74,7 @@ SIGNATURES = {
     "mvuld_fusion_head_mode": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mvuld_linear_small": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvuld_transpose_bf16": [_P, _I, _P, _I, _I, _I, _P],
+    "mvuld_transpose_bf16_batched": [_P, _P, _I, _I, _P],
     "mvuld_gemm_dw": [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P],
     "mvuld_gemm_dw_workspace": [_I, _I, _I],
     "mvuld_colsum": [_P, _I, _I, _P, _P, _I, _I, _P],
@@ -205,6 +206,30 @@ def gelu_bwd_colsum(pre: torch.Tensor, dh: torch.Tensor, dpre: torch.Tensor, dbi
     slabs = load().mvuld_colsum_slabs(int(M), int(Cc))
     part = torch.empty(slabs * Cc, device=pre.device, dtype=torch.float32) if slabs > 1 else None
     call("mvuld_gelu_bwd_colsum", pre, dh, dpre, dbias, part, M, Cc)
+
+
+class TransposeTable:
+    """bf16 [R, C] -> [C, Rp] (Rp = R rounded up to 8, zero filled) for a fixed list of (source, destination) pairs in ONE
+    launch (``mvuld_transpose_bf16_batched``).  The table lives on the device; the tensors must stay where they are."""
+
+    def __init__(self, pairs):
+        desc, ends, tot = [], [], 0
+        for x, out in pairs:
+            R, Cc = x.shape
+            assert x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and x.stride(1) == 1 and out.is_contiguous()
+            assert out.shape[0] == Cc and out.shape[1] >= R
+            ldo = out.shape[1]
+            desc += [x.data_ptr(), out.data_ptr(), R, Cc, x.stride(0), ldo]
+            tot += ((ldo + 31) // 32) * ((Cc + 31) // 32)
+            ends.append(tot)
+        dev = pairs[0][0].device
+        self.keep = pairs
+        self.desc = torch.tensor(desc, dtype=torch.int64, device=dev)
+        self.ends = torch.tensor(ends, dtype=torch.int32, device=dev)
+        self.n, self.total = len(pairs), tot
+
+    def run(self):
+        call("mvuld_transpose_bf16_batched", self.desc, self.ends, self.n, self.total)
 
 
 def ln_rows_bwd_partials(M: int, C: int, device) -> torch.Tensor:

@@ -40,6 +40,34 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ in, int ldi, bf16
     if (c < C && r < ldo) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
   }
 }
+// The same transpose for a TABLE of matrices in one launch (the trainers refresh ~100 transposed weight copies per step:
+// 100 launches of a few microseconds each were launch latency, not work).  desc[k] = {in, out, R, C, ldi, ldo} as six
+// 64-bit words, tile_end[k] = exclusive end of matrix k's 32 x 32 tiles in the flattened grid.
+__global__ void transpose_bf16_batched_kernel(const long long* __restrict__ desc, const int* __restrict__ tile_end,
+                                              int nmat) {
+  __shared__ bf16 tile[32][33];
+  int lo = 0, hi = nmat - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int)blockIdx.x < tile_end[mid]) hi = mid; else lo = mid + 1;
+  }
+  const long long* d = desc + (size_t)lo * 6;
+  const bf16* in = reinterpret_cast<const bf16*>(d[0]);
+  bf16* out = reinterpret_cast<bf16*>(d[1]);
+  const int R = (int)d[2], C = (int)d[3], ldi = (int)d[4], ldo = (int)d[5];
+  const int t = (int)blockIdx.x - (lo ? tile_end[lo - 1] : 0);
+  const int tx = (C + 31) / 32;
+  const int r0 = (t / tx) * 32, c0 = (t % tx) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * ldi + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < ldo) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
 
 template <typename T>
 __device__ __forceinline__ float ldf(const T* p, size_t i);
@@ -1238,6 +1266,14 @@ using namespace mv;
 
 #define GRID1(n, t) (unsigned)(((n) + (t) - 1) / (t))
 
+extern "C" int mvuld_transpose_bf16_batched(const long long* desc, const int* tile_end, int nmat, int total_tiles,
+                                            cudaStream_t stream) {
+  MV_CHECK_ARG(desc && tile_end && nmat >= 1, "transpose_batched: null table");
+  if (total_tiles <= 0) return 0;
+  transpose_bf16_batched_kernel<<<total_tiles, dim3(32, 8), 0, stream>>>(desc, tile_end, nmat);
+  MV_LAUNCH_OK();
+  return 0;
+}
 extern "C" int mvuld_transpose_bf16(const void* in, int ldi, void* out, int R, int C, int ldo, cudaStream_t stream) {
   MV_CHECK_ARG(ldo >= R && ldi >= C, "transpose: ldo < R or ldi < C");
   if (R <= 0 || C <= 0) return 0;

@@ -115,14 +115,21 @@ class RobertaTrainer:
     def _refresh(self):
         """bf16 copies of the weight matrices (forward operands) and their transposes (dX = dY W)."""
         _lib.call("mvuld_f32_to_bf16", self.flat_p, self.flat_w16, self.total)
-        self.w, self.wt = [], []
-        for i in range(len(self.enc.encoder.layer)):
-            p = f"encoder.layer.{i}."
-            w = dict(qkv=self._qkv(self.flat_w16, i, "weight"), o=self._view(self.flat_w16, p + "attention.output.dense.weight"),
-                     i=self._view(self.flat_w16, p + "intermediate.dense.weight"),
-                     o2=self._view(self.flat_w16, p + "output.dense.weight"))
-            self.w.append(w)
-            self.wt.append({k: self._transpose(v) for k, v in w.items()})
+        if not hasattr(self, "_wt_table"):
+            # the bf16 weights are views of flat_w16 (fixed addresses) and the transposed copies are allocated once: the
+            # 48 transposes of a step are ONE launch over a device-side table
+            self.w, self.wt = [], []
+            for i in range(len(self.enc.encoder.layer)):
+                p = f"encoder.layer.{i}."
+                w = dict(qkv=self._qkv(self.flat_w16, i, "weight"),
+                         o=self._view(self.flat_w16, p + "attention.output.dense.weight"),
+                         i=self._view(self.flat_w16, p + "intermediate.dense.weight"),
+                         o2=self._view(self.flat_w16, p + "output.dense.weight"))
+                self.w.append(w)
+                self.wt.append({k: torch.empty(v.shape[1], (v.shape[0] + 7) // 8 * 8, device=self.dev, dtype=torch.bfloat16)
+                                for k, v in w.items()})
+            self._wt_table = _lib.TransposeTable([(w[k], wt[k]) for w, wt in zip(self.w, self.wt) for k in w])
+        self._wt_table.run()
         self.enc.invalidate()
 
     def refresh(self):

@@ -138,12 +138,14 @@ class SwinTrainer:
             self._tab_max_all = torch.zeros(off, device=self.dev, dtype=torch.float32)
             self._fixed_host = torch.zeros(len(self.blocks), dtype=torch.float32).pin_memory()
             self.w, self.wt = {}, {}
-        for n, shape in self._mats:
-            self.w[n] = w16(n, shape)
-            if first:
+        if first:
+            for n, shape in self._mats:
+                self.w[n] = w16(n, shape)                          # views of flat_w16: fixed addresses
                 R, C = self.w[n].shape
                 self._wt_buf[n] = torch.empty(C, (R + 7) // 8 * 8, device=self.dev, dtype=torch.bfloat16)
-            self.wt[n] = self._transpose(self.w[n], out=self._wt_buf[n])
+                self.wt[n] = self._wt_buf[n]
+            self._wt_table = _lib.TransposeTable([(self.w[n], self.wt[n]) for n, _ in self._mats])
+        self._wt_table.run()                                       # every transposed copy in one launch
         qs_all = torch.clamp(self.flat_p[self._ls_index], max=math.log(100.0)).exp() * LOG2E
         for b in self.blocks:
             pre, nH, ws = b["prefix"] + "attn.", b["nH"], b["ws"]
