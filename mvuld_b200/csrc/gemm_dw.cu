@@ -166,14 +166,31 @@ __global__ void dw_reduce_kernel(const float* __restrict__ partial, long long sp
 
 using namespace mv;
 
-// how the host splits the M rows: enough CTAs to fill the GPU, at least 8 pipeline stages of work per split, split
-// boundaries on multiples of 64 rows
+// How the host splits the M rows.  One CTA per SM (192 KB of shared memory), so a launch runs in ceil(CTAs / SMs) waves;
+// a CTA's time is its k blocks (bound by the L2 -> SM path: ~0.6 us per 64-row block of a 128 x 256 tile, 0.4 us at
+// 128 x 128) plus ~3 us of prologue / epilogue, and every split adds one partial tile set to write and
+// read back.  Take the split count that minimises that estimate -- "two CTAs per SM's worth of splits" put the SwinV2
+// stage-2 products at 2.16 waves = three waves (93 us for [2048, 512] x 25 088 rows; one wave of four splits: 65 us).
+// Split boundaries on multiples of 64 rows, at least 8 pipeline stages of work per split.
 static void dw_plan(int M, int n_out, int k_in, int& bn, int& tiles, int& splits, int& rows_per_split) {
   bn = k_in > 128 ? 256 : 128;
   const int tiles_m = (n_out + DW_BM - 1) / DW_BM, tiles_n = (k_in + bn - 1) / bn;
   tiles = tiles_m * tiles_n;
   const int kb_total = (M + DW_BK - 1) / DW_BK;
-  splits = std::max(1, std::min((2 * num_sms() + tiles - 1) / tiles, kb_total / 8));
+  const int sms = num_sms();
+  const int max_splits = std::max(1, std::min(kb_total / 8, 64));
+  const double t_kb = bn == 256 ? 0.6 : 0.4, t_cta = 3.0;
+  const double t_split = (double)n_out * k_in * 8.0 / 5.0e6;         // us: write + read of one fp32 partial set at 5 TB/s
+  double best = 1e30;
+  int best_s = 1;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const int kb_per = (kb_total + sp - 1) / sp;
+    const int real = (kb_total + kb_per - 1) / kb_per;               // splits that actually get rows
+    const long long waves = ((long long)tiles * real + sms - 1) / sms;
+    const double cost = waves * (kb_per * t_kb + t_cta) + (real > 1 ? real * t_split : 0.0);
+    if (cost < best) { best = cost; best_s = real; }
+  }
+  splits = best_s;
   const int kb_per = (kb_total + splits - 1) / splits;
   rows_per_split = kb_per * DW_BK;
   splits = (kb_total + kb_per - 1) / kb_per;
