@@ -68,6 +68,30 @@ def test_transpose_and_colsum():
     assert rel_err(s2, y[:, :40].sum(0) + 1.0) < 1e-5
 
 
+def test_batched_transpose_table_and_large_colsum():
+    """One launch for a table of matrices (the trainers' per-step refresh of the transposed weight copies): ragged
+    shapes, a strided source, zero-filled padding columns; and the column sums at sizes that take several row slabs
+    and two column segments, twice (fixed summation order: bit-identical)."""
+    g = gen(71)
+    shapes = [(70, 200), (512, 1536), (3, 8), (1024, 3072), (129, 33)]
+    srcs = [torch.randn(r, c, generator=g).to(torch.bfloat16).to(DEV) for r, c in shapes]
+    wide = torch.randn(96, 640, generator=g).to(torch.bfloat16).to(DEV)
+    srcs.append(wide[:, 128:448])                                   # strided view: ldi 640, 320 columns
+    outs = [torch.full((x.shape[1], (x.shape[0] + 7) // 8 * 8), 7.0, dtype=torch.bfloat16, device=DEV) for x in srcs]
+    table = _lib.TransposeTable(list(zip(srcs, outs)))
+    table.run()
+    for x, o in zip(srcs, outs):
+        assert torch.equal(o[:, :x.shape[0]], x.t()) and float(o[:, x.shape[0]:].float().abs().sum()) == 0.0
+    for R, C in ((25088, 512), (5000, 4096), (401408 // 4, 128)):
+        x = torch.randn(R, C, generator=g).to(torch.bfloat16).to(DEV)
+        a, b = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        _lib.colsum(x, 1, C, a, R, C)
+        _lib.colsum(x, 1, C, b, R, C)
+        assert torch.equal(a, b)
+        ref = x.double().sum(0)
+        assert float((a.double() - ref).abs().max()) < 1e-3 * float(x.double().abs().sum(0).max())
+
+
 @pytest.mark.parametrize("R,C", [(6, 1536), (600, 512)])
 def test_bn_cols_forward_backward(R, C):
     r = gen(3)
@@ -286,20 +310,21 @@ def test_head_kernels_l2norm_ce_linear():
     assert rel_err(dx, xr.grad) < 1e-5 and rel_err(dw, wr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
 
 
-def test_adamw_with_clipping_matches_torch():
+@pytest.mark.parametrize("n,b0,b1", [(5000, 1024, 3008), (4999, 1022, 3005)])
+def test_adamw_with_clipping_matches_torch(n, b0, b1):
+    """The second case puts the segment boundaries inside a thread's four elements and leaves a scalar tail."""
     r = gen(9)
-    n = 5000
     p0, g0 = torch.randn(n, generator=r), torch.randn(n, generator=r) * 3
-    seg_end = torch.tensor([1024, 3008, n], dtype=torch.int64)
+    seg_end = torch.tensor([b0, b1, n], dtype=torch.int64)
     seg_wd = torch.tensor([0.005, 0.0, 0.005])
-    parts = [p0[:1024].clone().requires_grad_(True), p0[1024:3008].clone().requires_grad_(True),
-             p0[3008:].clone().requires_grad_(True)]
+    parts = [p0[:b0].clone().requires_grad_(True), p0[b0:b1].clone().requires_grad_(True),
+             p0[b1:].clone().requires_grad_(True)]
     opt = torch.optim.AdamW([{"params": [parts[0], parts[2]], "weight_decay": 0.005},
                              {"params": [parts[1]], "weight_decay": 0.0}], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
     p, m, v = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
     for step in (1, 2, 3):
         gs = g0 * step
-        for q, (lo, hi) in zip(parts, ((0, 1024), (1024, 3008), (3008, n))):
+        for q, (lo, hi) in zip(parts, ((0, b0), (b0, b1), (b1, n))):
             q.grad = gs[lo:hi].clone()
         torch.nn.utils.clip_grad_norm_(parts, 5.0)
         opt.step()
