@@ -258,8 +258,12 @@ def test_mlp_ln_fused_matches_reference_and_two_kernel_path(M, C):
     _lib.gemm_ln(hid, W2, gamma, beta, 1e-5, bias=b2, shortcut=x32_a, x32=x32_a, xb=xb_a)
     first = None
     for it in range(6):
-        x32, xb = res.clone(), X.clone()                             # xb aliases the operand, shortcut aliases x32
+        # xb aliases the operand, shortcut aliases x32; three guard rows behind both outputs must stay untouched
+        x32g, xbg = torch.full((M + 3, C), 5.0, device=DEV), torch.full((M + 3, C), 5.0, device=DEV, dtype=torch.bfloat16)
+        x32g[:M], xbg[:M] = res, X
+        x32, xb = x32g[:M], xbg[:M]
         _lib.mlp_ln(xb, W1, b1, W2, b2, gamma, beta, 1e-5, shortcut=x32, x32=x32, xb=xb)
+        assert float((x32g[M:] - 5.0).abs().sum()) == 0.0 and float((xbg[M:].float() - 5.0).abs().sum()) == 0.0
         if first is None:
             first = (x32, xb)
             torch.cuda.synchronize()
