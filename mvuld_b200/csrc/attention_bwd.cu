@@ -355,22 +355,24 @@ attn_bwd_prep_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, co
                      const __half* __restrict__ qh, const __half* __restrict__ kh, bf16* __restrict__ dOw,
                      float2* __restrict__ ld, bf16* __restrict__ qb, bf16* __restrict__ kb, int B, int H, int W, int C,
                      int nH, int ws, int shift) {
+  // Threads walk the WINDOW-major order (consecutive threads = consecutive slots of one (window, head)): six of the eight
+  // tensors touched here are window-major, so a warp reads / writes 2 KB runs instead of 32 pieces 50 KB apart; the two
+  // token-major operands (dO, O) are then 64-byte pieces one token row apart.
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * H * W * nH;
   if (idx >= total) return;
-  const int head = (int)(idx % nH);
-  const long long row = idx / nH;                 // token
-  const int HW = H * W;
-  const int b = (int)(row / HW);
-  const int t = (int)(row - (long long)b * HW);
-  int hh = t / W, ww = t - hh * W;
-  hh -= shift; if (hh < 0) hh += H;
-  ww -= shift; if (ww < 0) ww += W;
-  const int nWw = W / ws;
-  const int win = (hh / ws) * nWw + (ww / ws);
-  const int slot = (hh % ws) * ws + (ww % ws);
-  const int nW = (H / ws) * nWw;
-  const size_t wrow = (((size_t)b * nW + win) * nH + head) * (size_t)(ws * ws) + slot;
+  const int N = ws * ws;
+  const int slot = (int)(idx % N);
+  const long long bwh = idx / N;
+  const int head = (int)(bwh % nH);
+  const long long bw = bwh / nH;
+  const int nWw = W / ws, nW = (H / ws) * nWw;
+  const int win = (int)(bw % nW), b = (int)(bw / nW);
+  int hh = (win / nWw) * ws + slot / ws + shift, ww = (win % nWw) * ws + slot % ws + shift;   // undo the cyclic shift
+  if (hh >= H) hh -= H;
+  if (ww >= W) ww -= W;
+  const long long row = (long long)b * H * W + (long long)hh * W + ww;                         // token
+  const size_t wrow = (size_t)idx;
   const uint4* dp = reinterpret_cast<const uint4*>(dO + (size_t)row * C + head * 32);
   const uint4* op = reinterpret_cast<const uint4*>(O + (size_t)row * C + head * 32);
   uint4* dst = reinterpret_cast<uint4*>(dOw + wrow * 32);

@@ -183,6 +183,8 @@ swin_qkv_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ dk, 
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * H * W * nH;
   float ls = 0.f;
+  // (token-major thread order kept here: the window-major order that helps attn_bwd_prep_kernel made this kernel slower,
+  // 2.5 -> 3.0 ms per step -- its per-head logit-scale partials then need a serial walk over the block's 256 entries)
   if (idx < total) {
     const int head = (int)(idx % nH);
     const long long row = idx / nH;
