@@ -179,21 +179,29 @@ class FusionTrainer:
     def _refresh_shadows(self):
         """bf16 copies of every weight (GEMM operands) and their transposes (dX = dY W needs W^T as the K-major operand)."""
         _lib.call("mvuld_f32_to_bf16", self.flat_p, self.flat_w16, self.total)
-        self.wt = {}
-        lin = ["swinfc", "fc_text", "fc_gat", "fc", "gat2.fc"] + [f"hidden.{i}" for i in range(8)]
-        for name in lin:
-            w = self._mat(self.flat_w16, name + ".weight")
-            self.wt[name] = self._transpose(w)
-        self.w3 = {}
-        for k in range(1, 9):
-            self.wt[f"gcn{k}.cat"] = self._transpose(self._gcn_cat(self.flat_w16, k, "weight"))
-            self.wt[f"gcn{k}.W0"] = self._transpose(self._mat(self.flat_w16, f"Rs_GCN_{k}.W.0.weight"))
-            # forward operands of the Rs_GCN 1x1 convolutions: bf16x3 split (W_hi | W_hi | W_lo) of the fp32 weights
-            for key, w32 in ((f"gcn{k}.cat", self._gcn_cat(self.flat_p, k, "weight")),
-                             (f"gcn{k}.W0", self._mat(self.flat_p, f"Rs_GCN_{k}.W.0.weight"))):
-                w3 = torch.empty(w32.shape[0], 3 * w32.shape[1], device=self.dev, dtype=torch.bfloat16)
-                _lib.call("mvuld_split3_bf16", w32, w32.shape[1], w3, w32.shape[0], w32.shape[1], 1)
-                self.w3[key] = w3
+        first = not hasattr(self, "_wt_table")
+        if first:
+            # sources are views of the flat bf16 / fp32 buffers (fixed addresses), destinations are allocated once: the
+            # 29 transposes of a step are ONE launch over a device-side table
+            self.wt, self.w3, self._w3_src, pairs = {}, {}, [], []
+            lin = ["swinfc", "fc_text", "fc_gat", "fc", "gat2.fc"] + [f"hidden.{i}" for i in range(8)]
+            srcs = [(name, self._mat(self.flat_w16, name + ".weight")) for name in lin]
+            for k in range(1, 9):
+                srcs.append((f"gcn{k}.cat", self._gcn_cat(self.flat_w16, k, "weight")))
+                srcs.append((f"gcn{k}.W0", self._mat(self.flat_w16, f"Rs_GCN_{k}.W.0.weight")))
+                # forward operands of the Rs_GCN 1x1 convolutions: bf16x3 split (W_hi | W_hi | W_lo) of the fp32 weights
+                for key, w32 in ((f"gcn{k}.cat", self._gcn_cat(self.flat_p, k, "weight")),
+                                 (f"gcn{k}.W0", self._mat(self.flat_p, f"Rs_GCN_{k}.W.0.weight"))):
+                    self.w3[key] = torch.empty(w32.shape[0], 3 * w32.shape[1], device=self.dev, dtype=torch.bfloat16)
+                    self._w3_src.append((w32, self.w3[key]))
+            for name, w in srcs:
+                R, C = w.shape
+                self.wt[name] = torch.empty(C, (R + 7) // 8 * 8, device=self.dev, dtype=torch.bfloat16)
+                pairs.append((w, self.wt[name]))
+            self._wt_table = _lib.TransposeTable(pairs)
+        self._wt_table.run()
+        for w32, w3 in self._w3_src:
+            _lib.call("mvuld_split3_bf16", w32, w32.shape[1], w3, w32.shape[0], w32.shape[1], 1)
         self.model.invalidate()
 
     def _transpose(self, x: torch.Tensor) -> torch.Tensor:

@@ -6,7 +6,7 @@ import bench
 args = types.SimpleNamespace(batch=0, workload="full", padded_text=False)
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
-w = bench.build_train_workload(args, 0, dev, 1, encoders=True)
+w = bench.build_train_workload(args, 0, dev, 1, encoders=os.environ.get("ENCODERS", "1") == "1")
 d = w["to_dev"]()
 for _ in range(2):
     w["step"](d)
