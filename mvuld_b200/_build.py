@@ -71,7 +71,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     if force:
         for f in os.listdir(OBJDIR):
-            os.remove(os.path.join(OBJDIR, f))
+            if os.path.isfile(os.path.join(OBJDIR, f)):       # (build/variants/ holds experiment builds: left alone)
+                os.remove(os.path.join(OBJDIR, f))
     digest = _deps_digest()
     srcs = sources()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
