@@ -43,7 +43,10 @@ bias_grad_partial_kernel(const bf16* __restrict__ gt, int n_win, int nH, int npa
   // ncu (16-head stage, profiles/r2_ncu_biasgrad.md): 174 us, 3.6 TB/s of DRAM reads, 21 % warps active (two blocks per SM:
   // 128 registers and 88 KB of shared memory each), every stall a long scoreboard, 1.51 waves.  Tried and not kept:
   // the sums in thread-owned shared-memory slots instead of 88 registers (54 registers, all loads of a window in flight:
-  // 230 us, the LDS / STS round trip per load costs more than the occupancy returns).
+  // 230 us, the LDS / STS round trip per load costs more than the occupancy returns); a block's key columns split over
+  // three blocks (32 registers of sums, four resident blocks, 1 344 items instead of 448: 254 us on the 16-head stage,
+  // 591 vs 347 us on the 8-head stage) -- more, smaller streams per SM lower the DRAM efficiency here, occupancy is not
+  // what limits it.
   int w_beg = 0, w_end = n_win;
   if (SPLIT) {
     const int per = (n_win + (int)gridDim.z - 1) / (int)gridDim.z;
