@@ -704,6 +704,9 @@ static int swin_qkv(const void* X, const void* Wqkv, const float* q_bias, const 
   e.q = reinterpret_cast<__half*>(q); e.k = reinterpret_cast<__half*>(k); e.v = reinterpret_cast<bf16*>(v);
   e.rq = rq; e.rk = rk;
   e.C = C; e.nH = nH; e.H = H; e.W = W; e.ws = ws; e.shift = shift; e.M = B * H * W;
+  // (the weight-stationary schedule was tried for the narrow stages, K = C <= 256: 288 vs 284 us at C = 128, 159 vs 150
+  // at C = 256 -- these launches are bound by the normalise + scatter epilogue at ~2.9 TB/s of q / k / v writes, not by
+  // the operand path; tools/time_qkv.py)
   if ((3 * C) % 256 == 0) return launch_gemm<256, 4, EpiQkvSwin>(X, C, Wqkv, C, B * H * W, 3 * C, C, e, stream);
   return launch_gemm<128, 6, EpiQkvSwin>(X, C, Wqkv, C, B * H * W, 3 * C, C, e, stream);
 }
