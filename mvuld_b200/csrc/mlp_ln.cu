@@ -30,7 +30,9 @@
 // streamed from L2 by every SM = 6 TB/s of L2 -> SM traffic against the ~12 TB/s the fabric gives) is the floor, and the
 // GELU warps' time adds to it because G2(g) cannot be issued before GELU(g) is done.  Tried and not kept: the GELU warps
 // as two groups of four on alternate chunks (each group then waits for a G1 that sits behind the other group's G2 in the
-// MMA warp's in-order issue: 505 us); one set of eight warps for GELU and LayerNorm (667 us).
+// MMA warp's in-order issue: 505 us); one set of eight warps for GELU and LayerNorm (667 us); sixteen GELU warps at 32
+// columns per thread, with eight LayerNorm warps (72-register cap: 467 / 374 us) or four whole-row LayerNorm warps
+// (603 / 441 us: the LayerNorm epilogue becomes the longest stage).
 //
 // The accumulation order over K is that of the two-kernel path (k blocks of 64 in ascending order), and the GELU / LN
 // arithmetic is the same code, so the result is bit-identical to gemm + gemm_ln (tests/test_gpu_kernels.py).
