@@ -39,4 +39,4 @@ for M, C in ((802816, 128), (200704, 256)):
     fl = 2.0 * M * C * 4 * C * 2
     by = 12.0 * M * C
     print(f"M={M} C={C}: two kernels {t2:7.1f} us, fused {t1:7.1f} us ({fl / t1 / 1e6:5.0f} TFLOP/s, "
-          f"{by / t1 / 1e3:5.2f} TB/s of algorithmic bytes)", flush=True)
+          f"{by / t1 / 1e6:5.2f} TB/s of algorithmic bytes)", flush=True)
