@@ -359,8 +359,8 @@ int mvuld_bn_slot_fwd(const void* x, const float* gamma, const float* beta, floa
                       mvuld_stream_t stream);
 int mvuld_bn_slot_bwd(const void* x, const void* dy, const float* gamma, const float* mean, const float* rstd,
                       void* dx, float* dgamma, float* dbeta, int B, int n, int F, mvuld_stream_t stream);
-/* First row kernels of the encoder backward (the "whole path trainable" reading of configs[4]; not yet driven by a
- * trainer).  LayerNorm backward of the three mvuld_ln_rows forms: dout fp32 [M,C] = gradient of the LN output (mode 1:
+/* Row kernels of the encoder backward (the "whole path trainable" reading of configs[4]; driven by SwinTrainer /
+ * RobertaTrainer).  LayerNorm backward of the three mvuld_ln_rows forms: dout fp32 [M,C] = gradient of the LN output (mode 1:
  * the block output's gradient, which is also the shortcut's); the LN input is recomputed from y (bf16) (+ shortcut in
  * mode 2); dv = gradient of the LN input as bf16 and / or fp32; dgamma / dbeta accumulated.  swin_transformer_v2.py:301,
  * 304,362; HF RobertaSelfOutput / RobertaOutput. */

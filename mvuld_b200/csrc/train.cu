@@ -1403,7 +1403,7 @@ extern "C" int mvuld_ln_rows_bwd(const void* y, const float* shortcut, const flo
   return 0;
 }
 // rows of the partials workspace mvuld_ln_rows_bwd needs for M rows ([blocks, 3, C] floats)
-extern "C" int mvuld_ln_rows_bwd_blocks(int M) { return std::min((M + 7) / 8, 6 * num_sms()); }   // 2 blocks per SM left the row loop latency bound (5.6 ms of a 66 ms SwinV2 step)
+extern "C" int mvuld_ln_rows_bwd_blocks(int M) { return std::min((M + 7) / 8, 6 * num_sms()); }   // upper bound: the launch uses the resident blocks (<= 6 per SM)
 // GELU backward + the column sums of its result in one pass (dpre = dh GELU'(pre) is the gradient of fc1's output: its
 // column sums are fc1's bias gradient).  Thread = (row lane, 8-column unit) as in colsum_kernel; four rows in flight.
 namespace mv {
